@@ -1,0 +1,81 @@
+"""Dense-literal oracle == closed-form oracle (SURVEY.md §8c known-answer test 2)."""
+import math
+
+import pytest
+import torch
+
+from oracle import closed_form, dense
+from oracle import gp as ogp
+from tests.problems import make_inputs, make_problem, oracle_state
+
+CASES = [
+    # N, d, q, b, G, temp, randomized, ratio, refine, kind
+    (40, 3, 1, 6, 16, 3e-2, False, False, 0, "ucb"),
+    (40, 3, 1, 6, 16, 3e-2, True, True, 2, "ei"),
+    (33, 2, 2, 5, 12, 3e-2, True, True, 0, "ucb"),
+    (33, 2, 2, 5, 12, 0.0, False, False, 1, "ucb"),
+    (20, 4, 3, 4, 8, 1e-2, True, True, 3, "ei"),
+    (40, 3, 1, 6, 16, 1e-6, True, True, 0, "ucb"),
+    (8, 2, 1, 16, 64, 3e-2, True, False, 0, "ucb"),      # BASELINE config 1 shape (branin-like, N=8)
+    (257, 8, 1, 2, 8, 3e-2, False, True, 0, "ucb"),
+]
+
+
+@pytest.mark.parametrize("N,d,q,b,G,temp,rand,ratio_on,refine,kind", CASES)
+def test_dense_equals_closed_form(N, d, q, b, G, temp, rand, ratio_on, refine, kind):
+    p = make_problem(N, d, seed=N, fn="sin")
+    gp = oracle_state(p)
+    inp = make_inputs(N, d, b, q, G, S=2, seed=N + q)
+    ratio = ogp.make_ratio_mlp(d) if ratio_on else None
+    kw = dict(kind=kind, alpha=0.2, temp=temp, grid_res=G, max_grid_refinements=refine,
+              eps_grid=inp["eps_grid"], z=inp["z"], eps_mc=inp["eps_mc"], ratio=ratio, randomized=rand,
+              u_rand=inp["u_rand"], optimistic=True, beta_prime=math.sqrt(0.2 * math.pi / 2), best_f=0.3)
+    a = dense.conformal_acquisition(gp, inp["Xq"], **kw)
+    c = closed_form.conformal_acquisition(gp, inp["Xq"], **kw)
+    for key in ("acq", "target_grid", "logp", "mask", "ood", "values"):
+        assert torch.allclose(a[key], c[key], rtol=1e-9, atol=1e-11), key
+
+
+def test_untrained_ratio_estimator_is_identity():
+    """ratio_estimation.py:81-86: a zero target network gives w == 1 (up to the 1e-6 clamps) -> same as None."""
+    N, d, b, G = 30, 3, 4, 16
+    gp = oracle_state(make_problem(N, d, seed=3, fn="sin"))
+    inp = make_inputs(N, d, b, 1, G, seed=5)
+    zero = ogp.RatioMLP(*(torch.zeros(s, dtype=torch.float64) for s in [(64, d), (64,), (64, 64), (64,), (1, 64), (1,)]))
+    kw = dict(kind="ucb", alpha=0.1, temp=3e-2, grid_res=G, eps_grid=inp["eps_grid"], z=inp["z"],
+              eps_mc=inp["eps_mc"], beta_prime=1.0)
+    a = closed_form.conformal_acquisition(gp, inp["Xq"], ratio=None, **kw)
+    c = closed_form.conformal_acquisition(gp, inp["Xq"], ratio=zero, **kw)
+    assert torch.allclose(a["acq"], c["acq"], rtol=1e-12)
+
+
+def test_hard_path_is_limit_of_soft_path():
+    N, d, b, G = 30, 3, 6, 16
+    gp = oracle_state(make_problem(N, d, seed=4, fn="sin"))
+    inp = make_inputs(N, d, b, 1, G, seed=6)
+    kw = dict(kind="ucb", alpha=0.15, grid_res=G, eps_grid=inp["eps_grid"], z=inp["z"], eps_mc=inp["eps_mc"], beta_prime=1.0)
+    hard = closed_form.conformal_acquisition(gp, inp["Xq"], temp=0.0, **kw)
+    soft = closed_form.conformal_acquisition(gp, inp["Xq"], temp=1e-9, **kw)
+    assert torch.equal(hard["mask"], (soft["mask"] >= 0.5).double())
+
+
+def test_finite_sample_coverage():
+    """Unweighted, hard, non-randomised full conformal: marginal coverage >= 1 - alpha (the paper's guarantee)."""
+    torch.manual_seed(0)
+    N, d, alpha, G = 24, 2, 0.2, 128
+    hits, trials = 0, 60
+    from oracle.pure import conf_mask_to_bounds
+    for trial in range(trials):
+        Xall = torch.rand(N + 1, d, dtype=torch.float64)
+        ls = torch.full((d,), 0.4, dtype=torch.float64)
+        K = ogp.matern52(Xall, Xall, ls, 1.0) + 0.05 * torch.eye(N + 1, dtype=torch.float64)
+        yall = torch.linalg.cholesky(K) @ torch.randn(N + 1, dtype=torch.float64)
+        gp = ogp.build_state(Xall[:N], yall[:N], 0.0, ls, 1.0, 0.05)
+        eps = torch.linspace(-4, 4, G, dtype=torch.float64).view(G, 1)
+        z = 2.0 * ((torch.rand(N + 1, 8) > 0.5).double() - 0.5)
+        out = closed_form.conformal_acquisition(
+            gp, Xall[N:].view(1, 1, d), kind="ucb", alpha=alpha, temp=0.0, grid_res=G, eps_grid=eps, z=z,
+            eps_mc=torch.zeros(1, G, 1, dtype=torch.float64), beta_prime=1.0)
+        lb, ub = conf_mask_to_bounds(out["target_grid"].unsqueeze(-1), out["mask"].unsqueeze(-1))
+        hits += int(lb.item() <= yall[N].item() <= ub.item())
+    assert hits / trials >= 1 - alpha - 0.12   # 60 trials: ~2.3 sigma slack below the nominal 0.8
