@@ -1,0 +1,434 @@
+// cbo_api.cu -- C ABI of libcbo (see include/cbo.h): workspace carving and kernel orchestration.
+// No torch types, no allocation, everything on the caller's stream.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/cbo.h"
+#include "bounds.cuh"
+#include "common.cuh"
+#include "gemm_tri.cuh"
+#include "rows.cuh"
+#include "score.cuh"
+
+namespace {
+
+thread_local char g_last_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_last_err, sizeof(g_last_err), "%s: %s", where, cudaGetErrorString(e));
+    return CBO_ERR_CUDA;
+}
+#define CBO_CUDA(call)                                         \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);  \
+    } while (0)
+
+constexpr int64_t kDefaultChunk = 16384;
+
+// ---- optional per-kernel-class timing (CUDA events on the caller's stream; bench.py's roofline) ----
+enum { T_PREP = 0, T_ROWS = 1, T_GEMM1 = 2, T_GEMM2 = 3, T_SCORE = 4, T_NCLASS = 5 };
+struct Timing {
+    bool enabled = false;
+    std::vector<cudaEvent_t> ev[T_NCLASS];     // start/stop pairs
+    std::vector<cudaEvent_t> pool;
+    int64_t launches[T_NCLASS] = {0, 0, 0, 0, 0};
+    cudaEvent_t get() {
+        cudaEvent_t e;
+        if (!pool.empty()) { e = pool.back(); pool.pop_back(); return e; }
+        cudaEventCreate(&e);
+        return e;
+    }
+} g_timing;
+struct TimeScope {
+    int cls; cudaStream_t s; bool on;
+    TimeScope(int c, cudaStream_t st, int nlaunch) : cls(c), s(st), on(g_timing.enabled) {
+        if (on) { cudaEvent_t e = g_timing.get(); cudaEventRecord(e, s); g_timing.ev[cls].push_back(e); g_timing.launches[cls] += nlaunch; }
+    }
+    ~TimeScope() {
+        if (on) { cudaEvent_t e = g_timing.get(); cudaEventRecord(e, s); g_timing.ev[cls].push_back(e); }
+    }
+};
+constexpr size_t kAlign = 256;
+
+size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+struct Carver {
+    char* base;
+    size_t off;
+    explicit Carver(void* p) : base(static_cast<char*>(p)), off(0) {}
+    template <typename T>
+    T* take(size_t n) {
+        T* r = reinterpret_cast<T*>(base ? base + off : nullptr);
+        off += align_up(n * sizeof(T));
+        return r;
+    }
+};
+
+struct Workspace {
+    double *zp, *tmp, *T, *a, *h0, *dr_train, *sum_dr;
+    uint32_t* zb;
+    double *UW, *V, *mu, *ut, *drc, *rn;
+    double *cscale, *nacc, *stats;      // refinement only
+    size_t bytes;
+};
+
+int64_t pick_chunk(int64_t b, const cbo_params* p, int64_t chunk) {
+    if (p->max_grid_refinements > 0) return b;     // batch-global statistics need every candidate resident
+    if (chunk <= 0) chunk = kDefaultChunk;
+    return chunk < b ? chunk : b;
+}
+
+Workspace carve(void* ws, int64_t N, int64_t b, const cbo_params* p, int64_t chunk) {
+    const int64_t Np = cbo_padded_n(N), Sp = p->num_probes, C = pick_chunk(b, p, chunk);
+    const int64_t tiles_n = Np / cbo::GEMM_BN;
+    Carver c(ws);
+    Workspace w;
+    w.zp = c.take<double>(Np * Sp);
+    w.tmp = c.take<double>(Np * Sp);
+    w.T = c.take<double>(Np * Sp);
+    w.a = c.take<double>(Np);
+    w.h0 = c.take<double>(Np);
+    w.dr_train = c.take<double>(Np);
+    w.sum_dr = c.take<double>(8);
+    w.zb = c.take<uint32_t>(Np);
+    w.UW = c.take<double>(C * Np);
+    w.V = c.take<double>(C * Np);
+    w.mu = c.take<double>(C);
+    w.ut = c.take<double>(C * Sp);
+    w.drc = c.take<double>(C);
+    w.rn = c.take<double>(C * tiles_n);
+    const int64_t R = p->max_grid_refinements;
+    w.cscale = c.take<double>(R > 0 ? (R + 1) * b : 1);
+    w.nacc = c.take<double>(R > 0 ? b : 1);
+    w.stats = c.take<double>(8);
+    w.bytes = c.off;
+    return w;
+}
+
+// min / max / sum((n/G - 1/2)^2) of the accepted counts, in float like the reference (helpers.py:150-155)
+__global__ void k_accept_stats(const double* __restrict__ nacc, int b, int G, double* __restrict__ stats) {
+    __shared__ float smin[256], smax[256], ssum[256];
+    float mn = 3.4e38f, mx = -3.4e38f, sm = 0.f;
+    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+        float n = (float)nacc[i];
+        mn = fminf(mn, n); mx = fmaxf(mx, n);
+        float d = n / (float)G - 0.5f;
+        sm += d * d;
+    }
+    smin[threadIdx.x] = mn; smax[threadIdx.x] = mx; ssum[threadIdx.x] = sm;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            smin[threadIdx.x] = fminf(smin[threadIdx.x], smin[threadIdx.x + o]);
+            smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + o]);
+            ssum[threadIdx.x] += ssum[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { stats[0] = smin[0]; stats[1] = smax[0]; stats[2] = ssum[0] / (float)b; }
+}
+
+// covar_scale = 1 + sign(diff) |diff|^(2/q) in float (helpers.py:153-167), accumulated into the grid covariance scale
+__global__ void k_rescale(const double* __restrict__ nacc, const double* __restrict__ cur, double* __restrict__ next,
+                          int b, int G, int q) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b) return;
+    float d = (float)nacc[i] / (float)G - 0.5f;
+    float ad = fabsf(d);
+    float pw = (q == 1) ? ad * ad : (q == 2 ? ad : powf(ad, 2.f / (float)q));
+    float sg = (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f);
+    next[i] = (double)(1.f + sg * pw) * cur[i];
+}
+
+int validate(const cbo_gp_f64* gp, const cbo_params* p, int64_t b) {
+    if (!gp || !p || b <= 0) return CBO_ERR_INVALID_ARG;
+    if (!gp->X || !gp->alpha || !gp->linv || !gp->linv_t || !gp->inv_lengthscale) return CBO_ERR_INVALID_ARG;
+    if (gp->N <= 0 || gp->d <= 0 || gp->Np != cbo_padded_n(gp->N)) return CBO_ERR_INVALID_ARG;
+    if (p->grid_res < 2) return CBO_ERR_INVALID_ARG;                       // helpers.py:113
+    if (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI) return CBO_ERR_INVALID_ARG;
+    if (p->q != 1) return CBO_ERR_UNSUPPORTED;
+    if (gp->d > cbo::MAX_D) return CBO_ERR_UNSUPPORTED;
+    if (p->num_probes < 1 || p->num_probes > cbo::MAX_SP) return CBO_ERR_UNSUPPORTED;
+    if (p->num_mc < 1 || p->num_mc > cbo::MAX_S) return CBO_ERR_UNSUPPORTED;
+    if (p->grid_res > 4096) return CBO_ERR_UNSUPPORTED;
+    if (cbo::score_smem_bytes((int)gp->Np, (int)p->grid_res) > 227 * 1024) return CBO_ERR_UNSUPPORTED;
+    return CBO_OK;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <bool SOFT>
+cudaError_t launch_score(const cbo::ScoreArgs& a, cudaStream_t st) {
+    size_t smem = cbo::score_smem_bytes(a.Np, a.G);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(cbo::k_score<SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbo::k_score<SOFT>, cbo::SCORE_THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    int grid = num_sms() * per_sm;
+    if (grid > a.n_cand) grid = a.n_cand;
+    cbo::k_score<SOFT><<<grid, cbo::SCORE_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int cbo_version(void) { return CBO_VERSION; }
+
+const char* cbo_status_str(int s) {
+    switch (s) {
+        case CBO_OK: return "ok";
+        case CBO_ERR_INVALID_ARG: return "invalid argument";
+        case CBO_ERR_UNSUPPORTED: return "unsupported shape";
+        case CBO_ERR_WORKSPACE: return "workspace too small or misaligned";
+        case CBO_ERR_CUDA: return "CUDA error";
+        case CBO_ERR_NO_DEVICE: return "no CUDA device";
+        default: return "unknown status";
+    }
+}
+
+const char* cbo_last_cuda_error(void) { return g_last_err; }
+
+int64_t cbo_padded_n(int64_t N) { return (N + 127) / 128 * 128; }
+
+size_t cbo_workspace_bytes(int64_t N, int64_t d, int64_t b, const cbo_params* params, int64_t chunk) {
+    (void)d;
+    if (!params || N <= 0 || b <= 0) return 0;
+    return carve(nullptr, N, b, params, chunk).bytes;
+}
+
+int cbo_gemm_tn_f64(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
+                    int64_t Nn, int64_t K, int32_t tri, double* rownorm_partial, void* stream) {
+    if (!A || !B || !C || M <= 0 || Nn <= 0 || K <= 0) return CBO_ERR_INVALID_ARG;
+    if (Nn % cbo::GEMM_BN || K % cbo::GEMM_BN || tri < 0 || tri > 2) return CBO_ERR_UNSUPPORTED;
+    if ((lda | ldb | ldc) & 1) return CBO_ERR_UNSUPPORTED;      // 16-byte cp.async / double2 stores
+    CBO_CUDA(cbo::launch_gemm_tn(A, lda, B, ldb, C, ldc, (int)M, (int)Nn, (int)K, tri, rownorm_partial,
+                                 static_cast<cudaStream_t>(stream)));
+    return CBO_OK;
+}
+
+int cbo_kernel_rows_f64(const cbo_gp_f64* gp, const double* Xq, int64_t n, double* U, double* mu, void* stream) {
+    if (!gp || !Xq || !U || n <= 0) return CBO_ERR_INVALID_ARG;
+    if (gp->d > cbo::MAX_D) return CBO_ERR_UNSUPPORTED;
+    const int per_block = cbo::ROWS_WARPS * cbo::ROWS_CPW;
+    int blocks = (int)((n + per_block - 1) / per_block);
+    size_t smem = sizeof(double) * per_block * gp->d;
+    cbo::k_kernel_rows<<<blocks, cbo::ROWS_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+        Xq, (int)n, gp->X, (int)gp->N, (int)gp->Np, (int)gp->d, gp->inv_lengthscale, gp->outputscale, gp->mean,
+        gp->alpha, nullptr, 0, U, mu, nullptr);
+    CBO_CUDA(cudaGetLastError());
+    return CBO_OK;
+}
+
+int cbo_ratio_forward_f64(const cbo_ratio_mlp_f64* r, const double* x, int64_t n, int64_t d, double* out, void* stream) {
+    if (!r || !x || !out || n <= 0 || d <= 0) return CBO_ERR_INVALID_ARG;
+    if (r->hidden < 1 || r->hidden > cbo::MAX_H) return CBO_ERR_UNSUPPORTED;
+    cbo::k_ratio_mlp<<<(int)((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, (int)n, (int)d, (int)r->hidden, r->W1, r->b1, r->W2, r->b2, r->W3, r->b3, 0.0, out);
+    CBO_CUDA(cudaGetLastError());
+    return CBO_OK;
+}
+
+int cbo_conf_mask_to_bounds_f64(const double* grid, const double* mask, int64_t b, int64_t G, int64_t t, double* lb,
+                                double* ub, void* stream) {
+    if (!grid || !mask || !lb || !ub || b <= 0 || G <= 0 || t <= 0) return CBO_ERR_INVALID_ARG;
+    if (G > cbo::BOUNDS_MAX_G) return CBO_ERR_UNSUPPORTED;
+    int Gp = 2;
+    while (Gp < G) Gp <<= 1;
+    cbo::k_mask_to_bounds<<<(int)(b * t), cbo::BOUNDS_THREADS, 2 * Gp * sizeof(double),
+                            static_cast<cudaStream_t>(stream)>>>(grid, mask, (int)b, (int)G, (int)t, Gp, lb, ub);
+    CBO_CUDA(cudaGetLastError());
+    return CBO_OK;
+}
+
+int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* p, const double* Xq,
+                          int64_t b, const double* eps_grid, const double* z, const double* eps_mc,
+                          const double* u_rand, const cbo_outputs_f64* out, void* workspace, size_t workspace_bytes,
+                          int64_t chunk, void* stream) {
+    int st = validate(gp, p, b);
+    if (st != CBO_OK) return st;
+    if (!Xq || !eps_grid || !z || !eps_mc || !out || !out->acq || !workspace) return CBO_ERR_INVALID_ARG;
+    if (p->randomized && !u_rand) return CBO_ERR_INVALID_ARG;
+    if (ratio && (ratio->hidden < 1 || ratio->hidden > cbo::MAX_H)) return CBO_ERR_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(workspace) % kAlign) return CBO_ERR_WORKSPACE;
+    Workspace w = carve(workspace, gp->N, b, p, chunk);
+    if (w.bytes > workspace_bytes) return CBO_ERR_WORKSPACE;
+
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int N = (int)gp->N, Np = (int)gp->Np, d = (int)gp->d, Sp = (int)p->num_probes, G = (int)p->grid_res;
+    const int tiles_n = Np / cbo::GEMM_BN;
+    const int64_t C = pick_chunk(b, p, chunk);
+
+    // ---- per-call tables: T = A^-1 z[:N], dr_train, a, h0, zb, sum_dr -------------------------------
+    {
+    TimeScope ts_(T_PREP, s, 5);
+    cbo::k_pad_probes<<<(Np * Sp + 255) / 256, 256, 0, s>>>(z, N, Np, Sp, w.zp);
+    cbo::k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(gp->linv, Np, w.zp, Sp, w.tmp, 0, 1);
+    cbo::k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(gp->linv_t, Np, w.tmp, Sp, w.T, 1, 0);
+    if (ratio)
+        cbo::k_ratio_mlp<<<(N + 127) / 128, 128, 0, s>>>(gp->X, N, d, (int)ratio->hidden, ratio->W1, ratio->b1,
+                                                          ratio->W2, ratio->b2, ratio->W3, ratio->b3, 1e-6, w.dr_train);
+    else
+        cbo::k_fill<<<(Np + 255) / 256, 256, 0, s>>>(w.dr_train, Np, 1.0);
+    cbo::k_train_tables<<<1, 256, 0, s>>>(gp->alpha, z, w.T, N, Np, Sp, gp->noise, w.dr_train, w.a, w.h0, w.zb,
+                                          w.sum_dr);
+    }
+    CBO_CUDA(cudaGetLastError());
+
+    const int R = (int)p->max_grid_refinements;
+    for (int64_t c0 = 0; c0 < b; c0 += C) {
+        const int n = (int)((b - c0 < C) ? (b - c0) : C);
+        const double* Xc = Xq + c0 * d;
+        // ---- kernel rows, mu, u^T T; candidate density ratios -------------------------------------
+        {
+            TimeScope ts_(T_ROWS, s, ratio ? 2 : 1);
+            const int per_block = cbo::ROWS_WARPS * cbo::ROWS_CPW;
+            cbo::k_kernel_rows<<<(n + per_block - 1) / per_block, cbo::ROWS_WARPS * 32,
+                                 sizeof(double) * per_block * d, s>>>(Xc, n, gp->X, N, Np, d, gp->inv_lengthscale,
+                                                                      gp->outputscale, gp->mean, gp->alpha, w.T, Sp,
+                                                                      w.UW, w.mu, w.ut);
+            if (ratio)
+                cbo::k_ratio_mlp<<<(n + 127) / 128, 128, 0, s>>>(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1,
+                                                                  ratio->W2, ratio->b2, ratio->W3, ratio->b3, 1e-6,
+                                                                  w.drc);
+            CBO_CUDA(cudaGetLastError());
+        }
+        // ---- v = L^-1 u (+ ||v||^2 partials), w = L^-T v ------------------------------------------
+        {
+            TimeScope ts_(T_GEMM1, s, 1);
+            CBO_CUDA(cbo::launch_gemm_tn(w.UW, Np, gp->linv, Np, w.V, Np, n, Np, Np, cbo::TRI_LOWER, w.rn, s));
+        }
+        {
+            TimeScope ts_(T_GEMM2, s, 1);
+            CBO_CUDA(cbo::launch_gemm_tn(w.V, Np, gp->linv_t, Np, w.UW, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s));
+        }
+
+        // ---- scores / rank / mask / integration ----------------------------------------------------
+        cbo::ScoreArgs a;
+        memset(&a, 0, sizeof(a));
+        a.N = N; a.Np = Np; a.G = G; a.S = (int)p->num_mc; a.Sp = Sp; a.n_cand = n; a.tiles_n = tiles_n;
+        a.noise = gp->noise; a.kappa = gp->outputscale; a.alpha_lvl = p->alpha; a.temp = p->temp;
+        a.beta_prime = p->beta_prime; a.best_f = p->best_f;
+        a.kind = p->kind; a.optimistic = p->optimistic; a.randomized = p->randomized;
+        a.eps_per_candidate = p->eps_per_candidate;
+        a.a = w.a; a.h0 = w.h0; a.zb = w.zb; a.dr = w.dr_train; a.sum_dr = w.sum_dr; a.z_cand = z + int64_t(N) * Sp;
+        a.W = w.UW; a.rn_partial = w.rn; a.mu = w.mu; a.ut = w.ut; a.drc = ratio ? w.drc : nullptr;
+        a.eps_grid = p->eps_per_candidate ? eps_grid + c0 * G : eps_grid;
+        a.eps_mc = eps_mc;
+        a.u_rand = u_rand ? u_rand + c0 * G : nullptr;
+        auto set_outputs = [&](cbo::ScoreArgs& x) {
+            x.acq = out->acq + c0;
+            x.grid = out->target_grid ? out->target_grid + c0 * G : nullptr;
+            x.logp = out->grid_logp ? out->grid_logp + c0 * G : nullptr;
+            x.mask = out->conf_pred_mask ? out->conf_pred_mask + c0 * G : nullptr;
+            x.qscore = out->q_conf_scores ? out->q_conf_scores + c0 * G : nullptr;
+            x.ood = out->ood_mask ? out->ood_mask + c0 : nullptr;
+            x.post_mean = out->post_mean ? out->post_mean + c0 : nullptr;
+            x.post_var = out->post_var ? out->post_var + c0 : nullptr;
+            x.num_acc = out->num_accepted ? out->num_accepted + c0 : nullptr;
+        };
+        const bool soft = p->temp > 0.0;
+        if (R == 0) {
+            set_outputs(a);
+            TimeScope ts_(T_SCORE, s, 1);
+            CBO_CUDA(soft ? launch_score<true>(a, s) : launch_score<false>(a, s));
+        } else {
+            // grid refinement (helpers.py:129-189): probe passes keep only the accepted counts; the pass with the
+            // smallest grid_score is then re-run into the caller's buffers.  One host sync per pass, like the
+            // reference (helpers.py:151-152,177).
+            cbo::k_fill<<<(n + 255) / 256, 256, 0, s>>>(w.cscale, n, 1.0);
+            float best_score = INFINITY;
+            int best_step = 0;
+            double* scratch_acq = w.V;                    // V is dead after pass 2
+            for (int step = 0; step <= R; ++step) {
+                cbo::ScoreArgs pa = a;
+                pa.cscale = w.cscale + int64_t(step) * b;
+                pa.acq = scratch_acq;
+                pa.num_acc = w.nacc;
+                CBO_CUDA(soft ? launch_score<true>(pa, s) : launch_score<false>(pa, s));
+                k_accept_stats<<<1, 256, 0, s>>>(w.nacc, n, G, w.stats);
+                double hs[3];
+                CBO_CUDA(cudaMemcpyAsync(hs, w.stats, sizeof(hs), cudaMemcpyDeviceToHost, s));
+                CBO_CUDA(cudaStreamSynchronize(s));
+                float score = (float)hs[2];
+                if (score < best_score) { best_score = score; best_step = step; }
+                bool rescale = hs[0] < 2.0 || hs[1] > double(G - 2);
+                if (!rescale) break;
+                if (step < R)
+                    k_rescale<<<(n + 255) / 256, 256, 0, s>>>(w.nacc, w.cscale + int64_t(step) * b,
+                                                              w.cscale + int64_t(step + 1) * b, n, G, (int)p->q);
+            }
+            cbo::ScoreArgs fa = a;
+            fa.cscale = w.cscale + int64_t(best_step) * b;
+            set_outputs(fa);
+            CBO_CUDA(soft ? launch_score<true>(fa, s) : launch_score<false>(fa, s));
+        }
+    }
+    return CBO_OK;
+}
+
+void cbo_timing_enable(int on) {
+    g_timing.enabled = on != 0;
+}
+
+// Sums elapsed ms per kernel class since the last collect (synchronises on the recorded events).
+int cbo_timing_collect(double* ms_out /* 5 */, int64_t* launches_out /* 5 */) {
+    if (!ms_out || !launches_out) return CBO_ERR_INVALID_ARG;
+    for (int c = 0; c < T_NCLASS; ++c) {
+        double tot = 0.0;
+        auto& v = g_timing.ev[c];
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+            CBO_CUDA(cudaEventSynchronize(v[i + 1]));
+            float ms = 0.f;
+            CBO_CUDA(cudaEventElapsedTime(&ms, v[i], v[i + 1]));
+            tot += ms;
+        }
+        for (cudaEvent_t e : v) g_timing.pool.push_back(e);
+        v.clear();
+        ms_out[c] = tot;
+        launches_out[c] = g_timing.launches[c];
+        g_timing.launches[c] = 0;
+    }
+    return CBO_OK;
+}
+
+int cbo_conformal_acq_host_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* p,
+                               const double* Xq_host, int64_t b, const double* eps_grid, const double* z,
+                               const double* eps_mc, const double* u_rand, double* acq_host, double* Xq_staging,
+                               double* acq_staging, void* workspace, size_t workspace_bytes, int64_t chunk,
+                               void* stream) {
+    if (!gp || !p || !Xq_host || !acq_host || !Xq_staging || !acq_staging || b <= 0) return CBO_ERR_INVALID_ARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CBO_CUDA(cudaMemcpyAsync(Xq_staging, Xq_host, sizeof(double) * b * p->q * gp->d, cudaMemcpyHostToDevice, s));
+    cbo_outputs_f64 out;
+    memset(&out, 0, sizeof(out));
+    out.acq = acq_staging;
+    int st = cbo_conformal_acq_f64(gp, ratio, p, Xq_staging, b, eps_grid, z, eps_mc, u_rand, &out, workspace,
+                                   workspace_bytes, chunk, stream);
+    if (st != CBO_OK) return st;
+    CBO_CUDA(cudaMemcpyAsync(acq_host, acq_staging, sizeof(double) * b, cudaMemcpyDeviceToHost, s));
+    CBO_CUDA(cudaStreamSynchronize(s));
+    return CBO_OK;
+}
+
+}  // extern "C"

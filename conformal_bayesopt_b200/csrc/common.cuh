@@ -1,0 +1,88 @@
+// common.cuh -- device helpers shared by the libcbo kernels (sm_100a, fp64).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cbo {
+
+constexpr int kWarp = 32;
+constexpr double kLog2Pi = 1.8378770664093453;   // log(2*pi)
+constexpr double kSqrt5 = 2.23606797749979;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- cp.async (LDGSTS) 16-byte copies -------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ---- fp64 tensor-core MMA (DMMA.8x8x4 in SASS) ----------------------------------------------
+// D(8x8) += A(8x4, row) * B(4x8, col).  Lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2*(l%4)+{0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- reduced-cost fp64 transcendental pieces for the soft-rank inner loop -------------------
+// exp(x) for x in [-745, 0], relative error <= 4e-11 (64-entry 2^(j/64) table + cubic).  The soft
+// rank needs rho to ~1e-9; this costs 7 fp64-pipe instructions instead of the
+// ~26 of libdevice exp (profiles/r01_fp64_peak.log).  `tab` is a 64-entry table of 2^(j/64).
+__device__ __forceinline__ double fast_exp_neg(double x, const double* __restrict__ tab) {
+    constexpr double kMagic = 6755399441055744.0;            // 1.5 * 2^52: integer lands in the low word
+    constexpr double kL2e64 = 92.332482616893657;            // 64 / ln 2
+    constexpr double kLn2o64 = 0.010830424696249145;         // ln 2 / 64
+    double t = fma(x, kL2e64, kMagic);
+    int n = __double2loint(t);                               // round(x * 64 / ln2), n <= 0
+    double nf = t - kMagic;
+    double y = fma(nf, -kLn2o64, x);                         // |y| <= ln2/128
+    double p = fma(y, 1.0 / 6.0, 0.5);
+    p = fma(p, y, 1.0);
+    p = p * y;                                               // y + y^2/2 + y^3/6
+    double tj = tab[n & 63];
+    double e = fma(tj, p, tj);
+    int k = n >> 6;                                          // floor(n / 64)
+    int hi = __double2hiint(e) + (k << 20);                  // scale by 2^k (result stays normal for x > -700)
+    e = __hiloint2double(hi, __double2loint(e));
+    return (k < -1000) ? 0.0 : e;
+}
+
+// 1 / d for d in [1, 2]: MUFU.RCP64H seed (rel. err 2^-23) + one Newton step -> ~2^-45.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
+
+// sigmoid(z) with absolute error ~1e-11; saturates exactly to 0/1 for |z| > 40.
+__device__ __forceinline__ double fast_sigmoid(double z, const double* __restrict__ tab) {
+    double az = fabs(z);
+    double e = fast_exp_neg(-fmin(az, 64.0), tab);
+    double r = fast_rcp(1.0 + e);
+    return (z >= 0.0) ? r : e * r;
+}
+
+// accurate sigmoid for the per-(candidate, grid point) epilogue (not in the inner loop)
+__device__ __forceinline__ double sigmoid_acc(double z) {
+    if (z >= 0.0) return 1.0 / (1.0 + exp(-z));
+    double e = exp(z);
+    return e / (1.0 + e);
+}
+
+}  // namespace cbo

@@ -1,0 +1,175 @@
+// gemm_tri.cuh -- fp64 tensor-core (DMMA) "TN" GEMM with triangular K-range skipping.
+//
+//   C[m, n] = sum_{k in range(n-tile)} A[m, k] * B[n, k]
+//
+// This is the fantasy-update solve of the conformal path: with
+// B = L^-1 (lower, explicit inverse of chol(K + noise I)) and A = U (kernel rows, one row per
+// candidate) pass 1 gives V = U L^-T, i.e. v = L^-1 u for every candidate (tri = lower: only
+// k < end of the n-tile contributes); with B = L^-T and A = V pass 2 gives w = L^-T v = A^-1 u
+// (tri = upper: only k >= begin of the n-tile).  It replaces what the reference does through
+// gp.condition_on_observations -> get_fantasy_strategy (cholesky_solve of the new kernel column,
+// conformalbo/helpers.py:243) -- there once per (candidate, grid point), here once per candidate.
+//
+// Design (B200, sm_100a): fp64 has no tcgen05 kind; the fp64 tensor path on Blackwell is
+// mma.sync m8n8k4 (SASS DMMA.8x8x4), measured at 37.0 TFLOP/s = the whole fp64 pipe
+// (profiles/r01_fp64_peak.log).  CTA tile 128 x 128, BK = 16, 3-stage cp.async pipeline into
+// padded shared memory (row stride 20 doubles: conflict-free 64-bit fragment loads), 8 warps as
+// 2 (m) x 4 (n), warp tile 64 x 32 = 8 x 4 DMMA fragments, 64 fp64 accumulators per thread.
+// Tiles are issued longest-K first so the triangular imbalance fills the tail of the grid.
+#pragma once
+#include "common.cuh"
+
+namespace cbo {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 128;
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_LDS = GEMM_BK + 4;       // padded row stride (doubles)
+constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_STAGE_DOUBLES = (GEMM_BM + GEMM_BN) * GEMM_LDS;
+constexpr size_t GEMM_SMEM_BYTES = size_t(GEMM_STAGES) * GEMM_STAGE_DOUBLES * sizeof(double);
+
+enum { TRI_FULL = 0, TRI_LOWER = 1, TRI_UPPER = 2 };
+
+__device__ __forceinline__ void gemm_load_stage(double* sA, double* sB, const double* __restrict__ A, int64_t lda,
+                                                const double* __restrict__ B, int64_t ldb, int m0, int n0, int k0,
+                                                int M, int tid) {
+    // A tile: 128 rows x 16 doubles = 1024 16-byte chunks; same for B.  4 + 4 chunks per thread.
+#pragma unroll
+    for (int it = 0; it < (GEMM_BM * GEMM_BK / 2) / GEMM_THREADS; ++it) {
+        int chunk = tid + it * GEMM_THREADS;
+        int r = chunk >> 3, cc = chunk & 7;
+        int gr = m0 + r;
+        gr = gr < M ? gr : M - 1;             // clamp: rows beyond M are computed but never stored
+        cp_async16(sA + r * GEMM_LDS + 2 * cc, A + int64_t(gr) * lda + k0 + 2 * cc);
+    }
+#pragma unroll
+    for (int it = 0; it < (GEMM_BN * GEMM_BK / 2) / GEMM_THREADS; ++it) {
+        int chunk = tid + it * GEMM_THREADS;
+        int r = chunk >> 3, cc = chunk & 7;
+        cp_async16(sB + r * GEMM_LDS + 2 * cc, B + int64_t(n0 + r) * ldb + k0 + 2 * cc);
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
+              double* __restrict__ C, int64_t ldc, int M, int Nn, int K, int tri,
+              double* __restrict__ rownorm_partial) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;                 // 2 x 4 warps
+    const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    const int tiles_n = Nn / GEMM_BN;
+    // longest-K tiles first: lower -> last n-tile first; upper / full -> first n-tile first
+    const int t = blockIdx.x;
+    const int n_ord = t / tiles_m;
+    const int n_tile = (tri == TRI_LOWER) ? (tiles_n - 1 - n_ord) : n_ord;
+    const int m_tile = t - n_ord * tiles_m;
+    const int m0 = m_tile * GEMM_BM, n0 = n_tile * GEMM_BN;
+    int k_begin = 0, k_end = K;
+    if (tri == TRI_LOWER) k_end = min(K, n0 + GEMM_BN);
+    if (tri == TRI_UPPER) k_begin = n0;
+    const int nk = (k_end - k_begin) / GEMM_BK;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // prologue: STAGES-1 tiles in flight
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+        if (s < nk) {
+            double* sA = smem + s * GEMM_STAGE_DOUBLES;
+            gemm_load_stage(sA, sA + GEMM_BM * GEMM_LDS, A, lda, B, ldb, m0, n0, k_begin + s * GEMM_BK, M, tid);
+        }
+        cp_async_commit();
+    }
+
+    const int fr = lane >> 2, fk = lane & 3;                 // fragment row / k within the 8x4 fragment
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<GEMM_STAGES - 2>();
+        __syncthreads();                                      // tile kt landed; everyone done with tile kt-1
+        {
+            int nt = kt + GEMM_STAGES - 1;
+            if (nt < nk) {
+                double* sA = smem + (nt % GEMM_STAGES) * GEMM_STAGE_DOUBLES;
+                gemm_load_stage(sA, sA + GEMM_BM * GEMM_LDS, A, lda, B, ldb, m0, n0, k_begin + nt * GEMM_BK, M, tid);
+            }
+            cp_async_commit();
+        }
+        const double* sA = smem + (kt % GEMM_STAGES) * GEMM_STAGE_DOUBLES + (wm * 64 + fr) * GEMM_LDS + fk;
+        const double* sB = smem + (kt % GEMM_STAGES) * GEMM_STAGE_DOUBLES + GEMM_BM * GEMM_LDS +
+                           (wn * 32 + fr) * GEMM_LDS + fk;
+#pragma unroll
+        for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = sA[i * 8 * GEMM_LDS + ks * 4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = sB[j * 8 * GEMM_LDS + ks * 4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: C tile; each thread owns rows (wm*64 + i*8 + fr), cols (wn*32 + j*8 + 2*fk + {0,1})
+    double rn[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int row = m0 + wm * 64 + i * 8 + fr;
+        double s2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s2 = fma(acc[i][j][0], acc[i][j][0], s2);
+            s2 = fma(acc[i][j][1], acc[i][j][1], s2);
+            if (row < M) {
+                double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+                *reinterpret_cast<double2*>(C + int64_t(row) * ldc + n0 + wn * 32 + j * 8 + 2 * fk) = v;
+            }
+        }
+        rn[i] = s2;
+    }
+    if (rownorm_partial != nullptr) {
+        __syncthreads();                                      // smem reuse
+        double* red = smem;                                   // [128 rows][4 n-warps]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double s2 = rn[i];
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+            if (fk == 0) red[(wm * 64 + i * 8 + fr) * 4 + wn] = s2;
+        }
+        __syncthreads();
+        if (tid < GEMM_BM) {
+            int row = m0 + tid;
+            if (row < M) {
+                double s2 = (red[tid * 4 + 0] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]);
+                rownorm_partial[int64_t(row) * tiles_n + n_tile] = s2;
+            }
+        }
+    }
+}
+
+inline cudaError_t launch_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                                  int M, int Nn, int K, int tri, double* rownorm_partial, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tn_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)GEMM_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int tiles_m = (M + GEMM_BM - 1) / GEMM_BM, tiles_n = Nn / GEMM_BN;
+    k_gemm_tn_f64<<<tiles_m * tiles_n, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(A, lda, B, ldb, C, ldc, M, Nn, K, tri,
+                                                                               rownorm_partial);
+    return cudaGetLastError();
+}
+
+}  // namespace cbo

@@ -1,0 +1,213 @@
+// rows.cuh -- kernel rows of the candidates against the training set, plus the per-call tables.
+//
+//   k_kernel_rows    U[c, i] = os * (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r),  r = ||(x_c - X_i) / l||
+//                    mu[c]   = mean + sum_i U[c,i] alpha_i                   (helpers.py:119, acquisitions.py:59)
+//                    ut[c,s] = sum_i U[c,i] T[i,s]                           (probe correction, App. A-4)
+//   k_ratio_mlp      RatioEstimator.forward on rows of x                     (ratio_estimation.py:97-99)
+//   k_probe_matvec   out[i, s] = sum_j Mat[i, j] in[j, s]   (T = L^-T (L^-1 z): 2 launches)
+//   k_train_tables   per-train-point tables for the score kernel             (helpers.py:396-405)
+#pragma once
+#include "common.cuh"
+
+namespace cbo {
+
+constexpr int ROWS_CPW = 4;          // candidates per warp
+constexpr int ROWS_WARPS = 8;
+constexpr int MAX_D = 64;
+constexpr int MAX_SP = 16;
+constexpr int MAX_H = 64;
+
+// One warp owns ROWS_CPW candidates and sweeps i = lane, lane+32, ...; X_i is loaded once per
+// sweep step and reused for the ROWS_CPW candidates; U stores are 256-byte coalesced.
+__global__ void __launch_bounds__(ROWS_WARPS * 32)
+k_kernel_rows(const double* __restrict__ Xq, int n, const double* __restrict__ X, int N, int Np, int d,
+              const double* __restrict__ inv_ls, double outputscale, double mean,
+              const double* __restrict__ alpha, const double* __restrict__ T, int Sp,
+              double* __restrict__ U, double* __restrict__ mu, double* __restrict__ ut) {
+    extern __shared__ double sx[];                      // [ROWS_WARPS][ROWS_CPW][d] scaled candidate coords
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = (blockIdx.x * ROWS_WARPS + warp) * ROWS_CPW;
+    double* myx = sx + warp * ROWS_CPW * d;
+    for (int e = lane; e < ROWS_CPW * d; e += 32) {
+        int cc = e / d, k = e - cc * d;
+        int c = min(c0 + cc, n - 1);
+        myx[e] = Xq[int64_t(c) * d + k] * inv_ls[k];
+    }
+    __syncwarp();
+    if (c0 >= n) return;
+
+    double acc_mu[ROWS_CPW];
+    double acc_ut[ROWS_CPW][MAX_SP];
+#pragma unroll
+    for (int cc = 0; cc < ROWS_CPW; ++cc) {
+        acc_mu[cc] = 0.0;
+#pragma unroll
+        for (int s = 0; s < MAX_SP; ++s) acc_ut[cc][s] = 0.0;
+    }
+    for (int i = lane; i < Np; i += 32) {
+        double kv[ROWS_CPW];
+        if (i < N) {
+            double r2[ROWS_CPW];
+#pragma unroll
+            for (int cc = 0; cc < ROWS_CPW; ++cc) r2[cc] = 0.0;
+            for (int k = 0; k < d; ++k) {
+                double xi = X[int64_t(i) * d + k] * inv_ls[k];
+#pragma unroll
+                for (int cc = 0; cc < ROWS_CPW; ++cc) {
+                    double df = myx[cc * d + k] - xi;
+                    r2[cc] = fma(df, df, r2[cc]);
+                }
+            }
+            double al = alpha[i];
+#pragma unroll
+            for (int cc = 0; cc < ROWS_CPW; ++cc) {
+                double r = sqrt(fmax(r2[cc], 1e-30));
+                double sr = kSqrt5 * r;
+                kv[cc] = outputscale * (1.0 + sr + (5.0 / 3.0) * r * r) * exp(-sr);
+                acc_mu[cc] = fma(kv[cc], al, acc_mu[cc]);
+            }
+            if (T != nullptr) {
+#pragma unroll
+                for (int s = 0; s < MAX_SP; ++s) {
+                    if (s < Sp) {
+                        double ts = T[int64_t(i) * Sp + s];
+#pragma unroll
+                        for (int cc = 0; cc < ROWS_CPW; ++cc) acc_ut[cc][s] = fma(kv[cc], ts, acc_ut[cc][s]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < ROWS_CPW; ++cc) kv[cc] = 0.0;
+        }
+#pragma unroll
+        for (int cc = 0; cc < ROWS_CPW; ++cc)
+            if (c0 + cc < n) U[int64_t(c0 + cc) * Np + i] = kv[cc];
+    }
+#pragma unroll
+    for (int cc = 0; cc < ROWS_CPW; ++cc) {
+        double m = warp_sum(acc_mu[cc]);
+        if (lane == 0 && c0 + cc < n && mu != nullptr) mu[c0 + cc] = mean + m;
+        if (ut != nullptr) {
+#pragma unroll
+            for (int s = 0; s < MAX_SP; ++s) {
+                if (s < Sp) {
+                    double v = warp_sum(acc_ut[cc][s]);
+                    if (lane == 0 && c0 + cc < n) ut[int64_t(c0 + cc) * Sp + s] = v;
+                }
+            }
+        }
+    }
+}
+
+// Thread per point.  w = min(p, 1-1e-6) / max(1-p, 1e-6), p = sigmoid(MLP(x)).  clamp_min(1e-6) of the
+// caller (helpers.py:292-293) is applied when `clamp_min` > 0.
+__global__ void __launch_bounds__(128)
+k_ratio_mlp(const double* __restrict__ x, int n, int d, int H, const double* __restrict__ W1,
+            const double* __restrict__ b1, const double* __restrict__ W2, const double* __restrict__ b2,
+            const double* __restrict__ W3, const double* __restrict__ b3, double clamp_min,
+            double* __restrict__ out) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    double h1[MAX_H];
+#pragma unroll 1
+    for (int j = 0; j < H; ++j) {
+        double a = b1[j];
+        for (int k = 0; k < d; ++k) a = fma(W1[j * d + k], x[int64_t(p) * d + k], a);
+        h1[j] = fmax(a, 0.0);
+    }
+    double logit = b3[0];
+#pragma unroll 1
+    for (int j = 0; j < H; ++j) {
+        double a = b2[j];
+#pragma unroll 8
+        for (int m = 0; m < MAX_H; ++m)
+            if (m < H) a = fma(W2[j * H + m], h1[m], a);
+        logit = fma(W3[j], fmax(a, 0.0), logit);
+    }
+    double pr = sigmoid_acc(logit);
+    double w = fmin(pr, 1.0 - 1e-6) / fmax(1.0 - pr, 1e-6);
+    out[p] = fmax(w, clamp_min);
+}
+
+__global__ void k_fill(double* __restrict__ out, int n, double v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
+// out[i, s] = sum_j Mat[i, j] * in[j, s]  for s < Sp.  One warp per row i; Mat is Np x Np.
+__global__ void __launch_bounds__(256)
+k_probe_matvec(const double* __restrict__ Mat, int Np, const double* __restrict__ in, int Sp,
+               double* __restrict__ out, int j_begin_is_row, int j_end_is_row) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= Np) return;
+    // triangular structure: lower matrix -> j <= i; upper -> j >= i
+    int jb = j_begin_is_row ? (i & ~31) : 0;
+    int je = j_end_is_row ? min(Np, (i | 31) + 1) : Np;
+    double acc[MAX_SP];
+#pragma unroll
+    for (int s = 0; s < MAX_SP; ++s) acc[s] = 0.0;
+    for (int j = jb + lane; j < je; j += 32) {
+        double m = Mat[int64_t(i) * Np + j];
+#pragma unroll
+        for (int s = 0; s < MAX_SP; ++s)
+            if (s < Sp) acc[s] = fma(m, in[int64_t(j) * Sp + s], acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < MAX_SP; ++s) {
+        if (s < Sp) {
+            double v = warp_sum(acc[s]);
+            if (lane == 0) out[int64_t(i) * Sp + s] = v;
+        }
+    }
+}
+
+// z (N+q) x Sp of +-1 -> padded copy zp (Np x Sp, zeros beyond N)
+__global__ void k_pad_probes(const double* __restrict__ z, int N, int Np, int Sp, double* __restrict__ zp) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Np * Sp) return;
+    int i = e / Sp;
+    zp[e] = (i < N) ? z[e] : 0.0;
+}
+
+// Per-train-point tables of the score kernel:
+//   a[i]   = noise * alpha_i
+//   h0[i]  = 1 + (Sp - noise * sum_s z_is T_is) / (Sp + 1e-6)       (g- and candidate-independent part of var/noise)
+//   zb[i]  = bit s set <=> z_is > 0
+// and sum_dr = sum_i dr_i (single block, deterministic tree).
+__global__ void __launch_bounds__(256)
+k_train_tables(const double* __restrict__ alpha, const double* __restrict__ z, const double* __restrict__ T, int N,
+               int Np, int Sp, double noise, const double* __restrict__ dr, double* __restrict__ a,
+               double* __restrict__ h0, uint32_t* __restrict__ zb, double* __restrict__ sum_dr) {
+    __shared__ double red[256];
+    double part = 0.0;
+    for (int i = threadIdx.x; i < Np; i += blockDim.x) {
+        if (i < N) {
+            double acc = 0.0;
+            uint32_t bits = 0;
+            for (int s = 0; s < Sp; ++s) {
+                double zs = z[int64_t(i) * Sp + s];
+                acc = fma(zs, T[int64_t(i) * Sp + s], acc);
+                bits |= (zs > 0.0) ? (1u << s) : 0u;
+            }
+            a[i] = noise * alpha[i];
+            h0[i] = 1.0 + (double(Sp) - noise * acc) / (double(Sp) + 1e-6);
+            zb[i] = bits;
+            part += dr[i];
+        } else {
+            a[i] = 0.0;
+            h0[i] = 1.0;
+            zb[i] = 0;
+        }
+    }
+    red[threadIdx.x] = part;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sum_dr[0] = red[0];
+}
+
+}  // namespace cbo

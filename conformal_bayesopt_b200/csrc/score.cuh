@@ -1,0 +1,284 @@
+// score.cuh -- nonconformity scores, density-ratio-weighted conformal rank, mask and the
+// importance-weighted acquisition value, one persistent CTA looping over candidates.
+//
+// Fuses, per candidate (q = 1, one output), what the reference evaluates as dense batched tensors
+// of shape (b, G, N+1, ...) (conformalbo/helpers.py:266-325, conformalbo/acquisitions.py:57-76,
+// 151-159, 88-98, 225-248), using the closed forms of SURVEY.md App. A-2..A-7:
+//   phase A  (all threads)   per-train-point Hutchinson variance for THIS candidate (A-4):
+//                            var_i = noise (h0_i + noise/(Sp+1e-6) * w_i * (z_i . c)),  c = (z_c - u^T T)/s
+//                            -> shared memory tables  ww = noise w_i, iv = 1/(2 var_i), lv = -log(var_i)/2 - log(2pi)/2
+//   phase B  (warp per 8 grid points) for every train point: residual, score, hard count,
+//                            soft rank sigmoid, weighted sums (A-3, A-5) -- the hot loop,
+//                            ~18 fp64-pipe instructions per (train point, grid point)
+//   phase C  (lane per grid point) weighted mass, randomised step, conformal mask, log-density,
+//                            optimistic mask, refit mean (A-5, A-6)
+//   phase D  (block reduce over the grid) importance-weighted integration (A-7)
+#pragma once
+#include "common.cuh"
+#include "rows.cuh"
+
+namespace cbo {
+
+constexpr int SCORE_THREADS = 256;
+constexpr int SCORE_WARPS = SCORE_THREADS / 32;
+constexpr int SCORE_GPW = 8;           // grid points per warp pass
+constexpr int MAX_S = 16;
+
+struct ScoreArgs {
+    // geometry
+    int N, Np, G, S, Sp, n_cand, tiles_n;
+    // model scalars
+    double noise, kappa, alpha_lvl, temp, beta_prime, best_f;
+    int kind, optimistic, randomized, eps_per_candidate;
+    // per-call tables (train side)
+    const double* a;        // Np  noise*alpha
+    const double* h0;       // Np
+    const uint32_t* zb;     // Np
+    const double* dr;       // Np
+    const double* sum_dr;   // 1
+    const double* z_cand;   // Sp  probe row of the candidate
+    // per-candidate inputs
+    const double* W;        // n_cand x Np
+    const double* rn_partial;  // n_cand x tiles_n   partial ||v||^2
+    const double* mu;       // n_cand
+    const double* ut;       // n_cand x Sp
+    const double* drc;      // n_cand (already clamp_min 1e-6) or nullptr -> 1
+    const double* cscale;   // n_cand grid covariance scale or nullptr -> 1
+    const double* eps_grid; // G or n_cand x G
+    const double* eps_mc;   // S x G
+    const double* u_rand;   // n_cand x G or nullptr
+    // outputs (nullable except acq)
+    double* acq; double* grid; double* logp; double* mask; double* ood; double* qscore;
+    double* post_mean; double* post_var; double* num_acc;
+};
+
+__host__ __device__ inline size_t score_smem_bytes(int Np, int G) {
+    // tab[64] | a, dr, ww, iv, lv [Np each] | g-arrays cw, nc, mf, mk [G each] | red[SCORE_WARPS * (2*MAX_S+3)] | zb[Np] u32
+    return sizeof(double) * (64 + 5 * size_t(Np) + 4 * size_t(G) + SCORE_WARPS * (2 * MAX_S + 3)) +
+           sizeof(uint32_t) * size_t(Np);
+}
+
+template <bool SOFT>
+__global__ void __launch_bounds__(SCORE_THREADS)
+k_score(const ScoreArgs p) {
+    extern __shared__ __align__(16) double sm[];
+    double* tab = sm;
+    double* sa = tab + 64;
+    double* sdr = sa + p.Np;
+    double* sww = sdr + p.Np;
+    double* siv = sww + p.Np;
+    double* slv = siv + p.Np;
+    double* g_cw = slv + p.Np;
+    double* g_nc = g_cw + p.G;
+    double* g_mf = g_nc + p.G;
+    double* g_mk = g_mf + p.G;
+    double* red = g_mk + p.G;
+    uint32_t* szb = reinterpret_cast<uint32_t*>(red + SCORE_WARPS * (2 * MAX_S + 3));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = p.N, G = p.G, Sp = p.Sp;
+
+    // ---- once per CTA: candidate-independent tables -------------------------------------------
+    if (tid < 64) tab[tid] = exp2(double(tid) / 64.0);
+    for (int i = tid; i < N; i += SCORE_THREADS) {
+        sa[i] = p.a[i];
+        sdr[i] = p.dr[i];
+        szb[i] = p.zb[i];
+    }
+    const double sum_dr = p.sum_dr[0];
+    const double kvar = p.noise / (double(Sp) + 1e-6);
+    const double inv_temp = SOFT ? 1.0 / p.temp : 0.0;
+    double zc[MAX_SP];
+#pragma unroll
+    for (int s = 0; s < MAX_SP; ++s) zc[s] = (s < Sp) ? p.z_cand[s] : 0.0;
+
+    for (int c = blockIdx.x; c < p.n_cand; c += gridDim.x) {
+        // ---- phase A ---------------------------------------------------------------------------
+        double vnorm = 0.0;
+        for (int t = 0; t < p.tiles_n; ++t) vnorm += p.rn_partial[int64_t(c) * p.tiles_n + t];
+        const double s_var = p.kappa + p.noise - vnorm;                 // Schur complement (noisy predictive variance)
+        const double mu = p.mu[c];
+        const double inv_s = 1.0 / s_var;
+        double cs[MAX_SP];
+        double zcc = 0.0;                                               // sum_s z_cs c_s
+#pragma unroll
+        for (int s = 0; s < MAX_SP; ++s) {
+            cs[s] = (s < Sp) ? (zc[s] - p.ut[int64_t(c) * Sp + s]) * inv_s : 0.0;
+            zcc = fma(zc[s], cs[s], zcc);
+        }
+        const double var_c = p.noise * (1.0 + (double(Sp) - p.noise * zcc) / (double(Sp) + 1e-6));
+        int bad = !(var_c > 0.0) || !(s_var > 0.0);
+        const double* Wc = p.W + int64_t(c) * p.Np;
+        for (int i = tid; i < N; i += SCORE_THREADS) {
+            double w = Wc[i];
+            uint32_t bits = szb[i];
+            double zdot = 0.0;
+#pragma unroll
+            for (int s = 0; s < MAX_SP; ++s)
+                if (s < Sp) zdot += ((bits >> s) & 1u) ? cs[s] : -cs[s];
+            double var = p.noise * fma(kvar * w, zdot, p.h0[i]);
+            bad |= !(var > 0.0);
+            sww[i] = p.noise * w;
+            siv[i] = 0.5 / var;
+            slv[i] = -0.5 * log(var) - 0.5 * kLog2Pi;
+        }
+        bad = __syncthreads_or(bad);
+        const double iv_c = 0.5 / var_c;
+        const double lv_c = -0.5 * log(var_c) - 0.5 * kLog2Pi;
+        const double cscale = p.cscale ? p.cscale[c] : 1.0;
+        const double gsd = sqrt(cscale * s_var);                        // sd of the grid distribution
+        const double drc = p.drc ? p.drc[c] : 1.0;
+        const double norm = sum_dr + drc;
+        const double omega_c = drc / norm;
+
+        // ---- phase B + C: warp per octet of grid points ----------------------------------------
+        for (int g0 = warp * SCORE_GPW; g0 < G; g0 += SCORE_WARPS * SCORE_GPW) {
+            double bg[SCORE_GPW], scc[SCORE_GPW], sr[SCORE_GPW], sw[SCORE_GPW];
+            int cnt[SCORE_GPW];
+#pragma unroll
+            for (int k = 0; k < SCORE_GPW; ++k) {
+                int g = min(g0 + k, G - 1);
+                double eps = p.eps_grid[p.eps_per_candidate ? int64_t(c) * G + g : g];
+                double dev = gsd * eps;                                 // y_g - mu
+                bg[k] = dev * inv_s;
+                double rc = p.noise * bg[k];
+                scc[k] = fma(-rc * rc, iv_c, lv_c);
+                sr[k] = 0.0; sw[k] = 0.0; cnt[k] = 0;
+            }
+            if (!bad) {
+                for (int i = lane; i < N; i += 32) {
+                    const double a = sa[i], ww = sww[i], iv = siv[i], lv = slv[i], dr = sdr[i];
+#pragma unroll
+                    for (int k = 0; k < SCORE_GPW; ++k) {
+                        double r = fma(-ww, bg[k], a);
+                        double sc = fma(-(r * r), iv, lv);
+                        double dd = scc[k] - sc;
+                        bool ge = dd >= 0.0;
+                        cnt[k] += ge ? 1 : 0;
+                        if (SOFT) {
+                            double rho = fast_sigmoid(dd * inv_temp, tab);
+                            sr[k] += rho;
+                            sw[k] = fma(rho, dr, sw[k]);
+                        } else {
+                            sw[k] += ge ? dr : 0.0;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < SCORE_GPW; ++k) {
+                cnt[k] = warp_sum_int(cnt[k]);
+                sw[k] = warp_sum(sw[k]);
+                if (SOFT) sr[k] = warp_sum(sr[k]);
+            }
+            // phase C: lane k finishes grid point g0 + k
+            double my_sr = 0.0, my_sw = 0.0, my_scc = 0.0, my_bg = 0.0;
+            int my_cnt = 0;
+#pragma unroll
+            for (int k = 0; k < SCORE_GPW; ++k)
+                if (lane == k) { my_sr = sr[k]; my_sw = sw[k]; my_cnt = cnt[k]; my_scc = scc[k]; my_bg = bg[k]; }
+            const int g = g0 + lane;
+            if (lane < SCORE_GPW && g < G) {
+                double n_g = double(my_cnt + 1);                        // includes the candidate itself
+                double M, rho_self;
+                if (SOFT) {
+                    double scale = n_g / (my_sr + 0.5);                 // self: sigmoid(0) = 1/2
+                    rho_self = 0.5 * scale;
+                    M = scale * (my_sw + 0.5 * drc) / norm;
+                } else {
+                    rho_self = 1.0;
+                    M = (my_sw + drc) / norm;
+                }
+                if (p.randomized) {
+                    double D = fmax(rho_self * omega_c, 1e-6);
+                    double pr = fmin(fmax((M - p.alpha_lvl) / D, 0.0), 1.0);
+                    double u = p.u_rand[int64_t(c) * G + g];
+                    M -= (u < pr) ? 0.0 : D;
+                }
+                double mk = SOFT ? sigmoid_acc((M - p.alpha_lvl) * inv_temp) : ((M > p.alpha_lvl) ? 1.0 : 0.0);
+                double dev = my_bg * s_var;
+                double eps = p.eps_grid[p.eps_per_candidate ? int64_t(c) * G + g : g];
+                double yg = mu + gsd * eps;
+                double lp = -0.5 * (eps * eps + log(cscale * s_var) + kLog2Pi);
+                double opt = p.optimistic ? ((yg >= mu) ? 1.0 : 0.0) : 1.0;
+                double shrink = 1.0 - p.noise * inv_s;
+                (void)dev;
+                g_mk[g] = mk;
+                g_cw[g] = mk * opt / fmax(exp(lp), 1e-6);
+                g_nc[g] = (1.0 - mk) * opt;
+                g_mf[g] = mu + (yg - mu) * shrink;
+                if (bad) { g_mk[g] = g_cw[g] = g_nc[g] = g_mf[g] = nan(""); mk = lp = nan(""); }
+                if (p.grid) p.grid[int64_t(c) * G + g] = yg;
+                if (p.logp) p.logp[int64_t(c) * G + g] = lp;
+                if (p.mask) p.mask[int64_t(c) * G + g] = mk;
+                if (p.qscore) p.qscore[int64_t(c) * G + g] = bad ? nan("") : my_scc;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase D: integrate over the grid ---------------------------------------------------
+        const double sd_f = sqrt(fmax(p.noise * (1.0 - p.noise * inv_s), 0.0));
+        const int S = p.S;
+        double accA[MAX_S], accB[MAX_S];
+#pragma unroll
+        for (int s = 0; s < MAX_S; ++s) accA[s] = accB[s] = 0.0;
+        double scw = 0.0, snc = 0.0, nacc = 0.0;
+        for (int g = tid; g < G; g += SCORE_THREADS) {
+            double cw = g_cw[g], nc = g_nc[g], mf = g_mf[g];
+            scw += cw; snc += nc; nacc += (g_mk[g] >= 0.5) ? 1.0 : 0.0;
+            double em = 0.0;
+            if (p.kind == 0 && S > 1) {
+                for (int s = 0; s < S; ++s) em += p.eps_mc[int64_t(s) * G + g];
+                em /= double(S);
+            }
+#pragma unroll
+            for (int s = 0; s < MAX_S; ++s) {
+                if (s < S) {
+                    double e = p.eps_mc[int64_t(s) * G + g];
+                    double f = fma(sd_f, e, mf);
+                    double val;
+                    if (p.kind == 0) {
+                        if (S > 1) { double m = fma(sd_f, em, mf); val = m + p.beta_prime * fabs(f - m); }
+                        else val = f;
+                    } else {
+                        double x = f - p.best_f;
+                        if (p.temp > 0.0) { double xt = x / p.temp; val = p.temp * (fmax(xt, 0.0) + log1p(exp(-fabs(xt)))); }
+                        else val = fmax(x, 0.0);
+                    }
+                    accA[s] = fma(cw, val, accA[s]);
+                    accB[s] = fma(nc, val, accB[s]);
+                }
+            }
+        }
+        const int nred = 2 * MAX_S + 3;
+        scw = warp_sum(scw); snc = warp_sum(snc); nacc = warp_sum(nacc);
+        if (lane == 0) { red[warp * nred + 0] = scw; red[warp * nred + 1] = snc; red[warp * nred + 2] = nacc; }
+#pragma unroll
+        for (int s = 0; s < MAX_S; ++s) {
+            if (s < S) {
+                double A = warp_sum(accA[s]), B = warp_sum(accB[s]);
+                if (lane == 0) { red[warp * nred + 3 + 2 * s] = A; red[warp * nred + 4 + 2 * s] = B; }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double tcw = 0.0, tnc = 0.0, tna = 0.0;
+            for (int w = 0; w < SCORE_WARPS; ++w) { tcw += red[w * nred]; tnc += red[w * nred + 1]; tna += red[w * nred + 2]; }
+            double ood = SOFT ? sigmoid_acc((omega_c - p.alpha_lvl) * inv_temp) : ((omega_c >= p.alpha_lvl) ? 1.0 : 0.0);
+            double tot = 0.0;
+            for (int s = 0; s < S; ++s) {
+                double A = 0.0, B = 0.0;
+                for (int w = 0; w < SCORE_WARPS; ++w) { A += red[w * nred + 3 + 2 * s]; B += red[w * nred + 4 + 2 * s]; }
+                tot += (1.0 - ood) * ((1.0 - p.alpha_lvl) * A / fmax(tcw, 1e-6) + p.alpha_lvl * B / fmax(tnc, 1e-6));
+            }
+            p.acq[c] = tot / double(S);
+            if (p.ood) p.ood[c] = ood;
+            if (p.post_mean) p.post_mean[c] = mu;
+            if (p.post_var) p.post_var[c] = s_var;
+            if (p.num_acc) p.num_acc[c] = tna;
+        }
+        // g-arrays / red are rewritten only after the next candidate's phase-A barrier
+    }
+}
+
+}  // namespace cbo

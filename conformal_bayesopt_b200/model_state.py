@@ -1,0 +1,113 @@
+"""Plain-tensor hand-off of an exact GP to the kernels (SURVEY.md §8b "Model-state hand-off").
+
+The reference passes a BoTorch `SingleTaskGP` object into its acquisition classes
+(conformalbo/utils.py:382-390, 440-458); the kernels need, per output, the training inputs, the
+hyper-parameters, alpha = A^-1 (y - m) and the explicit inverse Cholesky factor L^-1 of
+A = K + noise I (the same quantity GPyTorch's `root_inv_decomposition` holds for the reference's
+fantasy update, App. B-4).  Built once per model fit with torch.linalg on the device (library
+calls, outside the per-candidate path).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+SQRT5 = math.sqrt(5.0)
+
+
+def matern52(x1: torch.Tensor, x2: torch.Tensor, lengthscale: torch.Tensor, outputscale: float) -> torch.Tensor:
+    """ScaleKernel(MaternKernel(nu=2.5, ARD)) -- BoTorch SingleTaskGP's default covariance (App. B-1)."""
+    a = x1 / lengthscale
+    b = x2 / lengthscale
+    r = torch.cdist(a, b, compute_mode="donot_use_mm_for_euclid_dist").clamp_min(1e-15)
+    return outputscale * (1.0 + SQRT5 * r + (5.0 / 3.0) * r * r) * torch.exp(-SQRT5 * r)
+
+
+@dataclass
+class GPModelState:
+    """One output's exact GP as device tensors (fp64), padded to Np = multiple of 128."""
+    X: torch.Tensor                # (N, d)
+    y: torch.Tensor                # (N,)
+    mean: float
+    lengthscale: torch.Tensor      # (d,)
+    outputscale: float
+    noise: float
+    alpha: torch.Tensor = field(repr=False, default=None)     # (Np,)
+    linv: torch.Tensor = field(repr=False, default=None)      # (Np, Np) lower
+    linv_t: torch.Tensor = field(repr=False, default=None)    # (Np, Np) upper
+    inv_lengthscale: torch.Tensor = field(repr=False, default=None)
+    L: Optional[torch.Tensor] = field(repr=False, default=None)   # (N, N) Cholesky factor (kept for diagnostics)
+
+    @property
+    def N(self) -> int:
+        return self.X.shape[0]
+
+    @property
+    def d(self) -> int:
+        return self.X.shape[1]
+
+    @property
+    def Np(self) -> int:
+        return self.alpha.shape[0]
+
+    @property
+    def device(self):
+        return self.X.device
+
+    @classmethod
+    def fit_fixed(cls, X, y, mean, lengthscale, outputscale, noise, device=None) -> "GPModelState":
+        """Build the state for FIXED hyper-parameters (hyper-parameter fitting is out of scope)."""
+        device = torch.device(device) if device is not None else X.device
+        X = X.to(device=device, dtype=torch.float64).contiguous()
+        y = y.to(device=device, dtype=torch.float64).reshape(-1).contiguous()
+        N, d = X.shape
+        ls = torch.as_tensor(lengthscale, dtype=torch.float64, device=device).reshape(-1)
+        if ls.numel() == 1:
+            ls = ls.expand(d)
+        ls = ls.contiguous()
+        K = matern52(X, X, ls, float(outputscale))
+        K.diagonal().fill_(float(outputscale))
+        A = K + float(noise) * torch.eye(N, dtype=torch.float64, device=device)
+        L = torch.linalg.cholesky(A)
+        alpha = torch.cholesky_solve((y - float(mean)).unsqueeze(-1), L).squeeze(-1)
+        linv = torch.linalg.solve_triangular(L, torch.eye(N, dtype=torch.float64, device=device), upper=False)
+        Np = (N + 127) // 128 * 128
+        linv_p = torch.zeros(Np, Np, dtype=torch.float64, device=device)
+        linv_p[:N, :N] = torch.tril(linv)
+        alpha_p = torch.zeros(Np, dtype=torch.float64, device=device)
+        alpha_p[:N] = alpha
+        return cls(X=X, y=y, mean=float(mean), lengthscale=ls, outputscale=float(outputscale), noise=float(noise),
+                   alpha=alpha_p, linv=linv_p, linv_t=linv_p.t().contiguous(), inv_lengthscale=(1.0 / ls).contiguous(),
+                   L=L)
+
+    @classmethod
+    def from_botorch(cls, model, output_index: int = 0) -> "GPModelState":
+        """Duck-typed extraction from a BoTorch 0.7 `SingleTaskGP`.  botorch is not needed
+        to import this module; the attributes below are the ones the reference itself reads."""
+        X = model.train_inputs[0]
+        y = model.train_targets
+        ls = model.covar_module.base_kernel.lengthscale
+        os_ = model.covar_module.outputscale
+        noise = model.likelihood.noise
+        mean = model.mean_module.constant
+        if X.ndim == 3:  # batched multi-output model: (t, N, d)
+            X, y = X[output_index], y[output_index]
+            ls, os_, noise, mean = ls[output_index], os_[output_index], noise[output_index], mean[output_index]
+        return cls.fit_fixed(X.detach(), y.detach(), float(torch.as_tensor(mean).reshape(-1)[0]),
+                             ls.detach().reshape(-1), float(torch.as_tensor(os_).reshape(-1)[0]),
+                             float(torch.as_tensor(noise).reshape(-1)[0]), device=X.device)
+
+    def c_struct(self) -> "_lib.GpF64":
+        return _lib.GpF64(self.N, self.d, self.Np, self.X.data_ptr(), self.alpha.data_ptr(), self.linv.data_ptr(),
+                          self.linv_t.data_ptr(), self.inv_lengthscale.data_ptr(), self.mean, self.outputscale,
+                          self.noise)
+
+    def to(self, device) -> "GPModelState":
+        device = torch.device(device)
+        kw = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in self.__dict__.items()}
+        return GPModelState(**kw)

@@ -1,0 +1,204 @@
+"""Thin functional layer over the C ABI: tensors in, tensors out, current CUDA stream.
+
+No arithmetic of the hot path happens in Python/torch here -- every call lands in libcbo.so.
+A CPU tensor is an error (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .model_state import GPModelState
+
+ACQ_KINDS = {"ucb": 0, "ei": 1}
+_WORKSPACES: Dict[tuple, torch.Tensor] = {}
+LAUNCH_COUNT = 0   # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+@dataclass
+class RatioWeights:
+    """Device copies of RatioEstimator._target_network weights (ratio_estimation.py:73-86)."""
+    W1: torch.Tensor
+    b1: torch.Tensor
+    W2: torch.Tensor
+    b2: torch.Tensor
+    W3: torch.Tensor
+    b3: torch.Tensor
+
+    @classmethod
+    def from_sequential(cls, net, device) -> "RatioWeights":
+        lin = [m for m in net if isinstance(m, torch.nn.Linear)]
+        assert len(lin) == 3, "RatioEstimator network is d->H->H->1"
+        f = lambda t: t.detach().to(device=device, dtype=torch.float64).contiguous()
+        return cls(f(lin[0].weight), f(lin[0].bias), f(lin[1].weight), f(lin[1].bias), f(lin[2].weight), f(lin[2].bias))
+
+    def c_struct(self) -> "_lib.RatioMlpF64":
+        return _lib.RatioMlpF64(self.W1.shape[0], self.W1.data_ptr(), self.b1.data_ptr(), self.W2.data_ptr(),
+                                self.b2.data_ptr(), self.W3.data_ptr(), self.b3.data_ptr())
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.CboError("libcbo has no CPU path: tensors must live on a CUDA device")
+
+
+def _f64(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else t.to(torch.float64).contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def make_params(*, alpha, temp, grid_res, q=1, num_mc=1, num_probes=8, max_grid_refinements=0, kind="ucb",
+                optimistic=True, randomized=False, eps_per_candidate=False, beta_prime=0.0, best_f=0.0) -> "_lib.Params":
+    return _lib.Params(float(alpha), float(temp), int(grid_res), int(q), int(num_mc), int(num_probes),
+                       int(max_grid_refinements), ACQ_KINDS[kind], int(bool(optimistic)), int(bool(randomized)),
+                       int(bool(eps_per_candidate)), float(beta_prime), float(best_f))
+
+
+def workspace(state: GPModelState, b: int, params, chunk: int = 0) -> torch.Tensor:
+    """Caller-owned scratch (torch caching allocator), cached per (device, size)."""
+    lib = _lib.load()
+    nbytes = lib.cbo_workspace_bytes(state.N, state.d, b, C.byref(params), chunk)
+    key = (state.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=state.device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def count_launches(state: GPModelState, b: int, params, ratio: bool, chunk: int = 0) -> int:
+    """Kernels one cbo_conformal_acq_f64 call enqueues (mirrors csrc/cbo_api.cu)."""
+    C_ = b if params.max_grid_refinements > 0 else min(b, chunk if chunk > 0 else 16384)
+    n_chunks = (b + C_ - 1) // C_
+    per_call = 5                                   # pad_probes, 2 x probe_matvec, ratio/fill, train_tables
+    per_chunk = 1 + (1 if ratio else 0) + 2 + 1    # rows, ratio(cand), 2 x gemm, score
+    return per_call + n_chunks * per_chunk
+
+
+def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tensor, z: torch.Tensor,
+                  eps_mc: torch.Tensor, u_rand: Optional[torch.Tensor] = None, ratio: Optional[RatioWeights] = None,
+                  outputs: Sequence[str] = (), chunk: int = 0, **param_kw) -> Dict[str, torch.Tensor]:
+    """cbo_conformal_acq_f64.  Xq (b, q=1, d) or (b, d).  Returns {'acq': (b,), + requested outputs}."""
+    global LAUNCH_COUNT
+    lib = _lib.load()
+    _require_cuda(Xq, eps_grid, z, eps_mc, u_rand, state.X)
+    if Xq.ndim == 3:
+        if Xq.shape[1] != 1:
+            raise _lib.CboError("unsupported shape: q > 1 is not built yet")
+        Xq = Xq[:, 0, :]
+    Xq, eps_grid, z, eps_mc, u_rand = map(_f64, (Xq, eps_grid, z, eps_mc, u_rand))
+    b, G = Xq.shape[0], int(param_kw["grid_res"])
+    eps_per_candidate = eps_grid.numel() == b * G and eps_grid.ndim >= 2 and eps_grid.shape[0] == b
+    num_mc = eps_mc.reshape(-1, G).shape[0]
+    params = make_params(num_mc=num_mc, num_probes=z.shape[-1], eps_per_candidate=eps_per_candidate, **param_kw)
+    if z.shape[0] != state.N + 1:
+        raise _lib.CboError(f"z must have N+q = {state.N + 1} rows, got {z.shape[0]}")
+    dev = Xq.device
+    out_t = {"acq": torch.empty(b, dtype=torch.float64, device=dev)}
+    per_g = {"target_grid", "grid_logp", "conf_pred_mask", "q_conf_scores"}
+    for name in outputs:
+        out_t[name] = torch.empty((b, G) if name in per_g else (b,), dtype=torch.float64, device=dev)
+    cout = _lib.OutputsF64(**{k: _ptr(v) for k, v in out_t.items()})
+    ws = workspace(state, b, params, chunk)
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    gp_c = state.c_struct()
+    ratio_c = ratio.c_struct() if ratio is not None else None
+    st = lib.cbo_conformal_acq_f64(C.byref(gp_c), C.byref(ratio_c) if ratio_c is not None else None, C.byref(params),
+                                   Xq.data_ptr(), b, eps_grid.data_ptr(), z.data_ptr(), eps_mc.data_ptr(),
+                                   _ptr(u_rand), C.byref(cout), ws_ptr, ws.numel() - 256, chunk, _stream())
+    _lib.check(st, "cbo_conformal_acq_f64")
+    LAUNCH_COUNT += count_launches(state, b, params, ratio is not None, chunk)
+    return out_t
+
+
+def conformal_acq_host(state: GPModelState, Xq_host: torch.Tensor, acq_host: torch.Tensor, *, eps_grid, z, eps_mc,
+                       u_rand=None, ratio: Optional[RatioWeights] = None, chunk: int = 0, staging=None, **param_kw):
+    """cbo_conformal_acq_host_f64: HOST (pinned) candidates in, HOST acquisition values out; H2D and D2H inside."""
+    global LAUNCH_COUNT
+    lib = _lib.load()
+    assert not Xq_host.is_cuda and not acq_host.is_cuda
+    Xq_host = Xq_host.reshape(Xq_host.shape[0], -1)
+    b, G = Xq_host.shape[0], int(param_kw["grid_res"])
+    num_mc = eps_mc.reshape(-1, G).shape[0]
+    params = make_params(num_mc=num_mc, num_probes=z.shape[-1], **param_kw)
+    dev = state.device
+    if staging is None:
+        staging = (torch.empty(b, state.d, dtype=torch.float64, device=dev), torch.empty(b, dtype=torch.float64, device=dev))
+    ws = workspace(state, b, params, chunk)
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    gp_c = state.c_struct()
+    ratio_c = ratio.c_struct() if ratio is not None else None
+    st = lib.cbo_conformal_acq_host_f64(C.byref(gp_c), C.byref(ratio_c) if ratio_c is not None else None,
+                                        C.byref(params), Xq_host.data_ptr(), b, eps_grid.data_ptr(), z.data_ptr(),
+                                        eps_mc.data_ptr(), _ptr(u_rand), acq_host.data_ptr(), staging[0].data_ptr(),
+                                        staging[1].data_ptr(), ws_ptr, ws.numel() - 256, chunk, _stream())
+    _lib.check(st, "cbo_conformal_acq_host_f64")
+    LAUNCH_COUNT += count_launches(state, b, params, ratio is not None, chunk)
+    return acq_host
+
+
+def conf_mask_to_bounds(target_grid: torch.Tensor, conf_pred_mask: torch.Tensor):
+    """conf_mask_to_bounds (helpers.py:15-91): (b, G, 1, t) x2 -> lb, ub (b, 1, t)."""
+    lib = _lib.load()
+    _require_cuda(target_grid, conf_pred_mask)
+    assert target_grid.shape == conf_pred_mask.shape and target_grid.shape[-2] == 1, "q = 1 only (helpers.py:35-37)"
+    b, G, _, t = target_grid.shape
+    grid = _f64(target_grid.reshape(b, G, t))
+    mask = _f64(conf_pred_mask.reshape(b, G, t))
+    lb = torch.empty(b, t, dtype=torch.float64, device=grid.device)
+    ub = torch.empty_like(lb)
+    st = lib.cbo_conf_mask_to_bounds_f64(grid.data_ptr(), mask.data_ptr(), b, G, t, lb.data_ptr(), ub.data_ptr(), _stream())
+    _lib.check(st, "cbo_conf_mask_to_bounds_f64")
+    return lb.unsqueeze(1), ub.unsqueeze(1)
+
+
+def ratio_forward(ratio: RatioWeights, x: torch.Tensor) -> torch.Tensor:
+    """RatioEstimator.forward (ratio_estimation.py:97-99) on (..., d) points."""
+    lib = _lib.load()
+    _require_cuda(x)
+    shape = x.shape[:-1]
+    x2 = _f64(x.reshape(-1, x.shape[-1]))
+    out = torch.empty(x2.shape[0], dtype=torch.float64, device=x.device)
+    rc = ratio.c_struct()
+    st = lib.cbo_ratio_forward_f64(C.byref(rc), x2.data_ptr(), x2.shape[0], x2.shape[1], out.data_ptr(), _stream())
+    _lib.check(st, "cbo_ratio_forward_f64")
+    return out.reshape(shape)
+
+
+def gemm_tn(A: torch.Tensor, B: torch.Tensor, tri: int = 0, rownorm: bool = False):
+    """C = A @ B^T restricted to the triangular K-range (test / profiling hook for the DMMA kernel)."""
+    lib = _lib.load()
+    _require_cuda(A, B)
+    M, K = A.shape
+    Nn = B.shape[0]
+    Cm = torch.empty(M, Nn, dtype=torch.float64, device=A.device)
+    rn = torch.empty(M, Nn // 128, dtype=torch.float64, device=A.device) if rownorm else None
+    st = lib.cbo_gemm_tn_f64(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cm.data_ptr(), Cm.stride(0), M, Nn, K,
+                             tri, _ptr(rn), _stream())
+    _lib.check(st, "cbo_gemm_tn_f64")
+    return (Cm, rn) if rownorm else Cm
+
+
+def kernel_rows(state: GPModelState, Xq: torch.Tensor):
+    lib = _lib.load()
+    _require_cuda(Xq)
+    Xq = _f64(Xq.reshape(-1, state.d))
+    n = Xq.shape[0]
+    U = torch.empty(n, state.Np, dtype=torch.float64, device=Xq.device)
+    mu = torch.empty(n, dtype=torch.float64, device=Xq.device)
+    gp_c = state.c_struct()
+    st = lib.cbo_kernel_rows_f64(C.byref(gp_c), Xq.data_ptr(), n, U.data_ptr(), mu.data_ptr(), _stream())
+    _lib.check(st, "cbo_kernel_rows_f64")
+    return U, mu

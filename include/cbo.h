@@ -1,0 +1,158 @@
+/*
+ * cbo.h -- C ABI of libcbo: the B200-native full-conformal acquisition hot path.
+ *
+ * The reference (samuelstanton/conformal-bayesopt) is pure Python and has no FFI; these entry
+ * points are what a binding for this path replaces (file:line in the reference tree):
+ *
+ *   cbo_conformal_acq_f64      ConformalAcquisition._conformal_fwd + forward
+ *                              (conformalbo/acquisitions.py:53-76), i.e. fused
+ *                              construct_conformal_bands (conformalbo/helpers.py:94-202),
+ *                              conformal_gp_regression (helpers.py:218-333),
+ *                              est_train_post_var (helpers.py:390-412),
+ *                              RatioEstimator.forward (conformalbo/ratio_estimation.py:97-99),
+ *                              _nonconformal_fwd of cUCB / cEI (acquisitions.py:151-159, 88-98)
+ *                              and _conformal_integration (acquisitions.py:225-248).
+ *   cbo_conf_mask_to_bounds_f64  conf_mask_to_bounds (helpers.py:15-91).
+ *   cbo_ratio_forward_f64      RatioEstimator.forward (ratio_estimation.py:97-99).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer; the library allocates no device memory, ever;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); the only host
+ *     synchronisation is one per grid-refinement pass when max_grid_refinements > 0 (the
+ *     reference synchronises there too, helpers.py:151-152,177);
+ *   - every entry point returns a cbo_status (0 = ok); no C++ exception crosses the ABI;
+ *   - NaN inputs propagate to NaN outputs (no validation on device);
+ *   - re-entrant for distinct workspaces; the model arrays are read-only.
+ *
+ * Randomness of the reference is injected: eps_grid (grid sampler base
+ * samples), z (Hutchinson probes, +-1), eps_mc (acquisition sampler base samples), u_rand
+ * (uniforms behind Bernoulli.sample()).
+ */
+#ifndef CBO_H_
+#define CBO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBO_VERSION 100
+
+typedef enum {
+    CBO_OK = 0,
+    CBO_ERR_INVALID_ARG = 1,     /* null pointer / non-positive size / bad enum */
+    CBO_ERR_UNSUPPORTED = 2,     /* shape outside what the kernels cover (see cbo_limits) */
+    CBO_ERR_WORKSPACE = 3,       /* workspace too small or misaligned */
+    CBO_ERR_CUDA = 4,            /* a CUDA runtime call / launch failed (cbo_last_cuda_error) */
+    CBO_ERR_NO_DEVICE = 5        /* no sm_100 device visible */
+} cbo_status;
+
+typedef enum { CBO_ACQ_UCB = 0, CBO_ACQ_EI = 1 } cbo_acq_kind;
+
+/* One output's exact GP, prepared once per model fit (all device pointers, fp64, row-major).
+ * Np = cbo_padded_n(N) (N rounded up to a multiple of 128); rows/cols >= N are zero. */
+typedef struct {
+    int64_t N;                 /* training points */
+    int64_t d;                 /* input dimension (<= 64) */
+    int64_t Np;                /* padded N: leading dimension of linv / linv_t */
+    const double* X;           /* N x d training inputs                              */
+    const double* alpha;       /* Np    A^{-1}(y - mean), A = K + noise I            */
+    const double* linv;        /* Np x Np  explicit inverse of chol(A), lower        */
+    const double* linv_t;      /* Np x Np  its transpose (upper)                     */
+    const double* inv_lengthscale; /* d   1 / ARD lengthscale                        */
+    double mean;               /* constant prior mean                                */
+    double outputscale;        /* Matern-5/2 output scale                            */
+    double noise;              /* homoskedastic noise variance                       */
+} cbo_gp_f64;
+
+/* RatioEstimator target network d -> H -> ReLU -> H -> ReLU -> 1 (torch nn.Linear layout:
+ * weight[out][in]).  Pass NULL for "no ratio estimator" (unit importance weights). */
+typedef struct {
+    int64_t hidden;            /* H <= 64 */
+    const double* W1; const double* b1;   /* H x d, H */
+    const double* W2; const double* b2;   /* H x H, H */
+    const double* W3; const double* b3;   /* 1 x H, 1 */
+} cbo_ratio_mlp_f64;
+
+typedef struct {
+    double alpha;              /* miscoverage level                         (acquisitions.py:32) */
+    double temp;               /* sigmoid temperature; <= 0 selects the hard path (helpers.py:277,316) */
+    int64_t grid_res;          /* G >= 2                                    (helpers.py:113) */
+    int64_t q;                 /* joint batch size (this build: 1)          */
+    int64_t num_mc;            /* S, MC samples of the acquisition sampler  */
+    int64_t num_probes;        /* S_p Hutchinson probes (reference: 8; <= 16) (helpers.py:390) */
+    int64_t max_grid_refinements;  /*                                       (helpers.py:129) */
+    int32_t kind;              /* cbo_acq_kind */
+    int32_t optimistic;        /* opt_mask = [y_g >= mu]                    (acquisitions.py:57-62) */
+    int32_t randomized;        /* randomised tie-break, needs u_rand        (helpers.py:306-312) */
+    int32_t eps_per_candidate; /* 0: eps_grid is (G) shared (collapse_batch_dims), 1: (b x G) */
+    double beta_prime;         /* cUCB: sqrt(beta*pi/2)                     */
+    double best_f;             /* cEI incumbent                             */
+} cbo_params;
+
+/* Any pointer may be NULL (that output is skipped) except acq. */
+typedef struct {
+    double* acq;               /* b       acquisition value                                  */
+    double* target_grid;       /* b x G   y_g                                                */
+    double* grid_logp;         /* b x G   log N(y_g; mu, c s)                                */
+    double* conf_pred_mask;    /* b x G   conformal (soft) mask                              */
+    double* ood_mask;          /* b       sigma((omega_c - alpha)/temp)                      */
+    double* q_conf_scores;     /* b x G   candidate's own conformal score                    */
+    double* post_mean;         /* b       mu(x)                                              */
+    double* post_var;          /* b       s(x) = noisy predictive variance                   */
+    double* num_accepted;      /* b       #{g : mask >= 0.5}                                 */
+} cbo_outputs_f64;
+
+int cbo_version(void);
+const char* cbo_status_str(int status);
+const char* cbo_last_cuda_error(void);
+int64_t cbo_padded_n(int64_t N);
+
+/* Bytes of workspace cbo_conformal_acq_f64 needs for b candidates (chunked internally when
+ * max_grid_refinements == 0; `chunk` <= 0 selects the default chunk).  256-byte aligned. */
+size_t cbo_workspace_bytes(int64_t N, int64_t d, int64_t b, const cbo_params* params, int64_t chunk);
+
+/* The hot path.  Xq: b x q x d candidates; eps_grid: G (or b x G); z: (N+q) x S_p of +-1;
+ * eps_mc: S x G; u_rand: b x G or NULL; chunk: candidates per internal pass (<= 0: default). */
+int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* params,
+                          const double* Xq, int64_t b, const double* eps_grid, const double* z,
+                          const double* eps_mc, const double* u_rand, const cbo_outputs_f64* out,
+                          void* workspace, size_t workspace_bytes, int64_t chunk, void* stream);
+
+/* Same call with HOST candidate / result buffers (pinned for full speed): H2D of Xq_host and
+ * D2H of acq_host are issued on `stream` inside the call; synchronises the stream on return. */
+int cbo_conformal_acq_host_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* params,
+                               const double* Xq_host, int64_t b, const double* eps_grid, const double* z,
+                               const double* eps_mc, const double* u_rand, double* acq_host,
+                               double* Xq_staging /* b x q x d device */, double* acq_staging /* b device */,
+                               void* workspace, size_t workspace_bytes, int64_t chunk, void* stream);
+
+/* conf_mask_to_bounds: grid, mask: b x G x t (q = 1 squeezed) -> lb, ub: b x t.  G <= 2048. */
+int cbo_conf_mask_to_bounds_f64(const double* target_grid, const double* conf_pred_mask, int64_t b, int64_t G,
+                                int64_t t, double* lb, double* ub, void* stream);
+
+/* RatioEstimator.forward on n points (n x d) -> n density ratios (unclamped below, as the reference). */
+int cbo_ratio_forward_f64(const cbo_ratio_mlp_f64* ratio, const double* x, int64_t n, int64_t d, double* out,
+                          void* stream);
+
+/* Building blocks exported for tests and profiling (same kernels the hot path launches). */
+/* C[m, n] = sum_k A[m, k] * B[n, k] over the K-range implied by tri: 0 full, 1 lower (k < n-tile end),
+ * 2 upper (k >= n-tile begin).  A: M x K (lda), B: Nn x K (ldb), C: M x Nn (ldc); K, Nn multiples of 128.
+ * rownorm_partial (M x Nn/128) receives per-tile sums of squares of C when non-NULL. */
+int cbo_gemm_tn_f64(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                    int64_t M, int64_t Nn, int64_t K, int32_t tri, double* rownorm_partial, void* stream);
+/* U[c, i] = k(x_c, X_i) (Np-padded rows, zeros beyond N); mu[c] = mean + u.alpha. */
+int cbo_kernel_rows_f64(const cbo_gp_f64* gp, const double* Xq, int64_t n, double* U, double* mu, void* stream);
+
+/* Optional per-kernel-class timing with CUDA events on the caller's stream (bench.py's roofline leg).
+ * Classes: 0 per-call tables, 1 kernel rows (+candidate ratio MLP), 2 GEMM pass 1, 3 GEMM pass 2, 4 score. */
+void cbo_timing_enable(int on);
+int cbo_timing_collect(double* ms_out /* 5 */, int64_t* launches_out /* 5 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBO_H_ */
