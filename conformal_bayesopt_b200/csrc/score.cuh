@@ -9,7 +9,7 @@
 //                            -> shared memory tables  ww = noise w_i, iv = 1/(2 var_i), lv = -log(var_i)/2 - log(2pi)/2
 //   phase B  (warp per 8 grid points) for every train point: residual, score, hard count,
 //                            soft rank sigmoid, weighted sums (A-3, A-5) -- the hot loop,
-//                            ~18 fp64-pipe instructions per (train point, grid point)
+//                            16 fp64-pipe instructions per (train point, grid point), 8 independent chains per lane
 //   phase C  (lane per grid point) weighted mass, randomised step, conformal mask, log-density,
 //                            optimistic mask, refit mean (A-5, A-6)
 //   phase D  (block reduce over the grid) importance-weighted integration (A-7)
@@ -19,7 +19,7 @@
 
 namespace cbo {
 
-constexpr int SCORE_THREADS = 256;
+constexpr int SCORE_THREADS = 128;
 constexpr int SCORE_WARPS = SCORE_THREADS / 32;
 constexpr int SCORE_GPW = 8;           // grid points per warp pass
 constexpr int MAX_S = 16;
@@ -53,8 +53,8 @@ struct ScoreArgs {
 };
 
 __host__ __device__ inline size_t score_smem_bytes(int Np, int G) {
-    // tab[64] | a, dr, ww, iv, lv [Np each] | g-arrays cw, nc, mf, mk [G each] | red[SCORE_WARPS * (2*MAX_S+3)] | zb[Np] u32
-    return sizeof(double) * (64 + 5 * size_t(Np) + 4 * size_t(G) + SCORE_WARPS * (2 * MAX_S + 3)) +
+    // tab[16] | a, dr, ap, wp, lv [Np each] | g-arrays cw, nc, mf, mk [G each] | red[SCORE_WARPS * (2*MAX_S+3)] | zb[Np] u32
+    return sizeof(double) * (16 + 5 * size_t(Np) + 4 * size_t(G) + SCORE_WARPS * (2 * MAX_S + 3)) +
            sizeof(uint32_t) * size_t(Np);
 }
 
@@ -62,12 +62,12 @@ template <bool SOFT>
 __global__ void __launch_bounds__(SCORE_THREADS)
 k_score(const ScoreArgs p) {
     extern __shared__ __align__(16) double sm[];
-    double* tab = sm;
-    double* sa = tab + 64;
-    double* sdr = sa + p.Np;
-    double* sww = sdr + p.Np;
-    double* siv = sww + p.Np;
-    double* slv = siv + p.Np;
+    double* tab = sm;                 // 2^(j/16), j < 16: one shared-memory row, conflict-free for any index pattern
+    double* sa = tab + 16;            // noise * alpha_i                       (per model)
+    double* sdr = sa + p.Np;          // density ratio of train point i        (per model)
+    double* sap = sdr + p.Np;         // noise * alpha_i * sqrt(iv_i)          (per candidate)
+    double* swp = sap + p.Np;         // noise * w_i * sqrt(iv_i)              (per candidate)
+    double* slv = swp + p.Np;         // -log(var_i)/2 - log(2 pi)/2           (per candidate)
     double* g_cw = slv + p.Np;
     double* g_nc = g_cw + p.G;
     double* g_mf = g_nc + p.G;
@@ -79,7 +79,7 @@ k_score(const ScoreArgs p) {
     const int N = p.N, G = p.G, Sp = p.Sp;
 
     // ---- once per CTA: candidate-independent tables -------------------------------------------
-    if (tid < 64) tab[tid] = exp2(double(tid) / 64.0);
+    if (tid < 16) tab[tid] = exp2(double(tid) / 16.0);
     for (int i = tid; i < N; i += SCORE_THREADS) {
         sa[i] = p.a[i];
         sdr[i] = p.dr[i];
@@ -118,8 +118,9 @@ k_score(const ScoreArgs p) {
                 if (s < Sp) zdot += ((bits >> s) & 1u) ? cs[s] : -cs[s];
             double var = p.noise * fma(kvar * w, zdot, p.h0[i]);
             bad |= !(var > 0.0);
-            sww[i] = p.noise * w;
-            siv[i] = 0.5 / var;
+            double siv = sqrt(0.5 / var);                                // r' = r * sqrt(iv): r'^2 = r^2 / (2 var)
+            sap[i] = sa[i] * siv;
+            swp[i] = p.noise * w * siv;
             slv[i] = -0.5 * log(var) - 0.5 * kLog2Pi;
         }
         bad = __syncthreads_or(bad);
@@ -146,22 +147,79 @@ k_score(const ScoreArgs p) {
                 sr[k] = 0.0; sw[k] = 0.0; cnt[k] = 0;
             }
             if (!bad) {
-                for (int i = lane; i < N; i += 32) {
-                    const double a = sa[i], ww = sww[i], iv = siv[i], lv = slv[i], dr = sdr[i];
+                // Soft rank: rho = sigmoid(dd / temp), dd = score_c - score_i.  With u = |dd| and c1 = 16/(temp ln2):
+                //   e = exp(-u/temp) = 2^(-m/16) * exp(y' ln2/16),  m = round(u c1),  y' = m - u c1 in [-1/2, 1/2]
+                // (16-entry table + near-minimax cubic, rel. err 1.2e-9), rho = (dd >= 0 ? 1 : e) / (1 + e) with a
+                // MUFU.RCP64H seed and one Newton step.  |dd|/temp >= 41 saturates to exactly 0 / 1.
+                constexpr double kMagic = 6755399441055744.0;             // 1.5 * 2^52
+                constexpr double kC0 = 0.9999999988534117, kC1 = 0.043321698775061875,
+                                 kC2 = 0.0009384214835622084, kC3 = 1.3551125681305332e-05;
+                const double c1 = inv_temp * 23.083120654223414;          // 16 / ln 2
+                const int sat_hi = __double2hiint(41.0 * p.temp);
+                for (int i0 = 0; i0 < N; i0 += 32) {                     // warp-uniform trip count (vote inside)
+                    const int i = i0 + lane;
+                    const bool valid = i < N;
+                    // a lane past the end scores -1e300: never counted, saturated to rho = 0
+                    const double ap = valid ? sap[i] : 0.0, wp = valid ? swp[i] : 0.0, lv = valid ? slv[i] : 1e300,
+                                 dr = valid ? sdr[i] : 0.0;
+                    double dd[SCORE_GPW];
+                    int hi[SCORE_GPW];
 #pragma unroll
                     for (int k = 0; k < SCORE_GPW; ++k) {
-                        double r = fma(-ww, bg[k], a);
-                        double sc = fma(-(r * r), iv, lv);
-                        double dd = scc[k] - sc;
-                        bool ge = dd >= 0.0;
-                        cnt[k] += ge ? 1 : 0;
-                        if (SOFT) {
-                            double rho = fast_sigmoid(dd * inv_temp, tab);
-                            sr[k] += rho;
-                            sw[k] = fma(rho, dr, sw[k]);
+                        double rp = fma(-wp, bg[k], ap);
+                        dd[k] = fma(rp, rp, scc[k] - lv);                 // score_c - score_i
+                        hi[k] = __double2hiint(dd[k]);
+                        cnt[k] += (hi[k] >= 0) ? 1 : 0;
+                    }
+                    if (SOFT) {
+                        int allsat = 1;
+#pragma unroll
+                        for (int k = 0; k < SCORE_GPW; ++k) allsat &= ((hi[k] & 0x7fffffff) >= sat_hi) ? 1 : 0;
+                        if (__all_sync(0xffffffffu, allsat)) {
+#pragma unroll
+                            for (int k = 0; k < SCORE_GPW; ++k) {
+                                bool ge = hi[k] >= 0;
+                                sr[k] += ge ? 1.0 : 0.0;
+                                sw[k] += ge ? dr : 0.0;
+                            }
                         } else {
-                            sw[k] += ge ? dr : 0.0;
+                            double t[SCORE_GPW], y[SCORE_GPW], e[SCORE_GPW];
+#pragma unroll
+                            for (int k = 0; k < SCORE_GPW; ++k) {
+                                double u = __hiloint2double(hi[k] & 0x7fffffff, __double2loint(dd[k]));
+                                t[k] = fma(u, c1, kMagic);                // integer m in the low word
+                                y[k] = fma(-u, c1, t[k] - kMagic);        // m - u c1
+                            }
+#pragma unroll
+                            for (int k = 0; k < SCORE_GPW; ++k) {
+                                double pl = fma(y[k], kC3, kC2);
+                                pl = fma(pl, y[k], kC1);
+                                pl = fma(pl, y[k], kC0);
+                                int m = __double2loint(t[k]);
+                                double tj = tab[(-m) & 15];               // 2^(((-m) mod 16)/16)
+                                double ev = tj * pl;
+                                int kk = (-m - ((-m) & 15)) >> 4;         // -m = 16 kk + j  ->  2^(-m/16) = 2^kk 2^(j/16)
+                                int eh = __double2hiint(ev) + (kk << 20);
+                                bool sat = (hi[k] & 0x7fffffff) >= sat_hi;
+                                e[k] = __hiloint2double(sat ? 0 : eh, sat ? 0 : __double2loint(ev));
+                            }
+#pragma unroll
+                            for (int k = 0; k < SCORE_GPW; ++k) {
+                                double d = 1.0 + e[k];
+                                double y0;
+                                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+                                double err = fma(-d, y0, 1.0);
+                                bool ge = hi[k] >= 0;
+                                double num = __hiloint2double(ge ? 0x3ff00000 : __double2hiint(e[k]), ge ? 0 : __double2loint(e[k]));
+                                double t1 = num * y0;
+                                double rho = fma(t1, err, t1);
+                                sr[k] += rho;
+                                sw[k] = fma(rho, dr, sw[k]);
+                            }
                         }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < SCORE_GPW; ++k) sw[k] += (hi[k] >= 0) ? dr : 0.0;
                     }
                 }
             }
