@@ -65,10 +65,11 @@ k_score(const ScoreArgs p) {
     double* tab = sm;                 // 2^(j/16), j < 16: one shared-memory row, conflict-free for any index pattern
     double* sa = tab + 16;            // noise * alpha_i                       (per model)
     double* sdr = sa + p.Np;          // density ratio of train point i        (per model)
-    double* sap = sdr + p.Np;         // noise * alpha_i * sqrt(iv_i)          (per candidate)
-    double* swp = sap + p.Np;         // noise * w_i * sqrt(iv_i)              (per candidate)
-    double* slv = swp + p.Np;         // -log(var_i)/2 - log(2 pi)/2           (per candidate)
-    double* g_cw = slv + p.Np;
+    // per candidate: x_i(g) = c1 (score_c(g) - score_i(g)) = (qa_i b_g + qb_i) b_g + qc_i   (quadratic in b_g)
+    double* sqa = sdr + p.Np;
+    double* sqb = sqa + p.Np;
+    double* sqc = sqb + p.Np;
+    double* g_cw = sqc + p.Np;
     double* g_nc = g_cw + p.G;
     double* g_mf = g_nc + p.G;
     double* g_mk = g_mf + p.G;
@@ -88,6 +89,7 @@ k_score(const ScoreArgs p) {
     const double sum_dr = p.sum_dr[0];
     const double kvar = p.noise / (double(Sp) + 1e-6);
     const double inv_temp = SOFT ? 1.0 / p.temp : 0.0;
+    const double c1 = SOFT ? inv_temp * 23.083120654223414 : 1.0;        // 16 / (temp ln 2): exp(-|dd|/temp) = 2^(-|x|/16)
     double zc[MAX_SP];
 #pragma unroll
     for (int s = 0; s < MAX_SP; ++s) zc[s] = (s < Sp) ? p.z_cand[s] : 0.0;
@@ -108,6 +110,10 @@ k_score(const ScoreArgs p) {
         }
         const double var_c = p.noise * (1.0 + (double(Sp) - p.noise * zcc) / (double(Sp) + 1e-6));
         int bad = !(var_c > 0.0) || !(s_var > 0.0);
+        const double iv_c = 0.5 / var_c;
+        const double lv_c = -0.5 * log(var_c) - 0.5 * kLog2Pi;
+        // score_c(g) = lv_c - iv_c (noise b_g)^2 ;  score_i(g) = lv_i - iv_i (a_i - noise w_i b_g)^2
+        const double qa_c = -iv_c * p.noise * p.noise;
         const double* Wc = p.W + int64_t(c) * p.Np;
         for (int i = tid; i < N; i += SCORE_THREADS) {
             double w = Wc[i];
@@ -118,14 +124,14 @@ k_score(const ScoreArgs p) {
                 if (s < Sp) zdot += ((bits >> s) & 1u) ? cs[s] : -cs[s];
             double var = p.noise * fma(kvar * w, zdot, p.h0[i]);
             bad |= !(var > 0.0);
-            double siv = sqrt(0.5 / var);                                // r' = r * sqrt(iv): r'^2 = r^2 / (2 var)
-            sap[i] = sa[i] * siv;
-            swp[i] = p.noise * w * siv;
-            slv[i] = -0.5 * log(var) - 0.5 * kLog2Pi;
+            double iv = 0.5 / var;
+            double lv = -0.5 * log(var) - 0.5 * kLog2Pi;
+            double ai = sa[i], wi = p.noise * w;
+            sqa[i] = c1 * fma(iv * wi, wi, qa_c);                        // b_g^2 coefficient
+            sqb[i] = c1 * (-2.0 * iv * ai * wi);                         // b_g coefficient
+            sqc[i] = c1 * (fma(iv * ai, ai, lv_c - lv));                 // constant
         }
         bad = __syncthreads_or(bad);
-        const double iv_c = 0.5 / var_c;
-        const double lv_c = -0.5 * log(var_c) - 0.5 * kLog2Pi;
         const double cscale = p.cscale ? p.cscale[c] : 1.0;
         const double gsd = sqrt(cscale * s_var);                        // sd of the grid distribution
         const double drc = p.drc ? p.drc[c] : 1.0;
@@ -147,79 +153,60 @@ k_score(const ScoreArgs p) {
                 sr[k] = 0.0; sw[k] = 0.0; cnt[k] = 0;
             }
             if (!bad) {
-                // Soft rank: rho = sigmoid(dd / temp), dd = score_c - score_i.  With u = |dd| and c1 = 16/(temp ln2):
-                //   e = exp(-u/temp) = 2^(-m/16) * exp(y' ln2/16),  m = round(u c1),  y' = m - u c1 in [-1/2, 1/2]
-                // (16-entry table + near-minimax cubic, rel. err 1.2e-9), rho = (dd >= 0 ? 1 : e) / (1 + e) with a
-                // MUFU.RCP64H seed and one Newton step.  |dd|/temp >= 41 saturates to exactly 0 / 1.
+                // Soft rank: rho = sigmoid(dd / temp) = 1 / (1 + e),  e = exp(-dd/temp) = 2^(-x/16),  x = c1 dd,
+                // c1 = 16 / (temp ln 2).  With n = -round(x) = 16 kk + j:  e = 2^kk * tab[j] * P(x - round(x)),
+                // P(y) ~ exp(-y ln2/16) on [-1/2, 1/2] (16-entry table + near-minimax cubic, rel. err 1.2e-9);
+                // 1/(1+e) from a MUFU.RCP64H seed and one Newton step.  14 fp64-pipe instructions per
+                // (train point, grid point).  |x| is clamped at 946 = 41 * 16/ln2 in the integer domain
+                // (rho is 0 or 1 to 2e-18 beyond that).
                 constexpr double kMagic = 6755399441055744.0;             // 1.5 * 2^52
                 constexpr double kC0 = 0.9999999988534117, kC1 = 0.043321698775061875,
                                  kC2 = 0.0009384214835622084, kC3 = 1.3551125681305332e-05;
-                const double c1 = inv_temp * 23.083120654223414;          // 16 / ln 2
-                const int sat_hi = __double2hiint(41.0 * p.temp);
-                for (int i0 = 0; i0 < N; i0 += 32) {                     // warp-uniform trip count (vote inside)
+                constexpr int kSatHi = 0x408d9000;                        // hiword(946.0)
+                for (int i0 = 0; i0 < N; i0 += 32) {
                     const int i = i0 + lane;
                     const bool valid = i < N;
-                    // a lane past the end scores -1e300: never counted, saturated to rho = 0
-                    const double ap = valid ? sap[i] : 0.0, wp = valid ? swp[i] : 0.0, lv = valid ? slv[i] : 1e300,
+                    // a lane past the end has x = -1e300: never counted, rho ~ 1e-18 weighted by dr = 0
+                    const double qa = valid ? sqa[i] : 0.0, qb = valid ? sqb[i] : 0.0, qc = valid ? sqc[i] : -1e300,
                                  dr = valid ? sdr[i] : 0.0;
-                    double dd[SCORE_GPW];
-                    int hi[SCORE_GPW];
+                    double x[SCORE_GPW];
 #pragma unroll
                     for (int k = 0; k < SCORE_GPW; ++k) {
-                        double rp = fma(-wp, bg[k], ap);
-                        dd[k] = fma(rp, rp, scc[k] - lv);                 // score_c - score_i
-                        hi[k] = __double2hiint(dd[k]);
-                        cnt[k] += (hi[k] >= 0) ? 1 : 0;
+                        x[k] = fma(fma(qa, bg[k], qb), bg[k], qc);
+                        cnt[k] += (__double2hiint(x[k]) >= 0) ? 1 : 0;
                     }
                     if (SOFT) {
-                        int allsat = 1;
+                        double t[SCORE_GPW], yn[SCORE_GPW], e[SCORE_GPW];
 #pragma unroll
-                        for (int k = 0; k < SCORE_GPW; ++k) allsat &= ((hi[k] & 0x7fffffff) >= sat_hi) ? 1 : 0;
-                        if (__all_sync(0xffffffffu, allsat)) {
+                        for (int k = 0; k < SCORE_GPW; ++k) {
+                            int hi = __double2hiint(x[k]);
+                            int ch = min(hi & 0x7fffffff, kSatHi) | (hi & 0x80000000);
+                            double xc = __hiloint2double(ch, __double2loint(x[k]));         // clamp(x, -946, 946)
+                            t[k] = kMagic - xc;                           // low word = -round(x)
+                            yn[k] = xc + (t[k] - kMagic);                 // x - round(x) in [-1/2, 1/2]
+                        }
 #pragma unroll
-                            for (int k = 0; k < SCORE_GPW; ++k) {
-                                bool ge = hi[k] >= 0;
-                                sr[k] += ge ? 1.0 : 0.0;
-                                sw[k] += ge ? dr : 0.0;
-                            }
-                        } else {
-                            double t[SCORE_GPW], y[SCORE_GPW], e[SCORE_GPW];
+                        for (int k = 0; k < SCORE_GPW; ++k) {
+                            double pl = fma(yn[k], -kC3, kC2);
+                            pl = fma(pl, yn[k], -kC1);
+                            pl = fma(pl, yn[k], kC0);                     // exp(-yn ln2/16)
+                            int n = __double2loint(t[k]);
+                            double ev = tab[n & 15] * pl;
+                            e[k] = __hiloint2double(__double2hiint(ev) + ((n << 16) & 0xfff00000), __double2loint(ev));
+                        }
 #pragma unroll
-                            for (int k = 0; k < SCORE_GPW; ++k) {
-                                double u = __hiloint2double(hi[k] & 0x7fffffff, __double2loint(dd[k]));
-                                t[k] = fma(u, c1, kMagic);                // integer m in the low word
-                                y[k] = fma(-u, c1, t[k] - kMagic);        // m - u c1
-                            }
-#pragma unroll
-                            for (int k = 0; k < SCORE_GPW; ++k) {
-                                double pl = fma(y[k], kC3, kC2);
-                                pl = fma(pl, y[k], kC1);
-                                pl = fma(pl, y[k], kC0);
-                                int m = __double2loint(t[k]);
-                                double tj = tab[(-m) & 15];               // 2^(((-m) mod 16)/16)
-                                double ev = tj * pl;
-                                int kk = (-m - ((-m) & 15)) >> 4;         // -m = 16 kk + j  ->  2^(-m/16) = 2^kk 2^(j/16)
-                                int eh = __double2hiint(ev) + (kk << 20);
-                                bool sat = (hi[k] & 0x7fffffff) >= sat_hi;
-                                e[k] = __hiloint2double(sat ? 0 : eh, sat ? 0 : __double2loint(ev));
-                            }
-#pragma unroll
-                            for (int k = 0; k < SCORE_GPW; ++k) {
-                                double d = 1.0 + e[k];
-                                double y0;
-                                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
-                                double err = fma(-d, y0, 1.0);
-                                bool ge = hi[k] >= 0;
-                                double num = __hiloint2double(ge ? 0x3ff00000 : __double2hiint(e[k]), ge ? 0 : __double2loint(e[k]));
-                                double t1 = num * y0;
-                                double rho = fma(t1, err, t1);
-                                sr[k] += rho;
-                                sw[k] = fma(rho, dr, sw[k]);
-                            }
+                        for (int k = 0; k < SCORE_GPW; ++k) {
+                            double d = 1.0 + e[k];
+                            double y0;
+                            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+                            double err = fma(-d, y0, 1.0);
+                            double rho = fma(y0, err, y0);
+                            sr[k] += rho;
+                            sw[k] = fma(rho, dr, sw[k]);
                         }
                     } else {
 #pragma unroll
-                        for (int k = 0; k < SCORE_GPW; ++k) sw[k] += (hi[k] >= 0) ? dr : 0.0;
+                        for (int k = 0; k < SCORE_GPW; ++k) sw[k] += (__double2hiint(x[k]) >= 0) ? dr : 0.0;
                     }
                 }
             }
