@@ -156,7 +156,7 @@ int validate(const cbo_gp_f64* gp, const cbo_params* p, int64_t b) {
     if (p->num_probes < 1 || p->num_probes > cbo::MAX_SP) return CBO_ERR_UNSUPPORTED;
     if (p->num_mc < 1 || p->num_mc > cbo::MAX_S) return CBO_ERR_UNSUPPORTED;
     if (p->grid_res > 4096) return CBO_ERR_UNSUPPORTED;
-    if (cbo::score_smem_bytes((int)gp->Np, (int)p->grid_res) > 227 * 1024) return CBO_ERR_UNSUPPORTED;
+    if (cbo::score_warps_for((int)gp->Np, (int)p->grid_res) < 1) return CBO_ERR_UNSUPPORTED;
     return CBO_OK;
 }
 
@@ -173,19 +173,18 @@ int num_sms() {
 
 template <bool SOFT>
 cudaError_t launch_score(const cbo::ScoreArgs& a, cudaStream_t st) {
-    size_t smem = cbo::score_smem_bytes(a.Np, a.G);
+    const int nwarps = cbo::score_warps_for(a.Np, a.G);
+    if (nwarps < 1) return cudaErrorInvalidConfiguration;
+    size_t smem = cbo::score_smem_bytes(a.Np, a.G, nwarps);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(cbo::k_score<SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbo::k_score<SOFT>, cbo::SCORE_THREADS, smem);
-    if (per_sm < 1) per_sm = 1;
-    int grid = num_sms() * per_sm;
-    if (grid > a.n_cand) grid = a.n_cand;
-    cbo::k_score<SOFT><<<grid, cbo::SCORE_THREADS, smem, st>>>(a);
+    int grid = (a.n_cand + nwarps - 1) / nwarps;       // persistent: one CTA per SM, one warp per candidate in flight
+    if (grid > num_sms()) grid = num_sms();
+    cbo::k_score<SOFT><<<grid, nwarps * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 

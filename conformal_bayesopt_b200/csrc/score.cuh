@@ -1,27 +1,30 @@
 // score.cuh -- nonconformity scores, density-ratio-weighted conformal rank, mask and the
-// importance-weighted acquisition value, one persistent CTA looping over candidates.
+// importance-weighted acquisition value.  One WARP per candidate, no block-level barriers.
 //
 // Fuses, per candidate (q = 1, one output), what the reference evaluates as dense batched tensors
 // of shape (b, G, N+1, ...) (conformalbo/helpers.py:266-325, conformalbo/acquisitions.py:57-76,
 // 151-159, 88-98, 225-248), using the closed forms of SURVEY.md App. A-2..A-7:
-//   phase A  (all threads)   per-train-point Hutchinson variance for THIS candidate (A-4):
-//                            var_i = noise (h0_i + noise/(Sp+1e-6) * w_i * (z_i . c)),  c = (z_c - u^T T)/s
-//                            -> shared memory tables  ww = noise w_i, iv = 1/(2 var_i), lv = -log(var_i)/2 - log(2pi)/2
-//   phase B  (warp per 8 grid points) for every train point: residual, score, hard count,
-//                            soft rank sigmoid, weighted sums (A-3, A-5) -- the hot loop,
-//                            16 fp64-pipe instructions per (train point, grid point), 8 independent chains per lane
+//   phase A  per-train-point Hutchinson variance for THIS candidate (A-4):
+//              var_i = noise (h0_i + noise/(Sp+1e-6) * w_i * (z_i . c)),  c = (z_c - u^T T)/s
+//            and the coefficients of the score difference, which is a quadratic in b_g = (y_g - mu)/s:
+//              x_i(g) = c1 (score_c(g) - score_i(g)) = (qa_i b_g + qb_i) b_g + qc_i,  c1 = 16/(temp ln 2)
+//            -> warp-private shared-memory tables qa, qb, qc
+//   phase B  for 8 grid points at a time, every train point: hard count, soft-rank sigmoid and the
+//            weighted sums (A-3, A-5) -- the hot loop: 14 fp64-pipe instructions per
+//            (train point, grid point), 8 independent dependency chains per lane
 //   phase C  (lane per grid point) weighted mass, randomised step, conformal mask, log-density,
-//                            optimistic mask, refit mean (A-5, A-6)
-//   phase D  (block reduce over the grid) importance-weighted integration (A-7)
+//            optimistic mask, refit mean (A-5, A-6)
+//   phase D  (warp reduce over the grid) importance-weighted integration (A-7)
+// A warp never waits for another warp: while one warp is in the latency-bound phases A/C/D its
+// SM sub-partition neighbour keeps the fp64 pipe busy with phase B.
 #pragma once
 #include "common.cuh"
 #include "rows.cuh"
 
 namespace cbo {
 
-constexpr int SCORE_THREADS = 128;
-constexpr int SCORE_WARPS = SCORE_THREADS / 32;
-constexpr int SCORE_GPW = 8;           // grid points per warp pass
+constexpr int SCORE_MAX_WARPS = 8;
+constexpr int SCORE_GPW = 8;           // grid points per pass
 constexpr int MAX_S = 16;
 
 struct ScoreArgs {
@@ -52,50 +55,64 @@ struct ScoreArgs {
     double* post_mean; double* post_var; double* num_acc;
 };
 
-__host__ __device__ inline size_t score_smem_bytes(int Np, int G) {
-    // tab[16] | a, dr, ap, wp, lv [Np each] | g-arrays cw, nc, mf, mk [G each] | red[SCORE_WARPS * (2*MAX_S+3)] | zb[Np] u32
-    return sizeof(double) * (16 + 5 * size_t(Np) + 4 * size_t(G) + SCORE_WARPS * (2 * MAX_S + 3)) +
-           sizeof(uint32_t) * size_t(Np);
+// shared: tab[16] | dr[Np] | zb[Np] (u32)        per warp: qa, qb, qc [Np] | cw, nc, mf, mk [G]
+__host__ __device__ inline size_t score_smem_shared_bytes(int Np) {
+    return sizeof(double) * (16 + size_t(Np)) + sizeof(uint32_t) * size_t(Np);
+}
+__host__ __device__ inline size_t score_smem_warp_bytes(int Np, int G) {
+    return sizeof(double) * (3 * size_t(Np) + 4 * size_t(G));
+}
+__host__ __device__ inline size_t score_smem_bytes(int Np, int G, int nwarps) {
+    return score_smem_shared_bytes(Np) + size_t(nwarps) * score_smem_warp_bytes(Np, G);
+}
+// warps per CTA that fit 227 KB of shared memory (0: unsupported shape)
+inline int score_warps_for(int Np, int G) {
+    size_t avail = 227 * 1024;
+    if (score_smem_shared_bytes(Np) + score_smem_warp_bytes(Np, G) > avail) return 0;
+    size_t w = (avail - score_smem_shared_bytes(Np)) / score_smem_warp_bytes(Np, G);
+    return int(w > SCORE_MAX_WARPS ? SCORE_MAX_WARPS : w);
 }
 
 template <bool SOFT>
-__global__ void __launch_bounds__(SCORE_THREADS)
+__global__ void __launch_bounds__(SCORE_MAX_WARPS * 32, 1)
 k_score(const ScoreArgs p) {
     extern __shared__ __align__(16) double sm[];
-    double* tab = sm;                 // 2^(j/16), j < 16: one shared-memory row, conflict-free for any index pattern
-    double* sa = tab + 16;            // noise * alpha_i                       (per model)
-    double* sdr = sa + p.Np;          // density ratio of train point i        (per model)
-    // per candidate: x_i(g) = c1 (score_c(g) - score_i(g)) = (qa_i b_g + qb_i) b_g + qc_i   (quadratic in b_g)
-    double* sqa = sdr + p.Np;
-    double* sqb = sqa + p.Np;
-    double* sqc = sqb + p.Np;
-    double* g_cw = sqc + p.Np;
-    double* g_nc = g_cw + p.G;
-    double* g_mf = g_nc + p.G;
-    double* g_mk = g_mf + p.G;
-    double* red = g_mk + p.G;
-    uint32_t* szb = reinterpret_cast<uint32_t*>(red + SCORE_WARPS * (2 * MAX_S + 3));
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int N = p.N, G = p.G, Sp = p.Sp;
+    const int nwarps = blockDim.x >> 5;
+    const int N = p.N, Np = p.Np, G = p.G, Sp = p.Sp;
+    const int N32 = (N + 31) & ~31;                     // Np is a multiple of 128 >= N32
 
-    // ---- once per CTA: candidate-independent tables -------------------------------------------
+    double* tab = sm;                                   // 2^(j/16): one 128-byte row, conflict-free for any index pattern
+    double* sdr = tab + 16;                             // density ratio of train point i (0 beyond N)
+    uint32_t* szb = reinterpret_cast<uint32_t*>(sdr + Np);
+    double* wbase = reinterpret_cast<double*>(szb + Np) + size_t(warp) * (3 * size_t(Np) + 4 * size_t(G));
+    double* sqa = wbase;
+    double* sqb = sqa + Np;
+    double* sqc = sqb + Np;
+    double* g_cw = sqc + Np;
+    double* g_nc = g_cw + G;
+    double* g_mf = g_nc + G;
+    double* g_mk = g_mf + G;
+
+    // ---- once per CTA: candidate-independent tables ------------------------------------------------
     if (tid < 16) tab[tid] = exp2(double(tid) / 16.0);
-    for (int i = tid; i < N; i += SCORE_THREADS) {
-        sa[i] = p.a[i];
-        sdr[i] = p.dr[i];
-        szb[i] = p.zb[i];
+    for (int i = tid; i < Np; i += blockDim.x) {
+        sdr[i] = (i < N) ? p.dr[i] : 0.0;
+        szb[i] = (i < N) ? p.zb[i] : 0u;
     }
+    __syncthreads();                                    // the only block-level barrier
+
     const double sum_dr = p.sum_dr[0];
     const double kvar = p.noise / (double(Sp) + 1e-6);
     const double inv_temp = SOFT ? 1.0 / p.temp : 0.0;
-    const double c1 = SOFT ? inv_temp * 23.083120654223414 : 1.0;        // 16 / (temp ln 2): exp(-|dd|/temp) = 2^(-|x|/16)
+    const double c1 = SOFT ? inv_temp * 23.083120654223414 : 1.0;        // 16 / (temp ln 2)
     double zc[MAX_SP];
 #pragma unroll
     for (int s = 0; s < MAX_SP; ++s) zc[s] = (s < Sp) ? p.z_cand[s] : 0.0;
 
-    for (int c = blockIdx.x; c < p.n_cand; c += gridDim.x) {
-        // ---- phase A ---------------------------------------------------------------------------
+    const int total_warps = gridDim.x * nwarps;
+    for (int c = blockIdx.x * nwarps + warp; c < p.n_cand; c += total_warps) {
+        // ---- phase A -----------------------------------------------------------------------------
         double vnorm = 0.0;
         for (int t = 0; t < p.tiles_n; ++t) vnorm += p.rn_partial[int64_t(c) * p.tiles_n + t];
         const double s_var = p.kappa + p.noise - vnorm;                 // Schur complement (noisy predictive variance)
@@ -114,66 +131,64 @@ k_score(const ScoreArgs p) {
         const double lv_c = -0.5 * log(var_c) - 0.5 * kLog2Pi;
         // score_c(g) = lv_c - iv_c (noise b_g)^2 ;  score_i(g) = lv_i - iv_i (a_i - noise w_i b_g)^2
         const double qa_c = -iv_c * p.noise * p.noise;
-        const double* Wc = p.W + int64_t(c) * p.Np;
-        for (int i = tid; i < N; i += SCORE_THREADS) {
-            double w = Wc[i];
-            uint32_t bits = szb[i];
-            double zdot = 0.0;
+        const double* Wc = p.W + int64_t(c) * Np;
+#pragma unroll 2
+        for (int i = lane; i < N32; i += 32) {
+            double qa = 0.0, qb = 0.0, qc = -1e300;                      // padding lane: x = -1e300, never counted, dr = 0
+            if (i < N) {
+                double w = Wc[i];
+                uint32_t bits = szb[i];
+                double zdot = 0.0;
 #pragma unroll
-            for (int s = 0; s < MAX_SP; ++s)
-                if (s < Sp) zdot += ((bits >> s) & 1u) ? cs[s] : -cs[s];
-            double var = p.noise * fma(kvar * w, zdot, p.h0[i]);
-            bad |= !(var > 0.0);
-            double iv = 0.5 / var;
-            double lv = -0.5 * log(var) - 0.5 * kLog2Pi;
-            double ai = sa[i], wi = p.noise * w;
-            sqa[i] = c1 * fma(iv * wi, wi, qa_c);                        // b_g^2 coefficient
-            sqb[i] = c1 * (-2.0 * iv * ai * wi);                         // b_g coefficient
-            sqc[i] = c1 * (fma(iv * ai, ai, lv_c - lv));                 // constant
+                for (int s = 0; s < MAX_SP; ++s)
+                    if (s < Sp) zdot += ((bits >> s) & 1u) ? cs[s] : -cs[s];
+                double var = p.noise * fma(kvar * w, zdot, p.h0[i]);
+                bad |= !(var > 0.0);
+                double iv = 0.5 / var;
+                double lv = -0.5 * log(var) - 0.5 * kLog2Pi;
+                double ai = p.a[i], wi = p.noise * w;
+                qa = c1 * fma(iv * wi, wi, qa_c);                        // b_g^2 coefficient
+                qb = c1 * (-2.0 * iv * ai * wi);                         // b_g coefficient
+                qc = c1 * (fma(iv * ai, ai, lv_c - lv));                 // constant
+            }
+            sqa[i] = qa; sqb[i] = qb; sqc[i] = qc;
         }
-        bad = __syncthreads_or(bad);
+        bad = __any_sync(0xffffffffu, bad);
+        __syncwarp();
         const double cscale = p.cscale ? p.cscale[c] : 1.0;
         const double gsd = sqrt(cscale * s_var);                        // sd of the grid distribution
         const double drc = p.drc ? p.drc[c] : 1.0;
         const double norm = sum_dr + drc;
         const double omega_c = drc / norm;
 
-        // ---- phase B + C: warp per octet of grid points ----------------------------------------
-        for (int g0 = warp * SCORE_GPW; g0 < G; g0 += SCORE_WARPS * SCORE_GPW) {
-            double bg[SCORE_GPW], scc[SCORE_GPW], sr[SCORE_GPW], sw[SCORE_GPW];
-            int cnt[SCORE_GPW];
+        // ---- phase B + C: 8 grid points per pass ---------------------------------------------------
+        for (int g0 = 0; g0 < G; g0 += SCORE_GPW) {
+            double bg[SCORE_GPW], sr[SCORE_GPW], sw[SCORE_GPW];
+            unsigned cneg[SCORE_GPW];
 #pragma unroll
             for (int k = 0; k < SCORE_GPW; ++k) {
                 int g = min(g0 + k, G - 1);
                 double eps = p.eps_grid[p.eps_per_candidate ? int64_t(c) * G + g : g];
-                double dev = gsd * eps;                                 // y_g - mu
-                bg[k] = dev * inv_s;
-                double rc = p.noise * bg[k];
-                scc[k] = fma(-rc * rc, iv_c, lv_c);
-                sr[k] = 0.0; sw[k] = 0.0; cnt[k] = 0;
+                bg[k] = gsd * eps * inv_s;                              // (y_g - mu) / s
+                sr[k] = 0.0; sw[k] = 0.0; cneg[k] = 0u;
             }
             if (!bad) {
-                // Soft rank: rho = sigmoid(dd / temp) = 1 / (1 + e),  e = exp(-dd/temp) = 2^(-x/16),  x = c1 dd,
-                // c1 = 16 / (temp ln 2).  With n = -round(x) = 16 kk + j:  e = 2^kk * tab[j] * P(x - round(x)),
-                // P(y) ~ exp(-y ln2/16) on [-1/2, 1/2] (16-entry table + near-minimax cubic, rel. err 1.2e-9);
-                // 1/(1+e) from a MUFU.RCP64H seed and one Newton step.  14 fp64-pipe instructions per
-                // (train point, grid point).  |x| is clamped at 946 = 41 * 16/ln2 in the integer domain
-                // (rho is 0 or 1 to 2e-18 beyond that).
+                // Soft rank: rho = sigmoid(dd / temp) = 1 / (1 + e),  e = exp(-dd/temp) = 2^(-x/16),  x = c1 dd.
+                // With n = -round(x) = 16 kk + j:  e = 2^kk * tab[j] * P(x - round(x)),  P(y) ~ exp(-y ln2/16) on
+                // [-1/2, 1/2] (16-entry table + near-minimax cubic, rel. err 1.2e-9); 1/(1+e) from a MUFU.RCP64H
+                // seed and one Newton step.  |x| is clamped at 946 = 41 * 16/ln2 in the integer domain (rho is
+                // 0 or 1 to 2e-18 beyond that).
                 constexpr double kMagic = 6755399441055744.0;             // 1.5 * 2^52
                 constexpr double kC0 = 0.9999999988534117, kC1 = 0.043321698775061875,
                                  kC2 = 0.0009384214835622084, kC3 = 1.3551125681305332e-05;
                 constexpr int kSatHi = 0x408d9000;                        // hiword(946.0)
-                for (int i0 = 0; i0 < N; i0 += 32) {
-                    const int i = i0 + lane;
-                    const bool valid = i < N;
-                    // a lane past the end has x = -1e300: never counted, rho ~ 1e-18 weighted by dr = 0
-                    const double qa = valid ? sqa[i] : 0.0, qb = valid ? sqb[i] : 0.0, qc = valid ? sqc[i] : -1e300,
-                                 dr = valid ? sdr[i] : 0.0;
+                for (int i = lane; i < N32; i += 32) {
+                    const double qa = sqa[i], qb = sqb[i], qc = sqc[i], dr = sdr[i];
                     double x[SCORE_GPW];
 #pragma unroll
                     for (int k = 0; k < SCORE_GPW; ++k) {
                         x[k] = fma(fma(qa, bg[k], qb), bg[k], qc);
-                        cnt[k] += (__double2hiint(x[k]) >= 0) ? 1 : 0;
+                        cneg[k] += unsigned(__double2hiint(x[k])) >> 31;  // counts score_c < score_i
                     }
                     if (SOFT) {
                         double t[SCORE_GPW], yn[SCORE_GPW], e[SCORE_GPW];
@@ -192,7 +207,7 @@ k_score(const ScoreArgs p) {
                             pl = fma(pl, yn[k], kC0);                     // exp(-yn ln2/16)
                             int n = __double2loint(t[k]);
                             double ev = tab[n & 15] * pl;
-                            e[k] = __hiloint2double(__double2hiint(ev) + ((n << 16) & 0xfff00000), __double2loint(ev));
+                            e[k] = __hiloint2double(__double2hiint(ev) + ((n >> 4) << 20), __double2loint(ev));
                         }
 #pragma unroll
                         for (int k = 0; k < SCORE_GPW; ++k) {
@@ -210,18 +225,19 @@ k_score(const ScoreArgs p) {
                     }
                 }
             }
+            int cnt[SCORE_GPW];
 #pragma unroll
             for (int k = 0; k < SCORE_GPW; ++k) {
-                cnt[k] = warp_sum_int(cnt[k]);
+                cnt[k] = N32 - warp_sum_int(int(cneg[k]));                // #{i <= N : score_c >= score_i}
                 sw[k] = warp_sum(sw[k]);
                 if (SOFT) sr[k] = warp_sum(sr[k]);
             }
             // phase C: lane k finishes grid point g0 + k
-            double my_sr = 0.0, my_sw = 0.0, my_scc = 0.0, my_bg = 0.0;
+            double my_sr = 0.0, my_sw = 0.0, my_bg = 0.0;
             int my_cnt = 0;
 #pragma unroll
             for (int k = 0; k < SCORE_GPW; ++k)
-                if (lane == k) { my_sr = sr[k]; my_sw = sw[k]; my_cnt = cnt[k]; my_scc = scc[k]; my_bg = bg[k]; }
+                if (lane == k) { my_sr = sr[k]; my_sw = sw[k]; my_cnt = cnt[k]; my_bg = bg[k]; }
             const int g = g0 + lane;
             if (lane < SCORE_GPW && g < G) {
                 double n_g = double(my_cnt + 1);                        // includes the candidate itself
@@ -241,88 +257,70 @@ k_score(const ScoreArgs p) {
                     M -= (u < pr) ? 0.0 : D;
                 }
                 double mk = SOFT ? sigmoid_acc((M - p.alpha_lvl) * inv_temp) : ((M > p.alpha_lvl) ? 1.0 : 0.0);
-                double dev = my_bg * s_var;
                 double eps = p.eps_grid[p.eps_per_candidate ? int64_t(c) * G + g : g];
                 double yg = mu + gsd * eps;
                 double lp = -0.5 * (eps * eps + log(cscale * s_var) + kLog2Pi);
                 double opt = p.optimistic ? ((yg >= mu) ? 1.0 : 0.0) : 1.0;
                 double shrink = 1.0 - p.noise * inv_s;
-                (void)dev;
+                double rc = p.noise * my_bg;
+                double scc = fma(-rc * rc, iv_c, lv_c);                 // candidate's own conformal score
                 g_mk[g] = mk;
                 g_cw[g] = mk * opt / fmax(exp(lp), 1e-6);
                 g_nc[g] = (1.0 - mk) * opt;
                 g_mf[g] = mu + (yg - mu) * shrink;
-                if (bad) { g_mk[g] = g_cw[g] = g_nc[g] = g_mf[g] = nan(""); mk = lp = nan(""); }
+                if (bad) { g_mk[g] = g_cw[g] = g_nc[g] = g_mf[g] = nan(""); mk = lp = scc = nan(""); }
                 if (p.grid) p.grid[int64_t(c) * G + g] = yg;
                 if (p.logp) p.logp[int64_t(c) * G + g] = lp;
                 if (p.mask) p.mask[int64_t(c) * G + g] = mk;
-                if (p.qscore) p.qscore[int64_t(c) * G + g] = bad ? nan("") : my_scc;
+                if (p.qscore) p.qscore[int64_t(c) * G + g] = scc;
             }
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- phase D: integrate over the grid ---------------------------------------------------
+        // ---- phase D: integrate over the grid --------------------------------------------------------
         const double sd_f = sqrt(fmax(p.noise * (1.0 - p.noise * inv_s), 0.0));
         const int S = p.S;
-        double accA[MAX_S], accB[MAX_S];
-#pragma unroll
-        for (int s = 0; s < MAX_S; ++s) accA[s] = accB[s] = 0.0;
         double scw = 0.0, snc = 0.0, nacc = 0.0;
-        for (int g = tid; g < G; g += SCORE_THREADS) {
-            double cw = g_cw[g], nc = g_nc[g], mf = g_mf[g];
-            scw += cw; snc += nc; nacc += (g_mk[g] >= 0.5) ? 1.0 : 0.0;
-            double em = 0.0;
-            if (p.kind == 0 && S > 1) {
-                for (int s = 0; s < S; ++s) em += p.eps_mc[int64_t(s) * G + g];
-                em /= double(S);
-            }
-#pragma unroll
-            for (int s = 0; s < MAX_S; ++s) {
-                if (s < S) {
-                    double e = p.eps_mc[int64_t(s) * G + g];
-                    double f = fma(sd_f, e, mf);
-                    double val;
-                    if (p.kind == 0) {
-                        if (S > 1) { double m = fma(sd_f, em, mf); val = m + p.beta_prime * fabs(f - m); }
-                        else val = f;
-                    } else {
-                        double x = f - p.best_f;
-                        if (p.temp > 0.0) { double xt = x / p.temp; val = p.temp * (fmax(xt, 0.0) + log1p(exp(-fabs(xt)))); }
-                        else val = fmax(x, 0.0);
-                    }
-                    accA[s] = fma(cw, val, accA[s]);
-                    accB[s] = fma(nc, val, accB[s]);
-                }
-            }
+        for (int g = lane; g < G; g += 32) {
+            scw += g_cw[g]; snc += g_nc[g]; nacc += (g_mk[g] >= 0.5) ? 1.0 : 0.0;
         }
-        const int nred = 2 * MAX_S + 3;
         scw = warp_sum(scw); snc = warp_sum(snc); nacc = warp_sum(nacc);
-        if (lane == 0) { red[warp * nred + 0] = scw; red[warp * nred + 1] = snc; red[warp * nred + 2] = nacc; }
-#pragma unroll
-        for (int s = 0; s < MAX_S; ++s) {
-            if (s < S) {
-                double A = warp_sum(accA[s]), B = warp_sum(accB[s]);
-                if (lane == 0) { red[warp * nred + 3 + 2 * s] = A; red[warp * nred + 4 + 2 * s] = B; }
+        const double ood = SOFT ? sigmoid_acc((omega_c - p.alpha_lvl) * inv_temp) : ((omega_c >= p.alpha_lvl) ? 1.0 : 0.0);
+        double tot = 0.0;
+        for (int s = 0; s < S; ++s) {
+            double A = 0.0, B = 0.0;
+            for (int g = lane; g < G; g += 32) {
+                double cw = g_cw[g], nc = g_nc[g], mf = g_mf[g];
+                double f = fma(sd_f, p.eps_mc[int64_t(s) * G + g], mf);
+                double val;
+                if (p.kind == 0) {
+                    if (S > 1) {
+                        double em = 0.0;
+                        for (int s2 = 0; s2 < S; ++s2) em += p.eps_mc[int64_t(s2) * G + g];
+                        double m = fma(sd_f, em / double(S), mf);
+                        val = m + p.beta_prime * fabs(f - m);
+                    } else {
+                        val = f;
+                    }
+                } else {
+                    double xx = f - p.best_f;
+                    if (p.temp > 0.0) { double xt = xx / p.temp; val = p.temp * (fmax(xt, 0.0) + log1p(exp(-fabs(xt)))); }
+                    else val = fmax(xx, 0.0);
+                }
+                A = fma(cw, val, A);
+                B = fma(nc, val, B);
             }
+            A = warp_sum(A); B = warp_sum(B);
+            tot += (1.0 - ood) * ((1.0 - p.alpha_lvl) * A / fmax(scw, 1e-6) + p.alpha_lvl * B / fmax(snc, 1e-6));
         }
-        __syncthreads();
-        if (tid == 0) {
-            double tcw = 0.0, tnc = 0.0, tna = 0.0;
-            for (int w = 0; w < SCORE_WARPS; ++w) { tcw += red[w * nred]; tnc += red[w * nred + 1]; tna += red[w * nred + 2]; }
-            double ood = SOFT ? sigmoid_acc((omega_c - p.alpha_lvl) * inv_temp) : ((omega_c >= p.alpha_lvl) ? 1.0 : 0.0);
-            double tot = 0.0;
-            for (int s = 0; s < S; ++s) {
-                double A = 0.0, B = 0.0;
-                for (int w = 0; w < SCORE_WARPS; ++w) { A += red[w * nred + 3 + 2 * s]; B += red[w * nred + 4 + 2 * s]; }
-                tot += (1.0 - ood) * ((1.0 - p.alpha_lvl) * A / fmax(tcw, 1e-6) + p.alpha_lvl * B / fmax(tnc, 1e-6));
-            }
+        if (lane == 0) {
             p.acq[c] = tot / double(S);
             if (p.ood) p.ood[c] = ood;
             if (p.post_mean) p.post_mean[c] = mu;
             if (p.post_var) p.post_var[c] = s_var;
-            if (p.num_acc) p.num_acc[c] = tna;
+            if (p.num_acc) p.num_acc[c] = nacc;
         }
-        // g-arrays / red are rewritten only after the next candidate's phase-A barrier
+        __syncwarp();                                     // g-arrays / tables are rewritten by the next candidate
     }
 }
 
