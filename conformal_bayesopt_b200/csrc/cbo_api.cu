@@ -156,7 +156,7 @@ int validate(const cbo_gp_f64* gp, const cbo_params* p, int64_t b) {
     if (p->num_probes < 1 || p->num_probes > cbo::MAX_SP) return CBO_ERR_UNSUPPORTED;
     if (p->num_mc < 1 || p->num_mc > cbo::MAX_S) return CBO_ERR_UNSUPPORTED;
     if (p->grid_res > 4096) return CBO_ERR_UNSUPPORTED;
-    if (cbo::score_warps_for((int)gp->Np, (int)p->grid_res) < 1) return CBO_ERR_UNSUPPORTED;
+    if (cbo::score_pairs_for((int)gp->Np, (int)p->grid_res) < 1) return CBO_ERR_UNSUPPORTED;
     return CBO_OK;
 }
 
@@ -173,18 +173,18 @@ int num_sms() {
 
 template <bool SOFT>
 cudaError_t launch_score(const cbo::ScoreArgs& a, cudaStream_t st) {
-    const int nwarps = cbo::score_warps_for(a.Np, a.G);
-    if (nwarps < 1) return cudaErrorInvalidConfiguration;
-    size_t smem = cbo::score_smem_bytes(a.Np, a.G, nwarps);
+    const int npairs = cbo::score_pairs_for(a.Np, a.G);
+    if (npairs < 1) return cudaErrorInvalidConfiguration;
+    size_t smem = cbo::score_smem_bytes(a.Np, a.G, npairs);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(cbo::k_score<SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    int grid = (a.n_cand + nwarps - 1) / nwarps;       // persistent: one CTA per SM, one warp per candidate in flight
+    int grid = (a.n_cand + npairs - 1) / npairs;       // persistent: one CTA per SM, one warp pair per candidate in flight
     if (grid > num_sms()) grid = num_sms();
-    cbo::k_score<SOFT><<<grid, nwarps * 32, smem, st>>>(a);
+    cbo::k_score<SOFT><<<grid, npairs * 64, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -1,5 +1,5 @@
 // score.cuh -- nonconformity scores, density-ratio-weighted conformal rank, mask and the
-// importance-weighted acquisition value.  One WARP per candidate, no block-level barriers.
+// importance-weighted acquisition value.  One warp PAIR per candidate, pair-local named barriers.
 //
 // Fuses, per candidate (q = 1, one output), what the reference evaluates as dense batched tensors
 // of shape (b, G, N+1, ...) (conformalbo/helpers.py:266-325, conformalbo/acquisitions.py:57-76,
@@ -8,23 +8,24 @@
 //              var_i = noise (h0_i + noise/(Sp+1e-6) * w_i * (z_i . c)),  c = (z_c - u^T T)/s
 //            and the coefficients of the score difference, which is a quadratic in b_g = (y_g - mu)/s:
 //              x_i(g) = c1 (score_c(g) - score_i(g)) = (qa_i b_g + qb_i) b_g + qc_i,  c1 = 16/(temp ln 2)
-//            -> warp-private shared-memory tables qa, qb, qc
-//   phase B  for 8 grid points at a time, every train point: hard count, soft-rank sigmoid and the
+//            -> pair-private shared-memory tables qa, qb, qc
+//   phase B  4 grid points per pass, every train point: hard count, soft-rank sigmoid and the
 //            weighted sums (A-3, A-5) -- the hot loop: 14 fp64-pipe instructions per
-//            (train point, grid point), 8 independent dependency chains per lane
-//   phase C  (lane per grid point) weighted mass, randomised step, conformal mask, log-density,
+//            (train point, grid point), 4 independent dependency chains per lane, 16 warps per SM
+//   phase C  (thread per grid point) weighted mass, randomised step, conformal mask, log-density,
 //            optimistic mask, refit mean (A-5, A-6)
 //   phase D  (warp reduce over the grid) importance-weighted integration (A-7)
-// A warp never waits for another warp: while one warp is in the latency-bound phases A/C/D its
-// SM sub-partition neighbour keeps the fp64 pipe busy with phase B.
+// Pairs never wait for each other (bar.sync on a pair-private barrier id, 64 threads): while one
+// pair is in the latency-bound phases A/C/D the other warps of the SM sub-partition keep the fp64
+// pipe busy with phase B.
 #pragma once
 #include "common.cuh"
 #include "rows.cuh"
 
 namespace cbo {
 
-constexpr int SCORE_MAX_WARPS = 8;
-constexpr int SCORE_GPW = 8;           // grid points per pass
+constexpr int SCORE_MAX_PAIRS = 8;
+constexpr int SCORE_GPW = 4;           // grid points per pass
 constexpr int MAX_S = 16;
 
 struct ScoreArgs {
@@ -55,64 +56,75 @@ struct ScoreArgs {
     double* post_mean; double* post_var; double* num_acc;
 };
 
-// shared: tab[16] | dr[Np] | zb[Np] (u32)        per warp: qa, qb, qc [Np] | cw, nc, mf, mk [G]
-__host__ __device__ inline size_t score_smem_shared_bytes(int Np) {
-    return sizeof(double) * (16 + size_t(Np)) + sizeof(uint32_t) * size_t(Np);
-}
-__host__ __device__ inline size_t score_smem_warp_bytes(int Np, int G) {
+// shared: tab[16] | dr[Np]        per pair: qa, qb, qc [Np] | 4 x [G] (raw cnt/sr/sw, then cw/nc/mf/mk)
+__host__ __device__ inline size_t score_smem_shared_bytes(int Np) { return sizeof(double) * (16 + size_t(Np)); }
+__host__ __device__ inline size_t score_smem_pair_bytes(int Np, int G) {
     return sizeof(double) * (3 * size_t(Np) + 4 * size_t(G));
 }
-__host__ __device__ inline size_t score_smem_bytes(int Np, int G, int nwarps) {
-    return score_smem_shared_bytes(Np) + size_t(nwarps) * score_smem_warp_bytes(Np, G);
+__host__ __device__ inline size_t score_smem_bytes(int Np, int G, int npairs) {
+    return score_smem_shared_bytes(Np) + size_t(npairs) * score_smem_pair_bytes(Np, G);
 }
-// warps per CTA that fit 227 KB of shared memory (0: unsupported shape)
-inline int score_warps_for(int Np, int G) {
+// warp pairs per CTA that fit 227 KB of shared memory (0: unsupported shape)
+inline int score_pairs_for(int Np, int G) {
     size_t avail = 227 * 1024;
-    if (score_smem_shared_bytes(Np) + score_smem_warp_bytes(Np, G) > avail) return 0;
-    size_t w = (avail - score_smem_shared_bytes(Np)) / score_smem_warp_bytes(Np, G);
-    return int(w > SCORE_MAX_WARPS ? SCORE_MAX_WARPS : w);
+    if (score_smem_shared_bytes(Np) + score_smem_pair_bytes(Np, G) > avail) return 0;
+    size_t w = (avail - score_smem_shared_bytes(Np)) / score_smem_pair_bytes(Np, G);
+    return int(w > SCORE_MAX_PAIRS ? SCORE_MAX_PAIRS : w);
+}
+
+__device__ __forceinline__ void pair_barrier(int pair) {
+    asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+}
+// barrier over the 64 threads of a pair that also ORs a predicate across them
+__device__ __forceinline__ int pair_barrier_or(int pair, int pred) {
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %2, 0;\n\tbar.red.or.pred p, %1, 64, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"(pair + 1), "r"(pred)
+        : "memory");
+    return r;
 }
 
 template <bool SOFT>
-__global__ void __launch_bounds__(SCORE_MAX_WARPS * 32, 1)
+__global__ void __launch_bounds__(SCORE_MAX_PAIRS * 64, 1)
 k_score(const ScoreArgs p) {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nwarps = blockDim.x >> 5;
+    const int pair = warp >> 1, half = warp & 1, ptid = tid & 63;      // thread index within the pair
+    const int npairs = blockDim.x >> 6;
     const int N = p.N, Np = p.Np, G = p.G, Sp = p.Sp;
     const int N32 = (N + 31) & ~31;                     // Np is a multiple of 128 >= N32
 
     double* tab = sm;                                   // 2^(j/16): one 128-byte row, conflict-free for any index pattern
     double* sdr = tab + 16;                             // density ratio of train point i (0 beyond N)
-    uint32_t* szb = reinterpret_cast<uint32_t*>(sdr + Np);
-    double* wbase = reinterpret_cast<double*>(szb + Np) + size_t(warp) * (3 * size_t(Np) + 4 * size_t(G));
-    double* sqa = wbase;
+    double* pbase = sdr + Np + size_t(pair) * (3 * size_t(Np) + 4 * size_t(G));
+    double* sqa = pbase;
     double* sqb = sqa + Np;
     double* sqc = sqb + Np;
-    double* g_cw = sqc + Np;
-    double* g_nc = g_cw + G;
-    double* g_mf = g_nc + G;
-    double* g_mk = g_mf + G;
+    double* g_cw = sqc + Np;                            // phase B stores the hard count here, phase C the conf. weight
+    double* g_nc = g_cw + G;                            // sum rho        -> non-conformal weight
+    double* g_mf = g_nc + G;                            // sum rho * dr   -> refit mean
+    double* g_mk = g_mf + G;                            // mask
 
     // ---- once per CTA: candidate-independent tables ------------------------------------------------
     if (tid < 16) tab[tid] = exp2(double(tid) / 16.0);
-    for (int i = tid; i < Np; i += blockDim.x) {
-        sdr[i] = (i < N) ? p.dr[i] : 0.0;
-        szb[i] = (i < N) ? p.zb[i] : 0u;
-    }
-    __syncthreads();                                    // the only block-level barrier
+    for (int i = tid; i < Np; i += blockDim.x) sdr[i] = (i < N) ? p.dr[i] : 0.0;
+    __syncthreads();                                    // the only block-wide barrier
 
     const double sum_dr = p.sum_dr[0];
     const double kvar = p.noise / (double(Sp) + 1e-6);
     const double inv_temp = SOFT ? 1.0 / p.temp : 0.0;
     const double c1 = SOFT ? inv_temp * 23.083120654223414 : 1.0;        // 16 / (temp ln 2)
-    double zc[MAX_SP];
-#pragma unroll
-    for (int s = 0; s < MAX_SP; ++s) zc[s] = (s < Sp) ? p.z_cand[s] : 0.0;
 
-    const int total_warps = gridDim.x * nwarps;
-    for (int c = blockIdx.x * nwarps + warp; c < p.n_cand; c += total_warps) {
-        // ---- phase A -----------------------------------------------------------------------------
+    const int total_pairs = gridDim.x * npairs;
+    for (int c = blockIdx.x * npairs + pair; c < p.n_cand; c += total_pairs) {
+        // ---- phase A (64 threads) ------------------------------------------------------------------
+        {   // pull the next candidate's W row towards L2 while this one is processed
+            int cn = c + total_pairs;
+            if (cn < p.n_cand && ptid * 16 < Np)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.W + int64_t(cn) * Np + ptid * 16));
+        }
         double vnorm = 0.0;
         for (int t = 0; t < p.tiles_n; ++t) vnorm += p.rn_partial[int64_t(c) * p.tiles_n + t];
         const double s_var = p.kappa + p.noise - vnorm;                 // Schur complement (noisy predictive variance)
@@ -122,8 +134,9 @@ k_score(const ScoreArgs p) {
         double zcc = 0.0;                                               // sum_s z_cs c_s
 #pragma unroll
         for (int s = 0; s < MAX_SP; ++s) {
-            cs[s] = (s < Sp) ? (zc[s] - p.ut[int64_t(c) * Sp + s]) * inv_s : 0.0;
-            zcc = fma(zc[s], cs[s], zcc);
+            double zcs = (s < Sp) ? p.z_cand[s] : 0.0;
+            cs[s] = (s < Sp) ? (zcs - p.ut[int64_t(c) * Sp + s]) * inv_s : 0.0;
+            zcc = fma(zcs, cs[s], zcc);
         }
         const double var_c = p.noise * (1.0 + (double(Sp) - p.noise * zcc) / (double(Sp) + 1e-6));
         int bad = !(var_c > 0.0) || !(s_var > 0.0);
@@ -132,37 +145,50 @@ k_score(const ScoreArgs p) {
         // score_c(g) = lv_c - iv_c (noise b_g)^2 ;  score_i(g) = lv_i - iv_i (a_i - noise w_i b_g)^2
         const double qa_c = -iv_c * p.noise * p.noise;
         const double* Wc = p.W + int64_t(c) * Np;
-#pragma unroll 2
-        for (int i = lane; i < N32; i += 32) {
-            double qa = 0.0, qb = 0.0, qc = -1e300;                      // padding lane: x = -1e300, never counted, dr = 0
-            if (i < N) {
-                double w = Wc[i];
-                uint32_t bits = szb[i];
-                double zdot = 0.0;
+        for (int i0 = ptid; i0 < N32; i0 += 256) {                       // 4 independent loads in flight per thread
+            double w[4], h0[4], ai[4];
+            uint32_t bits[4];
 #pragma unroll
-                for (int s = 0; s < MAX_SP; ++s)
-                    if (s < Sp) zdot += ((bits >> s) & 1u) ? cs[s] : -cs[s];
-                double var = p.noise * fma(kvar * w, zdot, p.h0[i]);
-                bad |= !(var > 0.0);
-                double iv = 0.5 / var;
-                double lv = -0.5 * log(var) - 0.5 * kLog2Pi;
-                double ai = p.a[i], wi = p.noise * w;
-                qa = c1 * fma(iv * wi, wi, qa_c);                        // b_g^2 coefficient
-                qb = c1 * (-2.0 * iv * ai * wi);                         // b_g coefficient
-                qc = c1 * (fma(iv * ai, ai, lv_c - lv));                 // constant
+            for (int j = 0; j < 4; ++j) {
+                int i = i0 + 64 * j;
+                bool ok = i < N;
+                w[j] = ok ? Wc[i] : 0.0;
+                h0[j] = ok ? p.h0[i] : 1.0;
+                ai[j] = ok ? p.a[i] : 0.0;
+                bits[j] = ok ? p.zb[i] : 0u;
             }
-            sqa[i] = qa; sqb[i] = qb; sqc[i] = qc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int i = i0 + 64 * j;
+                if (i < N32) {
+                    double qa = 0.0, qb = 0.0, qc = -1e300;              // padding: x = -1e300, never counted, dr = 0
+                    if (i < N) {
+                        double zdot = 0.0;
+#pragma unroll
+                        for (int s = 0; s < MAX_SP; ++s)
+                            if (s < Sp) zdot += ((bits[j] >> s) & 1u) ? cs[s] : -cs[s];
+                        double var = p.noise * fma(kvar * w[j], zdot, h0[j]);
+                        bad |= !(var > 0.0);
+                        double iv = 0.5 / var;
+                        double lv = -0.5 * log(var) - 0.5 * kLog2Pi;
+                        double wi = p.noise * w[j];
+                        qa = c1 * fma(iv * wi, wi, qa_c);                // b_g^2 coefficient
+                        qb = c1 * (-2.0 * iv * ai[j] * wi);              // b_g coefficient
+                        qc = c1 * (fma(iv * ai[j], ai[j], lv_c - lv));   // constant
+                    }
+                    sqa[i] = qa; sqb[i] = qb; sqc[i] = qc;
+                }
+            }
         }
-        bad = __any_sync(0xffffffffu, bad);
-        __syncwarp();
         const double cscale = p.cscale ? p.cscale[c] : 1.0;
         const double gsd = sqrt(cscale * s_var);                        // sd of the grid distribution
         const double drc = p.drc ? p.drc[c] : 1.0;
         const double norm = sum_dr + drc;
         const double omega_c = drc / norm;
+        bad = pair_barrier_or(pair, bad);                                 // tables complete; any non-positive variance?
 
-        // ---- phase B + C: 8 grid points per pass ---------------------------------------------------
-        for (int g0 = 0; g0 < G; g0 += SCORE_GPW) {
+        // ---- phase B: 4 grid points per pass, passes alternate between the two warps ----------------
+        for (int g0 = half * SCORE_GPW; g0 < G; g0 += 2 * SCORE_GPW) {
             double bg[SCORE_GPW], sr[SCORE_GPW], sw[SCORE_GPW];
             unsigned cneg[SCORE_GPW];
 #pragma unroll
@@ -182,8 +208,10 @@ k_score(const ScoreArgs p) {
                 constexpr double kC0 = 0.9999999988534117, kC1 = 0.043321698775061875,
                                  kC2 = 0.0009384214835622084, kC3 = 1.3551125681305332e-05;
                 constexpr int kSatHi = 0x408d9000;                        // hiword(946.0)
+                double qa = sqa[lane], qb = sqb[lane], qc = sqc[lane], dr = sdr[lane];
                 for (int i = lane; i < N32; i += 32) {
-                    const double qa = sqa[i], qb = sqb[i], qc = sqc[i], dr = sdr[i];
+                    const int in = (i + 32 < N32) ? i + 32 : lane;        // prefetch the next row's coefficients
+                    const double qa_n = sqa[in], qb_n = sqb[in], qc_n = sqc[in], dr_n = sdr[in];
                     double x[SCORE_GPW];
 #pragma unroll
                     for (int k = 0; k < SCORE_GPW; ++k) {
@@ -223,104 +251,103 @@ k_score(const ScoreArgs p) {
 #pragma unroll
                         for (int k = 0; k < SCORE_GPW; ++k) sw[k] += (__double2hiint(x[k]) >= 0) ? dr : 0.0;
                     }
+                    qa = qa_n; qb = qb_n; qc = qc_n; dr = dr_n;
                 }
             }
-            int cnt[SCORE_GPW];
 #pragma unroll
             for (int k = 0; k < SCORE_GPW; ++k) {
-                cnt[k] = N32 - warp_sum_int(int(cneg[k]));                // #{i <= N : score_c >= score_i}
-                sw[k] = warp_sum(sw[k]);
-                if (SOFT) sr[k] = warp_sum(sr[k]);
-            }
-            // phase C: lane k finishes grid point g0 + k
-            double my_sr = 0.0, my_sw = 0.0, my_bg = 0.0;
-            int my_cnt = 0;
-#pragma unroll
-            for (int k = 0; k < SCORE_GPW; ++k)
-                if (lane == k) { my_sr = sr[k]; my_sw = sw[k]; my_cnt = cnt[k]; my_bg = bg[k]; }
-            const int g = g0 + lane;
-            if (lane < SCORE_GPW && g < G) {
-                double n_g = double(my_cnt + 1);                        // includes the candidate itself
-                double M, rho_self;
-                if (SOFT) {
-                    double scale = n_g / (my_sr + 0.5);                 // self: sigmoid(0) = 1/2
-                    rho_self = 0.5 * scale;
-                    M = scale * (my_sw + 0.5 * drc) / norm;
-                } else {
-                    rho_self = 1.0;
-                    M = (my_sw + drc) / norm;
-                }
-                if (p.randomized) {
-                    double D = fmax(rho_self * omega_c, 1e-6);
-                    double pr = fmin(fmax((M - p.alpha_lvl) / D, 0.0), 1.0);
-                    double u = p.u_rand[int64_t(c) * G + g];
-                    M -= (u < pr) ? 0.0 : D;
-                }
-                double mk = SOFT ? sigmoid_acc((M - p.alpha_lvl) * inv_temp) : ((M > p.alpha_lvl) ? 1.0 : 0.0);
-                double eps = p.eps_grid[p.eps_per_candidate ? int64_t(c) * G + g : g];
-                double yg = mu + gsd * eps;
-                double lp = -0.5 * (eps * eps + log(cscale * s_var) + kLog2Pi);
-                double opt = p.optimistic ? ((yg >= mu) ? 1.0 : 0.0) : 1.0;
-                double shrink = 1.0 - p.noise * inv_s;
-                double rc = p.noise * my_bg;
-                double scc = fma(-rc * rc, iv_c, lv_c);                 // candidate's own conformal score
-                g_mk[g] = mk;
-                g_cw[g] = mk * opt / fmax(exp(lp), 1e-6);
-                g_nc[g] = (1.0 - mk) * opt;
-                g_mf[g] = mu + (yg - mu) * shrink;
-                if (bad) { g_mk[g] = g_cw[g] = g_nc[g] = g_mf[g] = nan(""); mk = lp = scc = nan(""); }
-                if (p.grid) p.grid[int64_t(c) * G + g] = yg;
-                if (p.logp) p.logp[int64_t(c) * G + g] = lp;
-                if (p.mask) p.mask[int64_t(c) * G + g] = mk;
-                if (p.qscore) p.qscore[int64_t(c) * G + g] = scc;
+                int cnt = N32 - warp_sum_int(int(cneg[k]));               // #{i <= N : score_c >= score_i}
+                double tw = warp_sum(sw[k]);
+                double tr = SOFT ? warp_sum(sr[k]) : 0.0;
+                if (lane == 0 && g0 + k < G) { g_cw[g0 + k] = double(cnt); g_nc[g0 + k] = tr; g_mf[g0 + k] = tw; }
             }
         }
-        __syncwarp();
+        pair_barrier(pair);                                               // raw sums of every grid point are in shared memory
 
-        // ---- phase D: integrate over the grid --------------------------------------------------------
-        const double sd_f = sqrt(fmax(p.noise * (1.0 - p.noise * inv_s), 0.0));
-        const int S = p.S;
-        double scw = 0.0, snc = 0.0, nacc = 0.0;
-        for (int g = lane; g < G; g += 32) {
-            scw += g_cw[g]; snc += g_nc[g]; nacc += (g_mk[g] >= 0.5) ? 1.0 : 0.0;
-        }
-        scw = warp_sum(scw); snc = warp_sum(snc); nacc = warp_sum(nacc);
-        const double ood = SOFT ? sigmoid_acc((omega_c - p.alpha_lvl) * inv_temp) : ((omega_c >= p.alpha_lvl) ? 1.0 : 0.0);
-        double tot = 0.0;
-        for (int s = 0; s < S; ++s) {
-            double A = 0.0, B = 0.0;
-            for (int g = lane; g < G; g += 32) {
-                double cw = g_cw[g], nc = g_nc[g], mf = g_mf[g];
-                double f = fma(sd_f, p.eps_mc[int64_t(s) * G + g], mf);
-                double val;
-                if (p.kind == 0) {
-                    if (S > 1) {
-                        double em = 0.0;
-                        for (int s2 = 0; s2 < S; ++s2) em += p.eps_mc[int64_t(s2) * G + g];
-                        double m = fma(sd_f, em / double(S), mf);
-                        val = m + p.beta_prime * fabs(f - m);
-                    } else {
-                        val = f;
-                    }
-                } else {
-                    double xx = f - p.best_f;
-                    if (p.temp > 0.0) { double xt = xx / p.temp; val = p.temp * (fmax(xt, 0.0) + log1p(exp(-fabs(xt)))); }
-                    else val = fmax(xx, 0.0);
-                }
-                A = fma(cw, val, A);
-                B = fma(nc, val, B);
+        // ---- phase C: thread per grid point -----------------------------------------------------------
+        for (int g = ptid; g < G; g += 64) {
+            const double my_cnt = g_cw[g], my_sr = g_nc[g], my_sw = g_mf[g];
+            double n_g = my_cnt + 1.0;                                  // includes the candidate itself
+            double M, rho_self;
+            if (SOFT) {
+                double scale = n_g / (my_sr + 0.5);                     // self: sigmoid(0) = 1/2
+                rho_self = 0.5 * scale;
+                M = scale * (my_sw + 0.5 * drc) / norm;
+            } else {
+                rho_self = 1.0;
+                M = (my_sw + drc) / norm;
             }
-            A = warp_sum(A); B = warp_sum(B);
-            tot += (1.0 - ood) * ((1.0 - p.alpha_lvl) * A / fmax(scw, 1e-6) + p.alpha_lvl * B / fmax(snc, 1e-6));
+            if (p.randomized) {
+                double D = fmax(rho_self * omega_c, 1e-6);
+                double pr = fmin(fmax((M - p.alpha_lvl) / D, 0.0), 1.0);
+                double u = p.u_rand[int64_t(c) * G + g];
+                M -= (u < pr) ? 0.0 : D;
+            }
+            double mk = SOFT ? sigmoid_acc((M - p.alpha_lvl) * inv_temp) : ((M > p.alpha_lvl) ? 1.0 : 0.0);
+            double eps = p.eps_grid[p.eps_per_candidate ? int64_t(c) * G + g : g];
+            double yg = mu + gsd * eps;
+            double lp = -0.5 * (eps * eps + log(cscale * s_var) + kLog2Pi);
+            double opt = p.optimistic ? ((yg >= mu) ? 1.0 : 0.0) : 1.0;
+            double shrink = 1.0 - p.noise * inv_s;
+            double rc = p.noise * (gsd * eps * inv_s);
+            double scc = fma(-rc * rc, iv_c, lv_c);                     // candidate's own conformal score
+            double cw = mk * opt / fmax(exp(lp), 1e-6), nc = (1.0 - mk) * opt, mf = mu + (yg - mu) * shrink;
+            if (bad) { cw = nc = mf = mk = lp = scc = nan(""); }
+            g_mk[g] = mk; g_cw[g] = cw; g_nc[g] = nc; g_mf[g] = mf;
+            if (p.grid) p.grid[int64_t(c) * G + g] = yg;
+            if (p.logp) p.logp[int64_t(c) * G + g] = lp;
+            if (p.mask) p.mask[int64_t(c) * G + g] = mk;
+            if (p.qscore) p.qscore[int64_t(c) * G + g] = scc;
         }
-        if (lane == 0) {
-            p.acq[c] = tot / double(S);
-            if (p.ood) p.ood[c] = ood;
-            if (p.post_mean) p.post_mean[c] = mu;
-            if (p.post_var) p.post_var[c] = s_var;
-            if (p.num_acc) p.num_acc[c] = nacc;
+        pair_barrier(pair);
+
+        // ---- phase D (first warp of the pair): integrate over the grid ---------------------------------
+        if (half == 0) {
+            const double sd_f = sqrt(fmax(p.noise * (1.0 - p.noise * inv_s), 0.0));
+            const int S = p.S;
+            double scw = 0.0, snc = 0.0, nacc = 0.0;
+            for (int g = lane; g < G; g += 32) {
+                scw += g_cw[g]; snc += g_nc[g]; nacc += (g_mk[g] >= 0.5) ? 1.0 : 0.0;
+            }
+            scw = warp_sum(scw); snc = warp_sum(snc); nacc = warp_sum(nacc);
+            const double ood = SOFT ? sigmoid_acc((omega_c - p.alpha_lvl) * inv_temp)
+                                    : ((omega_c >= p.alpha_lvl) ? 1.0 : 0.0);
+            double tot = 0.0;
+            for (int s = 0; s < S; ++s) {
+                double A = 0.0, B = 0.0;
+                for (int g = lane; g < G; g += 32) {
+                    double cw = g_cw[g], nc = g_nc[g], mf = g_mf[g];
+                    double f = fma(sd_f, p.eps_mc[int64_t(s) * G + g], mf);
+                    double val;
+                    if (p.kind == 0) {
+                        if (S > 1) {
+                            double em = 0.0;
+                            for (int s2 = 0; s2 < S; ++s2) em += p.eps_mc[int64_t(s2) * G + g];
+                            double m = fma(sd_f, em / double(S), mf);
+                            val = m + p.beta_prime * fabs(f - m);
+                        } else {
+                            val = f;
+                        }
+                    } else {
+                        double xx = f - p.best_f;
+                        if (p.temp > 0.0) { double xt = xx / p.temp; val = p.temp * (fmax(xt, 0.0) + log1p(exp(-fabs(xt)))); }
+                        else val = fmax(xx, 0.0);
+                    }
+                    A = fma(cw, val, A);
+                    B = fma(nc, val, B);
+                }
+                A = warp_sum(A); B = warp_sum(B);
+                tot += (1.0 - ood) * ((1.0 - p.alpha_lvl) * A / fmax(scw, 1e-6) + p.alpha_lvl * B / fmax(snc, 1e-6));
+            }
+            if (lane == 0) {
+                p.acq[c] = tot / double(S);
+                if (p.ood) p.ood[c] = ood;
+                if (p.post_mean) p.post_mean[c] = mu;
+                if (p.post_var) p.post_var[c] = s_var;
+                if (p.num_acc) p.num_acc[c] = nacc;
+            }
         }
-        __syncwarp();                                     // g-arrays / tables are rewritten by the next candidate
+        // the next candidate's phase A touches only the tables; its barriers order the g-arrays
     }
 }
 
