@@ -86,7 +86,7 @@ def load():
     lib.cbo_gemm_tn_f64.argtypes = [c_dp, C.c_int64, c_dp, C.c_int64, c_dp, C.c_int64, C.c_int64, C.c_int64,
                                     C.c_int64, C.c_int32, c_dp, c_dp]
     lib.cbo_kernel_rows_f64.restype = C.c_int
-    lib.cbo_kernel_rows_f64.argtypes = [C.POINTER(GpF64), c_dp, C.c_int64, c_dp, c_dp, c_dp]
+    lib.cbo_kernel_rows_f64.argtypes = [C.POINTER(GpF64), c_dp, C.c_int64, c_dp, c_dp, c_dp, c_dp]
     lib.cbo_timing_enable.restype = None
     lib.cbo_timing_enable.argtypes = [C.c_int]
     lib.cbo_timing_collect.restype = C.c_int

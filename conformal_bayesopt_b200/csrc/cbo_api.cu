@@ -70,7 +70,7 @@ struct Carver {
 };
 
 struct Workspace {
-    double *zp, *tmp, *T, *a, *h0, *dr_train, *sum_dr;
+    double *zp, *tmp, *T, *a, *h0, *dr_train, *sum_dr, *XsT;
     uint32_t* zb;
     double *UW, *V, *mu, *ut, *drc, *rn;
     double *cscale, *nacc, *stats;      // refinement only
@@ -83,7 +83,7 @@ int64_t pick_chunk(int64_t b, const cbo_params* p, int64_t chunk) {
     return chunk < b ? chunk : b;
 }
 
-Workspace carve(void* ws, int64_t N, int64_t b, const cbo_params* p, int64_t chunk) {
+Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, int64_t chunk) {
     const int64_t Np = cbo_padded_n(N), Sp = p->num_probes, C = pick_chunk(b, p, chunk);
     const int64_t tiles_n = Np / cbo::GEMM_BN;
     Carver c(ws);
@@ -96,6 +96,7 @@ Workspace carve(void* ws, int64_t N, int64_t b, const cbo_params* p, int64_t chu
     w.dr_train = c.take<double>(Np);
     w.sum_dr = c.take<double>(8);
     w.zb = c.take<uint32_t>(Np);
+    w.XsT = c.take<double>(Np * d);
     w.UW = c.take<double>(C * Np);
     w.V = c.take<double>(C * Np);
     w.mu = c.take<double>(C);
@@ -211,9 +212,8 @@ const char* cbo_last_cuda_error(void) { return g_last_err; }
 int64_t cbo_padded_n(int64_t N) { return (N + 127) / 128 * 128; }
 
 size_t cbo_workspace_bytes(int64_t N, int64_t d, int64_t b, const cbo_params* params, int64_t chunk) {
-    (void)d;
     if (!params || N <= 0 || b <= 0) return 0;
-    return carve(nullptr, N, b, params, chunk).bytes;
+    return carve(nullptr, N, d, b, params, chunk).bytes;
 }
 
 int cbo_gemm_tn_f64(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
@@ -226,15 +226,19 @@ int cbo_gemm_tn_f64(const double* A, int64_t lda, const double* B, int64_t ldb, 
     return CBO_OK;
 }
 
-int cbo_kernel_rows_f64(const cbo_gp_f64* gp, const double* Xq, int64_t n, double* U, double* mu, void* stream) {
-    if (!gp || !Xq || !U || n <= 0) return CBO_ERR_INVALID_ARG;
+int cbo_kernel_rows_f64(const cbo_gp_f64* gp, const double* Xq, int64_t n, double* U, double* mu, double* scratch,
+                        void* stream) {
+    if (!gp || !Xq || !U || !scratch || n <= 0) return CBO_ERR_INVALID_ARG;
     if (gp->d > cbo::MAX_D) return CBO_ERR_UNSUPPORTED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int per_block = cbo::ROWS_WARPS * cbo::ROWS_CPW;
     int blocks = (int)((n + per_block - 1) / per_block);
-    size_t smem = sizeof(double) * per_block * gp->d;
-    cbo::k_kernel_rows<<<blocks, cbo::ROWS_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-        Xq, (int)n, gp->X, (int)gp->N, (int)gp->Np, (int)gp->d, gp->inv_lengthscale, gp->outputscale, gp->mean,
-        gp->alpha, nullptr, 0, U, mu, nullptr);
+    size_t smem = sizeof(double) * (16 + per_block * gp->d);
+    cbo::k_scale_transpose<<<(int)((gp->Np * gp->d + 255) / 256), 256, 0, s>>>(gp->X, (int)gp->N, (int)gp->Np, (int)gp->d,
+                                                                             gp->inv_lengthscale, scratch);
+    cbo::k_kernel_rows<<<blocks, cbo::ROWS_WARPS * 32, smem, s>>>(Xq, (int)n, scratch, (int)gp->N, (int)gp->Np,
+                                                                  (int)gp->d, gp->inv_lengthscale, gp->outputscale,
+                                                                  gp->mean, gp->alpha, nullptr, 0, U, mu, nullptr);
     CBO_CUDA(cudaGetLastError());
     return CBO_OK;
 }
@@ -270,7 +274,7 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
     if (p->randomized && !u_rand) return CBO_ERR_INVALID_ARG;
     if (ratio && (ratio->hidden < 1 || ratio->hidden > cbo::MAX_H)) return CBO_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(workspace) % kAlign) return CBO_ERR_WORKSPACE;
-    Workspace w = carve(workspace, gp->N, b, p, chunk);
+    Workspace w = carve(workspace, gp->N, gp->d, b, p, chunk);
     if (w.bytes > workspace_bytes) return CBO_ERR_WORKSPACE;
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -280,7 +284,8 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
 
     // ---- per-call tables: T = A^-1 z[:N], dr_train, a, h0, zb, sum_dr -------------------------------
     {
-    TimeScope ts_(T_PREP, s, 5);
+    TimeScope ts_(T_PREP, s, 6);
+    cbo::k_scale_transpose<<<(Np * d + 255) / 256, 256, 0, s>>>(gp->X, N, Np, d, gp->inv_lengthscale, w.XsT);
     cbo::k_pad_probes<<<(Np * Sp + 255) / 256, 256, 0, s>>>(z, N, Np, Sp, w.zp);
     cbo::k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(gp->linv, Np, w.zp, Sp, w.tmp, 0, 1);
     cbo::k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(gp->linv_t, Np, w.tmp, Sp, w.T, 1, 0);
@@ -303,7 +308,7 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
             TimeScope ts_(T_ROWS, s, ratio ? 2 : 1);
             const int per_block = cbo::ROWS_WARPS * cbo::ROWS_CPW;
             cbo::k_kernel_rows<<<(n + per_block - 1) / per_block, cbo::ROWS_WARPS * 32,
-                                 sizeof(double) * per_block * d, s>>>(Xc, n, gp->X, N, Np, d, gp->inv_lengthscale,
+                                 sizeof(double) * (16 + per_block * d), s>>>(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale,
                                                                       gp->outputscale, gp->mean, gp->alpha, w.T, Sp,
                                                                       w.UW, w.mu, w.ut);
             if (ratio)

@@ -59,7 +59,9 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;                 // 2 x 4 warps
+    // 2 x 4 warps.  Warps w and w+4 share an SM sub-partition (w % 4): give them n-slices wn and 3-wn so that the
+    // triangular skipping on the diagonal block (below) loads every sub-partition's fp64 pipe equally.
+    const int wm = warp >> 2, wn = (warp < 4) ? warp : 7 - warp;
     const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
     const int tiles_n = Nn / GEMM_BN;
     // longest-K tiles first: lower -> last n-tile first; upper / full -> first n-tile first
@@ -100,6 +102,13 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
                 gemm_load_stage(sA, sA + GEMM_BM * GEMM_LDS, A, lda, B, ldb, m0, n0, k_begin + nt * GEMM_BK, M, tid);
             }
             cp_async_commit();
+        }
+        // On the diagonal 128 x 128 block of the triangular factor this warp's 32 columns see only zeros for part of
+        // the K range: lower  -> k < n_warp_end,  upper -> k + BK > n_warp_begin.  Skip those MMAs (warp-uniform).
+        {
+            const int k0 = k_begin + kt * GEMM_BK;
+            if (tri == TRI_LOWER && k0 >= n0 + 32 * (wn + 1)) continue;
+            if (tri == TRI_UPPER && k0 + GEMM_BK <= n0 + 32 * wn) continue;
         }
         const double* sA = smem + (kt % GEMM_STAGES) * GEMM_STAGE_DOUBLES + (wm * 64 + fr) * GEMM_LDS + fk;
         const double* sB = smem + (kt % GEMM_STAGES) * GEMM_STAGE_DOUBLES + GEMM_BM * GEMM_LDS +

@@ -56,10 +56,10 @@ struct ScoreArgs {
     double* post_mean; double* post_var; double* num_acc;
 };
 
-// shared: tab[16] | dr[Np]        per pair: qa, qb, qc [Np] | 4 x [G] (raw cnt/sr/sw, then cw/nc/mf/mk)
+// shared: tab[16] | dr[Np]        per pair: qa, qb, qc [Np] | 4 x [G] (raw cnt/sr/sw, then cw/nc/mf/mk) | zt[4][16]
 __host__ __device__ inline size_t score_smem_shared_bytes(int Np) { return sizeof(double) * (16 + size_t(Np)); }
 __host__ __device__ inline size_t score_smem_pair_bytes(int Np, int G) {
-    return sizeof(double) * (3 * size_t(Np) + 4 * size_t(G));
+    return sizeof(double) * (3 * size_t(Np) + 4 * size_t(G) + 64);
 }
 __host__ __device__ inline size_t score_smem_bytes(int Np, int G, int npairs) {
     return score_smem_shared_bytes(Np) + size_t(npairs) * score_smem_pair_bytes(Np, G);
@@ -98,7 +98,7 @@ k_score(const ScoreArgs p) {
 
     double* tab = sm;                                   // 2^(j/16): one 128-byte row, conflict-free for any index pattern
     double* sdr = tab + 16;                             // density ratio of train point i (0 beyond N)
-    double* pbase = sdr + Np + size_t(pair) * (3 * size_t(Np) + 4 * size_t(G));
+    double* pbase = sdr + Np + size_t(pair) * (3 * size_t(Np) + 4 * size_t(G) + 64);
     double* sqa = pbase;
     double* sqb = sqa + Np;
     double* sqc = sqb + Np;
@@ -106,6 +106,7 @@ k_score(const ScoreArgs p) {
     double* g_nc = g_cw + G;                            // sum rho        -> non-conformal weight
     double* g_mf = g_nc + G;                            // sum rho * dr   -> refit mean
     double* g_mk = g_mf + G;                            // mask
+    double* zt = g_mk + G;                              // zt[t][e] = sum_{b<4} (+-) c_{4t+b}, sign from bit b of e
 
     // ---- once per CTA: candidate-independent tables ------------------------------------------------
     if (tid < 16) tab[tid] = exp2(double(tid) / 16.0);
@@ -130,13 +131,23 @@ k_score(const ScoreArgs p) {
         const double s_var = p.kappa + p.noise - vnorm;                 // Schur complement (noisy predictive variance)
         const double mu = p.mu[c];
         const double inv_s = 1.0 / s_var;
-        double cs[MAX_SP];
         double zcc = 0.0;                                               // sum_s z_cs c_s
+        for (int s = 0; s < Sp; ++s) {
+            double zcs = p.z_cand[s];
+            zcc = fma(zcs, (zcs - p.ut[int64_t(c) * Sp + s]) * inv_s, zcc);
+        }
+        {   // nibble tables of z_i . c (z_i in {+-1}^Sp is stored as a bit mask): one entry per thread
+            const int t4 = (ptid >> 4) * 4, e = ptid & 15;
+            double acc = 0.0;
 #pragma unroll
-        for (int s = 0; s < MAX_SP; ++s) {
-            double zcs = (s < Sp) ? p.z_cand[s] : 0.0;
-            cs[s] = (s < Sp) ? (zcs - p.ut[int64_t(c) * Sp + s]) * inv_s : 0.0;
-            zcc = fma(zcs, cs[s], zcc);
+            for (int bb = 0; bb < 4; ++bb) {
+                int s = t4 + bb;
+                if (s < Sp) {
+                    double csv = (p.z_cand[s] - p.ut[int64_t(c) * Sp + s]) * inv_s;
+                    acc += ((e >> bb) & 1) ? csv : -csv;
+                }
+            }
+            zt[ptid] = acc;
         }
         const double var_c = p.noise * (1.0 + (double(Sp) - p.noise * zcc) / (double(Sp) + 1e-6));
         int bad = !(var_c > 0.0) || !(s_var > 0.0);
@@ -145,6 +156,7 @@ k_score(const ScoreArgs p) {
         // score_c(g) = lv_c - iv_c (noise b_g)^2 ;  score_i(g) = lv_i - iv_i (a_i - noise w_i b_g)^2
         const double qa_c = -iv_c * p.noise * p.noise;
         const double* Wc = p.W + int64_t(c) * Np;
+        pair_barrier(pair);                                              // nibble tables visible
         for (int i0 = ptid; i0 < N32; i0 += 256) {                       // 4 independent loads in flight per thread
             double w[4], h0[4], ai[4];
             uint32_t bits[4];
@@ -163,14 +175,14 @@ k_score(const ScoreArgs p) {
                 if (i < N32) {
                     double qa = 0.0, qb = 0.0, qc = -1e300;              // padding: x = -1e300, never counted, dr = 0
                     if (i < N) {
-                        double zdot = 0.0;
-#pragma unroll
-                        for (int s = 0; s < MAX_SP; ++s)
-                            if (s < Sp) zdot += ((bits[j] >> s) & 1u) ? cs[s] : -cs[s];
+                        double zdot = zt[bits[j] & 15] + zt[16 + ((bits[j] >> 4) & 15)];
+                        if (Sp > 8) zdot += zt[32 + ((bits[j] >> 8) & 15)] + zt[48 + ((bits[j] >> 12) & 15)];
                         double var = p.noise * fma(kvar * w[j], zdot, h0[j]);
-                        bad |= !(var > 0.0);
-                        double iv = 0.5 / var;
-                        double lv = -0.5 * log(var) - 0.5 * kLog2Pi;
+                        bool okv = var > 0.0;
+                        bad |= !okv;
+                        var = okv ? var : 1.0;                           // flagged: the candidate's outputs become NaN
+                        double iv = 0.5 * rcp_full(var);
+                        double lv = -0.5 * log_fast(var) - 0.5 * kLog2Pi;
                         double wi = p.noise * w[j];
                         qa = c1 * fma(iv * wi, wi, qa_c);                // b_g^2 coefficient
                         qb = c1 * (-2.0 * iv * ai[j] * wi);              // b_g coefficient

@@ -144,8 +144,9 @@ int cbo_ratio_forward_f64(const cbo_ratio_mlp_f64* ratio, const double* x, int64
  * rownorm_partial (M x Nn/128) receives per-tile sums of squares of C when non-NULL. */
 int cbo_gemm_tn_f64(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                     int64_t M, int64_t Nn, int64_t K, int32_t tri, double* rownorm_partial, void* stream);
-/* U[c, i] = k(x_c, X_i) (Np-padded rows, zeros beyond N); mu[c] = mean + u.alpha. */
-int cbo_kernel_rows_f64(const cbo_gp_f64* gp, const double* Xq, int64_t n, double* U, double* mu, void* stream);
+/* U[c, i] = k(x_c, X_i) (Np-padded rows, zeros beyond N); mu[c] = mean + u.alpha.  scratch: d x Np doubles. */
+int cbo_kernel_rows_f64(const cbo_gp_f64* gp, const double* Xq, int64_t n, double* U, double* mu, double* scratch,
+                        void* stream);
 
 /* Optional per-kernel-class timing with CUDA events on the caller's stream (bench.py's roofline leg).
  * Classes: 0 per-call tables, 1 kernel rows (+candidate ratio MLP), 2 GEMM pass 1, 3 GEMM pass 2, 4 score. */
