@@ -231,14 +231,10 @@ int cbo_kernel_rows_f64(const cbo_gp_f64* gp, const double* Xq, int64_t n, doubl
     if (!gp || !Xq || !U || !scratch || n <= 0) return CBO_ERR_INVALID_ARG;
     if (gp->d > cbo::MAX_D) return CBO_ERR_UNSUPPORTED;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int per_block = cbo::ROWS_WARPS * cbo::ROWS_CPW;
-    int blocks = (int)((n + per_block - 1) / per_block);
-    size_t smem = sizeof(double) * (16 + per_block * gp->d);
     cbo::k_scale_transpose<<<(int)((gp->Np * gp->d + 255) / 256), 256, 0, s>>>(gp->X, (int)gp->N, (int)gp->Np, (int)gp->d,
                                                                              gp->inv_lengthscale, scratch);
-    cbo::k_kernel_rows<<<blocks, cbo::ROWS_WARPS * 32, smem, s>>>(Xq, (int)n, scratch, (int)gp->N, (int)gp->Np,
-                                                                  (int)gp->d, gp->inv_lengthscale, gp->outputscale,
-                                                                  gp->mean, gp->alpha, nullptr, 0, U, mu, nullptr);
+    CBO_CUDA(cbo::launch_kernel_rows(Xq, (int)n, scratch, (int)gp->N, (int)gp->Np, (int)gp->d, gp->inv_lengthscale,
+                                     gp->outputscale, gp->mean, gp->alpha, nullptr, 0, U, mu, nullptr, num_sms(), s));
     CBO_CUDA(cudaGetLastError());
     return CBO_OK;
 }
@@ -306,11 +302,8 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
         // ---- kernel rows, mu, u^T T; candidate density ratios -------------------------------------
         {
             TimeScope ts_(T_ROWS, s, ratio ? 2 : 1);
-            const int per_block = cbo::ROWS_WARPS * cbo::ROWS_CPW;
-            cbo::k_kernel_rows<<<(n + per_block - 1) / per_block, cbo::ROWS_WARPS * 32,
-                                 sizeof(double) * (16 + per_block * d), s>>>(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale,
-                                                                      gp->outputscale, gp->mean, gp->alpha, w.T, Sp,
-                                                                      w.UW, w.mu, w.ut);
+            CBO_CUDA(cbo::launch_kernel_rows(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->mean,
+                                             gp->alpha, w.T, Sp, w.UW, w.mu, w.ut, num_sms(), s));
             if (ratio)
                 cbo::k_ratio_mlp<<<(n + 127) / 128, 128, 0, s>>>(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1,
                                                                   ratio->W2, ratio->b2, ratio->W3, ratio->b3, 1e-6,

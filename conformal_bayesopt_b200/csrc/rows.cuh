@@ -12,7 +12,7 @@
 namespace cbo {
 
 constexpr int ROWS_CPW = 4;          // candidates per warp
-constexpr int ROWS_WARPS = 8;
+constexpr int ROWS_WARPS = 16;
 constexpr int MAX_D = 64;
 constexpr int MAX_SP = 16;
 constexpr int MAX_H = 64;
@@ -64,91 +64,147 @@ __global__ void k_scale_transpose(const double* __restrict__ X, int N, int Np, i
     XsT[e] = (i < N) ? X[int64_t(i) * d + k] * inv_ls[k] : 0.0;
 }
 
-// One warp owns ROWS_CPW candidates and sweeps i = lane, lane+32, ...; the scaled training coordinates are read
-// lane-contiguously from XsT (L1-resident) once per sweep step and reused for the ROWS_CPW candidates; U stores are
-// 256-byte coalesced.  ~49 fp64 ops per kernel value (distance 2d, sqrt 7, exp 12, Matern poly 4, mu / u^T T 1 + Sp).
-__global__ void __launch_bounds__(ROWS_WARPS * 32)
-k_kernel_rows(const double* __restrict__ Xq, int n, const double* __restrict__ XsT, int N, int Np, int d,
+// Persistent CTAs of 16 warps; the scaled, transposed training inputs XsT (d x Np), alpha and the probe solves T^T
+// (Sp x Np) are staged in shared memory once per CTA (STAGE) so that the sweep never waits on L2.  One warp owns
+// ROWS_CPW candidates at a time and sweeps i = lane, lane+32, ...: X_i is read once per sweep step (conflict-free,
+// lane-contiguous) and reused for the ROWS_CPW candidates; U stores are 256-byte coalesced streaming stores.
+// ~41 + NSP fp64 ops per kernel value (distance 2d, sqrt 7, exp 12, Matern polynomial 4, mu 1, u^T T NSP).
+template <bool STAGE, int NSP>
+__global__ void __launch_bounds__(ROWS_WARPS * 32, 1)
+k_kernel_rows(const double* __restrict__ Xq, int n, const double* __restrict__ XsT_g, int N, int Np, int d,
               const double* __restrict__ inv_ls, double outputscale, double mean,
-              const double* __restrict__ alpha, const double* __restrict__ T, int Sp,
+              const double* __restrict__ alpha_g, const double* __restrict__ T, int Sp,
               double* __restrict__ U, double* __restrict__ mu, double* __restrict__ ut) {
-    extern __shared__ double sx[];                      // tab[16] | [ROWS_WARPS][ROWS_CPW][d] scaled candidate coords
+    extern __shared__ double sx[];  // tab[16] | [WARPS][CPW][d] coords | (STAGE) alpha[Np] | XsT[d][Np] | TT[Sp][Np]
     double* tab = sx;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = (blockIdx.x * ROWS_WARPS + warp) * ROWS_CPW;
     double* myx = sx + 16 + warp * ROWS_CPW * d;
+    double* s_alpha = sx + 16 + ROWS_WARPS * ROWS_CPW * d;
+    double* s_xst = s_alpha + Np;
+    double* s_tt = s_xst + size_t(d) * Np;
+    const bool want_ut = (T != nullptr) && (ut != nullptr);
     if (threadIdx.x < 16) tab[threadIdx.x] = exp2(double(threadIdx.x) / 16.0);
-    for (int e = lane; e < ROWS_CPW * d; e += 32) {
-        int cc = e / d, k = e - cc * d;
-        int c = min(c0 + cc, n - 1);
-        myx[e] = Xq[int64_t(c) * d + k] * inv_ls[k];
+    if (STAGE) {
+        for (int e = threadIdx.x; e < Np; e += blockDim.x) s_alpha[e] = alpha_g[e];
+        for (int e = threadIdx.x; e < d * Np; e += blockDim.x) s_xst[e] = XsT_g[e];
+        if (want_ut)
+            for (int e = threadIdx.x; e < Sp * Np; e += blockDim.x) {
+                int s = e / Np, i = e - s * Np;
+                s_tt[e] = T[int64_t(i) * Sp + s];
+            }
     }
     __syncthreads();
-    if (c0 >= n) return;
-
-    double acc_mu[ROWS_CPW];
-    double acc_ut[ROWS_CPW][MAX_SP];
+    const double* __restrict__ XsT = STAGE ? s_xst : XsT_g;
+    const double* __restrict__ alpha = STAGE ? s_alpha : alpha_g;
+    const int groups = (n + ROWS_CPW - 1) / ROWS_CPW;
+    for (int grp = blockIdx.x * ROWS_WARPS + warp; grp < groups; grp += gridDim.x * ROWS_WARPS) {
+        const int c0 = grp * ROWS_CPW;
+        __syncwarp();
+        for (int e = lane; e < ROWS_CPW * d; e += 32) {
+            int cc = e / d, k = e - cc * d;
+            int c = min(c0 + cc, n - 1);
+            myx[e] = Xq[int64_t(c) * d + k] * inv_ls[k];
+        }
+        __syncwarp();
+        double acc_mu[ROWS_CPW], acc_ut[ROWS_CPW][NSP];
 #pragma unroll
-    for (int cc = 0; cc < ROWS_CPW; ++cc) {
-        acc_mu[cc] = 0.0;
+        for (int cc = 0; cc < ROWS_CPW; ++cc) {
+            acc_mu[cc] = 0.0;
 #pragma unroll
-        for (int s = 0; s < MAX_SP; ++s) acc_ut[cc][s] = 0.0;
-    }
-    for (int i = lane; i < Np; i += 32) {
-        double kv[ROWS_CPW];
-        if (i < N) {
-            double r2[ROWS_CPW];
+            for (int s = 0; s < NSP; ++s) acc_ut[cc][s] = 0.0;
+        }
+        for (int i = lane; i < Np; i += 32) {
+            double kv[ROWS_CPW];
+            if (i < N) {
+                double r2[ROWS_CPW];
 #pragma unroll
-            for (int cc = 0; cc < ROWS_CPW; ++cc) r2[cc] = 0.0;
+                for (int cc = 0; cc < ROWS_CPW; ++cc) r2[cc] = 0.0;
 #pragma unroll 4
-            for (int k = 0; k < d; ++k) {
-                double xi = XsT[int64_t(k) * Np + i];
+                for (int k = 0; k < d; ++k) {
+                    double xi = XsT[k * Np + i];
+#pragma unroll
+                    for (int cc = 0; cc < ROWS_CPW; ++cc) {
+                        double df = myx[cc * d + k] - xi;
+                        r2[cc] = fma(df, df, r2[cc]);
+                    }
+                }
+                double al = alpha[i];
 #pragma unroll
                 for (int cc = 0; cc < ROWS_CPW; ++cc) {
-                    double df = myx[cc * d + k] - xi;
-                    r2[cc] = fma(df, df, r2[cc]);
+                    double t = kSqrt5 * sqrt_fast(fmax(r2[cc], 1e-30));      // sqrt5 * r
+                    double pm = fma(fma(t, 1.0 / 3.0, 1.0), t, 1.0);          // 1 + sqrt5 r + 5/3 r^2
+                    kv[cc] = (outputscale * exp_neg_fast(t, tab)) * pm;
+                    acc_mu[cc] = fma(kv[cc], al, acc_mu[cc]);
                 }
-            }
-            double al = alpha[i];
+                if (want_ut) {
 #pragma unroll
-            for (int cc = 0; cc < ROWS_CPW; ++cc) {
-                double t = kSqrt5 * sqrt_fast(fmax(r2[cc], 1e-30));      // sqrt5 * r
-                double pm = fma(fma(t, 1.0 / 3.0, 1.0), t, 1.0);          // 1 + sqrt5 r + 5/3 r^2
-                kv[cc] = (outputscale * exp_neg_fast(t, tab)) * pm;
-                acc_mu[cc] = fma(kv[cc], al, acc_mu[cc]);
-            }
-            if (T != nullptr) {
+                    for (int s = 0; s < NSP; ++s) {
+                        if (s < Sp) {
+                            double ts = STAGE ? s_tt[s * Np + i] : T[int64_t(i) * Sp + s];
 #pragma unroll
-                for (int s = 0; s < MAX_SP; ++s) {
+                            for (int cc = 0; cc < ROWS_CPW; ++cc) acc_ut[cc][s] = fma(kv[cc], ts, acc_ut[cc][s]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < ROWS_CPW; ++cc) kv[cc] = 0.0;
+            }
+#pragma unroll
+            for (int cc = 0; cc < ROWS_CPW; ++cc)
+                if (c0 + cc < n) __stcs(U + int64_t(c0 + cc) * Np + i, kv[cc]);
+        }
+#pragma unroll
+        for (int cc = 0; cc < ROWS_CPW; ++cc) {
+            double m = warp_sum(acc_mu[cc]);
+            if (lane == 0 && c0 + cc < n && mu != nullptr) mu[c0 + cc] = mean + m;
+            if (want_ut) {
+#pragma unroll
+                for (int s = 0; s < NSP; ++s) {
                     if (s < Sp) {
-                        double ts = T[int64_t(i) * Sp + s];
-#pragma unroll
-                        for (int cc = 0; cc < ROWS_CPW; ++cc) acc_ut[cc][s] = fma(kv[cc], ts, acc_ut[cc][s]);
+                        double v = warp_sum(acc_ut[cc][s]);
+                        if (lane == 0 && c0 + cc < n) ut[int64_t(c0 + cc) * Sp + s] = v;
                     }
                 }
             }
-        } else {
-#pragma unroll
-            for (int cc = 0; cc < ROWS_CPW; ++cc) kv[cc] = 0.0;
-        }
-#pragma unroll
-        for (int cc = 0; cc < ROWS_CPW; ++cc)
-            if (c0 + cc < n) U[int64_t(c0 + cc) * Np + i] = kv[cc];
-    }
-#pragma unroll
-    for (int cc = 0; cc < ROWS_CPW; ++cc) {
-        double m = warp_sum(acc_mu[cc]);
-        if (lane == 0 && c0 + cc < n && mu != nullptr) mu[c0 + cc] = mean + m;
-        if (ut != nullptr) {
-#pragma unroll
-            for (int s = 0; s < MAX_SP; ++s) {
-                if (s < Sp) {
-                    double v = warp_sum(acc_ut[cc][s]);
-                    if (lane == 0 && c0 + cc < n) ut[int64_t(c0 + cc) * Sp + s] = v;
-                }
-            }
         }
     }
+}
+
+inline size_t rows_smem_bytes(int Np, int d, int Sp, bool stage) {
+    return sizeof(double) * (16 + size_t(ROWS_WARPS) * ROWS_CPW * d + (stage ? size_t(Np) * (d + 1 + Sp) : 0));
+}
+
+template <bool STAGE, int NSP>
+inline cudaError_t launch_kernel_rows_t(const double* Xq, int n, const double* XsT, int N, int Np, int d,
+                                        const double* inv_ls, double outputscale, double mean, const double* alpha,
+                                        const double* T, int Sp, double* U, double* mu, double* ut, int num_sms,
+                                        cudaStream_t st) {
+    const size_t smem = rows_smem_bytes(Np, d, (T && ut) ? Sp : 0, STAGE);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_kernel_rows<STAGE, NSP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int groups = (n + ROWS_CPW - 1) / ROWS_CPW;
+    int grid = (groups + ROWS_WARPS - 1) / ROWS_WARPS;
+    if (grid > num_sms) grid = num_sms;                              // persistent: one 16-warp CTA per SM
+    k_kernel_rows<STAGE, NSP><<<grid, ROWS_WARPS * 32, smem, st>>>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, mean, alpha,
+                                                                   T, Sp, U, mu, ut);
+    return cudaGetLastError();
+}
+
+inline cudaError_t launch_kernel_rows(const double* Xq, int n, const double* XsT, int N, int Np, int d,
+                                      const double* inv_ls, double outputscale, double mean, const double* alpha,
+                                      const double* T, int Sp, double* U, double* mu, double* ut, int num_sms,
+                                      cudaStream_t st) {
+    const bool stage = rows_smem_bytes(Np, d, (T && ut) ? Sp : 0, true) <= 220 * 1024;
+#define CBO_ROWS_DISPATCH(ST, NS) \
+    return launch_kernel_rows_t<ST, NS>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, mean, alpha, T, Sp, U, mu, ut, num_sms, st)
+    if (stage) { if (Sp <= 8) CBO_ROWS_DISPATCH(true, 8); else CBO_ROWS_DISPATCH(true, 16); }
+    else       { if (Sp <= 8) CBO_ROWS_DISPATCH(false, 8); else CBO_ROWS_DISPATCH(false, 16); }
+#undef CBO_ROWS_DISPATCH
 }
 
 // Thread per point.  w = min(p, 1-1e-6) / max(1-p, 1e-6), p = sigmoid(MLP(x)).  clamp_min(1e-6) of the

@@ -45,7 +45,7 @@ struct ScoreArgs {
     const double* W;        // n_cand x Np
     const double* rn_partial;  // n_cand x tiles_n   partial ||v||^2
     const double* mu;       // n_cand
-    const double* ut;       // n_cand x Sp
+    const double* ut;       // n_cand x Sp   u^T T_s
     const double* drc;      // n_cand (already clamp_min 1e-6) or nullptr -> 1
     const double* cscale;   // n_cand grid covariance scale or nullptr -> 1
     const double* eps_grid; // G or n_cand x G
@@ -131,6 +131,7 @@ k_score(const ScoreArgs p) {
         const double s_var = p.kappa + p.noise - vnorm;                 // Schur complement (noisy predictive variance)
         const double mu = p.mu[c];
         const double inv_s = 1.0 / s_var;
+        const double* Wc = p.W + int64_t(c) * Np;
         double zcc = 0.0;                                               // sum_s z_cs c_s
         for (int s = 0; s < Sp; ++s) {
             double zcs = p.z_cand[s];
@@ -155,8 +156,7 @@ k_score(const ScoreArgs p) {
         const double lv_c = -0.5 * log(var_c) - 0.5 * kLog2Pi;
         // score_c(g) = lv_c - iv_c (noise b_g)^2 ;  score_i(g) = lv_i - iv_i (a_i - noise w_i b_g)^2
         const double qa_c = -iv_c * p.noise * p.noise;
-        const double* Wc = p.W + int64_t(c) * Np;
-        pair_barrier(pair);                                              // nibble tables visible
+        pair_barrier(pair);                                              // nibble tables visible 
         for (int i0 = ptid; i0 < N32; i0 += 256) {                       // 4 independent loads in flight per thread
             double w[4], h0[4], ai[4];
             uint32_t bits[4];
