@@ -1,0 +1,138 @@
+"""Conformal acquisition classes with the reference's interface (conformalbo/acquisitions.py).
+
+`forward(X: b x q x d) -> Tensor(b)` is one call into libcbo: the fused kernels take over
+`ConformalAcquisition._conformal_fwd` as a whole (construct_conformal_bands + the refit-model
+`_nonconformal_fwd` + `_conformal_integration`).  Constructor keywords follow the
+reference (acquisitions.py:80-86, 107-113, 143-149) and the BoTorch bases it mixes in
+(`model`, `beta` / `best_f`, `sampler`, `objective`, `posterior_transform`, `X_pending`).
+
+Not built yet (raise, never silently fall back): q > 1 (incl. X_pending), non-identity
+objectives / posterior transforms, autograd through `forward`.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .helpers import _ratio_weights, as_state, draw_probes
+from .sampling import IIDNormalSampler
+
+
+class ConformalAcquisition(nn.Module):
+    """Mixin state of acquisitions.py:29-39 plus the BoTorch MC-acquisition attributes the callers probe
+    (`model`, `X_pending`, `set_X_pending`, `ratio_estimator`; conformalbo/utils.py:243, optim/optimize.py:214)."""
+
+    _kind = None
+
+    def __init__(self, alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic=False,
+                 grid_sampler=None, randomized=False, *, model=None, sampler=None, objective=None,
+                 posterior_transform=None, X_pending=None):
+        super().__init__()
+        if objective is not None or posterior_transform is not None:
+            raise NotImplementedError("only the identity objective / no posterior transform are built")
+        self.alpha = alpha
+        self.temp = temp
+        self.grid_res = grid_res
+        self.max_grid_refinements = max_grid_refinements
+        self.ratio_estimator = ratio_estimator
+        self.optimistic = optimistic
+        self.randomized = randomized
+        self.grid_sampler = IIDNormalSampler(grid_res) if grid_sampler is None else grid_sampler
+        self.model = model
+        # every conformal hydra config uses IIDNormalSampler(num_samples=1, batch_range=(0,-3)) (acq_fn/c*.yaml)
+        self.sampler = IIDNormalSampler(1, batch_range=(0, -3)) if sampler is None else sampler
+        self.X_pending = None
+        self.set_X_pending(X_pending)
+        self.fixed_probes: Optional[torch.Tensor] = None      # inject z; None: fresh CPU draw per call
+        self.fixed_uniforms: Optional[torch.Tensor] = None    # inject the Bernoulli uniforms (App. C-3)
+        self.last_outputs = {}
+
+    def set_X_pending(self, X_pending=None):
+        self.X_pending = None if X_pending is None else X_pending.detach().clone()
+
+    # --- the reference's hooks, kept for API parity -------------------------------------------------------
+    def _conformalize_model(self, X):
+        if self.model is None:
+            raise AttributeError("ConformalAcquisition must be subclassed")     # acquisitions.py:42-43
+        from .helpers import construct_conformal_bands
+        return construct_conformal_bands(self.model, X, self.alpha, self.temp, self.grid_res, self.max_grid_refinements,
+                                         self.grid_sampler, self.ratio_estimator, mask_ood=True,
+                                         randomized=self.randomized, probes=self.fixed_probes, u_rand=self.fixed_uniforms)
+
+    def _acq_params(self):
+        raise NotImplementedError("ConformalAcquisition must be subclassed")     # acquisitions.py:50-51
+
+    def _conformal_fwd(self, X: torch.Tensor, outputs=()) -> torch.Tensor:
+        if self.model is None:
+            raise AttributeError("ConformalAcquisition must be subclassed")
+        if X.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("d acq / d X is not built yet (SURVEY.md §8f-1); call under torch.no_grad()")
+        state = as_state(self.model)
+        if X.ndim == 2:                                          # t_batch_mode_transform: add the t-batch dim
+            X = X.unsqueeze(0)
+        if self.X_pending is not None:                           # concatenate_pending_points
+            X = torch.cat([X, self.X_pending.to(X).expand(*X.shape[:-2], -1, -1)], dim=-2)
+        lead, (q, d) = X.shape[:-2], X.shape[-2:]
+        dev = X.device
+        Xf = X.reshape(-1, q, d)
+        b, G = Xf.shape[0], self.grid_res
+        self.grid_sampler._sample_shape = torch.Size([G])
+        if self.grid_sampler.collapse_batch_dims:
+            eps = self.grid_sampler.draw((G, q), dev)
+            eps = eps[:, 0] if q == 1 else eps
+        else:
+            eps = self.grid_sampler.draw((G, b, q), dev).movedim(0, 1)[:, :, 0].contiguous()
+        S = int(self.sampler.sample_shape[0])
+        eps_mc = self.sampler.draw((S, G, q), dev)[:, :, 0].contiguous()
+        z = (self.fixed_probes if self.fixed_probes is not None else draw_probes(state.N + q)).to(dev)
+        u = self.fixed_uniforms
+        if self.randomized and u is None:
+            u = torch.rand(b, G, dtype=torch.float64, device=dev)
+        out = ops.conformal_acq(state, Xf, eps_grid=eps, z=z, eps_mc=eps_mc, u_rand=u,
+                                ratio=_ratio_weights(self.ratio_estimator, dev), outputs=outputs,
+                                alpha=self.alpha, temp=self.temp, grid_res=G,
+                                max_grid_refinements=self.max_grid_refinements, randomized=self.randomized,
+                                optimistic=self.optimistic, **self._acq_params())
+        self.last_outputs = out
+        return out["acq"].reshape(lead).to(X.dtype)
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        return self._conformal_fwd(X)                            # max over q / mean over S happen in the kernel epilogue
+
+
+class qConformalUpperConfidenceBound(ConformalAcquisition):
+    """acquisitions.py:142-164 (+ botorch qUpperConfidenceBound(model, beta, sampler, ...))."""
+
+    def __init__(self, alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic=True,
+                 grid_sampler=None, randomized=False, *, model=None, beta=None, sampler=None, objective=None,
+                 posterior_transform=None, X_pending=None):
+        super().__init__(alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic, grid_sampler,
+                         randomized, model=model, sampler=sampler, objective=objective,
+                         posterior_transform=posterior_transform, X_pending=X_pending)
+        if beta is None:
+            raise TypeError("qConformalUpperConfidenceBound needs beta")
+        self.beta_prime = math.sqrt(beta * math.pi / 2)          # botorch qUpperConfidenceBound (App. B-10)
+
+    def _acq_params(self):
+        return dict(kind="ucb", beta_prime=self.beta_prime)
+
+
+class qConformalExpectedImprovement(ConformalAcquisition):
+    """acquisitions.py:79-103 (+ botorch qExpectedImprovement(model, best_f, sampler, ...))."""
+
+    def __init__(self, alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic=False,
+                 grid_sampler=None, randomized=False, *, model=None, best_f=None, sampler=None, objective=None,
+                 posterior_transform=None, X_pending=None):
+        super().__init__(alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic, grid_sampler,
+                         randomized, model=model, sampler=sampler, objective=objective,
+                         posterior_transform=posterior_transform, X_pending=X_pending)
+        if best_f is None:
+            raise TypeError("qConformalExpectedImprovement needs best_f")
+        self.register_buffer("best_f", torch.as_tensor(best_f, dtype=torch.float64).reshape(()))
+
+    def _acq_params(self):
+        return dict(kind="ei", best_f=float(self.best_f))

@@ -1,0 +1,116 @@
+"""Drop-in replacements for the lower boundary of the reference (conformalbo/helpers.py).
+
+Same names, argument meaning and return layout as the reference; the arithmetic runs in libcbo
+(no torch fallback).  `model` is a `GPModelState` (or a duck-typed BoTorch `SingleTaskGP`).
+Differences that cannot be avoided: the 4th return value of
+`construct_conformal_bands` (a GPyTorch model object conditioned on every grid point) is `None` --
+the fused kernels never materialise it; the acquisition classes take over `_conformal_fwd` instead.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from .model_state import GPModelState
+from .sampling import IIDNormalSampler
+
+
+def as_state(model) -> GPModelState:
+    if isinstance(model, GPModelState):
+        return model
+    cached = getattr(model, "_cbo_state", None)
+    if cached is not None:
+        return cached
+    state = GPModelState.from_botorch(model)
+    try:
+        model._cbo_state = state
+    except Exception:
+        pass
+    return state
+
+
+def draw_probes(n_rows: int, num_samples: int = 8) -> torch.Tensor:
+    """Rademacher probes drawn from the CPU default generator, as est_train_post_var does (helpers.py:399-400)."""
+    z = (torch.rand(n_rows, num_samples) > 0.5).to(torch.float64)
+    return 2.0 * (z - 0.5)
+
+
+def _ratio_weights(ratio_estimator, device):
+    if ratio_estimator is None:
+        return None
+    if isinstance(ratio_estimator, ops.RatioWeights):
+        return ratio_estimator
+    return ratio_estimator.device_weights(device)
+
+
+def conf_mask_to_bounds(target_grid: torch.Tensor, conf_pred_mask: torch.Tensor):
+    """helpers.py:15-91.  (*, G, 1, t) x 2 -> conf_lb, conf_ub (*, 1, t)."""
+    lead = target_grid.shape[:-3]
+    G, q, t = target_grid.shape[-3:]
+    lb, ub = ops.conf_mask_to_bounds(target_grid.reshape(-1, G, q, t), conf_pred_mask.reshape(-1, G, q, t))
+    return lb.reshape(*lead, 1, t).to(target_grid.dtype), ub.reshape(*lead, 1, t).to(target_grid.dtype)
+
+
+def construct_conformal_bands(model, inputs, alpha, temp, grid_res, max_grid_refinements, sampler,
+                              ratio_estimator=None, mask_ood=True, randomized=False, *, probes=None, u_rand=None):
+    """helpers.py:94-202.  inputs (b, q, d) -> target_grid (b,G,q,t), weights (b,G,1,1), conf_pred_mask (b,G,q,t),
+    None, ood_mask (b,G,q,t).  `probes` / `u_rand` inject the reference's internal randomness (App. C-2/3)."""
+    shape_msg = "inputs should have shape (*q_batch_shape, q_batch_size, input_dim)" \
+                f"instead has shape {inputs.shape}"
+    assert inputs.ndim >= 3, shape_msg
+    assert grid_res >= 2, "grid resolution must be at least 2"
+    state = as_state(model)
+    dev = inputs.device
+    lead = inputs.shape[:-2]
+    q, d = inputs.shape[-2:]
+    X = inputs.reshape(-1, q, d)
+    b = X.shape[0]
+    sampler._sample_shape = torch.Size([grid_res])                      # helpers.py:132
+    if sampler.collapse_batch_dims:
+        eps = sampler.draw((grid_res, q), dev)[:, 0] if q == 1 else sampler.draw((grid_res, q), dev)
+    else:
+        eps = sampler.draw((grid_res, b, q), dev).movedim(0, 1)[:, :, 0].contiguous()
+    z = (probes if probes is not None else draw_probes(state.N + q)).to(dev)
+    if randomized and u_rand is None:
+        u_rand = torch.rand(b, grid_res, dtype=torch.float64, device=dev)
+    out = ops.conformal_acq(
+        state, X, eps_grid=eps, z=z, eps_mc=torch.zeros(1, grid_res, dtype=torch.float64, device=dev), u_rand=u_rand,
+        ratio=_ratio_weights(ratio_estimator, dev), outputs=("target_grid", "grid_logp", "conf_pred_mask", "ood_mask"),
+        kind="ucb", alpha=alpha, temp=temp, grid_res=grid_res, max_grid_refinements=max_grid_refinements,
+        randomized=randomized, optimistic=False)
+    dt = inputs.dtype
+    tg = out["target_grid"].reshape(*lead, grid_res, q, 1).to(dt)
+    w = out["grid_logp"].reshape(*lead, grid_res, 1, 1).to(dt)
+    mk = out["conf_pred_mask"].reshape(*lead, grid_res, q, 1).to(dt)
+    ood = out["ood_mask"].reshape(*lead, 1, q, 1).expand(*lead, grid_res, q, 1).to(dt)
+    return tg, w, mk, None, ood
+
+
+def assess_coverage(model, inputs, targets, alpha, temp, grid_res, max_grid_refinements, ratio_estimator=None,
+                    randomized=False, *, probes=None, u_rand=None, grid_sampler: Optional[IIDNormalSampler] = None):
+    """helpers.py:336-387.  inputs (n, d), targets (n, t) -> (std_coverage, conformal_coverage) floats."""
+    from scipy import stats
+    state = as_state(model)
+    dev = inputs.device
+    n = inputs.shape[0]
+    if grid_sampler is None:
+        grid_sampler = IIDNormalSampler(grid_res, resample=False, collapse_batch_dims=False)   # helpers.py:364
+    grid_sampler._sample_shape = torch.Size([grid_res])
+    eps = grid_sampler.draw((grid_res, n, 1), dev).movedim(0, 1)[:, :, 0].contiguous()
+    z = (probes if probes is not None else draw_probes(state.N + 1)).to(dev)
+    if randomized and u_rand is None:
+        u_rand = torch.rand(n, grid_res, dtype=torch.float64, device=dev)
+    out = ops.conformal_acq(
+        state, inputs[:, None], eps_grid=eps, z=z, eps_mc=torch.zeros(1, grid_res, dtype=torch.float64, device=dev),
+        u_rand=u_rand, ratio=_ratio_weights(ratio_estimator, dev),
+        outputs=("target_grid", "conf_pred_mask", "post_mean", "post_var"), kind="ucb", alpha=alpha, temp=temp,
+        grid_res=grid_res, max_grid_refinements=max_grid_refinements, randomized=randomized, optimistic=False)
+    tg = targets.reshape(n, -1).to(torch.float64)
+    y_mean, y_std = out["post_mean"].unsqueeze(-1), out["post_var"].sqrt().unsqueeze(-1)
+    std_scale = stats.norm.ppf(1 - alpha / 2.0)
+    std_coverage = ((tg >= y_mean - std_scale * y_std) * (tg <= y_mean + std_scale * y_std)).float().mean()
+    lb, ub = ops.conf_mask_to_bounds(out["target_grid"][:, :, None, None], out["conf_pred_mask"][:, :, None, None])
+    conformal_coverage = ((tg >= lb.squeeze(-2)) * (tg <= ub.squeeze(-2))).float().nanmean()
+    return std_coverage.item(), conformal_coverage.item()

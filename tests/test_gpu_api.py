@@ -1,0 +1,166 @@
+"""GPU tests of the reference-facing interface (acquisition classes / helpers) against the oracle."""
+import math
+
+import pytest
+import torch
+
+from oracle import closed_form, pure
+from oracle import gp as ogp
+from tests.problems import make_inputs, make_problem, oracle_state
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _state(p, dev):
+    from conformal_bayesopt_b200 import GPModelState
+    return GPModelState.fit_fixed(p["X"], p["y"], p["mean"], p["lengthscale"], p["outputscale"], p["noise"], device=dev)
+
+
+def _estimator(d, dev):
+    """RatioEstimator whose target network carries the oracle's seeded weights."""
+    from conformal_bayesopt_b200.ratio_estimation import RatioEstimator
+    r = ogp.make_ratio_mlp(d)
+    est = RatioEstimator(in_size=d, device=dev, dtype=torch.float64)
+    lin = [m for m in est._target_network if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():
+        for m, (W, b) in zip(lin, [(r.W1, r.b1), (r.W2, r.b2), (r.W3, r.b3)]):
+            m.weight.copy_(W)
+            m.bias.copy_(b)
+    return r, est
+
+
+@pytest.mark.parametrize("cls_name,extra,kind", [("qConformalUpperConfidenceBound", dict(beta=0.2), "ucb"),
+                                                 ("qConformalExpectedImprovement", dict(best_f=0.3), "ei")])
+def test_acquisition_forward_matches_oracle(cls_name, extra, kind):
+    from conformal_bayesopt_b200 import acquisitions
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    dev = _dev()
+    N, d, b, G = 120, 6, 33, 64
+    p = make_problem(N, d, seed=11)
+    inp = make_inputs(N, d, b, 1, G, S=1, seed=11)
+    ratio, est = _estimator(d, dev)
+    grid_sampler = IIDNormalSampler(G)
+    grid_sampler.set_base_samples(inp["eps_grid"])
+    mc = IIDNormalSampler(1, batch_range=(0, -3))
+    mc.set_base_samples(inp["eps_mc"])
+    acq = getattr(acquisitions, cls_name)(alpha=0.1, temp=3e-2, grid_res=G, max_grid_refinements=0, ratio_estimator=est,
+                                          grid_sampler=grid_sampler, randomized=True, model=_state(p, dev), sampler=mc,
+                                          **extra)
+    acq.fixed_probes = inp["z"]
+    acq.fixed_uniforms = inp["u_rand"][:, :, 0].to(dev)
+    with torch.no_grad():
+        got = acq(inp["Xq"].to(dev))
+    assert got.shape == (b,)
+    kw = dict(kind=kind, alpha=0.1, temp=3e-2, grid_res=G, randomized=True, optimistic=acq.optimistic,
+              beta_prime=math.sqrt(0.2 * math.pi / 2), best_f=0.3)
+    want = closed_form.conformal_acquisition(oracle_state(p), inp["Xq"], eps_grid=inp["eps_grid"], z=inp["z"],
+                                             eps_mc=inp["eps_mc"], ratio=ratio, u_rand=inp["u_rand"], **kw)
+    assert torch.allclose(got.cpu(), want["acq"], rtol=1e-6, atol=1e-9)
+    # 2-D input gets a t-batch dimension (t_batch_mode_transform); output shape == X.shape[:-2]
+    with torch.no_grad():
+        one = acq(inp["Xq"][0].to(dev))
+    assert one.shape == (1,) and torch.allclose(one.cpu(), want["acq"][:1], rtol=1e-6, atol=1e-9)
+    # gradients are not built: fail loudly instead of returning a constant
+    with pytest.raises(NotImplementedError):
+        acq(inp["Xq"].to(dev).requires_grad_(True))
+    # q > 1 (here via X_pending) is refused, not silently mis-evaluated
+    acq.set_X_pending(inp["Xq"][0].to(dev))
+    from conformal_bayesopt_b200 import _lib
+    with pytest.raises(_lib.CboError):
+        with torch.no_grad():
+            acq(inp["Xq"].to(dev))
+
+
+def test_fresh_probes_change_values_like_the_reference():
+    """helpers.py:399: z is redrawn on every call, so values are stochastic call to call; seeding the CPU generator pins them."""
+    from conformal_bayesopt_b200.acquisitions import qConformalUpperConfidenceBound
+    dev = _dev()
+    p = make_problem(60, 3, seed=2)
+    X = torch.rand(16, 1, 3, dtype=torch.float64, device=dev)
+    acq = qConformalUpperConfidenceBound(alpha=0.1, temp=3e-2, grid_res=32, max_grid_refinements=0, ratio_estimator=None,
+                                         model=_state(p, dev), beta=0.2)
+    with torch.no_grad():
+        torch.manual_seed(5); a = acq(X)
+        torch.manual_seed(5); b = acq(X)
+        c = acq(X)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+def test_construct_conformal_bands_and_coverage():
+    from conformal_bayesopt_b200 import helpers
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    dev = _dev()
+    N, d, n, G = 150, 4, 40, 64
+    p = make_problem(N, d, seed=21)
+    gp = oracle_state(p)
+    g = torch.Generator().manual_seed(7)
+    Xh = torch.rand(n, d, generator=g, dtype=torch.float64)
+    mean_h = gp.mean + gp.k(Xh, gp.X) @ gp.alpha
+    Yh = (mean_h + 0.1 * torch.randn(n, generator=g, dtype=torch.float64)).unsqueeze(-1)
+    z = 2.0 * ((torch.rand(N + 1, 8, generator=g) > 0.5).double() - 0.5)
+    eps = torch.randn(G, n, 1, generator=g, dtype=torch.float64)           # collapse_batch_dims=False layout (G, b, q)
+    sampler = IIDNormalSampler(G, collapse_batch_dims=False)
+    sampler.set_base_samples(eps)
+    alpha, temp = 0.1, 1e-2
+    tg, w, mk, cond, ood = helpers.construct_conformal_bands(_state(p, dev), Xh[:, None].to(dev), alpha, temp, G, 0, sampler,
+                                                             probes=z)
+    assert tg.shape == (n, G, 1, 1) and w.shape == (n, G, 1, 1) and mk.shape == (n, G, 1, 1) and ood.shape == (n, G, 1, 1)
+    assert cond is None
+    want = closed_form.conformal_acquisition(gp, Xh[:, None], kind="ucb", alpha=alpha, temp=temp, grid_res=G,
+                                             eps_grid=eps.movedim(0, 1), z=z, eps_mc=torch.zeros(1, G, 1, dtype=torch.float64),
+                                             beta_prime=1.0, optimistic=False)
+    assert torch.allclose(tg.cpu()[..., 0], want["target_grid"], rtol=1e-6, atol=1e-9)
+    assert torch.allclose(mk.cpu()[..., 0], want["mask"], rtol=0, atol=1e-6)
+    assert torch.allclose(w.cpu()[:, :, 0, 0], want["logp"], rtol=1e-6, atol=1e-9)
+    lb, ub = helpers.conf_mask_to_bounds(tg, mk)
+    lbo, ubo = pure.conf_mask_to_bounds(want["target_grid"].unsqueeze(-1), want["mask"].unsqueeze(-1))
+    assert torch.allclose(lb.cpu(), lbo, rtol=1e-6, atol=1e-7) and torch.allclose(ub.cpu(), ubo, rtol=1e-6, atol=1e-7)
+    # assess_coverage (helpers.py:336-387) against the same quantities computed from the oracle
+    sampler2 = IIDNormalSampler(G, collapse_batch_dims=False)
+    sampler2.set_base_samples(eps)
+    std_c, conf_c = helpers.assess_coverage(_state(p, dev), Xh.to(dev), Yh.to(dev), alpha, temp, G, 0, probes=z,
+                                            grid_sampler=sampler2)
+    from scipy import stats
+    sd = want["S"][:, 0, 0].sqrt().unsqueeze(-1)
+    sc = stats.norm.ppf(1 - alpha / 2)
+    std_o = ((Yh >= want["mu"] - sc * sd) * (Yh <= want["mu"] + sc * sd)).float().mean().item()
+    conf_o = ((Yh >= lbo.squeeze(-2)) * (Yh <= ubo.squeeze(-2))).float().nanmean().item()
+    assert abs(std_c - std_o) < 1e-6 and abs(conf_c - conf_o) < 1e-6
+    assert conf_c >= 1 - alpha - 0.15                      # full conformal bands cover (n = 40: loose statistical check)
+
+
+def test_reference_coverage_tests_on_cuda():
+    """tests/test_coverage.py:38-87 ported verbatim onto the CUDA conf_mask_to_bounds (t = 1 and t = 2)."""
+    from conformal_bayesopt_b200 import helpers
+    dev = _dev()
+    torch.manual_seed(0)
+    for target_dim in (1, 2):
+        b, G, cvrg = 256, 256, 0.8
+        grid = torch.randn(b, G, 1, target_dim)
+        idx_shape = (b, 1, 1, target_dim)
+        s1 = torch.gather(grid, index=torch.randint(G // 2, G, idx_shape), dim=-3).squeeze(-3)
+        s2 = torch.gather(grid, index=torch.randint(0, G // 2, idx_shape), dim=-3).squeeze(-3)
+        real_lb, real_ub = torch.min(s1, s2) - 1e-6, torch.max(s1, s2) + 1e-6
+        inb = real_lb + torch.rand_like(real_lb) * (real_ub - real_lb)
+        rm = (torch.rand_like(real_lb) < 0.5).float()
+        outb = rm * (real_lb - 1.0) + (1 - rm) * (real_ub + 1.0)
+        rm = (torch.rand_like(real_lb) < cvrg).float()
+        tgts = rm * inb + (1 - rm) * outb
+        mask = ((grid >= real_lb.unsqueeze(-3)) * (grid <= real_ub.unsqueeze(-3))).float()
+        est_lb, est_ub = helpers.conf_mask_to_bounds(grid.to(dev), mask.to(dev))
+        est = ((tgts >= est_lb.cpu()) * (tgts <= est_ub.cpu())).float().mean(dim=[0, -2])
+        act = ((tgts >= real_lb) * (tgts <= real_ub)).float().mean(dim=[0, -2])
+        assert torch.allclose(act, est)
+
+
+def test_ratio_estimator_forward_on_cuda():
+    dev = _dev()
+    ratio, est = _estimator(5, dev)
+    x = torch.randn(3, 7, 5, dtype=torch.float64)
+    out = est(x.to(dev))
+    assert out.shape == (3, 7) and torch.allclose(out.cpu(), ratio(x), rtol=1e-10)

@@ -1,0 +1,101 @@
+"""CPU tests of the host-side mirror (no CUDA calls): samplers, ratio estimator, sharding, class conventions."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conformal_bayesopt_b200 import distributed as cdist
+from conformal_bayesopt_b200.acquisitions import (ConformalAcquisition, qConformalExpectedImprovement,
+                                                  qConformalUpperConfidenceBound)
+from conformal_bayesopt_b200.ratio_estimation import RatioEstimator
+from conformal_bayesopt_b200.sampling import IIDNormalSampler
+
+
+def test_sampler_reuses_base_samples_until_shape_changes():
+    s = IIDNormalSampler(4, seed=3)
+    a = s.draw((4, 1))
+    assert torch.equal(a, s.draw((4, 1)))                 # resample=False: cached (App. B-7)
+    b = s.draw((8, 1))
+    assert b.shape == (8, 1)
+    assert torch.equal(IIDNormalSampler(4, seed=3).draw((4, 1)), a)
+    r = IIDNormalSampler(4, resample=True, seed=3)
+    assert not torch.equal(r.draw((4, 1)), r.draw((4, 1)))
+    s.set_base_samples(torch.ones(4, 1))
+    assert torch.equal(s.draw((4, 1)), torch.ones(4, 1, dtype=torch.float64))
+
+
+def test_untrained_ratio_estimator_is_one():
+    r = RatioEstimator(in_size=3, dtype=torch.float64)
+    out = r(torch.randn(5, 3, dtype=torch.float64))
+    assert torch.allclose(out, torch.ones(5, dtype=torch.float64))          # ratio_estimation.py:81-86
+    r.update_target_network()
+    assert any(p.abs().sum() > 0 for p in r._target_network.parameters())
+    with pytest.raises(NotImplementedError):
+        r.optimize_callback(None)
+
+
+def test_class_conventions():
+    kw = dict(alpha=0.1, temp=0.03, grid_res=8, max_grid_refinements=0, ratio_estimator=None)
+    ucb = qConformalUpperConfidenceBound(**kw, model=None, beta=0.2)
+    assert ucb.optimistic is True and ucb.ratio_estimator is None and ucb.X_pending is None   # acquisitions.py:144
+    ei = qConformalExpectedImprovement(**kw, model=None, best_f=0.5)
+    assert ei.optimistic is False                                                             # acquisitions.py:81
+    with pytest.raises(AttributeError):                  # acquisitions.py:42-43
+        ucb(torch.zeros(2, 1, 3, dtype=torch.float64))
+    with pytest.raises(TypeError):
+        qConformalUpperConfidenceBound(**kw, model=None)
+    with pytest.raises(NotImplementedError):
+        ConformalAcquisition(**kw, model=None, objective=lambda s, X=None: s)
+    ucb.set_X_pending(torch.zeros(1, 3))
+    assert ucb.X_pending.shape == (1, 3)
+    assert abs(ucb.beta_prime - (0.2 * torch.pi / 2) ** 0.5) < 1e-15                          # App. B-10
+
+
+def test_shard_bounds_cover_the_batch():
+    for b in (1, 7, 128, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [cdist.shard_bounds(b, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == b
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _acq_standin(X):
+    return torch.sin(3.0 * X.sum(dim=(-1, -2))) + 0.1 * X[..., 0, 0]
+
+
+def _worker(rank, world, port, b, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        X = torch.rand(b, 1, 4, generator=g, dtype=torch.float64)
+        X[5] = X[b - 2]                                   # an exact tie across shards: lowest index must win
+        full = cdist.sharded_acquisition(_acq_standin, X)
+        lo, hi = cdist.shard_bounds(b, rank, world)
+        val, idx = cdist.sharded_argmax(_acq_standin, X[lo:hi], lo)
+        shared = torch.full((3,), float(rank), dtype=torch.float64)
+        cdist.broadcast_shared_inputs([shared])
+        results[rank] = (full, val, idx, shared)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("b", [37, 64])
+def test_sharded_scoring_world_size_2_gloo(b):
+    world, port = 2, 29500 + (os.getpid() % 2000) + b
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, port, b, results), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(b, 1, 4, generator=g, dtype=torch.float64)
+    X[5] = X[b - 2]
+    want = _acq_standin(X)
+    for rank in range(world):
+        full, val, idx, shared = results[rank]
+        assert torch.equal(full, want)                    # sharded == unsharded, bit for bit
+        assert idx == int(torch.argmax(want)) and val == float(want.max())
+        assert torch.equal(shared, torch.zeros(3, dtype=torch.float64))
