@@ -32,6 +32,8 @@ FLOP_PER_EVAL = 51811.0            # algorithmic fp64 flop per (
 GEMM_FLOP_PER_CAND_PASS = float(N_TRAIN) * N_TRAIN      # one triangular solve pass: N^2 flop (N^2/2 FMA)
 SCORE_FLOP_PER_EVAL = 17.0 * (N_TRAIN + 1)              # SURVEY.md §8d per-(cand,grid) term
 FP64_PEAK_TFLOPS = 37.0            # measured on this pool's B200 (profiles/r01_fp64_peak.log): DMMA.8x8x4 = whole fp64 pipe
+NCU_DRAM_BYTES_PER_LAUNCH = {"score_rank_integrate": 141.3e6, "gemm_pass1_dmma": 566.3e6, "gemm_pass2_dmma": 494.4e6,
+                             "kernel_rows": 78.2e6}
 BYTES_PER_EVAL = (8 * DIM + 8) / GRID                   # SURVEY.md §8d algorithmic HBM bytes per eval (no mask output)
 
 
@@ -294,7 +296,10 @@ def run_ours(args):
         "kernel": names[dom], "achieved": kernels[dom].get("achieved_tflops"), "peak": FP64_PEAK_TFLOPS,
         "unit": "TFLOP/s", "frac": kernels[dom].get("frac_of_fp64_peak"),
         "peak_source": "measured on this pool (profiles/r01_fp64_peak.log); MEASURED_PEAKS.json has no fp64 figure",
-        "avg_launch_ms": per_launch_ms, "traffic": None,
+        "avg_launch_ms": per_launch_ms,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel from one `ncu --set full` capture at the
+        # bench's chunk size (16384 candidates / launch): profiles/r01_ncu_summary.txt
+        "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(names[dom]),
         "whole_path": {"achieved": value / world * FLOP_PER_EVAL / 1e12, "frac": value / world * FLOP_PER_EVAL / 1e12 / FP64_PEAK_TFLOPS,
                        "flop_per_eval": FLOP_PER_EVAL},
         "hbm": {"achieved_gbs": value / world * BYTES_PER_EVAL / 1e9, "bytes_per_eval": BYTES_PER_EVAL, "peak_gbs": 6539.2,
