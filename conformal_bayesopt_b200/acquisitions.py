@@ -6,8 +6,8 @@
 reference (acquisitions.py:80-86, 107-113, 143-149) and the BoTorch bases it mixes in
 (`model`, `beta` / `best_f`, `sampler`, `objective`, `posterior_transform`, `X_pending`).
 
-Not built yet (raise, never silently fall back): q > 1 (incl. X_pending), non-identity
-objectives / posterior transforms, autograd through `forward`.
+Joint batches q <= 4 (incl. X_pending) are supported.  Not built yet (raise, never silently fall back):
+non-identity objectives / posterior transforms, autograd through `forward`.
 """
 from __future__ import annotations
 
@@ -82,16 +82,15 @@ class ConformalAcquisition(nn.Module):
         b, G = Xf.shape[0], self.grid_res
         self.grid_sampler._sample_shape = torch.Size([G])
         if self.grid_sampler.collapse_batch_dims:
-            eps = self.grid_sampler.draw((G, q), dev)
-            eps = eps[:, 0] if q == 1 else eps
+            eps = self.grid_sampler.draw((G, q), dev)                              # shared by all candidates (App. B-7)
         else:
-            eps = self.grid_sampler.draw((G, b, q), dev).movedim(0, 1)[:, :, 0].contiguous()
+            eps = self.grid_sampler.draw((G, b, q), dev).movedim(0, 1).contiguous()
         S = int(self.sampler.sample_shape[0])
-        eps_mc = self.sampler.draw((S, G, q), dev)[:, :, 0].contiguous()
+        eps_mc = self.sampler.draw((S, G, q), dev)
         z = (self.fixed_probes if self.fixed_probes is not None else draw_probes(state.N + q)).to(dev)
         u = self.fixed_uniforms
         if self.randomized and u is None:
-            u = torch.rand(b, G, dtype=torch.float64, device=dev)
+            u = torch.rand(b, G, q, dtype=torch.float64, device=dev)
         out = ops.conformal_acq(state, Xf, eps_grid=eps, z=z, eps_mc=eps_mc, u_rand=u,
                                 ratio=_ratio_weights(self.ratio_estimator, dev), outputs=outputs,
                                 alpha=self.alpha, temp=self.temp, grid_res=G,

@@ -13,6 +13,7 @@
 #include "gemm_tri.cuh"
 #include "rows.cuh"
 #include "score.cuh"
+#include "score_q.cuh"
 
 namespace {
 
@@ -73,7 +74,7 @@ struct Workspace {
     double *zp, *tmp, *T, *a, *h0, *dr_train, *sum_dr, *XsT;
     uint32_t* zb;
     double *UW, *V, *mu, *ut, *drc, *rn;
-    double *cscale, *nacc, *stats;      // refinement only
+    double *cscale, *nacc, *acq_scratch, *stats;      // refinement only
     size_t bytes;
 };
 
@@ -84,7 +85,7 @@ int64_t pick_chunk(int64_t b, const cbo_params* p, int64_t chunk) {
 }
 
 Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, int64_t chunk) {
-    const int64_t Np = cbo_padded_n(N), Sp = p->num_probes, C = pick_chunk(b, p, chunk);
+    const int64_t Np = cbo_padded_n(N), Sp = p->num_probes, C = pick_chunk(b, p, chunk) * p->q;   // rows per chunk
     const int64_t tiles_n = Np / cbo::GEMM_BN;
     Carver c(ws);
     Workspace w;
@@ -104,8 +105,9 @@ Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, 
     w.drc = c.take<double>(C);
     w.rn = c.take<double>(C * tiles_n);
     const int64_t R = p->max_grid_refinements;
-    w.cscale = c.take<double>(R > 0 ? (R + 1) * b : 1);
-    w.nacc = c.take<double>(R > 0 ? b : 1);
+    w.cscale = c.take<double>(R > 0 ? (R + 1) * b * p->q : 1);
+    w.nacc = c.take<double>(R > 0 ? b * p->q : 1);
+    w.acq_scratch = c.take<double>(R > 0 ? b : 1);
     w.stats = c.take<double>(8);
     w.bytes = c.off;
     return w;
@@ -141,7 +143,7 @@ __global__ void k_rescale(const double* __restrict__ nacc, const double* __restr
     if (i >= b) return;
     float d = (float)nacc[i] / (float)G - 0.5f;
     float ad = fabsf(d);
-    float pw = (q == 1) ? ad * ad : (q == 2 ? ad : powf(ad, 2.f / (float)q));
+    float pw = (q == 1) ? ad * ad : (q == 2 ? ad : (float)pow((double)ad, (double)(2.f / (float)q)));
     float sg = (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f);
     next[i] = (double)(1.f + sg * pw) * cur[i];
 }
@@ -152,7 +154,8 @@ int validate(const cbo_gp_f64* gp, const cbo_params* p, int64_t b) {
     if (gp->N <= 0 || gp->d <= 0 || gp->Np != cbo_padded_n(gp->N)) return CBO_ERR_INVALID_ARG;
     if (p->grid_res < 2) return CBO_ERR_INVALID_ARG;                       // helpers.py:113
     if (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI) return CBO_ERR_INVALID_ARG;
-    if (p->q != 1) return CBO_ERR_UNSUPPORTED;
+    if (p->q < 1 || p->q > cbo::MAX_Q) return CBO_ERR_UNSUPPORTED;
+    if (p->q > 1 && cbo::score_q_smem_bytes((int)gp->Np, (int)p->grid_res, (int)p->q) > 227 * 1024) return CBO_ERR_UNSUPPORTED;
     if (gp->d > cbo::MAX_D) return CBO_ERR_UNSUPPORTED;
     if (p->num_probes < 1 || p->num_probes > cbo::MAX_SP) return CBO_ERR_UNSUPPORTED;
     if (p->num_mc < 1 || p->num_mc > cbo::MAX_S) return CBO_ERR_UNSUPPORTED;
@@ -187,6 +190,31 @@ cudaError_t launch_score(const cbo::ScoreArgs& a, cudaStream_t st) {
     if (grid > num_sms()) grid = num_sms();
     cbo::k_score<SOFT><<<grid, npairs * 64, smem, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int Q, bool SOFT>
+cudaError_t launch_score_q_t(const cbo::ScoreQArgs& a, cudaStream_t st) {
+    size_t smem = cbo::score_q_smem_bytes(a.base.Np, a.base.G, Q);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(cbo::k_score_q<Q, SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    int grid = a.base.n_cand < per_sm * num_sms() ? a.base.n_cand : per_sm * num_sms();
+    cbo::k_score_q<Q, SOFT><<<grid, cbo::SQ_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_score_q(const cbo::ScoreQArgs& a, int q, bool soft, cudaStream_t st) {
+    switch (q) {
+        case 2: return soft ? launch_score_q_t<2, true>(a, st) : launch_score_q_t<2, false>(a, st);
+        case 3: return soft ? launch_score_q_t<3, true>(a, st) : launch_score_q_t<3, false>(a, st);
+        case 4: return soft ? launch_score_q_t<4, true>(a, st) : launch_score_q_t<4, false>(a, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace
@@ -274,6 +302,7 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
     if (w.bytes > workspace_bytes) return CBO_ERR_WORKSPACE;
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool soft_path = p->temp > 0.0;
     const int N = (int)gp->N, Np = (int)gp->Np, d = (int)gp->d, Sp = (int)p->num_probes, G = (int)p->grid_res;
     const int tiles_n = Np / cbo::GEMM_BN;
     const int64_t C = pick_chunk(b, p, chunk);
@@ -296,9 +325,11 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
     CBO_CUDA(cudaGetLastError());
 
     const int R = (int)p->max_grid_refinements;
+    const int q = (int)p->q;
     for (int64_t c0 = 0; c0 < b; c0 += C) {
-        const int n = (int)((b - c0 < C) ? (b - c0) : C);
-        const double* Xc = Xq + c0 * d;
+        const int ncand = (int)((b - c0 < C) ? (b - c0) : C);
+        const int n = ncand * q;                                  // kernel rows of this chunk: one per candidate POINT
+        const double* Xc = Xq + c0 * q * d;
         // ---- kernel rows, mu, u^T T; candidate density ratios -------------------------------------
         {
             TimeScope ts_(T_ROWS, s, ratio ? 2 : 1);
@@ -323,32 +354,40 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
         // ---- scores / rank / mask / integration ----------------------------------------------------
         cbo::ScoreArgs a;
         memset(&a, 0, sizeof(a));
-        a.N = N; a.Np = Np; a.G = G; a.S = (int)p->num_mc; a.Sp = Sp; a.n_cand = n; a.tiles_n = tiles_n;
+        a.N = N; a.Np = Np; a.G = G; a.S = (int)p->num_mc; a.Sp = Sp; a.n_cand = ncand; a.tiles_n = tiles_n;
         a.noise = gp->noise; a.kappa = gp->outputscale; a.alpha_lvl = p->alpha; a.temp = p->temp;
         a.beta_prime = p->beta_prime; a.best_f = p->best_f;
         a.kind = p->kind; a.optimistic = p->optimistic; a.randomized = p->randomized;
         a.eps_per_candidate = p->eps_per_candidate;
         a.a = w.a; a.h0 = w.h0; a.zb = w.zb; a.dr = w.dr_train; a.sum_dr = w.sum_dr; a.z_cand = z + int64_t(N) * Sp;
         a.W = w.UW; a.rn_partial = w.rn; a.mu = w.mu; a.ut = w.ut; a.drc = ratio ? w.drc : nullptr;
-        a.eps_grid = p->eps_per_candidate ? eps_grid + c0 * G : eps_grid;
+        a.eps_grid = p->eps_per_candidate ? eps_grid + c0 * G * q : eps_grid;
         a.eps_mc = eps_mc;
-        a.u_rand = u_rand ? u_rand + c0 * G : nullptr;
+        a.u_rand = u_rand ? u_rand + c0 * G * q : nullptr;
+        cbo::ScoreQArgs aq;
+        aq.V = w.V; aq.Xq = Xc; aq.inv_ls = gp->inv_lengthscale; aq.d = d;
+        aq.post_cov = (q > 1 && out->post_var) ? out->post_var + c0 * q * q : nullptr;
+        auto run_score = [&](const cbo::ScoreArgs& x) -> cudaError_t {
+            if (q == 1) return soft_path ? launch_score<true>(x, s) : launch_score<false>(x, s);
+            cbo::ScoreQArgs y = aq;
+            y.base = x;
+            return launch_score_q(y, q, soft_path, s);
+        };
         auto set_outputs = [&](cbo::ScoreArgs& x) {
             x.acq = out->acq + c0;
-            x.grid = out->target_grid ? out->target_grid + c0 * G : nullptr;
+            x.grid = out->target_grid ? out->target_grid + c0 * G * q : nullptr;
             x.logp = out->grid_logp ? out->grid_logp + c0 * G : nullptr;
-            x.mask = out->conf_pred_mask ? out->conf_pred_mask + c0 * G : nullptr;
-            x.qscore = out->q_conf_scores ? out->q_conf_scores + c0 * G : nullptr;
-            x.ood = out->ood_mask ? out->ood_mask + c0 : nullptr;
-            x.post_mean = out->post_mean ? out->post_mean + c0 : nullptr;
-            x.post_var = out->post_var ? out->post_var + c0 : nullptr;
-            x.num_acc = out->num_accepted ? out->num_accepted + c0 : nullptr;
+            x.mask = out->conf_pred_mask ? out->conf_pred_mask + c0 * G * q : nullptr;
+            x.qscore = out->q_conf_scores ? out->q_conf_scores + c0 * G * q : nullptr;
+            x.ood = out->ood_mask ? out->ood_mask + c0 * q : nullptr;
+            x.post_mean = out->post_mean ? out->post_mean + c0 * q : nullptr;
+            x.post_var = (q == 1 && out->post_var) ? out->post_var + c0 : nullptr;   // q > 1: full q x q via post_cov
+            x.num_acc = out->num_accepted ? out->num_accepted + c0 * q : nullptr;
         };
-        const bool soft = p->temp > 0.0;
         if (R == 0) {
             set_outputs(a);
             TimeScope ts_(T_SCORE, s, 1);
-            CBO_CUDA(soft ? launch_score<true>(a, s) : launch_score<false>(a, s));
+            CBO_CUDA(run_score(a));
         } else {
             // grid refinement (helpers.py:129-189): probe passes keep only the accepted counts; the pass with the
             // smallest grid_score is then re-run into the caller's buffers.  One host sync per pass, like the
@@ -356,13 +395,13 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
             cbo::k_fill<<<(n + 255) / 256, 256, 0, s>>>(w.cscale, n, 1.0);
             float best_score = INFINITY;
             int best_step = 0;
-            double* scratch_acq = w.V;                    // V is dead after pass 2
+            double* scratch_acq = w.acq_scratch;          // acquisition values of probe passes are discarded
             for (int step = 0; step <= R; ++step) {
                 cbo::ScoreArgs pa = a;
-                pa.cscale = w.cscale + int64_t(step) * b;
+                pa.cscale = w.cscale + int64_t(step) * b * q;
                 pa.acq = scratch_acq;
                 pa.num_acc = w.nacc;
-                CBO_CUDA(soft ? launch_score<true>(pa, s) : launch_score<false>(pa, s));
+                CBO_CUDA(run_score(pa));
                 k_accept_stats<<<1, 256, 0, s>>>(w.nacc, n, G, w.stats);
                 double hs[3];
                 CBO_CUDA(cudaMemcpyAsync(hs, w.stats, sizeof(hs), cudaMemcpyDeviceToHost, s));
@@ -372,13 +411,13 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
                 bool rescale = hs[0] < 2.0 || hs[1] > double(G - 2);
                 if (!rescale) break;
                 if (step < R)
-                    k_rescale<<<(n + 255) / 256, 256, 0, s>>>(w.nacc, w.cscale + int64_t(step) * b,
-                                                              w.cscale + int64_t(step + 1) * b, n, G, (int)p->q);
+                    k_rescale<<<(n + 255) / 256, 256, 0, s>>>(w.nacc, w.cscale + int64_t(step) * b * q,
+                                                              w.cscale + int64_t(step + 1) * b * q, n, G, q);
             }
             cbo::ScoreArgs fa = a;
-            fa.cscale = w.cscale + int64_t(best_step) * b;
+            fa.cscale = w.cscale + int64_t(best_step) * b * q;
             set_outputs(fa);
-            CBO_CUDA(soft ? launch_score<true>(fa, s) : launch_score<false>(fa, s));
+            CBO_CUDA(run_score(fa));
         }
     }
     return CBO_OK;

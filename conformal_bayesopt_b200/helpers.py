@@ -69,14 +69,14 @@ def construct_conformal_bands(model, inputs, alpha, temp, grid_res, max_grid_ref
     b = X.shape[0]
     sampler._sample_shape = torch.Size([grid_res])                      # helpers.py:132
     if sampler.collapse_batch_dims:
-        eps = sampler.draw((grid_res, q), dev)[:, 0] if q == 1 else sampler.draw((grid_res, q), dev)
+        eps = sampler.draw((grid_res, q), dev)
     else:
-        eps = sampler.draw((grid_res, b, q), dev).movedim(0, 1)[:, :, 0].contiguous()
+        eps = sampler.draw((grid_res, b, q), dev).movedim(0, 1).contiguous()
     z = (probes if probes is not None else draw_probes(state.N + q)).to(dev)
     if randomized and u_rand is None:
-        u_rand = torch.rand(b, grid_res, dtype=torch.float64, device=dev)
+        u_rand = torch.rand(b, grid_res, q, dtype=torch.float64, device=dev)
     out = ops.conformal_acq(
-        state, X, eps_grid=eps, z=z, eps_mc=torch.zeros(1, grid_res, dtype=torch.float64, device=dev), u_rand=u_rand,
+        state, X, eps_grid=eps, z=z, eps_mc=torch.zeros(1, grid_res, q, dtype=torch.float64, device=dev), u_rand=u_rand,
         ratio=_ratio_weights(ratio_estimator, dev), outputs=("target_grid", "grid_logp", "conf_pred_mask", "ood_mask"),
         kind="ucb", alpha=alpha, temp=temp, grid_res=grid_res, max_grid_refinements=max_grid_refinements,
         randomized=randomized, optimistic=False)

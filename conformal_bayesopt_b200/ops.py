@@ -94,22 +94,28 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
     global LAUNCH_COUNT
     lib = _lib.load()
     _require_cuda(Xq, eps_grid, z, eps_mc, u_rand, state.X)
-    if Xq.ndim == 3:
-        if Xq.shape[1] != 1:
-            raise _lib.CboError("unsupported shape: q > 1 is not built yet")
-        Xq = Xq[:, 0, :]
+    if Xq.ndim == 2:
+        Xq = Xq.unsqueeze(1)
+    b, q, _ = Xq.shape
+    if q > 4:
+        raise _lib.CboError("unsupported shape: q > 4")
+    G = int(param_kw["grid_res"])
     Xq, eps_grid, z, eps_mc, u_rand = map(_f64, (Xq, eps_grid, z, eps_mc, u_rand))
-    b, G = Xq.shape[0], int(param_kw["grid_res"])
-    eps_per_candidate = eps_grid.numel() == b * G and eps_grid.ndim >= 2 and eps_grid.shape[0] == b
-    num_mc = eps_mc.reshape(-1, G).shape[0]
-    params = make_params(num_mc=num_mc, num_probes=z.shape[-1], eps_per_candidate=eps_per_candidate, **param_kw)
-    if z.shape[0] != state.N + 1:
-        raise _lib.CboError(f"z must have N+q = {state.N + 1} rows, got {z.shape[0]}")
+    eps_per_candidate = eps_grid.numel() == b * G * q and eps_grid.numel() != G * q
+    if eps_grid.numel() not in (G * q, b * G * q):
+        raise _lib.CboError(f"eps_grid must hold G*q or b*G*q values, got {tuple(eps_grid.shape)}")
+    num_mc = eps_mc.numel() // (G * q)
+    params = make_params(q=q, num_mc=num_mc, num_probes=z.shape[-1], eps_per_candidate=eps_per_candidate, **param_kw)
+    if z.shape[0] != state.N + q:
+        raise _lib.CboError(f"z must have N+q = {state.N + q} rows, got {z.shape[0]}")
+    if u_rand is not None and u_rand.numel() != b * G * q:
+        raise _lib.CboError("u_rand must hold b*G*q uniforms")
     dev = Xq.device
     out_t = {"acq": torch.empty(b, dtype=torch.float64, device=dev)}
-    per_g = {"target_grid", "grid_logp", "conf_pred_mask", "q_conf_scores"}
+    shapes = {"target_grid": (b, G, q), "conf_pred_mask": (b, G, q), "q_conf_scores": (b, G, q), "grid_logp": (b, G),
+              "ood_mask": (b, q), "post_mean": (b, q), "num_accepted": (b, q), "post_var": (b,) if q == 1 else (b, q, q)}
     for name in outputs:
-        out_t[name] = torch.empty((b, G) if name in per_g else (b,), dtype=torch.float64, device=dev)
+        out_t[name] = torch.empty(shapes[name], dtype=torch.float64, device=dev)
     cout = _lib.OutputsF64(**{k: _ptr(v) for k, v in out_t.items()})
     ws = workspace(state, b, params, chunk)
     ws_ptr = (ws.data_ptr() + 255) // 256 * 256
@@ -120,6 +126,9 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
                                    _ptr(u_rand), C.byref(cout), ws_ptr, ws.numel() - 256, chunk, _stream())
     _lib.check(st, "cbo_conformal_acq_f64")
     LAUNCH_COUNT += count_launches(state, b, params, ratio is not None, chunk)
+    if q == 1:   # squeeze the q axis (the q = 1 layout of round-1 callers)
+        out_t = {k: (v.squeeze(-1) if k in ("target_grid", "conf_pred_mask", "q_conf_scores", "ood_mask", "post_mean",
+                                             "num_accepted") else v) for k, v in out_t.items()}
     return out_t
 
 

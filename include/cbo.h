@@ -81,7 +81,7 @@ typedef struct {
     double alpha;              /* miscoverage level                         (acquisitions.py:32) */
     double temp;               /* sigmoid temperature; <= 0 selects the hard path (helpers.py:277,316) */
     int64_t grid_res;          /* G >= 2                                    (helpers.py:113) */
-    int64_t q;                 /* joint batch size (this build: 1)          */
+    int64_t q;                 /* joint batch size, 1..4 (q = 1 is the throughput path) */
     int64_t num_mc;            /* S, MC samples of the acquisition sampler  */
     int64_t num_probes;        /* S_p Hutchinson probes (reference: 8; <= 16) (helpers.py:390) */
     int64_t max_grid_refinements;  /*                                       (helpers.py:129) */
@@ -95,15 +95,15 @@ typedef struct {
 
 /* Any pointer may be NULL (that output is skipped) except acq. */
 typedef struct {
-    double* acq;               /* b       acquisition value                                  */
-    double* target_grid;       /* b x G   y_g                                                */
-    double* grid_logp;         /* b x G   log N(y_g; mu, c s)                                */
-    double* conf_pred_mask;    /* b x G   conformal (soft) mask                              */
-    double* ood_mask;          /* b       sigma((omega_c - alpha)/temp)                      */
-    double* q_conf_scores;     /* b x G   candidate's own conformal score                    */
-    double* post_mean;         /* b       mu(x)                                              */
-    double* post_var;          /* b       s(x) = noisy predictive variance                   */
-    double* num_accepted;      /* b       #{g : mask >= 0.5}                                 */
+    double* acq;               /* b           acquisition value (max over q, mean over S)        */
+    double* target_grid;       /* b x G x q   y_g                                                */
+    double* grid_logp;         /* b x G       log N(y_g; mu, c S)  (joint over q)                */
+    double* conf_pred_mask;    /* b x G x q   conformal (soft) mask                              */
+    double* ood_mask;          /* b x q       sigma((omega_c - alpha)/temp)                      */
+    double* q_conf_scores;     /* b x G x q   the candidates' own conformal scores               */
+    double* post_mean;         /* b x q       mu(x)                                              */
+    double* post_var;          /* q = 1: b, noisy predictive variance s(x); q > 1: b x q x q covariance S */
+    double* num_accepted;      /* b x q       #{g : mask >= 0.5}                                 */
 } cbo_outputs_f64;
 
 int cbo_version(void);
@@ -115,8 +115,8 @@ int64_t cbo_padded_n(int64_t N);
  * max_grid_refinements == 0; `chunk` <= 0 selects the default chunk).  256-byte aligned. */
 size_t cbo_workspace_bytes(int64_t N, int64_t d, int64_t b, const cbo_params* params, int64_t chunk);
 
-/* The hot path.  Xq: b x q x d candidates; eps_grid: G (or b x G); z: (N+q) x S_p of +-1;
- * eps_mc: S x G; u_rand: b x G or NULL; chunk: candidates per internal pass (<= 0: default). */
+/* The hot path.  Xq: b x q x d candidates; eps_grid: G x q (or b x G x q); z: (N+q) x S_p of +-1;
+ * eps_mc: S x G x q; u_rand: b x G x q or NULL; chunk: candidates per internal pass (<= 0: default). */
 int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* params,
                           const double* Xq, int64_t b, const double* eps_grid, const double* z,
                           const double* eps_mc, const double* u_rand, const cbo_outputs_f64* out,

@@ -107,7 +107,7 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
     best = (float("inf"),)
     for _ in range(max_grid_refinements + 1):
         grid, logp, mask, dev = one_pass(cov)
-        num_acc = (mask >= 0.5).to(U).sum(1)
+        num_acc = (mask >= 0.5).float().sum(1)                              # float32 statistics, as helpers.py:150-167
         diff = num_acc / G - 0.5
         score = diff.pow(2).mean()
         if score < best[0]:

@@ -185,15 +185,15 @@ def construct_conformal_bands(gp: GPState, Xq, alpha, temp, grid_res, max_grid_r
         conf_pred_mask, refit, _, ood_mask = conformal_gp_regression(
             gp, Xq, target_grid, alpha, temp, z, ratio=ratio, randomized=randomized, u_rand=u_rand)
 
-        num_accepted = (conf_pred_mask >= 0.5).to(cov).sum(1)        # (b,q)
+        num_accepted = (conf_pred_mask >= 0.5).float().sum(1)        # (b,q)  float32, as helpers.py:150-155
         min_acc, max_acc = num_accepted.min(), num_accepted.max()
         diff = num_accepted / grid_res - 0.5
         grid_score = diff.pow(2).mean()
         if grid_score < best[0]:
             best = (grid_score, target_grid, weights, conf_pred_mask, refit, ood_mask)
-        covar_scale = 1.0 + diff.sign() * diff.abs().pow(2.0 / q)    # (b,q)
+        covar_scale = 1.0 + diff.sign() * diff.abs().pow(2.0 / q)    # (b,q) float32 (helpers.py:166-167)
         if min_acc < 2 or max_acc > grid_res - 2:
-            cov = covar_scale.unsqueeze(-1) * cov                    # helpers.py:170,178 (row scaling)
+            cov = covar_scale.unsqueeze(-1) * cov                    # helpers.py:170,178 (row scaling; promotes to fp64)
         else:
             break
     return best[1:]

@@ -62,18 +62,32 @@ def test_acquisition_forward_matches_oracle(cls_name, extra, kind):
                                              eps_mc=inp["eps_mc"], ratio=ratio, u_rand=inp["u_rand"], **kw)
     assert torch.allclose(got.cpu(), want["acq"], rtol=1e-6, atol=1e-9)
     # 2-D input gets a t-batch dimension (t_batch_mode_transform); output shape == X.shape[:-2]
+    acq.fixed_uniforms = inp["u_rand"][:1, :, 0].to(dev)
     with torch.no_grad():
         one = acq(inp["Xq"][0].to(dev))
     assert one.shape == (1,) and torch.allclose(one.cpu(), want["acq"][:1], rtol=1e-6, atol=1e-9)
     # gradients are not built: fail loudly instead of returning a constant
     with pytest.raises(NotImplementedError):
         acq(inp["Xq"].to(dev).requires_grad_(True))
-    # q > 1 (here via X_pending) is refused, not silently mis-evaluated
+    # X_pending makes q = 2: injected inputs of the wrong shape (z has N+1 rows) are refused, not silently mis-read
     acq.set_X_pending(inp["Xq"][0].to(dev))
     from conformal_bayesopt_b200 import _lib
     with pytest.raises(_lib.CboError):
         with torch.no_grad():
             acq(inp["Xq"].to(dev))
+    # ... and with consistent inputs the pending point is scored jointly (concatenate_pending_points)
+    inp2 = make_inputs(N, d, 7, 2, G, S=1, seed=12)
+    grid_sampler.set_base_samples(inp2["eps_grid"])
+    mc.set_base_samples(inp2["eps_mc"])
+    acq.fixed_probes = inp2["z"]
+    acq.fixed_uniforms = inp2["u_rand"].to(dev)
+    acq.set_X_pending(inp2["Xq"][0, 1:].to(dev))
+    Xj = torch.cat([inp2["Xq"][:, :1], inp2["Xq"][0, 1:].expand(7, 1, d)], dim=1)
+    with torch.no_grad():
+        got2 = acq(inp2["Xq"][:, :1].to(dev))
+    want2 = closed_form.conformal_acquisition(oracle_state(p), Xj, eps_grid=inp2["eps_grid"], z=inp2["z"],
+                                              eps_mc=inp2["eps_mc"], ratio=ratio, u_rand=inp2["u_rand"], **kw)
+    assert torch.allclose(got2.cpu(), want2["acq"], rtol=1e-6, atol=1e-9)
 
 
 def test_fresh_probes_change_values_like_the_reference():

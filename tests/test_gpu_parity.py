@@ -221,3 +221,42 @@ def test_error_conventions():
     Xq[1] = float("nan")
     got = _run(p, dict(inp, Xq=Xq), dev, kind="ucb", alpha=0.1, temp=0.1, grid_res=8, beta_prime=1.0)
     assert torch.isnan(got["acq"][1]) and torch.isfinite(got["acq"][[0, 2, 3]]).all()
+
+
+QCASES = [
+    # N, d, q, b, G, temp, randomized, ratio, refine, kind, S
+    (33, 2, 2, 5, 12, 3e-2, True, True, 0, "ucb", 2),
+    (33, 2, 2, 5, 12, 0.0, False, False, 1, "ucb", 1),
+    (20, 4, 3, 4, 8, 1e-2, True, True, 3, "ei", 2),
+    (8, 2, 2, 128, 64, 3e-2, True, False, 0, "ucb", 1),     # BASELINE config 1: branin-like, N=8, q_batch_size=2, 128 raw samples
+    (150, 8, 4, 9, 32, 3e-2, True, True, 2, "ucb", 1),
+    (130, 5, 2, 300, 64, 1e-6, True, True, 1, "ei", 1),
+]
+
+
+@pytest.mark.parametrize("N,d,q,b,G,temp,rand,ratio_on,refine,kind,S", QCASES)
+def test_joint_batches_match_oracle(N, d, q, b, G, temp, rand, ratio_on, refine, kind, S):
+    """q > 1 against the closed-form oracle (itself pinned against the dense refit for q = 2, 3)."""
+    from conformal_bayesopt_b200 import ops
+    dev = _dev()
+    p = make_problem(N, d, seed=N + q)
+    inp = make_inputs(N, d, b, q, G, S=S, seed=N + q)
+    ratio, ratio_w = _ratio(d, dev) if ratio_on else (None, None)
+    kw = dict(kind=kind, alpha=0.2, temp=temp, grid_res=G, max_grid_refinements=refine, randomized=rand,
+              optimistic=True, beta_prime=math.sqrt(0.2 * math.pi / 2), best_f=0.3)
+    want = closed_form.conformal_acquisition(oracle_state(p), inp["Xq"], eps_grid=inp["eps_grid"], z=inp["z"],
+                                             eps_mc=inp["eps_mc"], ratio=ratio, u_rand=inp["u_rand"], **kw)
+    got = ops.conformal_acq(_state(p, dev), inp["Xq"].to(dev), eps_grid=inp["eps_grid"].to(dev), z=inp["z"].to(dev),
+                            eps_mc=inp["eps_mc"].to(dev), u_rand=inp["u_rand"].to(dev), ratio=ratio_w,
+                            outputs=("target_grid", "grid_logp", "conf_pred_mask", "ood_mask", "post_mean", "post_var"), **kw)
+    torch.cuda.synchronize()
+    got = {k: v.cpu() for k, v in got.items()}
+    assert _close(got["post_mean"], want["mu"]) and _close(got["post_var"], want["S"])
+    # q >= 3 with refinement: the rescale factor |diff|^(2/q) is a float32 pow in the reference (helpers.py:167); device and
+    # host float pow may differ by one float ulp, i.e. 6e-8 relative on (y_g - mu) -- allow for it in absolute terms
+    gtol = 1e-7 if (q >= 3 and refine > 0) else 1e-9
+    assert _close(got["target_grid"], want["target_grid"], atol=gtol)
+    assert _close(got["grid_logp"], want["logp"])
+    assert torch.allclose(got["conf_pred_mask"], want["mask"], rtol=0, atol=1e-6)
+    assert torch.allclose(got["ood_mask"], want["ood"][:, 0, :], rtol=RTOL, atol=1e-12)
+    assert _close(got["acq"], want["acq"])
