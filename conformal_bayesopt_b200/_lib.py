@@ -13,6 +13,7 @@ EXPORTS = [
     "cbo_version", "cbo_status_str", "cbo_last_cuda_error", "cbo_padded_n", "cbo_workspace_bytes",
     "cbo_conformal_acq_f64", "cbo_conformal_acq_host_f64", "cbo_conf_mask_to_bounds_f64",
     "cbo_ratio_forward_f64", "cbo_gemm_tn_f64", "cbo_kernel_rows_f64", "cbo_timing_enable", "cbo_timing_collect",
+    "cbo_cehvi_integrate_f64",
 ]
 
 c_dp = C.c_void_p  # device pointers travel as integers
@@ -38,7 +39,8 @@ class Params(C.Structure):
 
 class OutputsF64(C.Structure):
     _fields_ = [(n, c_dp) for n in ("acq", "target_grid", "grid_logp", "conf_pred_mask", "ood_mask",
-                                     "q_conf_scores", "post_mean", "post_var", "num_accepted")]
+                                     "q_conf_scores", "post_mean", "post_var", "num_accepted", "refit_mean",
+                                     "refit_sd")]
 
 
 class CboError(RuntimeError):
@@ -87,6 +89,10 @@ def load():
                                     C.c_int64, C.c_int32, c_dp, c_dp]
     lib.cbo_kernel_rows_f64.restype = C.c_int
     lib.cbo_kernel_rows_f64.argtypes = [C.POINTER(GpF64), c_dp, C.c_int64, c_dp, c_dp, c_dp, c_dp]
+    PP = C.POINTER(C.c_void_p)
+    lib.cbo_cehvi_integrate_f64.restype = C.c_int
+    lib.cbo_cehvi_integrate_f64.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64, PP, PP, PP, PP, PP, PP, PP, c_dp,
+                                            c_dp, c_dp, C.c_int64, C.c_double, C.c_int32, c_dp, c_dp]
     lib.cbo_timing_enable.restype = None
     lib.cbo_timing_enable.argtypes = [C.c_int]
     lib.cbo_timing_collect.restype = C.c_int

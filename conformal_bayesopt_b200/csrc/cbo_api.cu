@@ -14,6 +14,7 @@
 #include "rows.cuh"
 #include "score.cuh"
 #include "score_q.cuh"
+#include "mobo.cuh"
 
 namespace {
 
@@ -383,6 +384,8 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
             x.post_mean = out->post_mean ? out->post_mean + c0 * q : nullptr;
             x.post_var = (q == 1 && out->post_var) ? out->post_var + c0 : nullptr;   // q > 1: full q x q via post_cov
             x.num_acc = out->num_accepted ? out->num_accepted + c0 * q : nullptr;
+            x.refit_mean = (q == 1 && out->refit_mean) ? out->refit_mean + c0 * G : nullptr;
+            x.refit_sd = (q == 1 && out->refit_sd) ? out->refit_sd + c0 : nullptr;
         };
         if (R == 0) {
             set_outputs(a);
@@ -420,6 +423,36 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
             CBO_CUDA(run_score(fa));
         }
     }
+    return CBO_OK;
+}
+
+int cbo_cehvi_integrate_f64(int64_t m, int64_t b, int64_t G, int64_t S, const double* const* mask,
+                            const double* const* logp, const double* const* grid, const double* const* mu,
+                            const double* const* ood, const double* const* refit_mean, const double* const* refit_sd,
+                            const double* eps_mc, const double* cell_lower, const double* cell_upper, int64_t n_cells,
+                            double alpha, int32_t optimistic, double* acq, void* stream) {
+    if (!mask || !logp || !grid || !mu || !ood || !refit_mean || !refit_sd || !eps_mc || !cell_lower || !cell_upper || !acq)
+        return CBO_ERR_INVALID_ARG;
+    if (m < 1 || b <= 0 || G < 2 || S < 1 || n_cells < 1) return CBO_ERR_INVALID_ARG;
+    if (m > cbo::MAX_M || size_t(2 * n_cells * m) * sizeof(double) > 200 * 1024) return CBO_ERR_UNSUPPORTED;
+    cbo::EhviArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = (int)m; a.b = (int)b; a.G = (int)G; a.S = (int)S; a.n_cells = (int)n_cells; a.optimistic = optimistic;
+    a.alpha_lvl = alpha;
+    for (int k = 0; k < m; ++k) {
+        if (!mask[k] || !logp[k] || !grid[k] || !mu[k] || !ood[k] || !refit_mean[k] || !refit_sd[k]) return CBO_ERR_INVALID_ARG;
+        a.mask[k] = mask[k]; a.logp[k] = logp[k]; a.grid[k] = grid[k]; a.mu[k] = mu[k]; a.ood[k] = ood[k];
+        a.mf[k] = refit_mean[k]; a.sd[k] = refit_sd[k];
+    }
+    a.eps_mc = eps_mc; a.cell_lower = cell_lower; a.cell_upper = cell_upper; a.acq = acq;
+    size_t smem = size_t(2 * n_cells * m) * sizeof(double);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        CBO_CUDA(cudaFuncSetAttribute(cbo::k_ehvi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    cbo::k_ehvi<<<(int)((b + 7) / 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    CBO_CUDA(cudaGetLastError());
     return CBO_OK;
 }
 

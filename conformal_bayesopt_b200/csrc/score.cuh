@@ -53,7 +53,7 @@ struct ScoreArgs {
     const double* u_rand;   // n_cand x G or nullptr
     // outputs (nullable except acq)
     double* acq; double* grid; double* logp; double* mask; double* ood; double* qscore;
-    double* post_mean; double* post_var; double* num_acc;
+    double* post_mean; double* post_var; double* num_acc; double* refit_mean; double* refit_sd;
 };
 
 // shared: tab[16] | dr[Np]        per pair: qa, qb, qc [Np] | 4 x [G] (raw cnt/sr/sw, then cw/nc/mf/mk) | zt[4][16]
@@ -310,6 +310,7 @@ k_score(const ScoreArgs p) {
             if (p.logp) p.logp[int64_t(c) * G + g] = lp;
             if (p.mask) p.mask[int64_t(c) * G + g] = mk;
             if (p.qscore) p.qscore[int64_t(c) * G + g] = scc;
+            if (p.refit_mean) p.refit_mean[int64_t(c) * G + g] = mf;
         }
         pair_barrier(pair);
 
@@ -357,6 +358,7 @@ k_score(const ScoreArgs p) {
                 if (p.post_mean) p.post_mean[c] = mu;
                 if (p.post_var) p.post_var[c] = s_var;
                 if (p.num_acc) p.num_acc[c] = nacc;
+                if (p.refit_sd) p.refit_sd[c] = sd_f;
             }
         }
         // the next candidate's phase A touches only the tables; its barriers order the g-arrays

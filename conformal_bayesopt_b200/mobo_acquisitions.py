@@ -1,0 +1,98 @@
+"""Multi-objective conformal acquisition (reference: conformalbo/mobo_acquisitions.py:24-45).
+
+`qConformalExpectedHypervolumeImprovement.forward(X: b x 1 x d) -> Tensor(b)`: one cbo_conformal_acq_f64 call per
+objective (independent GPs) and one cbo_cehvi_integrate_f64.  The reference's EHVI integration is shape-broken
+(raises unless b in {1, G}) and scrambles multi-output labels (App. C-6); this implements the
+intent -- see oracle/mobo.py.  Built: q = 1, max_grid_refinements = 0.  cNEHVI is a "next" row.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from . import ops
+from .acquisitions import ConformalAcquisition
+from .helpers import _ratio_weights, as_state, draw_probes
+from .sampling import IIDNormalSampler
+
+
+def box_decomposition_2d(ref_point: torch.Tensor, Y: torch.Tensor):
+    """Cells of the non-dominated region for m = 2 (maximisation): (lower, upper), each (n_front + 1, 2).
+    Host-side stand-in for botorch's FastNondominatedPartitioning(ref_point, Y).get_hypercell_bounds()."""
+    ref_point = ref_point.detach().double().cpu()
+    Y = Y.detach().double().cpu()
+    Y = Y[(Y > ref_point).all(-1)]
+    Y = Y[torch.argsort(Y[:, 0])]
+    keep, best2 = [], -float("inf")
+    for i in range(Y.shape[0] - 1, -1, -1):
+        if Y[i, 1] > best2:
+            keep.append(i)
+            best2 = float(Y[i, 1])
+    front = Y[keep[::-1]] if keep else Y.new_zeros(0, 2)
+    n, inf = front.shape[0], float("inf")
+    lower = [[float(ref_point[0]) if i == 0 else float(front[i - 1, 0]),
+              float(ref_point[1]) if i == n else float(front[i, 1])] for i in range(n + 1)]
+    upper = [[inf if i == n else float(front[i, 0]), inf] for i in range(n + 1)]
+    return torch.tensor(lower, dtype=torch.float64), torch.tensor(upper, dtype=torch.float64)
+
+
+class qConformalExpectedHypervolumeImprovement(ConformalAcquisition):
+    def __init__(self, alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic=False,
+                 grid_sampler=None, randomized=False, *, model=None, ref_point=None, partitioning=None, sampler=None,
+                 objective=None, constraints=None, X_pending=None, eta=1e-3):
+        super().__init__(alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic, grid_sampler,
+                         randomized, model=model, sampler=sampler, objective=objective, X_pending=X_pending)
+        assert constraints is None   # for simplicity of code (mobo_acquisitions.py:33)
+        if partitioning is None:
+            raise TypeError("qConformalExpectedHypervolumeImprovement needs a partitioning")
+        if hasattr(partitioning, "get_hypercell_bounds"):          # botorch partitioning object
+            bounds = partitioning.get_hypercell_bounds()
+            lower, upper = bounds[0], bounds[1]
+        else:
+            lower, upper = partitioning
+        self.register_buffer("cell_lower", lower.detach().double().reshape(-1, lower.shape[-1]).contiguous())
+        self.register_buffer("cell_upper", upper.detach().double().reshape(-1, upper.shape[-1]).contiguous())
+        self.ref_point = ref_point
+
+    def _states(self):
+        models: Sequence = self.model if isinstance(self.model, (list, tuple)) else [self.model]
+        return [as_state(m) for m in models]
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        if self.model is None:
+            raise AttributeError("ConformalAcquisition must be subclassed")
+        if X.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("d acq / d X is not built yet (SURVEY.md §8f-1); call under torch.no_grad()")
+        if self.max_grid_refinements > 0:
+            raise NotImplementedError("cEHVI grid refinement (joint over the objectives) is not built yet")
+        states = self._states()
+        m = len(states)
+        if X.ndim == 2:
+            X = X.unsqueeze(0)
+        if self.X_pending is not None or X.shape[-2] != 1:
+            raise NotImplementedError("cEHVI is built for q = 1")
+        lead, d = X.shape[:-2], X.shape[-1]
+        dev = X.device
+        Xf = X.reshape(-1, 1, d)
+        b, G = Xf.shape[0], self.grid_res
+        self.grid_sampler._sample_shape = torch.Size([G])
+        eps = self.grid_sampler.draw((G, 1, m), dev)[:, 0, :]                       # (G, m): base samples (G,1,q,t)
+        S = int(self.sampler.sample_shape[0])
+        eps_mc = self.sampler.draw((S, G, 1, m), dev)[:, :, 0, :].contiguous()      # (S, G, m)
+        z = (self.fixed_probes if self.fixed_probes is not None else draw_probes(states[0].N + 1)).to(dev)
+        u = self.fixed_uniforms                                                     # (b, G, m)
+        if self.randomized and u is None:
+            u = torch.rand(b, G, m, dtype=torch.float64, device=dev)
+        outs = []
+        for k, st in enumerate(states):
+            outs.append(ops.conformal_acq(
+                st, Xf, eps_grid=eps[:, k].contiguous(), z=z, eps_mc=torch.zeros(1, G, dtype=torch.float64, device=dev),
+                u_rand=None if u is None else u[:, :, k].contiguous(), ratio=_ratio_weights(self.ratio_estimator, dev),
+                outputs=("conf_pred_mask", "grid_logp", "target_grid", "post_mean", "ood_mask", "refit_mean", "refit_sd"),
+                kind="ucb", alpha=self.alpha, temp=self.temp, grid_res=G, max_grid_refinements=0,
+                randomized=self.randomized, optimistic=self.optimistic))
+        acq = ops.cehvi_integrate(outs, eps_mc, self.cell_lower.to(dev), self.cell_upper.to(dev), alpha=self.alpha,
+                                  optimistic=self.optimistic)
+        self.last_outputs = {"per_output": outs, "acq": acq}
+        return acq.reshape(lead).to(X.dtype)

@@ -113,7 +113,10 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
     dev = Xq.device
     out_t = {"acq": torch.empty(b, dtype=torch.float64, device=dev)}
     shapes = {"target_grid": (b, G, q), "conf_pred_mask": (b, G, q), "q_conf_scores": (b, G, q), "grid_logp": (b, G),
-              "ood_mask": (b, q), "post_mean": (b, q), "num_accepted": (b, q), "post_var": (b,) if q == 1 else (b, q, q)}
+              "ood_mask": (b, q), "post_mean": (b, q), "num_accepted": (b, q), "post_var": (b,) if q == 1 else (b, q, q),
+              "refit_mean": (b, G), "refit_sd": (b,)}
+    if q > 1 and ("refit_mean" in outputs or "refit_sd" in outputs):
+        raise _lib.CboError("refit_mean / refit_sd are q = 1 outputs")
     for name in outputs:
         out_t[name] = torch.empty(shapes[name], dtype=torch.float64, device=dev)
     cout = _lib.OutputsF64(**{k: _ptr(v) for k, v in out_t.items()})
@@ -156,6 +159,33 @@ def conformal_acq_host(state: GPModelState, Xq_host: torch.Tensor, acq_host: tor
     _lib.check(st, "cbo_conformal_acq_host_f64")
     LAUNCH_COUNT += count_launches(state, b, params, ratio is not None, chunk)
     return acq_host
+
+
+def cehvi_integrate(per_output, eps_mc: torch.Tensor, cell_lower: torch.Tensor, cell_upper: torch.Tensor, *, alpha: float,
+                    optimistic: bool) -> torch.Tensor:
+    """cbo_cehvi_integrate_f64.  `per_output`: list (one per objective) of the dicts returned by `conformal_acq` with
+    outputs conf_pred_mask, grid_logp, target_grid, post_mean, ood_mask, refit_mean, refit_sd.  eps_mc (S, G, m)."""
+    global LAUNCH_COUNT
+    lib = _lib.load()
+    m = len(per_output)
+    keys = ("conf_pred_mask", "grid_logp", "target_grid", "post_mean", "ood_mask", "refit_mean", "refit_sd")
+    b, G = per_output[0]["conf_pred_mask"].shape
+    arrs = []
+    keep = []
+    for kname in keys:
+        ts = [_f64(o[kname]) for o in per_output]
+        keep.append(ts)
+        arrs.append((C.c_void_p * m)(*[t.data_ptr() for t in ts]))
+    eps_mc, cell_lower, cell_upper = map(_f64, (eps_mc, cell_lower, cell_upper))
+    _require_cuda(eps_mc, cell_lower, cell_upper)
+    S = eps_mc.numel() // (G * m)
+    n_cells = cell_lower.shape[0]
+    acq = torch.empty(b, dtype=torch.float64, device=eps_mc.device)
+    st = lib.cbo_cehvi_integrate_f64(m, b, G, S, *arrs, eps_mc.data_ptr(), cell_lower.data_ptr(), cell_upper.data_ptr(),
+                                     n_cells, float(alpha), int(bool(optimistic)), acq.data_ptr(), _stream())
+    _lib.check(st, "cbo_cehvi_integrate_f64")
+    LAUNCH_COUNT += 1
+    return acq
 
 
 def conf_mask_to_bounds(target_grid: torch.Tensor, conf_pred_mask: torch.Tensor):

@@ -104,6 +104,8 @@ typedef struct {
     double* post_mean;         /* b x q       mu(x)                                              */
     double* post_var;          /* q = 1: b, noisy predictive variance s(x); q > 1: b x q x q covariance S */
     double* num_accepted;      /* b x q       #{g : mask >= 0.5}                                 */
+    double* refit_mean;        /* b x G       q = 1: posterior mean at x under the model refit on (x, y_g)  */
+    double* refit_sd;          /* b           q = 1: its (noise-free) posterior sd                          */
 } cbo_outputs_f64;
 
 int cbo_version(void);
@@ -129,6 +131,16 @@ int cbo_conformal_acq_host_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ra
                                const double* eps_mc, const double* u_rand, double* acq_host,
                                double* Xq_staging /* b x q x d device */, double* acq_staging /* b device */,
                                void* workspace, size_t workspace_bytes, int64_t chunk, void* stream);
+
+/* cEHVI (conformalbo/mobo_acquisitions.py:24-45 + acquisitions.py:225-248, q = 1): combines the per-output results of m
+ * cbo_conformal_acq_f64 calls (arrays of m device pointers, each b x G or b) with the box decomposition
+ * (cell_lower / cell_upper: n_cells x m, as botorch's partitioning.get_hypercell_bounds()) into one value per candidate.
+ * eps_mc: S x G x m base samples of the acquisition sampler.  m <= 4. */
+int cbo_cehvi_integrate_f64(int64_t m, int64_t b, int64_t G, int64_t S, const double* const* mask,
+                            const double* const* logp, const double* const* grid, const double* const* mu,
+                            const double* const* ood, const double* const* refit_mean, const double* const* refit_sd,
+                            const double* eps_mc, const double* cell_lower, const double* cell_upper, int64_t n_cells,
+                            double alpha, int32_t optimistic, double* acq, void* stream);
 
 /* conf_mask_to_bounds: grid, mask: b x G x t (q = 1 squeezed) -> lb, ub: b x t.  G <= 2048. */
 int cbo_conf_mask_to_bounds_f64(const double* target_grid, const double* conf_pred_mask, int64_t b, int64_t G,

@@ -79,3 +79,26 @@ def test_finite_sample_coverage():
         lb, ub = conf_mask_to_bounds(out["target_grid"].unsqueeze(-1), out["mask"].unsqueeze(-1))
         hits += int(lb.item() <= yall[N].item() <= ub.item())
     assert hits / trials >= 1 - alpha - 0.12   # 60 trials: ~2.3 sigma slack below the nominal 0.8
+
+
+def test_cehvi_dense_equals_closed_form():
+    """Multi-objective oracle (intent semantics, App. C-5/C-6): dense refit pieces == closed-form pieces."""
+    from oracle import mobo
+    N, d, b, G, m = 16, 2, 5, 12, 2          # BASELINE config 3 shape: BraninCurrin-like d=2, t=2, N=16
+    g = torch.Generator().manual_seed(3)
+    X = torch.rand(N, d, generator=g, dtype=torch.float64)
+    Y = torch.stack([torch.sin(3 * X.sum(-1)), torch.cos(2 * X[:, 0]) - X[:, 1]], -1)
+    gps = [ogp.build_state(X, Y[:, k], 0.0, [0.4 + 0.1 * k] * d, 1.0 + 0.2 * k, 1e-2 * (k + 1)) for k in range(m)]
+    Xq = torch.rand(b, 1, d, generator=g, dtype=torch.float64)
+    eps_grid = torch.randn(G, m, generator=g, dtype=torch.float64)
+    eps_mc = torch.randn(3, G, m, generator=g, dtype=torch.float64)
+    z = 2.0 * ((torch.rand(N + 1, 8, generator=g) > 0.5).double() - 0.5)
+    u = torch.rand(b, G, m, generator=g, dtype=torch.float64)
+    lo, up = mobo.box_decomposition_2d(torch.tensor([-1.5, -1.5], dtype=torch.float64), Y)
+    assert lo.shape[0] >= 2 and torch.isinf(up[:, 1]).all()
+    kw = dict(alpha=0.2, temp=3e-2, grid_res=G, eps_grid=eps_grid, z=z, eps_mc=eps_mc, cell_lower=lo, cell_upper=up,
+              randomized=True, u_rand=u, optimistic=False)
+    a = mobo.cehvi(gps, Xq, impl="dense", **kw)
+    c = mobo.cehvi(gps, Xq, impl="closed", **kw)
+    assert (a > 0).any()
+    assert torch.allclose(a, c, rtol=1e-9, atol=1e-12)
