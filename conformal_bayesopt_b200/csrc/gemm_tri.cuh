@@ -12,7 +12,7 @@
 //
 // Design (B200, sm_100a): fp64 has no tcgen05 kind; the fp64 tensor path on Blackwell is
 // mma.sync m8n8k4 (SASS DMMA.8x8x4), measured at 37.0 TFLOP/s = the whole fp64 pipe
-// (profiles/r01_fp64_peak.log).  CTA tile 128 x 128, BK = 16, 3-stage cp.async pipeline into
+// (profiles/r01_fp64_peak.log).  CTA tile 128 x 128, BK = 16, 4-stage cp.async + mbarrier ring into
 // padded shared memory (row stride 20 doubles: conflict-free 64-bit fragment loads), 8 warps as
 // 2 (m) x 4 (n), warp tile 64 x 32 = 8 x 4 DMMA fragments, 64 fp64 accumulators per thread.
 // Tiles are issued longest-K first so the triangular imbalance fills the tail of the grid.
@@ -25,10 +25,11 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 128;
 constexpr int GEMM_BK = 16;
 constexpr int GEMM_LDS = GEMM_BK + 4;       // padded row stride (doubles)
-constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_PREFETCH = 2;         // tiles in flight; STAGES - PREFETCH = tiles of slack between warps
 constexpr int GEMM_THREADS = 256;
 constexpr int GEMM_STAGE_DOUBLES = (GEMM_BM + GEMM_BN) * GEMM_LDS;
-constexpr size_t GEMM_SMEM_BYTES = size_t(GEMM_STAGES) * GEMM_STAGE_DOUBLES * sizeof(double);
+constexpr size_t GEMM_SMEM_BYTES = size_t(GEMM_STAGES) * GEMM_STAGE_DOUBLES * sizeof(double) + 2 * GEMM_STAGES * sizeof(uint64_t);
 
 enum { TRI_FULL = 0, TRI_LOWER = 1, TRI_UPPER = 2 };
 
@@ -81,52 +82,65 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    // prologue: STAGES-1 tiles in flight
+    // Warp-decoupled pipeline: no CTA-wide barrier in the main loop.  full[s] completes when all 256 threads' cp.async
+    // copies of the tile in stage s have landed (cp.async.mbarrier.arrive); empty[s] completes when all 8 warps have
+    // consumed it.  Tiles are prefetched PREFETCH ahead into a ring of STAGES, so warps may drift apart by
+    // STAGES - PREFETCH tiles (absorbs the triangular imbalance on the diagonal block and scheduling jitter).
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(GEMM_STAGES) * GEMM_STAGE_DOUBLES);
+    uint64_t* empty = full + GEMM_STAGES;
+    if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+        for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full[s], GEMM_THREADS); mbar_init(&empty[s], GEMM_THREADS / 32); }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < GEMM_PREFETCH; ++s) {
         if (s < nk) {
             double* sA = smem + s * GEMM_STAGE_DOUBLES;
             gemm_load_stage(sA, sA + GEMM_BM * GEMM_LDS, A, lda, B, ldb, m0, n0, k_begin + s * GEMM_BK, M, tid);
+            cp_async_mbar_arrive(&full[s]);
         }
-        cp_async_commit();
     }
 
     const int fr = lane >> 2, fk = lane & 3;                 // fragment row / k within the 8x4 fragment
     for (int kt = 0; kt < nk; ++kt) {
-        cp_async_wait<GEMM_STAGES - 2>();
-        __syncthreads();                                      // tile kt landed; everyone done with tile kt-1
-        {
-            int nt = kt + GEMM_STAGES - 1;
+        {   // producer side: tile kt + PREFETCH goes into the stage last used by tile kt + PREFETCH - STAGES
+            const int nt = kt + GEMM_PREFETCH;
             if (nt < nk) {
-                double* sA = smem + (nt % GEMM_STAGES) * GEMM_STAGE_DOUBLES;
+                const int st = nt % GEMM_STAGES;
+                mbar_wait(&empty[st], ((nt / GEMM_STAGES) & 1) ^ 1);
+                double* sA = smem + st * GEMM_STAGE_DOUBLES;
                 gemm_load_stage(sA, sA + GEMM_BM * GEMM_LDS, A, lda, B, ldb, m0, n0, k_begin + nt * GEMM_BK, M, tid);
+                cp_async_mbar_arrive(&full[st]);
             }
-            cp_async_commit();
         }
+        const int st = kt % GEMM_STAGES;
         // On the diagonal 128 x 128 block of the triangular factor this warp's 32 columns see only zeros for part of
         // the K range: lower  -> k < n_warp_end,  upper -> k + BK > n_warp_begin.  Skip those MMAs (warp-uniform).
-        {
-            const int k0 = k_begin + kt * GEMM_BK;
-            if (tri == TRI_LOWER && k0 >= n0 + 32 * (wn + 1)) continue;
-            if (tri == TRI_UPPER && k0 + GEMM_BK <= n0 + 32 * wn) continue;
+        const int k0 = k_begin + kt * GEMM_BK;
+        const bool skip = (tri == TRI_LOWER && k0 >= n0 + 32 * (wn + 1)) || (tri == TRI_UPPER && k0 + GEMM_BK <= n0 + 32 * wn);
+        if (!skip) {
+            mbar_wait(&full[st], (kt / GEMM_STAGES) & 1);
+            const double* sA = smem + st * GEMM_STAGE_DOUBLES + (wm * 64 + fr) * GEMM_LDS + fk;
+            const double* sB = smem + st * GEMM_STAGE_DOUBLES + GEMM_BM * GEMM_LDS + (wn * 32 + fr) * GEMM_LDS + fk;
+#pragma unroll
+            for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
+                double a[8], b[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = sA[i * 8 * GEMM_LDS + ks * 4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = sB[j * 8 * GEMM_LDS + ks * 4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
         }
-        const double* sA = smem + (kt % GEMM_STAGES) * GEMM_STAGE_DOUBLES + (wm * 64 + fr) * GEMM_LDS + fk;
-        const double* sB = smem + (kt % GEMM_STAGES) * GEMM_STAGE_DOUBLES + GEMM_BM * GEMM_LDS +
-                           (wn * 32 + fr) * GEMM_LDS + fk;
-#pragma unroll
-        for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
-            double a[8], b[4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = sA[i * 8 * GEMM_LDS + ks * 4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = sB[j * 8 * GEMM_LDS + ks * 4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);              // this warp is done with the stage (also when it skipped)
     }
     cp_async_wait<0>();
+    __syncthreads();
 
     // epilogue: C tile; each thread owns rows (wm*64 + i*8 + fr), cols (wn*32 + j*8 + 2*fk + {0,1})
     double rn[8];
