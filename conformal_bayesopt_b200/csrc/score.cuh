@@ -34,6 +34,8 @@ struct ScoreArgs {
     // model scalars
     double noise, kappa, alpha_lvl, temp, beta_prime, best_f;
     int kind, optimistic, randomized, eps_per_candidate;
+    // sigmoid constants, passed as parameters so that they are constant-bank operands instead of per-iteration moves
+    double k_magic, k_c0, k_c1n, k_c2, k_c3n;
     // per-call tables (train side)
     const double* a;        // Np  noise*alpha
     const double* h0;       // Np
@@ -99,10 +101,8 @@ k_score(const ScoreArgs p) {
     double* tab = sm;                                   // 2^(j/16): one 128-byte row, conflict-free for any index pattern
     double* sdr = tab + 16;                             // density ratio of train point i (0 beyond N)
     double* pbase = sdr + Np + size_t(pair) * (3 * size_t(Np) + 4 * size_t(G) + 64);
-    double* sqa = pbase;
-    double* sqb = sqa + Np;
-    double* sqc = sqb + Np;
-    double* g_cw = sqc + Np;                            // phase B stores the hard count here, phase C the conf. weight
+    double* sq = pbase;                                 // [i][3] = (qa_i, qb_i, qc_i): 24-byte stride, conflict-free LDS.64
+    double* g_cw = sq + 3 * size_t(Np);                            // phase B stores the hard count here, phase C the conf. weight
     double* g_nc = g_cw + G;                            // sum rho        -> non-conformal weight
     double* g_mf = g_nc + G;                            // sum rho * dr   -> refit mean
     double* g_mk = g_mf + G;                            // mask
@@ -188,7 +188,7 @@ k_score(const ScoreArgs p) {
                         qb = c1 * (-2.0 * iv * ai[j] * wi);              // b_g coefficient
                         qc = c1 * (fma(iv * ai[j], ai[j], lv_c - lv));   // constant
                     }
-                    sqa[i] = qa; sqb[i] = qb; sqc[i] = qc;
+                    sq[3 * i] = qa; sq[3 * i + 1] = qb; sq[3 * i + 2] = qc;
                 }
             }
         }
@@ -216,14 +216,15 @@ k_score(const ScoreArgs p) {
                 // [-1/2, 1/2] (16-entry table + near-minimax cubic, rel. err 1.2e-9); 1/(1+e) from a MUFU.RCP64H
                 // seed and one Newton step.  |x| is clamped at 946 = 41 * 16/ln2 in the integer domain (rho is
                 // 0 or 1 to 2e-18 beyond that).
-                constexpr double kMagic = 6755399441055744.0;             // 1.5 * 2^52
-                constexpr double kC0 = 0.9999999988534117, kC1 = 0.043321698775061875,
-                                 kC2 = 0.0009384214835622084, kC3 = 1.3551125681305332e-05;
+                const double kMagic = p.k_magic;                          // 1.5 * 2^52
+                const double kC0 = p.k_c0, kC1n = p.k_c1n, kC2 = p.k_c2, kC3n = p.k_c3n;
                 constexpr int kSatHi = 0x408d9000;                        // hiword(946.0)
-                double qa = sqa[lane], qb = sqb[lane], qc = sqc[lane], dr = sdr[lane];
+                const double* tq = sq + 3 * lane;
+                const double* td = sdr + lane;
+                double qa = tq[0], qb = tq[1], qc = tq[2], dr = td[0];
                 for (int i = lane; i < N32; i += 32) {
-                    const int in = (i + 32 < N32) ? i + 32 : lane;        // prefetch the next row's coefficients
-                    const double qa_n = sqa[in], qb_n = sqb[in], qc_n = sqc[in], dr_n = sdr[in];
+                    tq += 96; td += 32;                                   // next row (reads past N32 stay inside shared memory)
+                    const double qa_n = tq[0], qb_n = tq[1], qc_n = tq[2], dr_n = td[0];
                     double x[SCORE_GPW];
 #pragma unroll
                     for (int k = 0; k < SCORE_GPW; ++k) {
@@ -242,8 +243,8 @@ k_score(const ScoreArgs p) {
                         }
 #pragma unroll
                         for (int k = 0; k < SCORE_GPW; ++k) {
-                            double pl = fma(yn[k], -kC3, kC2);
-                            pl = fma(pl, yn[k], -kC1);
+                            double pl = fma(yn[k], kC3n, kC2);
+                            pl = fma(pl, yn[k], kC1n);
                             pl = fma(pl, yn[k], kC0);                     // exp(-yn ln2/16)
                             int n = __double2loint(t[k]);
                             double ev = tab[n & 15] * pl;
