@@ -58,10 +58,10 @@ struct ScoreArgs {
     double* post_mean; double* post_var; double* num_acc; double* refit_mean; double* refit_sd;
 };
 
-// shared: tab[16] | dr[Np]        per pair: qa, qb, qc [Np] | 4 x [G] (raw cnt/sr/sw, then cw/nc/mf/mk) | zt[4][16]
+// shared: tab[16] | dr[Np]        per pair: qa, qb, qc [Np] | 4 x [G] (raw cnt/sr/sw, then cw/nc/mf/mk) | zt[4][16] | pad[96]
 __host__ __device__ inline size_t score_smem_shared_bytes(int Np) { return sizeof(double) * (16 + size_t(Np)); }
 __host__ __device__ inline size_t score_smem_pair_bytes(int Np, int G) {
-    return sizeof(double) * (3 * size_t(Np) + 4 * size_t(G) + 64);
+    return sizeof(double) * (3 * size_t(Np) + 4 * size_t(G) + 64 + 96);   // +96: the coefficient prefetch reads one row past N32
 }
 __host__ __device__ inline size_t score_smem_bytes(int Np, int G, int npairs) {
     return score_smem_shared_bytes(Np) + size_t(npairs) * score_smem_pair_bytes(Np, G);
@@ -100,7 +100,7 @@ k_score(const ScoreArgs p) {
 
     double* tab = sm;                                   // 2^(j/16): one 128-byte row, conflict-free for any index pattern
     double* sdr = tab + 16;                             // density ratio of train point i (0 beyond N)
-    double* pbase = sdr + Np + size_t(pair) * (3 * size_t(Np) + 4 * size_t(G) + 64);
+    double* pbase = sdr + Np + size_t(pair) * (3 * size_t(Np) + 4 * size_t(G) + 64 + 96);
     double* sq = pbase;                                 // [i][3] = (qa_i, qb_i, qc_i): 24-byte stride, conflict-free LDS.64
     double* g_cw = sq + 3 * size_t(Np);                            // phase B stores the hard count here, phase C the conf. weight
     double* g_nc = g_cw + G;                            // sum rho        -> non-conformal weight

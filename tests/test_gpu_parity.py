@@ -260,3 +260,44 @@ def test_joint_batches_match_oracle(N, d, q, b, G, temp, rand, ratio_on, refine,
     assert torch.allclose(got["conf_pred_mask"], want["mask"], rtol=0, atol=1e-6)
     assert torch.allclose(got["ood_mask"], want["ood"][:, 0, :], rtol=RTOL, atol=1e-12)
     assert _close(got["acq"], want["acq"])
+
+
+BIGCASES = [
+    # N, d, b, G, temp, S, Sp  -- shapes that leave the tuned configuration (fewer warp pairs per SM, unstaged rows kernel,
+    # 16 probes, many MC samples, long grids)
+    (2500, 3, 6, 16, 3e-2, 1, 8),
+    (1300, 33, 5, 200, 1e-2, 16, 16),
+    (4000, 2, 3, 8, 3e-2, 2, 4),
+    (600, 64, 4, 1000, 3e-2, 1, 8),
+]
+
+
+@pytest.mark.parametrize("N,d,b,G,temp,S,Sp", BIGCASES)
+def test_shapes_outside_the_tuned_configuration(N, d, b, G, temp, S, Sp):
+    from conformal_bayesopt_b200 import ops
+    dev = _dev()
+    p = make_problem(N, d, seed=N, fn="sin", lengthscale=0.5 * math.sqrt(d / 3.0))
+    inp = make_inputs(N, d, b, 1, G, S=S, Sp=Sp, seed=N)
+    ratio, ratio_w = _ratio(d, dev)
+    kw = dict(kind="ucb", alpha=0.1, temp=temp, grid_res=G, max_grid_refinements=1, randomized=True, optimistic=True,
+              beta_prime=1.3)
+    want = closed_form.conformal_acquisition(oracle_state(p), inp["Xq"], eps_grid=inp["eps_grid"], z=inp["z"],
+                                             eps_mc=inp["eps_mc"], ratio=ratio, u_rand=inp["u_rand"], **kw)
+    got = _run(p, inp, dev, ratio_w, outputs=("conf_pred_mask", "post_var"), **kw)
+    assert _close(got["post_var"], want["S"][:, 0, 0])
+    assert torch.allclose(got["conf_pred_mask"], want["mask"][:, :, 0], rtol=0, atol=1e-6)
+    assert _close(got["acq"], want["acq"])
+
+
+def test_unsupported_shapes_are_refused():
+    from conformal_bayesopt_b200 import _lib
+    dev = _dev()
+    p = make_problem(16, 2, seed=1)
+    inp = make_inputs(16, 2, 4, 1, 8, S=17, seed=1)               # 17 MC samples > MAX_S
+    with pytest.raises(_lib.CboError, match="unsupported"):
+        _run(p, inp, dev, kind="ucb", alpha=0.1, temp=0.1, grid_res=8, beta_prime=1.0)
+    inp = make_inputs(16, 2, 4, 5, 8, seed=1)                      # q = 5
+    with pytest.raises(_lib.CboError):
+        from conformal_bayesopt_b200 import ops
+        ops.conformal_acq(_state(p, dev), inp["Xq"].to(dev), eps_grid=inp["eps_grid"].to(dev), z=inp["z"].to(dev),
+                          eps_mc=inp["eps_mc"].to(dev), kind="ucb", alpha=0.1, temp=0.1, grid_res=8, beta_prime=1.0)
