@@ -177,19 +177,24 @@ int num_sms() {
 }
 
 template <bool SOFT>
-cudaError_t launch_score(const cbo::ScoreArgs& a, cudaStream_t st) {
-    const int npairs = cbo::score_pairs_for(a.Np, a.G);
-    if (npairs < 1) return cudaErrorInvalidConfiguration;
-    size_t smem = cbo::score_smem_bytes(a.Np, a.G, npairs);
+cudaError_t launch_score(const cbo::ScoreArgs& a_in, cudaStream_t st) {
+    cbo::ScoreArgs a = a_in;
+    // warps per candidate: pairs when there are enough candidates to fill the SMs, wider groups for small batches
+    int wl = 1;
+    while (wl < 4 && a.n_cand * (1 << wl) < 16 * num_sms()) ++wl;
+    const int ngroups = cbo::score_groups_for(a.Np, a.G, 1 << wl);
+    if (ngroups < 1) return cudaErrorInvalidConfiguration;
+    a.wpg_log2 = wl;
+    size_t smem = cbo::score_smem_bytes(a.Np, a.G, ngroups);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(cbo::k_score<SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    int grid = (a.n_cand + npairs - 1) / npairs;       // persistent: one CTA per SM, one warp pair per candidate in flight
+    int grid = (a.n_cand + ngroups - 1) / ngroups;     // persistent: one CTA per SM, one warp group per candidate in flight
     if (grid > num_sms()) grid = num_sms();
-    cbo::k_score<SOFT><<<grid, npairs * 64, smem, st>>>(a);
+    cbo::k_score<SOFT><<<grid, ngroups * (32 << wl), smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -345,11 +350,11 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
         // ---- v = L^-1 u (+ ||v||^2 partials), w = L^-T v ------------------------------------------
         {
             TimeScope ts_(T_GEMM1, s, 1);
-            CBO_CUDA(cbo::launch_gemm_tn(w.UW, Np, gp->linv, Np, w.V, Np, n, Np, Np, cbo::TRI_LOWER, w.rn, s));
+            CBO_CUDA(cbo::launch_gemm_tn(w.UW, Np, gp->linv, Np, w.V, Np, n, Np, Np, cbo::TRI_LOWER, w.rn, s, num_sms()));
         }
         {
             TimeScope ts_(T_GEMM2, s, 1);
-            CBO_CUDA(cbo::launch_gemm_tn(w.V, Np, gp->linv_t, Np, w.UW, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s));
+            CBO_CUDA(cbo::launch_gemm_tn(w.V, Np, gp->linv_t, Np, w.UW, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms()));
         }
 
         // ---- scores / rank / mask / integration ----------------------------------------------------

@@ -33,17 +33,21 @@ constexpr size_t GEMM_SMEM_BYTES = size_t(GEMM_STAGES) * GEMM_STAGE_DOUBLES * si
 
 enum { TRI_FULL = 0, TRI_LOWER = 1, TRI_UPPER = 2 };
 
+template <int BM>
 __device__ __forceinline__ void gemm_load_stage(double* sA, double* sB, const double* __restrict__ A, int64_t lda,
                                                 const double* __restrict__ B, int64_t ldb, int m0, int n0, int k0,
                                                 int M, int tid) {
-    // A tile: 128 rows x 16 doubles = 1024 16-byte chunks; same for B.  4 + 4 chunks per thread.
+    // A tile: BM rows x 16 doubles = BM * 8 16-byte chunks; B tile: 128 rows = 1024 chunks (4 per thread).
+    constexpr int A_CHUNKS = BM * GEMM_BK / 2;
 #pragma unroll
-    for (int it = 0; it < (GEMM_BM * GEMM_BK / 2) / GEMM_THREADS; ++it) {
+    for (int it = 0; it < (A_CHUNKS + GEMM_THREADS - 1) / GEMM_THREADS; ++it) {
         int chunk = tid + it * GEMM_THREADS;
-        int r = chunk >> 3, cc = chunk & 7;
-        int gr = m0 + r;
-        gr = gr < M ? gr : M - 1;             // clamp: rows beyond M are computed but never stored
-        cp_async16(sA + r * GEMM_LDS + 2 * cc, A + int64_t(gr) * lda + k0 + 2 * cc);
+        if (A_CHUNKS % GEMM_THREADS == 0 || chunk < A_CHUNKS) {
+            int r = chunk >> 3, cc = chunk & 7;
+            int gr = m0 + r;
+            gr = gr < M ? gr : M - 1;             // clamp: rows beyond M are computed but never stored
+            cp_async16(sA + r * GEMM_LDS + 2 * cc, A + int64_t(gr) * lda + k0 + 2 * cc);
+        }
     }
 #pragma unroll
     for (int it = 0; it < (GEMM_BN * GEMM_BK / 2) / GEMM_THREADS; ++it) {
@@ -53,6 +57,9 @@ __device__ __forceinline__ void gemm_load_stage(double* sA, double* sB, const do
     }
 }
 
+// MF = 8-row DMMA fragments per warp in m: CTA tile (16 MF) x 128.  MF = 8 is the throughput configuration; smaller MF
+// keep all SMs busy (and cut the wasted rows) when there are only a few hundred candidate rows.
+template <int MF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
               double* __restrict__ C, int64_t ldc, int M, int Nn, int K, int tri,
@@ -63,22 +70,24 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     // 2 x 4 warps.  Warps w and w+4 share an SM sub-partition (w % 4): give them n-slices wn and 3-wn so that the
     // triangular skipping on the diagonal block (below) loads every sub-partition's fp64 pipe equally.
     const int wm = warp >> 2, wn = (warp < 4) ? warp : 7 - warp;
-    const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    constexpr int BM = 16 * MF;
+    constexpr int PF = GEMM_PREFETCH;
+    const int tiles_m = (M + BM - 1) / BM;
     const int tiles_n = Nn / GEMM_BN;
     // longest-K tiles first: lower -> last n-tile first; upper / full -> first n-tile first
     const int t = blockIdx.x;
     const int n_ord = t / tiles_m;
     const int n_tile = (tri == TRI_LOWER) ? (tiles_n - 1 - n_ord) : n_ord;
     const int m_tile = t - n_ord * tiles_m;
-    const int m0 = m_tile * GEMM_BM, n0 = n_tile * GEMM_BN;
+    const int m0 = m_tile * BM, n0 = n_tile * GEMM_BN;
     int k_begin = 0, k_end = K;
     if (tri == TRI_LOWER) k_end = min(K, n0 + GEMM_BN);
     if (tri == TRI_UPPER) k_begin = n0;
     const int nk = (k_end - k_begin) / GEMM_BK;
 
-    double acc[8][4][2];
+    double acc[MF][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MF; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -94,10 +103,10 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     }
     __syncthreads();
 #pragma unroll
-    for (int s = 0; s < GEMM_PREFETCH; ++s) {
+    for (int s = 0; s < PF; ++s) {
         if (s < nk) {
             double* sA = smem + s * GEMM_STAGE_DOUBLES;
-            gemm_load_stage(sA, sA + GEMM_BM * GEMM_LDS, A, lda, B, ldb, m0, n0, k_begin + s * GEMM_BK, M, tid);
+            gemm_load_stage<BM>(sA, sA + BM * GEMM_LDS, A, lda, B, ldb, m0, n0, k_begin + s * GEMM_BK, M, tid);
             cp_async_mbar_arrive(&full[s]);
         }
     }
@@ -105,12 +114,12 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     const int fr = lane >> 2, fk = lane & 3;                 // fragment row / k within the 8x4 fragment
     for (int kt = 0; kt < nk; ++kt) {
         {   // producer side: tile kt + PREFETCH goes into the stage last used by tile kt + PREFETCH - STAGES
-            const int nt = kt + GEMM_PREFETCH;
+            const int nt = kt + PF;
             if (nt < nk) {
                 const int st = nt % GEMM_STAGES;
                 mbar_wait(&empty[st], ((nt / GEMM_STAGES) & 1) ^ 1);
                 double* sA = smem + st * GEMM_STAGE_DOUBLES;
-                gemm_load_stage(sA, sA + GEMM_BM * GEMM_LDS, A, lda, B, ldb, m0, n0, k_begin + nt * GEMM_BK, M, tid);
+                gemm_load_stage<BM>(sA, sA + BM * GEMM_LDS, A, lda, B, ldb, m0, n0, k_begin + nt * GEMM_BK, M, tid);
                 cp_async_mbar_arrive(&full[st]);
             }
         }
@@ -121,17 +130,17 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
         const bool skip = (tri == TRI_LOWER && k0 >= n0 + 32 * (wn + 1)) || (tri == TRI_UPPER && k0 + GEMM_BK <= n0 + 32 * wn);
         if (!skip) {
             mbar_wait(&full[st], (kt / GEMM_STAGES) & 1);
-            const double* sA = smem + st * GEMM_STAGE_DOUBLES + (wm * 64 + fr) * GEMM_LDS + fk;
-            const double* sB = smem + st * GEMM_STAGE_DOUBLES + GEMM_BM * GEMM_LDS + (wn * 32 + fr) * GEMM_LDS + fk;
+            const double* sA = smem + st * GEMM_STAGE_DOUBLES + (wm * (8 * MF) + fr) * GEMM_LDS + fk;
+            const double* sB = smem + st * GEMM_STAGE_DOUBLES + BM * GEMM_LDS + (wn * 32 + fr) * GEMM_LDS + fk;
 #pragma unroll
             for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
-                double a[8], b[4];
+                double a[MF], b[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = sA[i * 8 * GEMM_LDS + ks * 4];
+                for (int i = 0; i < MF; ++i) a[i] = sA[i * 8 * GEMM_LDS + ks * 4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) b[j] = sB[j * 8 * GEMM_LDS + ks * 4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < MF; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
@@ -142,11 +151,11 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     cp_async_wait<0>();
     __syncthreads();
 
-    // epilogue: C tile; each thread owns rows (wm*64 + i*8 + fr), cols (wn*32 + j*8 + 2*fk + {0,1})
-    double rn[8];
+    // epilogue: C tile; each thread owns rows (wm*8*MF + i*8 + fr), cols (wn*32 + j*8 + 2*fk + {0,1})
+    double rn[MF];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int row = m0 + wm * 64 + i * 8 + fr;
+    for (int i = 0; i < MF; ++i) {
+        int row = m0 + wm * (8 * MF) + i * 8 + fr;
         double s2 = 0.0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -161,16 +170,16 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     }
     if (rownorm_partial != nullptr) {
         __syncthreads();                                      // smem reuse
-        double* red = smem;                                   // [128 rows][4 n-warps]
+        double* red = smem;                                   // [BM rows][4 n-warps]
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < MF; ++i) {
             double s2 = rn[i];
             s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
             s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-            if (fk == 0) red[(wm * 64 + i * 8 + fr) * 4 + wn] = s2;
+            if (fk == 0) red[(wm * (8 * MF) + i * 8 + fr) * 4 + wn] = s2;
         }
         __syncthreads();
-        if (tid < GEMM_BM) {
+        if (tid < BM) {
             int row = m0 + tid;
             if (row < M) {
                 double s2 = (red[tid * 4 + 0] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]);
@@ -180,19 +189,35 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     }
 }
 
-inline cudaError_t launch_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
-                                  int M, int Nn, int K, int tri, double* rownorm_partial, cudaStream_t stream) {
+template <int MF>
+inline cudaError_t launch_gemm_tn_t(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                                    int M, int Nn, int K, int tri, double* rownorm_partial, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tn_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tn_f64<MF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)GEMM_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    int tiles_m = (M + GEMM_BM - 1) / GEMM_BM, tiles_n = Nn / GEMM_BN;
-    k_gemm_tn_f64<<<tiles_m * tiles_n, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(A, lda, B, ldb, C, ldc, M, Nn, K, tri,
-                                                                               rownorm_partial);
+    int tiles_m = (M + 16 * MF - 1) / (16 * MF), tiles_n = Nn / GEMM_BN;
+    k_gemm_tn_f64<MF><<<tiles_m * tiles_n, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(A, lda, B, ldb, C, ldc, M, Nn, K, tri,
+                                                                                   rownorm_partial);
     return cudaGetLastError();
+}
+
+inline cudaError_t launch_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                                  int M, int Nn, int K, int tri, double* rownorm_partial, cudaStream_t stream,
+                                  int num_sms = 148) {
+    // pick the largest m-tile that still yields ~2 CTAs per SM; few rows -> small tiles (latency, no wasted rows)
+    const int tiles_n = Nn / GEMM_BN;
+    auto ctas = [&](int bm) { return ((M + bm - 1) / bm) * tiles_n; };
+    if (ctas(128) >= 2 * num_sms || M > 2048)
+        return launch_gemm_tn_t<8>(A, lda, B, ldb, C, ldc, M, Nn, K, tri, rownorm_partial, stream);
+    if (ctas(64) >= 2 * num_sms || M > 64)
+        return launch_gemm_tn_t<4>(A, lda, B, ldb, C, ldc, M, Nn, K, tri, rownorm_partial, stream);
+    if (M > 16)
+        return launch_gemm_tn_t<2>(A, lda, B, ldb, C, ldc, M, Nn, K, tri, rownorm_partial, stream);
+    return launch_gemm_tn_t<1>(A, lda, B, ldb, C, ldc, M, Nn, K, tri, rownorm_partial, stream);
 }
 
 }  // namespace cbo

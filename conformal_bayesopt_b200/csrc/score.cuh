@@ -1,5 +1,5 @@
 // score.cuh -- nonconformity scores, density-ratio-weighted conformal rank, mask and the
-// importance-weighted acquisition value.  One warp PAIR per candidate, pair-local named barriers.
+// importance-weighted acquisition value.  One warp GROUP (2..16 warps) per candidate, group-local named barriers.
 //
 // Fuses, per candidate (q = 1, one output), what the reference evaluates as dense batched tensors
 // of shape (b, G, N+1, ...) (conformalbo/helpers.py:266-325, conformalbo/acquisitions.py:57-76,
@@ -15,9 +15,10 @@
 //   phase C  (thread per grid point) weighted mass, randomised step, conformal mask, log-density,
 //            optimistic mask, refit mean (A-5, A-6)
 //   phase D  (warp reduce over the grid) importance-weighted integration (A-7)
-// Pairs never wait for each other (bar.sync on a pair-private barrier id, 64 threads): while one
-// pair is in the latency-bound phases A/C/D the other warps of the SM sub-partition keep the fp64
-// pipe busy with phase B.
+// Groups never wait for each other (bar.sync on a group-private barrier id): while one group is in the
+// latency-bound phases A/C/D the other warps of the SM sub-partition keep the fp64 pipe busy with phase B.
+// Large batches use pairs (8 candidates in flight per SM); small batches widen the group (up to 16 warps on one
+// candidate) so that a handful of candidates still uses whole SMs -- latency instead of throughput.
 #pragma once
 #include "common.cuh"
 #include "rows.cuh"
@@ -34,6 +35,7 @@ struct ScoreArgs {
     // model scalars
     double noise, kappa, alpha_lvl, temp, beta_prime, best_f;
     int kind, optimistic, randomized, eps_per_candidate;
+    int wpg_log2;           // log2(warps per candidate group): 1 (pairs) .. 4
     // sigmoid constants, passed as parameters so that they are constant-bank operands instead of per-iteration moves
     double k_magic, k_c0, k_c1n, k_c2, k_c3n;
     // per-call tables (train side)
@@ -66,24 +68,27 @@ __host__ __device__ inline size_t score_smem_pair_bytes(int Np, int G) {
 __host__ __device__ inline size_t score_smem_bytes(int Np, int G, int npairs) {
     return score_smem_shared_bytes(Np) + size_t(npairs) * score_smem_pair_bytes(Np, G);
 }
-// warp pairs per CTA that fit 227 KB of shared memory (0: unsupported shape)
-inline int score_pairs_for(int Np, int G) {
+// warp groups (of `wpg` warps) per CTA that fit 227 KB of shared memory and 16 warps (0: unsupported shape)
+inline int score_groups_for(int Np, int G, int wpg) {
     size_t avail = 227 * 1024;
     if (score_smem_shared_bytes(Np) + score_smem_pair_bytes(Np, G) > avail) return 0;
     size_t w = (avail - score_smem_shared_bytes(Np)) / score_smem_pair_bytes(Np, G);
-    return int(w > SCORE_MAX_PAIRS ? SCORE_MAX_PAIRS : w);
+    size_t cap = size_t(2 * SCORE_MAX_PAIRS / wpg);
+    return int(w > cap ? cap : w);
 }
+inline int score_pairs_for(int Np, int G) { return score_groups_for(Np, G, 2); }
 
-__device__ __forceinline__ void pair_barrier(int pair) {
-    asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+// barrier over the `nthr` threads of one warp group (barrier ids 1..8; id 0 is __syncthreads)
+__device__ __forceinline__ void pair_barrier(int group, int nthr) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(nthr) : "memory");
 }
-// barrier over the 64 threads of a pair that also ORs a predicate across them
-__device__ __forceinline__ int pair_barrier_or(int pair, int pred) {
+// ... that also ORs a predicate across them
+__device__ __forceinline__ int pair_barrier_or(int group, int nthr, int pred) {
     int r;
     asm volatile(
-        "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %2, 0;\n\tbar.red.or.pred p, %1, 64, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %3, 0;\n\tbar.red.or.pred p, %1, %2, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
         : "=r"(r)
-        : "r"(pair + 1), "r"(pred)
+        : "r"(group + 1), "r"(nthr), "r"(pred)
         : "memory");
     return r;
 }
@@ -93,8 +98,9 @@ __global__ void __launch_bounds__(SCORE_MAX_PAIRS * 64, 1)
 k_score(const ScoreArgs p) {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pair = warp >> 1, half = warp & 1, ptid = tid & 63;      // thread index within the pair
-    const int npairs = blockDim.x >> 6;
+    const int wl = p.wpg_log2, GT = 32 << wl;                            // threads per candidate group
+    const int pair = warp >> wl, half = warp & ((1 << wl) - 1), ptid = tid & (GT - 1);   // group, warp in group, thread in group
+    const int npairs = blockDim.x >> (5 + wl);
     const int N = p.N, Np = p.Np, G = p.G, Sp = p.Sp;
     const int N32 = (N + 31) & ~31;                     // Np is a multiple of 128 >= N32
 
@@ -123,8 +129,9 @@ k_score(const ScoreArgs p) {
         // ---- phase A (64 threads) ------------------------------------------------------------------
         {   // pull the next candidate's W row towards L2 while this one is processed
             int cn = c + total_pairs;
-            if (cn < p.n_cand && ptid * 16 < Np)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.W + int64_t(cn) * Np + ptid * 16));
+            if (cn < p.n_cand)
+                for (int o = ptid * 16; o < Np; o += GT * 16)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.W + int64_t(cn) * Np + o));
         }
         double vnorm = 0.0;
         for (int t = 0; t < p.tiles_n; ++t) vnorm += p.rn_partial[int64_t(c) * p.tiles_n + t];
@@ -137,7 +144,7 @@ k_score(const ScoreArgs p) {
             double zcs = p.z_cand[s];
             zcc = fma(zcs, (zcs - p.ut[int64_t(c) * Sp + s]) * inv_s, zcc);
         }
-        {   // nibble tables of z_i . c (z_i in {+-1}^Sp is stored as a bit mask): one entry per thread
+        if (ptid < 64) {   // nibble tables of z_i . c (z_i in {+-1}^Sp is stored as a bit mask): one entry per thread
             const int t4 = (ptid >> 4) * 4, e = ptid & 15;
             double acc = 0.0;
 #pragma unroll
@@ -156,13 +163,13 @@ k_score(const ScoreArgs p) {
         const double lv_c = -0.5 * log(var_c) - 0.5 * kLog2Pi;
         // score_c(g) = lv_c - iv_c (noise b_g)^2 ;  score_i(g) = lv_i - iv_i (a_i - noise w_i b_g)^2
         const double qa_c = -iv_c * p.noise * p.noise;
-        pair_barrier(pair);                                              // nibble tables visible 
-        for (int i0 = ptid; i0 < N32; i0 += 256) {                       // 4 independent loads in flight per thread
+        pair_barrier(pair, GT);                                          // nibble tables visible
+        for (int i0 = ptid; i0 < N32; i0 += 4 * GT) {                    // 4 independent loads in flight per thread
             double w[4], h0[4], ai[4];
             uint32_t bits[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                int i = i0 + 64 * j;
+                int i = i0 + GT * j;
                 bool ok = i < N;
                 w[j] = ok ? Wc[i] : 0.0;
                 h0[j] = ok ? p.h0[i] : 1.0;
@@ -171,7 +178,7 @@ k_score(const ScoreArgs p) {
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                int i = i0 + 64 * j;
+                int i = i0 + GT * j;
                 if (i < N32) {
                     double qa = 0.0, qb = 0.0, qc = -1e300;              // padding: x = -1e300, never counted, dr = 0
                     if (i < N) {
@@ -197,10 +204,10 @@ k_score(const ScoreArgs p) {
         const double drc = p.drc ? p.drc[c] : 1.0;
         const double norm = sum_dr + drc;
         const double omega_c = drc / norm;
-        bad = pair_barrier_or(pair, bad);                                 // tables complete; any non-positive variance?
+        bad = pair_barrier_or(pair, GT, bad);                                 // tables complete; any non-positive variance?
 
         // ---- phase B: 4 grid points per pass, passes alternate between the two warps ----------------
-        for (int g0 = half * SCORE_GPW; g0 < G; g0 += 2 * SCORE_GPW) {
+        for (int g0 = half * SCORE_GPW; g0 < G; g0 += (SCORE_GPW << wl)) {
             double bg[SCORE_GPW], sr[SCORE_GPW], sw[SCORE_GPW];
             unsigned cneg[SCORE_GPW];
 #pragma unroll
@@ -275,10 +282,10 @@ k_score(const ScoreArgs p) {
                 if (lane == 0 && g0 + k < G) { g_cw[g0 + k] = double(cnt); g_nc[g0 + k] = tr; g_mf[g0 + k] = tw; }
             }
         }
-        pair_barrier(pair);                                               // raw sums of every grid point are in shared memory
+        pair_barrier(pair, GT);                                           // raw sums of every grid point are in shared memory
 
         // ---- phase C: thread per grid point -----------------------------------------------------------
-        for (int g = ptid; g < G; g += 64) {
+        for (int g = ptid; g < G; g += GT) {
             const double my_cnt = g_cw[g], my_sr = g_nc[g], my_sw = g_mf[g];
             double n_g = my_cnt + 1.0;                                  // includes the candidate itself
             double M, rho_self;
@@ -313,7 +320,7 @@ k_score(const ScoreArgs p) {
             if (p.qscore) p.qscore[int64_t(c) * G + g] = scc;
             if (p.refit_mean) p.refit_mean[int64_t(c) * G + g] = mf;
         }
-        pair_barrier(pair);
+        pair_barrier(pair, GT);
 
         // ---- phase D (first warp of the pair): integrate over the grid ---------------------------------
         if (half == 0) {
