@@ -72,7 +72,7 @@ struct Carver {
 };
 
 struct Workspace {
-    double *zp, *tmp, *T, *a, *h0, *dr_train, *sum_dr, *XsT;
+    double *zp, *tmp, *T, *a, *h0, *dr_train, *sum_dr, *XsT, *eps_absmax;
     uint32_t* zb;
     double *UW, *V, *mu, *ut, *drc, *rn;
     double *cscale, *nacc, *acq_scratch, *stats;      // refinement only
@@ -99,6 +99,7 @@ Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, 
     w.sum_dr = c.take<double>(8);
     w.zb = c.take<uint32_t>(Np);
     w.XsT = c.take<double>(Np * d);
+    w.eps_absmax = c.take<double>(p->eps_per_candidate ? b : 8);
     w.UW = c.take<double>(C * Np);
     w.V = c.take<double>(C * Np);
     w.mu = c.take<double>(C);
@@ -315,7 +316,7 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
 
     // ---- per-call tables: T = A^-1 z[:N], dr_train, a, h0, zb, sum_dr -------------------------------
     {
-    TimeScope ts_(T_PREP, s, 6);
+    TimeScope ts_(T_PREP, s, 7);
     cbo::k_scale_transpose<<<(Np * d + 255) / 256, 256, 0, s>>>(gp->X, N, Np, d, gp->inv_lengthscale, w.XsT);
     cbo::k_pad_probes<<<(Np * Sp + 255) / 256, 256, 0, s>>>(z, N, Np, Sp, w.zp);
     cbo::k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(gp->linv, Np, w.zp, Sp, w.tmp, 0, 1);
@@ -325,6 +326,10 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
                                                           ratio->W2, ratio->b2, ratio->W3, ratio->b3, 1e-6, w.dr_train);
     else
         cbo::k_fill<<<(Np + 255) / 256, 256, 0, s>>>(w.dr_train, Np, 1.0);
+    if (p->q == 1) {
+        const int rows = p->eps_per_candidate ? (int)b : 1;
+        cbo::k_eps_absmax<<<(rows + 7) / 8, 256, 0, s>>>(eps_grid, rows, G, w.eps_absmax);
+    }
     cbo::k_train_tables<<<1, 256, 0, s>>>(gp->alpha, z, w.T, N, Np, Sp, gp->noise, w.dr_train, w.a, w.h0, w.zb,
                                           w.sum_dr);
     }
@@ -371,6 +376,7 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
         a.W = w.UW; a.rn_partial = w.rn; a.mu = w.mu; a.ut = w.ut; a.drc = ratio ? w.drc : nullptr;
         a.eps_grid = p->eps_per_candidate ? eps_grid + c0 * G * q : eps_grid;
         a.eps_mc = eps_mc;
+        a.eps_absmax = p->eps_per_candidate ? w.eps_absmax + c0 : w.eps_absmax;
         a.u_rand = u_rand ? u_rand + c0 * G * q : nullptr;
         cbo::ScoreQArgs aq;
         aq.V = w.V; aq.Xq = Xc; aq.inv_ls = gp->inv_lengthscale; aq.d = d;

@@ -270,6 +270,17 @@ k_probe_matvec(const double* __restrict__ Mat, int Np, const double* __restrict_
     }
 }
 
+// out[c] = max_g |eps[c, g]|  (one warp per row; rows = 1 for a shared grid)
+__global__ void k_eps_absmax(const double* __restrict__ eps, int rows, int G, double* __restrict__ out) {
+    int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    double m = 0.0;
+    for (int g = lane; g < G; g += 32) m = fmax(m, fabs(eps[int64_t(r) * G + g]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) out[r] = m;
+}
+
 // z (N+q) x Sp of +-1 -> padded copy zp (Np x Sp, zeros beyond N)
 __global__ void k_pad_probes(const double* __restrict__ z, int N, int Np, int Sp, double* __restrict__ zp) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;

@@ -53,6 +53,7 @@ struct ScoreArgs {
     const double* drc;      // n_cand (already clamp_min 1e-6) or nullptr -> 1
     const double* cscale;   // n_cand grid covariance scale or nullptr -> 1
     const double* eps_grid; // G or n_cand x G
+    const double* eps_absmax; // 1 or n_cand: max_g |eps_g| (bounds the sigmoid argument; see CLAMP)
     const double* eps_mc;   // S x G
     const double* u_rand;   // n_cand x G or nullptr
     // outputs (nullable except acq)
@@ -91,6 +92,73 @@ __device__ __forceinline__ int pair_barrier_or(int group, int nthr, int pred) {
         : "r"(group + 1), "r"(nthr), "r"(pred)
         : "memory");
     return r;
+}
+
+// Phase B row sweep for SCORE_GPW grid points: hard count, soft-rank sigmoid, weighted sums.
+// Soft rank: rho = sigmoid(dd / temp) = 1 / (1 + e),  e = exp(-dd/temp) = 2^(-x/16),  x = c1 dd.  With
+// n = -round(x) = 16 kk + j:  e = 2^kk * tab[j] * P(x - round(x)),  P(y) ~ exp(-y ln2/16) on [-1/2, 1/2] (16-entry
+// table + near-minimax cubic, rel. err 1.2e-9); 1/(1+e) from a MUFU.RCP64H seed and one Newton step: 14 fp64-pipe
+// instructions per (train point, grid point).  CLAMP = true clamps |x| at 946 = 41 * 16/ln2 in the integer domain
+// (rho is 0 or 1 to 2e-18 beyond that); phase A proves |x| < 900 for most candidates and then the clamp (4 integer
+// instructions per element of an issue-bound loop) is compiled out.
+template <bool SOFT, bool CLAMP>
+__device__ __forceinline__ void score_rows(const ScoreArgs& p, const double* __restrict__ sq, const double* __restrict__ sdr,
+                                           const double* __restrict__ tab, int lane, int N32,
+                                           const double (&bg)[SCORE_GPW], double (&sr)[SCORE_GPW], double (&sw)[SCORE_GPW],
+                                           unsigned (&cneg)[SCORE_GPW]) {
+    const double kMagic = p.k_magic;                          // 1.5 * 2^52
+    const double kC0 = p.k_c0, kC1n = p.k_c1n, kC2 = p.k_c2, kC3n = p.k_c3n;
+    constexpr int kSatHi = 0x408d9000;                        // hiword(946.0)
+    const double* tq = sq + 3 * lane;
+    const double* td = sdr + lane;
+    double qa = tq[0], qb = tq[1], qc = tq[2], dr = td[0];
+    for (int i = lane; i < N32; i += 32) {
+        tq += 96; td += 32;                                   // next row (reads past N32 stay inside shared memory)
+        const double qa_n = tq[0], qb_n = tq[1], qc_n = tq[2], dr_n = td[0];
+        double x[SCORE_GPW];
+#pragma unroll
+        for (int k = 0; k < SCORE_GPW; ++k) {
+            x[k] = fma(fma(qa, bg[k], qb), bg[k], qc);
+            cneg[k] += unsigned(__double2hiint(x[k])) >> 31;  // counts score_c < score_i
+        }
+        if (SOFT) {
+            double t[SCORE_GPW], yn[SCORE_GPW], e[SCORE_GPW];
+#pragma unroll
+            for (int k = 0; k < SCORE_GPW; ++k) {
+                double xc = x[k];
+                if (CLAMP) {
+                    int hi = __double2hiint(x[k]);
+                    int ch = min(hi & 0x7fffffff, kSatHi) | (hi & 0x80000000);
+                    xc = __hiloint2double(ch, __double2loint(x[k]));         // clamp(x, -946, 946)
+                }
+                t[k] = kMagic - xc;                           // low word = -round(x)
+                yn[k] = xc + (t[k] - kMagic);                 // x - round(x) in [-1/2, 1/2]
+            }
+#pragma unroll
+            for (int k = 0; k < SCORE_GPW; ++k) {
+                double pl = fma(yn[k], kC3n, kC2);
+                pl = fma(pl, yn[k], kC1n);
+                pl = fma(pl, yn[k], kC0);                     // exp(-yn ln2/16)
+                int n = __double2loint(t[k]);
+                double ev = tab[n & 15] * pl;
+                e[k] = __hiloint2double(__double2hiint(ev) + ((n >> 4) << 20), __double2loint(ev));
+            }
+#pragma unroll
+            for (int k = 0; k < SCORE_GPW; ++k) {
+                double d = 1.0 + e[k];
+                double y0;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+                double err = fma(-d, y0, 1.0);
+                double rho = fma(y0, err, y0);
+                sr[k] += rho;
+                sw[k] = fma(rho, dr, sw[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCORE_GPW; ++k) sw[k] += (__double2hiint(x[k]) >= 0) ? dr : 0.0;
+        }
+        qa = qa_n; qb = qb_n; qc = qc_n; dr = dr_n;
+    }
 }
 
 template <bool SOFT>
@@ -163,6 +231,11 @@ k_score(const ScoreArgs p) {
         const double lv_c = -0.5 * log(var_c) - 0.5 * kLog2Pi;
         // score_c(g) = lv_c - iv_c (noise b_g)^2 ;  score_i(g) = lv_i - iv_i (a_i - noise w_i b_g)^2
         const double qa_c = -iv_c * p.noise * p.noise;
+        // bmax >= |b_g| for every grid point of this candidate: the sigmoid argument is bounded by (|qa| bmax + |qb|) bmax + |qc|
+        const double cscale = p.cscale ? p.cscale[c] : 1.0;
+        const double gsd = sqrt(cscale * s_var);                        // sd of the grid distribution
+        const double bmax = gsd * p.eps_absmax[p.eps_per_candidate ? c : 0] * inv_s;
+        int big = 0;
         pair_barrier(pair, GT);                                          // nibble tables visible
         for (int i0 = ptid; i0 < N32; i0 += 4 * GT) {                    // 4 independent loads in flight per thread
             double w[4], h0[4], ai[4];
@@ -180,7 +253,7 @@ k_score(const ScoreArgs p) {
             for (int j = 0; j < 4; ++j) {
                 int i = i0 + GT * j;
                 if (i < N32) {
-                    double qa = 0.0, qb = 0.0, qc = -1e300;              // padding: x = -1e300, never counted, dr = 0
+                    double qa = 0.0, qb = 0.0, qc = -900.0;              // padding: x = -900: never counted, rho ~ 1e-17, dr = 0
                     if (i < N) {
                         double zdot = zt[bits[j] & 15] + zt[16 + ((bits[j] >> 4) & 15)];
                         if (Sp > 8) zdot += zt[32 + ((bits[j] >> 8) & 15)] + zt[48 + ((bits[j] >> 12) & 15)];
@@ -194,17 +267,17 @@ k_score(const ScoreArgs p) {
                         qa = c1 * fma(iv * wi, wi, qa_c);                // b_g^2 coefficient
                         qb = c1 * (-2.0 * iv * ai[j] * wi);              // b_g coefficient
                         qc = c1 * (fma(iv * ai[j], ai[j], lv_c - lv));   // constant
+                        big |= !(fma(fma(fabs(qa), bmax, fabs(qb)), bmax, fabs(qc)) < 900.0);
                     }
                     sq[3 * i] = qa; sq[3 * i + 1] = qb; sq[3 * i + 2] = qc;
                 }
             }
         }
-        const double cscale = p.cscale ? p.cscale[c] : 1.0;
-        const double gsd = sqrt(cscale * s_var);                        // sd of the grid distribution
         const double drc = p.drc ? p.drc[c] : 1.0;
         const double norm = sum_dr + drc;
         const double omega_c = drc / norm;
-        bad = pair_barrier_or(pair, GT, bad);                                 // tables complete; any non-positive variance?
+        bad = pair_barrier_or(pair, GT, bad);                             // tables complete; any non-positive variance?
+        big = SOFT ? pair_barrier_or(pair, GT, big) : 0;                  // can any sigmoid argument leave the unclamped range?
 
         // ---- phase B: 4 grid points per pass, passes alternate between the two warps ----------------
         for (int g0 = half * SCORE_GPW; g0 < G; g0 += (SCORE_GPW << wl)) {
@@ -218,61 +291,8 @@ k_score(const ScoreArgs p) {
                 sr[k] = 0.0; sw[k] = 0.0; cneg[k] = 0u;
             }
             if (!bad) {
-                // Soft rank: rho = sigmoid(dd / temp) = 1 / (1 + e),  e = exp(-dd/temp) = 2^(-x/16),  x = c1 dd.
-                // With n = -round(x) = 16 kk + j:  e = 2^kk * tab[j] * P(x - round(x)),  P(y) ~ exp(-y ln2/16) on
-                // [-1/2, 1/2] (16-entry table + near-minimax cubic, rel. err 1.2e-9); 1/(1+e) from a MUFU.RCP64H
-                // seed and one Newton step.  |x| is clamped at 946 = 41 * 16/ln2 in the integer domain (rho is
-                // 0 or 1 to 2e-18 beyond that).
-                const double kMagic = p.k_magic;                          // 1.5 * 2^52
-                const double kC0 = p.k_c0, kC1n = p.k_c1n, kC2 = p.k_c2, kC3n = p.k_c3n;
-                constexpr int kSatHi = 0x408d9000;                        // hiword(946.0)
-                const double* tq = sq + 3 * lane;
-                const double* td = sdr + lane;
-                double qa = tq[0], qb = tq[1], qc = tq[2], dr = td[0];
-                for (int i = lane; i < N32; i += 32) {
-                    tq += 96; td += 32;                                   // next row (reads past N32 stay inside shared memory)
-                    const double qa_n = tq[0], qb_n = tq[1], qc_n = tq[2], dr_n = td[0];
-                    double x[SCORE_GPW];
-#pragma unroll
-                    for (int k = 0; k < SCORE_GPW; ++k) {
-                        x[k] = fma(fma(qa, bg[k], qb), bg[k], qc);
-                        cneg[k] += unsigned(__double2hiint(x[k])) >> 31;  // counts score_c < score_i
-                    }
-                    if (SOFT) {
-                        double t[SCORE_GPW], yn[SCORE_GPW], e[SCORE_GPW];
-#pragma unroll
-                        for (int k = 0; k < SCORE_GPW; ++k) {
-                            int hi = __double2hiint(x[k]);
-                            int ch = min(hi & 0x7fffffff, kSatHi) | (hi & 0x80000000);
-                            double xc = __hiloint2double(ch, __double2loint(x[k]));         // clamp(x, -946, 946)
-                            t[k] = kMagic - xc;                           // low word = -round(x)
-                            yn[k] = xc + (t[k] - kMagic);                 // x - round(x) in [-1/2, 1/2]
-                        }
-#pragma unroll
-                        for (int k = 0; k < SCORE_GPW; ++k) {
-                            double pl = fma(yn[k], kC3n, kC2);
-                            pl = fma(pl, yn[k], kC1n);
-                            pl = fma(pl, yn[k], kC0);                     // exp(-yn ln2/16)
-                            int n = __double2loint(t[k]);
-                            double ev = tab[n & 15] * pl;
-                            e[k] = __hiloint2double(__double2hiint(ev) + ((n >> 4) << 20), __double2loint(ev));
-                        }
-#pragma unroll
-                        for (int k = 0; k < SCORE_GPW; ++k) {
-                            double d = 1.0 + e[k];
-                            double y0;
-                            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
-                            double err = fma(-d, y0, 1.0);
-                            double rho = fma(y0, err, y0);
-                            sr[k] += rho;
-                            sw[k] = fma(rho, dr, sw[k]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < SCORE_GPW; ++k) sw[k] += (__double2hiint(x[k]) >= 0) ? dr : 0.0;
-                    }
-                    qa = qa_n; qb = qb_n; qc = qc_n; dr = dr_n;
-                }
+                if (big) score_rows<SOFT, true>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
+                else score_rows<SOFT, false>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
             }
 #pragma unroll
             for (int k = 0; k < SCORE_GPW; ++k) {

@@ -82,7 +82,7 @@ def count_launches(state: GPModelState, b: int, params, ratio: bool, chunk: int 
     """Kernels one cbo_conformal_acq_f64 call enqueues (mirrors csrc/cbo_api.cu)."""
     C_ = b if params.max_grid_refinements > 0 else min(b, chunk if chunk > 0 else 16384)
     n_chunks = (b + C_ - 1) // C_
-    per_call = 6                                   # scale_transpose, pad_probes, 2 x probe_matvec, ratio/fill, train_tables
+    per_call = 7                                   # scale_transpose, pad_probes, 2 x probe_matvec, ratio/fill, eps_absmax, train_tables
     per_chunk = 1 + (1 if ratio else 0) + 2 + 1    # rows, ratio(cand), 2 x gemm, score
     return per_call + n_chunks * per_chunk
 
