@@ -370,6 +370,7 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
         a.beta_prime = p->beta_prime; a.best_f = p->best_f;
         a.k_magic = 6755399441055744.0; a.k_c0 = 0.9999999988534117; a.k_c1n = -0.043321698775061875;
         a.k_c2 = 0.0009384214835622084; a.k_c3n = -1.3551125681305332e-05;
+        a.unit_dr = ratio ? 0 : 1;
         a.kind = p->kind; a.optimistic = p->optimistic; a.randomized = p->randomized;
         a.eps_per_candidate = p->eps_per_candidate;
         a.a = w.a; a.h0 = w.h0; a.zb = w.zb; a.dr = w.dr_train; a.sum_dr = w.sum_dr; a.z_cand = z + int64_t(N) * Sp;

@@ -36,6 +36,7 @@ struct ScoreArgs {
     double noise, kappa, alpha_lvl, temp, beta_prime, best_f;
     int kind, optimistic, randomized, eps_per_candidate;
     int wpg_log2;           // log2(warps per candidate group): 1 (pairs) .. 4
+    int unit_dr;            // no ratio estimator: all train-point importance weights are 1
     // sigmoid constants, passed as parameters so that they are constant-bank operands instead of per-iteration moves
     double k_magic, k_c0, k_c1n, k_c2, k_c3n;
     // per-call tables (train side)
@@ -101,7 +102,9 @@ __device__ __forceinline__ int pair_barrier_or(int group, int nthr, int pred) {
 // instructions per (train point, grid point).  CLAMP = true clamps |x| at 946 = 41 * 16/ln2 in the integer domain
 // (rho is 0 or 1 to 2e-18 beyond that); phase A proves |x| < 900 for most candidates and then the clamp (4 integer
 // instructions per element of an issue-bound loop) is compiled out.
-template <bool SOFT, bool CLAMP>
+// UNIT = true: no ratio estimator, every train point has importance weight 1 (the reference's `ratio_estimator=None`
+// branch, helpers.py:286-290): sum rho * dr == sum rho, one fp64 instruction and one shared-memory load less.
+template <bool SOFT, bool CLAMP, bool UNIT>
 __device__ __forceinline__ void score_rows(const ScoreArgs& p, const double* __restrict__ sq, const double* __restrict__ sdr,
                                            const double* __restrict__ tab, int lane, int N32,
                                            const double (&bg)[SCORE_GPW], double (&sr)[SCORE_GPW], double (&sw)[SCORE_GPW],
@@ -111,10 +114,10 @@ __device__ __forceinline__ void score_rows(const ScoreArgs& p, const double* __r
     constexpr int kSatHi = 0x408d9000;                        // hiword(946.0)
     const double* tq = sq + 3 * lane;
     const double* td = sdr + lane;
-    double qa = tq[0], qb = tq[1], qc = tq[2], dr = td[0];
+    double qa = tq[0], qb = tq[1], qc = tq[2], dr = UNIT ? 1.0 : td[0];
     for (int i = lane; i < N32; i += 32) {
         tq += 96; td += 32;                                   // next row (reads past N32 stay inside shared memory)
-        const double qa_n = tq[0], qb_n = tq[1], qc_n = tq[2], dr_n = td[0];
+        const double qa_n = tq[0], qb_n = tq[1], qc_n = tq[2], dr_n = UNIT ? 1.0 : td[0];
         double x[SCORE_GPW];
 #pragma unroll
         for (int k = 0; k < SCORE_GPW; ++k) {
@@ -141,7 +144,7 @@ __device__ __forceinline__ void score_rows(const ScoreArgs& p, const double* __r
                 pl = fma(pl, yn[k], kC0);                     // exp(-yn ln2/16)
                 int n = __double2loint(t[k]);
                 double ev = tab[n & 15] * pl;
-                e[k] = __hiloint2double(__double2hiint(ev) + ((n >> 4) << 20), __double2loint(ev));
+                e[k] = __hiloint2double(__double2hiint(ev) + ((n & ~15) << 16), __double2loint(ev));   // * 2^kk
             }
 #pragma unroll
             for (int k = 0; k < SCORE_GPW; ++k) {
@@ -151,9 +154,9 @@ __device__ __forceinline__ void score_rows(const ScoreArgs& p, const double* __r
                 double err = fma(-d, y0, 1.0);
                 double rho = fma(y0, err, y0);
                 sr[k] += rho;
-                sw[k] = fma(rho, dr, sw[k]);
+                if (!UNIT) sw[k] = fma(rho, dr, sw[k]);
             }
-        } else {
+        } else if (!UNIT) {
 #pragma unroll
             for (int k = 0; k < SCORE_GPW; ++k) sw[k] += (__double2hiint(x[k]) >= 0) ? dr : 0.0;
         }
@@ -291,14 +294,19 @@ k_score(const ScoreArgs p) {
                 sr[k] = 0.0; sw[k] = 0.0; cneg[k] = 0u;
             }
             if (!bad) {
-                if (big) score_rows<SOFT, true>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
-                else score_rows<SOFT, false>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
+                if (p.unit_dr) {       // padded rows carry rho ~ 1e-17 each into sum rho * dr here (dr is not read): negligible
+                    if (big) score_rows<SOFT, true, true>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
+                    else score_rows<SOFT, false, true>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
+                } else {
+                    if (big) score_rows<SOFT, true, false>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
+                    else score_rows<SOFT, false, false>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
+                }
             }
 #pragma unroll
             for (int k = 0; k < SCORE_GPW; ++k) {
                 int cnt = N32 - warp_sum_int(int(cneg[k]));               // #{i <= N : score_c >= score_i}
-                double tw = warp_sum(sw[k]);
                 double tr = SOFT ? warp_sum(sr[k]) : 0.0;
+                double tw = p.unit_dr ? (SOFT ? tr : double(cnt)) : warp_sum(sw[k]);
                 if (lane == 0 && g0 + k < G) { g_cw[g0 + k] = double(cnt); g_nc[g0 + k] = tr; g_mf[g0 + k] = tw; }
             }
         }
