@@ -30,11 +30,16 @@ class RatioMlpF64(C.Structure):
                 ("b3", c_dp)]
 
 
+class NeiBaselineF64(C.Structure):
+    _fields_ = [("nb", C.c_int64), ("Xb", c_dp), ("KbX", c_dp), ("Sbb", c_dp), ("mub", c_dp)]
+
+
 class Params(C.Structure):
     _fields_ = [("alpha", C.c_double), ("temp", C.c_double), ("grid_res", C.c_int64), ("q", C.c_int64),
                 ("num_mc", C.c_int64), ("num_probes", C.c_int64), ("max_grid_refinements", C.c_int64),
                 ("kind", C.c_int32), ("optimistic", C.c_int32), ("randomized", C.c_int32),
-                ("eps_per_candidate", C.c_int32), ("beta_prime", C.c_double), ("best_f", C.c_double)]
+                ("eps_per_candidate", C.c_int32), ("beta_prime", C.c_double), ("best_f", C.c_double),
+                ("nei", C.POINTER(NeiBaselineF64))]
 
 
 class OutputsF64(C.Structure):

@@ -66,6 +66,10 @@ class ConformalAcquisition(nn.Module):
     def _acq_params(self):
         raise NotImplementedError("ConformalAcquisition must be subclassed")     # acquisitions.py:50-51
 
+    def _mc_width(self, q):
+        """Trailing dimension of the acquisition sampler's base samples (q; nb + q for the noisy-EI joint sample)."""
+        return q
+
     def _conformal_fwd(self, X: torch.Tensor, outputs=()) -> torch.Tensor:
         if self.model is None:
             raise AttributeError("ConformalAcquisition must be subclassed")
@@ -86,7 +90,7 @@ class ConformalAcquisition(nn.Module):
         else:
             eps = self.grid_sampler.draw((G, b, q), dev).movedim(0, 1).contiguous()
         S = int(self.sampler.sample_shape[0])
-        eps_mc = self.sampler.draw((S, G, q), dev)
+        eps_mc = self.sampler.draw((S, G, self._mc_width(q)), dev)
         z = (self.fixed_probes if self.fixed_probes is not None else draw_probes(state.N + q)).to(dev)
         u = self.fixed_uniforms
         if self.randomized and u is None:
@@ -135,3 +139,32 @@ class qConformalExpectedImprovement(ConformalAcquisition):
 
     def _acq_params(self):
         return dict(kind="ei", best_f=float(self.best_f))
+
+
+class qConformalNoisyExpectedImprovement(ConformalAcquisition):
+    """acquisitions.py:106-139 (+ botorch qNoisyExpectedImprovement(model, X_baseline, sampler, ..., prune_baseline)).
+
+    Joint sampling over [X_baseline; X] under every refit model.  Built for q = 1 and at most 31 baseline points -- pass
+    the pruned baseline (the reference configs set `prune_baseline: true`, hydra_config/acq_fn/cnei.yaml:3; botorch's
+    `prune_inferior_points` is an MC procedure outside this path)."""
+
+    def __init__(self, alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic=False,
+                 grid_sampler=None, randomized=False, *, model=None, X_baseline=None, sampler=None, objective=None,
+                 posterior_transform=None, X_pending=None, prune_baseline=False, cache_root=False):
+        super().__init__(alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic, grid_sampler,
+                         randomized, model=model, sampler=sampler, objective=objective,
+                         posterior_transform=posterior_transform, X_pending=X_pending)
+        if X_baseline is None:
+            raise TypeError("qConformalNoisyExpectedImprovement needs X_baseline")
+        if X_baseline.reshape(-1, X_baseline.shape[-1]).shape[0] > 31:
+            raise NotImplementedError("cNEI is built for at most 31 baseline points: pass the pruned baseline")
+        self.X_baseline = X_baseline
+        self._baseline = None
+
+    def _mc_width(self, q):
+        return self.X_baseline.reshape(-1, self.X_baseline.shape[-1]).shape[0] + q
+
+    def _acq_params(self):
+        if self._baseline is None:
+            self._baseline = ops.NeiBaseline.build(as_state(self.model), self.X_baseline)
+        return dict(kind="nei", nei_baseline=self._baseline)

@@ -15,6 +15,7 @@
 #include "score.cuh"
 #include "score_q.cuh"
 #include "mobo.cuh"
+#include "nei.cuh"
 
 namespace {
 
@@ -76,6 +77,7 @@ struct Workspace {
     uint32_t* zb;
     double *UW, *V, *mu, *ut, *drc, *rn;
     double *cscale, *nacc, *acq_scratch, *stats;      // refinement only
+    double* nei_values;                               // cNEI only: C x S x G
     size_t bytes;
 };
 
@@ -111,6 +113,7 @@ Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, 
     w.nacc = c.take<double>(R > 0 ? b * p->q : 1);
     w.acq_scratch = c.take<double>(R > 0 ? b : 1);
     w.stats = c.take<double>(8);
+    w.nei_values = c.take<double>(p->kind == CBO_ACQ_NEI ? C * p->num_mc * p->grid_res : 1);
     w.bytes = c.off;
     return w;
 }
@@ -155,7 +158,11 @@ int validate(const cbo_gp_f64* gp, const cbo_params* p, int64_t b) {
     if (!gp->X || !gp->alpha || !gp->linv || !gp->linv_t || !gp->inv_lengthscale) return CBO_ERR_INVALID_ARG;
     if (gp->N <= 0 || gp->d <= 0 || gp->Np != cbo_padded_n(gp->N)) return CBO_ERR_INVALID_ARG;
     if (p->grid_res < 2) return CBO_ERR_INVALID_ARG;                       // helpers.py:113
-    if (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI) return CBO_ERR_INVALID_ARG;
+    if (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI && p->kind != CBO_ACQ_NEI) return CBO_ERR_INVALID_ARG;
+    if (p->kind == CBO_ACQ_NEI) {
+        if (!p->nei || !p->nei->Xb || !p->nei->KbX || !p->nei->Sbb || !p->nei->mub || p->nei->nb < 1) return CBO_ERR_INVALID_ARG;
+        if (p->q != 1 || p->nei->nb > cbo::NEI_MAX_NB) return CBO_ERR_UNSUPPORTED;
+    }
     if (p->q < 1 || p->q > cbo::MAX_Q) return CBO_ERR_UNSUPPORTED;
     if (p->q > 1 && cbo::score_q_smem_bytes((int)gp->Np, (int)p->grid_res, (int)p->q) > 227 * 1024) return CBO_ERR_UNSUPPORTED;
     if (gp->d > cbo::MAX_D) return CBO_ERR_UNSUPPORTED;
@@ -382,7 +389,19 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
         cbo::ScoreQArgs aq;
         aq.V = w.V; aq.Xq = Xc; aq.inv_ls = gp->inv_lengthscale; aq.d = d;
         aq.post_cov = (q > 1 && out->post_var) ? out->post_var + c0 * q * q : nullptr;
-        auto run_score = [&](const cbo::ScoreArgs& x) -> cudaError_t {
+        auto run_score = [&](const cbo::ScoreArgs& x_in) -> cudaError_t {
+            cbo::ScoreArgs x = x_in;
+            if (p->kind == CBO_ACQ_NEI) {
+                cbo::NeiArgs na;
+                na.N = N; na.Np = Np; na.d = d; na.nb = (int)p->nei->nb; na.G = G; na.S = (int)p->num_mc; na.n_cand = ncand;
+                na.tiles_n = tiles_n; na.noise = gp->noise; na.kappa = gp->outputscale; na.temp = p->temp;
+                na.Xq = Xc; na.inv_ls = gp->inv_lengthscale; na.Xb = p->nei->Xb; na.KbX = p->nei->KbX; na.Sbb = p->nei->Sbb;
+                na.mub = p->nei->mub; na.W = w.UW; na.rn_partial = w.rn; na.mu = w.mu; na.cscale = x.cscale;
+                na.eps_grid = x.eps_grid; na.eps_per_candidate = x.eps_per_candidate; na.eps_mc = eps_mc;
+                na.values = w.nei_values;
+                cbo::k_nei_values<<<(ncand + 3) / 4, 128, 0, s>>>(na);
+                x.ext_values = w.nei_values;
+            }
             if (q == 1) return soft_path ? launch_score<true>(x, s) : launch_score<false>(x, s);
             cbo::ScoreQArgs y = aq;
             y.base = x;

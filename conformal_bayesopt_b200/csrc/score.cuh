@@ -57,6 +57,7 @@ struct ScoreArgs {
     const double* eps_absmax; // 1 or n_cand: max_g |eps_g| (bounds the sigmoid argument; see CLAMP)
     const double* eps_mc;   // S x G
     const double* u_rand;   // n_cand x G or nullptr
+    const double* ext_values; // n_cand x S x G sample values computed by another kernel (cNEI), or nullptr
     // outputs (nullable except acq)
     double* acq; double* grid; double* logp; double* mask; double* ood; double* qscore;
     double* post_mean; double* post_var; double* num_acc; double* refit_mean; double* refit_sd;
@@ -368,7 +369,9 @@ k_score(const ScoreArgs p) {
                     double cw = g_cw[g], nc = g_nc[g], mf = g_mf[g];
                     double f = fma(sd_f, p.eps_mc[int64_t(s) * G + g], mf);
                     double val;
-                    if (p.kind == 0) {
+                    if (p.ext_values) {
+                        val = p.ext_values[(int64_t(c) * S + s) * G + g];
+                    } else if (p.kind == 0) {
                         if (S > 1) {
                             double em = 0.0;
                             for (int s2 = 0; s2 < S; ++s2) em += p.eps_mc[int64_t(s2) * G + g];

@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from .model_state import GPModelState
 
-ACQ_KINDS = {"ucb": 0, "ei": 1}
+ACQ_KINDS = {"ucb": 0, "ei": 1, "nei": 2}
 _WORKSPACES: Dict[tuple, torch.Tensor] = {}
 LAUNCH_COUNT = 0   # kernels launched through this module (bench.py reports it as gpu_launches)
 
@@ -59,11 +59,38 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+@dataclass
+class NeiBaseline:
+    """Device arrays of the cNEI baseline (acquisitions.py:117-122), built once per acquisition object with torch.linalg."""
+    Xb: torch.Tensor     # (nb, d)
+    KbX: torch.Tensor    # (nb, Np)
+    Sbb: torch.Tensor    # (nb, nb)
+    mub: torch.Tensor    # (nb,)
+
+    @classmethod
+    def build(cls, state: GPModelState, X_baseline: torch.Tensor) -> "NeiBaseline":
+        from .model_state import matern52
+        Xb = X_baseline.detach().to(state.device, torch.float64).reshape(-1, state.d).contiguous()
+        Kb = matern52(Xb, state.X, state.lengthscale, state.outputscale)
+        Vb = torch.linalg.solve_triangular(state.L, Kb.T, upper=False)
+        Kbb = matern52(Xb, Xb, state.lengthscale, state.outputscale)
+        Kbb.diagonal().fill_(state.outputscale)
+        KbX = torch.zeros(Xb.shape[0], state.Np, dtype=torch.float64, device=state.device)
+        KbX[:, :state.N] = Kb
+        return cls(Xb, KbX, (Kbb - Vb.T @ Vb).contiguous(), (state.mean + Kb @ state.alpha[:state.N]).contiguous())
+
+    def c_struct(self) -> "_lib.NeiBaselineF64":
+        return _lib.NeiBaselineF64(self.Xb.shape[0], self.Xb.data_ptr(), self.KbX.data_ptr(), self.Sbb.data_ptr(),
+                                   self.mub.data_ptr())
+
+
 def make_params(*, alpha, temp, grid_res, q=1, num_mc=1, num_probes=8, max_grid_refinements=0, kind="ucb",
-                optimistic=True, randomized=False, eps_per_candidate=False, beta_prime=0.0, best_f=0.0) -> "_lib.Params":
+                optimistic=True, randomized=False, eps_per_candidate=False, beta_prime=0.0, best_f=0.0,
+                nei=None) -> "_lib.Params":
     return _lib.Params(float(alpha), float(temp), int(grid_res), int(q), int(num_mc), int(num_probes),
                        int(max_grid_refinements), ACQ_KINDS[kind], int(bool(optimistic)), int(bool(randomized)),
-                       int(bool(eps_per_candidate)), float(beta_prime), float(best_f))
+                       int(bool(eps_per_candidate)), float(beta_prime), float(best_f),
+                       C.pointer(nei) if nei is not None else None)
 
 
 def workspace(state: GPModelState, b: int, params, chunk: int = 0) -> torch.Tensor:
@@ -104,8 +131,12 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
     eps_per_candidate = eps_grid.numel() == b * G * q and eps_grid.numel() != G * q
     if eps_grid.numel() not in (G * q, b * G * q):
         raise _lib.CboError(f"eps_grid must hold G*q or b*G*q values, got {tuple(eps_grid.shape)}")
-    num_mc = eps_mc.numel() // (G * q)
-    params = make_params(q=q, num_mc=num_mc, num_probes=z.shape[-1], eps_per_candidate=eps_per_candidate, **param_kw)
+    baseline = param_kw.pop("nei_baseline", None)
+    nei_c = baseline.c_struct() if baseline is not None else None          # kept alive until the call returns
+    per_sample = (baseline.Xb.shape[0] + 1) if baseline is not None else q
+    num_mc = eps_mc.numel() // (G * per_sample)
+    params = make_params(q=q, num_mc=num_mc, num_probes=z.shape[-1], eps_per_candidate=eps_per_candidate, nei=nei_c,
+                         **param_kw)
     if z.shape[0] != state.N + q:
         raise _lib.CboError(f"z must have N+q = {state.N + q} rows, got {z.shape[0]}")
     if u_rand is not None and u_rand.numel() != b * G * q:

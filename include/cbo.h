@@ -50,7 +50,7 @@ typedef enum {
     CBO_ERR_NO_DEVICE = 5        /* no sm_100 device visible */
 } cbo_status;
 
-typedef enum { CBO_ACQ_UCB = 0, CBO_ACQ_EI = 1 } cbo_acq_kind;
+typedef enum { CBO_ACQ_UCB = 0, CBO_ACQ_EI = 1, CBO_ACQ_NEI = 2 } cbo_acq_kind;
 
 /* One output's exact GP, prepared once per model fit (all device pointers, fp64, row-major).
  * Np = cbo_padded_n(N) (N rounded up to a multiple of 128); rows/cols >= N are zero. */
@@ -77,6 +77,15 @@ typedef struct {
     const double* W3; const double* b3;   /* 1 x H, 1 */
 } cbo_ratio_mlp_f64;
 
+/* cNEI baseline (conformalbo/acquisitions.py:115-134), prepared once per acquisition object; q = 1, nb <= 31 */
+typedef struct {
+    int64_t nb;                /* baseline points (after botorch's prune_baseline)              */
+    const double* Xb;          /* nb x d                                                        */
+    const double* KbX;         /* nb x Np   k(X_b, X), zero-padded columns                      */
+    const double* Sbb;         /* nb x nb   noise-free posterior covariance of f(X_b) given D   */
+    const double* mub;         /* nb        posterior mean of f(X_b)                            */
+} cbo_nei_baseline_f64;
+
 typedef struct {
     double alpha;              /* miscoverage level                         (acquisitions.py:32) */
     double temp;               /* sigmoid temperature; <= 0 selects the hard path (helpers.py:277,316) */
@@ -91,6 +100,7 @@ typedef struct {
     int32_t eps_per_candidate; /* 0: eps_grid is (G) shared (collapse_batch_dims), 1: (b x G) */
     double beta_prime;         /* cUCB: sqrt(beta*pi/2)                     */
     double best_f;             /* cEI incumbent                             */
+    const cbo_nei_baseline_f64* nei;   /* kind == CBO_ACQ_NEI only (eps_mc is then S x G x (nb+1)), else NULL */
 } cbo_params;
 
 /* Any pointer may be NULL (that output is skipped) except acq. */

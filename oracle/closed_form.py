@@ -39,7 +39,7 @@ def candidate_solves(gp: GPState, Xq: torch.Tensor):
 
 def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_grid_refinements=0,
                           eps_grid, z, eps_mc, ratio=None, randomized=False, u_rand=None,
-                          optimistic=True, beta_prime=None, best_f=None):
+                          optimistic=True, beta_prime=None, best_f=None, X_baseline=None):
     b, q, _ = Xq.shape
     N, G, noise = gp.N, grid_res, gp.noise
     Sp = z.shape[-1]
@@ -118,19 +118,48 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
             break
     _, grid, logp, mask, dev = best
 
+    if kind == "nei":
+        assert q == 1, "closed-form cNEI is written for q = 1"
+        # joint posterior of the refit model over [X_baseline; x] (acquisitions.py:115-134): with c = Cov_D(f(X_b), y(x)),
+        # P = Var_D(f(x)) = s - noise:  mean = [mu_b + c b_g ; mu + P b_g],
+        # cov = [[Sigma_bb - c c^T/s, c noise/s], [., P noise/s]]   (g-independent)
+        nb = X_baseline.shape[0]
+        Kb = gp.k(X_baseline, gp.X)                                        # (nb,N)
+        mu_b = gp.mean + Kb @ gp.alpha
+        Vb = torch.linalg.solve_triangular(gp.L, Kb.T, upper=False)
+        Sig_bb = gp.k(X_baseline, X_baseline) - Vb.T @ Vb
+        s1 = S[:, 0, 0]
+        P = s1 - noise
+        c = gp.k(X_baseline.unsqueeze(0).expand(b, nb, -1), Xq)[..., 0] - W[:, 0, :] @ Kb.T      # (b,nb)
+        cov = torch.zeros(b, nb + 1, nb + 1, dtype=U.dtype)
+        cov[:, :nb, :nb] = Sig_bb - c.unsqueeze(-1) * c.unsqueeze(-2) / s1[:, None, None]
+        cov[:, :nb, nb] = c * (noise / s1)[:, None]
+        cov[:, nb, :nb] = cov[:, :nb, nb]
+        cov[:, nb, nb] = P * noise / s1
+        root = torch.linalg.cholesky(cov)
+        bg = dev[..., 0] / s1[:, None]                                     # (b,G)
+        mean = torch.cat([mu_b.view(1, 1, nb) + c.unsqueeze(1) * bg.unsqueeze(-1),
+                          (mu[:, :1].unsqueeze(1) + (P[:, None] * bg).unsqueeze(-1))], dim=-1)   # (b,G,nb+1)
+        samples = mean.unsqueeze(0) + torch.einsum("bij,sgj->sbgi", root, eps_mc)
+        fb, fx = samples[..., :nb] / temp, samples[..., nb:]
+        diffs = (fx - temp * torch.logsumexp(fb, -1, keepdim=True)) / temp
+        values = temp * (torch.clamp_min(diffs, 0) + torch.log1p(torch.exp(-diffs.abs())))
     # ---- A-6 values under the refit model ------------------------------------------------
     shrink = eye - noise * Sinv                                            # (b,q,q)
     mean_f = mu.unsqueeze(1) + dev @ shrink.transpose(-1, -2)              # (b,G,q)
     cov_f = noise * shrink
     cov_f = 0.5 * (cov_f + cov_f.transpose(-1, -2))
     root = cov_f.clamp_min(0.0).sqrt() if q == 1 else torch.linalg.cholesky(cov_f)
-    samples = mean_f.unsqueeze(0) + torch.einsum("bij,sgj->sbgi", root, eps_mc)
+    if kind != "nei":
+        samples = mean_f.unsqueeze(0) + torch.einsum("bij,sgj->sbgi", root, eps_mc)
     if kind == "ucb":
         m = samples.mean(0)
         values = m + beta_prime * (samples - m).abs()
     elif kind == "ei":
         x = (samples - best_f) / temp
         values = temp * (torch.clamp_min(x, 0) + torch.log1p(torch.exp(-x.abs())))
+    elif kind == "nei":
+        pass                                                               # computed above from the joint posterior
     else:
         raise ValueError(kind)
 

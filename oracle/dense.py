@@ -142,6 +142,26 @@ def refit_posterior_at_candidates(gp: GPState, refit, q: int):
     return mean_f, cov_f
 
 
+def nei_values(gp, refit, Xq, X_baseline, eps_mc, temp):
+    """qConformalNoisyExpectedImprovement._nonconformal_fwd (acquisitions.py:115-134): joint posterior of the refit model over
+    X_full = [X_baseline; X], joint samples (base samples (S,G,nb+q)), smooth improvement over the baseline."""
+    b, q, d = Xq.shape
+    N, nb = gp.N, X_baseline.shape[0]
+    K_full, L_full, alpha_new = refit["K_full"], refit["L_full"], refit["alpha_new"]
+    G = K_full.shape[1]
+    X_train_full = torch.cat([gp.X.expand(b, N, d), Xq], dim=1)                                  # (b,N+q,d)
+    X_eval = torch.cat([X_baseline.expand(b, nb, d), Xq], dim=1)                                 # (b,nb+q,d)
+    Kx = gp.k(X_eval, X_train_full).unsqueeze(1).expand(b, G, nb + q, N + q)                     # cross-covariance (same for all g)
+    mean = gp.mean + (Kx @ alpha_new.unsqueeze(-1)).squeeze(-1)                                  # (b,G,nb+q)
+    sol = torch.cholesky_solve(Kx.transpose(-1, -2), L_full)
+    cov = gp.k(X_eval, X_eval).unsqueeze(1) - Kx @ sol                                           # (b,G,nb+q,nb+q)
+    cov = 0.5 * (cov + cov.transpose(-1, -2))
+    root = _chol(cov)
+    samples = mean.unsqueeze(0) + (root.unsqueeze(0) @ eps_mc.unsqueeze(1).unsqueeze(-1)).squeeze(-1)   # (S,b,G,nb+q)
+    diffs = samples[..., -q:] - softplus(samples[..., :-q], -1, temp, keepdim=True)
+    return softplus(torch.stack([diffs, torch.zeros_like(diffs)], dim=-1), -1, temp)             # (S,b,G,q)
+
+
 def nonconformal_values(gp, refit, q, eps_mc, kind, *, beta_prime=None, best_f=None, temp=None):
     """_nonconformal_fwd of cUCB (acquisitions.py:151-159) / cEI (acquisitions.py:88-98).
 
@@ -201,7 +221,7 @@ def construct_conformal_bands(gp: GPState, Xq, alpha, temp, grid_res, max_grid_r
 
 def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_grid_refinements=0,
                           eps_grid, z, eps_mc, ratio=None, randomized=False, u_rand=None,
-                          optimistic=True, beta_prime=None, best_f=None):
+                          optimistic=True, beta_prime=None, best_f=None, X_baseline=None):
     """ConformalAcquisition.forward (acquisitions.py:53-76).  Returns dict with acq (b,) and the bands."""
     b, q, _ = Xq.shape
     target_grid, logp, mask, refit, ood = construct_conformal_bands(
@@ -211,7 +231,10 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
         opt_mask = (target_grid >= mean.unsqueeze(1)).to(target_grid)
     else:
         opt_mask = torch.ones_like(target_grid)
-    values = nonconformal_values(gp, refit, q, eps_mc, kind, beta_prime=beta_prime, best_f=best_f, temp=temp)
+    if kind == "nei":
+        values = nei_values(gp, refit, Xq, X_baseline, eps_mc, temp)
+    else:
+        values = nonconformal_values(gp, refit, q, eps_mc, kind, beta_prime=beta_prime, best_f=best_f, temp=temp)
     res = conformal_integration(values, mask.unsqueeze(-1), logp[..., None, None], alpha,
                                 opt_mask.unsqueeze(-1), ood.unsqueeze(-1))          # (S,b,q)
     acq = res.max(dim=-1).values.mean(0)

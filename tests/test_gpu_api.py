@@ -219,3 +219,36 @@ def test_cehvi_matches_oracle():
                           cell_upper=up, randomized=True, u_rand=u, optimistic=optimistic)
         assert got.shape == (b,) and (want > 0).any()
         assert torch.allclose(got.cpu(), want, rtol=1e-6, atol=1e-10)
+
+
+@pytest.mark.parametrize("temp,refine", [(3e-2, 0), (1e-2, 2)])
+def test_cnei_matches_oracle(temp, refine):
+    """qConformalNoisyExpectedImprovement (acquisitions.py:106-139) with a pruned baseline, against the closed-form oracle."""
+    from conformal_bayesopt_b200.acquisitions import qConformalNoisyExpectedImprovement
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    dev = _dev()
+    N, d, b, G, nb, S = 90, 4, 21, 32, 7, 2
+    p = make_problem(N, d, seed=13)
+    inp = make_inputs(N, d, b, 1, G, S=S, seed=13)
+    g = torch.Generator().manual_seed(4)
+    Xb = torch.cat([p["X"][torch.randperm(N, generator=g)[:nb - 1]], torch.rand(1, d, generator=g, dtype=torch.float64)])
+    eps_mc = torch.randn(S, G, nb + 1, generator=g, dtype=torch.float64)
+    ratio, est = _estimator(d, dev)
+    gs = IIDNormalSampler(G)
+    gs.set_base_samples(inp["eps_grid"])
+    mc = IIDNormalSampler(S, batch_range=(0, -3))
+    mc.set_base_samples(eps_mc)
+    acq = qConformalNoisyExpectedImprovement(alpha=0.15, temp=temp, grid_res=G, max_grid_refinements=refine,
+                                             ratio_estimator=est, grid_sampler=gs, randomized=True, model=_state(p, dev),
+                                             X_baseline=Xb.to(dev), sampler=mc, prune_baseline=True)
+    acq.fixed_probes, acq.fixed_uniforms = inp["z"], inp["u_rand"].to(dev)
+    with torch.no_grad():
+        got = acq(inp["Xq"].to(dev))
+    want = closed_form.conformal_acquisition(oracle_state(p), inp["Xq"], kind="nei", alpha=0.15, temp=temp, grid_res=G,
+                                             max_grid_refinements=refine, eps_grid=inp["eps_grid"], z=inp["z"], eps_mc=eps_mc,
+                                             ratio=ratio, randomized=True, u_rand=inp["u_rand"], optimistic=False, X_baseline=Xb)
+    assert (want["acq"] > 0).any()
+    assert torch.allclose(got.cpu(), want["acq"], rtol=1e-6, atol=1e-10)
+    with pytest.raises(NotImplementedError):
+        qConformalNoisyExpectedImprovement(alpha=0.15, temp=temp, grid_res=G, max_grid_refinements=0, ratio_estimator=None,
+                                           model=_state(p, dev), X_baseline=p["X"].to(dev))      # 90 baseline points: prune first
