@@ -66,11 +66,16 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
     ood = torch.sigmoid((omega_c - alpha) / temp) if temp > 0 else (omega_c >= alpha).to(U)
 
     def one_pass(cov):
-        Lc = torch.linalg.cholesky(cov)
-        dev = (Lc.unsqueeze(1) @ eps_grid.unsqueeze(-1)).squeeze(-1)        # (b,G,q) = y_g - mu
-        sol = torch.linalg.solve_triangular(Lc.unsqueeze(1), dev.unsqueeze(-1), upper=False).squeeze(-1)
-        logdet = 2.0 * torch.diagonal(Lc, dim1=-2, dim2=-1).log().sum(-1)
-        logp = -0.5 * (sol.pow(2).sum(-1) + logdet.unsqueeze(1) + q * LOG2PI)
+        # the grid and its log-density are built under torch.no_grad() in the reference (helpers.py:118-119): constants
+        # w.r.t. the candidate; everything below (the refit on (x, y_g)) is differentiable in x
+        with torch.no_grad():
+            Lc = torch.linalg.cholesky(cov)
+            dev0 = (Lc.unsqueeze(1) @ eps_grid.unsqueeze(-1)).squeeze(-1)   # (b,G,q) = y_g - mu
+            sol = torch.linalg.solve_triangular(Lc.unsqueeze(1), dev0.unsqueeze(-1), upper=False).squeeze(-1)
+            logdet = 2.0 * torch.diagonal(Lc, dim1=-2, dim2=-1).log().sum(-1)
+            logp = -0.5 * (sol.pow(2).sum(-1) + logdet.unsqueeze(1) + q * LOG2PI)
+            grid_const = mu.unsqueeze(1) + dev0
+        dev = grid_const - mu.unsqueeze(1)                                  # same numbers; carries d/dx of mu
         Bg = dev @ Sinv.transpose(-1, -2)                                   # (b,G,q)  S^-1 (y_g - mu)
         r_train = noise * (gp.alpha.view(1, 1, N) - Bg @ W)                 # (b,G,N)
         r_cand = noise * Bg                                                 # (b,G,q)
@@ -101,13 +106,13 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
                 use_ub = (u_rand[..., j] < p).to(U)
                 M = M - (1.0 - use_ub) * D
             mask[..., j] = torch.sigmoid((M - alpha) / temp) if temp > 0 else (M > alpha).to(U)
-        return mu.unsqueeze(1) + dev, logp, mask, dev
+        return grid_const, logp, mask, dev
 
-    cov = S.clone()
+    cov = S.detach().clone()
     best = (float("inf"),)
     for _ in range(max_grid_refinements + 1):
         grid, logp, mask, dev = one_pass(cov)
-        num_acc = (mask >= 0.5).float().sum(1)                              # float32 statistics, as helpers.py:150-167
+        num_acc = (mask.detach() >= 0.5).float().sum(1)                     # float32 statistics, as helpers.py:150-167
         diff = num_acc / G - 0.5
         score = diff.pow(2).mean()
         if score < best[0]:
@@ -164,7 +169,7 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
         raise ValueError(kind)
 
     # ---- A-7 integration -----------------------------------------------------------------
-    opt = (grid >= mu.unsqueeze(1)).to(U) if optimistic else torch.ones_like(grid)
+    opt = (grid >= mu.detach().unsqueeze(1)).to(U) if optimistic else torch.ones_like(grid)
     nonconf = (1.0 - mask) * opt
     nonconf = nonconf / nonconf.sum(1, keepdim=True).clamp_min(1e-6)
     conf = mask * opt / logp.exp().clamp_min(1e-6).unsqueeze(-1)

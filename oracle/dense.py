@@ -189,7 +189,8 @@ def construct_conformal_bands(gp: GPState, Xq, alpha, temp, grid_res, max_grid_r
     refit (dense caches of the kept pass), ood_mask (b,G,q)."""
     assert Xq.ndim >= 3 and grid_res >= 2
     b, q, _ = Xq.shape
-    mean, cov = posterior(gp, Xq, observation_noise=True)
+    with torch.no_grad():                                            # helpers.py:118-119
+        mean, cov = posterior(gp, Xq, observation_noise=True)
     if eps_grid.ndim == 2:
         eps_grid = eps_grid.unsqueeze(0).expand(b, -1, -1)           # collapse_batch_dims=True: shared over candidates
     best = (float("inf"), None, None, None, None, None)
@@ -205,7 +206,7 @@ def construct_conformal_bands(gp: GPState, Xq, alpha, temp, grid_res, max_grid_r
         conf_pred_mask, refit, _, ood_mask = conformal_gp_regression(
             gp, Xq, target_grid, alpha, temp, z, ratio=ratio, randomized=randomized, u_rand=u_rand)
 
-        num_accepted = (conf_pred_mask >= 0.5).float().sum(1)        # (b,q)  float32, as helpers.py:150-155
+        num_accepted = (conf_pred_mask.detach() >= 0.5).float().sum(1)   # (b,q)  float32, as helpers.py:150-155
         min_acc, max_acc = num_accepted.min(), num_accepted.max()
         diff = num_accepted / grid_res - 0.5
         grid_score = diff.pow(2).mean()
@@ -227,7 +228,8 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
     target_grid, logp, mask, refit, ood = construct_conformal_bands(
         gp, Xq, alpha, temp, grid_res, max_grid_refinements, eps_grid, z, ratio, randomized, u_rand)
     if optimistic:
-        mean, _ = posterior(gp, Xq, observation_noise=False)
+        with torch.no_grad():                                        # acquisitions.py:58-59
+            mean, _ = posterior(gp, Xq, observation_noise=False)
         opt_mask = (target_grid >= mean.unsqueeze(1)).to(target_grid)
     else:
         opt_mask = torch.ones_like(target_grid)

@@ -121,3 +121,24 @@ def test_cnei_dense_equals_closed_form():
     assert (a["acq"] > 0).any()
     assert torch.allclose(a["values"], c["values"], rtol=1e-7, atol=1e-10)
     assert torch.allclose(a["acq"], c["acq"], rtol=1e-7, atol=1e-11)
+
+
+@pytest.mark.parametrize("kind,ratio_on,rand", [("ucb", True, True), ("ei", False, False)])
+def test_gradients_dense_equals_closed_form(kind, ratio_on, rand):
+    """d acq / d X by autograd through both restatements (grid, its log-density and the optimistic mask are constants,
+    as in the reference: helpers.py:118-119, acquisitions.py:58-59)."""
+    N, d, b, G = 24, 3, 4, 10
+    p = make_problem(N, d, seed=21, fn="sin")
+    gp = oracle_state(p)
+    inp = make_inputs(N, d, b, 1, G, S=2, seed=21)
+    ratio = ogp.make_ratio_mlp(d) if ratio_on else None
+    kw = dict(kind=kind, alpha=0.2, temp=5e-2, grid_res=G, eps_grid=inp["eps_grid"], z=inp["z"], eps_mc=inp["eps_mc"],
+              ratio=ratio, randomized=rand, u_rand=inp["u_rand"], optimistic=True, beta_prime=1.2, best_f=0.1)
+    grads = []
+    for mod in (dense, closed_form):
+        X = inp["Xq"].clone().requires_grad_(True)
+        out = mod.conformal_acquisition(gp, X, **kw)
+        (g,) = torch.autograd.grad(out["acq"].sum(), X)
+        grads.append(g)
+    assert grads[0].abs().max() > 1e-3
+    assert torch.allclose(grads[0], grads[1], rtol=1e-6, atol=1e-9)
