@@ -221,8 +221,8 @@ def run_ours(args):
         step()
     barrier()
     lib.cbo_timing_enable(1)
-    ms = (C.c_double * 5)()
-    nl = (C.c_int64 * 5)()
+    ms = (C.c_double * 8)()
+    nl = (C.c_int64 * 8)()
     lib.cbo_timing_collect(ms, nl)
     sampler = ClockSampler(local)
     launches0 = ops.LAUNCH_COUNT

@@ -13,7 +13,7 @@ EXPORTS = [
     "cbo_version", "cbo_status_str", "cbo_last_cuda_error", "cbo_padded_n", "cbo_workspace_bytes",
     "cbo_conformal_acq_f64", "cbo_conformal_acq_host_f64", "cbo_conf_mask_to_bounds_f64",
     "cbo_ratio_forward_f64", "cbo_gemm_tn_f64", "cbo_kernel_rows_f64", "cbo_timing_enable", "cbo_timing_collect",
-    "cbo_cehvi_integrate_f64",
+    "cbo_cehvi_integrate_f64", "cbo_conformal_acq_grad_f64", "cbo_workspace_bytes_grad",
 ]
 
 c_dp = C.c_void_p  # device pointers travel as integers
@@ -81,6 +81,12 @@ def load():
     lib.cbo_conformal_acq_f64.argtypes = [C.POINTER(GpF64), C.POINTER(RatioMlpF64), C.POINTER(Params), c_dp, C.c_int64,
                                           c_dp, c_dp, c_dp, c_dp, C.POINTER(OutputsF64), c_dp, C.c_size_t, C.c_int64,
                                           c_dp]
+    lib.cbo_workspace_bytes_grad.restype = C.c_size_t
+    lib.cbo_workspace_bytes_grad.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.POINTER(Params), C.c_int64]
+    lib.cbo_conformal_acq_grad_f64.restype = C.c_int
+    lib.cbo_conformal_acq_grad_f64.argtypes = [C.POINTER(GpF64), C.POINTER(RatioMlpF64), C.POINTER(Params), c_dp, C.c_int64,
+                                               c_dp, c_dp, c_dp, c_dp, C.POINTER(OutputsF64), c_dp, c_dp, C.c_size_t,
+                                               C.c_int64, c_dp]
     lib.cbo_conformal_acq_host_f64.restype = C.c_int
     lib.cbo_conformal_acq_host_f64.argtypes = [C.POINTER(GpF64), C.POINTER(RatioMlpF64), C.POINTER(Params), c_dp,
                                                C.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_size_t,

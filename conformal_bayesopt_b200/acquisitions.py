@@ -6,8 +6,11 @@
 reference (acquisitions.py:80-86, 107-113, 143-149) and the BoTorch bases it mixes in
 (`model`, `beta` / `best_f`, `sampler`, `objective`, `posterior_transform`, `X_pending`).
 
-Joint batches q <= 4 (incl. X_pending) are supported.  Not built yet (raise, never silently fall back):
-non-identity objectives / posterior transforms, autograd through `forward`.
+Joint batches q <= 4 (incl. X_pending) are supported.  `forward` is differentiable in X for q = 1 cUCB / cEI
+(SURVEY.md §8f-1): when X requires grad, ONE call of cbo_conformal_acq_grad_f64 returns the values and d acq / d X, and a
+custom autograd.Function hands the stored Jacobian rows to `backward` (what optimize_acqf_sgld / L-BFGS-B need:
+conformalbo/optim/optimize.py:224-235).  Not built yet (raise, never silently fall back): non-identity objectives /
+posterior transforms, gradients for q > 1 or cNEI.
 """
 from __future__ import annotations
 
@@ -20,6 +23,21 @@ from torch import nn
 from . import ops
 from .helpers import _ratio_weights, as_state, draw_probes
 from .sampling import IIDNormalSampler
+
+
+class _ConformalAcqFn(torch.autograd.Function):
+    """acq = f(X) with the per-candidate Jacobian rows computed by the kernels in the same call (acq[c] depends on X[c]
+    only, so the vector-Jacobian product is a row scaling)."""
+
+    @staticmethod
+    def forward(ctx, X, acq, dacq_dX):
+        ctx.save_for_backward(dacq_dX)
+        return acq.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dacq_dX,) = ctx.saved_tensors
+        return (grad_out.reshape(-1, 1, 1) * dacq_dX).to(dacq_dX.dtype), None, None
 
 
 class ConformalAcquisition(nn.Module):
@@ -73,16 +91,18 @@ class ConformalAcquisition(nn.Module):
     def _conformal_fwd(self, X: torch.Tensor, outputs=()) -> torch.Tensor:
         if self.model is None:
             raise AttributeError("ConformalAcquisition must be subclassed")
-        if X.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError("d acq / d X is not built yet (SURVEY.md §8f-1); call under torch.no_grad()")
+        want_grad = X.requires_grad and torch.is_grad_enabled()
+        X_in = X
         state = as_state(self.model)
         if X.ndim == 2:                                          # t_batch_mode_transform: add the t-batch dim
             X = X.unsqueeze(0)
         if self.X_pending is not None:                           # concatenate_pending_points
             X = torch.cat([X, self.X_pending.to(X).expand(*X.shape[:-2], -1, -1)], dim=-2)
         lead, (q, d) = X.shape[:-2], X.shape[-2:]
+        if want_grad and (q != 1 or self._kind not in ("ucb", "ei")):
+            raise NotImplementedError("d acq / d X is built for q = 1 cUCB / cEI (SURVEY.md §8f-1); call under torch.no_grad()")
         dev = X.device
-        Xf = X.reshape(-1, q, d)
+        Xf = X.detach().reshape(-1, q, d)
         b, G = Xf.shape[0], self.grid_res
         self.grid_sampler._sample_shape = torch.Size([G])
         if self.grid_sampler.collapse_batch_dims:
@@ -96,11 +116,15 @@ class ConformalAcquisition(nn.Module):
         if self.randomized and u is None:
             u = torch.rand(b, G, q, dtype=torch.float64, device=dev)
         out = ops.conformal_acq(state, Xf, eps_grid=eps, z=z, eps_mc=eps_mc, u_rand=u,
-                                ratio=_ratio_weights(self.ratio_estimator, dev), outputs=outputs,
+                                ratio=_ratio_weights(self.ratio_estimator, dev), outputs=outputs, want_grad=want_grad,
                                 alpha=self.alpha, temp=self.temp, grid_res=G,
                                 max_grid_refinements=self.max_grid_refinements, randomized=self.randomized,
                                 optimistic=self.optimistic, **self._acq_params())
         self.last_outputs = out
+        if want_grad:
+            Xg = X_in.unsqueeze(0) if X_in.ndim == 2 else X_in           # q = 1 and no pending points here
+            acq = _ConformalAcqFn.apply(Xg.reshape(-1, 1, d), out["acq"], out["dacq_dX"].to(X.dtype))
+            return acq.reshape(lead).to(X.dtype)
         return out["acq"].reshape(lead).to(X.dtype)
 
     def forward(self, X: torch.Tensor) -> torch.Tensor:
@@ -120,6 +144,8 @@ class qConformalUpperConfidenceBound(ConformalAcquisition):
             raise TypeError("qConformalUpperConfidenceBound needs beta")
         self.beta_prime = math.sqrt(beta * math.pi / 2)          # botorch qUpperConfidenceBound (App. B-10)
 
+    _kind = "ucb"
+
     def _acq_params(self):
         return dict(kind="ucb", beta_prime=self.beta_prime)
 
@@ -136,6 +162,8 @@ class qConformalExpectedImprovement(ConformalAcquisition):
         if best_f is None:
             raise TypeError("qConformalExpectedImprovement needs best_f")
         self.register_buffer("best_f", torch.as_tensor(best_f, dtype=torch.float64).reshape(()))
+
+    _kind = "ei"
 
     def _acq_params(self):
         return dict(kind="ei", best_f=float(self.best_f))

@@ -16,6 +16,8 @@
 #include "score_q.cuh"
 #include "mobo.cuh"
 #include "nei.cuh"
+#include "score_bwd.cuh"
+#include "rows_bwd.cuh"
 
 namespace {
 
@@ -34,12 +36,12 @@ int cuda_fail(cudaError_t e, const char* where) {
 constexpr int64_t kDefaultChunk = 16384;
 
 // ---- optional per-kernel-class timing (CUDA events on the caller's stream; bench.py's roofline) ----
-enum { T_PREP = 0, T_ROWS = 1, T_GEMM1 = 2, T_GEMM2 = 3, T_SCORE = 4, T_NCLASS = 5 };
+enum { T_PREP = 0, T_ROWS = 1, T_GEMM1 = 2, T_GEMM2 = 3, T_SCORE = 4, T_SCORE_BWD = 5, T_GEMM_BWD = 6, T_ROWS_BWD = 7, T_NCLASS = 8 };
 struct Timing {
     bool enabled = false;
     std::vector<cudaEvent_t> ev[T_NCLASS];     // start/stop pairs
     std::vector<cudaEvent_t> pool;
-    int64_t launches[T_NCLASS] = {0, 0, 0, 0, 0};
+    int64_t launches[T_NCLASS] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t get() {
         cudaEvent_t e;
         if (!pool.empty()) { e = pool.back(); pool.pop_back(); return e; }
@@ -78,6 +80,7 @@ struct Workspace {
     double *UW, *V, *mu, *ut, *drc, *rn;
     double *cscale, *nacc, *acq_scratch, *stats;      // refinement only
     double* nei_values;                               // cNEI only: C x S x G
+    double *X3, *adj;                                 // gradient only: C x Np solve scratch, C x ADJ_STRIDE adjoints
     size_t bytes;
 };
 
@@ -87,7 +90,7 @@ int64_t pick_chunk(int64_t b, const cbo_params* p, int64_t chunk) {
     return chunk < b ? chunk : b;
 }
 
-Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, int64_t chunk) {
+Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, int64_t chunk, bool grad = false) {
     const int64_t Np = cbo_padded_n(N), Sp = p->num_probes, C = pick_chunk(b, p, chunk) * p->q;   // rows per chunk
     const int64_t tiles_n = Np / cbo::GEMM_BN;
     Carver c(ws);
@@ -114,6 +117,8 @@ Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, 
     w.acq_scratch = c.take<double>(R > 0 ? b : 1);
     w.stats = c.take<double>(8);
     w.nei_values = c.take<double>(p->kind == CBO_ACQ_NEI ? C * p->num_mc * p->grid_res : 1);
+    w.X3 = c.take<double>(grad ? C * Np : 1);
+    w.adj = c.take<double>(grad ? C * cbo::ADJ_STRIDE : 1);
     w.bytes = c.off;
     return w;
 }
@@ -203,6 +208,31 @@ cudaError_t launch_score(const cbo::ScoreArgs& a_in, cudaStream_t st) {
     int grid = (a.n_cand + ngroups - 1) / ngroups;     // persistent: one CTA per SM, one warp group per candidate in flight
     if (grid > num_sms()) grid = num_sms();
     cbo::k_score<SOFT><<<grid, ngroups * (32 << wl), smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <bool SOFT>
+cudaError_t launch_score_bwd(const cbo::ScoreBwdArgs& a_in, cudaStream_t st) {
+    cbo::ScoreBwdArgs a = a_in;
+    // 4 warps per candidate when there are enough candidates to fill the SMs (the per-group tables are larger than the
+    // forward kernel's: 4 groups x 4 warps), wider groups for small batches
+    int wl = 2;
+    while (wl < 4 && a.f.n_cand * (1 << wl) < 16 * num_sms()) ++wl;
+    while (wl < 4 && a.f.G > 4 * (32 << wl)) ++wl;
+    if (a.f.G > 4 * (32 << wl)) return cudaErrorInvalidConfiguration;
+    const int ngroups = cbo::score_bwd_groups_for(a.f.Np, a.f.G, 1 << wl);
+    if (ngroups < 1) return cudaErrorInvalidConfiguration;
+    a.f.wpg_log2 = wl;
+    size_t smem = cbo::score_bwd_smem_bytes(a.f.Np, a.f.G, ngroups);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(cbo::k_score_bwd<SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    int grid = (a.f.n_cand + ngroups - 1) / ngroups;
+    if (grid > num_sms()) grid = num_sms();
+    cbo::k_score_bwd<SOFT><<<grid, ngroups * (32 << wl), smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -302,17 +332,22 @@ int cbo_conf_mask_to_bounds_f64(const double* grid, const double* mask, int64_t 
     return CBO_OK;
 }
 
-int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* p, const double* Xq,
-                          int64_t b, const double* eps_grid, const double* z, const double* eps_mc,
-                          const double* u_rand, const cbo_outputs_f64* out, void* workspace, size_t workspace_bytes,
-                          int64_t chunk, void* stream) {
+static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* p, const double* Xq,
+                              int64_t b, const double* eps_grid, const double* z, const double* eps_mc,
+                              const double* u_rand, const cbo_outputs_f64* out, double* dX, void* workspace,
+                              size_t workspace_bytes, int64_t chunk, void* stream) {
     int st = validate(gp, p, b);
     if (st != CBO_OK) return st;
+    const bool grad = dX != nullptr;
+    if (grad) {   // the reverse pass is built for the throughput path: q = 1, cUCB / cEI
+        if (p->q != 1 || (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI)) return CBO_ERR_UNSUPPORTED;
+        if (p->grid_res > 2048 || cbo::score_bwd_groups_for((int)gp->Np, (int)p->grid_res, 16) < 1) return CBO_ERR_UNSUPPORTED;
+    }
     if (!Xq || !eps_grid || !z || !eps_mc || !out || !out->acq || !workspace) return CBO_ERR_INVALID_ARG;
     if (p->randomized && !u_rand) return CBO_ERR_INVALID_ARG;
     if (ratio && (ratio->hidden < 1 || ratio->hidden > cbo::MAX_H)) return CBO_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(workspace) % kAlign) return CBO_ERR_WORKSPACE;
-    Workspace w = carve(workspace, gp->N, gp->d, b, p, chunk);
+    Workspace w = carve(workspace, gp->N, gp->d, b, p, chunk, grad);
     if (w.bytes > workspace_bytes) return CBO_ERR_WORKSPACE;
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -420,10 +455,45 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
             x.refit_mean = (q == 1 && out->refit_mean) ? out->refit_mean + c0 * G : nullptr;
             x.refit_sd = (q == 1 && out->refit_sd) ? out->refit_sd + c0 : nullptr;
         };
+        // final pass: value only, or value + reverse pass (k_score_bwd -> A^-1 solve of w_bar -> k_rows_bwd)
+        auto run_final = [&](const cbo::ScoreArgs& fa) -> int {
+            const bool extra = out->target_grid || out->grid_logp || out->conf_pred_mask || out->ood_mask ||
+                               out->q_conf_scores || out->post_mean || out->post_var || out->num_accepted ||
+                               out->refit_mean || out->refit_sd;
+            if (!grad || extra) {
+                TimeScope ts_(T_SCORE, s, 1);
+                CBO_CUDA(run_score(fa));
+            }
+            if (!grad) return CBO_OK;
+            {
+                TimeScope ts_(T_SCORE_BWD, s, 1);
+                cbo::ScoreBwdArgs ba;
+                ba.f = fa;
+                ba.wbar = w.V;                                       // v is dead after ||v||^2
+                ba.adj = w.adj;
+                CBO_CUDA(soft_path ? launch_score_bwd<true>(ba, s) : launch_score_bwd<false>(ba, s));
+            }
+            {
+                TimeScope ts_(T_GEMM_BWD, s, 2);
+                CBO_CUDA(cbo::launch_gemm_tn(w.V, Np, gp->linv, Np, w.X3, Np, n, Np, Np, cbo::TRI_LOWER, nullptr, s, num_sms()));
+                CBO_CUDA(cbo::launch_gemm_tn(w.X3, Np, gp->linv_t, Np, w.V, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms()));
+            }
+            {
+                TimeScope ts_(T_ROWS_BWD, s, ratio ? 2 : 1);
+                CBO_CUDA(cbo::launch_rows_bwd(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->alpha, w.V,
+                                              w.UW, w.adj, dX + c0 * d, num_sms(), s));
+                if (ratio)
+                    cbo::k_ratio_mlp_bwd<<<(n + 127) / 128, 128, 0, s>>>(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1,
+                                                                          ratio->W2, ratio->b2, ratio->W3, ratio->b3, w.adj,
+                                                                          dX + c0 * d);
+                CBO_CUDA(cudaGetLastError());
+            }
+            return CBO_OK;
+        };
         if (R == 0) {
             set_outputs(a);
-            TimeScope ts_(T_SCORE, s, 1);
-            CBO_CUDA(run_score(a));
+            int rs = run_final(a);
+            if (rs != CBO_OK) return rs;
         } else {
             // grid refinement (helpers.py:129-189): probe passes keep only the accepted counts; the pass with the
             // smallest grid_score is then re-run into the caller's buffers.  One host sync per pass, like the
@@ -453,10 +523,33 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
             cbo::ScoreArgs fa = a;
             fa.cscale = w.cscale + int64_t(best_step) * b * q;
             set_outputs(fa);
-            CBO_CUDA(run_score(fa));
+            int rs = run_final(fa);
+            if (rs != CBO_OK) return rs;
         }
     }
     return CBO_OK;
+}
+
+int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* p, const double* Xq,
+                          int64_t b, const double* eps_grid, const double* z, const double* eps_mc,
+                          const double* u_rand, const cbo_outputs_f64* out, void* workspace, size_t workspace_bytes,
+                          int64_t chunk, void* stream) {
+    return conformal_acq_impl(gp, ratio, p, Xq, b, eps_grid, z, eps_mc, u_rand, out, nullptr, workspace, workspace_bytes,
+                              chunk, stream);
+}
+
+int cbo_conformal_acq_grad_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* p, const double* Xq,
+                               int64_t b, const double* eps_grid, const double* z, const double* eps_mc,
+                               const double* u_rand, const cbo_outputs_f64* out, double* dacq_dX, void* workspace,
+                               size_t workspace_bytes, int64_t chunk, void* stream) {
+    if (!dacq_dX) return CBO_ERR_INVALID_ARG;
+    return conformal_acq_impl(gp, ratio, p, Xq, b, eps_grid, z, eps_mc, u_rand, out, dacq_dX, workspace, workspace_bytes,
+                              chunk, stream);
+}
+
+size_t cbo_workspace_bytes_grad(int64_t N, int64_t d, int64_t b, const cbo_params* params, int64_t chunk) {
+    if (!params || N <= 0 || b <= 0) return 0;
+    return carve(nullptr, N, d, b, params, chunk, true).bytes;
 }
 
 int cbo_cehvi_integrate_f64(int64_t m, int64_t b, int64_t G, int64_t S, const double* const* mask,
@@ -494,7 +587,7 @@ void cbo_timing_enable(int on) {
 }
 
 // Sums elapsed ms per kernel class since the last collect (synchronises on the recorded events).
-int cbo_timing_collect(double* ms_out /* 5 */, int64_t* launches_out /* 5 */) {
+int cbo_timing_collect(double* ms_out /* 8 */, int64_t* launches_out /* 8 */) {
     if (!ms_out || !launches_out) return CBO_ERR_INVALID_ARG;
     for (int c = 0; c < T_NCLASS; ++c) {
         double tot = 0.0;

@@ -93,10 +93,11 @@ def make_params(*, alpha, temp, grid_res, q=1, num_mc=1, num_probes=8, max_grid_
                        C.pointer(nei) if nei is not None else None)
 
 
-def workspace(state: GPModelState, b: int, params, chunk: int = 0) -> torch.Tensor:
+def workspace(state: GPModelState, b: int, params, chunk: int = 0, grad: bool = False) -> torch.Tensor:
     """Caller-owned scratch (torch caching allocator), cached per (device, size)."""
     lib = _lib.load()
-    nbytes = lib.cbo_workspace_bytes(state.N, state.d, b, C.byref(params), chunk)
+    fn = lib.cbo_workspace_bytes_grad if grad else lib.cbo_workspace_bytes
+    nbytes = fn(state.N, state.d, b, C.byref(params), chunk)
     key = (state.device.index, torch.cuda.current_stream().cuda_stream)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
@@ -105,19 +106,23 @@ def workspace(state: GPModelState, b: int, params, chunk: int = 0) -> torch.Tens
     return ws
 
 
-def count_launches(state: GPModelState, b: int, params, ratio: bool, chunk: int = 0) -> int:
-    """Kernels one cbo_conformal_acq_f64 call enqueues (mirrors csrc/cbo_api.cu)."""
+def count_launches(state: GPModelState, b: int, params, ratio: bool, chunk: int = 0, grad: bool = False,
+                   extra_outputs: bool = False) -> int:
+    """Kernels one cbo_conformal_acq[_grad]_f64 call enqueues (mirrors csrc/cbo_api.cu)."""
     C_ = b if params.max_grid_refinements > 0 else min(b, chunk if chunk > 0 else 16384)
     n_chunks = (b + C_ - 1) // C_
     per_call = 7                                   # scale_transpose, pad_probes, 2 x probe_matvec, ratio/fill, eps_absmax, train_tables
     per_chunk = 1 + (1 if ratio else 0) + 2 + 1    # rows, ratio(cand), 2 x gemm, score
+    if grad:                                       # score value+reverse (replaces score unless extra outputs), 2 x gemm, rows reverse, ratio reverse
+        per_chunk += (1 if extra_outputs else 0) + 2 + 1 + (1 if ratio else 0)
     return per_call + n_chunks * per_chunk
 
 
 def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tensor, z: torch.Tensor,
                   eps_mc: torch.Tensor, u_rand: Optional[torch.Tensor] = None, ratio: Optional[RatioWeights] = None,
-                  outputs: Sequence[str] = (), chunk: int = 0, **param_kw) -> Dict[str, torch.Tensor]:
-    """cbo_conformal_acq_f64.  Xq (b, q=1, d) or (b, d).  Returns {'acq': (b,), + requested outputs}."""
+                  outputs: Sequence[str] = (), chunk: int = 0, want_grad: bool = False, **param_kw) -> Dict[str, torch.Tensor]:
+    """cbo_conformal_acq_f64 (or cbo_conformal_acq_grad_f64 with `want_grad`: adds 'dacq_dX' (b, q, d)).
+    Xq (b, q, d) or (b, d).  Returns {'acq': (b,), + requested outputs}."""
     global LAUNCH_COUNT
     lib = _lib.load()
     _require_cuda(Xq, eps_grid, z, eps_mc, u_rand, state.X)
@@ -151,18 +156,28 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
     for name in outputs:
         out_t[name] = torch.empty(shapes[name], dtype=torch.float64, device=dev)
     cout = _lib.OutputsF64(**{k: _ptr(v) for k, v in out_t.items()})
-    ws = workspace(state, b, params, chunk)
+    ws = workspace(state, b, params, chunk, grad=want_grad)
     ws_ptr = (ws.data_ptr() + 255) // 256 * 256
     gp_c = state.c_struct()
     ratio_c = ratio.c_struct() if ratio is not None else None
-    st = lib.cbo_conformal_acq_f64(C.byref(gp_c), C.byref(ratio_c) if ratio_c is not None else None, C.byref(params),
-                                   Xq.data_ptr(), b, eps_grid.data_ptr(), z.data_ptr(), eps_mc.data_ptr(),
-                                   _ptr(u_rand), C.byref(cout), ws_ptr, ws.numel() - 256, chunk, _stream())
-    _lib.check(st, "cbo_conformal_acq_f64")
-    LAUNCH_COUNT += count_launches(state, b, params, ratio is not None, chunk)
+    ratio_p = C.byref(ratio_c) if ratio_c is not None else None
+    if want_grad:
+        dX = torch.empty(b, q, Xq.shape[-1], dtype=torch.float64, device=dev)
+        st = lib.cbo_conformal_acq_grad_f64(C.byref(gp_c), ratio_p, C.byref(params), Xq.data_ptr(), b, eps_grid.data_ptr(),
+                                            z.data_ptr(), eps_mc.data_ptr(), _ptr(u_rand), C.byref(cout), dX.data_ptr(),
+                                            ws_ptr, ws.numel() - 256, chunk, _stream())
+        _lib.check(st, "cbo_conformal_acq_grad_f64")
+    else:
+        st = lib.cbo_conformal_acq_f64(C.byref(gp_c), ratio_p, C.byref(params), Xq.data_ptr(), b, eps_grid.data_ptr(),
+                                       z.data_ptr(), eps_mc.data_ptr(), _ptr(u_rand), C.byref(cout), ws_ptr,
+                                       ws.numel() - 256, chunk, _stream())
+        _lib.check(st, "cbo_conformal_acq_f64")
+    LAUNCH_COUNT += count_launches(state, b, params, ratio is not None, chunk, grad=want_grad, extra_outputs=len(outputs) > 0)
     if q == 1:   # squeeze the q axis (the q = 1 layout of round-1 callers)
         out_t = {k: (v.squeeze(-1) if k in ("target_grid", "conf_pred_mask", "q_conf_scores", "ood_mask", "post_mean",
                                              "num_accepted") else v) for k, v in out_t.items()}
+    if want_grad:
+        out_t["dacq_dX"] = dX
     return out_t
 
 

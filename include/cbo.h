@@ -134,6 +134,17 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
                           const double* eps_mc, const double* u_rand, const cbo_outputs_f64* out,
                           void* workspace, size_t workspace_bytes, int64_t chunk, void* stream);
 
+/* Value and gradient (q = 1, cUCB / cEI): additionally writes dacq_dX (b x d) = d acq[c] / d Xq[c, :], what the reference
+ * obtains by autograd through the same path inside optimize_acqf_sgld (conformalbo/optim/optimize.py:224-235:
+ * acq_function(X).sum().backward()); the target grid, its log-density and the optimistic mask are constants, as they are
+ * built under torch.no_grad() there (helpers.py:118-119, acquisitions.py:58-59).  temp <= 0: the masks are step functions
+ * (zero gradient through them), the value path still differentiates.  Workspace: cbo_workspace_bytes_grad. */
+size_t cbo_workspace_bytes_grad(int64_t N, int64_t d, int64_t b, const cbo_params* params, int64_t chunk);
+int cbo_conformal_acq_grad_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* params,
+                               const double* Xq, int64_t b, const double* eps_grid, const double* z,
+                               const double* eps_mc, const double* u_rand, const cbo_outputs_f64* out,
+                               double* dacq_dX, void* workspace, size_t workspace_bytes, int64_t chunk, void* stream);
+
 /* Same call with HOST candidate / result buffers (pinned for full speed): H2D of Xq_host and
  * D2H of acq_host are issued on `stream` inside the call; synchronises the stream on return. */
 int cbo_conformal_acq_host_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* params,
@@ -171,9 +182,10 @@ int cbo_kernel_rows_f64(const cbo_gp_f64* gp, const double* Xq, int64_t n, doubl
                         void* stream);
 
 /* Optional per-kernel-class timing with CUDA events on the caller's stream (bench.py's roofline leg).
- * Classes: 0 per-call tables, 1 kernel rows (+candidate ratio MLP), 2 GEMM pass 1, 3 GEMM pass 2, 4 score. */
+ * Classes: 0 per-call tables, 1 kernel rows (+candidate ratio MLP), 2 GEMM pass 1, 3 GEMM pass 2, 4 score,
+ * 5 score value+reverse, 6 reverse GEMM passes, 7 kernel-row reverse (+ratio MLP reverse). */
 void cbo_timing_enable(int on);
-int cbo_timing_collect(double* ms_out /* 5 */, int64_t* launches_out /* 5 */);
+int cbo_timing_collect(double* ms_out /* 8 */, int64_t* launches_out /* 8 */);
 
 #ifdef __cplusplus
 }

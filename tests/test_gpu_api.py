@@ -66,9 +66,12 @@ def test_acquisition_forward_matches_oracle(cls_name, extra, kind):
     with torch.no_grad():
         one = acq(inp["Xq"][0].to(dev))
     assert one.shape == (1,) and torch.allclose(one.cpu(), want["acq"][:1], rtol=1e-6, atol=1e-9)
-    # gradients are not built: fail loudly instead of returning a constant
-    with pytest.raises(NotImplementedError):
-        acq(inp["Xq"].to(dev).requires_grad_(True))
+    # gradients: built for q = 1 (tests/test_gpu_grad.py); the value of a grad-enabled call is the same value
+    acq.fixed_uniforms = inp["u_rand"][:, :, 0].to(dev)
+    Xg = inp["Xq"].to(dev).requires_grad_(True)
+    val = acq(Xg)
+    val.sum().backward()
+    assert torch.allclose(val.detach().cpu(), want["acq"], rtol=1e-6, atol=1e-9) and torch.isfinite(Xg.grad).all()
     # X_pending makes q = 2: injected inputs of the wrong shape (z has N+1 rows) are refused, not silently mis-read
     acq.set_X_pending(inp["Xq"][0].to(dev))
     from conformal_bayesopt_b200 import _lib

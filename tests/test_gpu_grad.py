@@ -1,0 +1,166 @@
+"""GPU parity of d acq / d X: cbo_conformal_acq_grad_f64 against torch.autograd through the closed-form
+oracle and against the hand-derived reverse pass (oracle/analytic_grad.py), stage by stage.
+
+Tolerance: 1e-6 relative (north_star) on the gradient rows, with an absolute floor of 1e-9 times the largest entry
+(the soft-rank sigmoid is evaluated to ~3e-10 absolute in the kernels).
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import analytic_grad, closed_form
+from oracle import gp as ogp
+from tests.problems import make_inputs, make_problem, oracle_state
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    assert torch.cuda.is_available(), "run with -m gpu on a CUDA box"
+    return torch.device("cuda:0")
+
+
+def _state(p, dev):
+    from conformal_bayesopt_b200 import GPModelState
+    return GPModelState.fit_fixed(p["X"], p["y"], p["mean"], p["lengthscale"], p["outputscale"], p["noise"], device=dev)
+
+
+def _ratio(d, dev):
+    from conformal_bayesopt_b200 import ops
+    r = ogp.make_ratio_mlp(d)
+    return r, ops.RatioWeights(*[t.to(dev) for t in (r.W1, r.b1, r.W2, r.b2, r.W3, r.b3)])
+
+
+def _oracle_grad(gp, inp, ratio, **kw):
+    X = inp["Xq"].clone().requires_grad_(True)
+    out = closed_form.conformal_acquisition(gp, X, eps_grid=inp["eps_grid"], z=inp["z"], eps_mc=inp["eps_mc"], ratio=ratio,
+                                            u_rand=inp["u_rand"], **kw)
+    (g,) = torch.autograd.grad(out["acq"].sum(), X)
+    return out["acq"].detach(), g
+
+
+def _gpu(p, inp, dev, ratio_w, chunk=0, outputs=(), **kw):
+    from conformal_bayesopt_b200 import ops
+    out = ops.conformal_acq(_state(p, dev), inp["Xq"].to(dev), eps_grid=inp["eps_grid"][:, 0].to(dev), z=inp["z"].to(dev),
+                            eps_mc=inp["eps_mc"][:, :, 0].to(dev), u_rand=inp["u_rand"][:, :, 0].to(dev), ratio=ratio_w,
+                            want_grad=True, chunk=chunk, outputs=outputs, **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu() for k, v in out.items()}
+
+
+def _grad_close(got, want):
+    scale = want.abs().max().clamp_min(1e-300)
+    return torch.allclose(got, want, rtol=1e-6, atol=float(1e-9 * scale))
+
+
+CASES = [
+    # N, d, b, G, temp, randomized, ratio, kind, S, optimistic
+    (40, 3, 6, 16, 3e-2, False, False, "ucb", 1, True),
+    (200, 8, 37, 64, 3e-2, True, True, "ucb", 1, True),
+    (130, 4, 9, 32, 5e-2, True, True, "ei", 2, False),
+    (257, 8, 5, 7, 1e-2, False, True, "ei", 4, True),         # ragged N and G
+    (300, 8, 50, 64, 3e-2, True, False, "ucb", 3, True),
+    (8, 2, 128, 64, 3e-2, True, False, "ucb", 1, True),       # BASELINE config 1 shape
+    (32, 12, 224, 64, 3e-2, False, True, "ucb", 1, True),     # BASELINE config 4 shape, d > 8 (two register chunks)
+    (128, 3, 1, 2, 3e-2, False, False, "ucb", 1, True),       # minimum grid, single candidate
+    (130, 4, 9, 32, 0.0, True, True, "ucb", 2, True),         # hard path: step masks, only the value path carries gradient
+    (64, 5, 700, 200, 3e-2, False, True, "ucb", 1, True),     # G > threads of one 4-warp group
+]
+
+
+@pytest.mark.parametrize("N,d,b,G,temp,rand,ratio_on,kind,S,opt", CASES)
+def test_grad_matches_autograd_of_oracle(N, d, b, G, temp, rand, ratio_on, kind, S, opt):
+    dev = _dev()
+    p = make_problem(N, d, seed=N)
+    inp = make_inputs(N, d, b, 1, G, S=S, seed=N)
+    ratio, ratio_w = _ratio(d, dev) if ratio_on else (None, None)
+    kw = dict(kind=kind, alpha=0.1, temp=temp, grid_res=G, randomized=rand, optimistic=opt,
+              beta_prime=math.sqrt(0.2 * math.pi / 2), best_f=0.3)
+    acq, g = _oracle_grad(oracle_state(p), inp, ratio, **kw)
+    got = _gpu(p, inp, dev, ratio_w, **kw)
+    assert torch.allclose(got["acq"], acq, rtol=1e-6, atol=1e-9)
+    assert G == 2 or g.abs().max() > 0          # (two grid points: the normalised weights do not move)
+    assert _grad_close(got["dacq_dX"], g)
+
+
+def test_grad_call_value_equals_forward_call_and_chunking():
+    from conformal_bayesopt_b200 import ops
+    dev = _dev()
+    N, d, b, G = 150, 6, 100, 33
+    p = make_problem(N, d, seed=5)
+    inp = make_inputs(N, d, b, 1, G, S=2, seed=5)
+    _, ratio_w = _ratio(d, dev)
+    kw = dict(kind="ucb", alpha=0.1, temp=3e-2, grid_res=G, randomized=True, optimistic=True, beta_prime=1.1)
+    full = _gpu(p, inp, dev, ratio_w, outputs=("conf_pred_mask",), **kw)
+    chunked = _gpu(p, inp, dev, ratio_w, chunk=32, **kw)
+    fwd = ops.conformal_acq(_state(p, dev), inp["Xq"].to(dev), eps_grid=inp["eps_grid"][:, 0].to(dev), z=inp["z"].to(dev),
+                            eps_mc=inp["eps_mc"][:, :, 0].to(dev), u_rand=inp["u_rand"][:, :, 0].to(dev), ratio=ratio_w,
+                            outputs=("conf_pred_mask",), **kw)
+    assert torch.allclose(full["acq"], fwd["acq"].cpu(), rtol=1e-12, atol=1e-14)
+    assert torch.equal(full["conf_pred_mask"], fwd["conf_pred_mask"].cpu())
+    assert torch.equal(full["dacq_dX"], chunked["dacq_dX"]) and torch.equal(full["acq"], chunked["acq"])
+
+
+def test_grad_stage_adjoints_match_analytic_reverse_pass():
+    """Same call, checked against the hand-derived reverse pass (identical algebra) -- tight tolerance."""
+    dev = _dev()
+    N, d, b, G = 96, 4, 12, 24
+    p = make_problem(N, d, seed=9)
+    inp = make_inputs(N, d, b, 1, G, S=1, seed=9)
+    ratio, ratio_w = _ratio(d, dev)
+    kw = dict(kind="ucb", alpha=0.15, temp=3e-2, grid_res=G, randomized=True, optimistic=True, beta_prime=1.0)
+    want = analytic_grad.conformal_acquisition_grad(oracle_state(p), inp["Xq"], eps_grid=inp["eps_grid"], z=inp["z"],
+                                                    eps_mc=inp["eps_mc"], ratio=ratio, u_rand=inp["u_rand"], **kw)
+    got = _gpu(p, inp, dev, ratio_w, **kw)
+    assert _grad_close(got["dacq_dX"], want["grad"])
+
+
+def test_grad_with_grid_refinement_uses_the_kept_pass():
+    dev = _dev()
+    N, d, b, G = 64, 2, 20, 32
+    p = make_problem(N, d, seed=64)
+    inp = make_inputs(N, d, b, 1, G, S=1, seed=64)
+    kw = dict(kind="ei", alpha=0.1, temp=3e-2, grid_res=G, randomized=False, optimistic=True, best_f=0.3,
+              max_grid_refinements=2)
+    acq, g = _oracle_grad(oracle_state(p), inp, None, **kw)
+    got = _gpu(p, inp, dev, None, **kw)
+    assert torch.allclose(got["acq"], acq, rtol=1e-6, atol=1e-9)
+    assert _grad_close(got["dacq_dX"], g)
+
+
+def test_acquisition_class_backward():
+    """forward(X) with X.requires_grad -> .sum().backward(), the call pattern of optimize_acqf_sgld (optim/optimize.py:224-235)."""
+    from conformal_bayesopt_b200.acquisitions import qConformalExpectedImprovement, qConformalUpperConfidenceBound
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    dev = _dev()
+    N, d, b, G = 80, 3, 10, 16
+    p = make_problem(N, d, seed=80)
+    inp = make_inputs(N, d, b, 1, G, S=1, seed=80)
+    state = _state(p, dev)
+    for cls, extra, okw in ((qConformalUpperConfidenceBound, dict(beta=0.2), dict(kind="ucb", beta_prime=math.sqrt(0.2 * math.pi / 2))),
+                            (qConformalExpectedImprovement, dict(best_f=0.3), dict(kind="ei", best_f=0.3))):
+        gs, ms = IIDNormalSampler(G), IIDNormalSampler(1, batch_range=(0, -3))
+        gs.set_base_samples(inp["eps_grid"]); ms.set_base_samples(inp["eps_mc"])
+        acqf = cls(0.1, 3e-2, G, 0, None, optimistic=True, grid_sampler=gs, model=state, sampler=ms, **extra)
+        acqf.fixed_probes = inp["z"]
+        X = inp["Xq"].to(dev).requires_grad_(True)
+        val = acqf(X)
+        (2.0 * val).sum().backward()
+        acq, g = _oracle_grad(oracle_state(p), inp, None, alpha=0.1, temp=3e-2, grid_res=G, optimistic=True, **okw)
+        assert torch.allclose(val.detach().cpu(), acq, rtol=1e-6, atol=1e-9)
+        assert _grad_close(X.grad.cpu(), 2.0 * g)
+        with torch.no_grad():
+            assert torch.allclose(acqf(X), val.detach(), rtol=1e-12)
+
+
+def test_grad_refuses_what_is_not_built():
+    from conformal_bayesopt_b200 import _lib
+    dev = _dev()
+    p = make_problem(40, 3, seed=1)
+    inp = make_inputs(40, 3, 4, 2, 8, seed=1)
+    from conformal_bayesopt_b200 import ops
+    with pytest.raises(_lib.CboError, match="unsupported"):
+        ops.conformal_acq(_state(p, dev), inp["Xq"].to(dev), eps_grid=inp["eps_grid"].to(dev), z=inp["z"].to(dev),
+                          eps_mc=inp["eps_mc"].to(dev), want_grad=True, kind="ucb", alpha=0.1, temp=3e-2, grid_res=8,
+                          beta_prime=1.0)

@@ -142,3 +142,24 @@ def test_gradients_dense_equals_closed_form(kind, ratio_on, rand):
         grads.append(g)
     assert grads[0].abs().max() > 1e-3
     assert torch.allclose(grads[0], grads[1], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind,ratio_on,rand,temp,S,opt", [
+    ("ucb", True, True, 5e-2, 2, True), ("ei", False, False, 5e-2, 2, True), ("ucb", False, False, 3e-2, 1, True),
+    ("ei", True, True, 3e-2, 1, False), ("ucb", True, True, 0.0, 2, True)])
+def test_hand_derived_reverse_pass_equals_autograd(kind, ratio_on, rand, temp, S, opt):
+    """oracle/analytic_grad.py (the algebra of the CUDA reverse pass) against autograd through the closed-form oracle."""
+    from oracle import analytic_grad
+    N, d, b, G = 24, 3, 5, 10
+    gp = oracle_state(make_problem(N, d, seed=21, fn="sin"))
+    inp = make_inputs(N, d, b, 1, G, S=S, seed=21)
+    ratio = ogp.make_ratio_mlp(d) if ratio_on else None
+    kw = dict(kind=kind, alpha=0.2, temp=temp, grid_res=G, eps_grid=inp["eps_grid"], z=inp["z"], eps_mc=inp["eps_mc"],
+              ratio=ratio, randomized=rand, u_rand=inp["u_rand"], optimistic=opt, beta_prime=1.2, best_f=0.1)
+    X = inp["Xq"].clone().requires_grad_(True)
+    out = closed_form.conformal_acquisition(gp, X, **kw)
+    (g,) = torch.autograd.grad(out["acq"].sum(), X)
+    an = analytic_grad.conformal_acquisition_grad(gp, inp["Xq"], **kw)
+    assert torch.allclose(an["acq"], out["acq"].detach(), rtol=1e-12, atol=1e-14)
+    assert g.abs().max() > 1e-3
+    assert torch.allclose(an["grad"], g, rtol=1e-9, atol=1e-12)

@@ -16,7 +16,7 @@ for b in (8, 128, 1024, 4096):
         ops.conformal_acq(st, Xq, eps_grid=eg, z=z, eps_mc=em, **kw)
     torch.cuda.synchronize()
     lib.cbo_timing_enable(1)
-    ms = (C.c_double * 5)(); nl = (C.c_int64 * 5)()
+    ms = (C.c_double * 8)(); nl = (C.c_int64 * 8)()
     lib.cbo_timing_collect(ms, nl)
     reps = 10
     for _ in range(reps):
