@@ -61,8 +61,8 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = lib_path()
-    if _build.is_stale():
+    path = os.environ.get("CBO_LIB_PATH") or lib_path()     # CBO_LIB_PATH: experiment builds (tools/); never a fallback
+    if path == lib_path() and _build.is_stale():
         try:
             _build.build()
         except Exception as e:  # no nvcc on this host: use the shipped .so if there is one

@@ -195,6 +195,7 @@ cudaError_t launch_score(const cbo::ScoreArgs& a_in, cudaStream_t st) {
     // warps per candidate: pairs when there are enough candidates to fill the SMs, wider groups for small batches
     int wl = 1;
     while (wl < 4 && a.n_cand * (1 << wl) < 16 * num_sms()) ++wl;
+    while (wl > 1 && (1 << wl) > 2 * cbo::SCORE_FWD_PAIRS) --wl;
     const int ngroups = cbo::score_groups_for(a.Np, a.G, 1 << wl);
     if (ngroups < 1) return cudaErrorInvalidConfiguration;
     a.wpg_log2 = wl;

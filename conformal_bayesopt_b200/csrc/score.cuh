@@ -25,8 +25,16 @@
 
 namespace cbo {
 
-constexpr int SCORE_MAX_PAIRS = 8;
-constexpr int SCORE_GPW = 4;           // grid points per pass
+#ifndef CBO_FWD_PAIRS
+#define CBO_FWD_PAIRS 8
+#endif
+#ifndef CBO_FWD_GPW
+#define CBO_FWD_GPW 4
+#endif
+constexpr int SCORE_MAX_PAIRS = 8;     // warp pairs per CTA of the value+reverse kernel
+constexpr int SCORE_GPW = 4;           // grid points per pass (value+reverse kernel)
+constexpr int SCORE_FWD_PAIRS = CBO_FWD_PAIRS;   // forward kernel: warp pairs per CTA ...
+constexpr int SCORE_FWD_GPW = CBO_FWD_GPW;       // ... and grid points per pass (independent chains per lane)
 constexpr int MAX_S = 16;
 
 struct ScoreArgs {
@@ -76,7 +84,7 @@ inline int score_groups_for(int Np, int G, int wpg) {
     size_t avail = 227 * 1024;
     if (score_smem_shared_bytes(Np) + score_smem_pair_bytes(Np, G) > avail) return 0;
     size_t w = (avail - score_smem_shared_bytes(Np)) / score_smem_pair_bytes(Np, G);
-    size_t cap = size_t(2 * SCORE_MAX_PAIRS / wpg);
+    size_t cap = size_t(2 * SCORE_FWD_PAIRS / wpg);
     return int(w > cap ? cap : w);
 }
 inline int score_pairs_for(int Np, int G) { return score_groups_for(Np, G, 2); }
@@ -99,17 +107,31 @@ __device__ __forceinline__ int pair_barrier_or(int group, int nthr, int pred) {
 // Phase B row sweep for SCORE_GPW grid points: hard count, soft-rank sigmoid, weighted sums.
 // Soft rank: rho = sigmoid(dd / temp) = 1 / (1 + e),  e = exp(-dd/temp) = 2^(-x/16),  x = c1 dd.  With
 // n = -round(x) = 16 kk + j:  e = 2^kk * tab[j] * P(x - round(x)),  P(y) ~ exp(-y ln2/16) on [-1/2, 1/2] (16-entry
-// table + near-minimax cubic, rel. err 1.2e-9); 1/(1+e) from a MUFU.RCP64H seed and one Newton step: 14 fp64-pipe
-// instructions per (train point, grid point).  CLAMP = true clamps |x| at 946 = 41 * 16/ln2 in the integer domain
+// table + near-minimax cubic, rel. err 1.2e-9); 1/(1+e) from a MUFU.RCP64H seed and one Newton step folded into the
+// running sum: 11 fp64-pipe instructions per (train point, grid point) without a ratio estimator, 13 with one.  CLAMP = true clamps |x| at 946 = 41 * 16/ln2 in the integer domain
 // (rho is 0 or 1 to 2e-18 beyond that); phase A proves |x| < 900 for most candidates and then the clamp (4 integer
 // instructions per element of an issue-bound loop) is compiled out.
 // UNIT = true: no ratio estimator, every train point has importance weight 1 (the reference's `ratio_estimator=None`
 // branch, helpers.py:286-290): sum rho * dr == sum rho, one fp64 instruction and one shared-memory load less.
-template <bool SOFT, bool CLAMP, bool UNIT>
+// 2^(n/16) for n = 16 kk + j from the 16-entry table of bit patterns  bits(2^(j/16)) - (j << 48):  adding n << 16 to the
+// high word then yields exactly high(2^(j/16)) + (kk << 20).  Three non-fp64 instructions and one LDS: shift, LOP3
+// (mask and OR with the 128-byte-aligned table address), load, LEA.
+__device__ __forceinline__ double exp_tab_scaled(unsigned tab_s, int n) {
+    unsigned addr = ((unsigned(n) << 3) & 0x78u) | tab_s;
+    int lo, hi;
+    asm("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
+    return __hiloint2double(hi + (n << 16), lo);
+}
+__device__ __forceinline__ void exp_tab_init(double* tab, int j) {
+    double v = exp2(double(j) / 16.0);
+    tab[j] = __hiloint2double(__double2hiint(v) - (j << 16), __double2loint(v));
+}
+
+template <bool SOFT, bool CLAMP, bool UNIT, int GPW>
 __device__ __forceinline__ void score_rows(const ScoreArgs& p, const double* __restrict__ sq, const double* __restrict__ sdr,
-                                           const double* __restrict__ tab, int lane, int N32,
-                                           const double (&bg)[SCORE_GPW], double (&sr)[SCORE_GPW], double (&sw)[SCORE_GPW],
-                                           unsigned (&cneg)[SCORE_GPW]) {
+                                           unsigned tab_s, int lane, int N32,
+                                           const double (&bg)[GPW], double (&sr)[GPW], double (&sw)[GPW],
+                                           unsigned (&cneg)[GPW]) {
     const double kMagic = p.k_magic;                          // 1.5 * 2^52
     const double kC0 = p.k_c0, kC1n = p.k_c1n, kC2 = p.k_c2, kC3n = p.k_c3n;
     constexpr int kSatHi = 0x408d9000;                        // hiword(946.0)
@@ -119,16 +141,16 @@ __device__ __forceinline__ void score_rows(const ScoreArgs& p, const double* __r
     for (int i = lane; i < N32; i += 32) {
         tq += 96; td += 32;                                   // next row (reads past N32 stay inside shared memory)
         const double qa_n = tq[0], qb_n = tq[1], qc_n = tq[2], dr_n = UNIT ? 1.0 : td[0];
-        double x[SCORE_GPW];
+        double x[GPW];
 #pragma unroll
-        for (int k = 0; k < SCORE_GPW; ++k) {
+        for (int k = 0; k < GPW; ++k) {
             x[k] = fma(fma(qa, bg[k], qb), bg[k], qc);
             cneg[k] += unsigned(__double2hiint(x[k])) >> 31;  // counts score_c < score_i
         }
         if (SOFT) {
-            double t[SCORE_GPW], yn[SCORE_GPW], e[SCORE_GPW];
+            double t[GPW], yn[GPW], e[GPW];
 #pragma unroll
-            for (int k = 0; k < SCORE_GPW; ++k) {
+            for (int k = 0; k < GPW; ++k) {
                 double xc = x[k];
                 if (CLAMP) {
                     int hi = __double2hiint(x[k]);
@@ -139,34 +161,37 @@ __device__ __forceinline__ void score_rows(const ScoreArgs& p, const double* __r
                 yn[k] = xc + (t[k] - kMagic);                 // x - round(x) in [-1/2, 1/2]
             }
 #pragma unroll
-            for (int k = 0; k < SCORE_GPW; ++k) {
+            for (int k = 0; k < GPW; ++k) {
                 double pl = fma(yn[k], kC3n, kC2);
                 pl = fma(pl, yn[k], kC1n);
                 pl = fma(pl, yn[k], kC0);                     // exp(-yn ln2/16)
-                int n = __double2loint(t[k]);
-                double ev = tab[n & 15] * pl;
-                e[k] = __hiloint2double(__double2hiint(ev) + ((n & ~15) << 16), __double2loint(ev));   // * 2^kk
+                double ts = exp_tab_scaled(tab_s, __double2loint(t[k]));   // 2^(j/16) 2^kk
+                e[k] = fma(ts, pl, 1.0);                      // 1 + e: the product and the sum are ONE fma
             }
 #pragma unroll
-            for (int k = 0; k < SCORE_GPW; ++k) {
-                double d = 1.0 + e[k];
+            for (int k = 0; k < GPW; ++k) {
+                double d = e[k];
                 double y0;
                 asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
-                double err = fma(-d, y0, 1.0);
-                double rho = fma(y0, err, y0);
-                sr[k] += rho;
-                if (!UNIT) sw[k] = fma(rho, dr, sw[k]);
+                double err1 = fma(-d, y0, 2.0);               // Newton: rho = y0 (2 - d y0), folded into the running sum
+                if (UNIT) {
+                    sr[k] = fma(y0, err1, sr[k]);
+                } else {
+                    double rho = y0 * err1;
+                    sr[k] += rho;
+                    sw[k] = fma(rho, dr, sw[k]);
+                }
             }
         } else if (!UNIT) {
 #pragma unroll
-            for (int k = 0; k < SCORE_GPW; ++k) sw[k] += (__double2hiint(x[k]) >= 0) ? dr : 0.0;
+            for (int k = 0; k < GPW; ++k) sw[k] += (__double2hiint(x[k]) >= 0) ? dr : 0.0;
         }
         qa = qa_n; qb = qb_n; qc = qc_n; dr = dr_n;
     }
 }
 
 template <bool SOFT>
-__global__ void __launch_bounds__(SCORE_MAX_PAIRS * 64, 1)
+__global__ void __launch_bounds__(SCORE_FWD_PAIRS * 64, 1)
 k_score(const ScoreArgs p) {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -176,8 +201,9 @@ k_score(const ScoreArgs p) {
     const int N = p.N, Np = p.Np, G = p.G, Sp = p.Sp;
     const int N32 = (N + 31) & ~31;                     // Np is a multiple of 128 >= N32
 
-    double* tab = sm;                                   // 2^(j/16): one 128-byte row, conflict-free for any index pattern
-    double* sdr = tab + 16;                             // density ratio of train point i (0 beyond N)
+    __shared__ __align__(128) double tab[16];           // 2^(j/16): one 128-byte row, conflict-free for any index pattern;
+                                                        // static, so that its address is an immediate of the table load
+    double* sdr = sm + 16;                             // density ratio of train point i (0 beyond N)
     double* pbase = sdr + Np + size_t(pair) * (3 * size_t(Np) + 4 * size_t(G) + 64 + 96);
     double* sq = pbase;                                 // [i][3] = (qa_i, qb_i, qc_i): 24-byte stride, conflict-free LDS.64
     double* g_cw = sq + 3 * size_t(Np);                            // phase B stores the hard count here, phase C the conf. weight
@@ -187,7 +213,8 @@ k_score(const ScoreArgs p) {
     double* zt = g_mk + G;                              // zt[t][e] = sum_{b<4} (+-) c_{4t+b}, sign from bit b of e
 
     // ---- once per CTA: candidate-independent tables ------------------------------------------------
-    if (tid < 16) tab[tid] = exp2(double(tid) / 16.0);
+    if (tid < 16) exp_tab_init(tab, tid);
+    const unsigned tab_s = smem_u32(tab);
     for (int i = tid; i < Np; i += blockDim.x) sdr[i] = (i < N) ? p.dr[i] : 0.0;
     __syncthreads();                                    // the only block-wide barrier
 
@@ -284,11 +311,11 @@ k_score(const ScoreArgs p) {
         big = SOFT ? pair_barrier_or(pair, GT, big) : 0;                  // can any sigmoid argument leave the unclamped range?
 
         // ---- phase B: 4 grid points per pass, passes alternate between the two warps ----------------
-        for (int g0 = half * SCORE_GPW; g0 < G; g0 += (SCORE_GPW << wl)) {
-            double bg[SCORE_GPW], sr[SCORE_GPW], sw[SCORE_GPW];
-            unsigned cneg[SCORE_GPW];
+        for (int g0 = half * SCORE_FWD_GPW; g0 < G; g0 += (SCORE_FWD_GPW << wl)) {
+            double bg[SCORE_FWD_GPW], sr[SCORE_FWD_GPW], sw[SCORE_FWD_GPW];
+            unsigned cneg[SCORE_FWD_GPW];
 #pragma unroll
-            for (int k = 0; k < SCORE_GPW; ++k) {
+            for (int k = 0; k < SCORE_FWD_GPW; ++k) {
                 int g = min(g0 + k, G - 1);
                 double eps = p.eps_grid[p.eps_per_candidate ? int64_t(c) * G + g : g];
                 bg[k] = gsd * eps * inv_s;                              // (y_g - mu) / s
@@ -296,15 +323,15 @@ k_score(const ScoreArgs p) {
             }
             if (!bad) {
                 if (p.unit_dr) {       // padded rows carry rho ~ 1e-17 each into sum rho * dr here (dr is not read): negligible
-                    if (big) score_rows<SOFT, true, true>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
-                    else score_rows<SOFT, false, true>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
+                    if (big) score_rows<SOFT, true, true, SCORE_FWD_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
+                    else score_rows<SOFT, false, true, SCORE_FWD_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
                 } else {
-                    if (big) score_rows<SOFT, true, false>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
-                    else score_rows<SOFT, false, false>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
+                    if (big) score_rows<SOFT, true, false, SCORE_FWD_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
+                    else score_rows<SOFT, false, false, SCORE_FWD_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
                 }
             }
 #pragma unroll
-            for (int k = 0; k < SCORE_GPW; ++k) {
+            for (int k = 0; k < SCORE_FWD_GPW; ++k) {
                 int cnt = N32 - warp_sum_int(int(cneg[k]));               // #{i <= N : score_c >= score_i}
                 double tr = SOFT ? warp_sum(sr[k]) : 0.0;
                 double tw = p.unit_dr ? (SOFT ? tr : double(cnt)) : warp_sum(sw[k]);

@@ -46,9 +46,9 @@ inline int score_bwd_groups_for(int Np, int G, int wpg) {
     return int(w > cap ? cap : w);
 }
 
-// rho = sigmoid(x ln2 / 16): the 14-instruction sequence of score_rows
+// rho = sigmoid(x ln2 / 16): the instruction sequence of score_rows, with rho materialised (12 fp64-pipe instructions)
 template <bool CLAMP>
-__device__ __forceinline__ double soft_rho(double x, const double* __restrict__ tab, double kMagic, double kC0, double kC1n,
+__device__ __forceinline__ double soft_rho(double x, unsigned tab_s, double kMagic, double kC0, double kC1n,
                                            double kC2, double kC3n) {
     constexpr int kSatHi = 0x408d9000;
     double xc = x;
@@ -62,20 +62,17 @@ __device__ __forceinline__ double soft_rho(double x, const double* __restrict__ 
     double pl = fma(yn, kC3n, kC2);
     pl = fma(pl, yn, kC1n);
     pl = fma(pl, yn, kC0);
-    int n = __double2loint(t);
-    double ev = tab[n & 15] * pl;
-    double e = __hiloint2double(__double2hiint(ev) + ((n & ~15) << 16), __double2loint(ev));
-    double dd = 1.0 + e, y0;
+    double dd = fma(exp_tab_scaled(tab_s, __double2loint(t)), pl, 1.0), y0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(dd));
-    double err = fma(-dd, y0, 1.0);
-    return fma(y0, err, y0);
+    double err1 = fma(-dd, y0, 2.0);
+    return y0 * err1;
 }
 
 // Pass 2 for SB_RI train points of one thread: E_k = sum_g Gamma_g b_g^k.
 // rec[g] = UNIT ? {b, pq, pq b, pq b^2} : {b, b^2, P, Q}   (P, Q, pq already divided by temp)
 template <bool CLAMP, bool UNIT>
 __device__ __forceinline__ void moment_sweep(const ScoreArgs& p, const double* __restrict__ rec, int G,
-                                             const double* __restrict__ tab, const double (&qa)[SB_RI],
+                                             unsigned tab_s, const double (&qa)[SB_RI],
                                              const double (&qb)[SB_RI], const double (&qc)[SB_RI], const double (&dri)[SB_RI],
                                              double (&E0)[SB_RI], double (&E1)[SB_RI], double (&E2)[SB_RI]) {
     const double kMagic = p.k_magic, kC0 = p.k_c0, kC1n = p.k_c1n, kC2 = p.k_c2, kC3n = p.k_c3n;
@@ -87,7 +84,7 @@ __device__ __forceinline__ void moment_sweep(const ScoreArgs& p, const double* _
 #pragma unroll
         for (int r = 0; r < SB_RI; ++r) {
             double x = fma(fma(qa[r], bg, qb[r]), bg, qc[r]);
-            double rho = soft_rho<CLAMP>(x, tab, kMagic, kC0, kC1n, kC2, kC3n);
+            double rho = soft_rho<CLAMP>(x, tab_s, kMagic, kC0, kC1n, kC2, kC3n);
             double h = fma(-rho, rho, rho);
             if (UNIT) {
                 E0[r] = fma(r01.y, h, E0[r]);
@@ -115,8 +112,8 @@ k_score_bwd(const ScoreBwdArgs q) {
     const int N = p.N, Np = p.Np, G = p.G, Sp = p.Sp, S = p.S;
     const int N32 = (N + 31) & ~31;
 
-    double* tab = sm;
-    double* sdr = tab + 16;
+    __shared__ __align__(128) double tab[16];
+    double* sdr = sm + 16;
     double* pbase = sdr + Np + size_t(grp) * score_bwd_group_doubles(Np, G);
     double* sq = pbase;                                 // [i][3] scaled quadratic coefficients
     double* ga = sq + 3 * size_t(Np);                   // SB_GARR per-grid arrays
@@ -129,7 +126,8 @@ k_score_bwd(const ScoreBwdArgs q) {
     double* part2 = part1 + 16 * 32;                    // [WPG][32]: phase E partial sums
     double* s_utb = part2 + 16 * 32;                    // ut_bar[Sp] of the current candidate
 
-    if (tid < 16) tab[tid] = exp2(double(tid) / 16.0);
+    if (tid < 16) exp_tab_init(tab, tid);
+    const unsigned tab_s = smem_u32(tab);
     for (int i = tid; i < Np; i += blockDim.x) sdr[i] = (i < N) ? p.dr[i] : 0.0;
     __syncthreads();
 
@@ -238,11 +236,11 @@ k_score_bwd(const ScoreBwdArgs q) {
             }
             if (!bad) {
                 if (p.unit_dr) {
-                    if (big) score_rows<SOFT, true, true>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
-                    else score_rows<SOFT, false, true>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
+                    if (big) score_rows<SOFT, true, true, SCORE_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
+                    else score_rows<SOFT, false, true, SCORE_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
                 } else {
-                    if (big) score_rows<SOFT, true, false>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
-                    else score_rows<SOFT, false, false>(p, sq, sdr, tab, lane, N32, bg, sr, sw, cneg);
+                    if (big) score_rows<SOFT, true, false, SCORE_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
+                    else score_rows<SOFT, false, false, SCORE_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
                 }
             }
 #pragma unroll
@@ -407,11 +405,11 @@ k_score_bwd(const ScoreBwdArgs q) {
                     E0[r] = E1[r] = E2[r] = 0.0;
                 }
                 if (p.unit_dr) {
-                    if (big) moment_sweep<true, true>(p, rec, G, tab, qa, qb, qc, dri, E0, E1, E2);
-                    else moment_sweep<false, true>(p, rec, G, tab, qa, qb, qc, dri, E0, E1, E2);
+                    if (big) moment_sweep<true, true>(p, rec, G, tab_s, qa, qb, qc, dri, E0, E1, E2);
+                    else moment_sweep<false, true>(p, rec, G, tab_s, qa, qb, qc, dri, E0, E1, E2);
                 } else {
-                    if (big) moment_sweep<true, false>(p, rec, G, tab, qa, qb, qc, dri, E0, E1, E2);
-                    else moment_sweep<false, false>(p, rec, G, tab, qa, qb, qc, dri, E0, E1, E2);
+                    if (big) moment_sweep<true, false>(p, rec, G, tab_s, qa, qb, qc, dri, E0, E1, E2);
+                    else moment_sweep<false, false>(p, rec, G, tab_s, qa, qb, qc, dri, E0, E1, E2);
                 }
 #pragma unroll
                 for (int r = 0; r < SB_RI; ++r) {
