@@ -127,6 +127,36 @@ __device__ __forceinline__ void exp_tab_init(double* tab, int j) {
     tab[j] = __hiloint2double(__double2hiint(v) - (j << 16), __double2loint(v));
 }
 
+// exp(-t), t in [0, 700], relative error < 1e-15, from the same pattern table (rows.cuh exp_neg_fast with the table
+// entry already carrying the exponent): 12 fp64 instructions instead of the ~35 of libdevice exp.
+__device__ __forceinline__ double exp_neg_pat(double t, unsigned tab_s) {
+    constexpr double kMagic = 6755399441055744.0;            // 1.5 * 2^52
+    constexpr double kL2e16 = 23.083120654223414;            // 16 / ln 2
+    constexpr double kLn2o16Hi = 0.04332169877307024;        // ln2/16, low 21 bits zeroed
+    constexpr double kLn2o16Lo = 1.1926343307941173e-11;     // ln2/16 - hi
+    t = fmin(t, 700.0);
+    double tt = fma(-t, kL2e16, kMagic);
+    int n = __double2loint(tt);                              // round(-t * 16 / ln2) <= 0
+    double nf = tt - kMagic;
+    double y = fma(nf, -kLn2o16Hi, -t);
+    y = fma(nf, -kLn2o16Lo, y);
+    double pp = fma(y, 1.0 / 5040.0, 1.0 / 720.0);
+    pp = fma(pp, y, 1.0 / 120.0);
+    pp = fma(pp, y, 1.0 / 24.0);
+    pp = fma(pp, y, 1.0 / 6.0);
+    pp = fma(pp, y, 0.5);
+    pp = fma(pp, y, 1.0);
+    pp = pp * y;
+    double tj = exp_tab_scaled(tab_s, n);
+    return fma(tj, pp, tj);
+}
+// sigmoid(z) to ~2 ulp (per-grid-point epilogue: conformal mask)
+__device__ __forceinline__ double sigmoid_pat(double z, unsigned tab_s) {
+    double e = exp_neg_pat(fabs(z), tab_s);
+    double r = rcp_full(1.0 + e);
+    return (z >= 0.0) ? r : e * r;
+}
+
 template <bool SOFT, bool CLAMP, bool UNIT, int GPW>
 __device__ __forceinline__ void score_rows(const ScoreArgs& p, const double* __restrict__ sq, const double* __restrict__ sdr,
                                            unsigned tab_s, int lane, int N32,
@@ -236,7 +266,7 @@ k_score(const ScoreArgs p) {
         for (int t = 0; t < p.tiles_n; ++t) vnorm += p.rn_partial[int64_t(c) * p.tiles_n + t];
         const double s_var = p.kappa + p.noise - vnorm;                 // Schur complement (noisy predictive variance)
         const double mu = p.mu[c];
-        const double inv_s = 1.0 / s_var;
+        const double inv_s = rcp_full(s_var);
         const double* Wc = p.W + int64_t(c) * Np;
         double zcc = 0.0;                                               // sum_s z_cs c_s
         for (int s = 0; s < Sp; ++s) {
@@ -256,15 +286,18 @@ k_score(const ScoreArgs p) {
             }
             zt[ptid] = acc;
         }
-        const double var_c = p.noise * (1.0 + (double(Sp) - p.noise * zcc) / (double(Sp) + 1e-6));
+        const double var_c = fma(kvar, double(Sp) - p.noise * zcc, p.noise);   // noise (1 + (Sp - noise zcc)/(Sp + 1e-6))
         int bad = !(var_c > 0.0) || !(s_var > 0.0);
-        const double iv_c = 0.5 / var_c;
-        const double lv_c = -0.5 * log(var_c) - 0.5 * kLog2Pi;
+        const double iv_c = 0.5 * rcp_full(var_c);
+        const double lv_c = -0.5 * log_fast(var_c) - 0.5 * kLog2Pi;
         // score_c(g) = lv_c - iv_c (noise b_g)^2 ;  score_i(g) = lv_i - iv_i (a_i - noise w_i b_g)^2
         const double qa_c = -iv_c * p.noise * p.noise;
         // bmax >= |b_g| for every grid point of this candidate: the sigmoid argument is bounded by (|qa| bmax + |qb|) bmax + |qc|
         const double cscale = p.cscale ? p.cscale[c] : 1.0;
-        const double gsd = sqrt(cscale * s_var);                        // sd of the grid distribution
+        const double gvar = cscale * s_var;
+        const double gsd = sqrt_fast(gvar);                             // sd of the grid distribution
+        const double lp_c = -0.5 * (log_fast(gvar) + kLog2Pi);          // log-density of the grid distribution at its mean
+        const double dens_c = 0.3989422804014327 * rcp_full(gsd);       // exp(lp_c) = 1 / sqrt(2 pi gvar)
         const double bmax = gsd * p.eps_absmax[p.eps_per_candidate ? c : 0] * inv_s;
         int big = 0;
         pair_barrier(pair, GT);                                          // nibble tables visible
@@ -306,7 +339,8 @@ k_score(const ScoreArgs p) {
         }
         const double drc = p.drc ? p.drc[c] : 1.0;
         const double norm = sum_dr + drc;
-        const double omega_c = drc / norm;
+        const double inv_norm = rcp_full(norm);
+        const double omega_c = drc / norm;                               // true division: the hard path compares it with alpha
         bad = pair_barrier_or(pair, GT, bad);                             // tables complete; any non-positive variance?
         big = SOFT ? pair_barrier_or(pair, GT, big) : 0;                  // can any sigmoid argument leave the unclamped range?
 
@@ -330,12 +364,24 @@ k_score(const ScoreArgs p) {
                     else score_rows<SOFT, false, false, SCORE_FWD_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
                 }
             }
+            if (SCORE_FWD_GPW == 4) {   // transposed reductions: lanes 8k..8k+7 end up with the totals of grid point g0 + k
+                int ci[4];
+                double srr[4], swr[4];
 #pragma unroll
-            for (int k = 0; k < SCORE_FWD_GPW; ++k) {
-                int cnt = N32 - warp_sum_int(int(cneg[k]));               // #{i <= N : score_c >= score_i}
-                double tr = SOFT ? warp_sum(sr[k]) : 0.0;
-                double tw = p.unit_dr ? (SOFT ? tr : double(cnt)) : warp_sum(sw[k]);
-                if (lane == 0 && g0 + k < G) { g_cw[g0 + k] = double(cnt); g_nc[g0 + k] = tr; g_mf[g0 + k] = tw; }
+                for (int k = 0; k < 4; ++k) { ci[k] = int(cneg[k]); srr[k] = sr[k]; swr[k] = sw[k]; }
+                const int k = lane >> 3;
+                const int cnt = N32 - warp_sum4(ci, lane);                    // #{i <= N : score_c >= score_i}
+                const double tr = SOFT ? warp_sum4(srr, lane) : 0.0;
+                const double tw = p.unit_dr ? (SOFT ? tr : double(cnt)) : warp_sum4(swr, lane);
+                if ((lane & 7) == 0 && g0 + k < G) { g_cw[g0 + k] = double(cnt); g_nc[g0 + k] = tr; g_mf[g0 + k] = tw; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < SCORE_FWD_GPW; ++k) {
+                    int cnt = N32 - warp_sum_int(int(cneg[k]));
+                    double tr = SOFT ? warp_sum(sr[k]) : 0.0;
+                    double tw = p.unit_dr ? (SOFT ? tr : double(cnt)) : warp_sum(sw[k]);
+                    if (lane == 0 && g0 + k < G) { g_cw[g0 + k] = double(cnt); g_nc[g0 + k] = tr; g_mf[g0 + k] = tw; }
+                }
             }
         }
         pair_barrier(pair, GT);                                           // raw sums of every grid point are in shared memory
@@ -346,9 +392,9 @@ k_score(const ScoreArgs p) {
             double n_g = my_cnt + 1.0;                                  // includes the candidate itself
             double M, rho_self;
             if (SOFT) {
-                double scale = n_g / (my_sr + 0.5);                     // self: sigmoid(0) = 1/2
+                double scale = n_g * rcp_full(my_sr + 0.5);             // self: sigmoid(0) = 1/2
                 rho_self = 0.5 * scale;
-                M = scale * (my_sw + 0.5 * drc) / norm;
+                M = scale * (my_sw + 0.5 * drc) * inv_norm;
             } else {
                 rho_self = 1.0;
                 M = (my_sw + drc) / norm;
@@ -359,15 +405,16 @@ k_score(const ScoreArgs p) {
                 double u = p.u_rand[int64_t(c) * G + g];
                 M -= (u < pr) ? 0.0 : D;
             }
-            double mk = SOFT ? sigmoid_acc((M - p.alpha_lvl) * inv_temp) : ((M > p.alpha_lvl) ? 1.0 : 0.0);
+            double mk = SOFT ? sigmoid_pat((M - p.alpha_lvl) * inv_temp, tab_s) : ((M > p.alpha_lvl) ? 1.0 : 0.0);
             double eps = p.eps_grid[p.eps_per_candidate ? int64_t(c) * G + g : g];
             double yg = mu + gsd * eps;
-            double lp = -0.5 * (eps * eps + log(cscale * s_var) + kLog2Pi);
+            double lp = fma(-0.5 * eps, eps, lp_c);
+            double dens = dens_c * exp_neg_pat(0.5 * eps * eps, tab_s);  // exp(lp)
             double opt = p.optimistic ? ((yg >= mu) ? 1.0 : 0.0) : 1.0;
             double shrink = 1.0 - p.noise * inv_s;
             double rc = p.noise * (gsd * eps * inv_s);
             double scc = fma(-rc * rc, iv_c, lv_c);                     // candidate's own conformal score
-            double cw = mk * opt / fmax(exp(lp), 1e-6), nc = (1.0 - mk) * opt, mf = mu + (yg - mu) * shrink;
+            double cw = mk * opt * rcp_full(fmax(dens, 1e-6)), nc = (1.0 - mk) * opt, mf = mu + (yg - mu) * shrink;
             if (bad) { cw = nc = mf = mk = lp = scc = nan(""); }
             g_mk[g] = mk; g_cw[g] = cw; g_nc[g] = nc; g_mf[g] = mf;
             if (p.grid) p.grid[int64_t(c) * G + g] = yg;

@@ -151,7 +151,7 @@ k_score_bwd(const ScoreBwdArgs q) {
         for (int t = 0; t < p.tiles_n; ++t) vnorm += p.rn_partial[int64_t(c) * p.tiles_n + t];
         const double s_var = p.kappa + noise - vnorm;
         const double mu = p.mu[c];
-        const double inv_s = 1.0 / s_var;
+        const double inv_s = rcp_full(s_var);
         const double* Wc = p.W + int64_t(c) * Np;
         double zcc = 0.0;
         for (int s = 0; s < Sp; ++s) {
@@ -171,13 +171,15 @@ k_score_bwd(const ScoreBwdArgs q) {
             }
             zt[ptid] = acc;
         }
-        const double var_c = noise * (1.0 + (double(Sp) - noise * zcc) / (double(Sp) + 1e-6));
+        const double var_c = fma(kvar, double(Sp) - noise * zcc, noise);
         int bad = !(var_c > 0.0) || !(s_var > 0.0);
-        const double iv_c = 0.5 / var_c;
-        const double lv_c = -0.5 * log(var_c) - 0.5 * kLog2Pi;
+        const double iv_c = 0.5 * rcp_full(var_c);
+        const double lv_c = -0.5 * log_fast(var_c) - 0.5 * kLog2Pi;
         const double qa_c = -iv_c * noise * noise;
         const double cscale = p.cscale ? p.cscale[c] : 1.0;
-        const double gsd = sqrt(cscale * s_var);
+        const double gvar = cscale * s_var;
+        const double gsd = sqrt_fast(gvar);
+        const double dens_c = 0.3989422804014327 * rcp_full(gsd);       // 1 / sqrt(2 pi gvar): grid density at its mean
         const double bmax = gsd * p.eps_absmax[p.eps_per_candidate ? c : 0] * inv_s;
         int big = 0;
         pair_barrier(grp, GT);
@@ -219,6 +221,7 @@ k_score_bwd(const ScoreBwdArgs q) {
         }
         const double drc = p.drc ? p.drc[c] : 1.0;
         const double norm = sum_dr + drc;
+        const double inv_norm = rcp_full(norm);
         const double omega_c = drc / norm;
         bad = pair_barrier_or(grp, GT, bad);
         big = SOFT ? pair_barrier_or(grp, GT, big) : 0;
@@ -243,12 +246,16 @@ k_score_bwd(const ScoreBwdArgs q) {
                     else score_rows<SOFT, false, false, SCORE_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
                 }
             }
+            {   // transposed reductions: lanes 8k..8k+7 end up with the totals of grid point g0 + k
+                static_assert(SCORE_GPW == 4, "warp_sum4");
+                int ci[4];
 #pragma unroll
-            for (int k = 0; k < SCORE_GPW; ++k) {
-                int cnt = N32 - warp_sum_int(int(cneg[k]));
-                double tr = SOFT ? warp_sum(sr[k]) : 0.0;
-                double tw = p.unit_dr ? (SOFT ? tr : double(cnt)) : warp_sum(sw[k]);
-                if (lane == 0 && g0 + k < G) { g_cnt[g0 + k] = double(cnt); g_sr[g0 + k] = tr; g_sw[g0 + k] = tw; }
+                for (int k = 0; k < 4; ++k) ci[k] = int(cneg[k]);
+                const int k = lane >> 3;
+                const int cnt = N32 - warp_sum4(ci, lane);
+                const double tr = SOFT ? warp_sum4(sr, lane) : 0.0;
+                const double tw = p.unit_dr ? (SOFT ? tr : double(cnt)) : warp_sum4(sw, lane);
+                if ((lane & 7) == 0 && g0 + k < G) { g_cnt[g0 + k] = double(cnt); g_sr[g0 + k] = tr; g_sw[g0 + k] = tw; }
             }
         }
         pair_barrier(grp, GT);
@@ -263,9 +270,9 @@ k_score_bwd(const ScoreBwdArgs q) {
             const double n_g = cnt + 1.0;
             double M, rho_self, scale = 0.0;
             if (SOFT) {
-                scale = n_g / (my_sr + 0.5);
+                scale = n_g * rcp_full(my_sr + 0.5);
                 rho_self = 0.5 * scale;
-                M = scale * (my_sw + 0.5 * drc) / norm;
+                M = scale * (my_sw + 0.5 * drc) * inv_norm;
             } else {
                 rho_self = 1.0;
                 M = (my_sw + drc) / norm;
@@ -280,12 +287,12 @@ k_score_bwd(const ScoreBwdArgs q) {
                 M -= keep ? D : 0.0;
                 keep_live = (keep && Dr > 1e-6) ? 1.0 : 0.0;
             }
-            const double mk = SOFT ? sigmoid_acc((M - alpha_lvl) * inv_temp) : ((M > alpha_lvl) ? 1.0 : 0.0);
+            const double mk = SOFT ? sigmoid_pat((M - alpha_lvl) * inv_temp, tab_s) : ((M > alpha_lvl) ? 1.0 : 0.0);
             const double eps = p.eps_grid[p.eps_per_candidate ? int64_t(c) * G + g : g];
             const double dev = gsd * eps;
-            const double lp = -0.5 * (eps * eps + log(cscale * s_var) + kLog2Pi);
+            const double dens = dens_c * exp_neg_pat(0.5 * eps * eps, tab_s);     // exp(log-density of y_g)
             const double opt = p.optimistic ? ((mu + dev >= mu) ? 1.0 : 0.0) : 1.0;
-            const double kap = opt / fmax(exp(lp), 1e-6);
+            const double kap = opt * rcp_full(fmax(dens, 1e-6));
             const double mf = mu + dev * shrink;
             double vs = 0.0, dmf = 0.0, dsd = 0.0;
             double ebar = 0.0;
@@ -357,15 +364,15 @@ k_score_bwd(const ScoreBwdArgs q) {
                         const double mk_bar = fma(ka, vs, scw_bar) * kap - fma(kb, vs, snc_bar) * opt;
                         const double M_bar = mk_bar * mk * (1.0 - mk) * inv_temp;
                         const double scale = g_scale[g], my_sr = g_sr[g], my_sw = g_sw[g], kl = g_kl[g];
-                        const double Mraw = scale * (my_sw + 0.5 * drc) / norm;
-                        double scale_bar = M_bar * (my_sw + 0.5 * drc) / norm;
+                        const double Mraw = scale * (my_sw + 0.5 * drc) * inv_norm;
+                        double scale_bar = M_bar * (my_sw + 0.5 * drc) * inv_norm;
                         const double D_bar = -kl * M_bar;                       // randomised step: M -= max(rho_self omega, 1e-6)
                         scale_bar = fma(D_bar, 0.5 * omega_c, scale_bar);
                         e_om = fma(D_bar, 0.5 * scale, e_om);
-                        P = M_bar * scale / norm;
-                        Q = -scale_bar * scale / (my_sr + 0.5);
+                        P = M_bar * scale * inv_norm;
+                        Q = -scale_bar * scale * rcp_full(my_sr + 0.5);
                         e_drc = fma(0.5, P, e_drc);
-                        e_norm -= M_bar * Mraw / norm;
+                        e_norm -= M_bar * Mraw * inv_norm;
                     }
                     r_b[own] = bgv; r_P[own] = P * inv_temp; r_Q[own] = Q * inv_temp;
                 }
