@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--temp", type=float, default=3e-2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-grad-leg", action="store_true")
     return ap.parse_args()
 
 
@@ -289,6 +290,33 @@ def run_ours(args):
         cfg2 = {"workload": "ackley 8-D cucb, N=1024, 64-point grid, 4096 raw candidates per call (BASELINE configs[1])",
                 "ms_per_call": ms2, "value": 4096 * GRID / (ms2 * 1e-3), "unit": "evals/s"}
 
+    # ---- value + gradient sweep (cbo_conformal_acq_grad_f64: what optimize_acqf's L-BFGS / SGLD steps call), rank 0 only,
+    # outside the timed region; per-kernel-class CUDA-event times from the library
+    cfg_grad = None
+    if rank == 0 and not args.no_grad_leg:
+        bg_ = min(b, 1 << 18)
+        Xg = Xq[:bg_].contiguous()
+        for _ in range(2):
+            ops.conformal_acq(state, Xg, want_grad=True, **kw)
+        torch.cuda.synchronize()
+        lib.cbo_timing_enable(1)
+        msg_, nlg_ = (C.c_double * 8)(), (C.c_int64 * 8)()
+        lib.cbo_timing_collect(msg_, nlg_)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            ops.conformal_acq(state, Xg, want_grad=True, **kw)
+        g1.record()
+        torch.cuda.synchronize()
+        lib.cbo_timing_collect(msg_, nlg_)
+        lib.cbo_timing_enable(0)
+        msg3 = g0.elapsed_time(g1) / 3
+        gnames = ["prep_tables", "kernel_rows", "gemm_pass1_dmma", "gemm_pass2_dmma", "score_rank_integrate",
+                  "score_value_and_reverse", "gemm_reverse_x2_dmma", "kernel_rows_reverse"]
+        cfg_grad = {"workload": f"value + d acq/dX of {bg_} candidates per call (N=1024, d=8, grid=64, cucb), device-resident",
+                    "ms_per_call": msg3, "value": bg_ * GRID / (msg3 * 1e-3), "unit": "evals/s (each with its gradient row)",
+                    "kernels_ms_per_call": {n: msg_[i] / 3 for i, n in enumerate(gnames) if msg_[i] > 0}}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -296,7 +324,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (CUDA-event times from the same timed region) ---------------------------
     names = ["prep_tables", "kernel_rows", "gemm_pass1_dmma", "gemm_pass2_dmma", "score_rank_integrate"]
-    tot_ms = sum(ms)
+    tot_ms = sum(ms[:5])
     cand_total = b * args.steps
     alg_flop = [0.0, b * args.steps * N_TRAIN * (3 * DIM + 12 + 6 * 8 + 8.0), cand_total * GEMM_FLOP_PER_CAND_PASS,
                 cand_total * GEMM_FLOP_PER_CAND_PASS, cand_total * GRID * SCORE_FLOP_PER_EVAL]
@@ -338,7 +366,7 @@ def run_ours(args):
         "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
     }
     if cfg2 is not None:
-        line["other_configs"] = [cfg2]
+        line["other_configs"] = [c for c in (cfg2, cfg_grad) if c is not None]
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

@@ -18,6 +18,7 @@
 #include "nei.cuh"
 #include "score_bwd.cuh"
 #include "rows_bwd.cuh"
+#include "ratio_mma.cuh"
 
 namespace {
 
@@ -315,9 +316,9 @@ int cbo_kernel_rows_f64(const cbo_gp_f64* gp, const double* Xq, int64_t n, doubl
 int cbo_ratio_forward_f64(const cbo_ratio_mlp_f64* r, const double* x, int64_t n, int64_t d, double* out, void* stream) {
     if (!r || !x || !out || n <= 0 || d <= 0) return CBO_ERR_INVALID_ARG;
     if (r->hidden < 1 || r->hidden > cbo::MAX_H) return CBO_ERR_UNSUPPORTED;
-    cbo::k_ratio_mlp<<<(int)((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, (int)n, (int)d, (int)r->hidden, r->W1, r->b1, r->W2, r->b2, r->W3, r->b3, 0.0, out);
-    CBO_CUDA(cudaGetLastError());
+    if (d > cbo::MAX_D) return CBO_ERR_UNSUPPORTED;
+    CBO_CUDA(cbo::launch_ratio_mlp(x, (int)n, (int)d, (int)r->hidden, r->W1, r->b1, r->W2, r->b2, r->W3, r->b3, 0.0, out,
+                                   num_sms(), static_cast<cudaStream_t>(stream)));
     return CBO_OK;
 }
 
@@ -365,8 +366,8 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
     cbo::k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(gp->linv, Np, w.zp, Sp, w.tmp, 0, 1);
     cbo::k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(gp->linv_t, Np, w.tmp, Sp, w.T, 1, 0);
     if (ratio)
-        cbo::k_ratio_mlp<<<(N + 127) / 128, 128, 0, s>>>(gp->X, N, d, (int)ratio->hidden, ratio->W1, ratio->b1,
-                                                          ratio->W2, ratio->b2, ratio->W3, ratio->b3, 1e-6, w.dr_train);
+        CBO_CUDA(cbo::launch_ratio_mlp(gp->X, N, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2, ratio->b2,
+                                       ratio->W3, ratio->b3, 1e-6, w.dr_train, num_sms(), s));
     else
         cbo::k_fill<<<(Np + 255) / 256, 256, 0, s>>>(w.dr_train, Np, 1.0);
     if (p->q == 1) {
@@ -390,9 +391,8 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             CBO_CUDA(cbo::launch_kernel_rows(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->mean,
                                              gp->alpha, w.T, Sp, w.UW, w.mu, w.ut, num_sms(), s));
             if (ratio)
-                cbo::k_ratio_mlp<<<(n + 127) / 128, 128, 0, s>>>(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1,
-                                                                  ratio->W2, ratio->b2, ratio->W3, ratio->b3, 1e-6,
-                                                                  w.drc);
+                CBO_CUDA(cbo::launch_ratio_mlp(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2, ratio->b2,
+                                               ratio->W3, ratio->b3, 1e-6, w.drc, num_sms(), s));
             CBO_CUDA(cudaGetLastError());
         }
         // ---- v = L^-1 u (+ ||v||^2 partials), w = L^-T v ------------------------------------------
@@ -484,9 +484,8 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 CBO_CUDA(cbo::launch_rows_bwd(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->alpha, w.V,
                                               w.UW, w.adj, dX + c0 * d, num_sms(), s));
                 if (ratio)
-                    cbo::k_ratio_mlp_bwd<<<(n + 127) / 128, 128, 0, s>>>(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1,
-                                                                          ratio->W2, ratio->b2, ratio->W3, ratio->b3, w.adj,
-                                                                          dX + c0 * d);
+                    CBO_CUDA(cbo::launch_ratio_mlp_bwd(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2,
+                                                       ratio->b2, ratio->W3, ratio->b3, 1e-6, w.adj, dX + c0 * d, num_sms(), s));
                 CBO_CUDA(cudaGetLastError());
             }
             return CBO_OK;

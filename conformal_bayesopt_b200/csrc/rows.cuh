@@ -3,7 +3,6 @@
 //   k_kernel_rows    U[c, i] = os * (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r),  r = ||(x_c - X_i) / l||
 //                    mu[c]   = mean + sum_i U[c,i] alpha_i                   (helpers.py:119, acquisitions.py:59)
 //                    ut[c,s] = sum_i U[c,i] T[i,s]                           (probe correction, App. A-4)
-//   k_ratio_mlp      RatioEstimator.forward on rows of x                     (ratio_estimation.py:97-99)
 //   k_probe_matvec   out[i, s] = sum_j Mat[i, j] in[j, s]   (T = L^-T (L^-1 z): 2 launches)
 //   k_train_tables   per-train-point tables for the score kernel             (helpers.py:396-405)
 #pragma once
@@ -205,36 +204,6 @@ inline cudaError_t launch_kernel_rows(const double* Xq, int n, const double* XsT
     if (stage) { if (Sp <= 8) CBO_ROWS_DISPATCH(true, 8); else CBO_ROWS_DISPATCH(true, 16); }
     else       { if (Sp <= 8) CBO_ROWS_DISPATCH(false, 8); else CBO_ROWS_DISPATCH(false, 16); }
 #undef CBO_ROWS_DISPATCH
-}
-
-// Thread per point.  w = min(p, 1-1e-6) / max(1-p, 1e-6), p = sigmoid(MLP(x)).  clamp_min(1e-6) of the
-// caller (helpers.py:292-293) is applied when `clamp_min` > 0.
-__global__ void __launch_bounds__(128)
-k_ratio_mlp(const double* __restrict__ x, int n, int d, int H, const double* __restrict__ W1,
-            const double* __restrict__ b1, const double* __restrict__ W2, const double* __restrict__ b2,
-            const double* __restrict__ W3, const double* __restrict__ b3, double clamp_min,
-            double* __restrict__ out) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    double h1[MAX_H];
-#pragma unroll 1
-    for (int j = 0; j < H; ++j) {
-        double a = b1[j];
-        for (int k = 0; k < d; ++k) a = fma(W1[j * d + k], x[int64_t(p) * d + k], a);
-        h1[j] = fmax(a, 0.0);
-    }
-    double logit = b3[0];
-#pragma unroll 1
-    for (int j = 0; j < H; ++j) {
-        double a = b2[j];
-#pragma unroll 8
-        for (int m = 0; m < MAX_H; ++m)
-            if (m < H) a = fma(W2[j * H + m], h1[m], a);
-        logit = fma(W3[j], fmax(a, 0.0), logit);
-    }
-    double pr = sigmoid_acc(logit);
-    double w = fmin(pr, 1.0 - 1e-6) / fmax(1.0 - pr, 1e-6);
-    out[p] = fmax(w, clamp_min);
 }
 
 __global__ void k_fill(double* __restrict__ out, int n, double v) {

@@ -5,7 +5,7 @@
 //             sum_s ut_bar_s T_is = (A^-1 z ut_bar)_i is already folded into w_bar' = w_bar + z ut_bar by k_score_bwd)
 //   x_bar_k = (1/l_k) sum_i u_bar_i k'(r_i) (x_k - X_ik)/l_k / r_i,   k'(r)/r = -(5 os/3)(1 + sqrt5 r) exp(-sqrt5 r)
 //             (Matern-5/2: no singularity at r = 0)
-//   k_ratio_mlp_bwd adds drc_bar * d ratio(x) / d x (RatioEstimator.forward, ratio_estimation.py:97-99, incl. its clamps).
+//   (ratio_mma.cuh adds drc_bar * d ratio(x) / d x afterwards)
 //
 // Same organisation as k_kernel_rows: persistent 16-warp CTAs, XsT / alpha / T^T staged in shared memory, one warp owns
 // ROWS_CPW candidates and sweeps i = lane, lane + 32, ...; the two row reads (A^-1 w_bar and w) are 256-byte coalesced
@@ -138,53 +138,6 @@ inline cudaError_t launch_rows_bwd(const double* Xq, int n, const double* XsT, i
     if (rows_smem_bytes(Np, d, 0, true) <= 220 * 1024)
         return launch_rows_bwd_t<true>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, alpha, Aw, W, adj, dX, num_sms, st);
     return launch_rows_bwd_t<false>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, alpha, Aw, W, adj, dX, num_sms, st);
-}
-
-// dX[p, :] += drc_bar[p] * d ratio(x_p)/dx.  Thread per point; forward recomputed.  The outer clamp_min(1e-6) of the
-// caller (helpers.py:292-293) and the two inner clamps cut the gradient where they are active, as torch's clamp does.
-__global__ void __launch_bounds__(128)
-k_ratio_mlp_bwd(const double* __restrict__ x, int n, int d, int H, const double* __restrict__ W1,
-                const double* __restrict__ b1, const double* __restrict__ W2, const double* __restrict__ b2,
-                const double* __restrict__ W3, const double* __restrict__ b3, const double* __restrict__ adj,
-                double* __restrict__ dX) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    double h1[MAX_H], g1[MAX_H];
-#pragma unroll 1
-    for (int j = 0; j < H; ++j) {
-        double a = b1[j];
-        for (int k = 0; k < d; ++k) a = fma(W1[j * d + k], x[int64_t(p) * d + k], a);
-        h1[j] = fmax(a, 0.0);
-        g1[j] = 0.0;
-    }
-    double logit = b3[0];
-#pragma unroll 1
-    for (int j = 0; j < H; ++j) {
-        double a = b2[j];
-        for (int m = 0; m < H; ++m) a = fma(W2[j * H + m], h1[m], a);
-        logit = fma(W3[j], fmax(a, 0.0), logit);
-    }
-    const double pr = sigmoid_acc(logit);
-    const double num = fmin(pr, 1.0 - 1e-6), den = fmax(1.0 - pr, 1e-6);
-    const double w = num / den;
-    double dw_dp = ((pr <= 1.0 - 1e-6) ? 1.0 / den : 0.0) + ((1.0 - pr >= 1e-6) ? num / (den * den) : 0.0);
-    if (!(w >= 1e-6)) dw_dp = 0.0;
-    const double dlogit = adj[int64_t(p) * ADJ_STRIDE + 2] * dw_dp * pr * (1.0 - pr);
-#pragma unroll 1
-    for (int j = 0; j < H; ++j) {                       // second layer again: pre-activation sign, then W2^T
-        double a = b2[j];
-        for (int m = 0; m < H; ++m) a = fma(W2[j * H + m], h1[m], a);
-        if (a > 0.0) {
-            const double g2 = dlogit * W3[j];
-            for (int m = 0; m < H; ++m) g1[m] = fma(g2, W2[j * H + m], g1[m]);
-        }
-    }
-    for (int k = 0; k < d; ++k) {
-        double acc = 0.0;
-        for (int m = 0; m < H; ++m)
-            if (h1[m] > 0.0) acc = fma(g1[m], W1[m * d + k], acc);
-        dX[int64_t(p) * d + k] += acc;
-    }
 }
 
 }  // namespace cbo
