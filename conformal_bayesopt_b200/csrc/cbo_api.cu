@@ -19,6 +19,7 @@
 #include "score_bwd.cuh"
 #include "rows_bwd.cuh"
 #include "ratio_mma.cuh"
+#include "model_build.cuh"
 
 namespace {
 
@@ -579,6 +580,25 @@ int cbo_cehvi_integrate_f64(int64_t m, int64_t b, int64_t G, int64_t S, const do
     }
     cbo::k_ehvi<<<(int)((b + 7) / 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
     CBO_CUDA(cudaGetLastError());
+    return CBO_OK;
+}
+
+size_t cbo_model_workspace_bytes(int64_t N, int64_t d) {
+    if (N <= 0 || d <= 0) return 0;
+    return cbo::model_build_carve(nullptr, N, d).bytes;
+}
+
+int cbo_model_build_f64(const double* X, const double* y, int64_t N, int64_t d, const double* inv_lengthscale, double mean,
+                        double outputscale, double noise, double* alpha, double* linv, double* linv_t, int32_t* info,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (!X || !y || !inv_lengthscale || !alpha || !linv || !linv_t || !workspace || N <= 0 || d <= 0) return CBO_ERR_INVALID_ARG;
+    if (d > cbo::MAX_D || N > 32768) return CBO_ERR_UNSUPPORTED;
+    if (!(outputscale > 0.0) || !(noise > 0.0)) return CBO_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(workspace) % kAlign) return CBO_ERR_WORKSPACE;
+    cbo::ModelBuildWs w = cbo::model_build_carve(workspace, N, d);
+    if (w.bytes > workspace_bytes) return CBO_ERR_WORKSPACE;
+    CBO_CUDA(cbo::model_build(X, y, (int)N, (int)d, inv_lengthscale, mean, outputscale, noise, alpha, linv, linv_t, info, w,
+                              num_sms(), static_cast<cudaStream_t>(stream)));
     return CBO_OK;
 }
 

@@ -4,11 +4,13 @@ The reference passes a BoTorch `SingleTaskGP` object into its acquisition classe
 (conformalbo/utils.py:382-390, 440-458); the kernels need, per output, the training inputs, the
 hyper-parameters, alpha = A^-1 (y - m) and the explicit inverse Cholesky factor L^-1 of
 A = K + noise I (the same quantity GPyTorch's `root_inv_decomposition` holds for the reference's
-fantasy update, App. B-4).  Built once per model fit with torch.linalg on the device (library
-calls, outside the per-candidate path).
+fantasy update, App. B-4).  Built once per model fit by libcbo's own builder
+(`cbo_model_build_f64`: kernel matrix, blocked Cholesky and triangular inverse on the fp64 tensor
+path); no torch.linalg on the product path, no CPU fallback.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 from dataclasses import dataclass, field
 from typing import Optional
@@ -41,7 +43,6 @@ class GPModelState:
     linv: torch.Tensor = field(repr=False, default=None)      # (Np, Np) lower
     linv_t: torch.Tensor = field(repr=False, default=None)    # (Np, Np) upper
     inv_lengthscale: torch.Tensor = field(repr=False, default=None)
-    L: Optional[torch.Tensor] = field(repr=False, default=None)   # (N, N) Cholesky factor (kept for diagnostics)
 
     @property
     def N(self) -> int:
@@ -60,7 +61,7 @@ class GPModelState:
         return self.X.device
 
     @classmethod
-    def fit_fixed(cls, X, y, mean, lengthscale, outputscale, noise, device=None) -> "GPModelState":
+    def fit_fixed(cls, X, y, mean, lengthscale, outputscale, noise, device=None, check_pd: bool = True) -> "GPModelState":
         """Build the state for FIXED hyper-parameters (hyper-parameter fitting is out of scope, SURVEY §2 #9)."""
         device = torch.device(device) if device is not None else X.device
         X = X.to(device=device, dtype=torch.float64).contiguous()
@@ -70,20 +71,26 @@ class GPModelState:
         if ls.numel() == 1:
             ls = ls.expand(d)
         ls = ls.contiguous()
-        K = matern52(X, X, ls, float(outputscale))
-        K.diagonal().fill_(float(outputscale))
-        A = K + float(noise) * torch.eye(N, dtype=torch.float64, device=device)
-        L = torch.linalg.cholesky(A)
-        alpha = torch.cholesky_solve((y - float(mean)).unsqueeze(-1), L).squeeze(-1)
-        linv = torch.linalg.solve_triangular(L, torch.eye(N, dtype=torch.float64, device=device), upper=False)
+        if not X.is_cuda:
+            raise _lib.CboError("libcbo has no CPU path: the model state is built on a CUDA device")
+        lib = _lib.load()
         Np = (N + 127) // 128 * 128
-        linv_p = torch.zeros(Np, Np, dtype=torch.float64, device=device)
-        linv_p[:N, :N] = torch.tril(linv)
-        alpha_p = torch.zeros(Np, dtype=torch.float64, device=device)
-        alpha_p[:N] = alpha
+        inv_ls = (1.0 / ls).contiguous()
+        alpha = torch.empty(Np, dtype=torch.float64, device=device)
+        linv = torch.empty(Np, Np, dtype=torch.float64, device=device)
+        linv_t = torch.empty(Np, Np, dtype=torch.float64, device=device)
+        info = torch.zeros(1, dtype=torch.int32, device=device)
+        nbytes = lib.cbo_model_workspace_bytes(N, d)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        st = lib.cbo_model_build_f64(X.data_ptr(), y.data_ptr(), N, d, inv_ls.data_ptr(), float(mean), float(outputscale),
+                                     float(noise), alpha.data_ptr(), linv.data_ptr(), linv_t.data_ptr(), info.data_ptr(),
+                                     ws_ptr, nbytes, torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "cbo_model_build_f64")
+        if check_pd and int(info.item()) != 0:        # one host sync per model fit
+            raise _lib.CboError(f"K + noise I is not positive definite (pivot of row {int(info.item()) - 1})")
         return cls(X=X, y=y, mean=float(mean), lengthscale=ls, outputscale=float(outputscale), noise=float(noise),
-                   alpha=alpha_p, linv=linv_p, linv_t=linv_p.t().contiguous(), inv_lengthscale=(1.0 / ls).contiguous(),
-                   L=L)
+                   alpha=alpha, linv=linv, linv_t=linv_t, inv_lengthscale=inv_ls)
 
     @classmethod
     def from_botorch(cls, model, output_index: int = 0) -> "GPModelState":

@@ -72,7 +72,7 @@ class NeiBaseline:
         from .model_state import matern52
         Xb = X_baseline.detach().to(state.device, torch.float64).reshape(-1, state.d).contiguous()
         Kb = matern52(Xb, state.X, state.lengthscale, state.outputscale)
-        Vb = torch.linalg.solve_triangular(state.L, Kb.T, upper=False)
+        Vb = state.linv[:state.N, :state.N] @ Kb.T                         # L^-1 k(X, X_b)
         Kbb = matern52(Xb, Xb, state.lengthscale, state.outputscale)
         Kbb.diagonal().fill_(state.outputscale)
         KbX = torch.zeros(Xb.shape[0], state.Np, dtype=torch.float64, device=state.device)

@@ -171,6 +171,15 @@ int cbo_conf_mask_to_bounds_f64(const double* target_grid, const double* conf_pr
 int cbo_ratio_forward_f64(const cbo_ratio_mlp_f64* ratio, const double* x, int64_t n, int64_t d, double* out,
                           void* stream);
 
+/* Model-state builder (the step before the hot path; conformalbo/utils.py:382-390 refits SingleTaskGP and GPyTorch caches
+ * the same factors): raw training data + fixed hyper-parameters -> alpha (Np), linv and linv_t (Np x Np) of cbo_gp_f64.
+ * Blocked Cholesky and triangular inverse on the fp64 tensor path.  info (device int, may be NULL) receives 0, or
+ * 1 + the first row with a non-positive pivot (A not positive definite; outputs are then NaN).  No host sync. */
+size_t cbo_model_workspace_bytes(int64_t N, int64_t d);
+int cbo_model_build_f64(const double* X, const double* y, int64_t N, int64_t d, const double* inv_lengthscale, double mean,
+                        double outputscale, double noise, double* alpha, double* linv, double* linv_t, int32_t* info,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* Building blocks exported for tests and profiling (same kernels the hot path launches). */
 /* C[m, n] = sum_k A[m, k] * B[n, k] over the K-range implied by tri: 0 full, 1 lower (k < n-tile end),
  * 2 upper (k >= n-tile begin).  A: M x K (lda), B: Nn x K (ldb), C: M x Nn (ldc); K, Nn multiples of 128.

@@ -255,3 +255,35 @@ def test_cnei_matches_oracle(temp, refine):
     with pytest.raises(NotImplementedError):
         qConformalNoisyExpectedImprovement(alpha=0.15, temp=temp, grid_res=G, max_grid_refinements=0, ratio_estimator=None,
                                            model=_state(p, dev), X_baseline=p["X"].to(dev))      # 90 baseline points: prune first
+
+
+@pytest.mark.parametrize("N,d,noise", [(5, 2, 1e-2), (128, 3, 1e-2), (200, 8, 1e-4), (1024, 8, 1e-2), (1100, 6, 1e-3)])
+def test_model_build_matches_torch_linalg(N, d, noise):
+    """cbo_model_build_f64 (blocked Cholesky + triangular inverse on the DMMA GEMM) against torch.linalg on the CPU."""
+    from oracle import gp as ogp
+    dev = _dev()
+    p = make_problem(N, d, seed=N, noise=noise)
+    st = _state(p, dev)
+    gp = ogp.build_state(p["X"], p["y"], p["mean"], p["lengthscale"], p["outputscale"], p["noise"])
+    linv_ref = torch.linalg.solve_triangular(gp.L, torch.eye(N, dtype=torch.float64), upper=False)
+    linv = st.linv.cpu()
+    assert st.Np % 128 == 0 and st.Np >= N
+    scale = linv_ref.abs().max()
+    assert torch.allclose(linv[:N, :N], linv_ref, rtol=1e-8, atol=float(1e-11 * scale))
+    assert torch.equal(st.linv_t.cpu(), linv.T)
+    assert torch.all(linv[N:, :] == 0) and torch.all(linv[:, N:] == 0) and torch.all(torch.triu(linv, 1) == 0)
+    assert torch.allclose(st.alpha.cpu()[:N], gp.alpha, rtol=1e-7, atol=float(1e-10 * gp.alpha.abs().max()))
+    assert torch.all(st.alpha.cpu()[N:] == 0)
+    # A^-1 = L^-T L^-1 reproduces the identity against the kernel matrix
+    A = gp.k(gp.X, gp.X) + noise * torch.eye(N, dtype=torch.float64)
+    resid = (linv[:N, :N].T @ (linv[:N, :N] @ A) - torch.eye(N, dtype=torch.float64)).abs().max()
+    assert resid < 1e-7
+
+
+def test_model_build_reports_non_positive_definite():
+    from conformal_bayesopt_b200 import GPModelState, _lib
+    dev = _dev()
+    X = torch.rand(40, 2, dtype=torch.float64)
+    X[7] = X[3]                                            # duplicate point and (almost) no noise: singular to rounding
+    with pytest.raises(_lib.CboError, match="positive definite|invalid"):
+        GPModelState.fit_fixed(X, torch.zeros(40, dtype=torch.float64), 0.0, 0.5, 1.0, -1e-3, device=dev)
