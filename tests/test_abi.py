@@ -44,6 +44,20 @@ def test_workspace_bytes_and_argument_validation():
     assert lib.cbo_conformal_acq_f64(None, None, ctypes.byref(p), None, 4, None, None, None, None, None, None, 0, 0, None) == 1
     assert lib.cbo_gemm_tn_f64(None, 0, None, 0, None, 0, 1, 128, 128, 0, None, None) == 1
     assert lib.cbo_conf_mask_to_bounds_f64(None, None, 1, 8, 1, None, None, None) == 1
+    # gradient call: extra solve scratch + adjoints; model builder: O(Np^2) scratch
+    gsmall = lib.cbo_workspace_bytes_grad(1024, 8, 4096, ctypes.byref(p), 0)
+    assert gsmall % 256 == 0 and small + 4096 * 1024 * 8 <= gsmall < small + 1.1 * 4096 * 1024 * 8
+    assert lib.cbo_conformal_acq_grad_f64(None, None, ctypes.byref(p), None, 4, None, None, None, None, None, None, None, 0, 0, None) == 1
+    mb = lib.cbo_model_workspace_bytes(1000, 8)
+    assert mb % 256 == 0 and 1024 * 1024 * 8 < mb < 2 * 1024 * 1024 * 8
+    assert lib.cbo_model_build_f64(None, None, 10, 2, None, 0.0, 1.0, 0.1, None, None, None, None, None, 0, None) == 1
+
+
+def test_cpu_model_state_is_refused():
+    import torch
+    from conformal_bayesopt_b200 import GPModelState, _lib
+    with pytest.raises(_lib.CboError):
+        GPModelState.fit_fixed(torch.rand(8, 2, dtype=torch.float64), torch.zeros(8, dtype=torch.float64), 0.0, 0.5, 1.0, 1e-2)
 
 
 def test_ops_refuse_cpu_tensors():
