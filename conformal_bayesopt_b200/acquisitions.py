@@ -6,11 +6,12 @@
 reference (acquisitions.py:80-86, 107-113, 143-149) and the BoTorch bases it mixes in
 (`model`, `beta` / `best_f`, `sampler`, `objective`, `posterior_transform`, `X_pending`).
 
-Joint batches q <= 4 (incl. X_pending) are supported.  `forward` is differentiable in X for q = 1 cUCB / cEI
-(SURVEY.md §8f-1): when X requires grad, ONE call of cbo_conformal_acq_grad_f64 returns the values and d acq / d X, and a
-custom autograd.Function hands the stored Jacobian rows to `backward` (what optimize_acqf_sgld / L-BFGS-B need:
+Joint batches q <= 4 (incl. X_pending) are supported.  `forward` is differentiable in X for cUCB / cEI
+(q = 1 and joint batches up to 4, the reference's default SGLD loop uses q_batch_size = 2): when X
+requires grad, ONE call of cbo_conformal_acq_grad_f64 returns the values and d acq / d X, and a custom
+autograd.Function hands the stored Jacobian blocks to `backward` (what optimize_acqf_sgld / L-BFGS-B need:
 conformalbo/optim/optimize.py:224-235).  Not built yet (raise, never silently fall back): non-identity objectives /
-posterior transforms, gradients for q > 1 or cNEI.
+posterior transforms, gradients for cNEI / cEHVI.
 """
 from __future__ import annotations
 
@@ -99,8 +100,8 @@ class ConformalAcquisition(nn.Module):
         if self.X_pending is not None:                           # concatenate_pending_points
             X = torch.cat([X, self.X_pending.to(X).expand(*X.shape[:-2], -1, -1)], dim=-2)
         lead, (q, d) = X.shape[:-2], X.shape[-2:]
-        if want_grad and (q != 1 or self._kind not in ("ucb", "ei")):
-            raise NotImplementedError("d acq / d X is built for q = 1 cUCB / cEI (SURVEY.md §8f-1); call under torch.no_grad()")
+        if want_grad and self._kind not in ("ucb", "ei"):
+            raise NotImplementedError("d acq / d X is built for cUCB / cEI (SURVEY.md §8f-1); call under torch.no_grad()")
         dev = X.device
         Xf = X.detach().reshape(-1, q, d)
         b, G = Xf.shape[0], self.grid_res
@@ -122,8 +123,9 @@ class ConformalAcquisition(nn.Module):
                                 optimistic=self.optimistic, **self._acq_params())
         self.last_outputs = out
         if want_grad:
-            Xg = X_in.unsqueeze(0) if X_in.ndim == 2 else X_in           # q = 1 and no pending points here
-            acq = _ConformalAcqFn.apply(Xg.reshape(-1, 1, d), out["acq"], out["dacq_dX"].to(X.dtype))
+            Xg = X_in.unsqueeze(0) if X_in.ndim == 2 else X_in
+            q_in = Xg.shape[-2]                                          # pending points (appended last) carry no gradient
+            acq = _ConformalAcqFn.apply(Xg.reshape(-1, q_in, d), out["acq"], out["dacq_dX"][:, :q_in, :].to(X.dtype))
             return acq.reshape(lead).to(X.dtype)
         return out["acq"].reshape(lead).to(X.dtype)
 

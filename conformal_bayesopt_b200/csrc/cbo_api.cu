@@ -20,6 +20,7 @@
 #include "rows_bwd.cuh"
 #include "ratio_mma.cuh"
 #include "model_build.cuh"
+#include "score_q_bwd.cuh"
 
 namespace {
 
@@ -120,7 +121,7 @@ Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, 
     w.stats = c.take<double>(8);
     w.nei_values = c.take<double>(p->kind == CBO_ACQ_NEI ? C * p->num_mc * p->grid_res : 1);
     w.X3 = c.take<double>(grad ? C * Np : 1);
-    w.adj = c.take<double>(grad ? C * cbo::ADJ_STRIDE : 1);
+    w.adj = c.take<double>(grad ? C * (cbo::ADJQ_STRIDE > cbo::ADJ_STRIDE ? cbo::ADJQ_STRIDE : cbo::ADJ_STRIDE) : 1);
     w.bytes = c.off;
     return w;
 }
@@ -240,6 +241,29 @@ cudaError_t launch_score_bwd(const cbo::ScoreBwdArgs& a_in, cudaStream_t st) {
 }
 
 template <int Q, bool SOFT>
+cudaError_t launch_score_q_bwd_t(const cbo::ScoreQBwdArgs& a, cudaStream_t st) {
+    size_t smem = cbo::score_q_bwd_smem_bytes(a.f.base.Np, a.f.base.G, Q);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(cbo::k_score_q_bwd<Q, SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    int grid = a.f.base.n_cand < 2 * num_sms() ? a.f.base.n_cand : 2 * num_sms();
+    cbo::k_score_q_bwd<Q, SOFT><<<grid, cbo::SQ_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_score_q_bwd(const cbo::ScoreQBwdArgs& a, int q, bool soft, cudaStream_t st) {
+    switch (q) {
+        case 2: return soft ? launch_score_q_bwd_t<2, true>(a, st) : launch_score_q_bwd_t<2, false>(a, st);
+        case 3: return soft ? launch_score_q_bwd_t<3, true>(a, st) : launch_score_q_bwd_t<3, false>(a, st);
+        case 4: return soft ? launch_score_q_bwd_t<4, true>(a, st) : launch_score_q_bwd_t<4, false>(a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int Q, bool SOFT>
 cudaError_t launch_score_q_t(const cbo::ScoreQArgs& a, cudaStream_t st) {
     size_t smem = cbo::score_q_smem_bytes(a.base.Np, a.base.G, Q);
     static size_t configured = 0;
@@ -342,9 +366,10 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
     int st = validate(gp, p, b);
     if (st != CBO_OK) return st;
     const bool grad = dX != nullptr;
-    if (grad) {   // the reverse pass is built for the throughput path: q = 1, cUCB / cEI
-        if (p->q != 1 || (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI)) return CBO_ERR_UNSUPPORTED;
-        if (p->grid_res > 2048 || cbo::score_bwd_groups_for((int)gp->Np, (int)p->grid_res, 16) < 1) return CBO_ERR_UNSUPPORTED;
+    if (grad) {   // the reverse pass is built for cUCB / cEI (q = 1: throughput kernels; 2 <= q <= 4: k_score_q_bwd)
+        if (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI) return CBO_ERR_UNSUPPORTED;
+        if (p->q == 1 && (p->grid_res > 2048 || cbo::score_bwd_groups_for((int)gp->Np, (int)p->grid_res, 16) < 1)) return CBO_ERR_UNSUPPORTED;
+        if (p->q > 1 && cbo::score_q_bwd_smem_bytes((int)gp->Np, (int)p->grid_res, (int)p->q) > 227 * 1024) return CBO_ERR_UNSUPPORTED;
     }
     if (!Xq || !eps_grid || !z || !eps_mc || !out || !out->acq || !workspace) return CBO_ERR_INVALID_ARG;
     if (p->randomized && !u_rand) return CBO_ERR_INVALID_ARG;
@@ -467,26 +492,43 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 CBO_CUDA(run_score(fa));
             }
             if (!grad) return CBO_OK;
-            {
+            if (q == 1) {
                 TimeScope ts_(T_SCORE_BWD, s, 1);
                 cbo::ScoreBwdArgs ba;
                 ba.f = fa;
                 ba.wbar = w.V;                                       // v is dead after ||v||^2
                 ba.adj = w.adj;
                 CBO_CUDA(soft_path ? launch_score_bwd<true>(ba, s) : launch_score_bwd<false>(ba, s));
+            } else {
+                TimeScope ts_(T_SCORE_BWD, s, 1);
+                cbo::ScoreQBwdArgs bq;
+                bq.f = aq;
+                bq.f.base = fa;
+                bq.f.post_cov = nullptr;
+                bq.wbar = w.X3;                                      // v (w.V) is read by phase 0: right-hand sides go to the scratch buffer
+                bq.adjq = w.adj;
+                CBO_CUDA(launch_score_q_bwd(bq, q, soft_path, s));
             }
+            double* rhs = (q == 1) ? w.V : w.X3;                    // right-hand sides w_bar'
+            double* sol = (q == 1) ? w.X3 : w.V;                    // scratch of the two-pass solve
             {
                 TimeScope ts_(T_GEMM_BWD, s, 2);
-                CBO_CUDA(cbo::launch_gemm_tn(w.V, Np, gp->linv, Np, w.X3, Np, n, Np, Np, cbo::TRI_LOWER, nullptr, s, num_sms()));
-                CBO_CUDA(cbo::launch_gemm_tn(w.X3, Np, gp->linv_t, Np, w.V, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms()));
+                CBO_CUDA(cbo::launch_gemm_tn(rhs, Np, gp->linv, Np, sol, Np, n, Np, Np, cbo::TRI_LOWER, nullptr, s, num_sms()));
+                CBO_CUDA(cbo::launch_gemm_tn(sol, Np, gp->linv_t, Np, rhs, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms()));
             }
             {
                 TimeScope ts_(T_ROWS_BWD, s, ratio ? 2 : 1);
-                CBO_CUDA(cbo::launch_rows_bwd(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->alpha, w.V,
-                                              w.UW, w.adj, dX + c0 * d, num_sms(), s));
+                if (q == 1)
+                    CBO_CUDA(cbo::launch_rows_bwd(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->alpha, rhs,
+                                                  w.UW, w.adj, dX + c0 * q * d, num_sms(), s));
+                else
+                    cbo::k_rows_bwd_q<<<(n + 3) / 4, 128, 0, s>>>(Xc, n, q, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale,
+                                                                 gp->alpha, rhs, w.UW, w.adj, dX + c0 * q * d);
                 if (ratio)
                     CBO_CUDA(cbo::launch_ratio_mlp_bwd(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2,
-                                                       ratio->b2, ratio->W3, ratio->b3, 1e-6, w.adj, dX + c0 * d, num_sms(), s));
+                                                       ratio->b2, ratio->W3, ratio->b3, 1e-6, w.adj,
+                                                       q == 1 ? cbo::ADJ_STRIDE : cbo::ADJQ_STRIDE, q == 1 ? 2 : 1,
+                                                       dX + c0 * q * d, num_sms(), s));
                 CBO_CUDA(cudaGetLastError());
             }
             return CBO_OK;

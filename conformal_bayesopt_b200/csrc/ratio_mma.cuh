@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(RM_WARPS * 32)
 k_ratio_mlp_mma_bwd(const double* __restrict__ x, int n, int d, int H, const double* __restrict__ W1,
                     const double* __restrict__ b1, const double* __restrict__ W2, const double* __restrict__ b2,
                     const double* __restrict__ W3, const double* __restrict__ b3, double clamp_min,
-                    const double* __restrict__ adj, double* __restrict__ dX) {
+                    const double* __restrict__ adj, int adj_stride, int adj_off, double* __restrict__ dX) {
     extern __shared__ __align__(16) double rsm[];
     const RatioMmaSmem s = ratio_mma_stage(rsm, d, H, W1, b1, W2, b2, W3, true);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
@@ -185,7 +185,7 @@ k_ratio_mlp_mma_bwd(const double* __restrict__ x, int n, int d, int H, const dou
         double dwl;
         ratio_from_logit(part + bias3, clamp_min, &dwl);
         const int p = min(p0 + r, n - 1);
-        const double dlogit = adj[int64_t(p) * ADJ_STRIDE + 2] * dwl;
+        const double dlogit = adj[int64_t(p) * adj_stride + adj_off] * dwl;
 #pragma unroll
         for (int nt = 0; nt < RM_NT; ++nt) { g2[nt][0] *= dlogit; g2[nt][1] *= dlogit; }
         // G1 = (g2 W2) [H1 > 0], overwriting h1
@@ -239,7 +239,8 @@ inline cudaError_t launch_ratio_mlp(const double* x, int n, int d, int H, const 
 
 inline cudaError_t launch_ratio_mlp_bwd(const double* x, int n, int d, int H, const double* W1, const double* b1,
                                         const double* W2, const double* b2, const double* W3, const double* b3,
-                                        double clamp_min, const double* adj, double* dX, int num_sms, cudaStream_t st) {
+                                        double clamp_min, const double* adj, int adj_stride, int adj_off, double* dX,
+                                        int num_sms, cudaStream_t st) {
     const size_t smem = ratio_mma_smem_bytes(d, true);
     static size_t configured = 0;
     if (smem > configured) {
@@ -249,7 +250,7 @@ inline cudaError_t launch_ratio_mlp_bwd(const double* x, int n, int d, int H, co
     }
     int grid = ((n + 7) / 8 + RM_WARPS - 1) / RM_WARPS;
     if (grid > 2 * num_sms) grid = 2 * num_sms;
-    k_ratio_mlp_mma_bwd<<<grid, RM_WARPS * 32, smem, st>>>(x, n, d, H, W1, b1, W2, b2, W3, b3, clamp_min, adj, dX);
+    k_ratio_mlp_mma_bwd<<<grid, RM_WARPS * 32, smem, st>>>(x, n, d, H, W1, b1, W2, b2, W3, b3, clamp_min, adj, adj_stride, adj_off, dX);
     return cudaGetLastError();
 }
 

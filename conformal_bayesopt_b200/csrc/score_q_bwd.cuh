@@ -1,0 +1,774 @@
+// score_q_bwd.cuh -- value AND reverse pass for joint batches 2 <= q <= 4 (cUCB / cEI): what the reference's SGLD loop
+// differentiates with its default q_batch_size = 2 (conformalbo/optim/optimize.py:224-235, hydra_config/black_box_opt.yaml:10).
+// oracle/analytic_grad_q.py is the line-by-line CPU restatement (checked against torch.autograd to 1e-15).
+//
+// One CTA (128 threads) per candidate batch, as k_score_q (latency regime: batch_limit x restarts candidates per call):
+//   phases 0, A, B+C, D   as k_score_q, keeping the per-(grid point, column) sums
+//   phase E  (thread per grid point)  d acq/d values, d acq/d mask -> P_gj, Q_gj (d acq / d rho_ijg = P_gj dr_i + Q_gj),
+//            refit-mean / refit-factor / shrinkage adjoints, candidate-vs-candidate rank terms
+//   pass 2   (thread per train point, loop over the grid)  Gam_ijg = (P_gj dr_i + Q_gj) rho (1 - rho) / temp; per train
+//            point the moments m0, mrr, mr, mrd_k of Gam_ig = sum_j Gam_ijg against rp = sqrt(iv_i) r_ig; per column the totals
+//            of Gam_ijg {1, B_j^2, B_j, B_j dev_k}
+//   final    (one thread) q x q algebra: Cholesky reverse of the refit factor, S^-1 adjoint, S_bar = -S^-T Sinv_bar S^-T;
+//            per row: mu_bar, drc_bar, Ssym row, ut_bar;  w_bar rows (right-hand sides of the A^-1 solve) get z ut_bar folded in.
+#pragma once
+#include "score_q.cuh"
+
+namespace cbo {
+
+constexpr int ADJQ_STRIDE = 8 + MAX_SP;        // per row: {mu_bar, drc_bar, Ssym[0..3], -, -, ut_bar[Sp]}
+constexpr int SQB_GJ = 12;                     // per-(grid point, column) arrays
+constexpr int SQB_NT = 4 * MAX_Q + 4 * MAX_Q * MAX_Q + 4 * MAX_Q;   // totals: see enum below
+
+struct ScoreQBwdArgs {
+    ScoreQArgs f;
+    double* wbar;          // rows x Np
+    double* adjq;          // rows x ADJQ_STRIDE
+};
+
+__host__ __device__ inline size_t score_q_bwd_smem_bytes(int Np, int G, int Q) {
+    return sizeof(double) * (size_t(4 + Q) * Np + size_t(SQB_GJ * Q + 1) * G + 1024 + 4 * SQB_NT + SQB_NT);
+}
+
+// totals layout (doubles): per column / per pair accumulators reduced over the block
+struct SqbIdx {
+    static __host__ __device__ constexpr int drc(int j) { return j; }                               // sum_g 0.5 P
+    static __host__ __device__ constexpr int nrm(int j) { return MAX_Q + j; }                       // norm_bar partial
+    static __host__ __device__ constexpr int om(int j) { return 2 * MAX_Q + j; }                    // omega_bar partial
+    static __host__ __device__ constexpr int mu(int j) { return 3 * MAX_Q + j; }                    // sum_g meanf_bar_gj
+    static __host__ __device__ constexpr int lf(int j, int k) { return 4 * MAX_Q + j * MAX_Q + k; } // Lf_bar
+    static __host__ __device__ constexpr int shr(int j, int k) { return 4 * MAX_Q + MAX_Q * MAX_Q + j * MAX_Q + k; }
+    static __host__ __device__ constexpr int t3(int j, int k) { return 4 * MAX_Q + 2 * MAX_Q * MAX_Q + j * MAX_Q + k; }
+    static __host__ __device__ constexpr int sinv(int j, int k) { return 4 * MAX_Q + 3 * MAX_Q * MAX_Q + j * MAX_Q + k; }
+    static __host__ __device__ constexpr int t1(int j) { return 4 * MAX_Q + 4 * MAX_Q * MAX_Q + j; }
+    static __host__ __device__ constexpr int t2(int j) { return 5 * MAX_Q + 4 * MAX_Q * MAX_Q + j; }
+    static __host__ __device__ constexpr int t4(int j) { return 6 * MAX_Q + 4 * MAX_Q * MAX_Q + j; }
+    static __host__ __device__ constexpr int bsum(int j) { return 7 * MAX_Q + 4 * MAX_Q * MAX_Q + j; }
+};
+static_assert(SqbIdx::bsum(MAX_Q - 1) < SQB_NT, "totals layout");
+
+// add this thread's value to totals slot `slot` (deterministic: warp tree, then fixed-order sum of the 4 warp partials)
+struct SqbReducer {
+    double* wred;          // [SQ_WARPS][SQB_NT]
+    double* tot;           // [SQB_NT]
+    int tid;
+    __device__ __forceinline__ void put(int slot, double v) const {
+        v = warp_sum(v);
+        if ((tid & 31) == 0) wred[(tid >> 5) * SQB_NT + slot] = v;
+    }
+    __device__ __forceinline__ void zero_partials() const {
+        for (int e = tid; e < SQ_WARPS * SQB_NT; e += SQ_THREADS) wred[e] = 0.0;
+    }
+    __device__ __forceinline__ void commit() const {          // call between two __syncthreads()
+        for (int e = tid; e < SQB_NT; e += SQ_THREADS) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < SQ_WARPS; ++w) s += wred[w * SQB_NT + e];
+            tot[e] += s;
+        }
+    }
+};
+
+template <int Q, bool SOFT>
+__global__ void __launch_bounds__(SQ_THREADS)
+k_score_q_bwd(const ScoreQBwdArgs qb) {
+    const ScoreQArgs& pq = qb.f;
+    const ScoreArgs& p = pq.base;
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = p.N, Np = p.Np, G = p.G, Sp = p.Sp, S = p.S;
+    double* s_lv = sm;                       // Np
+    double* s_ap = s_lv + Np;                // Np
+    double* s_dr = s_ap + Np;                // Np
+    double* s_siv = s_dr + Np;               // Np   sqrt(iv_i)
+    double* s_wp = s_siv + Np;               // Q x Np   (pass 2 overwrites row j, entry i with zdot_bar_ji)
+    double* gj = s_wp + size_t(Q) * Np;      // SQB_GJ arrays of G x Q
+    const size_t GQ = size_t(G) * Q;
+    double* g_mask = gj;             double* g_opt = gj + GQ;        double* g_dev = gj + 2 * GQ;    double* g_Bg = gj + 3 * GQ;
+    double* g_thr = gj + 4 * GQ;     double* g_sr = gj + 5 * GQ;     double* g_sw = gj + 6 * GQ;     double* g_scale = gj + 7 * GQ;
+    double* g_P = gj + 8 * GQ;       double* g_Q = gj + 9 * GQ;      double* g_kl = gj + 10 * GQ;    double* g_Mraw = gj + 11 * GQ;
+    double* g_kd = gj + size_t(SQB_GJ) * GQ; // G   1 / max(exp(logp), 1e-6)
+    double* sc = g_kd + G;                   // scratch: 1024 doubles
+    double* red = sc;                        // [4]
+    double* s_S = sc + 8;                    // Q x Q
+    double* s_Sinv = s_S + 16;
+    double* s_Lc = s_Sinv + 16;
+    double* s_Lf = s_Lc + 16;
+    double* s_C = s_Lf + 16;                 // Q x MAX_SP
+    double* s_R = s_C + MAX_Q * MAX_SP;      // Q x MAX_SP   z_c - U^T T
+    double* s_misc = s_R + MAX_Q * MAX_SP;   // var_c[Q], logdet, bad
+    double* s_A = s_misc + 16;               // [MAX_S][MAX_Q]  A_sj
+    double* s_B = s_A + MAX_S * MAX_Q;       // [MAX_S][MAX_Q]
+    double* s_kap = s_B + MAX_S * MAX_Q;     // [MAX_S][MAX_Q]  d acq / d res_sj
+    double* s_col = s_kap + MAX_S * MAX_Q;   // [4][MAX_Q]: dcw, dnc, ood, live flags packed (cw live + 2 nc live)
+    double* s_Cbar = s_col + 4 * MAX_Q;      // Q x MAX_SP
+    double* s_utb = s_Cbar + MAX_Q * MAX_SP; // Q x MAX_SP
+    double* wred = sc + 1024;                // [4][SQB_NT]
+    double* tot = wred + 4 * SQB_NT;         // [SQB_NT]
+    const SqbReducer R{wred, tot, tid};
+    const double noise = p.noise;
+    const double kvar = noise / (double(Sp) + 1e-6);
+    const double inv_temp = SOFT ? 1.0 / p.temp : 0.0;
+    const double sum_dr = p.sum_dr[0];
+    const double alpha_lvl = p.alpha_lvl;
+
+    for (int i = tid; i < N; i += SQ_THREADS) s_dr[i] = p.dr[i];
+
+    for (int c = blockIdx.x; c < p.n_cand; c += gridDim.x) {
+        const int r0 = c * Q;
+        for (int e = tid; e < SQB_NT; e += SQ_THREADS) tot[e] = 0.0;
+        // ---- phase 0 (as k_score_q) -----------------------------------------------------------------------------------
+        double gsum[Q][Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+#pragma unroll
+            for (int k = 0; k < Q; ++k) gsum[j][k] = 0.0;
+        for (int i = tid; i < N; i += SQ_THREADS) {
+            double v[Q];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) v[j] = pq.V[int64_t(r0 + j) * Np + i];
+#pragma unroll
+            for (int j = 0; j < Q; ++j)
+#pragma unroll
+                for (int k = 0; k < Q; ++k)
+                    if (k <= j) gsum[j][k] = fma(v[j], v[k], gsum[j][k]);
+        }
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+#pragma unroll
+            for (int k = 0; k < Q; ++k)
+                if (k <= j) gsum[j][k] = block_sum(gsum[j][k], red, tid);
+        if (tid == 0) {
+            double Sm[Q][Q], Ls[Q][Q], Si[Q][Q];
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k <= j; ++k) {
+                    double r2 = 0.0;
+                    for (int e = 0; e < pq.d; ++e) {
+                        double df = (pq.Xq[(int64_t(r0 + j)) * pq.d + e] - pq.Xq[(int64_t(r0 + k)) * pq.d + e]) * pq.inv_ls[e];
+                        r2 = fma(df, df, r2);
+                    }
+                    double r = sqrt(fmax(r2, 1e-30));
+                    double kk = p.kappa * (1.0 + kSqrt5 * r + (5.0 / 3.0) * r * r) * exp(-kSqrt5 * r);
+                    double v = kk - gsum[j][k] + ((j == k) ? noise : 0.0);
+                    Sm[j][k] = v; Sm[k][j] = v;
+                }
+            bool ok = chol_lower<Q>(Sm, Ls);
+            inv_from_chol<Q>(Ls, Si);
+            double Cov[Q][Q], Lc[Q][Q];
+            for (int j = 0; j < Q; ++j) {
+                double rs = p.cscale ? p.cscale[r0 + j] : 1.0;
+                for (int k = 0; k < Q; ++k) Cov[j][k] = rs * Sm[j][k];
+            }
+            ok = chol_lower<Q>(Cov, Lc) && ok;
+            double logdet = 0.0;
+            for (int j = 0; j < Q; ++j) logdet += 2.0 * log(Lc[j][j]);
+            double Cf[Q][Q], Lf[Q][Q];
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k < Q; ++k)
+                    Cf[j][k] = noise * (((j == k) ? 1.0 : 0.0) - noise * 0.5 * (Si[j][k] + Si[k][j]));
+            ok = chol_lower<Q>(Cf, Lf) && ok;
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k < Q; ++k) {
+                    s_S[j * Q + k] = Sm[j][k]; s_Sinv[j * Q + k] = Si[j][k];
+                    s_Lc[j * Q + k] = Lc[j][k]; s_Lf[j * Q + k] = Lf[j][k];
+                }
+            for (int j = 0; j < Q; ++j)
+                for (int s = 0; s < Sp; ++s) s_R[j * MAX_SP + s] = p.z_cand[j * Sp + s] - p.ut[int64_t(r0 + j) * Sp + s];
+            for (int j = 0; j < Q; ++j) {
+                double zc_c = 0.0;
+                for (int s = 0; s < Sp; ++s) {
+                    double cv = 0.0;
+                    for (int k = 0; k < Q; ++k) cv += Si[j][k] * s_R[k * MAX_SP + s];
+                    s_C[j * MAX_SP + s] = cv;
+                    zc_c = fma(p.z_cand[j * Sp + s], cv, zc_c);
+                }
+                double vc = noise * (1.0 + (double(Sp) - noise * zc_c) / (double(Sp) + 1e-6));
+                s_misc[j] = vc;
+                ok = ok && (vc > 0.0);
+            }
+            s_misc[Q] = logdet;
+            s_misc[Q + 1] = ok ? 0.0 : 1.0;
+        }
+        __syncthreads();
+        int bad = s_misc[Q + 1] != 0.0;
+
+        // ---- phase A: per-train-point tables ---------------------------------------------------------------------------
+        for (int i = tid; i < N; i += SQ_THREADS) {
+            uint32_t bits = p.zb[i];
+            double w[Q], acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                w[j] = p.W[int64_t(r0 + j) * Np + i];
+                double zdot = 0.0;
+                for (int s = 0; s < Sp; ++s) zdot += ((bits >> s) & 1u) ? s_C[j * MAX_SP + s] : -s_C[j * MAX_SP + s];
+                acc = fma(w[j], zdot, acc);
+            }
+            double var = noise * fma(kvar, acc, p.h0[i]);
+            bad |= !(var > 0.0);
+            double iv = 0.5 / var;
+            double siv = sqrt(iv);
+            s_lv[i] = -0.5 * log(var) - 0.5 * kLog2Pi;
+            s_ap[i] = p.a[i] * siv;
+            s_siv[i] = siv;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) s_wp[size_t(j) * Np + i] = noise * w[j] * siv;
+        }
+        bad = __syncthreads_or(bad);
+
+        double mu[Q], drc[Q], norm[Q], omega[Q], ivc[Q], lvc[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            mu[j] = p.mu[r0 + j];
+            drc[j] = p.drc ? p.drc[r0 + j] : 1.0;
+            norm[j] = sum_dr + drc[j];
+            omega[j] = drc[j] / norm[j];
+            ivc[j] = 0.5 / s_misc[j];
+            lvc[j] = -0.5 * log(s_misc[j]) - 0.5 * kLog2Pi;
+        }
+        const double logdet = s_misc[Q];
+
+        // ---- phase B + C: warp per grid point (forward) -------------------------------------------------------------------
+        for (int g = warp; g < G; g += SQ_WARPS) {
+            double eps[Q], dev[Q], Bg[Q], thr[Q];
+            double e2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                eps[j] = p.eps_grid[(p.eps_per_candidate ? int64_t(c) * G + g : g) * Q + j];
+                e2 = fma(eps[j], eps[j], e2);
+            }
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < Q; ++k)
+                    if (k <= j) s = fma(s_Lc[j * Q + k], eps[k], s);
+                dev[j] = s;
+            }
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < Q; ++k) s = fma(s_Sinv[j * Q + k], dev[k], s);
+                Bg[j] = s;
+                double rc = noise * s;
+                thr[j] = fma(-rc * rc, ivc[j], lvc[j]);
+            }
+            double sr[Q], sw[Q];
+            int cnt[Q];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) { sr[j] = 0.0; sw[j] = 0.0; cnt[j] = 0; }
+            if (!bad) {
+                for (int i = lane; i < N; i += 32) {
+                    double rp = s_ap[i];
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) rp = fma(-s_wp[size_t(j) * Np + i], Bg[j], rp);
+                    double sci = fma(-rp, rp, s_lv[i]);
+                    double dr = s_dr[i];
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) {
+                        double dd = thr[j] - sci;
+                        bool ge = dd >= 0.0;
+                        cnt[j] += ge ? 1 : 0;
+                        if (SOFT) {
+                            double rho = sigmoid_acc(fmin(fmax(dd * inv_temp, -745.0), 745.0));
+                            sr[j] += rho;
+                            sw[j] = fma(rho, dr, sw[j]);
+                        } else {
+                            sw[j] += ge ? dr : 0.0;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                cnt[j] = warp_sum_int(cnt[j]);
+                sw[j] = warp_sum(sw[j]);
+                if (SOFT) sr[j] = warp_sum(sr[j]);
+            }
+            if (lane == 0) {
+                double lp = -0.5 * (e2 + logdet + double(Q) * kLog2Pi);
+                g_kd[g] = 1.0 / fmax(exp(lp), 1e-6);
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    int n_g = cnt[j];
+                    double srj = sr[j];
+#pragma unroll
+                    for (int k = 0; k < Q; ++k) {
+                        double dd = thr[j] - thr[k];
+                        n_g += (dd >= 0.0) ? 1 : 0;
+                        if (SOFT) srj += sigmoid_acc(fmin(fmax(dd * inv_temp, -745.0), 745.0));
+                    }
+                    double M, rho_self, scale = 0.0;
+                    if (SOFT) {
+                        scale = double(n_g) / srj;
+                        rho_self = 0.5 * scale;
+                        M = scale * (sw[j] + 0.5 * drc[j]) / norm[j];
+                    } else {
+                        rho_self = 1.0;
+                        M = (sw[j] + drc[j]) / norm[j];
+                    }
+                    const double Mraw = M;
+                    double kl = 0.0;
+                    if (p.randomized) {
+                        double Dr = rho_self * omega[j];
+                        double D = (j == Q - 1) ? fmax(Dr, 1e-6) : 1e-6;
+                        double pr = fmin(fmax((M - alpha_lvl) / D, 0.0), 1.0);
+                        double u = p.u_rand[(int64_t(c) * G + g) * Q + j];
+                        bool keep = !(u < pr);
+                        M -= keep ? D : 0.0;
+                        kl = (keep && j == Q - 1 && Dr > 1e-6) ? 1.0 : 0.0;
+                    }
+                    double mk = SOFT ? sigmoid_acc((M - alpha_lvl) * inv_temp) : ((M > alpha_lvl) ? 1.0 : 0.0);
+                    double yg = mu[j] + dev[j];
+                    const int o = g * Q + j;
+                    g_mask[o] = mk;
+                    g_opt[o] = p.optimistic ? ((yg >= mu[j]) ? 1.0 : 0.0) : 1.0;
+                    g_dev[o] = dev[j]; g_Bg[o] = Bg[j]; g_thr[o] = thr[j]; g_sr[o] = srj; g_sw[o] = sw[j];
+                    g_scale[o] = scale; g_kl[o] = kl; g_Mraw[o] = Mraw; g_P[o] = 0.0; g_Q[o] = 0.0;
+                }
+            }
+        }
+        __syncthreads();
+
+        // sample value of (s, g, j): f = refit mean + (L_f eps)_j; returns val, d val / d f pieces
+        auto sample_val = [&](int s, int g, int j, double& val, double& dv_f, double& sgn) {
+            double mf = mu[j], fs = 0.0, ms = 0.0;
+#pragma unroll
+            for (int k = 0; k < Q; ++k) {
+                double shr = ((j == k) ? 1.0 : 0.0) - noise * s_Sinv[j * Q + k];
+                mf = fma(shr, g_dev[g * Q + k], mf);
+                if (k <= j) {
+                    fs = fma(s_Lf[j * Q + k], p.eps_mc[(int64_t(s) * G + g) * Q + k], fs);
+                    if (p.kind == 0 && S > 1) {
+                        double em = 0.0;
+                        for (int s2 = 0; s2 < S; ++s2) em += p.eps_mc[(int64_t(s2) * G + g) * Q + k];
+                        ms = fma(s_Lf[j * Q + k], em / double(S), ms);
+                    }
+                }
+            }
+            double f = mf + fs;
+            sgn = 0.0; dv_f = 1.0;
+            if (p.kind == 0) {
+                if (S > 1) { double m = mf + ms; double dm = f - m; sgn = (dm > 0.0) ? 1.0 : (dm < 0.0 ? -1.0 : 0.0); val = m + p.beta_prime * fabs(dm); }
+                else val = f;
+            } else {
+                double xx = f - p.best_f;
+                if (p.temp > 0.0) { double xt = xx / p.temp; val = p.temp * (fmax(xt, 0.0) + log1p(exp(-fabs(xt)))); dv_f = sigmoid_acc(xt); }
+                else { val = fmax(xx, 0.0); dv_f = (xx > 0.0) ? 1.0 : 0.0; }
+            }
+        };
+
+        // ---- phase D: forward integration per column; arg-max over q per MC sample ----------------------------------------
+        double ood[Q], scw[Q], snc[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            ood[j] = SOFT ? sigmoid_acc((omega[j] - alpha_lvl) * inv_temp) : ((omega[j] >= alpha_lvl) ? 1.0 : 0.0);
+            double a1 = 0.0, a2 = 0.0;
+            for (int g = tid; g < G; g += SQ_THREADS) {
+                double mk = g_mask[g * Q + j], op = g_opt[g * Q + j];
+                a1 += mk * op * g_kd[g];
+                a2 += (1.0 - mk) * op;
+            }
+            scw[j] = block_sum(a1, red, tid);
+            snc[j] = block_sum(a2, red, tid);
+        }
+        double tot_acq = 0.0;
+        for (int s = 0; s < S; ++s) {
+            double best = -INFINITY;
+            int jbest = 0;
+            bool isnan_any = false;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                double A = 0.0, B = 0.0;
+                for (int g = tid; g < G; g += SQ_THREADS) {
+                    double val, dv, sg;
+                    sample_val(s, g, j, val, dv, sg);
+                    double mk = g_mask[g * Q + j], op = g_opt[g * Q + j];
+                    A = fma(mk * op * g_kd[g], val, A);
+                    B = fma((1.0 - mk) * op, val, B);
+                }
+                A = block_sum(A, red, tid);
+                B = block_sum(B, red, tid);
+                double r = (1.0 - ood[j]) * ((1.0 - alpha_lvl) * A / fmax(scw[j], 1e-6) + alpha_lvl * B / fmax(snc[j], 1e-6));
+                isnan_any = isnan_any || (r != r);
+                if (r > best) { best = r; jbest = j; }
+                if (tid == 0) { s_A[s * MAX_Q + j] = A; s_B[s * MAX_Q + j] = B; }
+            }
+            tot_acq += isnan_any ? nan("") : best;
+            if (tid == 0)
+                for (int j = 0; j < Q; ++j) s_kap[s * MAX_Q + j] = (j == jbest) ? 1.0 / double(S) : 0.0;
+        }
+        __syncthreads();
+
+        // ---- phase E: thread per grid point (reverse) ------------------------------------------------------------------------
+        R.zero_partials();
+        __syncthreads();
+        {
+            double a_drc[Q], a_nrm[Q], a_om[Q], a_mu[Q], a_lf[Q][Q], a_shr[Q][Q], a_t1[Q], a_t2[Q], a_t4[Q], a_t3[Q][Q];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                a_drc[j] = a_nrm[j] = a_om[j] = a_mu[j] = a_t1[j] = a_t2[j] = a_t4[j] = 0.0;
+#pragma unroll
+                for (int k = 0; k < Q; ++k) a_lf[j][k] = a_shr[j][k] = a_t3[j][k] = 0.0;
+            }
+            if (!bad) {
+                for (int g = tid; g < G; g += SQ_THREADS) {
+                    double thr_bar[Q];
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) thr_bar[j] = 0.0;
+                    const double kd = g_kd[g];
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) {
+                        const int o = g * Q + j;
+                        const double mk = g_mask[o], op = g_opt[o];
+                        const double cw = mk * op * kd, nc = (1.0 - mk) * op;
+                        const double dcw = fmax(scw[j], 1e-6), dnc = fmax(snc[j], 1e-6);
+                        const double c1 = (1.0 - ood[j]) * (1.0 - alpha_lvl), c2 = (1.0 - ood[j]) * alpha_lvl;
+                        const double wv = c1 * cw / dcw + c2 * nc / dnc;      // d res_sj / d val_sgj
+                        double cw_bar = 0.0, nc_bar = 0.0, meanf_bar = 0.0;
+                        double m_bar = 0.0;
+                        // two sweeps over the MC samples for the S > 1 cUCB mean term
+                        for (int s = 0; s < S; ++s) {
+                            const double kap = s_kap[s * MAX_Q + j];
+                            if (kap == 0.0) continue;
+                            double val, dv, sg;
+                            sample_val(s, g, j, val, dv, sg);
+                            cw_bar += kap * c1 * (val / dcw - ((scw[j] > 1e-6) ? s_A[s * MAX_Q + j] / (dcw * dcw) : 0.0));
+                            nc_bar += kap * c2 * (val / dnc - ((snc[j] > 1e-6) ? s_B[s * MAX_Q + j] / (dnc * dnc) : 0.0));
+                            if (p.kind == 0) m_bar += kap * wv * (1.0 - p.beta_prime * sg);
+                        }
+                        for (int s = 0; s < S; ++s) {
+                            const double kap = s_kap[s * MAX_Q + j];
+                            double f_bar;
+                            if (p.kind == 0) {
+                                double val, dv, sg = 0.0;
+                                if (kap != 0.0 && S > 1) sample_val(s, g, j, val, dv, sg);
+                                f_bar = kap * wv * p.beta_prime * sg + m_bar / double(S);
+                                if (S == 1) f_bar = kap * wv;
+                            } else {
+                                if (kap == 0.0) continue;
+                                double val, dv, sg;
+                                sample_val(s, g, j, val, dv, sg);
+                                f_bar = kap * wv * dv;
+                            }
+                            meanf_bar += f_bar;
+#pragma unroll
+                            for (int k = 0; k < Q; ++k)
+                                if (k <= j) a_lf[j][k] = fma(f_bar, p.eps_mc[(int64_t(s) * G + g) * Q + k], a_lf[j][k]);
+                        }
+                        a_mu[j] += meanf_bar;
+#pragma unroll
+                        for (int k = 0; k < Q; ++k) a_shr[j][k] = fma(meanf_bar, g_dev[g * Q + k], a_shr[j][k]);
+                        if (SOFT) {
+                            const double mk_bar = (cw_bar * kd - nc_bar) * op;
+                            const double M_bar = mk_bar * mk * (1.0 - mk) * inv_temp;
+                            const double scale = g_scale[o], srj = g_sr[o], swj = g_sw[o], kl = g_kl[o], Mraw = g_Mraw[o];
+                            double scale_bar = M_bar * (swj + 0.5 * drc[j]) / norm[j];
+                            const double D_bar = -kl * M_bar;
+                            scale_bar = fma(D_bar, 0.5 * omega[j], scale_bar);
+                            a_om[j] = fma(D_bar, 0.5 * scale, a_om[j]);
+                            const double P = M_bar * scale / norm[j];
+                            const double Qv = -scale_bar * scale / srj;
+                            a_drc[j] = fma(0.5, P, a_drc[j]);
+                            a_nrm[j] -= M_bar * Mraw / norm[j];
+                            g_P[o] = P * inv_temp; g_Q[o] = Qv * inv_temp;
+                            // candidate-vs-candidate rank terms: d/d(thr_j - thr_k) = Q_gj rhoc (1 - rhoc) / temp
+#pragma unroll
+                            for (int k = 0; k < Q; ++k) {
+                                if (k != j) {
+                                    double rc = sigmoid_acc(fmin(fmax((g_thr[o] - g_thr[g * Q + k]) * inv_temp, -745.0), 745.0));
+                                    double gc = Qv * inv_temp * rc * (1.0 - rc);
+                                    thr_bar[j] += gc; thr_bar[k] -= gc;
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) {
+                        const double Bj = g_Bg[g * Q + j], tb = thr_bar[j];
+                        a_t1[j] += tb; a_t2[j] = fma(tb * Bj, Bj, a_t2[j]); a_t4[j] = fma(tb, Bj, a_t4[j]);
+#pragma unroll
+                        for (int k = 0; k < Q; ++k) a_t3[j][k] = fma(tb * Bj, g_dev[g * Q + k], a_t3[j][k]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                R.put(SqbIdx::drc(j), a_drc[j]); R.put(SqbIdx::nrm(j), a_nrm[j]); R.put(SqbIdx::om(j), a_om[j]);
+                R.put(SqbIdx::mu(j), a_mu[j]); R.put(SqbIdx::t1(j), a_t1[j]); R.put(SqbIdx::t2(j), a_t2[j]);
+                R.put(SqbIdx::t4(j), a_t4[j]);
+#pragma unroll
+                for (int k = 0; k < Q; ++k) {
+                    R.put(SqbIdx::lf(j, k), a_lf[j][k]); R.put(SqbIdx::shr(j, k), a_shr[j][k]); R.put(SqbIdx::t3(j, k), a_t3[j][k]);
+                }
+            }
+        }
+        __syncthreads();
+        R.commit();
+        __syncthreads();
+
+        // ---- pass 2: thread per train point, loop over the grid ------------------------------------------------------------------
+        R.zero_partials();
+        __syncthreads();
+        {
+            double a_t1[Q], a_t2[Q], a_t4[Q], a_t3[Q][Q], a_bs[Q], a_si[Q][Q];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                a_t1[j] = a_t2[j] = a_t4[j] = a_bs[j] = 0.0;
+#pragma unroll
+                for (int k = 0; k < Q; ++k) a_t3[j][k] = a_si[j][k] = 0.0;
+            }
+            for (int i = tid; i < Np; i += SQ_THREADS) {
+                if (i >= N || !SOFT || bad) {
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) {
+                        qb.wbar[int64_t(r0 + j) * Np + i] = 0.0;
+                        if (i < N) s_wp[size_t(j) * Np + i] = 0.0;
+                    }
+                    continue;
+                }
+                const double ap = s_ap[i], lv = s_lv[i], dr = s_dr[i], siv = s_siv[i];
+                double wp[Q];
+#pragma unroll
+                for (int j = 0; j < Q; ++j) wp[j] = s_wp[size_t(j) * Np + i];
+                double m0 = 0.0, mrr = 0.0, mr = 0.0, mrd[Q];
+#pragma unroll
+                for (int k = 0; k < Q; ++k) mrd[k] = 0.0;
+                for (int g = 0; g < G; ++g) {
+                    double rp = ap;
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) rp = fma(-wp[j], g_Bg[g * Q + j], rp);
+                    const double sci = fma(-rp, rp, lv);
+                    double gam = 0.0;
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) {
+                        const int o = g * Q + j;
+                        const double dd = g_thr[o] - sci;
+                        const double rho = sigmoid_acc(fmin(fmax(dd * inv_temp, -745.0), 745.0));
+                        const double gj_ = fma(g_P[o], dr, g_Q[o]) * rho * (1.0 - rho);
+                        gam += gj_;
+                        const double Bj = g_Bg[o];
+                        a_t1[j] += gj_; a_t2[j] = fma(gj_ * Bj, Bj, a_t2[j]); a_t4[j] = fma(gj_, Bj, a_t4[j]);
+#pragma unroll
+                        for (int k = 0; k < Q; ++k) a_t3[j][k] = fma(gj_ * Bj, g_dev[g * Q + k], a_t3[j][k]);
+                    }
+                    const double grp = gam * rp;
+                    m0 += gam; mrr = fma(grp, rp, mrr); mr += grp;
+#pragma unroll
+                    for (int k = 0; k < Q; ++k) mrd[k] = fma(grp, g_dev[g * Q + k], mrd[k]);
+                }
+                // per-train-point epilogue
+                const double iv = siv * siv;
+                const double var_bar = iv * (m0 - 2.0 * mrr);                     // -2 iv^2 (mrr/iv) - iv (-m0)
+                const double vk = var_bar * noise * kvar;
+                const uint32_t bits = p.zb[i];
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    double mrB = 0.0;
+#pragma unroll
+                    for (int k = 0; k < Q; ++k) mrB = fma(s_Sinv[j * Q + k], mrd[k], mrB);
+                    double zdot = 0.0;
+                    for (int s = 0; s < Sp; ++s) zdot += ((bits >> s) & 1u) ? s_C[j * MAX_SP + s] : -s_C[j * MAX_SP + s];
+                    const double w_ji = wp[j] / (noise * siv);
+                    qb.wbar[int64_t(r0 + j) * Np + i] = fma(vk, zdot, -2.0 * noise * siv * mrB);
+                    s_wp[size_t(j) * Np + i] = vk * w_ji;                           // zdot_bar_ji (this row's table entry is dead)
+                    a_bs[j] = fma(-2.0 * wp[j], mr, a_bs[j]);
+#pragma unroll
+                    for (int k = 0; k < Q; ++k) a_si[j][k] = fma(-2.0 * wp[j], mrd[k], a_si[j][k]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                R.put(SqbIdx::t1(j), a_t1[j]); R.put(SqbIdx::t2(j), a_t2[j]); R.put(SqbIdx::t4(j), a_t4[j]);
+                R.put(SqbIdx::bsum(j), a_bs[j]);
+#pragma unroll
+                for (int k = 0; k < Q; ++k) { R.put(SqbIdx::t3(j, k), a_t3[j][k]); R.put(SqbIdx::sinv(j, k), a_si[j][k]); }
+            }
+        }
+        __syncthreads();
+        R.commit();
+        // C_bar_js (train part) = sum_i (+-) zdot_bar_ji: thread per (j, s)
+        if (tid < Q * Sp) {
+            const int j = tid / Sp, s = tid - j * Sp;
+            double acc = 0.0;
+            for (int i = 0; i < N; ++i) {
+                const double zb_ = s_wp[size_t(j) * Np + i];
+                acc += ((p.zb[i] >> s) & 1u) ? zb_ : -zb_;
+            }
+            s_Cbar[j * MAX_SP + s] = acc;
+        }
+        __syncthreads();
+
+        // ---- final: q x q algebra (one thread) ----------------------------------------------------------------------------------
+        if (tid == 0) {
+            double Si[Q][Q], Lf[Q][Q], shr[Q][Q], shr_bar[Q][Q], Sinv_bar[Q][Q];
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k < Q; ++k) {
+                    Si[j][k] = s_Sinv[j * Q + k]; Lf[j][k] = s_Lf[j * Q + k];
+                    shr[j][k] = ((j == k) ? 1.0 : 0.0) - noise * Si[j][k];
+                    shr_bar[j][k] = tot[SqbIdx::shr(j, k)];
+                }
+            // Cholesky reverse of Lf = chol(Cf): Cf_bar = Lf^-T Phi(Lf^T Lf_bar) Lf^-1, symmetrised
+            double Lfb[Q][Q], Pm[Q][Q], Li[Q][Q], Tm[Q][Q], Cfb[Q][Q];
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k < Q; ++k) Lfb[j][k] = (k <= j) ? tot[SqbIdx::lf(j, k)] : 0.0;
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k < Q; ++k) {
+                    double s = 0.0;
+                    for (int m = 0; m < Q; ++m) s += Lf[m][j] * Lfb[m][k];                    // (Lf^T Lf_bar)_jk
+                    Pm[j][k] = (k < j) ? s : (k == j ? 0.5 * s : 0.0);                        // Phi
+                }
+            for (int j = 0; j < Q; ++j)                                                       // Li = Lf^-1 (lower)
+                for (int i2 = 0; i2 < Q; ++i2) {
+                    if (i2 < j) Li[i2][j] = 0.0;
+                    else if (i2 == j) Li[i2][j] = 1.0 / Lf[i2][i2];
+                    else {
+                        double s = 0.0;
+                        for (int k = j; k < i2; ++k) s += Lf[i2][k] * Li[k][j];
+                        Li[i2][j] = -s / Lf[i2][i2];
+                    }
+                }
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k < Q; ++k) {
+                    double s = 0.0;
+                    for (int m = 0; m < Q; ++m) s += Pm[j][m] * Li[m][k];
+                    Tm[j][k] = s;
+                }
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k < Q; ++k) {
+                    double s = 0.0;
+                    for (int m = 0; m < Q; ++m) s += Li[m][j] * Tm[m][k];
+                    Cfb[j][k] = s;
+                }
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k < Q; ++k) shr_bar[j][k] += noise * 0.5 * (Cfb[j][k] + Cfb[k][j]);
+            double var_c_bar[Q], Bsum[Q];
+            for (int j = 0; j < Q; ++j) {
+                const double lvb = tot[SqbIdx::t1(j)], ivb = -noise * noise * tot[SqbIdx::t2(j)];
+                var_c_bar[j] = -2.0 * ivc[j] * ivc[j] * ivb - ivc[j] * lvb;
+                Bsum[j] = tot[SqbIdx::bsum(j)] - 2.0 * ivc[j] * noise * noise * tot[SqbIdx::t4(j)];
+                for (int s = 0; s < Sp; ++s) s_Cbar[j * MAX_SP + s] += -var_c_bar[j] * kvar * noise * p.z_cand[j * Sp + s];
+            }
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k < Q; ++k) {
+                    double cr = 0.0;
+                    for (int s = 0; s < Sp; ++s) cr = fma(s_Cbar[j * MAX_SP + s], s_R[k * MAX_SP + s], cr);
+                    Sinv_bar[j][k] = -noise * shr_bar[j][k] + tot[SqbIdx::sinv(j, k)]
+                                     - 2.0 * ivc[j] * noise * noise * tot[SqbIdx::t3(j, k)] + cr;
+                }
+            // S_bar = -Sinv^T Sinv_bar Sinv^T
+            double Sb[Q][Q];
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k < Q; ++k) {
+                    double s = 0.0;
+                    for (int m = 0; m < Q; ++m) s += Sinv_bar[j][m] * Si[k][m];               // (Sinv_bar Sinv^T)_jk
+                    Tm[j][k] = s;
+                }
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k < Q; ++k) {
+                    double s = 0.0;
+                    for (int m = 0; m < Q; ++m) s += Si[m][j] * Tm[m][k];
+                    Sb[j][k] = -s;
+                }
+            for (int j = 0; j < Q; ++j) {
+                double* adj = qb.adjq + int64_t(r0 + j) * ADJQ_STRIDE;
+                // mu_bar_k = mu_part_k - sum_j mu_part_j shr_jk - sum_j Sinv_jk Bsum_j   (index j of this loop plays k)
+                double mb = tot[SqbIdx::mu(j)];
+                for (int m = 0; m < Q; ++m) mb -= tot[SqbIdx::mu(m)] * shr[m][j] + Si[m][j] * Bsum[m];
+                double drc_bar = 0.0;
+                if (SOFT) {
+                    double inner = 0.0;
+                    for (int s = 0; s < S; ++s)
+                        inner += s_kap[s * MAX_Q + j] * ((1.0 - alpha_lvl) * s_A[s * MAX_Q + j] / fmax(scw[j], 1e-6) +
+                                                         alpha_lvl * s_B[s * MAX_Q + j] / fmax(snc[j], 1e-6));
+                    const double om_bar = tot[SqbIdx::om(j)] - inner * ood[j] * (1.0 - ood[j]) * inv_temp;
+                    const double nrm_bar = tot[SqbIdx::nrm(j)] - om_bar * omega[j] / norm[j];
+                    drc_bar = tot[SqbIdx::drc(j)] + om_bar / norm[j] + nrm_bar;
+                }
+                adj[0] = bad ? nan("") : mb;
+                adj[1] = bad ? nan("") : drc_bar;
+                for (int k = 0; k < MAX_Q; ++k) adj[2 + k] = (k < Q) ? (bad ? nan("") : Sb[j][k] + Sb[k][j]) : 0.0;
+                for (int s = 0; s < Sp; ++s) {
+                    double ub = 0.0;
+                    for (int m = 0; m < Q; ++m) ub = fma(Si[m][j], s_Cbar[m * MAX_SP + s], ub);   // (Sinv^T C_bar)_js
+                    s_utb[j * MAX_SP + s] = bad ? 0.0 : -ub;
+                    adj[8 + s] = -ub;
+                }
+            }
+            p.acq[c] = tot_acq / double(S);
+        }
+        __syncthreads();
+        // fold the probe term into the right-hand sides: w_bar'_j = w_bar_j + z ut_bar_j   (T = A^-1 z)
+        if (SOFT && !bad)
+            for (int i = tid; i < N; i += SQ_THREADS) {
+                const uint32_t bits = p.zb[i];
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    double acc = qb.wbar[int64_t(r0 + j) * Np + i];
+                    for (int s = 0; s < Sp; ++s) acc += ((bits >> s) & 1u) ? s_utb[j * MAX_SP + s] : -s_utb[j * MAX_SP + s];
+                    qb.wbar[int64_t(r0 + j) * Np + i] = acc;
+                }
+            }
+        __syncthreads();
+    }
+}
+
+// Last stage for joint batches: warp per candidate POINT (row r = c q + j).
+//   u_bar_i = (A^-1 w_bar')_i + mu_bar alpha_i - sum_k Ssym_jk w_ki
+//   x_bar   = sum_i u_bar_i k'(r_i)/r_i (x - X_i)/l^2 + sum_{k != j} Ssym_jk k'(r_jk)/r_jk (x_j - x_k)/l^2
+__global__ void __launch_bounds__(128)
+k_rows_bwd_q(const double* __restrict__ Xq, int rows, int q, const double* __restrict__ XsT, int N, int Np, int d,
+             const double* __restrict__ inv_ls, double outputscale, const double* __restrict__ alpha,
+             const double* __restrict__ Aw, const double* __restrict__ W, const double* __restrict__ adjq,
+             double* __restrict__ dX) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int c = r / q, j = r - c * q;
+    const double* adj = adjq + int64_t(r) * ADJQ_STRIDE;
+    const double mu_bar = adj[0];
+    const double kfac = -(5.0 / 3.0) * outputscale;
+    for (int k0 = 0; k0 < d; k0 += 8) {
+        double acc[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) acc[kk] = 0.0;
+        for (int i = lane; i < N; i += 32) {
+            double r2 = 0.0;
+            for (int k = 0; k < d; ++k) {
+                double df = Xq[int64_t(r) * d + k] * inv_ls[k] - XsT[k * Np + i];
+                r2 = fma(df, df, r2);
+            }
+            double ub = fma(mu_bar, alpha[i], Aw[int64_t(r) * Np + i]);
+            for (int k = 0; k < q; ++k) ub = fma(-adj[2 + k], W[int64_t(c * q + k) * Np + i], ub);
+            const double t = kSqrt5 * sqrt(fmax(r2, 1e-30));
+            const double coef = ub * kfac * (1.0 + t) * exp(-t);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+                if (k0 + kk < d)
+                    acc[kk] = fma(coef, Xq[int64_t(r) * d + k0 + kk] * inv_ls[k0 + kk] - XsT[(k0 + kk) * Np + i], acc[kk]);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            if (k0 + kk < d) {
+                double v = warp_sum(acc[kk]);
+                if (lane == 0) {
+                    // candidate-vs-candidate kernel entries (the diagonal of K_qq is a constant)
+                    for (int k = 0; k < q; ++k) {
+                        if (k == j) continue;
+                        double r2 = 0.0;
+                        for (int e = 0; e < d; ++e) {
+                            double df = (Xq[int64_t(r) * d + e] - Xq[int64_t(c * q + k) * d + e]) * inv_ls[e];
+                            r2 = fma(df, df, r2);
+                        }
+                        const double t = kSqrt5 * sqrt(fmax(r2, 1e-30));
+                        const double dfk = (Xq[int64_t(r) * d + k0 + kk] - Xq[int64_t(c * q + k) * d + k0 + kk]) * inv_ls[k0 + kk];
+                        v = fma(adj[2 + k] * kfac * (1.0 + t) * exp(-t), dfk, v);
+                    }
+                    dX[int64_t(r) * d + k0 + kk] = v * inv_ls[k0 + kk];
+                }
+            }
+        }
+    }
+}
+
+}  // namespace cbo

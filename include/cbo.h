@@ -134,7 +134,7 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
                           const double* eps_mc, const double* u_rand, const cbo_outputs_f64* out,
                           void* workspace, size_t workspace_bytes, int64_t chunk, void* stream);
 
-/* Value and gradient (q = 1, cUCB / cEI): additionally writes dacq_dX (b x d) = d acq[c] / d Xq[c, :], what the reference
+/* Value and gradient (cUCB / cEI, q <= 4): additionally writes dacq_dX (b x q x d) = d acq[c] / d Xq[c, :, :], what the reference
  * obtains by autograd through the same path inside optimize_acqf_sgld (conformalbo/optim/optimize.py:224-235:
  * acq_function(X).sum().backward()); the target grid, its log-density and the optimistic mask are constants, as they are
  * built under torch.no_grad() there (helpers.py:118-119, acquisitions.py:58-59).  temp <= 0: the masks are step functions

@@ -154,11 +154,88 @@ def test_acquisition_class_backward():
             assert torch.allclose(acqf(X), val.detach(), rtol=1e-12)
 
 
+QCASES = [
+    # N, d, q, b, G, temp, randomized, ratio, kind, S
+    (40, 3, 2, 6, 16, 3e-2, False, False, "ucb", 1),
+    (120, 8, 2, 8, 64, 3e-2, True, True, "ucb", 1),          # the reference's default SGLD shape: q_batch_size 2, 8 restarts
+    (33, 2, 2, 5, 12, 5e-2, True, True, "ei", 2),
+    (60, 4, 3, 4, 10, 3e-2, True, True, "ucb", 3),
+    (200, 12, 4, 3, 24, 3e-2, True, False, "ei", 2),         # d > 8
+    (64, 3, 2, 4, 16, 0.0, True, True, "ucb", 2),            # hard path
+]
+
+
+def _gpu_q(p, inp, dev, ratio_w, **kw):
+    from conformal_bayesopt_b200 import ops
+    out = ops.conformal_acq(_state(p, dev), inp["Xq"].to(dev), eps_grid=inp["eps_grid"].to(dev), z=inp["z"].to(dev),
+                            eps_mc=inp["eps_mc"].to(dev), u_rand=inp["u_rand"].to(dev), ratio=ratio_w, want_grad=True, **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("N,d,q,b,G,temp,rand,ratio_on,kind,S", QCASES)
+def test_joint_batch_grad_matches_autograd_of_oracle(N, d, q, b, G, temp, rand, ratio_on, kind, S):
+    dev = _dev()
+    p = make_problem(N, d, seed=N + q)
+    inp = make_inputs(N, d, b, q, G, S=S, seed=N + q)
+    ratio, ratio_w = _ratio(d, dev) if ratio_on else (None, None)
+    kw = dict(kind=kind, alpha=0.15, temp=temp, grid_res=G, randomized=rand, optimistic=True,
+              beta_prime=math.sqrt(0.2 * math.pi / 2), best_f=0.3)
+    acq, g = _oracle_grad(oracle_state(p), inp, ratio, **kw)
+    got = _gpu_q(p, inp, dev, ratio_w, **kw)
+    assert torch.allclose(got["acq"], acq, rtol=1e-6, atol=1e-9)
+    assert g.abs().max() > 0
+    assert _grad_close(got["dacq_dX"], g)
+
+
+def test_joint_batch_grad_matches_hand_derived_reverse_pass():
+    from oracle import analytic_grad_q
+    dev = _dev()
+    N, d, q, b, G = 48, 3, 2, 6, 12
+    p = make_problem(N, d, seed=3)
+    inp = make_inputs(N, d, b, q, G, S=2, seed=3)
+    ratio, ratio_w = _ratio(d, dev)
+    kw = dict(kind="ucb", alpha=0.2, temp=5e-2, grid_res=G, randomized=True, optimistic=True, beta_prime=1.2)
+    want = analytic_grad_q.conformal_acquisition_grad_q(oracle_state(p), inp["Xq"], eps_grid=inp["eps_grid"], z=inp["z"],
+                                                        eps_mc=inp["eps_mc"], ratio=ratio, u_rand=inp["u_rand"], **kw)
+    got = _gpu_q(p, inp, dev, ratio_w, **kw)
+    assert _grad_close(got["dacq_dX"], want["grad"])
+
+
+def test_acquisition_class_backward_joint_batch_with_pending_point():
+    """q = 2 restarts with grad (optimize_acqf_sgld's call) and a pending point appended by concatenate_pending_points:
+    the gradient w.r.t. the optimised points only."""
+    from conformal_bayesopt_b200.acquisitions import qConformalUpperConfidenceBound
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    dev = _dev()
+    N, d, b, G = 60, 3, 8, 16
+    p = make_problem(N, d, seed=60)
+    inp = make_inputs(N, d, b, 3, G, S=1, seed=60)
+    gs, ms = IIDNormalSampler(G), IIDNormalSampler(1, batch_range=(0, -3))
+    gs.set_base_samples(inp["eps_grid"]); ms.set_base_samples(inp["eps_mc"])
+    acqf = qConformalUpperConfidenceBound(0.1, 3e-2, G, 0, None, optimistic=True, grid_sampler=gs, model=_state(p, dev),
+                                          sampler=ms, beta=0.2)
+    acqf.fixed_probes = inp["z"]
+    pend = inp["Xq"][0, 2:].clone()
+    acqf.set_X_pending(pend.to(dev))
+    X = inp["Xq"][:, :2].to(dev).requires_grad_(True)
+    val = acqf(X)
+    val.sum().backward()
+    Xo = inp["Xq"][:, :2].clone().requires_grad_(True)
+    Xfull = torch.cat([Xo, pend.expand(b, 1, d)], dim=1)
+    out = closed_form.conformal_acquisition(oracle_state(p), Xfull, kind="ucb", alpha=0.1, temp=3e-2, grid_res=G,
+                                            eps_grid=inp["eps_grid"], z=inp["z"], eps_mc=inp["eps_mc"], optimistic=True,
+                                            beta_prime=math.sqrt(0.2 * math.pi / 2))
+    (g,) = torch.autograd.grad(out["acq"].sum(), Xo)
+    assert torch.allclose(val.detach().cpu(), out["acq"].detach(), rtol=1e-6, atol=1e-9)
+    assert X.grad.shape == (b, 2, d) and _grad_close(X.grad.cpu(), g)
+
+
 def test_grad_refuses_what_is_not_built():
     from conformal_bayesopt_b200 import _lib
     dev = _dev()
     p = make_problem(40, 3, seed=1)
-    inp = make_inputs(40, 3, 4, 2, 8, seed=1)
+    inp = make_inputs(40, 3, 4, 5, 8, seed=1)
     from conformal_bayesopt_b200 import ops
     with pytest.raises(_lib.CboError, match="unsupported"):
         ops.conformal_acq(_state(p, dev), inp["Xq"].to(dev), eps_grid=inp["eps_grid"].to(dev), z=inp["z"].to(dev),

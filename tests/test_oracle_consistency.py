@@ -163,3 +163,22 @@ def test_hand_derived_reverse_pass_equals_autograd(kind, ratio_on, rand, temp, S
     assert torch.allclose(an["acq"], out["acq"].detach(), rtol=1e-12, atol=1e-14)
     assert g.abs().max() > 1e-3
     assert torch.allclose(an["grad"], g, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("q,kind,ratio_on,rand,S", [(1, "ucb", True, True, 2), (2, "ucb", False, False, 1), (2, "ucb", True, True, 2),
+                                                   (3, "ei", True, True, 2), (4, "ucb", True, True, 3)])
+def test_hand_derived_joint_batch_reverse_pass_equals_autograd(q, kind, ratio_on, rand, S):
+    """oracle/analytic_grad_q.py (the algebra of k_score_q_bwd / k_rows_bwd_q) against autograd through the closed-form oracle."""
+    from oracle import analytic_grad_q
+    N, d, b, G = 24, 3, 5, 10
+    gp = oracle_state(make_problem(N, d, seed=21, fn="sin"))
+    inp = make_inputs(N, d, b, q, G, S=S, seed=21 + q)
+    ratio = ogp.make_ratio_mlp(d) if ratio_on else None
+    kw = dict(kind=kind, alpha=0.2, temp=5e-2, grid_res=G, eps_grid=inp["eps_grid"], z=inp["z"], eps_mc=inp["eps_mc"],
+              ratio=ratio, randomized=rand, u_rand=inp["u_rand"], optimistic=True, beta_prime=1.2, best_f=0.1)
+    X = inp["Xq"].clone().requires_grad_(True)
+    out = closed_form.conformal_acquisition(gp, X, **kw)
+    (g,) = torch.autograd.grad(out["acq"].sum(), X)
+    an = analytic_grad_q.conformal_acquisition_grad_q(gp, inp["Xq"], **kw)
+    assert torch.allclose(an["acq"], out["acq"].detach(), rtol=1e-12, atol=1e-14)
+    assert torch.allclose(an["grad"], g, rtol=1e-9, atol=1e-12)
