@@ -13,10 +13,10 @@
 #include "gemm_tri.cuh"
 #include "rows.cuh"
 #include "score.cuh"
+#include "score_bwd.cuh"
 #include "score_q.cuh"
 #include "mobo.cuh"
 #include "nei.cuh"
-#include "score_bwd.cuh"
 #include "rows_bwd.cuh"
 #include "ratio_mma.cuh"
 #include "model_build.cuh"

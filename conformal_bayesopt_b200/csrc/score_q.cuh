@@ -9,17 +9,19 @@
 // hold the N train weights and only candidate j's own weight (helpers.py:288-297); the randomised step takes its
 // D from the LAST row only (helpers.py:307).  Grid refinement scales the ROWS of the grid covariance
 // (helpers.py:170,178) and the Cholesky reads its lower triangle.
-// One CTA (128 threads) per candidate batch; correctness-first (libdevice exp): joint batches are scored in small
-// numbers (batch_limit 8 x restarts), the q = 1 sweep kernel in score.cuh is the throughput path.
+// One CTA (256 threads) per candidate batch: joint batches are scored in small numbers (batch_limit 8 x restarts), the
+// q = 1 sweep kernel in score.cuh is the throughput path.  The (train point, grid point, column) soft ranks use the same
+// 12-instruction sigmoid as score.cuh (pattern table + cubic + MUFU.RCP64H + Newton).
 #pragma once
 #include "common.cuh"
 #include "rows.cuh"
 #include "score.cuh"
+#include "score_bwd.cuh"
 
 namespace cbo {
 
-constexpr int SQ_THREADS = 128;
-constexpr int SQ_WARPS = 4;
+constexpr int SQ_THREADS = 256;
+constexpr int SQ_WARPS = 8;
 constexpr int MAX_Q = 4;
 
 struct ScoreQArgs {
@@ -132,9 +134,14 @@ k_score_q(const ScoreQArgs pq) {
     double* s_misc = s_C + Q * MAX_SP;       // var_c[Q], logdet, bad
     const double kvar = p.noise / (double(Sp) + 1e-6);
     const double inv_temp = SOFT ? 1.0 / p.temp : 0.0;
+    const double c1q = inv_temp * 23.083120654223414;                    // 16 / (temp ln 2): sigmoid argument in table steps
     const double sum_dr = p.sum_dr[0];
+    __shared__ __align__(128) double tab[16];
+    if (tid < 16) exp_tab_init(tab, tid);
+    const unsigned tab_s = smem_u32(tab);
 
     for (int i = tid; i < N; i += SQ_THREADS) s_dr[i] = p.dr[i];
+    __syncthreads();
 
     for (int c = blockIdx.x; c < p.n_cand; c += gridDim.x) {
         const int r0 = c * Q;
@@ -291,7 +298,7 @@ k_score_q(const ScoreQArgs pq) {
                         bool ge = dd >= 0.0;
                         cnt[j] += ge ? 1 : 0;
                         if (SOFT) {
-                            double rho = sigmoid_acc(fmin(fmax(dd * inv_temp, -745.0), 745.0));
+                            double rho = soft_rho<true>(dd * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
                             sr[j] += rho;
                             sw[j] = fma(rho, dr, sw[j]);
                         } else {

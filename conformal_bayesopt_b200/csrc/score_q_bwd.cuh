@@ -2,7 +2,7 @@
 // differentiates with its default q_batch_size = 2 (conformalbo/optim/optimize.py:224-235, hydra_config/black_box_opt.yaml:10).
 // oracle/analytic_grad_q.py is the line-by-line CPU restatement (checked against torch.autograd to 1e-15).
 //
-// One CTA (128 threads) per candidate batch, as k_score_q (latency regime: batch_limit x restarts candidates per call):
+// One CTA (256 threads) per candidate batch, as k_score_q (latency regime: batch_limit x restarts candidates per call):
 //   phases 0, A, B+C, D   as k_score_q, keeping the per-(grid point, column) sums
 //   phase E  (thread per grid point)  d acq/d values, d acq/d mask -> P_gj, Q_gj (d acq / d rho_ijg = P_gj dr_i + Q_gj),
 //            refit-mean / refit-factor / shrinkage adjoints, candidate-vs-candidate rank terms
@@ -27,7 +27,7 @@ struct ScoreQBwdArgs {
 };
 
 __host__ __device__ inline size_t score_q_bwd_smem_bytes(int Np, int G, int Q) {
-    return sizeof(double) * (size_t(4 + Q) * Np + size_t(SQB_GJ * Q + 1) * G + 1024 + 4 * SQB_NT + SQB_NT);
+    return sizeof(double) * (size_t(4 + Q) * Np + size_t(SQB_GJ * Q + 1) * G + 1024 + SQ_WARPS * SQB_NT + SQB_NT);
 }
 
 // totals layout (doubles): per column / per pair accumulators reduced over the block
@@ -47,7 +47,7 @@ struct SqbIdx {
 };
 static_assert(SqbIdx::bsum(MAX_Q - 1) < SQB_NT, "totals layout");
 
-// add this thread's value to totals slot `slot` (deterministic: warp tree, then fixed-order sum of the 4 warp partials)
+// add this thread's value to totals slot `slot` (deterministic: warp tree, then fixed-order sum of the warp partials)
 struct SqbReducer {
     double* wred;          // [SQ_WARPS][SQB_NT]
     double* tot;           // [SQB_NT]
@@ -103,16 +103,21 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
     double* s_col = s_kap + MAX_S * MAX_Q;   // [4][MAX_Q]: dcw, dnc, ood, live flags packed (cw live + 2 nc live)
     double* s_Cbar = s_col + 4 * MAX_Q;      // Q x MAX_SP
     double* s_utb = s_Cbar + MAX_Q * MAX_SP; // Q x MAX_SP
-    double* wred = sc + 1024;                // [4][SQB_NT]
-    double* tot = wred + 4 * SQB_NT;         // [SQB_NT]
+    double* wred = sc + 1024;                // [SQ_WARPS][SQB_NT]
+    double* tot = wred + SQ_WARPS * SQB_NT;  // [SQB_NT]
     const SqbReducer R{wred, tot, tid};
     const double noise = p.noise;
     const double kvar = noise / (double(Sp) + 1e-6);
     const double inv_temp = SOFT ? 1.0 / p.temp : 0.0;
+    const double c1q = inv_temp * 23.083120654223414;                    // 16 / (temp ln 2)
     const double sum_dr = p.sum_dr[0];
     const double alpha_lvl = p.alpha_lvl;
+    __shared__ __align__(128) double tab[16];
+    if (tid < 16) exp_tab_init(tab, tid);
+    const unsigned tab_s = smem_u32(tab);
 
     for (int i = tid; i < N; i += SQ_THREADS) s_dr[i] = p.dr[i];
+    __syncthreads();
 
     for (int c = blockIdx.x; c < p.n_cand; c += gridDim.x) {
         const int r0 = c * Q;
@@ -270,7 +275,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                         bool ge = dd >= 0.0;
                         cnt[j] += ge ? 1 : 0;
                         if (SOFT) {
-                            double rho = sigmoid_acc(fmin(fmax(dd * inv_temp, -745.0), 745.0));
+                            double rho = soft_rho<true>(dd * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
                             sr[j] += rho;
                             sw[j] = fma(rho, dr, sw[j]);
                         } else {
@@ -544,8 +549,8 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                     for (int j = 0; j < Q; ++j) {
                         const int o = g * Q + j;
                         const double dd = g_thr[o] - sci;
-                        const double rho = sigmoid_acc(fmin(fmax(dd * inv_temp, -745.0), 745.0));
-                        const double gj_ = fma(g_P[o], dr, g_Q[o]) * rho * (1.0 - rho);
+                        const double rho = soft_rho<true>(dd * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
+                        const double gj_ = fma(g_P[o], dr, g_Q[o]) * fma(-rho, rho, rho);
                         gam += gj_;
                         const double Bj = g_Bg[o];
                         a_t1[j] += gj_; a_t2[j] = fma(gj_ * Bj, Bj, a_t2[j]); a_t4[j] = fma(gj_, Bj, a_t4[j]);

@@ -9,8 +9,11 @@ lib = _lib.load()
 p = make_problem(N, d, seed=0)
 st = GPModelState.fit_fixed(p["X"], p["y"], p["mean"], p["lengthscale"], p["outputscale"], p["noise"], device=dev)
 kw = dict(kind="ucb", alpha=1 / math.sqrt(N), temp=3e-2, grid_res=G, randomized=False, optimistic=True, beta_prime=1.0)
+q = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+grad = len(sys.argv) > 2 and sys.argv[2] == "grad"
+kw["want_grad"] = grad
 for b in (8, 128, 1024, 4096):
-    inp = make_inputs(N, d, b, 1, G, seed=0)
+    inp = make_inputs(N, d, b, q, G, seed=0)
     Xq = inp["Xq"].to(dev); eg = inp["eps_grid"].to(dev); z = inp["z"].to(dev); em = inp["eps_mc"].to(dev)
     for _ in range(3):
         ops.conformal_acq(st, Xq, eps_grid=eg, z=z, eps_mc=em, **kw)
@@ -24,4 +27,4 @@ for b in (8, 128, 1024, 4096):
     torch.cuda.synchronize()
     lib.cbo_timing_collect(ms, nl)
     lib.cbo_timing_enable(0)
-    print(b, " ".join(f"{n}={m / reps * 1e3:.0f}us" for n, m in zip(["prep", "rows", "gemm1", "gemm2", "score"], ms)))
+    print(f"q={q} grad={grad} b={b}:", " ".join(f"{n}={m / reps * 1e3:.0f}us" for n, m in zip(["prep", "rows", "gemm1", "gemm2", "score", "score_bwd", "gemm_bwd", "rows_bwd"], ms) if m > 0))
