@@ -32,8 +32,8 @@ FLOP_PER_EVAL = 51811.0            # algorithmic fp64 flop per (
 GEMM_FLOP_PER_CAND_PASS = float(N_TRAIN) * N_TRAIN      # one triangular solve pass: N^2 flop (N^2/2 FMA)
 SCORE_FLOP_PER_EVAL = 17.0 * (N_TRAIN + 1)              # SURVEY.md §8d per-(cand,grid) term
 FP64_PEAK_TFLOPS = 37.0            # measured on this pool's B200 (profiles/r01_fp64_peak.log): DMMA.8x8x4 = whole fp64 pipe
-NCU_DRAM_BYTES_PER_LAUNCH = {"score_rank_integrate": 141.3e6, "gemm_pass1_dmma": 566.3e6, "gemm_pass2_dmma": 494.4e6,
-                             "kernel_rows": 78.2e6}
+NCU_DRAM_BYTES_PER_LAUNCH = {"score_rank_integrate": 140.2e6, "gemm_pass1_dmma": 565.8e6, "gemm_pass2_dmma": 493.5e6,
+                             "kernel_rows": 78.9e6}          # profiles/r01_ncu_summary.txt (dram__bytes_read + write per launch)
 BYTES_PER_EVAL = (8 * DIM + 8) / GRID                   # SURVEY.md §8d algorithmic HBM bytes per eval (no mask output)
 
 
