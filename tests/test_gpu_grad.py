@@ -241,3 +241,32 @@ def test_grad_refuses_what_is_not_built():
         ops.conformal_acq(_state(p, dev), inp["Xq"].to(dev), eps_grid=inp["eps_grid"].to(dev), z=inp["z"].to(dev),
                           eps_mc=inp["eps_mc"].to(dev), want_grad=True, kind="ucb", alpha=0.1, temp=3e-2, grid_res=8,
                           beta_prime=1.0)
+
+
+def test_ratio_mlp_tensor_path_edge_shapes():
+    """k_ratio_mlp_mma / _bwd with hidden sizes and input dimensions that are not multiples of the DMMA tile (zero padding)."""
+    from conformal_bayesopt_b200 import ops
+    dev = _dev()
+    for d, H, n in ((20, 16, 37), (3, 40, 5), (64, 64, 130), (1, 8, 1)):
+        r = ogp.make_ratio_mlp(d, seed=d + H, hidden=H)
+        rw = ops.RatioWeights(*[t.to(dev) for t in (r.W1, r.b1, r.W2, r.b2, r.W3, r.b3)])
+        x = torch.randn(n, d, dtype=torch.float64, generator=torch.Generator().manual_seed(n))
+        got = ops.ratio_forward(rw, x.to(dev)).cpu()
+        assert torch.allclose(got, r(x), rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("N,d,b,G,Sp,H", [(20, 2, 3, 6, 16, 24), (2, 1, 2, 4, 8, 8), (31, 20, 40, 33, 5, 64)])
+def test_grad_edge_shapes(N, d, b, G, Sp, H):
+    """Few train points, 16 / odd numbers of Hutchinson probes, d not a multiple of 4 or 8, small ratio network."""
+    from conformal_bayesopt_b200 import ops
+    from conformal_bayesopt_b200.synthetic import make_inputs as mk
+    dev = _dev()
+    p = make_problem(N, d, seed=N + d)
+    inp = mk(N, d, b, 1, G, S=2, Sp=Sp, seed=N)
+    r = ogp.make_ratio_mlp(d, seed=3, hidden=H)
+    rw = ops.RatioWeights(*[t.to(dev) for t in (r.W1, r.b1, r.W2, r.b2, r.W3, r.b3)])
+    kw = dict(kind="ucb", alpha=0.2, temp=5e-2, grid_res=G, randomized=True, optimistic=True, beta_prime=1.1)
+    acq, g = _oracle_grad(oracle_state(p), inp, r, **kw)
+    got = _gpu(p, inp, dev, rw, **kw)
+    assert torch.allclose(got["acq"], acq, rtol=1e-6, atol=1e-9)
+    assert _grad_close(got["dacq_dX"], g)
