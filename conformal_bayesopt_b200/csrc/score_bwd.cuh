@@ -76,22 +76,46 @@ __device__ __forceinline__ void moment_sweep(const ScoreArgs& p, const double* _
                                              const double (&qb)[SB_RI], const double (&qc)[SB_RI], const double (&dri)[SB_RI],
                                              double (&E0)[SB_RI], double (&E1)[SB_RI], double (&E2)[SB_RI]) {
     const double kMagic = p.k_magic, kC0 = p.k_c0, kC1n = p.k_c1n, kC2 = p.k_c2, kC3n = p.k_c3n;
+    constexpr int kSatHi = 0x408d9000;
+    // Stage-wise over the SB_RI rows (as score_rows): written out so that the four dependency chains are interleaved
+    // instead of being scheduled one after the other.
 #pragma unroll 1
     for (int g = 0; g < G; ++g) {
         const double2 r01 = *reinterpret_cast<const double2*>(rec + 4 * g);
         const double2 r23 = *reinterpret_cast<const double2*>(rec + 4 * g + 2);
         const double bg = r01.x;
+        double t[SB_RI], yn[SB_RI], dd[SB_RI];
 #pragma unroll
         for (int r = 0; r < SB_RI; ++r) {
             double x = fma(fma(qa[r], bg, qb[r]), bg, qc[r]);
-            double rho = soft_rho<CLAMP>(x, tab_s, kMagic, kC0, kC1n, kC2, kC3n);
-            double h = fma(-rho, rho, rho);
+            if (CLAMP) {
+                int hi = __double2hiint(x);
+                int ch = min(hi & 0x7fffffff, kSatHi) | (hi & 0x80000000);
+                x = __hiloint2double(ch, __double2loint(x));
+            }
+            t[r] = kMagic - x;
+            yn[r] = x + (t[r] - kMagic);
+        }
+#pragma unroll
+        for (int r = 0; r < SB_RI; ++r) {
+            double pl = fma(yn[r], kC3n, kC2);
+            pl = fma(pl, yn[r], kC1n);
+            pl = fma(pl, yn[r], kC0);
+            dd[r] = fma(exp_tab_scaled(tab_s, __double2loint(t[r])), pl, 1.0);
+        }
+#pragma unroll
+        for (int r = 0; r < SB_RI; ++r) {
+            double y0;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(dd[r]));
+            const double err1 = fma(-dd[r], y0, 2.0);
+            const double rho = y0 * err1;
+            const double h = fma(-rho, rho, rho);
             if (UNIT) {
                 E0[r] = fma(r01.y, h, E0[r]);
                 E1[r] = fma(r23.x, h, E1[r]);
                 E2[r] = fma(r23.y, h, E2[r]);
             } else {
-                double gam = fma(r23.x, dri[r], r23.y) * h;
+                const double gam = fma(r23.x, dri[r], r23.y) * h;
                 E0[r] += gam;
                 E1[r] = fma(gam, bg, E1[r]);
                 E2[r] = fma(gam, r01.y, E2[r]);
