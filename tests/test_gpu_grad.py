@@ -188,6 +188,19 @@ def test_joint_batch_grad_matches_autograd_of_oracle(N, d, q, b, G, temp, rand, 
     assert _grad_close(got["dacq_dX"], g)
 
 
+def test_joint_batch_grad_with_grid_refinement():
+    dev = _dev()
+    N, d, q, b, G = 64, 2, 2, 10, 32
+    p = make_problem(N, d, seed=64)
+    inp = make_inputs(N, d, b, q, G, S=1, seed=65)
+    kw = dict(kind="ucb", alpha=0.1, temp=1e-2, grid_res=G, randomized=False, optimistic=True, beta_prime=1.0,
+              max_grid_refinements=2)
+    acq, g = _oracle_grad(oracle_state(p), inp, None, **kw)
+    got = _gpu_q(p, inp, dev, None, **kw)
+    assert torch.allclose(got["acq"], acq, rtol=1e-6, atol=1e-9)
+    assert _grad_close(got["dacq_dX"], g)
+
+
 def test_joint_batch_grad_matches_hand_derived_reverse_pass():
     from oracle import analytic_grad_q
     dev = _dev()
