@@ -84,6 +84,9 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     if (tri == TRI_LOWER) k_end = min(K, n0 + GEMM_BN);
     if (tri == TRI_UPPER) k_begin = n0;
     const int nk = (k_end - k_begin) / GEMM_BK;
+    // K is walked so that the diagonal block (where half of the warps skip and the loads are not covered by MMAs) comes
+    // LAST, when the prefetch ring is full: ascending for lower, descending for upper.
+    auto kpos = [&](int kt) { return (tri == TRI_UPPER) ? k_end - (kt + 1) * GEMM_BK : k_begin + kt * GEMM_BK; };
 
     double acc[MF][4][2];
 #pragma unroll
@@ -106,7 +109,7 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     for (int s = 0; s < PF; ++s) {
         if (s < nk) {
             double* sA = smem + s * GEMM_STAGE_DOUBLES;
-            gemm_load_stage<BM>(sA, sA + BM * GEMM_LDS, A, lda, B, ldb, m0, n0, k_begin + s * GEMM_BK, M, tid);
+            gemm_load_stage<BM>(sA, sA + BM * GEMM_LDS, A, lda, B, ldb, m0, n0, kpos(s), M, tid);
             cp_async_mbar_arrive(&full[s]);
         }
     }
@@ -119,14 +122,14 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
                 const int st = nt % GEMM_STAGES;
                 mbar_wait(&empty[st], ((nt / GEMM_STAGES) & 1) ^ 1);
                 double* sA = smem + st * GEMM_STAGE_DOUBLES;
-                gemm_load_stage<BM>(sA, sA + BM * GEMM_LDS, A, lda, B, ldb, m0, n0, k_begin + nt * GEMM_BK, M, tid);
+                gemm_load_stage<BM>(sA, sA + BM * GEMM_LDS, A, lda, B, ldb, m0, n0, kpos(nt), M, tid);
                 cp_async_mbar_arrive(&full[st]);
             }
         }
         const int st = kt % GEMM_STAGES;
         // On the diagonal 128 x 128 block of the triangular factor this warp's 32 columns see only zeros for part of
         // the K range: lower  -> k < n_warp_end,  upper -> k + BK > n_warp_begin.  Skip those MMAs (warp-uniform).
-        const int k0 = k_begin + kt * GEMM_BK;
+        const int k0 = kpos(kt);
         const bool skip = (tri == TRI_LOWER && k0 >= n0 + 32 * (wn + 1)) || (tri == TRI_UPPER && k0 + GEMM_BK <= n0 + 32 * wn);
         if (!skip) {
             mbar_wait(&full[st], (kt / GEMM_STAGES) & 1);
