@@ -66,6 +66,7 @@ CASES = [
     (128, 3, 1, 2, 3e-2, False, False, "ucb", 1, True),       # minimum grid, single candidate
     (130, 4, 9, 32, 0.0, True, True, "ucb", 2, True),         # hard path: step masks, only the value path carries gradient
     (64, 5, 700, 200, 3e-2, False, True, "ucb", 1, True),     # G > threads of one 4-warp group
+    (1500, 8, 24, 32, 3e-2, True, True, "ucb", 1, True),      # Np = 1536: 12 GEMM tiles, 2 score groups per SM
 ]
 
 
