@@ -21,7 +21,8 @@
 
 namespace cbo {
 
-constexpr int SB_RI = 4;              // train points per thread in pass 2 (independent dependency chains)
+constexpr int SB_RI = 2;              // train points per thread in pass 2 ...
+constexpr int SB_GI = 2;              // ... times grid points per step = independent dependency chains per thread
 constexpr int SB_GARR = 12;           // per-grid arrays
 constexpr int SB_PART = 24;           // doubles per warp of partial sums (4 + 6 + 4 + MAX_SP <= 32 is split in 2 regions)
 constexpr int ADJ_STRIDE = 4 + MAX_SP;   // adj[c] = {mu_bar, s_bar, drc_bar, -, ut_bar[Sp]}
@@ -77,50 +78,63 @@ __device__ __forceinline__ void moment_sweep(const ScoreArgs& p, const double* _
                                              double (&E0)[SB_RI], double (&E1)[SB_RI], double (&E2)[SB_RI]) {
     const double kMagic = p.k_magic, kC0 = p.k_c0, kC1n = p.k_c1n, kC2 = p.k_c2, kC3n = p.k_c3n;
     constexpr int kSatHi = 0x408d9000;
-    // Stage-wise over the SB_RI rows (as score_rows): written out so that the four dependency chains are interleaved
-    // instead of being scheduled one after the other.
+    // Stage-wise over SB_RI rows x SB_GI grid points (as score_rows): written out so that the dependency chains are
+    // interleaved instead of being scheduled one after the other; 2 x 2 keeps the live coefficients / moments at 12 doubles.
+    static_assert(SB_GI == 2, "moment_sweep is written for two grid points per step");
 #pragma unroll 1
-    for (int g = 0; g < G; ++g) {
-        const double2 r01 = *reinterpret_cast<const double2*>(rec + 4 * g);
-        const double2 r23 = *reinterpret_cast<const double2*>(rec + 4 * g + 2);
-        const double bg = r01.x;
-        double t[SB_RI], yn[SB_RI], dd[SB_RI];
+    for (int g = 0; g < G; g += SB_GI) {
+        const int g1 = (g + 1 < G) ? g + 1 : g;
+        const double w1 = (g + 1 < G) ? 1.0 : 0.0;               // odd G: the padded second slot contributes nothing
+        double2 r01[SB_GI], r23[SB_GI];
+        r01[0] = *reinterpret_cast<const double2*>(rec + 4 * g);
+        r23[0] = *reinterpret_cast<const double2*>(rec + 4 * g + 2);
+        r01[1] = *reinterpret_cast<const double2*>(rec + 4 * g1);
+        r23[1] = *reinterpret_cast<const double2*>(rec + 4 * g1 + 2);
+        double t[SB_RI][SB_GI], yn[SB_RI][SB_GI], dd[SB_RI][SB_GI];
 #pragma unroll
-        for (int r = 0; r < SB_RI; ++r) {
-            double x = fma(fma(qa[r], bg, qb[r]), bg, qc[r]);
-            if (CLAMP) {
-                int hi = __double2hiint(x);
-                int ch = min(hi & 0x7fffffff, kSatHi) | (hi & 0x80000000);
-                x = __hiloint2double(ch, __double2loint(x));
+        for (int r = 0; r < SB_RI; ++r)
+#pragma unroll
+            for (int k = 0; k < SB_GI; ++k) {
+                const double bg = r01[k].x;
+                double x = fma(fma(qa[r], bg, qb[r]), bg, qc[r]);
+                if (CLAMP) {
+                    int hi = __double2hiint(x);
+                    int ch = min(hi & 0x7fffffff, kSatHi) | (hi & 0x80000000);
+                    x = __hiloint2double(ch, __double2loint(x));
+                }
+                t[r][k] = kMagic - x;
+                yn[r][k] = x + (t[r][k] - kMagic);
             }
-            t[r] = kMagic - x;
-            yn[r] = x + (t[r] - kMagic);
-        }
 #pragma unroll
-        for (int r = 0; r < SB_RI; ++r) {
-            double pl = fma(yn[r], kC3n, kC2);
-            pl = fma(pl, yn[r], kC1n);
-            pl = fma(pl, yn[r], kC0);
-            dd[r] = fma(exp_tab_scaled(tab_s, __double2loint(t[r])), pl, 1.0);
-        }
+        for (int r = 0; r < SB_RI; ++r)
 #pragma unroll
-        for (int r = 0; r < SB_RI; ++r) {
-            double y0;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(dd[r]));
-            const double err1 = fma(-dd[r], y0, 2.0);
-            const double rho = y0 * err1;
-            const double h = fma(-rho, rho, rho);
-            if (UNIT) {
-                E0[r] = fma(r01.y, h, E0[r]);
-                E1[r] = fma(r23.x, h, E1[r]);
-                E2[r] = fma(r23.y, h, E2[r]);
-            } else {
-                const double gam = fma(r23.x, dri[r], r23.y) * h;
-                E0[r] += gam;
-                E1[r] = fma(gam, bg, E1[r]);
-                E2[r] = fma(gam, r01.y, E2[r]);
+            for (int k = 0; k < SB_GI; ++k) {
+                double pl = fma(yn[r][k], kC3n, kC2);
+                pl = fma(pl, yn[r][k], kC1n);
+                pl = fma(pl, yn[r][k], kC0);
+                dd[r][k] = fma(exp_tab_scaled(tab_s, __double2loint(t[r][k])), pl, 1.0);
             }
-        }
+#pragma unroll
+        for (int r = 0; r < SB_RI; ++r)
+#pragma unroll
+            for (int k = 0; k < SB_GI; ++k) {
+                double y0;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(dd[r][k]));
+                const double err1 = fma(-dd[r][k], y0, 2.0);
+                const double rho = y0 * err1;
+                double h = fma(-rho, rho, rho);
+                if (k == 1) h *= w1;
+                if (UNIT) {
+                    E0[r] = fma(r01[k].y, h, E0[r]);
+                    E1[r] = fma(r23[k].x, h, E1[r]);
+                    E2[r] = fma(r23[k].y, h, E2[r]);
+                } else {
+                    const double gam = fma(r23[k].x, dri[r], r23[k].y) * h;
+                    E0[r] += gam;
+                    E1[r] = fma(gam, r01[k].x, E1[r]);
+                    E2[r] = fma(gam, r01[k].y, E2[r]);
+                }
+            }
     }
 }
 
