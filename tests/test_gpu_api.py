@@ -287,3 +287,14 @@ def test_model_build_reports_non_positive_definite():
     X[7] = X[3]                                            # duplicate point and (almost) no noise: singular to rounding
     with pytest.raises(_lib.CboError, match="positive definite|invalid"):
         GPModelState.fit_fixed(X, torch.zeros(40, dtype=torch.float64), 0.0, 0.5, 1.0, -1e-3, device=dev)
+
+
+def test_bo_loop_demo_runs_on_the_drop_in_classes():
+    """tools/bo_demo.py: model build -> raw scoring -> SGLD steps with grad (q = 2) -> re-scoring, two rounds."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bo_demo", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "bo_demo.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    best = mod.run(rounds=2, sgld_steps=6, raw=256, verbose=False)
+    assert len(best) == 3 and all(math.isfinite(v) for v in best) and best[-1] >= best[0]
