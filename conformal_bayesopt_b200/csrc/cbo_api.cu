@@ -199,6 +199,11 @@ cudaError_t launch_score(const cbo::ScoreArgs& a_in, cudaStream_t st) {
     int wl = 1;
     while (wl < 4 && a.n_cand * (1 << wl) < 16 * num_sms()) ++wl;
     while (wl > 1 && (1 << wl) > 2 * cbo::SCORE_FWD_PAIRS) --wl;
+    // large N: shared memory admits only a few candidates per SM -- widen the groups until the CTA has its 16 warps again
+    while (wl < 4 && (2 << wl) <= 2 * cbo::SCORE_FWD_PAIRS &&
+           cbo::score_groups_for(a.Np, a.G, 1 << wl) * (1 << wl) < 2 * cbo::SCORE_FWD_PAIRS &&
+           cbo::score_groups_for(a.Np, a.G, 2 << wl) * (2 << wl) > cbo::score_groups_for(a.Np, a.G, 1 << wl) * (1 << wl))
+        ++wl;
     const int ngroups = cbo::score_groups_for(a.Np, a.G, 1 << wl);
     if (ngroups < 1) return cudaErrorInvalidConfiguration;
     a.wpg_log2 = wl;
@@ -224,6 +229,9 @@ cudaError_t launch_score_bwd(const cbo::ScoreBwdArgs& a_in, cudaStream_t st) {
     while (wl < 4 && a.f.n_cand * (1 << wl) < 16 * num_sms()) ++wl;
     while (wl < 4 && a.f.G > 4 * (32 << wl)) ++wl;
     if (a.f.G > 4 * (32 << wl)) return cudaErrorInvalidConfiguration;
+    while (wl < 4 && cbo::score_bwd_groups_for(a.f.Np, a.f.G, 1 << wl) * (1 << wl) < 16 &&
+           cbo::score_bwd_groups_for(a.f.Np, a.f.G, 2 << wl) * (2 << wl) > cbo::score_bwd_groups_for(a.f.Np, a.f.G, 1 << wl) * (1 << wl))
+        ++wl;
     const int ngroups = cbo::score_bwd_groups_for(a.f.Np, a.f.G, 1 << wl);
     if (ngroups < 1) return cudaErrorInvalidConfiguration;
     a.f.wpg_log2 = wl;
