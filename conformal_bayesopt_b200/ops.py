@@ -109,7 +109,7 @@ def workspace(state: GPModelState, b: int, params, chunk: int = 0, grad: bool = 
 def count_launches(state: GPModelState, b: int, params, ratio: bool, chunk: int = 0, grad: bool = False,
                    extra_outputs: bool = False) -> int:
     """Kernels one cbo_conformal_acq[_grad]_f64 call enqueues (mirrors csrc/cbo_api.cu)."""
-    C_ = b if params.max_grid_refinements > 0 else min(b, chunk if chunk > 0 else 16384)
+    C_ = b if params.max_grid_refinements > 0 else min(b, chunk if chunk > 0 else 65536)
     n_chunks = (b + C_ - 1) // C_
     per_call = 7                                   # scale_transpose, pad_probes, 2 x probe_matvec, ratio/fill, eps_absmax, train_tables
     per_chunk = 1 + (1 if ratio else 0) + 2 + 1    # rows, ratio(cand), 2 x gemm, score

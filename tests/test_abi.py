@@ -37,7 +37,7 @@ def test_workspace_bytes_and_argument_validation():
     small = lib.cbo_workspace_bytes(1024, 8, 4096, ctypes.byref(p), 0)
     big = lib.cbo_workspace_bytes(1024, 8, 1 << 20, ctypes.byref(p), 0)
     assert small % 256 == 0 and 2 * 4096 * 1024 * 8 < small < 2.2 * 4096 * 1024 * 8
-    assert big < 2.2 * 16384 * 1024 * 8          # chunked: independent of b beyond the chunk size
+    assert big < 2.2 * 65536 * 1024 * 8          # chunked: independent of b beyond the chunk size
     pr = ops.make_params(alpha=0.1, temp=0.03, grid_res=64, max_grid_refinements=2)
     assert lib.cbo_workspace_bytes(1024, 8, 1 << 16, ctypes.byref(pr), 0) > 2 * (1 << 16) * 1024 * 8   # refinement keeps all candidates
     # null pointers / bad sizes are rejected with status codes before any CUDA call
