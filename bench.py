@@ -350,7 +350,10 @@ def run_ours(args):
         "whole_path": {"achieved": value / world * FLOP_PER_EVAL / 1e12, "frac": value / world * FLOP_PER_EVAL / 1e12 / FP64_PEAK_TFLOPS,
                        "flop_per_eval": FLOP_PER_EVAL},
         "hbm": {"achieved_gbs": value / world * BYTES_PER_EVAL / 1e9, "bytes_per_eval": BYTES_PER_EVAL, "peak_gbs": 6539.2,
-                "frac": value / world * BYTES_PER_EVAL / 1e9 / 6539.2, "note": "path is fp64-compute bound, not HBM bound (SURVEY.md 8d)"},
+                "frac": value / world * BYTES_PER_EVAL / 1e9 / 6539.2,
+                # what the kernels really move (ncu dram bytes per 65536-candidate launch x launches per step / step time)
+                "actual_dram_gbs": sum(NCU_DRAM_BYTES_PER_LAUNCH.values()) * (b / 65536.0) / (elapsed_ms / args.steps * 1e-3) / 1e9,
+                "note": "path is fp64-compute bound, not HBM bound (SURVEY.md 8d): the U/V/W row round trips overlap the GEMMs"},
         "kernels": kernels,
     }
     line = {
