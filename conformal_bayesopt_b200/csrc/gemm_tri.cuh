@@ -28,6 +28,7 @@ constexpr int GEMM_LDS = GEMM_BK + 4;       // padded row stride (doubles)
 constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_PREFETCH = 2;         // tiles in flight; STAGES - PREFETCH = tiles of slack between warps
 constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_MGROUP = 64;          // m-tiles per L2 group (see the tile order in the kernel)
 constexpr int GEMM_STAGE_DOUBLES = (GEMM_BM + GEMM_BN) * GEMM_LDS;
 constexpr size_t GEMM_SMEM_BYTES = size_t(GEMM_STAGES) * GEMM_STAGE_DOUBLES * sizeof(double) + 2 * GEMM_STAGES * sizeof(uint64_t);
 
@@ -75,10 +76,16 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     const int tiles_m = (M + BM - 1) / BM;
     const int tiles_n = Nn / GEMM_BN;
     // longest-K tiles first: lower -> last n-tile first; upper / full -> first n-tile first
+    // ... within groups of GEMM_MGROUP m-tiles: a group's A rows (64 x 128 rows = 64 MB at K = 1024) stay in L2 while its
+    // n-tiles are swept, so A is read from HBM once instead of once per n-tile
     const int t = blockIdx.x;
-    const int n_ord = t / tiles_m;
+    const int grp = t / (GEMM_MGROUP * tiles_n);
+    const int gm0 = grp * GEMM_MGROUP;
+    const int gsz = min(GEMM_MGROUP, tiles_m - gm0);                  // m-tiles in this group
+    const int tg = t - grp * GEMM_MGROUP * tiles_n;
+    const int n_ord = tg / gsz;
     const int n_tile = (tri == TRI_LOWER) ? (tiles_n - 1 - n_ord) : n_ord;
-    const int m_tile = t - n_ord * tiles_m;
+    const int m_tile = gm0 + tg - n_ord * gsz;
     const int m0 = m_tile * BM, n0 = n_tile * GEMM_BN;
     int k_begin = 0, k_end = K;
     if (tri == TRI_LOWER) k_end = min(K, n0 + GEMM_BN);
