@@ -83,6 +83,7 @@ struct Workspace {
     double *UW, *V, *mu, *ut, *drc, *rn;
     double *cscale, *nacc, *acq_scratch, *stats;      // refinement only
     double* nei_values;                               // cNEI only: C x S x G
+    double* splitk;                                   // split-K partial tiles (calls with <= 32 candidate points)
     double *X3, *adj;                                 // gradient only: C x Np solve scratch, C x ADJ_STRIDE adjoints
     size_t bytes;
 };
@@ -120,6 +121,7 @@ Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, 
     w.acq_scratch = c.take<double>(R > 0 ? b : 1);
     w.stats = c.take<double>(8);
     w.nei_values = c.take<double>(p->kind == CBO_ACQ_NEI ? C * p->num_mc * p->grid_res : 1);
+    w.splitk = c.take<double>(cbo::gemm_splitk_scratch_doubles((int)Np));
     w.X3 = c.take<double>(grad ? C * Np : 1);
     w.adj = c.take<double>(grad ? C * (cbo::ADJQ_STRIDE > cbo::ADJ_STRIDE ? cbo::ADJQ_STRIDE : cbo::ADJ_STRIDE) : 1);
     w.bytes = c.off;
@@ -329,7 +331,7 @@ int cbo_gemm_tn_f64(const double* A, int64_t lda, const double* B, int64_t ldb, 
     if (Nn % cbo::GEMM_BN || K % cbo::GEMM_BN || tri < 0 || tri > 2) return CBO_ERR_UNSUPPORTED;
     if ((lda | ldb | ldc) & 1) return CBO_ERR_UNSUPPORTED;      // 16-byte cp.async / double2 stores
     CBO_CUDA(cbo::launch_gemm_tn(A, lda, B, ldb, C, ldc, (int)M, (int)Nn, (int)K, tri, rownorm_partial,
-                                 static_cast<cudaStream_t>(stream)));
+                                 static_cast<cudaStream_t>(stream), num_sms()));
     return CBO_OK;
 }
 
@@ -415,6 +417,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
 
     const int R = (int)p->max_grid_refinements;
     const int q = (int)p->q;
+    double* splitk = (b * q <= cbo::GEMM_SPLITK_MAX_M) ? w.splitk : nullptr;   // a handful of candidate points in the whole call: split-K GEMMs
     for (int64_t c0 = 0; c0 < b; c0 += C) {
         const int ncand = (int)((b - c0 < C) ? (b - c0) : C);
         const int n = ncand * q;                                  // kernel rows of this chunk: one per candidate POINT
@@ -432,11 +435,11 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
         // ---- v = L^-1 u (+ ||v||^2 partials), w = L^-T v ------------------------------------------
         {
             TimeScope ts_(T_GEMM1, s, 1);
-            CBO_CUDA(cbo::launch_gemm_tn(w.UW, Np, gp->linv, Np, w.V, Np, n, Np, Np, cbo::TRI_LOWER, w.rn, s, num_sms()));
+            CBO_CUDA(cbo::launch_gemm_tn(w.UW, Np, gp->linv, Np, w.V, Np, n, Np, Np, cbo::TRI_LOWER, w.rn, s, num_sms(), splitk));
         }
         {
             TimeScope ts_(T_GEMM2, s, 1);
-            CBO_CUDA(cbo::launch_gemm_tn(w.V, Np, gp->linv_t, Np, w.UW, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms()));
+            CBO_CUDA(cbo::launch_gemm_tn(w.V, Np, gp->linv_t, Np, w.UW, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms(), splitk));
         }
 
         // ---- scores / rank / mask / integration ----------------------------------------------------
@@ -521,8 +524,8 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             double* sol = (q == 1) ? w.X3 : w.V;                    // scratch of the two-pass solve
             {
                 TimeScope ts_(T_GEMM_BWD, s, 2);
-                CBO_CUDA(cbo::launch_gemm_tn(rhs, Np, gp->linv, Np, sol, Np, n, Np, Np, cbo::TRI_LOWER, nullptr, s, num_sms()));
-                CBO_CUDA(cbo::launch_gemm_tn(sol, Np, gp->linv_t, Np, rhs, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms()));
+                CBO_CUDA(cbo::launch_gemm_tn(rhs, Np, gp->linv, Np, sol, Np, n, Np, Np, cbo::TRI_LOWER, nullptr, s, num_sms(), splitk));
+                CBO_CUDA(cbo::launch_gemm_tn(sol, Np, gp->linv_t, Np, rhs, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms(), splitk));
             }
             {
                 TimeScope ts_(T_ROWS_BWD, s, ratio ? 2 : 1);
@@ -530,7 +533,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                     CBO_CUDA(cbo::launch_rows_bwd(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->alpha, rhs,
                                                   w.UW, w.adj, dX + c0 * q * d, num_sms(), s));
                 else
-                    cbo::k_rows_bwd_q<<<(n + 3) / 4, 128, 0, s>>>(Xc, n, q, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale,
+                    cbo::k_rows_bwd_q<<<n, cbo::RBQ_THREADS, 0, s>>>(Xc, n, q, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale,
                                                                  gp->alpha, rhs, w.UW, w.adj, dX + c0 * q * d);
                 if (ratio)
                     CBO_CUDA(cbo::launch_ratio_mlp_bwd(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2,

@@ -64,7 +64,7 @@ template <int MF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
               double* __restrict__ C, int64_t ldc, int M, int Nn, int K, int tri,
-              double* __restrict__ rownorm_partial) {
+              double* __restrict__ rownorm_partial, int splits, int64_t part_stride) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -90,6 +90,13 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     int k_begin = 0, k_end = K;
     if (tri == TRI_LOWER) k_end = min(K, n0 + GEMM_BN);
     if (tri == TRI_UPPER) k_begin = n0;
+    if (splits > 1) {          // split-K: this CTA owns the k-tiles [kt_lo, kt_hi) of the tile's range and its own partial C
+        const int nk_all = (k_end - k_begin) / GEMM_BK, per = (nk_all + splits - 1) / splits;
+        const int kt_lo = min(nk_all, int(blockIdx.y) * per), kt_hi = min(nk_all, kt_lo + per);
+        if (tri == TRI_UPPER) { const int e0 = k_end; k_end = e0 - kt_lo * GEMM_BK; k_begin = e0 - kt_hi * GEMM_BK; }
+        else { const int b0 = k_begin; k_begin = b0 + kt_lo * GEMM_BK; k_end = b0 + kt_hi * GEMM_BK; }
+        C += int64_t(blockIdx.y) * part_stride;
+    }
     const int nk = (k_end - k_begin) / GEMM_BK;
     // K is walked so that the diagonal block (where half of the warps skip and the loads are not covered by MMAs) comes
     // LAST, when the prefetch ring is full: ascending for lower, descending for upper.
@@ -201,7 +208,8 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
 
 template <int MF>
 inline cudaError_t launch_gemm_tn_t(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
-                                    int M, int Nn, int K, int tri, double* rownorm_partial, cudaStream_t stream) {
+                                    int M, int Nn, int K, int tri, double* rownorm_partial, cudaStream_t stream,
+                                    int splits = 1, int64_t part_stride = 0) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm_tn_f64<MF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -210,14 +218,60 @@ inline cudaError_t launch_gemm_tn_t(const double* A, int64_t lda, const double* 
         attr_set = true;
     }
     int tiles_m = (M + 16 * MF - 1) / (16 * MF), tiles_n = Nn / GEMM_BN;
-    k_gemm_tn_f64<MF><<<tiles_m * tiles_n, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(A, lda, B, ldb, C, ldc, M, Nn, K, tri,
-                                                                                   rownorm_partial);
+    k_gemm_tn_f64<MF><<<dim3(tiles_m * tiles_n, splits), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(
+        A, lda, B, ldb, C, ldc, M, Nn, K, tri, rownorm_partial, splits, part_stride);
     return cudaGetLastError();
 }
 
+// ---- split-K for a handful of rows (M <= 32: the SGLD regime) ---------------------------------------------------------------
+// The tiled kernel alone would run 8 CTAs through up to 64 sequential k-tiles (~35 us of latency).  With blockIdx.y = split
+// index every (n-tile, split) CTA walks 1/splits of the tile's k-tiles and writes its partial C tile; k_splitk_reduce sums
+// the partials in a fixed order (deterministic) and k_rownorm_tiles produces the per-tile row norms.
+// rownorm_partial[row][tile] = sum over the tile's 128 columns of C[row][n]^2 (one warp per (row, tile), fixed order)
+__global__ void k_rownorm_tiles(const double* __restrict__ C, int64_t ldc, int M, int tiles_n, double* __restrict__ rn) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= M * tiles_n) return;
+    const int row = w / tiles_n, tile = w - row * tiles_n;
+    const double* c = C + int64_t(row) * ldc + tile * GEMM_BN;
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < GEMM_BN / 32; ++j) { double v = c[lane + 32 * j]; s = fma(v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) rn[int64_t(row) * tiles_n + tile] = s;
+}
+
+// C[m][n] = sum_s part[s][m][n]  (fixed order)
+__global__ void k_splitk_reduce(const double* __restrict__ part, int splits, int64_t part_stride, int64_t ldp,
+                                double* __restrict__ C, int64_t ldc, int M, int Nn) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M * Nn) return;
+    const int m = e / Nn, n = e - m * Nn;
+    double s = 0.0;
+    for (int sp = 0; sp < splits; ++sp) s += part[sp * part_stride + int64_t(m) * ldp + n];
+    C[int64_t(m) * ldc + n] = s;
+}
+
+constexpr int GEMM_SPLITK = 8;
+constexpr int GEMM_SPLITK_MAX_M = 32;
+inline size_t gemm_splitk_scratch_doubles(int Nn) { return size_t(GEMM_SPLITK) * GEMM_SPLITK_MAX_M * Nn; }
+
 inline cudaError_t launch_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                                   int M, int Nn, int K, int tri, double* rownorm_partial, cudaStream_t stream,
-                                  int num_sms = 148) {
+                                  int num_sms = 148, double* splitk_scratch = nullptr) {
+    // split-K is decided per CALL by the API (all rows of the call <= 32, scratch given), never per chunk: chunking stays
+    // bit-invariant
+    if (splitk_scratch != nullptr && M <= GEMM_SPLITK_MAX_M) {
+        const int64_t ps = int64_t(GEMM_SPLITK_MAX_M) * Nn;
+        cudaError_t e = (M > 16)
+            ? launch_gemm_tn_t<2>(A, lda, B, ldb, splitk_scratch, Nn, M, Nn, K, tri, nullptr, stream, GEMM_SPLITK, ps)
+            : launch_gemm_tn_t<1>(A, lda, B, ldb, splitk_scratch, Nn, M, Nn, K, tri, nullptr, stream, GEMM_SPLITK, ps);
+        if (e != cudaSuccess) return e;
+        k_splitk_reduce<<<(M * Nn + 255) / 256, 256, 0, stream>>>(splitk_scratch, GEMM_SPLITK, ps, Nn, C, ldc, M, Nn);
+        if (rownorm_partial != nullptr)
+            k_rownorm_tiles<<<(M * (Nn / GEMM_BN) + 7) / 8, 256, 0, stream>>>(C, ldc, M, Nn / GEMM_BN, rownorm_partial);
+        return cudaGetLastError();
+    }
     // pick the largest m-tile that still yields ~2 CTAs per SM; few rows -> small tiles (latency, no wasted rows)
     const int tiles_n = Nn / GEMM_BN;
     auto ctas = [&](int bm) { return ((M + bm - 1) / bm) * tiles_n; };

@@ -718,61 +718,70 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
     }
 }
 
-// Last stage for joint batches: warp per candidate POINT (row r = c q + j).
+// Last stage for joint batches: one CTA (256 threads) per candidate POINT (row r = c q + j) -- a handful of rows per call, so
+// the train points of ONE row are spread over 8 warps (latency, not throughput).
 //   u_bar_i = (A^-1 w_bar')_i + mu_bar alpha_i - sum_k Ssym_jk w_ki
 //   x_bar   = sum_i u_bar_i k'(r_i)/r_i (x - X_i)/l^2 + sum_{k != j} Ssym_jk k'(r_jk)/r_jk (x_j - x_k)/l^2
-__global__ void __launch_bounds__(128)
+constexpr int RBQ_THREADS = 256;
+__global__ void __launch_bounds__(RBQ_THREADS)
 k_rows_bwd_q(const double* __restrict__ Xq, int rows, int q, const double* __restrict__ XsT, int N, int Np, int d,
              const double* __restrict__ inv_ls, double outputscale, const double* __restrict__ alpha,
              const double* __restrict__ Aw, const double* __restrict__ W, const double* __restrict__ adjq,
              double* __restrict__ dX) {
-    const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ double s_x[MAX_D], s_red[RBQ_THREADS / 32][8], s_adj[2 + MAX_Q];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = blockIdx.x;
     if (r >= rows) return;
     const int c = r / q, j = r - c * q;
-    const double* adj = adjq + int64_t(r) * ADJQ_STRIDE;
-    const double mu_bar = adj[0];
+    if (tid < d) s_x[tid] = Xq[int64_t(r) * d + tid] * inv_ls[tid];
+    if (tid < 2 + MAX_Q) s_adj[tid] = adjq[int64_t(r) * ADJQ_STRIDE + tid];
+    __syncthreads();
+    const double mu_bar = s_adj[0];
     const double kfac = -(5.0 / 3.0) * outputscale;
     for (int k0 = 0; k0 < d; k0 += 8) {
         double acc[8];
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) acc[kk] = 0.0;
-        for (int i = lane; i < N; i += 32) {
+        for (int i = tid; i < N; i += RBQ_THREADS) {
             double r2 = 0.0;
             for (int k = 0; k < d; ++k) {
-                double df = Xq[int64_t(r) * d + k] * inv_ls[k] - XsT[k * Np + i];
+                double df = s_x[k] - XsT[k * Np + i];
                 r2 = fma(df, df, r2);
             }
             double ub = fma(mu_bar, alpha[i], Aw[int64_t(r) * Np + i]);
-            for (int k = 0; k < q; ++k) ub = fma(-adj[2 + k], W[int64_t(c * q + k) * Np + i], ub);
+            for (int k = 0; k < q; ++k) ub = fma(-s_adj[2 + k], W[int64_t(c * q + k) * Np + i], ub);
             const double t = kSqrt5 * sqrt(fmax(r2, 1e-30));
             const double coef = ub * kfac * (1.0 + t) * exp(-t);
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
-                if (k0 + kk < d)
-                    acc[kk] = fma(coef, Xq[int64_t(r) * d + k0 + kk] * inv_ls[k0 + kk] - XsT[(k0 + kk) * Np + i], acc[kk]);
+                if (k0 + kk < d) acc[kk] = fma(coef, s_x[k0 + kk] - XsT[(k0 + kk) * Np + i], acc[kk]);
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-            if (k0 + kk < d) {
-                double v = warp_sum(acc[kk]);
-                if (lane == 0) {
-                    // candidate-vs-candidate kernel entries (the diagonal of K_qq is a constant)
-                    for (int k = 0; k < q; ++k) {
-                        if (k == j) continue;
-                        double r2 = 0.0;
-                        for (int e = 0; e < d; ++e) {
-                            double df = (Xq[int64_t(r) * d + e] - Xq[int64_t(c * q + k) * d + e]) * inv_ls[e];
-                            r2 = fma(df, df, r2);
-                        }
-                        const double t = kSqrt5 * sqrt(fmax(r2, 1e-30));
-                        const double dfk = (Xq[int64_t(r) * d + k0 + kk] - Xq[int64_t(c * q + k) * d + k0 + kk]) * inv_ls[k0 + kk];
-                        v = fma(adj[2 + k] * kfac * (1.0 + t) * exp(-t), dfk, v);
-                    }
-                    dX[int64_t(r) * d + k0 + kk] = v * inv_ls[k0 + kk];
-                }
-            }
+            double v = warp_sum(acc[kk]);
+            if (lane == 0) s_red[warp][kk] = v;
         }
+        __syncthreads();
+        if (tid < 8 && k0 + tid < d) {
+            const int kd = k0 + tid;
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < RBQ_THREADS / 32; ++w) v += s_red[w][tid];
+            // candidate-vs-candidate kernel entries (the diagonal of K_qq is a constant)
+            for (int k = 0; k < q; ++k) {
+                if (k == j) continue;
+                double r2 = 0.0;
+                for (int e = 0; e < d; ++e) {
+                    double df = s_x[e] - Xq[int64_t(c * q + k) * d + e] * inv_ls[e];
+                    r2 = fma(df, df, r2);
+                }
+                const double t = kSqrt5 * sqrt(fmax(r2, 1e-30));
+                const double dfk = s_x[kd] - Xq[int64_t(c * q + k) * d + kd] * inv_ls[kd];
+                v = fma(s_adj[2 + k] * kfac * (1.0 + t) * exp(-t), dfk, v);
+            }
+            dX[int64_t(r) * d + kd] = v * inv_ls[kd];
+        }
+        __syncthreads();
     }
 }
 
