@@ -426,7 +426,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
         {
             TimeScope ts_(T_ROWS, s, ratio ? 2 : 1);
             CBO_CUDA(cbo::launch_kernel_rows(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->mean,
-                                             gp->alpha, w.T, Sp, w.UW, w.mu, w.ut, num_sms(), s));
+                                             gp->alpha, w.T, Sp, w.UW, w.mu, w.ut, num_sms(), s, splitk != nullptr));
             if (ratio)
                 CBO_CUDA(cbo::launch_ratio_mlp(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2, ratio->b2,
                                                ratio->W3, ratio->b3, 1e-6, w.drc, num_sms(), s));
@@ -529,12 +529,14 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             }
             {
                 TimeScope ts_(T_ROWS_BWD, s, ratio ? 2 : 1);
-                if (q == 1)
+                if (q == 1 && splitk == nullptr)
                     CBO_CUDA(cbo::launch_rows_bwd(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->alpha, rhs,
                                                   w.UW, w.adj, dX + c0 * q * d, num_sms(), s));
-                else
+                else    // joint batches, and q = 1 calls with a handful of candidates (CTA per candidate point)
                     cbo::k_rows_bwd_q<<<n, cbo::RBQ_THREADS, 0, s>>>(Xc, n, q, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale,
-                                                                 gp->alpha, rhs, w.UW, w.adj, dX + c0 * q * d);
+                                                                 gp->alpha, rhs, w.UW, w.adj,
+                                                                 q == 1 ? cbo::ADJ_STRIDE : cbo::ADJQ_STRIDE, q == 1 ? 1 : 0,
+                                                                 dX + c0 * q * d);
                 if (ratio)
                     CBO_CUDA(cbo::launch_ratio_mlp_bwd(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2,
                                                        ratio->b2, ratio->W3, ratio->b3, 1e-6, w.adj,

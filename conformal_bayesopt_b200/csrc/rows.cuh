@@ -170,6 +170,64 @@ k_kernel_rows(const double* __restrict__ Xq, int n, const double* __restrict__ X
     }
 }
 
+// A handful of candidate points per call (the SGLD regime): one CTA (256 threads) per candidate point, the train points
+// spread over its 8 warps (latency instead of throughput; no staging).  Same outputs as k_kernel_rows.
+constexpr int ROWS_SMALL_THREADS = 256;
+__global__ void __launch_bounds__(ROWS_SMALL_THREADS)
+k_kernel_rows_small(const double* __restrict__ Xq, int n, const double* __restrict__ XsT, int N, int Np, int d,
+                    const double* __restrict__ inv_ls, double outputscale, double mean, const double* __restrict__ alpha,
+                    const double* __restrict__ T, int Sp, double* __restrict__ U, double* __restrict__ mu,
+                    double* __restrict__ ut) {
+    __shared__ double s_x[MAX_D], s_tab[16], s_red[ROWS_SMALL_THREADS / 32][1 + MAX_SP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x;
+    if (tid < 16) s_tab[tid] = exp2(double(tid) / 16.0);
+    if (tid < d) s_x[tid] = Xq[int64_t(c) * d + tid] * inv_ls[tid];
+    __syncthreads();
+    const bool want_ut = (T != nullptr) && (ut != nullptr);
+    double acc_mu = 0.0, acc_ut[MAX_SP];
+#pragma unroll
+    for (int s = 0; s < MAX_SP; ++s) acc_ut[s] = 0.0;
+    for (int i = tid; i < Np; i += ROWS_SMALL_THREADS) {
+        double kv = 0.0;
+        if (i < N) {
+            double r2 = 0.0;
+            for (int k = 0; k < d; ++k) {
+                double df = s_x[k] - XsT[k * Np + i];
+                r2 = fma(df, df, r2);
+            }
+            double t = kSqrt5 * sqrt_fast(fmax(r2, 1e-30));
+            double pm = fma(fma(t, 1.0 / 3.0, 1.0), t, 1.0);
+            kv = (outputscale * exp_neg_fast(t, s_tab)) * pm;
+            acc_mu = fma(kv, alpha[i], acc_mu);
+            if (want_ut) {
+#pragma unroll
+                for (int s = 0; s < MAX_SP; ++s)
+                    if (s < Sp) acc_ut[s] = fma(kv, T[int64_t(i) * Sp + s], acc_ut[s]);
+            }
+        }
+        U[int64_t(c) * Np + i] = kv;
+    }
+    acc_mu = warp_sum(acc_mu);
+    if (lane == 0) s_red[warp][0] = acc_mu;
+    if (want_ut) {
+#pragma unroll
+        for (int s = 0; s < MAX_SP; ++s)
+            if (s < Sp) {
+                double v = warp_sum(acc_ut[s]);
+                if (lane == 0) s_red[warp][1 + s] = v;
+            }
+    }
+    __syncthreads();
+    if (tid <= (want_ut ? Sp : 0)) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < ROWS_SMALL_THREADS / 32; ++w) v += s_red[w][tid];
+        if (tid == 0) { if (mu != nullptr) mu[c] = mean + v; }
+        else ut[int64_t(c) * Sp + tid - 1] = v;
+    }
+}
+
 inline size_t rows_smem_bytes(int Np, int d, int Sp, bool stage) {
     return sizeof(double) * (16 + size_t(ROWS_WARPS) * ROWS_CPW * d + (stage ? size_t(Np) * (d + 1 + Sp) : 0));
 }
@@ -197,7 +255,12 @@ inline cudaError_t launch_kernel_rows_t(const double* Xq, int n, const double* X
 inline cudaError_t launch_kernel_rows(const double* Xq, int n, const double* XsT, int N, int Np, int d,
                                       const double* inv_ls, double outputscale, double mean, const double* alpha,
                                       const double* T, int Sp, double* U, double* mu, double* ut, int num_sms,
-                                      cudaStream_t st) {
+                                      cudaStream_t st, bool small_call = false) {
+    if (small_call) {   // decided per CALL by the API (<= 32 candidate points), never per chunk
+        k_kernel_rows_small<<<n, ROWS_SMALL_THREADS, 0, st>>>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, mean, alpha, T, Sp, U,
+                                                              mu, ut);
+        return cudaGetLastError();
+    }
     const bool stage = rows_smem_bytes(Np, d, (T && ut) ? Sp : 0, true) <= 220 * 1024;
 #define CBO_ROWS_DISPATCH(ST, NS) \
     return launch_kernel_rows_t<ST, NS>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, mean, alpha, T, Sp, U, mu, ut, num_sms, st)

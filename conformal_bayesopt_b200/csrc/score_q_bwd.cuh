@@ -727,14 +727,18 @@ __global__ void __launch_bounds__(RBQ_THREADS)
 k_rows_bwd_q(const double* __restrict__ Xq, int rows, int q, const double* __restrict__ XsT, int N, int Np, int d,
              const double* __restrict__ inv_ls, double outputscale, const double* __restrict__ alpha,
              const double* __restrict__ Aw, const double* __restrict__ W, const double* __restrict__ adjq,
-             double* __restrict__ dX) {
+             int adj_stride, int q1_layout, double* __restrict__ dX) {
+    // q1_layout: the adjoint record of k_score_bwd ({mu_bar, s_bar, ...}; Ssym = 2 s_bar) instead of k_score_q_bwd's
     __shared__ double s_x[MAX_D], s_red[RBQ_THREADS / 32][8], s_adj[2 + MAX_Q];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = blockIdx.x;
     if (r >= rows) return;
     const int c = r / q, j = r - c * q;
     if (tid < d) s_x[tid] = Xq[int64_t(r) * d + tid] * inv_ls[tid];
-    if (tid < 2 + MAX_Q) s_adj[tid] = adjq[int64_t(r) * ADJQ_STRIDE + tid];
+    if (tid < 2 + MAX_Q) {
+        const double* a = adjq + int64_t(r) * adj_stride;
+        s_adj[tid] = q1_layout ? (tid == 0 ? a[0] : (tid == 2 ? 2.0 * a[1] : 0.0)) : a[tid];
+    }
     __syncthreads();
     const double mu_bar = s_adj[0];
     const double kfac = -(5.0 / 3.0) * outputscale;
