@@ -34,8 +34,8 @@ struct ScoreQArgs {
 };
 
 __host__ __device__ inline size_t score_q_smem_bytes(int Np, int G, int Q) {
-    // per-i tables: lv, ap, dr, wp[Q] | per-(g,j): mask, opt, dev | per-g: logp | small scratch
-    return sizeof(double) * (size_t(3 + Q) * Np + size_t(3 * Q + 1) * G + 512);
+    // per-i tables: lv, ap, dr, wp[Q] | per-(g,j): mask, opt, dev, thr, cnt, sr, sw | per-g: logp | small scratch
+    return sizeof(double) * (size_t(3 + Q) * Np + size_t(7 * Q + 1) * G + 512);
 }
 
 template <int Q>
@@ -123,7 +123,11 @@ k_score_q(const ScoreQArgs pq) {
     double* g_mask = s_wp + size_t(Q) * Np;  // G x Q
     double* g_opt = g_mask + size_t(Q) * G;  // G x Q
     double* g_dev = g_opt + size_t(Q) * G;   // G x Q
-    double* g_lp = g_dev + size_t(Q) * G;    // G
+    double* g_thr = g_dev + size_t(Q) * G;   // G x Q   candidate scores; raw sums of phase B until phase C has run
+    double* g_cnt = g_thr + size_t(Q) * G;
+    double* g_sr = g_cnt + size_t(Q) * G;
+    double* g_sw = g_sr + size_t(Q) * G;
+    double* g_lp = g_sw + size_t(Q) * G;     // G
     double* sc = g_lp + G;                   // scratch: 512 doubles
     double* red = sc;                        // [4]
     double* s_S = sc + 8;                    // Q x Q
@@ -313,47 +317,61 @@ k_score_q(const ScoreQArgs pq) {
                 sw[j] = warp_sum(sw[j]);
                 if (SOFT) sr[j] = warp_sum(sr[j]);
             }
-            if (lane == 0) {
-                double lp = -0.5 * (e2 + logdet + double(Q) * kLog2Pi);
-                g_lp[g] = bad ? nan("") : lp;
-                if (p.logp) p.logp[int64_t(c) * G + g] = bad ? nan("") : lp;
+            if (lane == 0) {           // raw sums only: the per-(grid point, column) epilogue runs thread-parallel below
+                g_lp[g] = e2;
 #pragma unroll
                 for (int j = 0; j < Q; ++j) {
-                    // rows of the q candidates themselves (weights zero except the own row, counted in n_g and sum rho)
-                    int n_g = cnt[j];
-                    double srj = sr[j];
-#pragma unroll
-                    for (int k = 0; k < Q; ++k) {
-                        double dd = thr[j] - thr[k];
-                        n_g += (dd >= 0.0) ? 1 : 0;
-                        if (SOFT) srj += sigmoid_acc(fmin(fmax(dd * inv_temp, -745.0), 745.0));
-                    }
-                    double M, rho_self;
-                    if (SOFT) {
-                        double scale = double(n_g) / srj;
-                        rho_self = 0.5 * scale;
-                        M = scale * (sw[j] + 0.5 * drc[j]) / norm[j];
-                    } else {
-                        rho_self = 1.0;
-                        M = (sw[j] + drc[j]) / norm[j];
-                    }
-                    if (p.randomized) {
-                        double D = (j == Q - 1) ? fmax(rho_self * omega[j], 1e-6) : 1e-6;     // helpers.py:307: last row only
-                        double pr = fmin(fmax((M - p.alpha_lvl) / D, 0.0), 1.0);
-                        double u = p.u_rand[(int64_t(c) * G + g) * Q + j];
-                        M -= (u < pr) ? 0.0 : D;
-                    }
-                    double mk = SOFT ? sigmoid_acc((M - p.alpha_lvl) * inv_temp) : ((M > p.alpha_lvl) ? 1.0 : 0.0);
-                    double yg = mu[j] + dev[j];
-                    if (bad) mk = nan("");
-                    g_mask[g * Q + j] = mk;
-                    g_opt[g * Q + j] = p.optimistic ? ((yg >= mu[j]) ? 1.0 : 0.0) : 1.0;
-                    g_dev[g * Q + j] = dev[j];
-                    if (p.grid) p.grid[(int64_t(c) * G + g) * Q + j] = yg;
-                    if (p.mask) p.mask[(int64_t(c) * G + g) * Q + j] = mk;
-                    if (p.qscore) p.qscore[(int64_t(c) * G + g) * Q + j] = bad ? nan("") : thr[j];
+                    const int o = g * Q + j;
+                    g_dev[o] = dev[j]; g_thr[o] = thr[j]; g_cnt[o] = double(cnt[j]); g_sr[o] = sr[j]; g_sw[o] = sw[j];
                 }
             }
+        }
+        __syncthreads();
+        // ---- phase C: thread per (grid point, column) ------------------------------------------------------------------------
+        for (int o = tid; o < G * Q; o += SQ_THREADS) {
+            const int g = o / Q, j = o - g * Q;
+            // rows of the q candidates themselves (weights zero except the own row, counted in n_g and sum rho)
+            int n_g = int(g_cnt[o]);
+            double srj = g_sr[o];
+            const double thr_j = g_thr[o], sw_j = g_sw[o];
+            for (int k = 0; k < Q; ++k) {
+                double dd = thr_j - g_thr[g * Q + k];
+                n_g += (dd >= 0.0) ? 1 : 0;
+                if (SOFT) srj += sigmoid_acc(fmin(fmax(dd * inv_temp, -745.0), 745.0));
+            }
+            double drc_j = drc[0], norm_j = norm[0], omega_j = omega[0], mu_j = mu[0];
+#pragma unroll
+            for (int k = 1; k < Q; ++k)
+                if (k == j) { drc_j = drc[k]; norm_j = norm[k]; omega_j = omega[k]; mu_j = mu[k]; }
+            double M, rho_self;
+            if (SOFT) {
+                double scale = double(n_g) / srj;
+                rho_self = 0.5 * scale;
+                M = scale * (sw_j + 0.5 * drc_j) / norm_j;
+            } else {
+                rho_self = 1.0;
+                M = (sw_j + drc_j) / norm_j;
+            }
+            if (p.randomized) {
+                double D = (j == Q - 1) ? fmax(rho_self * omega_j, 1e-6) : 1e-6;     // helpers.py:307: last row only
+                double pr = fmin(fmax((M - p.alpha_lvl) / D, 0.0), 1.0);
+                double u = p.u_rand[(int64_t(c) * G + g) * Q + j];
+                M -= (u < pr) ? 0.0 : D;
+            }
+            double mk = SOFT ? sigmoid_acc((M - p.alpha_lvl) * inv_temp) : ((M > p.alpha_lvl) ? 1.0 : 0.0);
+            const double dv = g_dev[o];
+            double yg = mu_j + dv;
+            if (bad) mk = nan("");
+            g_mask[o] = mk;
+            g_opt[o] = p.optimistic ? ((yg >= mu_j) ? 1.0 : 0.0) : 1.0;
+            if (p.grid) p.grid[(int64_t(c) * G + g) * Q + j] = yg;
+            if (p.mask) p.mask[(int64_t(c) * G + g) * Q + j] = mk;
+            if (p.qscore) p.qscore[(int64_t(c) * G + g) * Q + j] = bad ? nan("") : thr_j;
+        }
+        for (int g = tid; g < G; g += SQ_THREADS) {       // g_lp is not read by the loop above
+            double lp = -0.5 * (g_lp[g] + logdet + double(Q) * kLog2Pi);
+            g_lp[g] = bad ? nan("") : lp;
+            if (p.logp) p.logp[int64_t(c) * G + g] = bad ? nan("") : lp;
         }
         __syncthreads();
 

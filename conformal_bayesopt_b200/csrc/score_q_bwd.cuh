@@ -290,48 +290,63 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                 sw[j] = warp_sum(sw[j]);
                 if (SOFT) sr[j] = warp_sum(sr[j]);
             }
-            if (lane == 0) {
-                double lp = -0.5 * (e2 + logdet + double(Q) * kLog2Pi);
-                g_kd[g] = 1.0 / fmax(exp(lp), 1e-6);
+            if (lane == 0) {           // raw sums only: the per-(grid point, column) epilogue runs thread-parallel below
+                g_kd[g] = e2;
 #pragma unroll
                 for (int j = 0; j < Q; ++j) {
-                    int n_g = cnt[j];
-                    double srj = sr[j];
-#pragma unroll
-                    for (int k = 0; k < Q; ++k) {
-                        double dd = thr[j] - thr[k];
-                        n_g += (dd >= 0.0) ? 1 : 0;
-                        if (SOFT) srj += sigmoid_acc(fmin(fmax(dd * inv_temp, -745.0), 745.0));
-                    }
-                    double M, rho_self, scale = 0.0;
-                    if (SOFT) {
-                        scale = double(n_g) / srj;
-                        rho_self = 0.5 * scale;
-                        M = scale * (sw[j] + 0.5 * drc[j]) / norm[j];
-                    } else {
-                        rho_self = 1.0;
-                        M = (sw[j] + drc[j]) / norm[j];
-                    }
-                    const double Mraw = M;
-                    double kl = 0.0;
-                    if (p.randomized) {
-                        double Dr = rho_self * omega[j];
-                        double D = (j == Q - 1) ? fmax(Dr, 1e-6) : 1e-6;
-                        double pr = fmin(fmax((M - alpha_lvl) / D, 0.0), 1.0);
-                        double u = p.u_rand[(int64_t(c) * G + g) * Q + j];
-                        bool keep = !(u < pr);
-                        M -= keep ? D : 0.0;
-                        kl = (keep && j == Q - 1 && Dr > 1e-6) ? 1.0 : 0.0;
-                    }
-                    double mk = SOFT ? sigmoid_acc((M - alpha_lvl) * inv_temp) : ((M > alpha_lvl) ? 1.0 : 0.0);
-                    double yg = mu[j] + dev[j];
                     const int o = g * Q + j;
-                    g_mask[o] = mk;
-                    g_opt[o] = p.optimistic ? ((yg >= mu[j]) ? 1.0 : 0.0) : 1.0;
-                    g_dev[o] = dev[j]; g_Bg[o] = Bg[j]; g_thr[o] = thr[j]; g_sr[o] = srj; g_sw[o] = sw[j];
-                    g_scale[o] = scale; g_kl[o] = kl; g_Mraw[o] = Mraw; g_P[o] = 0.0; g_Q[o] = 0.0;
+                    g_dev[o] = dev[j]; g_Bg[o] = Bg[j]; g_thr[o] = thr[j];
+                    g_sr[o] = sr[j]; g_sw[o] = sw[j]; g_scale[o] = double(cnt[j]);
                 }
             }
+        }
+        __syncthreads();
+        // ---- phase C: thread per (grid point, column) ------------------------------------------------------------------------
+        for (int o = tid; o < G * Q; o += SQ_THREADS) {
+            const int g = o / Q, j = o - g * Q;
+            int n_g = int(g_scale[o]);
+            double srj = g_sr[o];
+            const double thr_j = g_thr[o], sw_j = g_sw[o];
+            for (int k = 0; k < Q; ++k) {
+                double dd = thr_j - g_thr[g * Q + k];
+                n_g += (dd >= 0.0) ? 1 : 0;
+                if (SOFT) srj += sigmoid_acc(fmin(fmax(dd * inv_temp, -745.0), 745.0));
+            }
+            // per-column scalars by index (the register arrays are indexed dynamically here)
+            double drc_j = drc[0], norm_j = norm[0], omega_j = omega[0], mu_j = mu[0];
+#pragma unroll
+            for (int k = 1; k < Q; ++k)
+                if (k == j) { drc_j = drc[k]; norm_j = norm[k]; omega_j = omega[k]; mu_j = mu[k]; }
+            double M, rho_self, scale = 0.0;
+            if (SOFT) {
+                scale = double(n_g) / srj;
+                rho_self = 0.5 * scale;
+                M = scale * (sw_j + 0.5 * drc_j) / norm_j;
+            } else {
+                rho_self = 1.0;
+                M = (sw_j + drc_j) / norm_j;
+            }
+            const double Mraw = M;
+            double kl = 0.0;
+            if (p.randomized) {
+                double Dr = rho_self * omega_j;
+                double D = (j == Q - 1) ? fmax(Dr, 1e-6) : 1e-6;
+                double pr = fmin(fmax((M - alpha_lvl) / D, 0.0), 1.0);
+                double u = p.u_rand[(int64_t(c) * G + g) * Q + j];
+                bool keep = !(u < pr);
+                M -= keep ? D : 0.0;
+                kl = (keep && j == Q - 1 && Dr > 1e-6) ? 1.0 : 0.0;
+            }
+            double mk = SOFT ? sigmoid_acc((M - alpha_lvl) * inv_temp) : ((M > alpha_lvl) ? 1.0 : 0.0);
+            double yg = mu_j + g_dev[o];
+            g_mask[o] = mk;
+            g_opt[o] = p.optimistic ? ((yg >= mu_j) ? 1.0 : 0.0) : 1.0;
+            g_sr[o] = srj; g_scale[o] = scale; g_kl[o] = kl; g_Mraw[o] = Mraw; g_P[o] = 0.0; g_Q[o] = 0.0;
+        }
+        __syncthreads();
+        for (int g = tid; g < G; g += SQ_THREADS) {
+            double lp = -0.5 * (g_kd[g] + logdet + double(Q) * kLog2Pi);
+            g_kd[g] = 1.0 / fmax(exp(lp), 1e-6);
         }
         __syncthreads();
 
@@ -592,15 +607,27 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
         }
         __syncthreads();
         R.commit();
-        // C_bar_js (train part) = sum_i (+-) zdot_bar_ji: thread per (j, s)
-        if (tid < Q * Sp) {
-            const int j = tid / Sp, s = tid - j * Sp;
-            double acc = 0.0;
-            for (int i = 0; i < N; ++i) {
-                const double zb_ = s_wp[size_t(j) * Np + i];
-                acc += ((p.zb[i] >> s) & 1u) ? zb_ : -zb_;
+        // C_bar_js (train part) = sum_i (+-) zdot_bar_ji: thread = (pair (j, s), slice of the train points), then a fixed-order sum
+        {
+            const int npair = Q * Sp, nslice = SQ_THREADS / npair;               // npair <= 64
+            double* cpart = wred;                                                 // [nslice][npair]; wred is free after commit
+            __syncthreads();
+            if (tid < nslice * npair) {
+                const int pr = tid % npair, sl = tid / npair;
+                const int j = pr / Sp, s2 = pr - j * Sp;
+                double acc = 0.0;
+                for (int i = sl; i < N; i += nslice) {
+                    const double zb_ = s_wp[size_t(j) * Np + i];
+                    acc += ((p.zb[i] >> s2) & 1u) ? zb_ : -zb_;
+                }
+                cpart[sl * npair + pr] = acc;
             }
-            s_Cbar[j * MAX_SP + s] = acc;
+            __syncthreads();
+            if (tid < npair) {
+                double acc = 0.0;
+                for (int sl = 0; sl < nslice; ++sl) acc += cpart[sl * npair + tid];
+                s_Cbar[(tid / Sp) * MAX_SP + (tid % Sp)] = acc;
+            }
         }
         __syncthreads();
 
