@@ -290,23 +290,32 @@ k_score_q(const ScoreQArgs pq) {
 #pragma unroll
             for (int j = 0; j < Q; ++j) { sr[j] = 0.0; sw[j] = 0.0; cnt[j] = 0; }
             if (!bad) {
-                for (int i = lane; i < N; i += 32) {
-                    double rp = s_ap[i];
-#pragma unroll
-                    for (int j = 0; j < Q; ++j) rp = fma(-s_wp[size_t(j) * Np + i], Bg[j], rp);
-                    double sci = fma(-rp, rp, s_lv[i]);
-                    double dr = s_dr[i];
+                // two train points per lane and step (i, i + 32): 2 Q independent sigmoid chains instead of Q
+                for (int i = lane; i < N; i += 64) {
+                    const int i2 = i + 32;
+                    const bool ok2 = i2 < N;
+                    const int i2c = ok2 ? i2 : i;
+                    double rp0 = s_ap[i], rp1 = s_ap[i2c];
 #pragma unroll
                     for (int j = 0; j < Q; ++j) {
-                        double dd = thr[j] - sci;
-                        bool ge = dd >= 0.0;
-                        cnt[j] += ge ? 1 : 0;
+                        rp0 = fma(-s_wp[size_t(j) * Np + i], Bg[j], rp0);
+                        rp1 = fma(-s_wp[size_t(j) * Np + i2c], Bg[j], rp1);
+                    }
+                    const double sci0 = fma(-rp0, rp0, s_lv[i]), sci1 = fma(-rp1, rp1, s_lv[i2c]);
+                    const double dr0 = s_dr[i], dr1 = ok2 ? s_dr[i2c] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) {
+                        const double dd0 = thr[j] - sci0, dd1 = thr[j] - sci1;
+                        const bool ge0 = dd0 >= 0.0, ge1 = ok2 && (dd1 >= 0.0);
+                        cnt[j] += (ge0 ? 1 : 0) + (ge1 ? 1 : 0);
                         if (SOFT) {
-                            double rho = soft_rho<true>(dd * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
-                            sr[j] += rho;
-                            sw[j] = fma(rho, dr, sw[j]);
+                            const double rho0 = soft_rho<true>(dd0 * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
+                            double rho1 = soft_rho<true>(dd1 * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
+                            rho1 = ok2 ? rho1 : 0.0;
+                            sr[j] += rho0 + rho1;
+                            sw[j] = fma(rho0, dr0, fma(rho1, dr1, sw[j]));
                         } else {
-                            sw[j] += ge ? dr : 0.0;
+                            sw[j] += (ge0 ? dr0 : 0.0) + (ge1 ? dr1 : 0.0);
                         }
                     }
                 }

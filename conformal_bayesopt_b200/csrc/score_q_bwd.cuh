@@ -263,23 +263,32 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
 #pragma unroll
             for (int j = 0; j < Q; ++j) { sr[j] = 0.0; sw[j] = 0.0; cnt[j] = 0; }
             if (!bad) {
-                for (int i = lane; i < N; i += 32) {
-                    double rp = s_ap[i];
-#pragma unroll
-                    for (int j = 0; j < Q; ++j) rp = fma(-s_wp[size_t(j) * Np + i], Bg[j], rp);
-                    double sci = fma(-rp, rp, s_lv[i]);
-                    double dr = s_dr[i];
+                // two train points per lane and step (i, i + 32): 2 Q independent sigmoid chains instead of Q
+                for (int i = lane; i < N; i += 64) {
+                    const int i2 = i + 32;
+                    const bool ok2 = i2 < N;
+                    const int i2c = ok2 ? i2 : i;
+                    double rp0 = s_ap[i], rp1 = s_ap[i2c];
 #pragma unroll
                     for (int j = 0; j < Q; ++j) {
-                        double dd = thr[j] - sci;
-                        bool ge = dd >= 0.0;
-                        cnt[j] += ge ? 1 : 0;
+                        rp0 = fma(-s_wp[size_t(j) * Np + i], Bg[j], rp0);
+                        rp1 = fma(-s_wp[size_t(j) * Np + i2c], Bg[j], rp1);
+                    }
+                    const double sci0 = fma(-rp0, rp0, s_lv[i]), sci1 = fma(-rp1, rp1, s_lv[i2c]);
+                    const double dr0 = s_dr[i], dr1 = ok2 ? s_dr[i2c] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) {
+                        const double dd0 = thr[j] - sci0, dd1 = thr[j] - sci1;
+                        const bool ge0 = dd0 >= 0.0, ge1 = ok2 && (dd1 >= 0.0);
+                        cnt[j] += (ge0 ? 1 : 0) + (ge1 ? 1 : 0);
                         if (SOFT) {
-                            double rho = soft_rho<true>(dd * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
-                            sr[j] += rho;
-                            sw[j] = fma(rho, dr, sw[j]);
+                            const double rho0 = soft_rho<true>(dd0 * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
+                            double rho1 = soft_rho<true>(dd1 * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
+                            rho1 = ok2 ? rho1 : 0.0;
+                            sr[j] += rho0 + rho1;
+                            sw[j] = fma(rho0, dr0, fma(rho1, dr1, sw[j]));
                         } else {
-                            sw[j] += ge ? dr : 0.0;
+                            sw[j] += (ge0 ? dr0 : 0.0) + (ge1 ? dr1 : 0.0);
                         }
                     }
                 }
@@ -538,63 +547,90 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
 #pragma unroll
                 for (int k = 0; k < Q; ++k) a_t3[j][k] = a_si[j][k] = 0.0;
             }
-            for (int i = tid; i < Np; i += SQ_THREADS) {
-                if (i >= N || !SOFT || bad) {
+            // RI train points per thread are swept together: RI Q independent sigmoid chains, and the per-column totals
+            // (which depend on the grid point only) are accumulated once per grid point for all RI rows
+            constexpr int RI = (Q <= 2) ? 4 : 2;
+            for (int i0 = tid; i0 < Np; i0 += SQ_THREADS * RI) {
+                double ap[RI], lv[RI], dr[RI], siv[RI], vm[RI], wp[RI][Q], m0[RI], mrr[RI], mr[RI], mrd[RI][Q];
 #pragma unroll
-                    for (int j = 0; j < Q; ++j) {
-                        qb.wbar[int64_t(r0 + j) * Np + i] = 0.0;
-                        if (i < N) s_wp[size_t(j) * Np + i] = 0.0;
-                    }
-                    continue;
+                for (int r = 0; r < RI; ++r) {
+                    const int i = i0 + r * SQ_THREADS;
+                    const bool ok = (i < N) && SOFT && !bad;
+                    const int ic = ok ? i : 0;
+                    vm[r] = ok ? 1.0 : 0.0;
+                    ap[r] = s_ap[ic]; lv[r] = s_lv[ic]; dr[r] = s_dr[ic]; siv[r] = s_siv[ic];
+                    m0[r] = mrr[r] = mr[r] = 0.0;
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) { wp[r][j] = s_wp[size_t(j) * Np + ic]; mrd[r][j] = 0.0; }
                 }
-                const double ap = s_ap[i], lv = s_lv[i], dr = s_dr[i], siv = s_siv[i];
-                double wp[Q];
+                if (SOFT && !bad && i0 < N) {
+                    for (int g = 0; g < G; ++g) {
+                        double rp[RI], sci[RI], gam[RI];
 #pragma unroll
-                for (int j = 0; j < Q; ++j) wp[j] = s_wp[size_t(j) * Np + i];
-                double m0 = 0.0, mrr = 0.0, mr = 0.0, mrd[Q];
+                        for (int r = 0; r < RI; ++r) {
+                            rp[r] = ap[r];
 #pragma unroll
-                for (int k = 0; k < Q; ++k) mrd[k] = 0.0;
-                for (int g = 0; g < G; ++g) {
-                    double rp = ap;
+                            for (int j = 0; j < Q; ++j) rp[r] = fma(-wp[r][j], g_Bg[g * Q + j], rp[r]);
+                            sci[r] = fma(-rp[r], rp[r], lv[r]);
+                            gam[r] = 0.0;
+                        }
 #pragma unroll
-                    for (int j = 0; j < Q; ++j) rp = fma(-wp[j], g_Bg[g * Q + j], rp);
-                    const double sci = fma(-rp, rp, lv);
-                    double gam = 0.0;
+                        for (int j = 0; j < Q; ++j) {
+                            const int o = g * Q + j;
+                            const double thr_j = g_thr[o], Pj = g_P[o], Qj = g_Q[o];
+                            double gsum = 0.0;
 #pragma unroll
-                    for (int j = 0; j < Q; ++j) {
-                        const int o = g * Q + j;
-                        const double dd = g_thr[o] - sci;
-                        const double rho = soft_rho<true>(dd * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
-                        const double gj_ = fma(g_P[o], dr, g_Q[o]) * fma(-rho, rho, rho);
-                        gam += gj_;
-                        const double Bj = g_Bg[o];
-                        a_t1[j] += gj_; a_t2[j] = fma(gj_ * Bj, Bj, a_t2[j]); a_t4[j] = fma(gj_, Bj, a_t4[j]);
+                            for (int r = 0; r < RI; ++r) {
+                                const double rho = soft_rho<true>((thr_j - sci[r]) * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
+                                const double gj_ = vm[r] * fma(Pj, dr[r], Qj) * fma(-rho, rho, rho);
+                                gam[r] += gj_;
+                                gsum += gj_;
+                            }
+                            const double Bj = g_Bg[o], gB = gsum * Bj;
+                            a_t1[j] += gsum; a_t2[j] = fma(gB, Bj, a_t2[j]); a_t4[j] += gB;
 #pragma unroll
-                        for (int k = 0; k < Q; ++k) a_t3[j][k] = fma(gj_ * Bj, g_dev[g * Q + k], a_t3[j][k]);
+                            for (int k = 0; k < Q; ++k) a_t3[j][k] = fma(gB, g_dev[g * Q + k], a_t3[j][k]);
+                        }
+#pragma unroll
+                        for (int r = 0; r < RI; ++r) {
+                            const double grp = gam[r] * rp[r];
+                            m0[r] += gam[r]; mrr[r] = fma(grp, rp[r], mrr[r]); mr[r] += grp;
+#pragma unroll
+                            for (int k = 0; k < Q; ++k) mrd[r][k] = fma(grp, g_dev[g * Q + k], mrd[r][k]);
+                        }
                     }
-                    const double grp = gam * rp;
-                    m0 += gam; mrr = fma(grp, rp, mrr); mr += grp;
-#pragma unroll
-                    for (int k = 0; k < Q; ++k) mrd[k] = fma(grp, g_dev[g * Q + k], mrd[k]);
                 }
                 // per-train-point epilogue
-                const double iv = siv * siv;
-                const double var_bar = iv * (m0 - 2.0 * mrr);                     // -2 iv^2 (mrr/iv) - iv (-m0)
-                const double vk = var_bar * noise * kvar;
-                const uint32_t bits = p.zb[i];
 #pragma unroll
-                for (int j = 0; j < Q; ++j) {
-                    double mrB = 0.0;
+                for (int r = 0; r < RI; ++r) {
+                    const int i = i0 + r * SQ_THREADS;
+                    if (i >= Np) continue;
+                    if (vm[r] == 0.0) {
 #pragma unroll
-                    for (int k = 0; k < Q; ++k) mrB = fma(s_Sinv[j * Q + k], mrd[k], mrB);
-                    double zdot = 0.0;
-                    for (int s = 0; s < Sp; ++s) zdot += ((bits >> s) & 1u) ? s_C[j * MAX_SP + s] : -s_C[j * MAX_SP + s];
-                    const double w_ji = wp[j] / (noise * siv);
-                    qb.wbar[int64_t(r0 + j) * Np + i] = fma(vk, zdot, -2.0 * noise * siv * mrB);
-                    s_wp[size_t(j) * Np + i] = vk * w_ji;                           // zdot_bar_ji (this row's table entry is dead)
-                    a_bs[j] = fma(-2.0 * wp[j], mr, a_bs[j]);
+                        for (int j = 0; j < Q; ++j) {
+                            qb.wbar[int64_t(r0 + j) * Np + i] = 0.0;
+                            if (i < N) s_wp[size_t(j) * Np + i] = 0.0;
+                        }
+                        continue;
+                    }
+                    const double iv = siv[r] * siv[r];
+                    const double var_bar = iv * (m0[r] - 2.0 * mrr[r]);           // -2 iv^2 (mrr/iv) - iv (-m0)
+                    const double vk = var_bar * noise * kvar;
+                    const uint32_t bits = p.zb[i];
 #pragma unroll
-                    for (int k = 0; k < Q; ++k) a_si[j][k] = fma(-2.0 * wp[j], mrd[k], a_si[j][k]);
+                    for (int j = 0; j < Q; ++j) {
+                        double mrB = 0.0;
+#pragma unroll
+                        for (int k = 0; k < Q; ++k) mrB = fma(s_Sinv[j * Q + k], mrd[r][k], mrB);
+                        double zdot = 0.0;
+                        for (int s = 0; s < Sp; ++s) zdot += ((bits >> s) & 1u) ? s_C[j * MAX_SP + s] : -s_C[j * MAX_SP + s];
+                        const double w_ji = wp[r][j] / (noise * siv[r]);
+                        qb.wbar[int64_t(r0 + j) * Np + i] = fma(vk, zdot, -2.0 * noise * siv[r] * mrB);
+                        s_wp[size_t(j) * Np + i] = vk * w_ji;                       // zdot_bar_ji (this row's table entry is dead)
+                        a_bs[j] = fma(-2.0 * wp[r][j], mr[r], a_bs[j]);
+#pragma unroll
+                        for (int k = 0; k < Q; ++k) a_si[j][k] = fma(-2.0 * wp[r][j], mrd[r][k], a_si[j][k]);
+                    }
                 }
             }
 #pragma unroll
