@@ -32,7 +32,7 @@ FLOP_PER_EVAL = 51811.0            # algorithmic fp64 flop per (
 GEMM_FLOP_PER_CAND_PASS = float(N_TRAIN) * N_TRAIN      # one triangular solve pass: N^2 flop (N^2/2 FMA)
 SCORE_FLOP_PER_EVAL = 17.0 * (N_TRAIN + 1)              # SURVEY.md §8d per-(cand,grid) term
 FP64_PEAK_TFLOPS = 37.0            # measured on this pool's B200 (profiles/r01_fp64_peak.log): DMMA.8x8x4 = whole fp64 pipe
-NCU_DRAM_BYTES_PER_LAUNCH = {"score_rank_integrate": 550.4e6, "gemm_pass1_dmma": 2958.3e6, "gemm_pass2_dmma": 2926.3e6,
+NCU_DRAM_BYTES_PER_LAUNCH = {"score_rank_integrate": 550.4e6, "gemm_pass1_dmma": 1401.7e6, "gemm_pass2_dmma": 1399.6e6,
                              "kernel_rows": 488.5e6}         # profiles/r01_ncu_summary.txt (dram__bytes_read + write per launch of 65536 candidates)
 BYTES_PER_EVAL = (8 * DIM + 8) / GRID                   # SURVEY.md §8d algorithmic HBM bytes per eval (no mask output)
 
