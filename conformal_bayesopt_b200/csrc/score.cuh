@@ -10,7 +10,7 @@
 //              x_i(g) = c1 (score_c(g) - score_i(g)) = (qa_i b_g + qb_i) b_g + qc_i,  c1 = 16/(temp ln 2)
 //            -> pair-private shared-memory tables qa, qb, qc
 //   phase B  4 grid points per pass, every train point: hard count, soft-rank sigmoid and the
-//            weighted sums (A-3, A-5) -- the hot loop: 14 fp64-pipe instructions per
+//            weighted sums (A-3, A-5) -- the hot loop: 11 fp64-pipe instructions (13 with a ratio estimator) per
 //            (train point, grid point), 4 independent dependency chains per lane, 16 warps per SM
 //   phase C  (thread per grid point) weighted mass, randomised step, conformal mask, log-density,
 //            optimistic mask, refit mean (A-5, A-6)

@@ -12,7 +12,7 @@
 //               Delta_ig = A_i b_g^2 + B_i b_g + C_i, the three moments carry everything: d acq/d(A_i,B_i,C_i) =
 //               (E_2, E_1, E_0) and sum_g b_bar_g b_g^m = sum_i (2 A_i E_{m+1} + B_i E_m).  A thread owns 4 train points
 //               (registers) and loops over the grid (per-grid record broadcast from shared memory): no atomics, no
-//               cross-lane traffic in the loop; ~17 fp64-pipe instructions per (train point, grid point).
+//               cross-lane traffic in the loop; 15 fp64-pipe instructions per (train point, grid point).
 //   epilogue    per train point: w_bar_i (written as one row of `wbar`, the right-hand side of the A^-1 solve done by
 //               the same two triangular GEMMs as the forward pass); per candidate: mu_bar, s_bar, drc_bar, ut_bar.
 // oracle/analytic_grad.py is the line-by-line CPU restatement of this algebra (checked against torch.autograd).
@@ -24,7 +24,6 @@ namespace cbo {
 constexpr int SB_RI = 2;              // train points per thread in pass 2 ...
 constexpr int SB_GI = 2;              // ... times grid points per step = independent dependency chains per thread
 constexpr int SB_GARR = 12;           // per-grid arrays
-constexpr int SB_PART = 24;           // doubles per warp of partial sums (4 + 6 + 4 + MAX_SP <= 32 is split in 2 regions)
 constexpr int ADJ_STRIDE = 4 + MAX_SP;   // adj[c] = {mu_bar, s_bar, drc_bar, -, ut_bar[Sp]}
 
 struct ScoreBwdArgs {

@@ -100,8 +100,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
     double* s_A = s_misc + 16;               // [MAX_S][MAX_Q]  A_sj
     double* s_B = s_A + MAX_S * MAX_Q;       // [MAX_S][MAX_Q]
     double* s_kap = s_B + MAX_S * MAX_Q;     // [MAX_S][MAX_Q]  d acq / d res_sj
-    double* s_col = s_kap + MAX_S * MAX_Q;   // [4][MAX_Q]: dcw, dnc, ood, live flags packed (cw live + 2 nc live)
-    double* s_Cbar = s_col + 4 * MAX_Q;      // Q x MAX_SP
+    double* s_Cbar = s_kap + MAX_S * MAX_Q;  // Q x MAX_SP
     double* s_utb = s_Cbar + MAX_Q * MAX_SP; // Q x MAX_SP
     double* wred = sc + 1024;                // [SQ_WARPS][SQB_NT]
     double* tot = wred + SQ_WARPS * SQB_NT;  // [SQB_NT]

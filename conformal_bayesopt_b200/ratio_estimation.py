@@ -1,7 +1,7 @@
 """Density-ratio estimator, inference side (reference: conformalbo/ratio_estimation.py:60-107).
 
 `forward` -- the part on the acquisition hot path (ratio_estimation.py:97-99) -- runs in the CUDA
-kernel `k_ratio_mlp` when the input is on a CUDA device; the acquisition kernels themselves consume
+kernel `k_ratio_mlp_mma` (fp64 tensor path) when the input is on a CUDA device; the acquisition kernels themselves consume
 the target-network weights directly (no per-candidate Python call).  Online training of the
 classifier (`optimize_callback`, `_Dataset`; ratio_estimation.py:110-144) is out of scope
 (SURVEY.md §2 #5): the EMA update of the target network is provided so that externally trained
