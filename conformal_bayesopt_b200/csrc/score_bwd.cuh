@@ -10,7 +10,7 @@
 //   pass 2      second sweep over (train point, grid point): Gamma_ig = (P_g dr_i + Q_g) rho_ig (1 - rho_ig) / temp,
 //               E_k,i = sum_g Gamma_ig b_g^k, k = 0,1,2.  Because the score difference is the quadratic
 //               Delta_ig = A_i b_g^2 + B_i b_g + C_i, the three moments carry everything: d acq/d(A_i,B_i,C_i) =
-//               (E_2, E_1, E_0) and sum_g b_bar_g b_g^m = sum_i (2 A_i E_{m+1} + B_i E_m).  A thread owns 4 train points
+//               (E_2, E_1, E_0) and sum_g b_bar_g b_g^m = sum_i (2 A_i E_{m+1} + B_i E_m).  A thread owns 2 train points
 //               (registers) and loops over the grid (per-grid record broadcast from shared memory): no atomics, no
 //               cross-lane traffic in the loop; 15 fp64-pipe instructions per (train point, grid point).
 //   epilogue    per train point: w_bar_i (written as one row of `wbar`, the right-hand side of the A^-1 solve done by
