@@ -284,3 +284,26 @@ def test_grad_edge_shapes(N, d, b, G, Sp, H):
     got = _gpu(p, inp, dev, rw, **kw)
     assert torch.allclose(got["acq"], acq, rtol=1e-6, atol=1e-9)
     assert _grad_close(got["dacq_dX"], g)
+
+
+@pytest.mark.parametrize("q,b", [(1, 8), (1, 3000), (2, 8), (2, 300), (4, 40)])
+def test_repeated_calls_are_bitwise_identical(q, b):
+    """No atomics, fixed reduction orders: the same call gives the same bits (values and gradient rows), also across the
+    latency path (<= 32 candidate points: split-K GEMM, CTA-per-point kernels) and the throughput path."""
+    from conformal_bayesopt_b200 import ops
+    dev = _dev()
+    N, d, G = 300, 5, 48
+    p = make_problem(N, d, seed=1)
+    inp = make_inputs(N, d, b, q, G, S=2, seed=2)
+    _, rw = _ratio(d, dev)
+    st = _state(p, dev)
+    kw = dict(kind="ucb", alpha=0.1, temp=3e-2, grid_res=G, randomized=True, optimistic=True, beta_prime=1.0)
+    outs = []
+    for _ in range(3):
+        o = ops.conformal_acq(st, inp["Xq"].to(dev), eps_grid=inp["eps_grid"].to(dev), z=inp["z"].to(dev),
+                              eps_mc=inp["eps_mc"].to(dev), u_rand=inp["u_rand"].to(dev), ratio=rw, want_grad=True, **kw)
+        torch.cuda.synchronize()
+        outs.append((o["acq"].cpu().clone(), o["dacq_dX"].cpu().clone()))
+    for a, g in outs[1:]:
+        assert torch.equal(a, outs[0][0]) and torch.equal(g, outs[0][1])
+    assert torch.isfinite(outs[0][1]).all()
