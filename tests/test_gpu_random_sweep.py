@@ -1,6 +1,7 @@
 """Seeded random sweep over shapes and flags: values AND gradient rows of the CUDA path against the closed-form oracle
 (autograd).  Complements the hand-picked cases of test_gpu_parity.py / test_gpu_grad.py."""
 import math
+import os
 import random
 
 import pytest
@@ -29,7 +30,7 @@ def _cases(n=28, seed=1234):
     return out
 
 
-@pytest.mark.parametrize("c", _cases(), ids=lambda c: f"{c['i']}-q{c['q']}-N{c['N']}-d{c['d']}-b{c['b']}-G{c['G']}")
+@pytest.mark.parametrize("c", _cases(int(os.environ.get("CBO_SWEEP_CASES", "28")), int(os.environ.get("CBO_SWEEP_SEED", "1234"))), ids=lambda c: f"{c['i']}-q{c['q']}-N{c['N']}-d{c['d']}-b{c['b']}-G{c['G']}")
 def test_random_case_value_and_gradient(c):
     from conformal_bayesopt_b200 import GPModelState, ops
     from conformal_bayesopt_b200.synthetic import make_inputs as mk
