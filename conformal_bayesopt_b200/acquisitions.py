@@ -68,6 +68,9 @@ class ConformalAcquisition(nn.Module):
         self.set_X_pending(X_pending)
         self.fixed_probes: Optional[torch.Tensor] = None      # inject z; None: fresh CPU draw per call
         self.fixed_uniforms: Optional[torch.Tensor] = None    # inject the Bernoulli uniforms (App. C-3)
+        # candidate-sharded scoring with max_grid_refinements > 0: distributed.refine_reducer() makes the refinement
+        # decisions batch-global again; None: per-call statistics
+        self.refine_reduce = None
         self.last_outputs = {}
 
     def set_X_pending(self, X_pending=None):
@@ -118,6 +121,7 @@ class ConformalAcquisition(nn.Module):
             u = torch.rand(b, G, q, dtype=torch.float64, device=dev)
         out = ops.conformal_acq(state, Xf, eps_grid=eps, z=z, eps_mc=eps_mc, u_rand=u,
                                 ratio=_ratio_weights(self.ratio_estimator, dev), outputs=outputs, want_grad=want_grad,
+                                refine_reduce=self.refine_reduce if self.max_grid_refinements > 0 else None,
                                 alpha=self.alpha, temp=self.temp, grid_res=G,
                                 max_grid_refinements=self.max_grid_refinements, randomized=self.randomized,
                                 optimistic=self.optimistic, **self._acq_params())

@@ -128,7 +128,8 @@ Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, 
     return w;
 }
 
-// min / max / sum((n/G - 1/2)^2) of the accepted counts, in float like the reference (helpers.py:150-155)
+// min / max / sum((n/G - 1/2)^2) of the accepted counts, in float like the reference (helpers.py:150-155); the host divides
+// by the batch size (after the optional cross-rank reduction)
 __global__ void k_accept_stats(const double* __restrict__ nacc, int b, int G, double* __restrict__ stats) {
     __shared__ float smin[256], smax[256], ssum[256];
     float mn = 3.4e38f, mx = -3.4e38f, sm = 0.f;
@@ -148,7 +149,7 @@ __global__ void k_accept_stats(const double* __restrict__ nacc, int b, int G, do
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { stats[0] = smin[0]; stats[1] = smax[0]; stats[2] = ssum[0] / (float)b; }
+    if (threadIdx.x == 0) { stats[0] = smin[0]; stats[1] = smax[0]; stats[2] = ssum[0]; }
 }
 
 // covar_scale = 1 + sign(diff) |diff|^(2/q) in float (helpers.py:153-167), accumulated into the grid covariance scale
@@ -565,10 +566,14 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 pa.num_acc = w.nacc;
                 CBO_CUDA(run_score(pa));
                 k_accept_stats<<<1, 256, 0, s>>>(w.nacc, n, G, w.stats);
-                double hs[3];
-                CBO_CUDA(cudaMemcpyAsync(hs, w.stats, sizeof(hs), cudaMemcpyDeviceToHost, s));
+                double hs[4];
+                CBO_CUDA(cudaMemcpyAsync(hs, w.stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
                 CBO_CUDA(cudaStreamSynchronize(s));
-                float score = (float)hs[2];
+                hs[3] = double(n);
+                // candidate-sharded calls: the reference's decisions are batch-global (helpers.py:151-160,177) -- the caller's
+                // hook reduces {min, max, sum, count} over the ranks (one tiny all-reduce per refinement step)
+                if (p->refine_reduce) p->refine_reduce(hs, p->refine_ctx);
+                float score = (float)hs[2] / (float)hs[3];
                 if (score < best_score) { best_score = score; best_step = step; }
                 bool rescale = hs[0] < 2.0 || hs[1] > double(G - 2);
                 if (!rescale) break;

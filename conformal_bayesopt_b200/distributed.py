@@ -29,6 +29,22 @@ def broadcast_shared_inputs(tensors, src: int = 0, group=None):
     return tensors
 
 
+def refine_reducer(group=None, device=None):
+    """Hook for `ops.conformal_acq(..., refine_reduce=...)` when the candidate batch is sharded and
+    max_grid_refinements > 0: one tiny all-reduce of {min, max, sum, count} per refinement pass makes the rescale /
+    best-pass decisions batch-global, as in the reference's single batch (helpers.py:151-160,177)."""
+    def reduce(stats):
+        if not (dist.is_available() and dist.is_initialized()):
+            return stats
+        t = torch.tensor(stats, dtype=torch.float64, device=device)
+        mn, mx, sm = t[0:1].clone(), t[1:2].clone(), t[2:4].clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=group)
+        return [float(mn), float(mx), float(sm[0]), float(sm[1])]
+    return reduce
+
+
 def sharded_acquisition(acq: Callable[[torch.Tensor], torch.Tensor], X: torch.Tensor, group=None) -> torch.Tensor:
     """Every rank holds the full candidate batch X (b, q, d); returns the full (b,) score vector on every rank."""
     if not (dist.is_available() and dist.is_initialized()):

@@ -101,6 +101,11 @@ typedef struct {
     double beta_prime;         /* cUCB: sqrt(beta*pi/2)                     */
     double best_f;             /* cEI incumbent                             */
     const cbo_nei_baseline_f64* nei;   /* kind == CBO_ACQ_NEI only (eps_mc is then S x G x (nb+1)), else NULL */
+    /* max_grid_refinements > 0 and the candidate batch is sharded over several ranks: called on the HOST once per
+     * refinement pass with stats = {min accepted, max accepted, sum of (accepted/G - 1/2)^2, candidates} of this rank's
+     * shard; must overwrite them with the values over all ranks (min / max / sum / sum).  NULL: single batch. */
+    void (*refine_reduce)(double* stats, void* ctx);
+    void* refine_ctx;
 } cbo_params;
 
 /* Any pointer may be NULL (that output is skipped) except acq. */

@@ -298,3 +298,53 @@ def test_bo_loop_demo_runs_on_the_drop_in_classes():
     spec.loader.exec_module(mod)
     best = mod.run(rounds=2, sgld_steps=6, raw=256, verbose=False)
     assert len(best) == 3 and all(math.isfinite(v) for v in best) and best[-1] >= best[0]
+
+
+def test_sharded_grid_refinement_matches_the_single_batch():
+    """SURVEY.md §8e exception: with max_grid_refinements > 0 the reference's rescale / best-pass decisions are batch-global.
+    Two 'ranks' (threads on their own streams, distinct workspaces) score the two halves of a batch; the refine_reduce hook
+    combines their statistics per refinement pass -> same results as one call on the whole batch."""
+    import threading
+    from conformal_bayesopt_b200 import ops
+    dev = _dev()
+    N, d, b, G = 64, 2, 40, 32
+    p = make_problem(N, d, seed=64)
+    inp = make_inputs(N, d, b, 1, G, S=1, seed=64)
+    st = _state(p, dev)
+    kw = dict(kind="ei", alpha=0.1, temp=1e-6, grid_res=G, randomized=True, optimistic=True, best_f=0.3, max_grid_refinements=3)
+    args = dict(eps_grid=inp["eps_grid"][:, 0].to(dev), z=inp["z"].to(dev), eps_mc=inp["eps_mc"][:, :, 0].to(dev))
+    full = ops.conformal_acq(st, inp["Xq"].to(dev), u_rand=inp["u_rand"][:, :, 0].to(dev), outputs=("conf_pred_mask",), **args, **kw)
+    torch.cuda.synchronize()
+    half = b // 2
+    barrier = threading.Barrier(2)
+    slots, lock, res, calls = {}, threading.Lock(), {}, []
+
+    def reducer_for(rank):
+        def reduce(stats):
+            with lock:
+                slots[rank] = stats
+            barrier.wait()
+            a, c = slots[0], slots[1]
+            out = [min(a[0], c[0]), max(a[1], c[1]), a[2] + c[2], a[3] + c[3]]
+            barrier.wait()
+            calls.append(rank)
+            return out
+        return reduce
+
+    def worker(rank):
+        sl = slice(0, half) if rank == 0 else slice(half, b)
+        with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+            o = ops.conformal_acq(st, inp["Xq"][sl].to(dev), u_rand=inp["u_rand"][sl, :, 0].to(dev), outputs=("conf_pred_mask",),
+                                  refine_reduce=reducer_for(rank), **args, **kw)
+            torch.cuda.synchronize()
+            res[rank] = {k: v.cpu() for k, v in o.items()}
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in (0, 1)]
+    [t.start() for t in ts]
+    [t.join(timeout=120) for t in ts]
+    assert len(res) == 2 and len(calls) >= 4          # at least two refinement passes on both ranks
+    got_acq = torch.cat([res[0]["acq"], res[1]["acq"]])
+    got_mask = torch.cat([res[0]["conf_pred_mask"], res[1]["conf_pred_mask"]])
+    assert torch.allclose(got_acq, full["acq"].cpu(), rtol=1e-12, atol=1e-14)
+    assert torch.allclose(got_mask, full["conf_pred_mask"].cpu(), rtol=0, atol=1e-12)
+    # without the hook the two halves refine on their own statistics (documented per-shard semantics): generally different

@@ -79,7 +79,9 @@ def _worker(rank, world, port, b, results):
         val, idx = cdist.sharded_argmax(_acq_standin, X[lo:hi], lo)
         shared = torch.full((3,), float(rank), dtype=torch.float64)
         cdist.broadcast_shared_inputs([shared])
-        results[rank] = (full, val, idx, shared)
+        # grid-refinement statistics hook: {min, max, sum, count} of this rank's shard -> batch-global values
+        stats = cdist.refine_reducer()([3.0 + rank, 40.0 - rank, 0.25 * (rank + 1), 10.0 + rank])
+        results[rank] = (full, val, idx, shared, stats)
     finally:
         dist.destroy_process_group()
 
@@ -95,7 +97,8 @@ def test_sharded_scoring_world_size_2_gloo(b):
     X[5] = X[b - 2]
     want = _acq_standin(X)
     for rank in range(world):
-        full, val, idx, shared = results[rank]
+        full, val, idx, shared, stats = results[rank]
+        assert stats == [3.0, 40.0, 0.75, 21.0]
         assert torch.equal(full, want)                    # sharded == unsharded, bit for bit
         assert idx == int(torch.argmax(want)) and val == float(want.max())
         assert torch.equal(shared, torch.zeros(3, dtype=torch.float64))
