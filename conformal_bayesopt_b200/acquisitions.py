@@ -115,7 +115,7 @@ class ConformalAcquisition(nn.Module):
             eps = self.grid_sampler.draw((G, b, q), dev).movedim(0, 1).contiguous()
         S = int(self.sampler.sample_shape[0])
         eps_mc = self.sampler.draw((S, G, self._mc_width(q)), dev)
-        z = (self.fixed_probes if self.fixed_probes is not None else draw_probes(state.N + q)).to(dev)
+        z = self.fixed_probes.to(dev) if self.fixed_probes is not None else draw_probes(state.N + q, device=dev)
         u = self.fixed_uniforms
         if self.randomized and u is None:
             u = torch.rand(b, G, q, dtype=torch.float64, device=dev)

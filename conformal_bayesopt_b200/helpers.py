@@ -31,10 +31,15 @@ def as_state(model) -> GPModelState:
     return state
 
 
-def draw_probes(n_rows: int, num_samples: int = 8) -> torch.Tensor:
-    """Rademacher probes drawn from the CPU default generator, as est_train_post_var does (helpers.py:399-400)."""
-    z = (torch.rand(n_rows, num_samples) > 0.5).to(torch.float64)
-    return 2.0 * (z - 0.5)
+def draw_probes(n_rows: int, num_samples: int = 8, device=None) -> torch.Tensor:
+    """Rademacher probes drawn from the CPU default generator, as est_train_post_var does (helpers.py:399-400): same draws
+    and values as `2 * ((rand > 0.5).double() - 0.5)`.  With `device`, only the sign bits cross the bus (1 byte per probe
+    entry) and the +-1 doubles are formed on the device."""
+    bits = torch.rand(n_rows, num_samples) > 0.5
+    if device is None:
+        return torch.where(bits, 1.0, -1.0).to(torch.float64)
+    one = torch.ones((), dtype=torch.float64, device=device)
+    return torch.where(bits.to(device), one, -one)
 
 
 def _ratio_weights(ratio_estimator, device):

@@ -48,7 +48,9 @@ def _require_cuda(*tensors):
 
 
 def _f64(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-    return None if t is None else t.to(torch.float64).contiguous()
+    if t is None or (t.dtype == torch.float64 and t.is_contiguous()):
+        return t
+    return t.to(torch.float64).contiguous()
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -95,12 +97,12 @@ def make_params(*, alpha, temp, grid_res, q=1, num_mc=1, num_probes=8, max_grid_
                        C.pointer(nei) if nei is not None else None, fn, None)
 
 
-def workspace(state: GPModelState, b: int, params, chunk: int = 0, grad: bool = False) -> torch.Tensor:
-    """Caller-owned scratch (torch caching allocator), cached per (device, size)."""
+def workspace(state: GPModelState, b: int, params, chunk: int = 0, grad: bool = False, stream: Optional[int] = None) -> torch.Tensor:
+    """Caller-owned scratch (torch caching allocator), cached per (device, stream)."""
     lib = _lib.load()
     fn = lib.cbo_workspace_bytes_grad if grad else lib.cbo_workspace_bytes
     nbytes = fn(state.N, state.d, b, C.byref(params), chunk)
-    key = (state.device.index, torch.cuda.current_stream().cuda_stream)
+    key = (state.device.index, stream if stream is not None else torch.cuda.current_stream().cuda_stream)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=state.device)
@@ -166,7 +168,8 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
     for name in outputs:
         out_t[name] = torch.empty(shapes[name], dtype=torch.float64, device=dev)
     cout = _lib.OutputsF64(**{k: _ptr(v) for k, v in out_t.items()})
-    ws = workspace(state, b, params, chunk, grad=want_grad)
+    cs = _stream()
+    ws = workspace(state, b, params, chunk, grad=want_grad, stream=cs)
     ws_ptr = (ws.data_ptr() + 255) // 256 * 256
     gp_c = state.c_struct()
     ratio_c = ratio.c_struct() if ratio is not None else None
@@ -175,12 +178,12 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
         dX = torch.empty(b, q, Xq.shape[-1], dtype=torch.float64, device=dev)
         st = lib.cbo_conformal_acq_grad_f64(C.byref(gp_c), ratio_p, C.byref(params), Xq.data_ptr(), b, eps_grid.data_ptr(),
                                             z.data_ptr(), eps_mc.data_ptr(), _ptr(u_rand), C.byref(cout), dX.data_ptr(),
-                                            ws_ptr, ws.numel() - 256, chunk, _stream())
+                                            ws_ptr, ws.numel() - 256, chunk, cs)
         _lib.check(st, "cbo_conformal_acq_grad_f64")
     else:
         st = lib.cbo_conformal_acq_f64(C.byref(gp_c), ratio_p, C.byref(params), Xq.data_ptr(), b, eps_grid.data_ptr(),
                                        z.data_ptr(), eps_mc.data_ptr(), _ptr(u_rand), C.byref(cout), ws_ptr,
-                                       ws.numel() - 256, chunk, _stream())
+                                       ws.numel() - 256, chunk, cs)
         _lib.check(st, "cbo_conformal_acq_f64")
     LAUNCH_COUNT += count_launches(state, b, params, ratio is not None, chunk, grad=want_grad, extra_outputs=len(outputs) > 0)
     if q == 1:   # squeeze the q axis (the q = 1 layout of round-1 callers)

@@ -42,7 +42,9 @@ class RatioEstimator(nn.Module):
 
     def device_weights(self, device) -> "ops.RatioWeights":
         """fp64 device copies of the target-network weights for the kernels (refreshed after every update)."""
-        key = (str(device), tuple(int(p._version) for p in self._target_network.parameters()))
+        if not hasattr(self, "_target_params"):
+            self._target_params = list(self._target_network.parameters())
+        key = (device, tuple(p._version for p in self._target_params))
         if self._weights_cache is None or self._weights_cache[0] != key:
             self._weights_cache = (key, ops.RatioWeights.from_sequential(self._target_network, device))
         return self._weights_cache[1]

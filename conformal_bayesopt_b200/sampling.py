@@ -22,6 +22,7 @@ class IIDNormalSampler:
         self.batch_range = batch_range
         self.seed = seed if seed is not None else int(torch.randint(0, 1000000, (1,)).item())
         self.base_samples: Optional[torch.Tensor] = None
+        self._device_copy = None              # (device, tensor): the cached base samples stay resident between calls
 
     @property
     def sample_shape(self) -> torch.Size:
@@ -33,10 +34,17 @@ class IIDNormalSampler:
         if self.resample or self.base_samples is None or tuple(self.base_samples.shape) != shape:
             g = torch.Generator().manual_seed(self.seed)
             self.base_samples = torch.randn(shape, generator=g, dtype=torch.float64)
+            self._device_copy = None
             if self.resample:
                 self.seed += 1
-        return self.base_samples.to(device) if device is not None else self.base_samples
+        if device is None:
+            return self.base_samples
+        device = torch.device(device)
+        if self._device_copy is None or self._device_copy[0] != device or self._device_copy[2] is not self.base_samples:
+            self._device_copy = (device, self.base_samples.to(device), self.base_samples)
+        return self._device_copy[1]
 
     def set_base_samples(self, base: torch.Tensor):
         """Inject base samples (parity tests)."""
         self.base_samples = base.detach().to("cpu", torch.float64).clone()
+        self._device_copy = None
