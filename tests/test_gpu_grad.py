@@ -307,3 +307,27 @@ def test_repeated_calls_are_bitwise_identical(q, b):
     for a, g in outs[1:]:
         assert torch.equal(a, outs[0][0]) and torch.equal(g, outs[0][1])
     assert torch.isfinite(outs[0][1]).all()
+
+
+def test_cuda_graph_replay_equals_direct_calls():
+    """graphs.GraphedConformalAcq: the captured value+gradient call replays bit-identically to direct calls (SGLD shape)."""
+    from conformal_bayesopt_b200 import ops
+    from conformal_bayesopt_b200.graphs import GraphedConformalAcq
+    dev = _dev()
+    N, d, b, q, G = 200, 4, 8, 2, 32
+    p = make_problem(N, d, seed=7)
+    st = _state(p, dev)
+    _, rw = _ratio(d, dev)
+    inp = make_inputs(N, d, b, q, G, S=1, seed=7)
+    kw = dict(kind="ucb", alpha=0.1, temp=3e-2, grid_res=G, randomized=True, optimistic=True, beta_prime=1.0)
+    gr = GraphedConformalAcq(st, b, q, eps_grid=inp["eps_grid"].to(dev), eps_mc=inp["eps_mc"].to(dev), ratio=rw, **kw)
+    for t in range(3):
+        it = make_inputs(N, d, b, q, G, S=1, seed=20 + t)
+        X, z, u = it["Xq"].to(dev), it["z"].to(dev), it["u_rand"].to(dev)
+        got = gr(X, z=z, u_rand=u)
+        want = ops.conformal_acq(st, X, eps_grid=inp["eps_grid"].to(dev), z=z, eps_mc=inp["eps_mc"].to(dev), u_rand=u, ratio=rw,
+                                 want_grad=True, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(got["acq"], want["acq"]) and torch.equal(got["dacq_dX"], want["dacq_dX"])
+    with pytest.raises(ValueError):
+        GraphedConformalAcq(st, b, q, eps_grid=inp["eps_grid"].to(dev), eps_mc=inp["eps_mc"].to(dev), max_grid_refinements=1, **kw)

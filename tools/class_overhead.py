@@ -40,6 +40,19 @@ with torch.no_grad():
         acqf(X)
     torch.cuda.synchronize()
     print(f"class path, value only: {(time.perf_counter() - t0) / n * 1e3:.3f} ms per call (host wall)")
+from conformal_bayesopt_b200.graphs import GraphedConformalAcq
+from conformal_bayesopt_b200.helpers import _ratio_weights
+eps = acqf.grid_sampler.draw((G, q), dev); em = acqf.sampler.draw((1, G, q), dev)
+gr = GraphedConformalAcq(st, b, q, eps_grid=eps, eps_mc=em, ratio=_ratio_weights(ratio, dev), kind="ucb", alpha=N ** -0.35, temp=3e-2,
+                         grid_res=G, randomized=True, optimistic=True, beta_prime=math.sqrt(0.2 * math.pi / 2))
+for _ in range(5):
+    gr(X)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(n):
+    out = gr(X)
+torch.cuda.synchronize()
+print(f"CUDA-graph replay, value+grad (fresh probes and uniforms per step): {(time.perf_counter() - t0) / n * 1e3:.3f} ms per SGLD step (host wall)")
 if len(sys.argv) > 1:
     pr = cProfile.Profile(); pr.enable()
     for _ in range(100):
