@@ -400,8 +400,9 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
     TimeScope ts_(T_PREP, s, 7);
     cbo::k_scale_transpose<<<(Np * d + 255) / 256, 256, 0, s>>>(gp->X, N, Np, d, gp->inv_lengthscale, w.XsT);
     cbo::k_pad_probes<<<(Np * Sp + 255) / 256, 256, 0, s>>>(z, N, Np, Sp, w.zp);
-    cbo::k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(gp->linv, Np, w.zp, Sp, w.tmp, 0, 1);
-    cbo::k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(gp->linv_t, Np, w.tmp, Sp, w.T, 1, 0);
+    // T^T = Z^T A^-1 (Sp x Np): the probe vectors are Sp more "rows" for the two triangular passes (split-K: a handful of rows)
+    CBO_CUDA(cbo::launch_gemm_tn(w.zp, Np, gp->linv, Np, w.tmp, Np, Sp, Np, Np, cbo::TRI_LOWER, nullptr, s, num_sms(), w.splitk));
+    CBO_CUDA(cbo::launch_gemm_tn(w.tmp, Np, gp->linv_t, Np, w.T, Np, Sp, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms(), w.splitk));
     if (ratio)
         CBO_CUDA(cbo::launch_ratio_mlp(gp->X, N, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2, ratio->b2,
                                        ratio->W3, ratio->b3, 1e-6, w.dr_train, num_sms(), s));

@@ -3,7 +3,7 @@
 //   k_kernel_rows    U[c, i] = os * (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r),  r = ||(x_c - X_i) / l||
 //                    mu[c]   = mean + sum_i U[c,i] alpha_i                   (helpers.py:119, acquisitions.py:59)
 //                    ut[c,s] = sum_i U[c,i] T[i,s]                           (probe correction, App. A-4)
-//   k_probe_matvec   out[i, s] = sum_j Mat[i, j] in[j, s]   (T = L^-T (L^-1 z): 2 launches)
+//   k_probe_matvec   out[i, s] = sum_j Mat[i, j] in[j, s]   (model builder: alpha = L^-T (L^-1 (y - m)))
 //   k_train_tables   per-train-point tables for the score kernel             (helpers.py:396-405)
 #pragma once
 #include "common.cuh"
@@ -87,10 +87,7 @@ k_kernel_rows(const double* __restrict__ Xq, int n, const double* __restrict__ X
         for (int e = threadIdx.x; e < Np; e += blockDim.x) s_alpha[e] = alpha_g[e];
         for (int e = threadIdx.x; e < d * Np; e += blockDim.x) s_xst[e] = XsT_g[e];
         if (want_ut)
-            for (int e = threadIdx.x; e < Sp * Np; e += blockDim.x) {
-                int s = e / Np, i = e - s * Np;
-                s_tt[e] = T[int64_t(i) * Sp + s];
-            }
+            for (int e = threadIdx.x; e < Sp * Np; e += blockDim.x) s_tt[e] = T[e];      // T is stored transposed: (Sp x Np)
     }
     __syncthreads();
     const double* __restrict__ XsT = STAGE ? s_xst : XsT_g;
@@ -139,7 +136,7 @@ k_kernel_rows(const double* __restrict__ Xq, int n, const double* __restrict__ X
 #pragma unroll
                     for (int s = 0; s < NSP; ++s) {
                         if (s < Sp) {
-                            double ts = STAGE ? s_tt[s * Np + i] : T[int64_t(i) * Sp + s];
+                            double ts = STAGE ? s_tt[s * Np + i] : T[int64_t(s) * Np + i];
 #pragma unroll
                             for (int cc = 0; cc < ROWS_CPW; ++cc) acc_ut[cc][s] = fma(kv[cc], ts, acc_ut[cc][s]);
                         }
@@ -203,7 +200,7 @@ k_kernel_rows_small(const double* __restrict__ Xq, int n, const double* __restri
             if (want_ut) {
 #pragma unroll
                 for (int s = 0; s < MAX_SP; ++s)
-                    if (s < Sp) acc_ut[s] = fma(kv, T[int64_t(i) * Sp + s], acc_ut[s]);
+                    if (s < Sp) acc_ut[s] = fma(kv, T[int64_t(s) * Np + i], acc_ut[s]);
             }
         }
         U[int64_t(c) * Np + i] = kv;
@@ -313,12 +310,13 @@ __global__ void k_eps_absmax(const double* __restrict__ eps, int rows, int G, do
     if (lane == 0) out[r] = m;
 }
 
-// z (N+q) x Sp of +-1 -> padded copy zp (Np x Sp, zeros beyond N)
-__global__ void k_pad_probes(const double* __restrict__ z, int N, int Np, int Sp, double* __restrict__ zp) {
+// z (N+q) x Sp of +-1 -> padded TRANSPOSED copy zt (Sp x Np, zeros beyond N): the Sp probe vectors become Sp rows that go
+// through the same two triangular GEMM passes as the candidates' kernel rows (T^T = Z^T A^-1)
+__global__ void k_pad_probes(const double* __restrict__ z, int N, int Np, int Sp, double* __restrict__ zt) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= Np * Sp) return;
-    int i = e / Sp;
-    zp[e] = (i < N) ? z[e] : 0.0;
+    int s = e / Np, i = e - s * Np;
+    zt[e] = (i < N) ? z[int64_t(i) * Sp + s] : 0.0;
 }
 
 // Per-train-point tables of the score kernel:
@@ -338,7 +336,7 @@ k_train_tables(const double* __restrict__ alpha, const double* __restrict__ z, c
             uint32_t bits = 0;
             for (int s = 0; s < Sp; ++s) {
                 double zs = z[int64_t(i) * Sp + s];
-                acc = fma(zs, T[int64_t(i) * Sp + s], acc);
+                acc = fma(zs, T[int64_t(s) * Np + i], acc);
                 bits |= (zs > 0.0) ? (1u << s) : 0u;
             }
             a[i] = noise * alpha[i];

@@ -115,10 +115,12 @@ def count_launches(state: GPModelState, b: int, params, ratio: bool, chunk: int 
     """Kernels one cbo_conformal_acq[_grad]_f64 call enqueues (mirrors csrc/cbo_api.cu)."""
     C_ = b if params.max_grid_refinements > 0 else min(b, chunk if chunk > 0 else 65536)
     n_chunks = (b + C_ - 1) // C_
-    per_call = 7                                   # scale_transpose, pad_probes, 2 x probe_matvec, ratio/fill, eps_absmax, train_tables
-    per_chunk = 1 + (1 if ratio else 0) + 2 + 1    # rows, ratio(cand), 2 x gemm, score
+    small = b * params.q <= 32                     # latency path: split-K GEMMs (gemm + reduce [+ row norms])
+    per_call = 9                                   # scale_transpose, pad_probes, 2 x (split-K gemm + reduce) for T, ratio/fill, eps_absmax, train_tables
+    g1, g2 = (3, 2) if small else (1, 1)
+    per_chunk = 1 + (1 if ratio else 0) + g1 + g2 + 1    # rows, ratio(cand), gemm pass 1, pass 2, score
     if grad:                                       # score value+reverse (replaces score unless extra outputs), 2 x gemm, rows reverse, ratio reverse
-        per_chunk += (1 if extra_outputs else 0) + 2 + 1 + (1 if ratio else 0)
+        per_chunk += (1 if extra_outputs else 0) + 2 * g2 + 1 + (1 if ratio else 0)
     return per_call + n_chunks * per_chunk
 
 
