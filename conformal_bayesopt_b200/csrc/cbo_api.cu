@@ -286,7 +286,9 @@ cudaError_t launch_score_q_t(const cbo::ScoreQArgs& a, cudaStream_t st) {
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
     int grid = a.base.n_cand < per_sm * num_sms() ? a.base.n_cand : per_sm * num_sms();
-    cbo::k_score_q<Q, SOFT><<<grid, cbo::SQ_THREADS, smem, st>>>(a);
+    // a handful of joint batches: 512 threads each (latency); many: 256 threads, more CTAs per SM
+    const int threads = (Q <= 2 && a.base.n_cand < 2 * num_sms()) ? cbo::SQ_THREADS_SMALL : cbo::SQ_THREADS;
+    cbo::k_score_q<Q, SOFT><<<grid, threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -20,8 +20,9 @@
 
 namespace cbo {
 
-constexpr int SQ_THREADS = 256;
+constexpr int SQ_THREADS = 256;     // value+reverse kernel, and the forward kernel for large batches
 constexpr int SQ_WARPS = 8;
+constexpr int SQ_THREADS_SMALL = 512;   // forward kernel when a handful of joint batches must fill their SMs (latency)
 constexpr int MAX_Q = 4;
 
 struct ScoreQArgs {
@@ -98,23 +99,23 @@ __device__ inline void inv_from_chol(const double (&L)[Q][Q], double (&Ainv)[Q][
         }
 }
 
-__device__ __forceinline__ double block_sum(double v, double* red, int tid) {
+__device__ __forceinline__ double block_sum(double v, double* red, int tid, int nwarps = SQ_WARPS) {
     v = warp_sum(v);
     __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = v;
     __syncthreads();
     double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < SQ_WARPS; ++w) t += red[w];
+    for (int w = 0; w < nwarps; ++w) t += red[w];
     return t;
 }
 
 template <int Q, bool SOFT>
-__global__ void __launch_bounds__(SQ_THREADS)
+__global__ void __launch_bounds__(Q <= 2 ? SQ_THREADS_SMALL : SQ_THREADS)      // q > 2 needs more than 128 registers
 k_score_q(const ScoreQArgs pq) {
     const ScoreArgs& p = pq.base;
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthr = blockDim.x, nwarps = blockDim.x >> 5;       // 256 or 512 threads
     const int N = p.N, Np = p.Np, G = p.G, Sp = p.Sp, S = p.S;
     double* s_lv = sm;                       // Np
     double* s_ap = s_lv + Np;                // Np
@@ -130,7 +131,7 @@ k_score_q(const ScoreQArgs pq) {
     double* g_lp = g_sw + size_t(Q) * G;     // G
     double* sc = g_lp + G;                   // scratch: 512 doubles
     double* red = sc;                        // [4]
-    double* s_S = sc + 8;                    // Q x Q
+    double* s_S = sc + 16;                   // Q x Q
     double* s_Sinv = s_S + 16;
     double* s_Lc = s_Sinv + 16;
     double* s_Lf = s_Lc + 16;
@@ -144,7 +145,7 @@ k_score_q(const ScoreQArgs pq) {
     if (tid < 16) exp_tab_init(tab, tid);
     const unsigned tab_s = smem_u32(tab);
 
-    for (int i = tid; i < N; i += SQ_THREADS) s_dr[i] = p.dr[i];
+    for (int i = tid; i < N; i += nthr) s_dr[i] = p.dr[i];
     __syncthreads();
 
     for (int c = blockIdx.x; c < p.n_cand; c += gridDim.x) {
@@ -155,7 +156,7 @@ k_score_q(const ScoreQArgs pq) {
         for (int j = 0; j < Q; ++j)
 #pragma unroll
             for (int k = 0; k < Q; ++k) gsum[j][k] = 0.0;
-        for (int i = tid; i < N; i += SQ_THREADS) {
+        for (int i = tid; i < N; i += nthr) {
             double v[Q];
 #pragma unroll
             for (int j = 0; j < Q; ++j) v[j] = pq.V[int64_t(r0 + j) * Np + i];
@@ -169,7 +170,7 @@ k_score_q(const ScoreQArgs pq) {
         for (int j = 0; j < Q; ++j)
 #pragma unroll
             for (int k = 0; k < Q; ++k)
-                if (k <= j) gsum[j][k] = block_sum(gsum[j][k], red, tid);
+                if (k <= j) gsum[j][k] = block_sum(gsum[j][k], red, tid, nwarps);
         if (tid == 0) {
             double Sm[Q][Q], Ls[Q][Q], Si[Q][Q];
             for (int j = 0; j < Q; ++j)
@@ -226,7 +227,7 @@ k_score_q(const ScoreQArgs pq) {
         int bad = s_misc[Q + 1] != 0.0;
 
         // ---- phase A: per-train-point tables -------------------------------------------------------------------
-        for (int i = tid; i < N; i += SQ_THREADS) {
+        for (int i = tid; i < N; i += nthr) {
             uint32_t bits = p.zb[i];
             double w[Q], acc = 0.0;
 #pragma unroll
@@ -260,7 +261,7 @@ k_score_q(const ScoreQArgs pq) {
         const double logdet = s_misc[Q];
 
         // ---- phase B + C: warp per grid point --------------------------------------------------------------------
-        for (int g = warp; g < G; g += SQ_WARPS) {
+        for (int g = warp; g < G; g += nwarps) {
             double eps[Q], dev[Q], Bg[Q], thr[Q];
             double e2 = 0.0;
 #pragma unroll
@@ -337,7 +338,7 @@ k_score_q(const ScoreQArgs pq) {
         }
         __syncthreads();
         // ---- phase C: thread per (grid point, column) ------------------------------------------------------------------------
-        for (int o = tid; o < G * Q; o += SQ_THREADS) {
+        for (int o = tid; o < G * Q; o += nthr) {
             const int g = o / Q, j = o - g * Q;
             // rows of the q candidates themselves (weights zero except the own row, counted in n_g and sum rho)
             int n_g = int(g_cnt[o]);
@@ -377,7 +378,7 @@ k_score_q(const ScoreQArgs pq) {
             if (p.mask) p.mask[(int64_t(c) * G + g) * Q + j] = mk;
             if (p.qscore) p.qscore[(int64_t(c) * G + g) * Q + j] = bad ? nan("") : thr_j;
         }
-        for (int g = tid; g < G; g += SQ_THREADS) {       // g_lp is not read by the loop above
+        for (int g = tid; g < G; g += nthr) {       // g_lp is not read by the loop above
             double lp = -0.5 * (g_lp[g] + logdet + double(Q) * kLog2Pi);
             g_lp[g] = bad ? nan("") : lp;
             if (p.logp) p.logp[int64_t(c) * G + g] = bad ? nan("") : lp;
@@ -390,15 +391,15 @@ k_score_q(const ScoreQArgs pq) {
         for (int j = 0; j < Q; ++j) {
             ood[j] = SOFT ? sigmoid_acc((omega[j] - p.alpha_lvl) * inv_temp) : ((omega[j] >= p.alpha_lvl) ? 1.0 : 0.0);
             double a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            for (int g = tid; g < G; g += SQ_THREADS) {
+            for (int g = tid; g < G; g += nthr) {
                 double mk = g_mask[g * Q + j], op = g_opt[g * Q + j];
                 a1 += mk * op / fmax(exp(g_lp[g]), 1e-6);
                 a2 += (1.0 - mk) * op;
                 a3 += (mk >= 0.5) ? 1.0 : 0.0;
             }
-            scw[j] = block_sum(a1, red, tid);
-            snc[j] = block_sum(a2, red, tid);
-            nacc[j] = block_sum(a3, red, tid);
+            scw[j] = block_sum(a1, red, tid, nwarps);
+            snc[j] = block_sum(a2, red, tid, nwarps);
+            nacc[j] = block_sum(a3, red, tid, nwarps);
         }
         double tot = 0.0;
         for (int s = 0; s < S; ++s) {
@@ -407,7 +408,7 @@ k_score_q(const ScoreQArgs pq) {
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
                 double A = 0.0, B = 0.0;
-                for (int g = tid; g < G; g += SQ_THREADS) {
+                for (int g = tid; g < G; g += nthr) {
                     // refit mean at candidate j: mu_j + sum_k (I - noise S^-1)_jk dev_k ; sample f = mean + (L_f eps')_j
                     double mf = mu[j], fs = 0.0, ms = 0.0;
 #pragma unroll
@@ -436,8 +437,8 @@ k_score_q(const ScoreQArgs pq) {
                     A = fma(mk * op / fmax(exp(g_lp[g]), 1e-6), val, A);
                     B = fma((1.0 - mk) * op, val, B);
                 }
-                A = block_sum(A, red, tid);
-                B = block_sum(B, red, tid);
+                A = block_sum(A, red, tid, nwarps);
+                B = block_sum(B, red, tid, nwarps);
                 double r = (1.0 - ood[j]) * ((1.0 - p.alpha_lvl) * A / fmax(scw[j], 1e-6) + p.alpha_lvl * B / fmax(snc[j], 1e-6));
                 isnan_any = isnan_any || (r != r);
                 best = fmax(best, r);
