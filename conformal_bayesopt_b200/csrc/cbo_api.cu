@@ -254,14 +254,36 @@ cudaError_t launch_score_bwd(const cbo::ScoreBwdArgs& a_in, cudaStream_t st) {
 template <int Q, bool SOFT>
 cudaError_t launch_score_q_bwd_t(const cbo::ScoreQBwdArgs& a, cudaStream_t st) {
     size_t smem = cbo::score_q_bwd_smem_bytes(a.f.base.Np, a.f.base.G, Q);
+    // a handful of joint batches (the SGLD loop): one thread-block cluster of 8 CTAs per joint batch (soft path)
+    const bool cluster = SOFT && a.f.base.n_cand * cbo::SQB_CLUSTER <= num_sms();
+    if (cluster) {
+        static size_t configured_cl = 0;
+        if (smem > configured_cl) {
+            cudaError_t e = cudaFuncSetAttribute(cbo::k_score_q_bwd<Q, SOFT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured_cl = smem;
+        }
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(a.f.base.n_cand * cbo::SQB_CLUSTER);
+        cfg.blockDim = dim3(cbo::SQ_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = cbo::SQB_CLUSTER; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, cbo::k_score_q_bwd<Q, SOFT, true>, a);
+    }
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(cbo::k_score_q_bwd<Q, SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(cbo::k_score_q_bwd<Q, SOFT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     int grid = a.f.base.n_cand < 2 * num_sms() ? a.f.base.n_cand : 2 * num_sms();
-    cbo::k_score_q_bwd<Q, SOFT><<<grid, cbo::SQ_THREADS, smem, st>>>(a);
+    cbo::k_score_q_bwd<Q, SOFT, false><<<grid, cbo::SQ_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -12,6 +12,7 @@
 //   final    (one thread) q x q algebra: Cholesky reverse of the refit factor, S^-1 adjoint, S_bar = -S^-T Sinv_bar S^-T;
 //            per row: mu_bar, drc_bar, Ssym row, ut_bar;  w_bar rows (right-hand sides of the A^-1 solve) get z ut_bar folded in.
 #pragma once
+#include <cooperative_groups.h>
 #include "score_q.cuh"
 
 namespace cbo {
@@ -69,9 +70,16 @@ struct SqbReducer {
     }
 };
 
-template <int Q, bool SOFT>
+// CL = true: a thread-block CLUSTER of SQB_CLUSTER CTAs works on ONE joint batch (a handful of joint batches per call would
+// otherwise keep 8 SMs busy): every CTA owns a window of the train points for the O(N G q) sweeps (phase 0 Gram sums, phase A
+// tables, phase B, pass 2), the partial sums are exchanged through distributed shared memory (cluster.map_shared_rank) at
+// three cluster barriers, the O(G q) phases C-E run redundantly in every CTA, rank 0 does the final q x q algebra.
+constexpr int SQB_CLUSTER = 8;
+
+template <int Q, bool SOFT, bool CL>
 __global__ void __launch_bounds__(SQ_THREADS)
 k_score_q_bwd(const ScoreQBwdArgs qb) {
+    namespace cg = cooperative_groups;
     const ScoreQArgs& pq = qb.f;
     const ScoreArgs& p = pq.base;
     extern __shared__ __align__(16) double sm[];
@@ -102,6 +110,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
     double* s_kap = s_B + MAX_S * MAX_Q;     // [MAX_S][MAX_Q]  d acq / d res_sj
     double* s_Cbar = s_kap + MAX_S * MAX_Q;  // Q x MAX_SP
     double* s_utb = s_Cbar + MAX_Q * MAX_SP; // Q x MAX_SP
+    double* s_xg = s_utb + MAX_Q * MAX_SP;   // [Q*Q + 1]: this CTA's Gram partial sums and its `bad` flag (cluster exchange)
     double* wred = sc + 1024;                // [SQ_WARPS][SQB_NT]
     double* tot = wred + SQ_WARPS * SQB_NT;  // [SQB_NT]
     const SqbReducer R{wred, tot, tid};
@@ -118,7 +127,16 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
     for (int i = tid; i < N; i += SQ_THREADS) s_dr[i] = p.dr[i];
     __syncthreads();
 
-    for (int c = blockIdx.x; c < p.n_cand; c += gridDim.x) {
+    // window of train points of this CTA: everything (one CTA per joint batch) or 1 / SQB_CLUSTER of it
+    int crank = 0;
+    if constexpr (CL) crank = int(cg::this_cluster().block_rank());
+    const int NS = CL ? ((N + SQB_CLUSTER * 32 - 1) / (SQB_CLUSTER * 32)) * 32 : N;
+    const int i_lo = CL ? min(N, crank * NS) : 0, i_hi = CL ? min(N, (crank + 1) * NS) : N;
+    const int p_lo = CL ? min(Np, crank * NS) : 0;                       // pass 2 also zero-fills the padding rows
+    const int p_hi = CL ? ((crank == SQB_CLUSTER - 1) ? Np : min(Np, (crank + 1) * NS)) : Np;
+    const int cstep = CL ? gridDim.x / SQB_CLUSTER : gridDim.x;
+
+    for (int c = CL ? blockIdx.x / SQB_CLUSTER : blockIdx.x; c < p.n_cand; c += cstep) {
         const int r0 = c * Q;
         for (int e = tid; e < SQB_NT; e += SQ_THREADS) tot[e] = 0.0;
         // ---- phase 0 (as k_score_q) -----------------------------------------------------------------------------------
@@ -127,7 +145,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
         for (int j = 0; j < Q; ++j)
 #pragma unroll
             for (int k = 0; k < Q; ++k) gsum[j][k] = 0.0;
-        for (int i = tid; i < N; i += SQ_THREADS) {
+        for (int i = i_lo + tid; i < i_hi; i += SQ_THREADS) {
             double v[Q];
 #pragma unroll
             for (int j = 0; j < Q; ++j) v[j] = pq.V[int64_t(r0 + j) * Np + i];
@@ -142,6 +160,19 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
 #pragma unroll
             for (int k = 0; k < Q; ++k)
                 if (k <= j) gsum[j][k] = block_sum(gsum[j][k], red, tid);
+        if constexpr (CL) {                                              // Gram sums over all windows, fixed rank order
+            if (tid == 0)
+                for (int j = 0; j < Q; ++j)
+                    for (int k = 0; k <= j; ++k) s_xg[j * Q + k] = gsum[j][k];
+            cg::this_cluster().sync();
+            if (tid == 0)
+                for (int j = 0; j < Q; ++j)
+                    for (int k = 0; k <= j; ++k) {
+                        double t = 0.0;
+                        for (int r = 0; r < SQB_CLUSTER; ++r) t += cg::this_cluster().map_shared_rank(s_xg, r)[j * Q + k];
+                        gsum[j][k] = t;
+                    }
+        }
         if (tid == 0) {
             double Sm[Q][Q], Ls[Q][Q], Si[Q][Q];
             for (int j = 0; j < Q; ++j)
@@ -197,7 +228,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
         int bad = s_misc[Q + 1] != 0.0;
 
         // ---- phase A: per-train-point tables ---------------------------------------------------------------------------
-        for (int i = tid; i < N; i += SQ_THREADS) {
+        for (int i = i_lo + tid; i < i_hi; i += SQ_THREADS) {
             uint32_t bits = p.zb[i];
             double w[Q], acc = 0.0;
 #pragma unroll
@@ -217,7 +248,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
 #pragma unroll
             for (int j = 0; j < Q; ++j) s_wp[size_t(j) * Np + i] = noise * w[j] * siv;
         }
-        bad = __syncthreads_or(bad);
+        bad = __syncthreads_or(bad);                                     // CL: this window only; combined after phase B
 
         double mu[Q], drc[Q], norm[Q], omega[Q], ivc[Q], lvc[Q];
 #pragma unroll
@@ -263,9 +294,9 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             for (int j = 0; j < Q; ++j) { sr[j] = 0.0; sw[j] = 0.0; cnt[j] = 0; }
             if (!bad) {
                 // two train points per lane and step (i, i + 32): 2 Q independent sigmoid chains instead of Q
-                for (int i = lane; i < N; i += 64) {
+                for (int i = i_lo + lane; i < i_hi; i += 64) {
                     const int i2 = i + 32;
-                    const bool ok2 = i2 < N;
+                    const bool ok2 = i2 < i_hi;
                     const int i2c = ok2 ? i2 : i;
                     double rp0 = s_ap[i], rp1 = s_ap[i2c];
 #pragma unroll
@@ -304,9 +335,26 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                 for (int j = 0; j < Q; ++j) {
                     const int o = g * Q + j;
                     g_dev[o] = dev[j]; g_Bg[o] = Bg[j]; g_thr[o] = thr[j];
-                    g_sr[o] = sr[j]; g_sw[o] = sw[j]; g_scale[o] = double(cnt[j]);
+                    if (CL) { g_P[o] = sr[j]; g_Q[o] = sw[j]; g_kl[o] = double(cnt[j]); }      // window partials
+                    else { g_sr[o] = sr[j]; g_sw[o] = sw[j]; g_scale[o] = double(cnt[j]); }
                 }
             }
+        }
+        if constexpr (CL) {        // sums over the windows of all CTAs of the cluster (fixed rank order) + the `bad` flags
+            if (tid == 0) s_xg[Q * Q] = bad ? 1.0 : 0.0;
+            cg::this_cluster().sync();
+            auto cl = cg::this_cluster();
+            for (int o = tid; o < G * Q; o += SQ_THREADS) {
+                double a = 0.0, b2 = 0.0, c2 = 0.0;
+                for (int r = 0; r < SQB_CLUSTER; ++r) {
+                    a += cl.map_shared_rank(g_P, r)[o]; b2 += cl.map_shared_rank(g_Q, r)[o]; c2 += cl.map_shared_rank(g_kl, r)[o];
+                }
+                g_sr[o] = a; g_sw[o] = b2; g_scale[o] = c2;
+            }
+            int anybad = 0;
+            for (int r = 0; r < SQB_CLUSTER; ++r) anybad |= cl.map_shared_rank(s_xg, r)[Q * Q] != 0.0;
+            bad = anybad;
+            cl.sync();             // every remote read of the partial arrays is done before phase C reuses them
         }
         __syncthreads();
         // ---- phase C: thread per (grid point, column) ------------------------------------------------------------------------
@@ -534,6 +582,10 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
         __syncthreads();
         R.commit();
         __syncthreads();
+        if (CL && crank != 0) {    // phases C-E ran redundantly: their totals count once (rank 0) in the cluster sum
+            for (int e = tid; e < SQB_NT; e += SQ_THREADS) tot[e] = 0.0;
+            __syncthreads();
+        }
 
         // ---- pass 2: thread per train point, loop over the grid ------------------------------------------------------------------
         R.zero_partials();
@@ -548,21 +600,21 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             }
             // RI train points per thread are swept together: RI Q independent sigmoid chains, and the per-column totals
             // (which depend on the grid point only) are accumulated once per grid point for all RI rows
-            constexpr int RI = (Q <= 2) ? 4 : 2;
-            for (int i0 = tid; i0 < Np; i0 += SQ_THREADS * RI) {
+            constexpr int RI = CL ? 1 : ((Q <= 2) ? 4 : 2);
+            for (int i0 = p_lo + tid; i0 < p_hi; i0 += SQ_THREADS * RI) {
                 double ap[RI], lv[RI], dr[RI], siv[RI], vm[RI], wp[RI][Q], m0[RI], mrr[RI], mr[RI], mrd[RI][Q];
 #pragma unroll
                 for (int r = 0; r < RI; ++r) {
                     const int i = i0 + r * SQ_THREADS;
-                    const bool ok = (i < N) && SOFT && !bad;
-                    const int ic = ok ? i : 0;
+                    const bool ok = (i < i_hi) && SOFT && !bad;
+                    const int ic = ok ? i : i_lo < N ? i_lo : 0;
                     vm[r] = ok ? 1.0 : 0.0;
                     ap[r] = s_ap[ic]; lv[r] = s_lv[ic]; dr[r] = s_dr[ic]; siv[r] = s_siv[ic];
                     m0[r] = mrr[r] = mr[r] = 0.0;
 #pragma unroll
                     for (int j = 0; j < Q; ++j) { wp[r][j] = s_wp[size_t(j) * Np + ic]; mrd[r][j] = 0.0; }
                 }
-                if (SOFT && !bad && i0 < N) {
+                if (SOFT && !bad && i0 < i_hi) {
                     for (int g = 0; g < G; ++g) {
                         double rp[RI], sci[RI], gam[RI];
 #pragma unroll
@@ -603,7 +655,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
 #pragma unroll
                 for (int r = 0; r < RI; ++r) {
                     const int i = i0 + r * SQ_THREADS;
-                    if (i >= Np) continue;
+                    if (i >= p_hi) continue;
                     if (vm[r] == 0.0) {
 #pragma unroll
                         for (int j = 0; j < Q; ++j) {
@@ -651,7 +703,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                 const int pr = tid % npair, sl = tid / npair;
                 const int j = pr / Sp, s2 = pr - j * Sp;
                 double acc = 0.0;
-                for (int i = sl; i < N; i += nslice) {
+                for (int i = i_lo + sl; i < i_hi; i += nslice) {
                     const double zb_ = s_wp[size_t(j) * Np + i];
                     acc += ((p.zb[i] >> s2) & 1u) ? zb_ : -zb_;
                 }
@@ -665,9 +717,34 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             }
         }
         __syncthreads();
+        if constexpr (CL) {        // totals and C_bar over the windows: rank 0 sums them (fixed rank order)
+            auto cl = cg::this_cluster();
+            cl.sync();
+            if (crank == 0) {
+                double tsum[(SQB_NT + SQ_THREADS - 1) / SQ_THREADS], csum = 0.0;
+#pragma unroll
+                for (int u = 0; u < (SQB_NT + SQ_THREADS - 1) / SQ_THREADS; ++u) {
+                    const int e = tid + u * SQ_THREADS;
+                    tsum[u] = 0.0;
+                    if (e < SQB_NT)
+                        for (int r = 0; r < SQB_CLUSTER; ++r) tsum[u] += cl.map_shared_rank(tot, r)[e];
+                }
+                const int cidx = (tid / Sp) * MAX_SP + (tid % Sp);
+                if (tid < Q * Sp)
+                    for (int r = 0; r < SQB_CLUSTER; ++r) csum += cl.map_shared_rank(s_Cbar, r)[cidx];
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < (SQB_NT + SQ_THREADS - 1) / SQ_THREADS; ++u) {
+                    const int e = tid + u * SQ_THREADS;
+                    if (e < SQB_NT) tot[e] = tsum[u];
+                }
+                if (tid < Q * Sp) s_Cbar[cidx] = csum;
+                __syncthreads();
+            }
+        }
 
-        // ---- final: q x q algebra (one thread) ----------------------------------------------------------------------------------
-        if (tid == 0) {
+        // ---- final: q x q algebra (one thread; rank 0 of the cluster) ------------------------------------------------------------
+        if (tid == 0 && crank == 0) {
             double Si[Q][Q], Lf[Q][Q], shr[Q][Q], shr_bar[Q][Q], Sinv_bar[Q][Q];
             for (int j = 0; j < Q; ++j)
                 for (int k = 0; k < Q; ++k) {
@@ -765,9 +842,15 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             p.acq[c] = tot_acq / double(S);
         }
         __syncthreads();
+        if constexpr (CL) {        // ut_bar lives in rank 0's shared memory
+            auto cl = cg::this_cluster();
+            cl.sync();
+            if (crank != 0 && tid < MAX_Q * MAX_SP) s_utb[tid] = cl.map_shared_rank(s_utb, 0)[tid];
+            __syncthreads();
+        }
         // fold the probe term into the right-hand sides: w_bar'_j = w_bar_j + z ut_bar_j   (T = A^-1 z)
         if (SOFT && !bad)
-            for (int i = tid; i < N; i += SQ_THREADS) {
+            for (int i = i_lo + tid; i < i_hi; i += SQ_THREADS) {
                 const uint32_t bits = p.zb[i];
 #pragma unroll
                 for (int j = 0; j < Q; ++j) {
@@ -777,6 +860,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                 }
             }
         __syncthreads();
+        if constexpr (CL) cg::this_cluster().sync();      // remote shared memory stays valid until every CTA is done with it
     }
 }
 
