@@ -92,10 +92,15 @@ class ConformalAcquisition(nn.Module):
         """Trailing dimension of the acquisition sampler's base samples (q; nb + q for the noisy-EI joint sample)."""
         return q
 
-    def _conformal_fwd(self, X: torch.Tensor, outputs=()) -> torch.Tensor:
+    def value_and_grad(self, X: torch.Tensor):
+        """(acq (b,), d acq / d X (b, q, d)) from ONE library call, without an autograd graph: what a device-side
+        optimiser loop needs per step (optim.optimize_acqf_sgld)."""
+        return self._conformal_fwd(X.detach(), raw_grad=True)
+
+    def _conformal_fwd(self, X: torch.Tensor, outputs=(), raw_grad=False) -> torch.Tensor:
         if self.model is None:
             raise AttributeError("ConformalAcquisition must be subclassed")
-        want_grad = X.requires_grad and torch.is_grad_enabled()
+        want_grad = raw_grad or (X.requires_grad and torch.is_grad_enabled())
         X_in = X
         state = as_state(self.model)
         if X.ndim == 2:                                          # t_batch_mode_transform: add the t-batch dim
@@ -126,6 +131,9 @@ class ConformalAcquisition(nn.Module):
                                 max_grid_refinements=self.max_grid_refinements, randomized=self.randomized,
                                 optimistic=self.optimistic, **self._acq_params())
         self.last_outputs = out
+        if raw_grad:
+            q_in = (X_in.unsqueeze(0) if X_in.ndim == 2 else X_in).shape[-2]
+            return out["acq"].reshape(lead), out["dacq_dX"][:, :q_in, :].reshape(*lead, q_in, d)
         if want_grad:
             Xg = X_in.unsqueeze(0) if X_in.ndim == 2 else X_in
             q_in = Xg.shape[-2]                                          # pending points (appended last) carry no gradient

@@ -9,6 +9,7 @@
 
 #include "../../include/cbo.h"
 #include "bounds.cuh"
+#include <cmath>
 #include "common.cuh"
 #include "gemm_tri.cuh"
 #include "rows.cuh"
@@ -19,6 +20,7 @@
 #include "nei.cuh"
 #include "rows_bwd.cuh"
 #include "ratio_mma.cuh"
+#include "ratio_train.cuh"
 #include "model_build.cuh"
 #include "score_q_bwd.cuh"
 
@@ -379,6 +381,59 @@ int cbo_ratio_forward_f64(const cbo_ratio_mlp_f64* r, const double* x, int64_t n
     if (d > cbo::MAX_D) return CBO_ERR_UNSUPPORTED;
     CBO_CUDA(cbo::launch_ratio_mlp(x, (int)n, (int)d, (int)r->hidden, r->W1, r->b1, r->W2, r->b2, r->W3, r->b3, 0.0, out,
                                    num_sms(), static_cast<cudaStream_t>(stream)));
+    return CBO_OK;
+}
+
+size_t cbo_ratio_train_workspace_bytes(int64_t n_rows, int64_t d) {
+    if (n_rows <= 0 || d <= 0 || d > cbo::RT_MAX_D) return 0;
+    const int64_t tiles = (n_rows + cbo::RT_ROWS - 1) / cbo::RT_ROWS;
+    return size_t(tiles) * size_t(cbo::ratio_num_params((int)d) + 1) * sizeof(double);
+}
+
+int cbo_ratio_train_step_f64(int64_t d, int64_t hidden, double* theta, double* adam_m, double* adam_v, double* target,
+                             const double* x_neg, int64_t n_neg, const double* x_pos, const int64_t* pos_idx,
+                             int64_t n_pos, int64_t step, double lr, double beta1, double beta2, double eps,
+                             double weight_decay, double ema_weight, double* loss, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+    if (!theta || !adam_m || !adam_v || !target || !workspace || d <= 0 || step < 1 || n_neg < 0 || n_pos < 0 ||
+        n_neg + n_pos <= 0 || (n_neg > 0 && !x_neg) || (n_pos > 0 && !x_pos))
+        return CBO_ERR_INVALID_ARG;
+    if (hidden != cbo::RT_H || d > cbo::RT_MAX_D || n_neg + n_pos > (int64_t(1) << 30)) return CBO_ERR_UNSUPPORTED;
+    const int64_t n_rows = n_neg + n_pos;
+    if (workspace_bytes < cbo_ratio_train_workspace_bytes(n_rows, d) || (reinterpret_cast<uintptr_t>(workspace) & 7))
+        return CBO_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int tiles = int((n_rows + cbo::RT_ROWS - 1) / cbo::RT_ROWS);
+    const size_t smem = cbo::ratio_train_smem_bytes((int)d);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CBO_CUDA(cudaFuncSetAttribute(cbo::k_ratio_train_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    double* partial = static_cast<double*>(workspace);
+    cbo::k_ratio_train_grad<<<tiles, cbo::RT_THREADS, smem, st>>>(theta, (int)d, x_neg, (int)n_neg, x_pos, pos_idx,
+                                                                  (int)n_pos, partial);
+    CBO_CUDA(cudaGetLastError());
+    const int64_t P = cbo::ratio_num_params((int)d);
+    const double bc1 = 1.0 - std::pow(beta1, double(step)), bc2 = 1.0 - std::pow(beta2, double(step));
+    cbo::k_ratio_adam_ema<<<int((P + 1 + 255) / 256), 256, 0, st>>>(theta, adam_m, adam_v, target, partial, tiles, P,
+                                                                   double(n_rows), lr / bc1, 1.0 / std::sqrt(bc2), beta1,
+                                                                   beta2, eps, weight_decay, ema_weight, loss);
+    CBO_CUDA(cudaGetLastError());
+    return CBO_OK;
+}
+
+int cbo_sgld_update_f64(double* X, double* momentum_buf, const double* dacq_dX, const double* noise, const double* lb,
+                        const double* ub, int64_t n_rows, int64_t d, double lr, double momentum, double temperature,
+                        double penalty_scale, double penalty_width, void* stream) {
+    if (!X || !dacq_dX || !noise || !lb || !ub || n_rows <= 0 || d <= 0 || lr < 0.0 || momentum < 0.0 ||
+        temperature < 0.0 || penalty_width <= 0.0 || (momentum > 0.0 && !momentum_buf))
+        return CBO_ERR_INVALID_ARG;
+    const int64_t n = n_rows * d;
+    const double ns = momentum > 0.0 ? std::sqrt(2.0 * lr * momentum * temperature) : std::sqrt(2.0 * lr * temperature);
+    cbo::k_sgld_update<<<int((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        X, momentum_buf, dacq_dX, noise, lb, ub, n, (int)d, lr, momentum, ns, penalty_scale, penalty_width);
+    CBO_CUDA(cudaGetLastError());
     return CBO_OK;
 }
 

@@ -36,6 +36,18 @@ class RatioWeights:
         f = lambda t: t.detach().to(device=device, dtype=torch.float64).contiguous()
         return cls(f(lin[0].weight), f(lin[0].bias), f(lin[1].weight), f(lin[1].bias), f(lin[2].weight), f(lin[2].bias))
 
+    @classmethod
+    def from_flat(cls, flat: torch.Tensor, d: int, hidden: int = 64) -> "RatioWeights":
+        """Views into a flat parameter vector in torch's parameter order (the layout cbo_ratio_train_step_f64 updates in
+        place): the acquisition kernels then always read the current target network, with no copies."""
+        o, out = 0, []
+        for n, shape in ((hidden * d, (hidden, d)), (hidden, (hidden,)), (hidden * hidden, (hidden, hidden)),
+                         (hidden, (hidden,)), (hidden, (1, hidden)), (1, (1,))):
+            out.append(flat[o:o + n].view(shape))
+            o += n
+        assert o == flat.numel()
+        return cls(*out)
+
     def c_struct(self) -> "_lib.RatioMlpF64":
         return _lib.RatioMlpF64(self.W1.shape[0], self.W1.data_ptr(), self.b1.data_ptr(), self.W2.data_ptr(),
                                 self.b2.data_ptr(), self.W3.data_ptr(), self.b3.data_ptr())
@@ -275,6 +287,50 @@ def ratio_forward(ratio: RatioWeights, x: torch.Tensor) -> torch.Tensor:
     st = lib.cbo_ratio_forward_f64(C.byref(rc), x2.data_ptr(), x2.shape[0], x2.shape[1], out.data_ptr(), _stream())
     _lib.check(st, "cbo_ratio_forward_f64")
     return out.reshape(shape)
+
+
+def ratio_num_params(d: int, hidden: int = 64) -> int:
+    return hidden * d + hidden + hidden * hidden + hidden + hidden + 1
+
+
+def ratio_train_step(theta: torch.Tensor, adam_m: torch.Tensor, adam_v: torch.Tensor, target: torch.Tensor, *,
+                     x_neg: torch.Tensor, x_pos: torch.Tensor, pos_idx: Optional[torch.Tensor], n_pos: int, step: int,
+                     lr: float, weight_decay: float, ema_weight: float, betas=(0.9, 0.999), eps: float = 1e-8,
+                     loss: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """One classifier training step + EMA, in place on the flat fp64 device vectors (ratio_estimation.py:133-144)."""
+    lib = _lib.load()
+    _require_cuda(theta, adam_m, adam_v, target, x_neg, x_pos, pos_idx, loss)
+    d = x_neg.shape[-1]
+    assert theta.numel() == ratio_num_params(d) and x_pos.shape[-1] == d
+    for t in (theta, adam_m, adam_v, target, x_neg, x_pos):
+        assert t.dtype == torch.float64 and t.is_contiguous()
+    assert pos_idx is None or (pos_idx.dtype == torch.int64 and pos_idx.numel() >= n_pos)
+    n_rows = x_neg.shape[0] + n_pos
+    need = lib.cbo_ratio_train_workspace_bytes(n_rows, d)
+    if workspace is None or workspace.numel() * 8 < need:
+        workspace = torch.empty((need + 7) // 8, dtype=torch.float64, device=theta.device)
+    st = lib.cbo_ratio_train_step_f64(d, 64, theta.data_ptr(), adam_m.data_ptr(), adam_v.data_ptr(), target.data_ptr(),
+                                      x_neg.data_ptr(), x_neg.shape[0], x_pos.data_ptr(), _ptr(pos_idx), n_pos, step,
+                                      lr, betas[0], betas[1], eps, weight_decay, ema_weight, _ptr(loss),
+                                      workspace.data_ptr(), workspace.numel() * 8, _stream())
+    _lib.check(st, "cbo_ratio_train_step_f64")
+    return workspace
+
+
+def sgld_update(X: torch.Tensor, momentum_buf: Optional[torch.Tensor], dacq_dX: torch.Tensor, noise: torch.Tensor,
+                lb: torch.Tensor, ub: torch.Tensor, *, lr: float, momentum: float, temperature: float,
+                penalty_scale: float = 1e2, penalty_width: float = 1e-2):
+    """In-place SGLD / SGHMC update of the candidates with the box penalty (optim/optimize.py:224-235, optim/sgld.py:9-47)."""
+    lib = _lib.load()
+    _require_cuda(X, momentum_buf, dacq_dX, noise, lb, ub)
+    d = X.shape[-1]
+    for t in (X, momentum_buf, dacq_dX, noise, lb, ub):
+        assert t is None or (t.dtype == torch.float64 and t.is_contiguous())
+    assert dacq_dX.shape == X.shape and noise.shape == X.shape and lb.numel() == d and ub.numel() == d
+    st = lib.cbo_sgld_update_f64(X.data_ptr(), _ptr(momentum_buf), dacq_dX.data_ptr(), noise.data_ptr(), lb.data_ptr(),
+                                 ub.data_ptr(), X.numel() // d, d, lr, momentum, temperature, penalty_scale,
+                                 penalty_width, _stream())
+    _lib.check(st, "cbo_sgld_update_f64")
 
 
 def gemm_tn(A: torch.Tensor, B: torch.Tensor, tri: int = 0, rownorm: bool = False):

@@ -1,0 +1,155 @@
+"""`optimize_acqf_sgld` with the reference's signature and loop (conformalbo/optim/optimize.py:23-283), run on the device.
+
+Per SGLD step the reference does: `callback(iterates.cpu())` (the ratio-estimator training step), `acq(X)`, autograd
+`backward()` through the conformal path and the box penalty, an SGHMC update (optim/sgld.py) and a cosine learning-rate
+step.  Here a step is: `RatioEstimator.optimize_callback` on the device iterates (two kernels, no `.cpu()`), ONE
+value+gradient library call (`acq.value_and_grad`), one normal draw and ONE `k_sgld_update` launch (penalty gradient +
+momentum + noise + parameter update); the learning rate follows the closed form of CosineAnnealingLR.
+
+The initial conditions come from botorch's `gen_batch_initial_conditions` in the reference [3P, not installed here]; its
+heuristic is restated from the published algorithm (Sobol raw samples, Boltzmann selection with eta = 2 on the
+standardised acquisition values, the best raw sample always kept).  Constraints, fixed features, `sequential=True` and
+one-shot acquisition functions are not built (the reference's scripts never pass them, scripts/black_box_opt.py:131-143).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Optional, Tuple, Union
+
+import torch
+
+from . import ops
+
+
+def gen_batch_initial_conditions(acq_function, bounds: torch.Tensor, q: int, num_restarts: int, raw_samples: int,
+                                 options: Optional[Dict] = None) -> torch.Tensor:
+    """botorch.optim.initializers.gen_batch_initial_conditions + initialize_q_batch [3P], restated."""
+    options = options or {}
+    d = bounds.shape[-1]
+    seed = options.get("seed")
+    batch_limit = options.get("init_batch_limit", options.get("batch_limit"))
+    eta = options.get("eta", 2.0)
+    engine = torch.quasirandom.SobolEngine(dimension=q * d, scramble=True, seed=seed)
+    X = engine.draw(raw_samples, dtype=torch.float64).view(raw_samples, q, d).to(bounds)
+    X = bounds[0] + (bounds[1] - bounds[0]) * X
+    with torch.no_grad():
+        Y = torch.cat([acq_function(x) for x in X.split(batch_limit or raw_samples)])
+    if num_restarts > raw_samples:
+        raise RuntimeError(f"num_restarts ({num_restarts}) exceeds raw_samples ({raw_samples})")
+    if num_restarts == raw_samples:
+        return X
+    Ystd = Y.std()
+    if not bool(Ystd > 0):
+        return X[torch.randperm(raw_samples, device=X.device)[:num_restarts]]
+    max_idx = Y.argmax()
+    etaZ = eta * (Y - Y.mean()) / Ystd
+    weights = torch.exp(etaZ)
+    while torch.isinf(weights).any():
+        etaZ = etaZ * 0.5
+        weights = torch.exp(etaZ)
+    idcs = torch.multinomial(weights, num_restarts)
+    if not bool((idcs == max_idx).any()):
+        idcs[-1] = max_idx
+    return X[idcs]
+
+
+def cosine_lr(step: int, lr: float, T_max: int, eta_min: float) -> float:
+    """Closed form of torch.optim.lr_scheduler.CosineAnnealingLR after `step` scheduler steps (cycles past T_max)."""
+    return eta_min + (lr - eta_min) * (1.0 + math.cos(math.pi * step / T_max)) / 2.0
+
+
+def _value_and_grad(acq_function, X):
+    if hasattr(acq_function, "value_and_grad"):
+        return acq_function.value_and_grad(X)
+    Xg = X.detach().clone().requires_grad_(True)           # any other differentiable acquisition function
+    vals = acq_function(Xg)
+    (g,) = torch.autograd.grad(vals.sum(), Xg)
+    return vals.detach(), g
+
+
+def optimize_acqf_sgld(
+    acq_function,
+    bounds: torch.Tensor,
+    q: int,
+    num_restarts: int,
+    raw_samples: Optional[int] = None,
+    options: Optional[Dict[str, Union[bool, float, int, str, Callable]]] = None,
+    inequality_constraints=None,
+    equality_constraints=None,
+    nonlinear_inequality_constraints=None,
+    fixed_features=None,
+    post_processing_func: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
+    batch_initial_conditions: Optional[torch.Tensor] = None,
+    return_best_only: bool = True,
+    sequential: bool = False,
+    warmup_steps: int = 32,
+    sgld_steps: int = 256,
+    lr: float = 1e-3,
+    temperature: float = 5e-2,
+    return_full_traj: bool = False,
+    **kwargs,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Multi-start SGLD on the acquisition surface; returns (candidates, acquisition values) as the reference does:
+    per restart the best in-bounds iterate of its trajectory, then the best restart if `return_best_only`."""
+    if inequality_constraints or equality_constraints or nonlinear_inequality_constraints or fixed_features:
+        raise NotImplementedError("constraints / fixed features are not built (unused by the reference's scripts)")
+    if sequential and q > 1:
+        raise NotImplementedError("sequential=True is not built (the reference's scripts optimise jointly)")
+    if not bounds.is_cuda:
+        raise RuntimeError("optimize_acqf_sgld runs on the device: `bounds` must be a CUDA tensor")
+    options = options or {}
+    bounds = bounds.to(torch.float64)
+    d = bounds.shape[-1]
+    if batch_initial_conditions is None:
+        if raw_samples is None:
+            raise ValueError("Must specify `raw_samples` when `batch_initial_conditions` is `None`.")
+        batch_initial_conditions = gen_batch_initial_conditions(acq_function, bounds, q, num_restarts, raw_samples, options)
+    batch_limit = options.get("batch_limit", num_restarts)
+    # one contiguous (restarts, q, d) fp64 buffer per optimiser batch, updated in place
+    batched_ics = [b.contiguous() for b in
+                   batch_initial_conditions.detach().to(bounds.device, torch.float64).clone().split(batch_limit)]
+    momentum = 0.1
+    scaled_temp = temperature / math.sqrt(d)               # rescale temp so noise has consistent norm (optimize.py:197)
+    bufs = [torch.zeros_like(b) for b in batched_ics]
+    T_max, eta_min = sgld_steps // 4, lr / 16.0            # cyclic learning rate (optimize.py:202-207)
+    lb, ub = bounds[0].contiguous(), bounds[1].contiguous()
+    callback = options.get("callback")
+    sgld_iterates = [[b.clone()] for b in batched_ics]
+
+    for _s in range(sgld_steps):
+        lr_s = cosine_lr(_s, lr, T_max, eta_min)
+        for batch_idx, ic_batch in enumerate(batched_ics):
+            if _s >= warmup_steps:                         # once the chain has warmed up, train the ratio estimator
+                sgld_iterates[batch_idx].append(ic_batch.clone())
+                if callable(callback):
+                    callback(ic_batch.clone())             # stays on the device (the reference hands over `.cpu()`)
+            if _s < sgld_steps - 1:
+                _, dacq = _value_and_grad(acq_function, ic_batch)
+                noise = torch.randn_like(ic_batch)
+                ops.sgld_update(ic_batch, bufs[batch_idx], dacq.to(torch.float64).contiguous(), noise, lb, ub, lr=lr_s,
+                                momentum=momentum, temperature=scaled_temp)
+
+    batch_candidates = torch.cat([torch.stack(it, dim=1) for it in sgld_iterates])      # (restarts, T, q, d)
+    if return_full_traj:
+        with torch.no_grad():
+            batch_acq_values = torch.cat([acq_function(c) for c in batch_candidates.flatten(0, -3).split(batch_limit)
+                                          ]).view(batch_candidates.shape[:-2])
+    else:
+        select_cands, select_vals = [], []
+        with torch.no_grad():
+            for cand_traj in batch_candidates:
+                in_bounds = ((cand_traj >= lb).all(-1) & (cand_traj <= ub).all(-1)).all(-1)
+                feas = cand_traj[in_bounds]
+                if feas.shape[0] == 0:
+                    raise RuntimeError("no SGLD iterate of a restart lies inside the bounds")
+                vals = torch.cat([acq_function(c) for c in feas.split(batch_limit)])
+                best = vals.argmax(0)
+                select_cands.append(feas[best])
+                select_vals.append(vals[best])
+        batch_candidates, batch_acq_values = torch.stack(select_cands), torch.stack(select_vals)
+        if return_best_only:
+            best = batch_acq_values.argmax(0)
+            batch_candidates, batch_acq_values = batch_candidates[best], batch_acq_values[best]
+    if post_processing_func is not None:
+        batch_candidates = post_processing_func(batch_candidates)
+    return batch_candidates, batch_acq_values

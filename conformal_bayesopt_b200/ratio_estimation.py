@@ -1,20 +1,24 @@
-"""Density-ratio estimator, inference side (reference: conformalbo/ratio_estimation.py:60-107).
+"""Density-ratio estimator (reference: conformalbo/ratio_estimation.py:60-144).
 
 `forward` -- the part on the acquisition hot path (ratio_estimation.py:97-99) -- runs in the CUDA
 kernel `k_ratio_mlp_mma` (fp64 tensor path) when the input is on a CUDA device; the acquisition kernels themselves consume
-the target-network weights directly (no per-candidate Python call).  Online training of the
-classifier (`optimize_callback`, `_Dataset`; ratio_estimation.py:110-144) is out of scope
-(SURVEY.md §2 #5): the EMA update of the target network is provided so that externally trained
-classifiers can be plugged in.
+the target-network weights directly (no per-candidate Python call).
+
+`optimize_callback` (ratio_estimation.py:110-144) trains on the device: the SGLD iterates are appended to
+a device-resident pool, and one call of `cbo_ratio_train_step_f64` (two launches) does the BCE forward/reverse pass over
+[negatives; sampled positives], the Adam step and the EMA of the target network, in place on flat fp64 parameter vectors
+that the acquisition kernels read directly -- no `.cpu()` round trip per SGLD step (optim/optimize.py:222).  The unused
+`_Dataset` bookkeeping of the reference (train/val/test splits that `optimize_callback` never reads) is not rebuilt.
 """
 from __future__ import annotations
 
 import copy
 
+import numpy as np
 import torch
 from torch import nn
 
-from . import ops
+from . import _lib, ops
 
 
 class RatioEstimator(nn.Module):
@@ -33,6 +37,12 @@ class RatioEstimator(nn.Module):
             tgt_p.data.fill_(0.0)
         self._ema_weight = ema_weight
         self._weights_cache = None
+        self._lr, self._weight_decay = lr, weight_decay       # torch.optim.Adam(lr, weight_decay) of the reference (:91)
+        self._train = None                # device training state, created by the first training step
+        self._pos_pool, self._num_pos = None, 0
+        self._neg_dev = None
+        self.device_permutation = False   # True: draw the positive minibatch with torch.randperm on the device
+        self.last_loss = None             # device scalar, minibatch loss of the latest step
 
     def set_neg_samples(self, neg_samples):
         self._neg_samples = neg_samples
@@ -40,8 +50,56 @@ class RatioEstimator(nn.Module):
     def set_pos_samples(self, pos_samples):
         self._pos_samples  # no-op, as in the reference (ratio_estimation.py:94-95)
 
+    @property
+    def num_positive(self) -> int:
+        return self._num_pos
+
+    @staticmethod
+    def _token(net):
+        return tuple((p.data_ptr(), p._version) for p in net.parameters())
+
+    def _train_state(self, device):
+        """Flat fp64 device vectors (theta, Adam moments, target) shared with the kernels.  The nn modules stay the
+        public view: cuda fp64 modules are re-pointed at slices of the flat vectors (zero copy), others are refreshed
+        after every step; edits made to the modules from outside are picked up (parameter version counters)."""
+        t = self._train
+        if t is None or t["device"] != device:
+            P = ops.ratio_num_params(self.in_size)
+            z = lambda: torch.zeros(P, dtype=torch.float64, device=device)
+            t = self._train = dict(device=device, theta=z(), m=z(), v=z(), target=z(), step=0, tok_c=None, tok_t=None,
+                                   loss=torch.zeros((), dtype=torch.float64, device=device), ws=None, views=False)
+            t["weights"] = ops.RatioWeights.from_flat(t["target"], self.in_size)
+        flatten = lambda net: torch.cat([p.detach().reshape(-1) for p in net.parameters()]).to(device, torch.float64)
+        if t["tok_c"] != self._token(self.classifier):
+            t["theta"].copy_(flatten(self.classifier))
+        if t["tok_t"] != self._token(self._target_network):
+            t["target"].copy_(flatten(self._target_network))
+        if t["tok_c"] is None:
+            p0 = next(self.classifier.parameters())
+            if p0.device == device and p0.dtype == torch.float64:
+                for net, flat in ((self.classifier, t["theta"]), (self._target_network, t["target"])):
+                    torch.nn.utils.vector_to_parameters(flat, net.parameters())
+                t["views"] = True
+        t["tok_c"], t["tok_t"] = self._token(self.classifier), self._token(self._target_network)
+        return t
+
+    def _publish(self, t):
+        if not t["views"]:
+            with torch.no_grad():
+                for net, flat in ((self.classifier, t["theta"]), (self._target_network, t["target"])):
+                    p0 = next(net.parameters())
+                    torch.nn.utils.vector_to_parameters(flat.to(device=p0.device, dtype=p0.dtype), net.parameters())
+            self._weights_cache = None
+        t["tok_c"], t["tok_t"] = self._token(self.classifier), self._token(self._target_network)
+
     def device_weights(self, device) -> "ops.RatioWeights":
         """fp64 device copies of the target-network weights for the kernels (refreshed after every update)."""
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        t = self._train
+        if t is not None and t["device"] == device:
+            return self._train_state(device)["weights"]       # the flat target vector itself: always current
         if not hasattr(self, "_target_params"):
             self._target_params = list(self._target_network.parameters())
         key = (device, tuple(p._version for p in self._target_params))
@@ -61,6 +119,54 @@ class RatioEstimator(nn.Module):
                 tgt_p.mul_(1.0 - self._ema_weight)
                 tgt_p.add_(self._ema_weight * src_p)
 
+    def _training_device(self, xk) -> torch.device:
+        for cand in (self.device, getattr(self._neg_samples, "device", None), xk.device):
+            if cand is not None and torch.device(cand).type == "cuda":
+                dev = torch.device(cand)
+                return dev if dev.index is not None else torch.device("cuda", torch.cuda.current_device())
+        raise _lib.CboError("RatioEstimator.optimize_callback trains on the device (libcbo has no CPU path): "
+                            "construct the estimator with a CUDA device or pass CUDA samples")
+
+    def _append_positives(self, xk, device):
+        n = xk.shape[0]
+        if self._pos_pool is None or self._pos_pool.device != device:
+            old = self._pos_pool
+            self._pos_pool = torch.empty(max(1024, 2 * n), self.in_size, dtype=torch.float64, device=device)
+            if old is not None:
+                self._pos_pool[:self._num_pos].copy_(old[:self._num_pos])
+        if self._num_pos + n > self._pos_pool.shape[0]:
+            grown = torch.empty(2 * (self._num_pos + n), self.in_size, dtype=torch.float64, device=device)
+            grown[:self._num_pos].copy_(self._pos_pool[:self._num_pos])
+            self._pos_pool = grown
+        self._pos_pool[self._num_pos:self._num_pos + n].copy_(xk, non_blocking=True)
+        self._num_pos += n
+
     def optimize_callback(self, xk):
-        raise NotImplementedError(
-            "online ratio-estimator training (ratio_estimation.py:110-144) is outside the hot path (SURVEY.md §8f-4)")
+        """ratio_estimation.py:110-144: collect the SGLD iterates as positives; once there are at least as many as
+        negatives, one Adam step on BCE-with-logits over [negatives; an equally large random subset of the positives],
+        then the EMA update of the target network.  Everything after the host-side bookkeeping runs in two kernels."""
+        if isinstance(xk, np.ndarray):
+            xk = torch.from_numpy(xk)
+        xk = xk.detach().reshape(-1, self.in_size)
+        device = self._training_device(xk)
+        self._append_positives(xk, device)
+        if self._neg_samples is None:
+            return None
+        num_negative, num_positive = self._neg_samples.size(0), self._num_pos
+        if num_positive < num_negative:
+            return None
+        if self._neg_dev is None or self._neg_dev[0] is not self._neg_samples or self._neg_dev[1].device != device:
+            self._neg_dev = (self._neg_samples, self._neg_samples.detach().to(device, torch.float64).contiguous())
+        if self.device_permutation:
+            idx = torch.randperm(num_positive, device=device)[:num_negative].contiguous()
+        else:       # the reference's generator and draw (:129-131), 8 bytes per row to the device
+            idx = torch.from_numpy(np.random.permutation(num_positive)[:num_negative].copy()).to(device, non_blocking=True)
+        t = self._train_state(device)
+        t["step"] += 1
+        t["ws"] = ops.ratio_train_step(t["theta"], t["m"], t["v"], t["target"], x_neg=self._neg_dev[1],
+                                       x_pos=self._pos_pool, pos_idx=idx, n_pos=num_negative, step=t["step"],
+                                       lr=self._lr, weight_decay=self._weight_decay, ema_weight=self._ema_weight,
+                                       loss=t["loss"], workspace=t["ws"])
+        self.last_loss = t["loss"]
+        self._publish(t)
+        return None

@@ -176,6 +176,30 @@ int cbo_conf_mask_to_bounds_f64(const double* target_grid, const double* conf_pr
 int cbo_ratio_forward_f64(const cbo_ratio_mlp_f64* ratio, const double* x, int64_t n, int64_t d, double* out,
                           void* stream);
 
+/* Density-ratio classifier, ONE training step on the device (conformalbo/ratio_estimation.py:133-144, the body of
+ * RatioEstimator.optimize_callback once the minibatch is chosen): mean BCE-with-logits over [x_neg (n_neg x d, label 0);
+ * x_pos[pos_idx] (n_pos rows, label 1; pos_idx NULL = the first n_pos rows)], one torch.optim.Adam step on the classifier
+ * (weight_decay is L2 added to the gradient; step is 1-based), then update_target_network (:101-107):
+ * target <- (1 - ema_weight) target + ema_weight theta.  theta, adam_m, adam_v, target: flat vectors of
+ * hidden*d + hidden + hidden^2 + hidden + hidden + 1 doubles in torch's parameter order (W1, b1, W2, b2, W3, b3); the
+ * cbo_ratio_mlp_f64 of the acquisition calls may point straight into `target`.  hidden must be 64, d <= 64.
+ * loss (device scalar, may be NULL) receives the minibatch loss.  Two launches, fixed-order reductions, no host sync. */
+size_t cbo_ratio_train_workspace_bytes(int64_t n_rows, int64_t d);
+int cbo_ratio_train_step_f64(int64_t d, int64_t hidden, double* theta, double* adam_m, double* adam_v, double* target,
+                             const double* x_neg, int64_t n_neg, const double* x_pos, const int64_t* pos_idx,
+                             int64_t n_pos, int64_t step, double lr, double beta1, double beta2, double eps,
+                             double weight_decay, double ema_weight, double* loss, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* One SGLD / SGHMC update of the candidates inside optimize_acqf_sgld (conformalbo/optim/optimize.py:224-235 with
+ * conformalbo/optim/sgld.py:9-47): gradient of  -sum(acq) + penalty_scale * (sigmoid((lb - X)/w).mean() +
+ * sigmoid((X - ub)/w).mean())  from dacq_dX, then  buf <- (1 - momentum) buf - lr g + sqrt(2 lr momentum T) noise,
+ * X <- X + buf  (momentum == 0: X <- X - lr g + sqrt(2 lr T) noise).  X, momentum_buf, dacq_dX, noise: n_rows x d; lb, ub: d.
+ * The reference uses penalty_scale = 1e2, w = 1e-2, momentum = .1, T = temperature / sqrt(d). */
+int cbo_sgld_update_f64(double* X, double* momentum_buf, const double* dacq_dX, const double* noise, const double* lb,
+                        const double* ub, int64_t n_rows, int64_t d, double lr, double momentum, double temperature,
+                        double penalty_scale, double penalty_width, void* stream);
+
 /* Model-state builder (the step before the hot path; conformalbo/utils.py:382-390 refits SingleTaskGP and GPyTorch caches
  * the same factors): raw training data + fixed hyper-parameters -> alpha (Np), linv and linv_t (Np x Np) of cbo_gp_f64.
  * Blocked Cholesky and triangular inverse on the fp64 tensor path.  info (device int, may be NULL) receives 0, or

@@ -1,0 +1,195 @@
+"""Training-side device steps through the C-ABI against outputs of the reference's own RatioEstimator and
+SGLD classes (tests/golden/ref_training.pt) and the numpy oracle (oracle/training.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import training as T
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_training.pt")
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLD)
+
+
+def _cmp(ref, got, tol):
+    ref = ref.numpy()
+    got = got.detach().cpu().numpy()
+    stride = 1 if ref.size == got.size else 37
+    np.testing.assert_allclose(got[::stride], ref, rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_train_step_kernel_replays_the_reference_class(gold, idx):
+    """cbo_ratio_train_step_f64 driven with the minibatches the reference drew: parameters and target network after every
+    callback.  Absolute tolerance 1e-9 (a 1e-6th of one Adam step): m / (sqrt(v) + eps) amplifies summation-order
+    rounding only where |g| ~ eps."""
+    from conformal_bayesopt_b200 import ops
+    case = gold["ratio_training"][idx]
+    d = case["d"]
+    theta = case["theta0"].to(DEV).clone()
+    m, v, target = torch.zeros_like(theta), torch.zeros_like(theta), torch.zeros_like(theta)
+    loss = torch.zeros((), dtype=torch.float64, device=DEV)
+    neg = case["neg"].to(DEV)
+    pool = torch.zeros(0, d, dtype=torch.float64, device=DEV)
+    step = 0
+    for k, (xk, perm, trained) in enumerate(zip(case["callbacks"], case["perms"], case["trained"])):
+        pool = torch.cat([pool, xk.to(DEV)])
+        if trained:
+            step += 1
+            th_before = theta.cpu().numpy().copy()
+            ops.ratio_train_step(theta, m, v, target, x_neg=neg, x_pos=pool, pos_idx=perm.to(DEV), n_pos=neg.shape[0],
+                                 step=step, lr=case["lr"], weight_decay=case["weight_decay"],
+                                 ema_weight=case["ema_weight"], loss=loss)
+            x = np.concatenate([neg.cpu().numpy(), pool.cpu().numpy()[perm.numpy()]])
+            y = np.concatenate([np.zeros(neg.shape[0]), np.ones(neg.shape[0])])
+            l_ref, _ = T.classifier_loss_grad(th_before, x, y, d)
+            assert abs(loss.item() - l_ref) < 1e-13
+        _cmp(case["theta"][k], theta, 1e-9)
+        _cmp(case["target"][k], target, 1e-9)
+
+
+@pytest.mark.parametrize("idx", [0, 2])
+def test_ratio_estimator_class_trains_like_the_reference(gold, idx):
+    """RatioEstimator.optimize_callback end to end (device pool, np.random minibatch draw, kernels, module views) and the
+    density ratios the trained target network then yields."""
+    from conformal_bayesopt_b200.ratio_estimation import RatioEstimator
+    case = gold["ratio_training"][idx]
+    d = case["d"]
+    est = RatioEstimator(in_size=d, device=DEV, dtype=torch.float64, ema_weight=case["ema_weight"], lr=case["lr"],
+                         weight_decay=case["weight_decay"])
+    torch.nn.utils.vector_to_parameters(case["theta0"].to(DEV).clone(), est.classifier.parameters())
+    est.set_neg_samples(case["neg"].to(DEV))
+    np.random.seed(case["seed"])
+    flat = lambda net: torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    for k, xk in enumerate(case["callbacks"]):
+        est.optimize_callback(xk.clone())                 # CPU iterates are accepted (copied into the device pool)
+        _cmp(case["theta"][k], flat(est.classifier), 1e-9)
+        _cmp(case["target"][k], flat(est._target_network), 1e-9)
+    r = est(case["x_test"].to(DEV))
+    np.testing.assert_allclose(r.cpu().numpy(), case["ratio_test"].numpy(), rtol=1e-7)
+    # the acquisition kernels read the flat target vector itself
+    w = est.device_weights(DEV)
+    assert w.W1.data_ptr() == est._train["target"].data_ptr()
+
+
+def test_float32_cpu_modules_are_refreshed_after_each_step():
+    from conformal_bayesopt_b200.ratio_estimation import RatioEstimator
+    torch.manual_seed(0)
+    est = RatioEstimator(in_size=3, device=None, dtype=torch.float32)
+    est.set_neg_samples(torch.rand(8, 3, device=DEV))
+    before = [p.detach().clone() for p in est.classifier.parameters()]
+    est.optimize_callback(torch.rand(16, 3, device=DEV))
+    after = list(est.classifier.parameters())
+    assert after[0].dtype == torch.float32 and after[0].device.type == "cpu"
+    assert any(not torch.equal(a, b) for a, b in zip(after, before))
+    tgt = torch.cat([p.reshape(-1) for p in est._target_network.parameters()])
+    np.testing.assert_allclose(tgt.numpy(), est._train["target"].cpu().numpy(), rtol=1e-6, atol=1e-8)
+    assert float(est.last_loss) > 0
+
+
+def test_training_without_a_device_fails_loudly():
+    from conformal_bayesopt_b200 import _lib
+    from conformal_bayesopt_b200.ratio_estimation import RatioEstimator
+    est = RatioEstimator(in_size=2, dtype=torch.float64)
+    est.set_neg_samples(torch.rand(4, 2, dtype=torch.float64))
+    with pytest.raises(_lib.CboError):
+        est.optimize_callback(torch.rand(8, 2, dtype=torch.float64))
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_sgld_update_kernel_replays_the_reference_optimizer(gold, idx):
+    from conformal_bayesopt_b200 import ops
+    from conformal_bayesopt_b200.optim import cosine_lr
+    case = gold["sgld"][idx]
+    X = case["x0"].to(DEV).clone()
+    buf = torch.zeros_like(X)
+    d = X.shape[-1]
+    lb = torch.full((d,), -1e6, dtype=torch.float64, device=DEV)      # penalty identically zero
+    ub = torch.full((d,), 1e6, dtype=torch.float64, device=DEV)
+    for s in range(len(case["grads"])):
+        lr = cosine_lr(s, case["lr0"], case["T_max"], case["lr0"] / 16.0)
+        assert abs(lr - case["lrs"][s]) <= 1e-15 * abs(lr) + 1e-18
+        ops.sgld_update(X, buf, (-case["grads"][s]).to(DEV), case["noise"][s].to(DEV), lb, ub, lr=case["lrs"][s],
+                        momentum=0.1, temperature=case["scaled_temp"])
+        np.testing.assert_allclose(X.cpu().numpy(), case["xs"][s].numpy(), rtol=0, atol=1e-14)
+        np.testing.assert_allclose(buf.cpu().numpy(), case["bufs"][s].numpy(), rtol=0, atol=1e-14)
+
+
+def test_sgld_update_box_penalty_gradient():
+    from conformal_bayesopt_b200 import ops
+    torch.manual_seed(5)
+    X0 = torch.rand(6, 2, 3, dtype=torch.float64) * 1.2 - 0.1
+    lb = torch.zeros(3, dtype=torch.float64)
+    ub = torch.tensor([1.0, 0.9, 1.1], dtype=torch.float64)
+    dacq = torch.randn_like(X0)
+    X = X0.to(DEV).clone()
+    zeros = torch.zeros_like(X)
+    ops.sgld_update(X, None, dacq.to(DEV), zeros, lb.to(DEV), ub.to(DEV), lr=1.0, momentum=0.0, temperature=0.0)
+    g = (X0 - X.cpu()).numpy()
+    ref = -dacq.numpy() + T.bounds_penalty_grad(X0.numpy(), lb.numpy(), ub.numpy())
+    np.testing.assert_allclose(g, ref, rtol=1e-9, atol=1e-12)
+
+
+def _problem(N=48, d=3, seed=0):
+    from conformal_bayesopt_b200.model_state import GPModelState
+    g = torch.Generator().manual_seed(seed)
+    X = torch.rand(N, d, generator=g, dtype=torch.float64)
+    y = torch.sin(3 * X).sum(-1) + 0.1 * torch.randn(N, generator=g, dtype=torch.float64)
+    y = (y - y.mean()) / y.std()
+    return GPModelState.fit_fixed(X.to(DEV), y.to(DEV), lengthscale=torch.full((d,), 0.5, dtype=torch.float64),
+                                  outputscale=1.0, noise=1e-2, mean=0.0), X
+
+
+def test_optimize_acqf_sgld_runs_the_reference_loop_on_the_device():
+    """The default loop shape of the reference (cUCB, q = 2, ratio estimator trained by the callback, randomised)."""
+    from conformal_bayesopt_b200.acquisitions import qConformalUpperConfidenceBound
+    from conformal_bayesopt_b200.optim import optimize_acqf_sgld
+    from conformal_bayesopt_b200.ratio_estimation import RatioEstimator
+    state, Xtr = _problem()
+    d = Xtr.shape[1]
+    torch.manual_seed(0)
+    np.random.seed(0)
+    est = RatioEstimator(in_size=d, device=DEV, dtype=torch.float64, lr=5e-3, ema_weight=2e-2, weight_decay=5e-6)
+    est.set_neg_samples(Xtr.to(DEV))
+    acq = qConformalUpperConfidenceBound(alpha=0.2, temp=3e-2, grid_res=32, max_grid_refinements=0, ratio_estimator=est,
+                                         randomized=True, model=state, beta=0.2)
+    bounds = torch.stack([torch.zeros(d), torch.ones(d)]).to(DEV, torch.float64)
+    cand, val = optimize_acqf_sgld(acq, bounds, q=2, num_restarts=4, raw_samples=32, sgld_steps=48, warmup_steps=8,
+                                   lr=2e-2, temperature=4e-3, options=dict(callback=est.optimize_callback, seed=1))
+    assert cand.shape == (2, d) and val.shape == ()
+    assert bool(((cand >= 0) & (cand <= 1)).all()) and bool(torch.isfinite(val))
+    assert est._train is not None and est._train["step"] > 0          # the callback trained on the device
+    assert float(est._train["target"].abs().max()) > 0
+    allc, allv = optimize_acqf_sgld(acq, bounds, q=2, num_restarts=4, raw_samples=32, sgld_steps=16, warmup_steps=4,
+                                    lr=2e-2, temperature=4e-3, return_best_only=False, options=dict(seed=1))
+    assert allc.shape == (4, 2, d) and allv.shape == (4,)
+    traj, tv = optimize_acqf_sgld(acq, bounds, q=2, num_restarts=4, raw_samples=32, sgld_steps=16, warmup_steps=4,
+                                  lr=2e-2, temperature=4e-3, return_full_traj=True, options=dict(seed=1))
+    assert traj.shape == (4, 13, 2, d) and tv.shape == (4, 13)
+
+
+def test_sgld_improves_the_acquisition_value_without_noise():
+    """temperature = 0: the loop is momentum gradient ascent on acq; the selected iterate is at least as good as the start."""
+    from conformal_bayesopt_b200.acquisitions import qConformalExpectedImprovement
+    from conformal_bayesopt_b200.optim import optimize_acqf_sgld
+    state, Xtr = _problem(seed=3)
+    d = Xtr.shape[1]
+    acq = qConformalExpectedImprovement(alpha=0.2, temp=3e-2, grid_res=32, max_grid_refinements=0, ratio_estimator=None,
+                                        model=state, best_f=0.5)
+    torch.manual_seed(2)
+    acq.fixed_probes = (2.0 * (torch.rand(state.N + 1, 8) > 0.5) - 1.0).double()
+    bounds = torch.stack([torch.zeros(d), torch.ones(d)]).to(DEV, torch.float64)
+    ics = (0.2 + 0.6 * torch.rand(6, 1, d, dtype=torch.float64)).to(DEV)
+    with torch.no_grad():
+        start = acq(ics)
+    cand, val = optimize_acqf_sgld(acq, bounds, q=1, num_restarts=6, batch_initial_conditions=ics, sgld_steps=40,
+                                   warmup_steps=0, lr=5e-3, temperature=0.0, return_best_only=False)
+    assert bool((val >= start - 1e-12).all())
+    assert float((val - start).max()) > 0

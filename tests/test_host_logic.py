@@ -32,8 +32,10 @@ def test_untrained_ratio_estimator_is_one():
     assert torch.allclose(out, torch.ones(5, dtype=torch.float64))          # ratio_estimation.py:81-86
     r.update_target_network()
     assert any(p.abs().sum() > 0 for p in r._target_network.parameters())
-    with pytest.raises(NotImplementedError):
-        r.optimize_callback(None)
+    # positives are pooled on the device and the training step is a kernel: CPU-only use fails loudly
+    from conformal_bayesopt_b200 import _lib
+    with pytest.raises(_lib.CboError):
+        r.optimize_callback(torch.randn(4, 3, dtype=torch.float64))
 
 
 def test_class_conventions():
