@@ -97,6 +97,30 @@ class ConformalAcquisition(nn.Module):
         optimiser loop needs per step (optim.optimize_acqf_sgld)."""
         return self._conformal_fwd(X.detach(), raw_grad=True)
 
+    def graphed(self, b: int, q: int, want_grad: bool = True):
+        """This acquisition function for ONE fixed call shape (b, q) as a CUDA graph (`graphs.GraphedConformalAcq`): same
+        base samples, parameters and ratio weights as `forward`; raises ValueError where a capture is impossible."""
+        from .graphs import GraphedConformalAcq
+        if self.model is None:
+            raise AttributeError("ConformalAcquisition must be subclassed")
+        if self.max_grid_refinements > 0 or self.X_pending is not None:
+            raise ValueError("grid refinement / pending points are not captured")
+        if not self.grid_sampler.collapse_batch_dims or self.grid_sampler.resample or self.sampler.resample:
+            raise ValueError("base samples that change per call are not captured")
+        if want_grad and self._kind not in ("ucb", "ei"):
+            raise ValueError("d acq / d X is built for cUCB / cEI")
+        state = as_state(self.model)
+        dev, G = state.device, self.grid_res
+        self.grid_sampler._sample_shape = torch.Size([G])
+        eps = self.grid_sampler.draw((G, q), dev)
+        eps_mc = self.sampler.draw((int(self.sampler.sample_shape[0]), G, self._mc_width(q)), dev)
+        if self.ratio_estimator is not None and hasattr(self.ratio_estimator, "prepare_device_training"):
+            self.ratio_estimator.prepare_device_training(dev)      # weights at a stable address while training goes on
+        return GraphedConformalAcq(state, b, q, eps_grid=eps, eps_mc=eps_mc, ratio=_ratio_weights(self.ratio_estimator, dev),
+                                   want_grad=want_grad, alpha=self.alpha, temp=self.temp, grid_res=G,
+                                   max_grid_refinements=0, randomized=self.randomized, optimistic=self.optimistic,
+                                   **self._acq_params())
+
     def _conformal_fwd(self, X: torch.Tensor, outputs=(), raw_grad=False) -> torch.Tensor:
         if self.model is None:
             raise AttributeError("ConformalAcquisition must be subclassed")

@@ -4,7 +4,8 @@ Per SGLD step the reference does: `callback(iterates.cpu())` (the ratio-estimato
 `backward()` through the conformal path and the box penalty, an SGHMC update (optim/sgld.py) and a cosine learning-rate
 step.  Here a step is: `RatioEstimator.optimize_callback` on the device iterates (two kernels, no `.cpu()`), ONE
 value+gradient library call (`acq.value_and_grad`), one normal draw and ONE `k_sgld_update` launch (penalty gradient +
-momentum + noise + parameter update); the learning rate follows the closed form of CosineAnnealingLR.
+momentum + noise + parameter update); the learning rate follows the closed form of CosineAnnealingLR.  The value+gradient
+call of each optimiser batch has a fixed shape and is replayed as a CUDA graph (`options["cuda_graph"]`, default on).
 
 The initial conditions come from botorch's `gen_batch_initial_conditions` in the reference [3P, not installed here]; its
 heuristic is restated from the published algorithm (Sobol raw samples, Boltzmann selection with eta = 2 on the
@@ -56,6 +57,22 @@ def gen_batch_initial_conditions(acq_function, bounds: torch.Tensor, q: int, num
 def cosine_lr(step: int, lr: float, T_max: int, eta_min: float) -> float:
     """Closed form of torch.optim.lr_scheduler.CosineAnnealingLR after `step` scheduler steps (cycles past T_max)."""
     return eta_min + (lr - eta_min) * (1.0 + math.cos(math.pi * step / T_max)) / 2.0
+
+
+def _stepper(acq_function, ic_batch, use_graph):
+    """X -> (acq, d acq / d X) for the fixed shape of one optimiser batch: a CUDA-graph replay where the acquisition
+    function can be captured (`ConformalAcquisition.graphed`), else one value+gradient call per step."""
+    if use_graph and hasattr(acq_function, "graphed"):
+        try:
+            graph = acq_function.graphed(ic_batch.shape[0], ic_batch.shape[1])
+        except ValueError:
+            graph = None
+        if graph is not None:
+            def step(X):
+                out = graph(X, z=acq_function.fixed_probes, u_rand=acq_function.fixed_uniforms)
+                return out["acq"], out["dacq_dX"]
+            return step
+    return lambda X: _value_and_grad(acq_function, X)
 
 
 def _value_and_grad(acq_function, X):
@@ -115,6 +132,7 @@ def optimize_acqf_sgld(
     lb, ub = bounds[0].contiguous(), bounds[1].contiguous()
     callback = options.get("callback")
     sgld_iterates = [[b.clone()] for b in batched_ics]
+    steppers = [_stepper(acq_function, b, options.get("cuda_graph", True)) for b in batched_ics]
 
     for _s in range(sgld_steps):
         lr_s = cosine_lr(_s, lr, T_max, eta_min)
@@ -124,7 +142,7 @@ def optimize_acqf_sgld(
                 if callable(callback):
                     callback(ic_batch.clone())             # stays on the device (the reference hands over `.cpu()`)
             if _s < sgld_steps - 1:
-                _, dacq = _value_and_grad(acq_function, ic_batch)
+                _, dacq = steppers[batch_idx](ic_batch)
                 noise = torch.randn_like(ic_batch)
                 ops.sgld_update(ic_batch, bufs[batch_idx], dacq.to(torch.float64).contiguous(), noise, lb, ub, lr=lr_s,
                                 momentum=momentum, temperature=scaled_temp)

@@ -83,6 +83,14 @@ class RatioEstimator(nn.Module):
         t["tok_c"], t["tok_t"] = self._token(self.classifier), self._token(self._target_network)
         return t
 
+    def prepare_device_training(self, device):
+        """Create the flat device vectors now: from here on `device_weights(device)` hands out views of the SAME target
+        vector, which training updates in place (needed by CUDA graphs that captured the pointers)."""
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self._publish(self._train_state(device))
+
     def _publish(self, t):
         if not t["views"]:
             with torch.no_grad():

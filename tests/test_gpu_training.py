@@ -193,3 +193,28 @@ def test_sgld_improves_the_acquisition_value_without_noise():
                                    warmup_steps=0, lr=5e-3, temperature=0.0, return_best_only=False)
     assert bool((val >= start - 1e-12).all())
     assert float((val - start).max()) > 0
+
+
+def test_graph_replay_loop_matches_the_direct_loop_bitwise():
+    from conformal_bayesopt_b200.acquisitions import qConformalUpperConfidenceBound
+    from conformal_bayesopt_b200.optim import optimize_acqf_sgld
+    from conformal_bayesopt_b200.ratio_estimation import RatioEstimator
+    state, Xtr = _problem(seed=4)
+    d = Xtr.shape[1]
+    bounds = torch.stack([torch.zeros(d), torch.ones(d)]).to(DEV, torch.float64)
+    ics = (0.1 + 0.8 * torch.rand(5, 2, d, dtype=torch.float64, generator=torch.Generator().manual_seed(9))).to(DEV)
+    res = []
+    for use_graph in (False, True):
+        torch.manual_seed(7)
+        np.random.seed(7)
+        est = RatioEstimator(in_size=d, device=DEV, dtype=torch.float64, lr=5e-3, ema_weight=2e-2, weight_decay=5e-6)
+        est.set_neg_samples(Xtr.to(DEV))
+        acq = qConformalUpperConfidenceBound(alpha=0.2, temp=3e-2, grid_res=32, max_grid_refinements=0,
+                                             ratio_estimator=est, randomized=True, model=state, beta=0.2)
+        acq.fixed_probes = (2.0 * (torch.rand(state.N + 2, 8, generator=torch.Generator().manual_seed(3)) > 0.5) - 1.0).double()
+        acq.fixed_uniforms = torch.rand(5, 32, 2, dtype=torch.float64, generator=torch.Generator().manual_seed(4)).to(DEV)
+        traj, vals = optimize_acqf_sgld(acq, bounds, q=2, num_restarts=5, batch_initial_conditions=ics, sgld_steps=24,
+                                        warmup_steps=4, lr=1e-2, temperature=4e-3, return_full_traj=True,
+                                        options=dict(callback=est.optimize_callback, cuda_graph=use_graph))
+        res.append((traj.clone(), vals.clone(), est._train["target"].clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
