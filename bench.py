@@ -317,6 +317,30 @@ def run_ours(args):
                     "ms_per_call": msg3, "value": bg_ * GRID / (msg3 * 1e-3), "unit": "evals/s (each with its gradient row)",
                     "kernels_ms_per_call": {n: msg_[i] / 3 for i, n in enumerate(gnames) if msg_[i] > 0}}
 
+    # ---- one SGLD step of the reference's default inner loop (optim/optimize.py:224-235: 8 restarts x q = 2, value+gradient,
+    # randomised, ratio estimator), replayed as a CUDA graph with fresh probes / uniforms per step; rank 0, outside the timed region
+    cfg_sgld = None
+    if rank == 0 and not args.no_grad_leg:
+        from conformal_bayesopt_b200.graphs import GraphedConformalAcq
+        from conformal_bayesopt_b200.synthetic import make_inputs, make_ratio_weights
+        import time as _time
+        inp_s = make_inputs(N_TRAIN, DIM, 8, 2, GRID, seed=3)
+        pk = {k: v for k, v in kw.items() if k not in ("eps_grid", "z", "eps_mc", "u_rand", "outputs", "chunk")}
+        pk.update(randomized=True, ratio=ops.RatioWeights(*[t.to(dev) for t in make_ratio_weights(DIM)]))
+        gacq = GraphedConformalAcq(state, 8, 2, eps_grid=inp_s["eps_grid"].to(dev), eps_mc=inp_s["eps_mc"].to(dev), **pk)
+        Xs = inp_s["Xq"].to(dev)
+        for _ in range(5):
+            gacq(Xs)
+        torch.cuda.synchronize()
+        t0 = _time.perf_counter()
+        for _ in range(50):
+            gacq(Xs)
+        torch.cuda.synchronize()
+        ms_s = (_time.perf_counter() - t0) / 50 * 1e3
+        cfg_sgld = {"workload": "one SGLD step of the reference's default loop: value + d acq/dX of 8 restarts x q=2 (N=1024, d=8, "
+                                "grid=64, cucb, randomised, ratio estimator), CUDA-graph replay, fresh probes and uniforms per step",
+                    "ms_per_call": ms_s, "value": 8 * GRID / (ms_s * 1e-3), "unit": "evals/s (joint batches x grid points)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -369,7 +393,7 @@ def run_ours(args):
         "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
     }
     if cfg2 is not None:
-        line["other_configs"] = [c for c in (cfg2, cfg_grad) if c is not None]
+        line["other_configs"] = [c for c in (cfg2, cfg_grad, cfg_sgld) if c is not None]
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

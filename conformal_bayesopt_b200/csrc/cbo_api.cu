@@ -257,14 +257,9 @@ template <int Q, bool SOFT>
 cudaError_t launch_score_q_bwd_t(const cbo::ScoreQBwdArgs& a, cudaStream_t st) {
     size_t smem = cbo::score_q_bwd_smem_bytes(a.f.base.Np, a.f.base.G, Q);
     // a handful of joint batches (the SGLD loop): one thread-block cluster of 8 CTAs per joint batch (soft path)
-    const bool cluster = SOFT && a.f.base.n_cand * cbo::SQB_CLUSTER <= num_sms();
-    if (cluster) {
+    if (SOFT && a.f.base.n_cand * cbo::SQB_CLUSTER <= num_sms()) {
         static size_t configured_cl = 0;
-        if (smem > configured_cl) {
-            cudaError_t e = cudaFuncSetAttribute(cbo::k_score_q_bwd<Q, SOFT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured_cl = smem;
-        }
+        static int max_clusters = 0;         // clusters of 8 that are resident at once (GPC granularity), per smem size
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(a.f.base.n_cand * cbo::SQB_CLUSTER);
@@ -276,7 +271,17 @@ cudaError_t launch_score_q_bwd_t(const cbo::ScoreQBwdArgs& a, cudaStream_t st) {
         attr.val.clusterDim.x = cbo::SQB_CLUSTER; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, cbo::k_score_q_bwd<Q, SOFT, true>, a);
+        if (smem > configured_cl) {
+            cudaError_t e = cudaFuncSetAttribute(cbo::k_score_q_bwd<Q, SOFT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured_cl = smem;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, cbo::k_score_q_bwd<Q, SOFT, true>, &cfg) != cudaSuccess) {
+                cudaGetLastError();
+                max_clusters = 0;
+            }
+        }
+        if (a.f.base.n_cand <= max_clusters)   // one wave of clusters; otherwise one CTA per joint batch is as fast
+            return cudaLaunchKernelEx(&cfg, cbo::k_score_q_bwd<Q, SOFT, true>, a);
     }
     static size_t configured = 0;
     if (smem > configured) {

@@ -39,7 +39,9 @@ def draw_probes(n_rows: int, num_samples: int = 8, device=None) -> torch.Tensor:
     if device is None:
         return torch.where(bits, 1.0, -1.0).to(torch.float64)
     one = torch.ones((), dtype=torch.float64, device=device)
-    return torch.where(bits.to(device), one, -one)
+    # pinned staging (torch's caching host allocator keeps the block alive until the copy has run): the upload does not
+    # synchronise the host with the stream, so the next step's host work overlaps this step's kernels
+    return torch.where(bits.pin_memory().to(device, non_blocking=True), one, -one)
 
 
 def _ratio_weights(ratio_estimator, device):

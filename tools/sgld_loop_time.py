@@ -43,9 +43,12 @@ for N in (80, 1024):
         torch.cuda.synchronize(); return (time.perf_counter() - t) / n * 1e3
     X = ics.clone(); buf = torch.zeros_like(X); noise = torch.randn_like(X)
     t_cb = timed(lambda: est.optimize_callback(X))
+    est.device_permutation = True
+    t_cbd = timed(lambda: est.optimize_callback(X))
+    est.device_permutation = False
     t_vg = timed(lambda: acq.value_and_grad(X))
     _, g = acq.value_and_grad(X)
     t_up = timed(lambda: (torch.randn_like(X), ops.sgld_update(X, buf, g, noise, bounds[0].contiguous(), bounds[1].contiguous(), lr=1e-9, momentum=0.1, temperature=0.0)))
     print(f"N={N:5d}: {steps} SGLD steps incl. final trajectory scoring {t_all*1e3:.1f} ms = {t_all/steps*1e3:.3f} ms/step | "
-          f"ratio training callback {t_cb:.3f} ms, value+grad {t_vg:.3f} ms, noise+update {t_up:.3f} ms; "
+          f"ratio training callback {t_cb:.3f} ms ({t_cbd:.3f} ms with device_permutation, pool of {est.num_positive} rows), value+grad {t_vg:.3f} ms, noise+update {t_up:.3f} ms; "
           f"without graph replay {t_nog/steps*1e3:.3f} ms/step; marginal per step {slope_g*1e3:.3f} ms (graph) / {slope_n*1e3:.3f} ms (direct); trained steps {est._train['step']}, loss {float(est.last_loss):.4f}")
