@@ -15,6 +15,7 @@ EXPORTS = [
     "cbo_ratio_forward_f64", "cbo_gemm_tn_f64", "cbo_kernel_rows_f64", "cbo_timing_enable", "cbo_timing_collect",
     "cbo_cehvi_integrate_f64", "cbo_conformal_acq_grad_f64", "cbo_workspace_bytes_grad",
     "cbo_model_workspace_bytes", "cbo_model_build_f64",
+    "cbo_model_append_workspace_bytes", "cbo_model_append_f64",
     "cbo_ratio_train_workspace_bytes", "cbo_ratio_train_step_f64", "cbo_sgld_update_f64",
 ]
 
@@ -114,6 +115,11 @@ def load():
     lib.cbo_model_build_f64.restype = C.c_int
     lib.cbo_model_build_f64.argtypes = [c_dp, c_dp, C.c_int64, C.c_int64, c_dp, C.c_double, C.c_double, C.c_double, c_dp,
                                         c_dp, c_dp, c_dp, c_dp, C.c_size_t, c_dp]
+    lib.cbo_model_append_workspace_bytes.restype = C.c_size_t
+    lib.cbo_model_append_workspace_bytes.argtypes = [C.c_int64]
+    lib.cbo_model_append_f64.restype = C.c_int
+    lib.cbo_model_append_f64.argtypes = [c_dp, C.c_int64, C.c_int64, C.c_int64, c_dp, C.c_double, C.c_double, C.c_double,
+                                         c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int64, c_dp, c_dp, C.c_size_t, c_dp]
     lib.cbo_ratio_train_workspace_bytes.restype = C.c_size_t
     lib.cbo_ratio_train_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
     lib.cbo_ratio_train_step_f64.restype = C.c_int

@@ -22,6 +22,7 @@
 #include "ratio_mma.cuh"
 #include "ratio_train.cuh"
 #include "model_build.cuh"
+#include "model_append.cuh"
 #include "score_q_bwd.cuh"
 
 namespace {
@@ -439,6 +440,24 @@ int cbo_sgld_update_f64(double* X, double* momentum_buf, const double* dacq_dX, 
     cbo::k_sgld_update<<<int((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         X, momentum_buf, dacq_dX, noise, lb, ub, n, (int)d, lr, momentum, ns, penalty_scale, penalty_width);
     CBO_CUDA(cudaGetLastError());
+    return CBO_OK;
+}
+
+size_t cbo_model_append_workspace_bytes(int64_t Np) {
+    return Np > 0 ? cbo::model_append_ws_doubles(Np) * sizeof(double) : 0;
+}
+
+int cbo_model_append_f64(double* X, int64_t N, int64_t d, int64_t Np, const double* inv_lengthscale, double mean,
+                         double outputscale, double noise, double* alpha, double* linv, double* linv_t,
+                         const double* x_new, const double* y_new, int64_t q, int32_t* info, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    if (!X || !inv_lengthscale || !alpha || !linv || !linv_t || !x_new || !y_new || !workspace || N < 0 || d <= 0 || q <= 0)
+        return CBO_ERR_INVALID_ARG;
+    if (d > cbo::MAX_D || Np % 128 != 0 || N + q > Np) return CBO_ERR_UNSUPPORTED;
+    if (workspace_bytes < cbo_model_append_workspace_bytes(Np) || (reinterpret_cast<uintptr_t>(workspace) & 7))
+        return CBO_ERR_WORKSPACE;
+    CBO_CUDA(cbo::model_append(X, N, d, Np, inv_lengthscale, mean, outputscale, noise, alpha, linv, linv_t, x_new, y_new, q,
+                               info, static_cast<double*>(workspace), static_cast<cudaStream_t>(stream)));
     return CBO_OK;
 }
 

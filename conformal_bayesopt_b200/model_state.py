@@ -109,6 +109,42 @@ class GPModelState:
                              ls.detach().reshape(-1), float(torch.as_tensor(os_).reshape(-1)[0]),
                              float(torch.as_tensor(noise).reshape(-1)[0]), device=X.device)
 
+    def append(self, X_new: torch.Tensor, y_new: torch.Tensor, check_pd: bool = True) -> "GPModelState":
+        """A NEW state with the observations (X_new (q, d), y_new (q)) added, hyper-parameters unchanged: rank-1 extensions
+        of L^-1 and alpha by `cbo_model_append_f64`, O(q N^2) instead of the O(N^3) rebuild.  This state is left untouched
+        (the factors are copied first: 2 x 8 MB at N = 1024, microseconds on HBM3e)."""
+        lib = _lib.load()
+        dev = self.device
+        X_new = X_new.to(device=dev, dtype=torch.float64).reshape(-1, self.d).contiguous()
+        y_new = y_new.to(device=dev, dtype=torch.float64).reshape(-1).contiguous()
+        q, N, Np = X_new.shape[0], self.N, self.Np
+        assert y_new.shape[0] == q and q > 0
+        Np2 = max(Np, (N + q + 127) // 128 * 128)
+        if Np2 == Np:
+            alpha, linv, linv_t = self.alpha.clone(), self.linv.clone(), self.linv_t.clone()
+        else:
+            alpha = torch.zeros(Np2, dtype=torch.float64, device=dev)
+            linv = torch.zeros(Np2, Np2, dtype=torch.float64, device=dev)
+            linv_t = torch.zeros(Np2, Np2, dtype=torch.float64, device=dev)
+            alpha[:Np].copy_(self.alpha)
+            linv[:Np, :Np].copy_(self.linv)
+            linv_t[:Np, :Np].copy_(self.linv_t)
+        Xbuf = torch.empty(N + q, self.d, dtype=torch.float64, device=dev)
+        Xbuf[:N].copy_(self.X)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        nbytes = lib.cbo_model_append_workspace_bytes(Np2)
+        ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+        st = lib.cbo_model_append_f64(Xbuf.data_ptr(), N, self.d, Np2, self.inv_lengthscale.data_ptr(), self.mean,
+                                      self.outputscale, self.noise, alpha.data_ptr(), linv.data_ptr(), linv_t.data_ptr(),
+                                      X_new.data_ptr(), y_new.data_ptr(), q, info.data_ptr(), ws.data_ptr(), nbytes,
+                                      torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "cbo_model_append_f64")
+        if check_pd and int(info.item()) != 0:
+            raise _lib.CboError(f"appended point {int(info.item()) - 1 - N} makes K + noise I numerically singular")
+        return GPModelState(X=Xbuf, y=torch.cat([self.y, y_new]), mean=self.mean, lengthscale=self.lengthscale,
+                            outputscale=self.outputscale, noise=self.noise, alpha=alpha, linv=linv, linv_t=linv_t,
+                            inv_lengthscale=self.inv_lengthscale)
+
     def c_struct(self) -> "_lib.GpF64":
         return _lib.GpF64(self.N, self.d, self.Np, self.X.data_ptr(), self.alpha.data_ptr(), self.linv.data_ptr(),
                           self.linv_t.data_ptr(), self.inv_lengthscale.data_ptr(), self.mean, self.outputscale,

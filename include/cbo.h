@@ -176,6 +176,17 @@ int cbo_conf_mask_to_bounds_f64(const double* target_grid, const double* conf_pr
 int cbo_ratio_forward_f64(const cbo_ratio_mlp_f64* ratio, const double* x, int64_t n, int64_t d, double* out,
                           void* stream);
 
+/* Append q observations to a built model state in O(q N^2) (rank-1 extensions of L^-1 and alpha) instead of the O(N^3)
+ * rebuild -- the BO loop adds q queries per round (scripts/black_box_opt.py:154-155) and fantasises pending points.
+ * In place: X must have room for N + q rows, alpha / linv / linv_t are padded to Np >= N + q (a multiple of 128, the
+ * leading dimension) with zero padding as cbo_model_build_f64 leaves it.  x_new: q x d, y_new: q (device).  Same
+ * hyper-parameters as the build.  info as in cbo_model_build_f64.  3 launches per point, no host sync. */
+size_t cbo_model_append_workspace_bytes(int64_t Np);
+int cbo_model_append_f64(double* X, int64_t N, int64_t d, int64_t Np, const double* inv_lengthscale, double mean,
+                         double outputscale, double noise, double* alpha, double* linv, double* linv_t,
+                         const double* x_new, const double* y_new, int64_t q, int32_t* info, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* Density-ratio classifier, ONE training step on the device (conformalbo/ratio_estimation.py:133-144, the body of
  * RatioEstimator.optimize_callback once the minibatch is chosen): mean BCE-with-logits over [x_neg (n_neg x d, label 0);
  * x_pos[pos_idx] (n_pos rows, label 1; pos_idx NULL = the first n_pos rows)], one torch.optim.Adam step on the classifier

@@ -348,3 +348,34 @@ def test_sharded_grid_refinement_matches_the_single_batch():
     assert torch.allclose(got_acq, full["acq"].cpu(), rtol=1e-12, atol=1e-14)
     assert torch.allclose(got_mask, full["conf_pred_mask"].cpu(), rtol=0, atol=1e-12)
     # without the hook the two halves refine on their own statistics (documented per-shard semantics): generally different
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,q", [(100, 2), (126, 4), (128, 1), (1000, 3), (1023, 2)])
+def test_model_append_matches_a_rebuild(N, q):
+    """cbo_model_append_f64 (rank-1 extensions, incl. growth across a 128-row padding boundary) against cbo_model_build_f64 on
+    the concatenated data: L^-1, alpha, and an acquisition call on top."""
+    from conformal_bayesopt_b200 import GPModelState, ops
+    from conformal_bayesopt_b200.synthetic import make_inputs, make_problem
+    d = 5
+    p = make_problem(N + q, d, seed=N)
+    dev = torch.device("cuda:0")
+    kw = dict(mean=p["mean"], lengthscale=p["lengthscale"], outputscale=p["outputscale"], noise=p["noise"], device=dev)
+    full = GPModelState.fit_fixed(p["X"], p["y"], **kw)
+    base = GPModelState.fit_fixed(p["X"][:N], p["y"][:N], **kw)
+    keep = base.linv.clone()
+    app = base.append(p["X"][N:], p["y"][N:])
+    assert torch.equal(base.linv, keep) and base.N == N                      # the old state is untouched
+    assert app.N == N + q and app.Np == full.Np
+    scale = full.linv.abs().max()
+    assert float((app.linv - full.linv).abs().max() / scale) < 1e-10
+    assert float((app.linv_t - full.linv_t).abs().max() / scale) < 1e-10
+    assert torch.equal(app.linv_t, app.linv.T)
+    assert float((app.alpha - full.alpha).abs().max() / full.alpha.abs().max()) < 1e-9
+    assert torch.equal(app.X, full.X) and torch.equal(app.y, full.y)
+    inp = make_inputs(N + q, d, 16, 1, 32, seed=1)
+    call = dict(eps_grid=inp["eps_grid"][:, 0].to(dev), z=inp["z"].to(dev), eps_mc=inp["eps_mc"][:, :, 0].to(dev), kind="ucb",
+                alpha=0.1, temp=3e-2, grid_res=32, optimistic=True, beta_prime=1.0)
+    a = ops.conformal_acq(app, inp["Xq"].to(dev), **call)["acq"]
+    b = ops.conformal_acq(full, inp["Xq"].to(dev), **call)["acq"]
+    assert float((a - b).abs().max() / b.abs().max()) < 1e-8

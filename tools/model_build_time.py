@@ -38,4 +38,16 @@ for N in (256, 1024, 2048, 4096):
     st = ours()
     linv_ref = torch_ref()[0]
     err = ((st.linv[:N, :N] - linv_ref).abs().max() / linv_ref.abs().max()).item()
-    print(f"N={N}: libcbo {res['libcbo']:.2f} ms, torch.linalg {res['torch.linalg']:.2f} ms, max |dLinv| / max|Linv| = {err:.1e}")
+    # appending q = 2 observations (one BO round of the default config) instead of rebuilding
+    Xn, yn = torch.rand(2, d, dtype=torch.float64, device=dev), torch.randn(2, dtype=torch.float64, device=dev) * 0.1
+    for _ in range(3):
+        st.append(Xn, yn, check_pd=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        st.append(Xn, yn, check_pd=False)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"N={N}: libcbo {res['libcbo']:.2f} ms, torch.linalg {res['torch.linalg']:.2f} ms, max |dLinv| / max|Linv| = {err:.1e}; "
+          f"append of 2 points {e0.elapsed_time(e1) / 10:.3f} ms (incl. the copy of the factors)")
