@@ -210,8 +210,8 @@ class qConformalExpectedImprovement(ConformalAcquisition):
 class qConformalNoisyExpectedImprovement(ConformalAcquisition):
     """acquisitions.py:106-139 (+ botorch qNoisyExpectedImprovement(model, X_baseline, sampler, ..., prune_baseline)).
 
-    Joint sampling over [X_baseline; X] under every refit model.  Built for q = 1 and at most 31 baseline points -- pass
-    the pruned baseline (the reference configs set `prune_baseline: true`, hydra_config/acq_fn/cnei.yaml:3; botorch's
+    Joint sampling over [X_baseline; X] under every refit model.  Built for q <= 4 (incl. pending points) and at most 31
+    baseline points (nb + q <= 32) -- pass the pruned baseline (the reference configs set `prune_baseline: true`, hydra_config/acq_fn/cnei.yaml:3; botorch's
     `prune_inferior_points` is an MC procedure outside this path)."""
 
     def __init__(self, alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic=False,

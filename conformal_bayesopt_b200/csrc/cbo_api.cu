@@ -175,7 +175,7 @@ int validate(const cbo_gp_f64* gp, const cbo_params* p, int64_t b) {
     if (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI && p->kind != CBO_ACQ_NEI) return CBO_ERR_INVALID_ARG;
     if (p->kind == CBO_ACQ_NEI) {
         if (!p->nei || !p->nei->Xb || !p->nei->KbX || !p->nei->Sbb || !p->nei->mub || p->nei->nb < 1) return CBO_ERR_INVALID_ARG;
-        if (p->q != 1 || p->nei->nb > cbo::NEI_MAX_NB) return CBO_ERR_UNSUPPORTED;
+        if (p->nei->nb > cbo::NEI_MAX_NB || p->nei->nb + p->q > 32) return CBO_ERR_UNSUPPORTED;
     }
     if (p->q < 1 || p->q > cbo::MAX_Q) return CBO_ERR_UNSUPPORTED;
     if (p->q > 1 && cbo::score_q_smem_bytes((int)gp->Np, (int)p->grid_res, (int)p->q) > 227 * 1024) return CBO_ERR_UNSUPPORTED;
@@ -577,7 +577,12 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 na.mub = p->nei->mub; na.W = w.UW; na.rn_partial = w.rn; na.mu = w.mu; na.cscale = x.cscale;
                 na.eps_grid = x.eps_grid; na.eps_per_candidate = x.eps_per_candidate; na.eps_mc = eps_mc;
                 na.values = w.nei_values;
-                cbo::k_nei_values<<<(ncand + 3) / 4, 128, 0, s>>>(na);
+                na.V = w.V;
+                if (q == 1) cbo::k_nei_values<<<(ncand + 3) / 4, 128, 0, s>>>(na);
+                else {
+                    cudaError_t e = cbo::launch_nei_values_q(na, q, s);
+                    if (e != cudaSuccess) return e;
+                }
                 x.ext_values = w.nei_values;
             }
             if (q == 1) return soft_path ? launch_score<true>(x, s) : launch_score<false>(x, s);

@@ -425,7 +425,9 @@ k_score_q(const ScoreQArgs pq) {
                         }
                     }
                     double f = mf + fs, val;
-                    if (p.kind == 0) {
+                    if (p.ext_values) {               // cNEI: joint-sample values from k_nei_values_q
+                        val = p.ext_values[((int64_t(c) * S + s) * G + g) * Q + j];
+                    } else if (p.kind == 0) {
                         if (S > 1) { double m = mf + ms; val = m + p.beta_prime * fabs(f - m); }
                         else val = f;
                     } else {

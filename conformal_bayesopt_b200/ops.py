@@ -116,7 +116,7 @@ def workspace(state: GPModelState, b: int, params, chunk: int = 0, grad: bool = 
     nbytes = fn(state.N, state.d, b, C.byref(params), chunk)
     key = (state.device.index, stream if stream is not None else torch.cuda.current_stream().cuda_stream)
     ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < nbytes:
+    if ws is None or ws.numel() < nbytes + 256:           # 256 spare bytes: the pointer is aligned up by the callers
         ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=state.device)
         _WORKSPACES[key] = ws
     return ws

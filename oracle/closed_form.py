@@ -124,31 +124,35 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
     _, grid, logp, mask, dev = best
 
     if kind == "nei":
-        assert q == 1, "closed-form cNEI is written for q = 1"
-        # joint posterior of the refit model over [X_baseline; x] (acquisitions.py:115-134): with c = Cov_D(f(X_b), y(x)),
-        # P = Var_D(f(x)) = s - noise:  mean = [mu_b + c b_g ; mu + P b_g],
-        # cov = [[Sigma_bb - c c^T/s, c noise/s], [., P noise/s]]   (g-independent)
+        # joint posterior of the refit model over [X_baseline; X] (acquisitions.py:115-134).  With c = Cov_D(f(X_b), y(X))
+        # (nb x q), Cov_D(f(X), y(X)) = S - noise I and B_g = S^-1 (y_g - mu):
+        #   mean = [mu_b + c B_g ; mu + (I - noise S^-1)(y_g - mu)]
+        #   cov  = [[Sigma_bb - c S^-1 c^T, noise c S^-1], [., noise (I - noise S^-1)]]      (g-independent)
         nb = X_baseline.shape[0]
         Kb = gp.k(X_baseline, gp.X)                                        # (nb,N)
         mu_b = gp.mean + Kb @ gp.alpha
         Vb = torch.linalg.solve_triangular(gp.L, Kb.T, upper=False)
         Sig_bb = gp.k(X_baseline, X_baseline) - Vb.T @ Vb
-        s1 = S[:, 0, 0]
-        P = s1 - noise
-        c = gp.k(X_baseline.unsqueeze(0).expand(b, nb, -1), Xq)[..., 0] - W[:, 0, :] @ Kb.T      # (b,nb)
-        cov = torch.zeros(b, nb + 1, nb + 1, dtype=U.dtype)
-        cov[:, :nb, :nb] = Sig_bb - c.unsqueeze(-1) * c.unsqueeze(-2) / s1[:, None, None]
-        cov[:, :nb, nb] = c * (noise / s1)[:, None]
-        cov[:, nb, :nb] = cov[:, :nb, nb]
-        cov[:, nb, nb] = P * noise / s1
+        c = gp.k(X_baseline.unsqueeze(0).expand(b, nb, -1), Xq) - Kb.unsqueeze(0) @ W.transpose(-1, -2)     # (b,nb,q)
+        Sinv_s = 0.5 * (Sinv + Sinv.transpose(-1, -2))
+        cSi = c @ Sinv_s                                                   # (b,nb,q)
+        cov = torch.zeros(b, nb + q, nb + q, dtype=U.dtype)
+        cov[:, :nb, :nb] = Sig_bb - cSi @ c.transpose(-1, -2)
+        cov[:, :nb, nb:] = noise * cSi
+        cov[:, nb:, :nb] = cov[:, :nb, nb:].transpose(-1, -2)
+        cov[:, nb:, nb:] = noise * (eye - noise * Sinv_s)
+        cov = 0.5 * (cov + cov.transpose(-1, -2))
         root = torch.linalg.cholesky(cov)
-        bg = dev[..., 0] / s1[:, None]                                     # (b,G)
-        mean = torch.cat([mu_b.view(1, 1, nb) + c.unsqueeze(1) * bg.unsqueeze(-1),
-                          (mu[:, :1].unsqueeze(1) + (P[:, None] * bg).unsqueeze(-1))], dim=-1)   # (b,G,nb+1)
+        Bg_v = dev @ Sinv.transpose(-1, -2)                                # (b,G,q)
+        mean = torch.cat([mu_b.view(1, 1, nb) + Bg_v @ c.transpose(-1, -2),
+                          mu.unsqueeze(1) + dev @ (eye - noise * Sinv).transpose(-1, -2)], dim=-1)          # (b,G,nb+q)
         samples = mean.unsqueeze(0) + torch.einsum("bij,sgj->sbgi", root, eps_mc)
-        fb, fx = samples[..., :nb] / temp, samples[..., nb:]
-        diffs = (fx - temp * torch.logsumexp(fb, -1, keepdim=True)) / temp
-        values = temp * (torch.clamp_min(diffs, 0) + torch.log1p(torch.exp(-diffs.abs())))
+        fb, fx = samples[..., :nb], samples[..., nb:]                      # (S,b,G,nb), (S,b,G,q)
+        if temp > 0:
+            diffs = (fx - temp * torch.logsumexp(fb / temp, -1, keepdim=True)) / temp
+            values = temp * (torch.clamp_min(diffs, 0) + torch.log1p(torch.exp(-diffs.abs())))
+        else:
+            values = torch.clamp_min(fx - fb.max(-1, keepdim=True).values, 0.0)
     # ---- A-6 values under the refit model ------------------------------------------------
     shrink = eye - noise * Sinv                                            # (b,q,q)
     mean_f = mu.unsqueeze(1) + dev @ shrink.transpose(-1, -2)              # (b,G,q)

@@ -224,18 +224,20 @@ def test_cehvi_matches_oracle():
         assert torch.allclose(got.cpu(), want, rtol=1e-6, atol=1e-10)
 
 
-@pytest.mark.parametrize("temp,refine", [(3e-2, 0), (1e-2, 2)])
-def test_cnei_matches_oracle(temp, refine):
-    """qConformalNoisyExpectedImprovement (acquisitions.py:106-139) with a pruned baseline, against the closed-form oracle."""
+@pytest.mark.parametrize("temp,refine,q", [(3e-2, 0, 1), (1e-2, 2, 1), (3e-2, 0, 2), (1e-2, 2, 2), (3e-2, 0, 3), (3e-2, 1, 4),
+                                           (0.0, 0, 2)])
+def test_cnei_matches_oracle(temp, refine, q):
+    """qConformalNoisyExpectedImprovement (acquisitions.py:106-139) with a pruned baseline, q = 1 and joint batches, against
+    the closed-form oracle (which the dense literal restatement pins, tests/test_oracle_consistency.py)."""
     from conformal_bayesopt_b200.acquisitions import qConformalNoisyExpectedImprovement
     from conformal_bayesopt_b200.sampling import IIDNormalSampler
     dev = _dev()
     N, d, b, G, nb, S = 90, 4, 21, 32, 7, 2
     p = make_problem(N, d, seed=13)
-    inp = make_inputs(N, d, b, 1, G, S=S, seed=13)
+    inp = make_inputs(N, d, b, q, G, S=S, seed=13)
     g = torch.Generator().manual_seed(4)
     Xb = torch.cat([p["X"][torch.randperm(N, generator=g)[:nb - 1]], torch.rand(1, d, generator=g, dtype=torch.float64)])
-    eps_mc = torch.randn(S, G, nb + 1, generator=g, dtype=torch.float64)
+    eps_mc = torch.randn(S, G, nb + q, generator=g, dtype=torch.float64)
     ratio, est = _estimator(d, dev)
     gs = IIDNormalSampler(G)
     gs.set_base_samples(inp["eps_grid"])

@@ -104,16 +104,17 @@ def test_cehvi_dense_equals_closed_form():
     assert torch.allclose(a, c, rtol=1e-9, atol=1e-12)
 
 
-def test_cnei_dense_equals_closed_form():
-    """qConformalNoisyExpectedImprovement (acquisitions.py:115-134): joint sampling over [X_baseline; x] under the refit model."""
+@pytest.mark.parametrize("q", [1, 2, 3])
+def test_cnei_dense_equals_closed_form(q):
+    """qConformalNoisyExpectedImprovement (acquisitions.py:115-134): joint sampling over [X_baseline; X] under the refit model."""
     N, d, b, G, nb, S = 30, 3, 5, 12, 6, 2
     p = make_problem(N, d, seed=8, fn="sin")
     gp = oracle_state(p)
-    inp = make_inputs(N, d, b, 1, G, S=S, seed=8)
+    inp = make_inputs(N, d, b, q, G, S=S, seed=8)
     g = torch.Generator().manual_seed(4)
     Xb = p["X"][torch.randperm(N, generator=g)[:nb]]                       # a pruned subset of the training inputs
     Xb = torch.cat([Xb[:-1], torch.rand(1, d, generator=g, dtype=torch.float64)])   # ... and one off-sample point
-    eps_mc = torch.randn(S, G, nb + 1, generator=g, dtype=torch.float64)
+    eps_mc = torch.randn(S, G, nb + q, generator=g, dtype=torch.float64)
     kw = dict(kind="nei", alpha=0.2, temp=3e-2, grid_res=G, eps_grid=inp["eps_grid"], z=inp["z"], eps_mc=eps_mc,
               randomized=True, u_rand=inp["u_rand"], optimistic=False, X_baseline=Xb)
     a = dense.conformal_acquisition(gp, inp["Xq"], **kw)
