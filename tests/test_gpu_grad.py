@@ -163,6 +163,8 @@ QCASES = [
     (60, 4, 3, 4, 10, 3e-2, True, True, "ucb", 3),
     (200, 12, 4, 3, 24, 3e-2, True, False, "ei", 2),         # d > 8
     (64, 3, 2, 4, 16, 0.0, True, True, "ucb", 2),            # hard path
+    (150, 5, 2, 24, 16, 3e-2, True, True, "ucb", 1),         # > 18 joint batches: one CTA per joint batch (no clusters)
+    (700, 6, 3, 5, 32, 3e-2, True, True, "ei", 1),           # cluster windows of 96 train points, last ranks partly empty
 ]
 
 
@@ -187,6 +189,26 @@ def test_joint_batch_grad_matches_autograd_of_oracle(N, d, q, b, G, temp, rand, 
     assert torch.allclose(got["acq"], acq, rtol=1e-6, atol=1e-9)
     assert g.abs().max() > 0
     assert _grad_close(got["dacq_dX"], g)
+
+
+def test_cluster_and_single_cta_reverse_kernels_agree():
+    """The same joint batches scored in a small call (thread-block clusters, train points split over 8 CTAs) and inside a
+    large call (one CTA per joint batch): identical algebra, different summation order."""
+    from conformal_bayesopt_b200 import ops
+    dev = _dev()
+    N, d, q, G = 300, 4, 2, 32
+    p = make_problem(N, d, seed=5)
+    inp = make_inputs(N, d, 40, q, G, S=1, seed=5)
+    _, ratio_w = _ratio(d, dev)
+    st = _state(p, dev)
+    kw = dict(eps_grid=inp["eps_grid"].to(dev), z=inp["z"].to(dev), eps_mc=inp["eps_mc"].to(dev), ratio=ratio_w, want_grad=True,
+              kind="ucb", alpha=0.1, temp=3e-2, grid_res=G, randomized=True, optimistic=True, beta_prime=1.0)
+    X, u = inp["Xq"].to(dev), inp["u_rand"].to(dev)
+    big = ops.conformal_acq(st, X, u_rand=u, **kw)
+    small = ops.conformal_acq(st, X[:8].contiguous(), u_rand=u[:8].contiguous(), **kw)
+    assert torch.allclose(small["acq"], big["acq"][:8], rtol=1e-11, atol=1e-13)
+    scale = big["dacq_dX"][:8].abs().max()
+    assert float((small["dacq_dX"] - big["dacq_dX"][:8]).abs().max() / scale) < 1e-9
 
 
 def test_joint_batch_grad_with_grid_refinement():
