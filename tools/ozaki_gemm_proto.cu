@@ -1,0 +1,237 @@
+// Prototype for the next round, NOT linked into libcbo: C (M x N, fp64) = A (M x K) * B (N x K)^T,
+// optionally restricted to k < (n-tile end) like the triangular pass of the hot path, computed from 7-bit integer slices on the
+// int8 tensor path (tcgen05.mma kind::i8, int32 accumulators in TMEM) -- the Ozaki scheme with fixed-point slices:
+//   x = 2^e * sum_i d_i 2^(-7 i),  d_i in [-64, 64]   (A: one global exponent, B: one exponent per row; all steps exact in fp64)
+//   C[m][n] = 2^(eA + eB[n]) * sum_t 2^(-7 t) D_t[m][n],   D_t = sum_{i+j=t} A_i B_j^T   (exact int32),  t = 2 .. S+1
+// One CTA per 128 x 128 output tile; the S anti-diagonals are accumulated four at a time (4 x 128 TMEM columns), i.e. K is
+// walked ceil(S/4) times.  Operands are staged by plain loads into the K-major no-swizzle canonical layout (see
+// i8_mma_probe.cu); v0 has no load/MMA overlap -- it exists to pin the arithmetic and to give a first rate.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/ozaki_gemm_proto tools/ozaki_gemm_proto.cu
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+constexpr int S = 8;            // slices per operand (8 x 7 bits = 56 bits)
+constexpr int TM = 128, TN = 128, KB = 32, THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
+}
+__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity) {
+    for (long it = 0; it < 4000000L; ++it) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+// ---- slicing: rows x K fp64 (ld) -> S planes of rows x K int8; per-row exponent (row_exp) or one global exponent -------------
+__global__ void k_row_exponent(const double* __restrict__ X, int rows, int K, int ld, int* __restrict__ row_exp) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    double m = 0.0;
+    for (int k = lane; k < K; k += 32) m = fmax(m, fabs(X[(size_t)r * ld + k]));
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) {
+        int e = 0;
+        if (m > 0.0) { frexp(m, &e); e += 1; }          // |x| < 2^(e-1): x 2^-e in (-0.5, 0.5)
+        row_exp[r] = e;
+    }
+}
+
+__global__ void k_slice(const double* __restrict__ X, int rows, int K, int ld, const int* __restrict__ row_exp, int global_exp,
+                        int8_t* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * K) return;
+    const int r = (int)(idx / K), k = (int)(idx % K);
+    const int e = row_exp ? row_exp[r] : global_exp;
+    double x = ldexp(X[(size_t)r * ld + k], -e);        // exact
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        x *= 128.0;
+        const double d = rint(x);
+        x -= d;                                         // exact: |x| <= 0.5 again
+        out[(size_t)s * rows * K + idx] = (int8_t)(int)d;
+    }
+}
+
+// ---- the slice-product GEMM ---------------------------------------------------------------------------------------------------
+// As: S x M x K int8, Bs: S x N x K int8.  tri != 0: only k < (n-tile end) contributes (B is lower triangular: B[n][k] = 0 for k > n).
+__global__ void __launch_bounds__(THREADS)
+k_ozaki_gemm(const int8_t* __restrict__ As, const int8_t* __restrict__ Bs, int M, int N, int K, int tri, int expA,
+             const int* __restrict__ expB, double* __restrict__ C, int ldc, int* __restrict__ fail) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_n = N / TN;
+    const int tile_m = blockIdx.x / tiles_n, tile_n = blockIdx.x % tiles_n;
+    const int m0 = tile_m * TM, n0 = tile_n * TN;
+    const int k_end = tri ? min(K, n0 + TN) : K;
+    uint8_t* sA = smem;                                  // S planes x (KB/16 chunks x 128 rows x 16 B)
+    uint8_t* sB = smem + (size_t)S * TM * KB;
+    constexpr int PLANE = TM * KB;                       // bytes of one slice plane of a stage (TM == TN)
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base;
+    const uint32_t idesc = make_idesc_i8(TM, TN);
+    uint32_t parity = 0;
+    bool ok = true;
+
+    for (int pass = 0; pass < (S + 3) / 4; ++pass) {
+        const int t_lo = 2 + 4 * pass, t_hi = min(S + 1, t_lo + 3);      // anti-diagonals of this pass
+        const int s_max = t_hi - 1;                                      // slices 1..s_max are needed (1-based)
+        for (int k0 = 0; k0 < k_end; k0 += KB) {
+            // stage slices 1..s_max of A (rows m0..) and B (rows n0..), columns k0..k0+KB, into the canonical layout
+            const int chunks = KB / 16;
+            for (int o = tid; o < 2 * s_max * TM * chunks; o += THREADS) {
+                const int c = o % chunks, r = (o / chunks) % TM, pl = (o / (chunks * TM)) % s_max, which = o / (chunks * TM * s_max);
+                const int8_t* src = which ? Bs + ((size_t)pl * N + n0 + r) * K + k0 + c * 16 : As + ((size_t)pl * M + m0 + r) * K + k0 + c * 16;
+                uint8_t* dst = (which ? sB : sA) + (size_t)pl * PLANE + (size_t)c * TM * 16 + r * 16;
+                *reinterpret_cast<int4*>(dst) = *reinterpret_cast<const int4*>(src);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+                for (int t = t_lo; t <= t_hi; ++t)
+                    for (int i = 1; i < t; ++i) {
+                        const int j = t - i;
+                        if (i > S || j > S) continue;
+                        const uint64_t ad = make_desc(a0 + (uint32_t)(i - 1) * PLANE, TM * 16, 128);
+                        const uint64_t bd = make_desc(b0 + (uint32_t)(j - 1) * PLANE, TN * 16, 128);
+                        mma_i8(tmem + (uint32_t)(t - t_lo) * TN, ad, bd, idesc, (k0 > 0) || (i > 1));
+                    }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            }
+            ok = mbar_wait_bounded(smem_u32(&bar), parity) && ok;        // v0: no overlap of loads and MMAs
+            parity ^= 1;
+            if (!ok) break;
+        }
+        if (!ok) break;
+        // epilogue of this pass: C (+)= 2^(eA + eB[n]) sum_t 2^(-7 t) D_t ; warps 0..3 own the four 32-lane TMEM quadrants
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        if (warp < 4) {
+            const int row = m0 + warp * 32 + lane;
+            for (int c0 = 0; c0 < TN; c0 += 32) {
+                double acc[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+                for (int t = t_hi; t >= t_lo; --t) {                     // small terms first
+                    uint32_t v[32];
+                    const uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t - t_lo) * TN + c0;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                                   "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                                   "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                 : "r"(addr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const double w = ldexp(1.0, -7 * t);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = fma((double)(int32_t)v[j], w, acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c0 + j;
+                    const double val = ldexp(acc[j], expA + expB[col]);
+                    double* dst = C + (size_t)row * ldc + col;
+                    *dst = pass == 0 ? val : *dst + val;                 // later passes add the lower-order diagonals
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();                                                 // TMEM is reused by the next pass
+        asm volatile("tcgen05.fence::after_thread_sync;");
+    }
+    if (!ok && tid == 0) atomicExch(fail, 1);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+static double urand() { return rand() / (double)RAND_MAX; }
+
+int main(int argc, char** argv) {
+    const int K = 1024, N = 1024;
+    const int Mcheck = 256, Mbig = argc > 1 ? atoi(argv[1]) : 16384;
+    srand(7);
+    // A like kernel rows (values in [0, 1], wide dynamic range), B like L^-1: lower triangular, entries of mixed sign / magnitude
+    std::vector<double> hA((size_t)Mbig * K), hB((size_t)N * K, 0.0);
+    for (auto& x : hA) x = exp(-8.0 * urand());
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k <= n; ++k) hB[(size_t)n * K + k] = (k == n ? 5.0 + 5.0 * urand() : (urand() - 0.5) * exp(-6.0 * urand()));
+    double *dA, *dB, *dC; int8_t *dAs, *dBs; int *dexpB, *dfail;
+    CK(cudaMalloc(&dA, hA.size() * 8)); CK(cudaMalloc(&dB, hB.size() * 8)); CK(cudaMalloc(&dC, (size_t)Mbig * N * 8));
+    CK(cudaMalloc(&dAs, (size_t)S * Mbig * K)); CK(cudaMalloc(&dBs, (size_t)S * N * K)); CK(cudaMalloc(&dexpB, N * 4)); CK(cudaMalloc(&dfail, 4));
+    CK(cudaMemcpy(dA, hA.data(), hA.size() * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, hB.data(), hB.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dfail, 0, 4));
+    const int expA = 1;                                   // |a| <= 1 < 2^(expA - 1) ... a 2^-1 in [0, 0.5]
+    k_row_exponent<<<(N + 7) / 8, 256>>>(dB, N, K, K, dexpB);
+    k_slice<<<(unsigned)(((size_t)N * K + 255) / 256), 256>>>(dB, N, K, K, dexpB, 0, dBs);
+    cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    const size_t smem = (size_t)2 * S * TM * KB;
+    CK(cudaFuncSetAttribute(k_ozaki_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int tri = 0; tri <= 1; ++tri) {
+        for (int rep = 0; rep < 2; ++rep) {
+            CK(cudaEventRecord(e0));
+            k_slice<<<(unsigned)(((size_t)Mbig * K + 255) / 256), 256>>>(dA, Mbig, K, K, nullptr, expA, dAs);
+            CK(cudaEventRecord(e1));
+            k_ozaki_gemm<<<(Mbig / TM) * (N / TN), THREADS, smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
+            CK(cudaEventRecord(e2));
+            CK(cudaDeviceSynchronize());
+        }
+        int hfail = 0; CK(cudaMemcpy(&hfail, dfail, 4, cudaMemcpyDeviceToHost));
+        if (hfail) { printf("MMA wait timed out\n"); return 1; }
+        float ms_s, ms_g; CK(cudaEventElapsedTime(&ms_s, e0, e1)); CK(cudaEventElapsedTime(&ms_g, e1, e2));
+        const double flop = 2.0 * Mbig * (double)N * K * (tri ? 0.5 + 0.5 * TN / N : 1.0);
+        printf("tri=%d M=%d: slicing A %.3f ms, slice-product GEMM %.3f ms = %.1f fp64-equivalent TFLOP/s (%d slices, %d int8 MMAs per k-step)\n",
+               tri, Mbig, ms_s, ms_g, flop / (ms_g * 1e-3) / 1e12, S, S * (S + 1) / 2);
+        // accuracy against a long-double CPU product on the first Mcheck rows
+        std::vector<double> hC((size_t)Mcheck * N);
+        CK(cudaMemcpy(hC.data(), dC, hC.size() * 8, cudaMemcpyDeviceToHost));
+        double max_err = 0.0, max_ref = 0.0, max_rel_scale = 0.0;
+        for (int m = 0; m < Mcheck; ++m)
+            for (int n = 0; n < N; ++n) {
+                long double s = 0.0L, sabs = 0.0L;
+                for (int k = 0; k < K; ++k) {
+                    const long double p = (long double)hA[(size_t)m * K + k] * hB[(size_t)n * K + k];
+                    s += p; sabs += fabsl(p);
+                }
+                const double err = fabs((double)(hC[(size_t)m * N + n] - s));
+                max_err = fmax(max_err, err); max_ref = fmax(max_ref, fabs((double)s));
+                if (sabs > 0) max_rel_scale = fmax(max_rel_scale, err / (double)sabs);
+            }
+        printf("  accuracy on %d rows: max abs err %.3e (max |C| %.3e), max err / sum|a b| %.3e (fp64 dot product bound ~ %.1e)\n",
+               Mcheck, max_err, max_ref, max_rel_scale, 1024 * 1.1e-16);
+    }
+    return 0;
+}
