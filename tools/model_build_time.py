@@ -39,7 +39,7 @@ for N in (256, 1024, 2048, 4096):
     linv_ref = torch_ref()[0]
     err = ((st.linv[:N, :N] - linv_ref).abs().max() / linv_ref.abs().max()).item()
     # appending q = 2 observations (one BO round of the default config) instead of rebuilding
-    Xn, yn = torch.rand(2, d, dtype=torch.float64, device=dev), torch.randn(2, dtype=torch.float64, device=dev) * 0.1
+    Xn, yn = torch.rand(2, 8, dtype=torch.float64, device=dev), torch.randn(2, dtype=torch.float64, device=dev) * 0.1
     for _ in range(3):
         st.append(Xn, yn, check_pd=False)
     torch.cuda.synchronize()
