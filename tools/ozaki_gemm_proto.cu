@@ -103,12 +103,14 @@ k_ozaki_gemm(const int8_t* __restrict__ As, const int8_t* __restrict__ Bs, int M
     const uint32_t idesc = make_idesc_i8(TM, TN);
     uint32_t parity = 0;
     bool ok = true;
+    long long t_load = 0, t_mma = 0, t_epi = 0, tc0;
 
     for (int pass = 0; pass < (S + 3) / 4; ++pass) {
         const int t_lo = 2 + 4 * pass, t_hi = min(S + 1, t_lo + 3);      // anti-diagonals of this pass
         const int s_max = t_hi - 1;                                      // slices 1..s_max are needed (1-based)
         for (int k0 = 0; k0 < k_end; k0 += KB) {
             // stage slices 1..s_max of A (rows m0..) and B (rows n0..), columns k0..k0+KB, into the canonical layout
+            tc0 = clock64();
             const int chunks = KB / 16;
             for (int o = tid; o < 2 * s_max * TM * chunks; o += THREADS) {
                 const int c = o % chunks, r = (o / chunks) % TM, pl = (o / (chunks * TM)) % s_max, which = o / (chunks * TM * s_max);
@@ -118,6 +120,7 @@ k_ozaki_gemm(const int8_t* __restrict__ As, const int8_t* __restrict__ Bs, int M
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
+            t_load += clock64() - tc0; tc0 = clock64();
             if (tid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
@@ -133,11 +136,13 @@ k_ozaki_gemm(const int8_t* __restrict__ As, const int8_t* __restrict__ Bs, int M
             }
             ok = mbar_wait_bounded(smem_u32(&bar), parity) && ok;        // v0: no overlap of loads and MMAs
             parity ^= 1;
+            t_mma += clock64() - tc0;
             if (!ok) break;
         }
         if (!ok) break;
         // epilogue of this pass: C (+)= 2^(eA + eB[n]) sum_t 2^(-7 t) D_t ; warps 0..3 own the four 32-lane TMEM quadrants
         asm volatile("tcgen05.fence::after_thread_sync;");
+        tc0 = clock64();
         if (warp < 4) {
             const int row = m0 + warp * 32 + lane;
             for (int c0 = 0; c0 < TN; c0 += 32) {
@@ -171,8 +176,170 @@ k_ozaki_gemm(const int8_t* __restrict__ As, const int8_t* __restrict__ Bs, int M
         asm volatile("tcgen05.fence::before_thread_sync;");
         __syncthreads();                                                 // TMEM is reused by the next pass
         asm volatile("tcgen05.fence::after_thread_sync;");
+        t_epi += clock64() - tc0;
     }
+    if (blockIdx.x == 0 && tid == 0) printf("  [v0 CTA 0] cycles: staging %lld, MMA issue+wait %lld, epilogue %lld\n", t_load, t_mma, t_epi);
     if (!ok && tid == 0) atomicExch(fail, 1);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// ---- v1: warp-specialised pipeline (loaders -> MMA issuer -> epilogue) ----------------------------------------------------------
+// warps 0..3 epilogue (TMEM lane quadrants), warp 4 issues the MMAs, warps 5..12 stage the slices (plain loads) into a ring of
+// NSTAGE shared-memory stages; full[] / empty[] mbarriers per stage, acc_full / acc_empty around the TMEM accumulators.
+constexpr int NSTAGE = 3, LOADERS = 256, V1_THREADS = 160 + LOADERS;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(V1_THREADS, 1)
+k_ozaki_gemm_v1(const int8_t* __restrict__ As, const int8_t* __restrict__ Bs, int M, int N, int K, int tri, int expA,
+                const int* __restrict__ expB, double* __restrict__ C, int ldc, int* __restrict__ fail) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE], acc_full, acc_empty;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_n = N / TN;
+    // longest-K tiles first in the triangular case
+    // ... within groups of 16 m-tiles, so that a group's A slices stay in L2 while its n-tiles are swept
+    const int grp = blockIdx.x / (16 * tiles_n), rem = blockIdx.x % (16 * tiles_n);
+    const int tile_m = grp * 16 + rem % 16, n_ord = rem / 16;
+    const int tile_n = tri ? tiles_n - 1 - n_ord : n_ord;
+    const int m0 = tile_m * TM, n0 = tile_n * TN;
+    const int k_end = tri ? min(K, n0 + TN) : K;
+    const int nk = k_end / KB;
+    constexpr int PLANE = TM * KB, STAGE = 2 * S * PLANE;
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(LOADERS));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&empty[s])));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&acc_full)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_u32(&acc_empty)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base;
+    constexpr int NPASS = (S + 3) / 4;
+    bool ok = true;
+
+    if (warp >= 5) {
+        // ===== loaders =====
+        const int lt = tid - 160;
+        int it = 0;
+        for (int pass = 0; pass < NPASS && ok; ++pass) {
+            const int s_max = min(S + 1, 2 + 4 * pass + 3) - 1;
+            for (int kt = 0; kt < nk && ok; ++kt, ++it) {
+                const int st = it % NSTAGE;
+                if (it >= NSTAGE) ok = mbar_wait_bounded(smem_u32(&empty[st]), ((it / NSTAGE) & 1) ^ 1);
+                uint8_t* sA = smem + (size_t)st * STAGE;
+                uint8_t* sB = sA + S * PLANE;
+                const int k0 = kt * KB;
+                constexpr int chunks = KB / 16;
+                const int total = 2 * s_max * TM * chunks;
+                for (int o0 = lt; o0 < total; o0 += LOADERS * 8) {
+                    int4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int o = o0 + u * LOADERS;
+                        if (o < total) {
+                            const int c = o % chunks, r = (o / chunks) % TM, pl = (o / (chunks * TM)) % s_max, which = o / (chunks * TM * s_max);
+                            const int8_t* src = which ? Bs + ((size_t)pl * N + n0 + r) * K + k0 + c * 16 : As + ((size_t)pl * M + m0 + r) * K + k0 + c * 16;
+                            v[u] = *reinterpret_cast<const int4*>(src);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int o = o0 + u * LOADERS;
+                        if (o < total) {
+                            const int c = o % chunks, r = (o / chunks) % TM, pl = (o / (chunks * TM)) % s_max, which = o / (chunks * TM * s_max);
+                            *reinterpret_cast<int4*>((which ? sB : sA) + (size_t)pl * PLANE + (size_t)c * TM * 16 + r * 16) = v[u];
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(smem_u32(&full[st]));
+            }
+        }
+    } else if (warp == 4) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = make_idesc_i8(TM, TN);
+        int it = 0;
+        for (int pass = 0; pass < NPASS && ok; ++pass) {
+            const int t_lo = 2 + 4 * pass, t_hi = min(S + 1, t_lo + 3);
+            if (pass > 0) ok = mbar_wait_bounded(smem_u32(&acc_empty), (pass - 1) & 1);     // epilogue has drained TMEM
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            for (int kt = 0; kt < nk && ok; ++kt, ++it) {
+                const int st = it % NSTAGE;
+                ok = mbar_wait_bounded(smem_u32(&full[st]), (it / NSTAGE) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                if (lane == 0 && ok) {
+                    const uint32_t a0 = smem_u32(smem + (size_t)st * STAGE), b0 = a0 + S * PLANE;
+                    for (int t = t_lo; t <= t_hi; ++t)
+                        for (int i = 1; i < t; ++i) {
+                            const int j = t - i;
+                            if (i > S || j > S) continue;
+                            mma_i8(tmem + (uint32_t)(t - t_lo) * TN, make_desc(a0 + (uint32_t)(i - 1) * PLANE, TM * 16, 128),
+                                   make_desc(b0 + (uint32_t)(j - 1) * PLANE, TN * 16, 128), idesc, (kt > 0) || (i > 1));
+                        }
+                    tc_commit(smem_u32(&empty[st]));
+                    if (kt == nk - 1) tc_commit(smem_u32(&acc_full));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue warps 0..3 =====
+        for (int pass = 0; pass < NPASS && ok; ++pass) {
+            const int t_lo = 2 + 4 * pass, t_hi = min(S + 1, t_lo + 3);
+            ok = mbar_wait_bounded(smem_u32(&acc_full), pass & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            if (!ok) break;
+            const int row = m0 + warp * 32 + lane;
+            for (int c0 = 0; c0 < TN; c0 += 32) {
+                double acc[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+                for (int t = t_hi; t >= t_lo; --t) {
+                    uint32_t v[32];
+                    const uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t - t_lo) * TN + c0;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                                   "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                                   "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                 : "r"(addr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const double w = ldexp(1.0, -7 * t);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = fma((double)(int32_t)v[j], w, acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c0 + j;
+                    const double val = ldexp(acc[j], expA + expB[col]);
+                    double* dst = C + (size_t)row * ldc + col;
+                    *dst = pass == 0 ? val : *dst + val;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            mbar_arrive(smem_u32(&acc_empty));
+        }
+    }
+    if (!ok && lane == 0) atomicExch(fail, 1);
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -200,12 +367,16 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
     const size_t smem = (size_t)2 * S * TM * KB;
     CK(cudaFuncSetAttribute(k_ozaki_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_ozaki_gemm_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NSTAGE * smem)));
+    for (int variant = 0; variant <= 1; ++variant)
     for (int tri = 0; tri <= 1; ++tri) {
+        CK(cudaMemset(dC, 0, (size_t)Mbig * N * 8));
         for (int rep = 0; rep < 2; ++rep) {
             CK(cudaEventRecord(e0));
             k_slice<<<(unsigned)(((size_t)Mbig * K + 255) / 256), 256>>>(dA, Mbig, K, K, nullptr, expA, dAs);
             CK(cudaEventRecord(e1));
-            k_ozaki_gemm<<<(Mbig / TM) * (N / TN), THREADS, smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
+            if (variant == 0) k_ozaki_gemm<<<(Mbig / TM) * (N / TN), THREADS, smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
+            else k_ozaki_gemm_v1<<<(Mbig / TM) * (N / TN), V1_THREADS, NSTAGE * smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
             CK(cudaEventRecord(e2));
             CK(cudaDeviceSynchronize());
         }
@@ -213,8 +384,8 @@ int main(int argc, char** argv) {
         if (hfail) { printf("MMA wait timed out\n"); return 1; }
         float ms_s, ms_g; CK(cudaEventElapsedTime(&ms_s, e0, e1)); CK(cudaEventElapsedTime(&ms_g, e1, e2));
         const double flop = 2.0 * Mbig * (double)N * K * (tri ? 0.5 + 0.5 * TN / N : 1.0);
-        printf("tri=%d M=%d: slicing A %.3f ms, slice-product GEMM %.3f ms = %.1f fp64-equivalent TFLOP/s (%d slices, %d int8 MMAs per k-step)\n",
-               tri, Mbig, ms_s, ms_g, flop / (ms_g * 1e-3) / 1e12, S, S * (S + 1) / 2);
+        printf("v%d tri=%d M=%d: slicing A %.3f ms, slice-product GEMM %.3f ms = %.1f fp64-equivalent TFLOP/s (%d slices, %d int8 MMAs per k-step)\n",
+               variant, tri, Mbig, ms_s, ms_g, flop / (ms_g * 1e-3) / 1e12, S, S * (S + 1) / 2);
         // accuracy against a long-double CPU product on the first Mcheck rows
         std::vector<double> hC((size_t)Mcheck * N);
         CK(cudaMemcpy(hC.data(), dC, hC.size() * 8, cudaMemcpyDeviceToHost));
