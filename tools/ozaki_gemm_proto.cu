@@ -7,6 +7,7 @@
 // walked ceil(S/4) times.  Operands are staged by plain loads into the K-major no-swizzle canonical layout (see
 // i8_mma_probe.cu); v0 has no load/MMA overlap -- it exists to pin the arithmetic and to give a first rate.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/ozaki_gemm_proto tools/ozaki_gemm_proto.cu
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -15,6 +16,9 @@
 #include <vector>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+__device__ unsigned long long g_t[4] = {~0ull, 0ull, ~0ull, 0ull};     // [spin start, spin end, gemm start, gemm end] (globaltimer ns)
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 constexpr int S = 8;            // slices per operand (8 x 7 bits = 56 bits)
 constexpr int TM = 128, TN = 128, KB = 32, THREADS = 256;
@@ -345,6 +349,202 @@ k_ozaki_gemm_v1(const int8_t* __restrict__ As, const int8_t* __restrict__ Bs, in
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+// ---- v2: TMA-fed pipeline -----------------------------------------------------------------------------------------------------
+// The slice planes are described to TMA as a 4-D byte tensor (16 B within a K-chunk, row, K-chunk, plane) so that ONE bulk copy
+// with box (16, 128, KB/16, 1) lands a plane of a stage directly in the canonical no-swizzle layout [chunk][row][16 B].
+// warp 4: TMA producer, warp 5: MMA issuer, warps 0..3: epilogue (coalesced through a padded shared-memory transpose).
+constexpr int V2_THREADS = 192, V2_STAGES = 2;
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(V2_THREADS, 2)
+k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, int K, int tri,
+                const double* __restrict__ scale, double* __restrict__ C, int ldc, int* __restrict__ fail) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full[V2_STAGES], empty[V2_STAGES], acc_full, acc_empty;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_n = N / TN;
+    const int grp = blockIdx.x / (16 * tiles_n), rem = blockIdx.x % (16 * tiles_n);
+    const int tile_m = grp * 16 + rem % 16, n_ord = rem / 16;
+    const int tile_n = tri ? tiles_n - 1 - n_ord : n_ord;
+    const int m0 = tile_m * TM, n0 = tile_n * TN;
+    const int k_end = tri ? min(K, n0 + TN) : K;
+    const int nk = k_end / KB;
+    constexpr int PLANE = TM * KB, STAGE = 2 * S * PLANE;
+    double* s_tr = reinterpret_cast<double*>(smem + (size_t)V2_STAGES * STAGE);      // 4 warps x 32 x 33 doubles
+    if (tid == 0) atomicMin(&g_t[2], gtime());
+    if (tid == 0) {
+        for (int s = 0; s < V2_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&empty[s])));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&acc_full)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_u32(&acc_empty)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base;
+    constexpr int NPASS = (S + 3) / 4;
+    bool ok = true;
+
+    if (warp == 4) {
+        if (lane == 0) {            // ===== TMA producer =====
+            int it = 0;
+            for (int pass = 0; pass < NPASS && ok; ++pass) {
+                const int s_max = min(S + 1, 2 + 4 * pass + 3) - 1;
+                for (int kt = 0; kt < nk && ok; ++kt, ++it) {
+                    const int st = it % V2_STAGES;
+                    if (it >= V2_STAGES) ok = mbar_wait_bounded(smem_u32(&empty[st]), ((it / V2_STAGES) & 1) ^ 1);
+                    const uint32_t bar = smem_u32(&full[st]);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * s_max * PLANE) : "memory");
+                    const uint32_t a0 = smem_u32(smem + (size_t)st * STAGE), b0 = a0 + S * PLANE;
+                    for (int pl = 0; pl < s_max; ++pl) {
+                        tma_load_4d(a0 + pl * PLANE, &mapA, 0, m0, kt * (KB / 16), pl, bar);
+                        tma_load_4d(b0 + pl * PLANE, &mapB, 0, n0, kt * (KB / 16), pl, bar);
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = make_idesc_i8(TM, TN);
+        int it = 0;
+        for (int pass = 0; pass < NPASS && ok; ++pass) {
+            const int t_lo = 2 + 4 * pass, t_hi = min(S + 1, t_lo + 3);
+            if (pass > 0) ok = mbar_wait_bounded(smem_u32(&acc_empty), (pass - 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            for (int kt = 0; kt < nk && ok; ++kt, ++it) {
+                const int st = it % V2_STAGES;
+                ok = mbar_wait_bounded(smem_u32(&full[st]), (it / V2_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                if (lane == 0 && ok) {
+                    const uint32_t a0 = smem_u32(smem + (size_t)st * STAGE), b0 = a0 + S * PLANE;
+                    for (int t = t_lo; t <= t_hi; ++t)
+                        for (int i = 1; i < t; ++i) {
+                            const int j = t - i;
+                            if (i > S || j > S) continue;
+                            mma_i8(tmem + (uint32_t)(t - t_lo) * TN, make_desc(a0 + (uint32_t)(i - 1) * PLANE, TM * 16, 128),
+                                   make_desc(b0 + (uint32_t)(j - 1) * PLANE, TN * 16, 128), idesc, (kt > 0) || (i > 1));
+                        }
+                    tc_commit(smem_u32(&empty[st]));
+                    if (kt == nk - 1) tc_commit(smem_u32(&acc_full));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue warps 0..3 =====
+        double* tr = s_tr + warp * 32 * 33;
+        for (int pass = 0; pass < NPASS && ok; ++pass) {
+            const int t_lo = 2 + 4 * pass, t_hi = min(S + 1, t_lo + 3);
+            ok = mbar_wait_bounded(smem_u32(&acc_full), pass & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            if (!ok) break;
+            for (int c0 = 0; c0 < TN; c0 += 32) {
+                double acc[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+                for (int t = t_hi; t >= t_lo; --t) {
+                    uint32_t v[32];
+                    const uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t - t_lo) * TN + c0;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                                   "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                                   "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                 : "r"(addr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const double w = ldexp(1.0, -7 * t);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = fma((double)(int32_t)v[j], w, acc[j]);
+                }
+                // transpose through shared memory: lane = row -> lane = column, 256-byte row segments to global memory
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = acc[j];
+                __syncwarp();
+                const double sc = scale[n0 + c0 + lane];
+                for (int r = 0; r < 32; ++r) {
+                    double* dst = C + (size_t)(m0 + warp * 32 + r) * ldc + n0 + c0 + lane;
+                    const double val = tr[r * 33 + lane] * sc;
+                    *dst = pass == 0 ? val : *dst + val;
+                }
+                __syncwarp();
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            mbar_arrive(smem_u32(&acc_empty));
+        }
+    }
+    if (!ok && lane == 0) atomicExch(fail, 1);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    if (tid == 0) atomicMax(&g_t[3], gtime());
+}
+
+__global__ void k_col_scale(const int* __restrict__ expB, int expA, int N, double* __restrict__ scale) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) scale[n] = ldexp(1.0, expA + expB[n]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static CUtensorMap make_slice_map(const int8_t* base, int rows, int K) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { printf("cuTensorMapEncodeTiled not available\n"); exit(1); }
+        encode = (EncodeTiledFn)fn;
+    }
+    CUtensorMap m;
+    const cuuint64_t gdim[4] = {16, (cuuint64_t)rows, (cuuint64_t)(K / 16), (cuuint64_t)S};
+    const cuuint64_t gstr[3] = {(cuuint64_t)K, 16, (cuuint64_t)rows * K};           // bytes, dims 1..3
+    const cuuint32_t box[4] = {16, 128, KB / 16, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)r); exit(1); }
+    return m;
+}
+
+__global__ void k_sleep(int slot, unsigned ns) {
+    if (threadIdx.x == 0) atomicMin(&g_t[slot], gtime());
+    const unsigned long long t0 = gtime();
+    while (gtime() - t0 < ns) __nanosleep(1000);
+    if (threadIdx.x == 0) atomicMax(&g_t[slot + 1], gtime());
+}
+
+// fp64-pipe load for the co-residency experiment: 8 independent DFMA chains per thread, no shared memory
+__global__ void __launch_bounds__(256) k_dfma_spin(int iters, double* out) {
+    if (threadIdx.x == 0) atomicMin(&g_t[0], gtime());
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = threadIdx.x * 1e-3 + j;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fma(a[j], 0.999999, 1e-9);
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j];
+    if (s == 12345.678) out[0] = s;
+    if (threadIdx.x == 0) atomicMax(&g_t[1], gtime());
+}
+
 static double urand() { return rand() / (double)RAND_MAX; }
 
 int main(int argc, char** argv) {
@@ -368,7 +568,12 @@ int main(int argc, char** argv) {
     const size_t smem = (size_t)2 * S * TM * KB;
     CK(cudaFuncSetAttribute(k_ozaki_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_ozaki_gemm_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NSTAGE * smem)));
-    for (int variant = 0; variant <= 1; ++variant)
+    double* dscale; CK(cudaMalloc(&dscale, N * 8));
+    k_col_scale<<<(N + 255) / 256, 256>>>(dexpB, expA, N, dscale);
+    const CUtensorMap mapA = make_slice_map(dAs, Mbig, K), mapB = make_slice_map(dBs, N, K);
+    const size_t smem_v2 = (size_t)V2_STAGES * smem + 4 * 32 * 33 * 8;
+    CK(cudaFuncSetAttribute(k_ozaki_gemm_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
+    for (int variant = 0; variant <= 2; ++variant)
     for (int tri = 0; tri <= 1; ++tri) {
         CK(cudaMemset(dC, 0, (size_t)Mbig * N * 8));
         for (int rep = 0; rep < 2; ++rep) {
@@ -376,7 +581,8 @@ int main(int argc, char** argv) {
             k_slice<<<(unsigned)(((size_t)Mbig * K + 255) / 256), 256>>>(dA, Mbig, K, K, nullptr, expA, dAs);
             CK(cudaEventRecord(e1));
             if (variant == 0) k_ozaki_gemm<<<(Mbig / TM) * (N / TN), THREADS, smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
-            else k_ozaki_gemm_v1<<<(Mbig / TM) * (N / TN), V1_THREADS, NSTAGE * smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
+            else if (variant == 1) k_ozaki_gemm_v1<<<(Mbig / TM) * (N / TN), V1_THREADS, NSTAGE * smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
+            else k_ozaki_gemm_v2<<<(Mbig / TM) * (N / TN), V2_THREADS, smem_v2>>>(mapA, mapB, Mbig, N, K, tri, dscale, dC, N, dfail);
             CK(cudaEventRecord(e2));
             CK(cudaDeviceSynchronize());
         }
@@ -403,6 +609,56 @@ int main(int argc, char** argv) {
             }
         printf("  accuracy on %d rows: max abs err %.3e (max |C| %.3e), max err / sum|a b| %.3e (fp64 dot product bound ~ %.1e)\n",
                Mcheck, max_err, max_ref, max_rel_scale, 1024 * 1.1e-16);
+    }
+    // ---- co-residency experiment: does the int8 tensor path run beside a saturated fp64 pipe? ----------------------------------
+    {
+        cudaStream_t s1, s2; CK(cudaStreamCreate(&s1)); CK(cudaStreamCreate(&s2));
+        int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+        const int grid = (Mbig / TM) * (N / TN);
+        const int iters = 30000;
+        // both kernels must ask for the same shared-memory carve-out, or the SM is drained between them
+        CK(cudaFuncSetAttribute(k_dfma_spin, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(k_ozaki_gemm_v2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        auto gemm = [&](cudaStream_t st) { k_ozaki_gemm_v2<<<grid, V2_THREADS, smem_v2, st>>>(mapA, mapB, Mbig, N, K, 0, dscale, dC, N, dfail); };
+        auto spin = [&](cudaStream_t st) { k_dfma_spin<<<sms, 256, 16384, st>>>(iters, dC); };
+        auto timed = [&](int which) {
+            CK(cudaDeviceSynchronize());
+            cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+            CK(cudaEventRecord(a, 0));
+            CK(cudaStreamWaitEvent(s1, a, 0)); CK(cudaStreamWaitEvent(s2, a, 0));
+            if (which & 1) spin(s1);
+            if (which & 2) gemm(s2);
+            cudaEvent_t e1_, e2_; CK(cudaEventCreate(&e1_)); CK(cudaEventCreate(&e2_));
+            CK(cudaEventRecord(e1_, s1)); CK(cudaEventRecord(e2_, s2));
+            CK(cudaStreamWaitEvent(0, e1_, 0)); CK(cudaStreamWaitEvent(0, e2_, 0));
+            CK(cudaEventRecord(b, 0));
+            CK(cudaDeviceSynchronize());
+            float ms; CK(cudaEventElapsedTime(&ms, a, b));
+            return ms;
+        };
+        {   // harness check: two independent one-warp-per-SM sleep kernels on the two streams must overlap
+            unsigned long long init0[4] = {~0ull, 0ull, ~0ull, 0ull}, got0[4];
+            CK(cudaMemcpyToSymbol(g_t, init0, sizeof(init0)));
+            CK(cudaDeviceSynchronize());
+            k_sleep<<<sms, 32, 0, s1>>>(0, 300000);
+            k_sleep<<<sms, 32, 0, s2>>>(2, 300000);
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpyFromSymbol(got0, g_t, sizeof(got0)));
+            const unsigned long long z0 = got0[0] < got0[2] ? got0[0] : got0[2];
+            printf("harness check (two sleep kernels): [%.1f, %.1f] and [%.1f, %.1f] us\n", (got0[0] - z0) * 1e-3, (got0[1] - z0) * 1e-3,
+                   (got0[2] - z0) * 1e-3, (got0[3] - z0) * 1e-3);
+        }
+        timed(3);
+        const float t_spin = timed(1), t_gemm = timed(2);
+        unsigned long long init[4] = {~0ull, 0ull, ~0ull, 0ull}, got[4];
+        CK(cudaMemcpyToSymbol(g_t, init, sizeof(init)));
+        const float t_both = timed(3);
+        CK(cudaMemcpyFromSymbol(got, g_t, sizeof(got)));
+        printf("device timeline of the concurrent run (us from the first start): DFMA kernel [%.1f, %.1f], GEMM [%.1f, %.1f]\n",
+               (got[0] - (got[0] < got[2] ? got[0] : got[2])) * 1e-3, (got[1] - (got[0] < got[2] ? got[0] : got[2])) * 1e-3,
+               (got[2] - (got[0] < got[2] ? got[0] : got[2])) * 1e-3, (got[3] - (got[0] < got[2] ? got[0] : got[2])) * 1e-3);
+        printf("co-residency: DFMA kernel alone %.3f ms, slice-product GEMM (v2, full K) alone %.3f ms, both on two streams %.3f ms "
+               "(serial would be %.3f ms)\n", t_spin, t_gemm, t_both, t_spin + t_gemm);
     }
     return 0;
 }
