@@ -68,6 +68,7 @@ class ConformalAcquisition(nn.Module):
         self.set_X_pending(X_pending)
         self.fixed_probes: Optional[torch.Tensor] = None      # inject z; None: fresh CPU draw per call
         self.fixed_uniforms: Optional[torch.Tensor] = None    # inject the Bernoulli uniforms (App. C-3)
+        self.device_probes = False        # True: draw the probes from the device generator (no host RNG / upload per call)
         # candidate-sharded scoring with max_grid_refinements > 0: distributed.refine_reducer() makes the refinement
         # decisions batch-global again; None: per-call statistics
         self.refine_reduce = None
@@ -119,7 +120,7 @@ class ConformalAcquisition(nn.Module):
         return GraphedConformalAcq(state, b, q, eps_grid=eps, eps_mc=eps_mc, ratio=_ratio_weights(self.ratio_estimator, dev),
                                    want_grad=want_grad, alpha=self.alpha, temp=self.temp, grid_res=G,
                                    max_grid_refinements=0, randomized=self.randomized, optimistic=self.optimistic,
-                                   **self._acq_params())
+                                   device_probes=self.device_probes, **self._acq_params())
 
     def _conformal_fwd(self, X: torch.Tensor, outputs=(), raw_grad=False) -> torch.Tensor:
         if self.model is None:
@@ -144,7 +145,8 @@ class ConformalAcquisition(nn.Module):
             eps = self.grid_sampler.draw((G, b, q), dev).movedim(0, 1).contiguous()
         S = int(self.sampler.sample_shape[0])
         eps_mc = self.sampler.draw((S, G, self._mc_width(q)), dev)
-        z = self.fixed_probes.to(dev) if self.fixed_probes is not None else draw_probes(state.N + q, device=dev)
+        z = self.fixed_probes.to(dev) if self.fixed_probes is not None else draw_probes(state.N + q, device=dev,
+                                                                                        on_device=self.device_probes)
         u = self.fixed_uniforms
         if self.randomized and u is None:
             u = torch.rand(b, G, q, dtype=torch.float64, device=dev)

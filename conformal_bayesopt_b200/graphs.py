@@ -26,12 +26,14 @@ class GraphedConformalAcq:
     """
 
     def __init__(self, state: GPModelState, b: int, q: int, *, eps_grid: torch.Tensor, eps_mc: torch.Tensor,
-                 ratio: Optional["ops.RatioWeights"] = None, want_grad: bool = True, num_probes: int = 8, **param_kw):
+                 ratio: Optional["ops.RatioWeights"] = None, want_grad: bool = True, num_probes: int = 8,
+                 device_probes: bool = False, **param_kw):
         if int(param_kw.get("max_grid_refinements", 0)) > 0:
             raise ValueError("grid refinement synchronises with the host once per pass and cannot be captured")
         dev = state.device
         self.state, self.b, self.q, self.want_grad = state, int(b), int(q), bool(want_grad)
         self.randomized = bool(param_kw.get("randomized", False))
+        self.device_probes = bool(device_probes)          # probes from the device generator: no host work per replay
         G = int(param_kw["grid_res"])
         f64 = dict(dtype=torch.float64, device=dev)
         self.X = torch.zeros(b, q, state.d, **f64)
@@ -52,8 +54,8 @@ class GraphedConformalAcq:
 
     def __call__(self, X: torch.Tensor, z: Optional[torch.Tensor] = None, u_rand: Optional[torch.Tensor] = None):
         self.X.copy_(X.reshape(self.X.shape), non_blocking=True)
-        self.z.copy_(z if z is not None else draw_probes(self.z.shape[0], self.z.shape[1], device=self.z.device),
-                     non_blocking=True)
+        self.z.copy_(z if z is not None else draw_probes(self.z.shape[0], self.z.shape[1], device=self.z.device,
+                                                         on_device=self.device_probes), non_blocking=True)
         if self.randomized:
             if u_rand is not None:
                 self.u.copy_(u_rand.reshape(self.u.shape), non_blocking=True)

@@ -31,17 +31,46 @@ def as_state(model) -> GPModelState:
     return state
 
 
-def draw_probes(n_rows: int, num_samples: int = 8, device=None) -> torch.Tensor:
+class _PinnedRing:
+    """A small ring of pinned staging buffers per (shape, dtype): an async upload that does not synchronise the host with the
+    stream and never allocates in steady state (torch's caching host allocator would `cudaHostAlloc` a new block whenever the
+    host runs ahead of the device).  Before a slot is reused its previous copy is waited for, which bounds the run-ahead."""
+    _rings = {}
+
+    @classmethod
+    def upload(cls, src: torch.Tensor, device, slots: int = 8) -> torch.Tensor:
+        key = (tuple(src.shape), src.dtype, torch.device(device))
+        ring = cls._rings.get(key)
+        if ring is None:
+            ring = cls._rings[key] = dict(i=0, buf=[torch.empty(src.shape, dtype=src.dtype).pin_memory() for _ in range(slots)],
+                                          ev=[None] * slots)
+        i = ring["i"]
+        ring["i"] = (i + 1) % slots
+        if ring["ev"][i] is not None:
+            ring["ev"][i].synchronize()
+        ring["buf"][i].copy_(src)
+        out = ring["buf"][i].to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        ring["ev"][i] = ev
+        return out
+
+
+def draw_probes(n_rows: int, num_samples: int = 8, device=None, on_device: bool = False) -> torch.Tensor:
     """Rademacher probes drawn from the CPU default generator, as est_train_post_var does (helpers.py:399-400): same draws
     and values as `2 * ((rand > 0.5).double() - 0.5)`.  With `device`, only the sign bits cross the bus (1 byte per probe
-    entry) and the +-1 doubles are formed on the device."""
+    entry) and the +-1 doubles are formed on the device.  `on_device=True` draws from the device generator instead (no host
+    work per call; a different random stream than the reference's)."""
+    if on_device and device is not None:
+        one = torch.ones((), dtype=torch.float64, device=device)
+        return torch.where(torch.rand(n_rows, num_samples, device=device) > 0.5, one, -one)
     bits = torch.rand(n_rows, num_samples) > 0.5
     if device is None:
         return torch.where(bits, 1.0, -1.0).to(torch.float64)
     one = torch.ones((), dtype=torch.float64, device=device)
-    # pinned staging (torch's caching host allocator keeps the block alive until the copy has run): the upload does not
-    # synchronise the host with the stream, so the next step's host work overlaps this step's kernels
-    return torch.where(bits.pin_memory().to(device, non_blocking=True), one, -one)
+    # pinned staging: the upload does not synchronise the host with the stream, so the next step's host work overlaps this
+    # step's kernels
+    return torch.where(_PinnedRing.upload(bits, device), one, -one)
 
 
 def _ratio_weights(ratio_estimator, device):

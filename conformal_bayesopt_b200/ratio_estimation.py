@@ -168,8 +168,8 @@ class RatioEstimator(nn.Module):
         if self.device_permutation:
             idx = torch.randperm(num_positive, device=device)[:num_negative].contiguous()
         else:       # the reference's generator and draw (:129-131), 8 bytes per row to the device
-            idx = torch.from_numpy(np.random.permutation(num_positive)[:num_negative].copy()).pin_memory().to(
-                device, non_blocking=True)
+            from .helpers import _PinnedRing
+            idx = _PinnedRing.upload(torch.from_numpy(np.random.permutation(num_positive)[:num_negative].copy()), device)
         t = self._train_state(device)
         t["step"] += 1
         t["ws"] = ops.ratio_train_step(t["theta"], t["m"], t["v"], t["target"], x_neg=self._neg_dev[1],

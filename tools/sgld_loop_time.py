@@ -35,6 +35,11 @@ for N in (80, 1024):
     slope_g = (loop(4 * steps, True) - t_all) / (3 * steps)
     t_nog = loop(steps, False)
     slope_n = (loop(4 * steps, False) - t_nog) / (3 * steps)
+    est.device_permutation, acq.device_probes = True, True      # no host RNG in the step
+    loop(40, True)
+    t_dev = loop(steps, True)
+    slope_dev = (loop(4 * steps, True) - t_dev) / (3 * steps)
+    est.device_permutation, acq.device_probes = False, False
     # parts, each timed alone over 100 repetitions
     def timed(fn, n=100):
         for _ in range(5): fn()
@@ -51,4 +56,4 @@ for N in (80, 1024):
     t_up = timed(lambda: (torch.randn_like(X), ops.sgld_update(X, buf, g, noise, bounds[0].contiguous(), bounds[1].contiguous(), lr=1e-9, momentum=0.1, temperature=0.0)))
     print(f"N={N:5d}: {steps} SGLD steps incl. final trajectory scoring {t_all*1e3:.1f} ms = {t_all/steps*1e3:.3f} ms/step | "
           f"ratio training callback {t_cb:.3f} ms ({t_cbd:.3f} ms with device_permutation, pool of {est.num_positive} rows), value+grad {t_vg:.3f} ms, noise+update {t_up:.3f} ms; "
-          f"without graph replay {t_nog/steps*1e3:.3f} ms/step; marginal per step {slope_g*1e3:.3f} ms (graph) / {slope_n*1e3:.3f} ms (direct); trained steps {est._train['step']}, loss {float(est.last_loss):.4f}")
+          f"without graph replay {t_nog/steps*1e3:.3f} ms/step; marginal per step {slope_g*1e3:.3f} ms (graph) / {slope_n*1e3:.3f} ms (direct) / {slope_dev*1e3:.3f} ms (graph, device-side probes and minibatch draw); trained steps {est._train['step']}, loss {float(est.last_loss):.4f}")
