@@ -104,3 +104,51 @@ def test_sharded_scoring_world_size_2_gloo(b):
         assert torch.equal(full, want)                    # sharded == unsharded, bit for bit
         assert idx == int(torch.argmax(want)) and val == float(want.max())
         assert torch.equal(shared, torch.zeros(3, dtype=torch.float64))
+
+
+def test_cosine_schedule_closed_form_matches_the_reference_scheduler():
+    """optim.cosine_lr against the learning rates torch's CosineAnnealingLR produced around the reference's SGLD class
+    (tests/golden/ref_training.pt), including the cycles past T_max."""
+    import os
+    from conformal_bayesopt_b200.optim import cosine_lr
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ref_training.pt"))
+    for case in gold["sgld"]:
+        for s, lr in enumerate(case["lrs"]):
+            assert abs(cosine_lr(s, case["lr0"], case["T_max"], case["lr0"] / 16.0) - lr) <= 1e-15 * abs(lr) + 1e-18
+
+
+def test_flat_parameter_views_follow_torch_parameter_order():
+    from conformal_bayesopt_b200 import ops
+    d = 5
+    net = torch.nn.Sequential(torch.nn.Linear(d, 64), torch.nn.ReLU(), torch.nn.Linear(64, 64), torch.nn.ReLU(),
+                              torch.nn.Linear(64, 1)).double()
+    flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    assert flat.numel() == ops.ratio_num_params(d)
+    w = ops.RatioWeights.from_flat(flat, d)
+    ref = ops.RatioWeights.from_sequential(net, "cpu")
+    for a, b in zip((w.W1, w.b1, w.W2, w.b2, w.W3, w.b3), (ref.W1, ref.b1, ref.W2, ref.b2, ref.W3, ref.b3)):
+        assert a.shape == b.shape and torch.equal(a, b)
+    flat[0] = 123.0                                   # views, not copies
+    assert w.W1[0, 0] == 123.0
+
+
+def test_initial_conditions_keep_the_best_raw_sample():
+    """gen_batch_initial_conditions (botorch's heuristic, restated): restarts inside the bounds, the best raw sample kept."""
+    from conformal_bayesopt_b200.optim import gen_batch_initial_conditions
+    bounds = torch.tensor([[0.0, -1.0, 2.0], [1.0, 1.0, 4.0]], dtype=torch.float64)
+    target = torch.tensor([0.3, 0.2, 3.1], dtype=torch.float64)
+    seen = []
+
+    def acq(X):                                       # (n, q, d) -> (n,)
+        seen.append(X)
+        return -((X - target) ** 2).sum(-1).min(-1).values
+
+    torch.manual_seed(0)
+    ics = gen_batch_initial_conditions(acq, bounds, q=2, num_restarts=5, raw_samples=64, options=dict(seed=3, batch_limit=16))
+    assert ics.shape == (5, 2, 3) and len(seen) == 4
+    assert bool(((ics >= bounds[0]) & (ics <= bounds[1])).all())
+    raw = torch.cat(seen)
+    best = raw[acq(raw).argmax()]
+    assert any(torch.equal(ic, best) for ic in ics)
+    with pytest.raises(RuntimeError):
+        gen_batch_initial_conditions(acq, bounds, q=2, num_restarts=100, raw_samples=64)
