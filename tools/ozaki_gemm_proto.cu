@@ -420,13 +420,18 @@ k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // ===== MMA issuer =====
         const uint32_t idesc = make_idesc_i8(TM, TN);
         int it = 0;
+        long long w_full = 0, w_acc = 0, t_begin = clock64();
         for (int pass = 0; pass < NPASS && ok; ++pass) {
             const int t_lo = 2 + 4 * pass, t_hi = min(S + 1, t_lo + 3);
+            long long c0_ = clock64();
             if (pass > 0) ok = mbar_wait_bounded(smem_u32(&acc_empty), (pass - 1) & 1);
+            w_acc += clock64() - c0_;
             asm volatile("tcgen05.fence::after_thread_sync;");
             for (int kt = 0; kt < nk && ok; ++kt, ++it) {
                 const int st = it % V2_STAGES;
+                c0_ = clock64();
                 ok = mbar_wait_bounded(smem_u32(&full[st]), (it / V2_STAGES) & 1);
+                w_full += clock64() - c0_;
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 if (lane == 0 && ok) {
                     const uint32_t a0 = smem_u32(smem + (size_t)st * STAGE), b0 = a0 + S * PLANE;
@@ -443,12 +448,18 @@ k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 __syncwarp();
             }
         }
+        if (blockIdx.x == 0 && lane == 0)
+            printf("  [v2 CTA 0, MMA warp] issue loop %lld clk, of which waiting for operands %lld, waiting for the epilogue %lld\n",
+                   clock64() - t_begin, w_full, w_acc);
     } else {
         // ===== epilogue warps 0..3 =====
         double* tr = s_tr + warp * 32 * 33;
+        long long t_epi = 0, w_accf = 0;
         for (int pass = 0; pass < NPASS && ok; ++pass) {
             const int t_lo = 2 + 4 * pass, t_hi = min(S + 1, t_lo + 3);
+            long long c1_ = clock64();
             ok = mbar_wait_bounded(smem_u32(&acc_full), pass & 1);
+            w_accf += clock64() - c1_; c1_ = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;");
             if (!ok) break;
             for (int c0 = 0; c0 < TN; c0 += 32) {
@@ -484,7 +495,10 @@ k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             mbar_arrive(smem_u32(&acc_empty));
+            t_epi += clock64() - c1_;
         }
+        if (blockIdx.x == 0 && tid == 0)
+            printf("  [v2 CTA 0, epilogue warp 0] waiting for accumulators %lld clk, epilogue work %lld clk\n", w_accf, t_epi);
     }
     if (!ok && lane == 0) atomicExch(fail, 1);
     asm volatile("tcgen05.fence::before_thread_sync;");
