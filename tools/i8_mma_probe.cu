@@ -164,6 +164,66 @@ static int run(int K, int reps, int grid, bool check) {
     return bad != 0;
 }
 
+// The MMA sequence of the slice-product GEMM (tools/ozaki_gemm_proto.cu) on RESIDENT operands: 8 A planes and 8 B planes of one
+// k-step (128 x 32 B each), 4 accumulators of 128 columns, the 10 + 26 (i, j) pairs of the two passes, no TMA traffic.
+__global__ void __launch_bounds__(128) k_probe_pattern(int reps, long long* __restrict__ cycles, int* __restrict__ fail) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int o = tid; o < 16 * 4096 / 16; o += 128) reinterpret_cast<int4*>(smem)[o] = make_int4(o * 0x01010101, o, ~o, o * 7);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base, idesc = make_idesc_i8(128, 128);
+    long long t0 = clock64();
+    if (tid == 0) {
+        const uint32_t a0 = smem_u32(smem), b0 = a0 + 8 * 4096;
+        for (int rep = 0; rep < reps; ++rep)
+            for (int pass = 0; pass < 2; ++pass)
+                for (int t = 2 + 4 * pass; t <= 5 + 4 * pass; ++t)
+                    for (int i = 1; i < t; ++i) {
+                        const int j = t - i;
+                        if (i > 8 || j > 8) continue;
+                        mma_i8(tmem + (uint32_t)(t - 2 - 4 * pass) * 128, make_desc(a0 + (i - 1) * 4096, 128 * 16, 128),
+                               make_desc(b0 + (j - 1) * 4096, 128 * 16, 128), idesc, 1);
+                    }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    const bool ok = mbar_wait_bounded(smem_u32(&bar), 0);
+    long long t1 = clock64();
+    if (!ok && tid == 0) atomicExch(fail, 1);
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+static void run_pattern(int sms) {
+    long long* dcyc; int* dfail;
+    CK(cudaMalloc(&dcyc, sms * 8)); CK(cudaMalloc(&dfail, 4)); CK(cudaMemset(dfail, 0, 4));
+    CK(cudaFuncSetAttribute(k_probe_pattern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    const int reps = 512;
+    k_probe_pattern<<<sms, 128, 65536>>>(reps, dcyc, dfail);
+    CK(cudaDeviceSynchronize());
+    k_probe_pattern<<<sms, 128, 65536>>>(reps, dcyc, dfail);
+    CK(cudaDeviceSynchronize());
+    int hfail = 0; CK(cudaMemcpy(&hfail, dfail, 4, cudaMemcpyDeviceToHost));
+    long long c0 = 0; CK(cudaMemcpy(&c0, dcyc, 8, cudaMemcpyDeviceToHost));
+    printf("slice-product MMA pattern on resident operands (16 planes, 4 accumulators, 36 MMAs per k-step): %s, %.1f clk per m128n128k32\n",
+           hfail ? "TIMED OUT" : "ok", (double)c0 / (reps * 36.0));
+}
+
 int main() {
     int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     int rc = 0;
@@ -174,5 +234,6 @@ int main() {
     run<256>(256, 2048, sms, false);
     run<128>(256, 2048, sms, false);
     run<64>(256, 2048, sms, false);
+    run_pattern(sms);
     return 0;
 }
