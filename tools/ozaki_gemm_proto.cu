@@ -353,7 +353,7 @@ k_ozaki_gemm_v1(const int8_t* __restrict__ As, const int8_t* __restrict__ Bs, in
 // The slice planes are described to TMA as a 4-D byte tensor (16 B within a K-chunk, row, K-chunk, plane) so that ONE bulk copy
 // with box (16, 128, KB/16, 1) lands a plane of a stage directly in the canonical no-swizzle layout [chunk][row][16 B].
 // warp 4: TMA producer, warp 5: MMA issuer, warps 0..3: epilogue (coalesced through a padded shared-memory transpose).
-constexpr int V2_THREADS = 192, V2_STAGES = 2;
+constexpr int V2_THREADS = 192, V2_STAGES = 3;
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -361,7 +361,8 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 }
 
 __global__ void __launch_bounds__(V2_THREADS, 2)
-k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, int K, int tri,
+k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const __grid_constant__ CUtensorMap mapA8, const __grid_constant__ CUtensorMap mapB8, int M, int N, int K, int tri,
                 const double* __restrict__ scale, double* __restrict__ C, int ldc, int* __restrict__ fail) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t full[V2_STAGES], empty[V2_STAGES], acc_full, acc_empty;
@@ -409,10 +410,9 @@ k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const uint32_t bar = smem_u32(&full[st]);
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * s_max * PLANE) : "memory");
                     const uint32_t a0 = smem_u32(smem + (size_t)st * STAGE), b0 = a0 + S * PLANE;
-                    for (int pl = 0; pl < s_max; ++pl) {
-                        tma_load_4d(a0 + pl * PLANE, &mapA, 0, m0, kt * (KB / 16), pl, bar);
-                        tma_load_4d(b0 + pl * PLANE, &mapB, 0, n0, kt * (KB / 16), pl, bar);
-                    }
+                    // one bulk copy per operand: the box spans the 4 (first pass) or 8 (second pass) slice planes of the stage
+                    tma_load_4d(a0, s_max == 4 ? &mapA : &mapA8, 0, m0, kt * (KB / 16), 0, bar);
+                    tma_load_4d(b0, s_max == 4 ? &mapB : &mapB8, 0, n0, kt * (KB / 16), 0, bar);
                 }
             }
         }
@@ -516,7 +516,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static CUtensorMap make_slice_map(const int8_t* base, int rows, int K) {
+static CUtensorMap make_slice_map(const int8_t* base, int rows, int K, int planes_in_box = 1) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -528,7 +528,7 @@ static CUtensorMap make_slice_map(const int8_t* base, int rows, int K) {
     CUtensorMap m;
     const cuuint64_t gdim[4] = {16, (cuuint64_t)rows, (cuuint64_t)(K / 16), (cuuint64_t)S};
     const cuuint64_t gstr[3] = {(cuuint64_t)K, 16, (cuuint64_t)rows * K};           // bytes, dims 1..3
-    const cuuint32_t box[4] = {16, 128, KB / 16, 1};
+    const cuuint32_t box[4] = {16, 128, KB / 16, (cuuint32_t)planes_in_box};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -584,7 +584,9 @@ int main(int argc, char** argv) {
     CK(cudaFuncSetAttribute(k_ozaki_gemm_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NSTAGE * smem)));
     double* dscale; CK(cudaMalloc(&dscale, N * 8));
     k_col_scale<<<(N + 255) / 256, 256>>>(dexpB, expA, N, dscale);
-    const CUtensorMap mapA = make_slice_map(dAs, Mbig, K), mapB = make_slice_map(dBs, N, K);
+    static_assert(S == 8, "the v2 tensor maps assume 4 + 8 slice planes per stage");
+    const CUtensorMap mapA = make_slice_map(dAs, Mbig, K, 4), mapB = make_slice_map(dBs, N, K, 4);
+    const CUtensorMap mapA8 = make_slice_map(dAs, Mbig, K, 8), mapB8 = make_slice_map(dBs, N, K, 8);
     const size_t smem_v2 = (size_t)V2_STAGES * smem + 4 * 32 * 33 * 8;
     CK(cudaFuncSetAttribute(k_ozaki_gemm_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
     for (int variant = 0; variant <= 2; ++variant)
@@ -596,7 +598,7 @@ int main(int argc, char** argv) {
             CK(cudaEventRecord(e1));
             if (variant == 0) k_ozaki_gemm<<<(Mbig / TM) * (N / TN), THREADS, smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
             else if (variant == 1) k_ozaki_gemm_v1<<<(Mbig / TM) * (N / TN), V1_THREADS, NSTAGE * smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
-            else k_ozaki_gemm_v2<<<(Mbig / TM) * (N / TN), V2_THREADS, smem_v2>>>(mapA, mapB, Mbig, N, K, tri, dscale, dC, N, dfail);
+            else k_ozaki_gemm_v2<<<(Mbig / TM) * (N / TN), V2_THREADS, smem_v2>>>(mapA, mapB, mapA8, mapB8, Mbig, N, K, tri, dscale, dC, N, dfail);
             CK(cudaEventRecord(e2));
             CK(cudaDeviceSynchronize());
         }
@@ -633,7 +635,7 @@ int main(int argc, char** argv) {
         // both kernels must ask for the same shared-memory carve-out, or the SM is drained between them
         CK(cudaFuncSetAttribute(k_dfma_spin, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CK(cudaFuncSetAttribute(k_ozaki_gemm_v2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        auto gemm = [&](cudaStream_t st) { k_ozaki_gemm_v2<<<grid, V2_THREADS, smem_v2, st>>>(mapA, mapB, Mbig, N, K, 0, dscale, dC, N, dfail); };
+        auto gemm = [&](cudaStream_t st) { k_ozaki_gemm_v2<<<grid, V2_THREADS, smem_v2, st>>>(mapA, mapB, mapA8, mapB8, Mbig, N, K, 0, dscale, dC, N, dfail); };
         auto spin = [&](cudaStream_t st) { k_dfma_spin<<<sms, 256, 16384, st>>>(iters, dC); };
         auto timed = [&](int which) {
             CK(cudaDeviceSynchronize());
