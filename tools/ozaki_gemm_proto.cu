@@ -404,15 +404,18 @@ k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             int it = 0;
             for (int pass = 0; pass < NPASS && ok; ++pass) {
                 const int s_max = min(S + 1, 2 + 4 * pass + 3) - 1;
-                for (int kt = 0; kt < nk && ok; ++kt, ++it) {
+                // the first pass needs 4 planes per operand: it takes 64 K-columns per stage, the second (8 planes) 32 -- both
+                // fill the 64 KB stage, and a first-pass stage then carries 20 MMAs, enough to hide the copy latency
+                const int kb = (s_max == 4) ? 2 * KB : KB, plane = TM * kb;
+                for (int kt = 0; kt < k_end / kb && ok; ++kt, ++it) {
                     const int st = it % V2_STAGES;
                     if (it >= V2_STAGES) ok = mbar_wait_bounded(smem_u32(&empty[st]), ((it / V2_STAGES) & 1) ^ 1);
                     const uint32_t bar = smem_u32(&full[st]);
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * s_max * PLANE) : "memory");
-                    const uint32_t a0 = smem_u32(smem + (size_t)st * STAGE), b0 = a0 + S * PLANE;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * s_max * plane) : "memory");
+                    const uint32_t a0 = smem_u32(smem + (size_t)st * STAGE), b0 = a0 + s_max * plane;
                     // one bulk copy per operand: the box spans the 4 (first pass) or 8 (second pass) slice planes of the stage
-                    tma_load_4d(a0, s_max == 4 ? &mapA : &mapA8, 0, m0, kt * (KB / 16), 0, bar);
-                    tma_load_4d(b0, s_max == 4 ? &mapB : &mapB8, 0, n0, kt * (KB / 16), 0, bar);
+                    tma_load_4d(a0, s_max == 4 ? &mapA : &mapA8, 0, m0, kt * (kb / 16), 0, bar);
+                    tma_load_4d(b0, s_max == 4 ? &mapB : &mapB8, 0, n0, kt * (kb / 16), 0, bar);
                 }
             }
         }
@@ -427,23 +430,27 @@ k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (pass > 0) ok = mbar_wait_bounded(smem_u32(&acc_empty), (pass - 1) & 1);
             w_acc += clock64() - c0_;
             asm volatile("tcgen05.fence::after_thread_sync;");
-            for (int kt = 0; kt < nk && ok; ++kt, ++it) {
+            const int s_max = t_hi - 1, kb = (s_max == 4) ? 2 * KB : KB, plane = TM * kb, nkp = k_end / kb;
+            for (int kt = 0; kt < nkp && ok; ++kt, ++it) {
                 const int st = it % V2_STAGES;
                 c0_ = clock64();
                 ok = mbar_wait_bounded(smem_u32(&full[st]), (it / V2_STAGES) & 1);
                 w_full += clock64() - c0_;
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 if (lane == 0 && ok) {
-                    const uint32_t a0 = smem_u32(smem + (size_t)st * STAGE), b0 = a0 + S * PLANE;
-                    for (int t = t_lo; t <= t_hi; ++t)
-                        for (int i = 1; i < t; ++i) {
-                            const int j = t - i;
-                            if (i > S || j > S) continue;
-                            mma_i8(tmem + (uint32_t)(t - t_lo) * TN, make_desc(a0 + (uint32_t)(i - 1) * PLANE, TM * 16, 128),
-                                   make_desc(b0 + (uint32_t)(j - 1) * PLANE, TN * 16, 128), idesc, (kt > 0) || (i > 1));
-                        }
+                    const uint32_t a0 = smem_u32(smem + (size_t)st * STAGE), b0 = a0 + s_max * plane;
+                    for (int sub = 0; sub < kb / 32; ++sub)                          // 32 K-columns = 2 chunks per MMA
+                        for (int t = t_lo; t <= t_hi; ++t)
+                            for (int i = 1; i < t; ++i) {
+                                const int j = t - i;
+                                if (i > S || j > S) continue;
+                                mma_i8(tmem + (uint32_t)(t - t_lo) * TN,
+                                       make_desc(a0 + (uint32_t)(i - 1) * plane + sub * 2 * TM * 16, TM * 16, 128),
+                                       make_desc(b0 + (uint32_t)(j - 1) * plane + sub * 2 * TN * 16, TN * 16, 128), idesc,
+                                       (kt > 0) || (sub > 0) || (i > 1));
+                            }
                     tc_commit(smem_u32(&empty[st]));
-                    if (kt == nk - 1) tc_commit(smem_u32(&acc_full));
+                    if (kt == nkp - 1) tc_commit(smem_u32(&acc_full));
                 }
                 __syncwarp();
             }
@@ -486,10 +493,16 @@ k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = acc[j];
                 __syncwarp();
                 const double sc = scale[n0 + c0 + lane];
-                for (int r = 0; r < 32; ++r) {
-                    double* dst = C + (size_t)(m0 + warp * 32 + r) * ldc + n0 + c0 + lane;
-                    const double val = tr[r * 33 + lane] * sc;
-                    *dst = pass == 0 ? val : *dst + val;
+                double* dst0 = C + (size_t)(m0 + warp * 32) * ldc + n0 + c0 + lane;
+                if (pass == 0) {
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) dst0[(size_t)r * ldc] = tr[r * 33 + lane] * sc;
+                } else {                                                     // all 32 loads of the earlier partial sums in flight
+                    double old[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) old[r] = dst0[(size_t)r * ldc];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) dst0[(size_t)r * ldc] = old[r] + tr[r * 33 + lane] * sc;
                 }
                 __syncwarp();
             }
@@ -516,7 +529,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static CUtensorMap make_slice_map(const int8_t* base, int rows, int K, int planes_in_box = 1) {
+static CUtensorMap make_slice_map(const int8_t* base, int rows, int K, int planes_in_box = 1, int chunks_in_box = KB / 16) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -528,7 +541,7 @@ static CUtensorMap make_slice_map(const int8_t* base, int rows, int K, int plane
     CUtensorMap m;
     const cuuint64_t gdim[4] = {16, (cuuint64_t)rows, (cuuint64_t)(K / 16), (cuuint64_t)S};
     const cuuint64_t gstr[3] = {(cuuint64_t)K, 16, (cuuint64_t)rows * K};           // bytes, dims 1..3
-    const cuuint32_t box[4] = {16, 128, KB / 16, (cuuint32_t)planes_in_box};
+    const cuuint32_t box[4] = {16, 128, (cuuint32_t)chunks_in_box, (cuuint32_t)planes_in_box};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -585,7 +598,7 @@ int main(int argc, char** argv) {
     double* dscale; CK(cudaMalloc(&dscale, N * 8));
     k_col_scale<<<(N + 255) / 256, 256>>>(dexpB, expA, N, dscale);
     static_assert(S == 8, "the v2 tensor maps assume 4 + 8 slice planes per stage");
-    const CUtensorMap mapA = make_slice_map(dAs, Mbig, K, 4), mapB = make_slice_map(dBs, N, K, 4);
+    const CUtensorMap mapA = make_slice_map(dAs, Mbig, K, 4, 2 * KB / 16), mapB = make_slice_map(dBs, N, K, 4, 2 * KB / 16);
     const CUtensorMap mapA8 = make_slice_map(dAs, Mbig, K, 8), mapB8 = make_slice_map(dBs, N, K, 8);
     const size_t smem_v2 = (size_t)V2_STAGES * smem + 4 * 32 * 33 * 8;
     CK(cudaFuncSetAttribute(k_ozaki_gemm_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
