@@ -28,6 +28,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
 }
+// K-major operand in a TMA-swizzled layout: rows of `row_bytes` (32 or 64) bytes, 8-row groups `8 * row_bytes` apart
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 64 ? 4 : 6;                 // SWIZZLE_64B = 4, SWIZZLE_32B = 6
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(((8 * row_bytes) >> 4) & 0x3fff) << 32) |
+           ((uint64_t)1 << 46) | (layout << 61);
+}
 __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -360,6 +366,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(V2_THREADS, 2)
 k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const __grid_constant__ CUtensorMap mapA8, const __grid_constant__ CUtensorMap mapB8, int M, int N, int K, int tri,
@@ -414,8 +425,8 @@ k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * s_max * plane) : "memory");
                     const uint32_t a0 = smem_u32(smem + (size_t)st * STAGE), b0 = a0 + s_max * plane;
                     // one bulk copy per operand: the box spans the 4 (first pass) or 8 (second pass) slice planes of the stage
-                    tma_load_4d(a0, s_max == 4 ? &mapA : &mapA8, 0, m0, kt * (kb / 16), 0, bar);
-                    tma_load_4d(b0, s_max == 4 ? &mapB : &mapB8, 0, n0, kt * (kb / 16), 0, bar);
+                    tma_load_3d(a0, s_max == 4 ? &mapA : &mapA8, kt * kb, m0, 0, bar);
+                    tma_load_3d(b0, s_max == 4 ? &mapB : &mapB8, kt * kb, n0, 0, bar);
                 }
             }
         }
@@ -445,8 +456,8 @@ k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                 const int j = t - i;
                                 if (i > S || j > S) continue;
                                 mma_i8(tmem + (uint32_t)(t - t_lo) * TN,
-                                       make_desc(a0 + (uint32_t)(i - 1) * plane + sub * 2 * TM * 16, TM * 16, 128),
-                                       make_desc(b0 + (uint32_t)(j - 1) * plane + sub * 2 * TN * 16, TN * 16, 128), idesc,
+                                       make_desc_sw(a0 + (uint32_t)(i - 1) * plane + sub * 32, kb),
+                                       make_desc_sw(b0 + (uint32_t)(j - 1) * plane + sub * 32, kb), idesc,
                                        (kt > 0) || (sub > 0) || (i > 1));
                             }
                     tc_commit(smem_u32(&empty[st]));
@@ -529,6 +540,27 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// 3-D byte tensor (K, rows, planes) with a swizzled box of `kb` (32 / 64) K-bytes x 128 rows x planes: rows of kb bytes in
+// shared memory, 16-byte chunks XOR-swizzled the way the UMMA SWIZZLE_32B / _64B layouts expect
+static CUtensorMap make_slice_map_sw(const int8_t* base, int rows, int K, int planes_in_box, int kb) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { printf("cuTensorMapEncodeTiled not available\n"); exit(1); }
+    typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                           const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    CUtensorMap m;
+    const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)S};
+    const cuuint64_t gstr[2] = {(cuuint64_t)K, (cuuint64_t)rows * K};
+    const cuuint32_t box[3] = {(cuuint32_t)kb, 128, (cuuint32_t)planes_in_box};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((Fn)fn)(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          kb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled (swizzled) failed: %d\n", (int)r); exit(1); }
+    return m;
+}
+
 static CUtensorMap make_slice_map(const int8_t* base, int rows, int K, int planes_in_box = 1, int chunks_in_box = KB / 16) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -598,8 +630,8 @@ int main(int argc, char** argv) {
     double* dscale; CK(cudaMalloc(&dscale, N * 8));
     k_col_scale<<<(N + 255) / 256, 256>>>(dexpB, expA, N, dscale);
     static_assert(S == 8, "the v2 tensor maps assume 4 + 8 slice planes per stage");
-    const CUtensorMap mapA = make_slice_map(dAs, Mbig, K, 4, 2 * KB / 16), mapB = make_slice_map(dBs, N, K, 4, 2 * KB / 16);
-    const CUtensorMap mapA8 = make_slice_map(dAs, Mbig, K, 8), mapB8 = make_slice_map(dBs, N, K, 8);
+    const CUtensorMap mapA = make_slice_map_sw(dAs, Mbig, K, 4, 2 * KB), mapB = make_slice_map_sw(dBs, N, K, 4, 2 * KB);
+    const CUtensorMap mapA8 = make_slice_map_sw(dAs, Mbig, K, 8, KB), mapB8 = make_slice_map_sw(dBs, N, K, 8, KB);
     const size_t smem_v2 = (size_t)V2_STAGES * smem + 4 * 32 * 33 * 8;
     CK(cudaFuncSetAttribute(k_ozaki_gemm_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
     for (int variant = 0; variant <= 2; ++variant)
