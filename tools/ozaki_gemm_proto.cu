@@ -531,6 +531,171 @@ k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (tid == 0) atomicMax(&g_t[3], gtime());
 }
 
+// ---- v3: the same pipeline with the tile width TN_ and the number of anti-diagonals per pass ACC as parameters ---------------------
+// (TN_ = 256, ACC = 2: four passes over K, m128n256k32 MMAs; every bulk copy brings 2 slice planes)
+template <int TN_, int ACC>
+__global__ void __launch_bounds__(V2_THREADS, 1)
+k_ozaki_gemm_v3(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const __grid_constant__ CUtensorMap mapA8, const __grid_constant__ CUtensorMap mapB8,   /* mapX: 64-byte rows, mapX8: 32-byte rows; 2 planes per box */ int M, int N, int K, int tri,
+                const double* __restrict__ scale, double* __restrict__ C, int ldc, int* __restrict__ fail) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int STAGE = S * (TM + TN_) * KB, V3_STAGES = (TN_ > 128) ? 2 : 3;
+    __shared__ __align__(8) uint64_t full[V3_STAGES], empty[V3_STAGES], acc_full, acc_empty;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_n = N / TN_;
+    const int grp = blockIdx.x / (16 * tiles_n), rem = blockIdx.x % (16 * tiles_n);
+    const int tile_m = grp * 16 + rem % 16, n_ord = rem / 16;
+    const int tile_n = tri ? tiles_n - 1 - n_ord : n_ord;
+    const int m0 = tile_m * TM, n0 = tile_n * TN_;
+    const int k_end = tri ? min(K, n0 + TN_) : K;
+    const int nk = k_end / KB;
+    double* s_tr = reinterpret_cast<double*>(smem + (size_t)V3_STAGES * STAGE);      // 4 warps x 32 x 33 doubles
+    if (tid == 0) atomicMin(&g_t[2], gtime());
+    if (tid == 0) {
+        for (int s = 0; s < V3_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&empty[s])));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&acc_full)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_u32(&acc_empty)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base;
+    constexpr int NPASS = (S + ACC - 1) / ACC;
+    bool ok = true;
+
+    if (warp == 4) {
+        if (lane == 0) {            // ===== TMA producer =====
+            int it = 0;
+            for (int pass = 0; pass < NPASS && ok; ++pass) {
+                const int s_max = min(S + 1, 2 + ACC * pass + ACC - 1) - 1;
+                // the first pass needs 4 planes per operand: it takes 64 K-columns per stage, the second (8 planes) 32 -- both
+                // fill the 64 KB stage, and a first-pass stage then carries 20 MMAs, enough to hide the copy latency
+                const int kb = (s_max <= 4) ? 2 * KB : KB, plane = TM * kb, planeB = TN_ * kb;
+                for (int kt = 0; kt < k_end / kb && ok; ++kt, ++it) {
+                    const int st = it % V3_STAGES;
+                    if (it >= V3_STAGES) ok = mbar_wait_bounded(smem_u32(&empty[st]), ((it / V3_STAGES) & 1) ^ 1);
+                    const uint32_t bar = smem_u32(&full[st]);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(s_max * (plane + planeB)) : "memory");
+                    const uint32_t a0 = smem_u32(smem + (size_t)st * STAGE), b0 = a0 + s_max * plane;
+                    // one bulk copy per operand: the box spans the 4 (first pass) or 8 (second pass) slice planes of the stage
+                    for (int pl = 0; pl < s_max; pl += 2) {
+                        tma_load_3d(a0 + pl * plane, kb == 64 ? &mapA : &mapA8, kt * kb, m0, pl, bar);
+                        tma_load_3d(b0 + pl * planeB, kb == 64 ? &mapB : &mapB8, kt * kb, n0, pl, bar);
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = make_idesc_i8(TM, TN_);
+        int it = 0;
+        long long w_full = 0, w_acc = 0, t_begin = clock64();
+        for (int pass = 0; pass < NPASS && ok; ++pass) {
+            const int t_lo = 2 + ACC * pass, t_hi = min(S + 1, t_lo + ACC - 1);
+            long long c0_ = clock64();
+            if (pass > 0) ok = mbar_wait_bounded(smem_u32(&acc_empty), (pass - 1) & 1);
+            w_acc += clock64() - c0_;
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const int s_max = t_hi - 1, kb = (s_max <= 4) ? 2 * KB : KB, plane = TM * kb, planeB = TN_ * kb, nkp = k_end / kb;
+            for (int kt = 0; kt < nkp && ok; ++kt, ++it) {
+                const int st = it % V3_STAGES;
+                c0_ = clock64();
+                ok = mbar_wait_bounded(smem_u32(&full[st]), (it / V3_STAGES) & 1);
+                w_full += clock64() - c0_;
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                if (lane == 0 && ok) {
+                    const uint32_t a0 = smem_u32(smem + (size_t)st * STAGE), b0 = a0 + s_max * plane;
+                    for (int sub = 0; sub < kb / 32; ++sub)                          // 32 K-columns = 2 chunks per MMA
+                        for (int t = t_lo; t <= t_hi; ++t)
+                            for (int i = 1; i < t; ++i) {
+                                const int j = t - i;
+                                if (i > S || j > S) continue;
+                                mma_i8(tmem + (uint32_t)(t - t_lo) * TN_,
+                                       make_desc_sw(a0 + (uint32_t)(i - 1) * plane + sub * 32, kb),
+                                       make_desc_sw(b0 + (uint32_t)(j - 1) * planeB + sub * 32, kb), idesc,
+                                       (kt > 0) || (sub > 0) || (i > 1));
+                            }
+                    tc_commit(smem_u32(&empty[st]));
+                    if (kt == nkp - 1) tc_commit(smem_u32(&acc_full));
+                }
+                __syncwarp();
+            }
+        }
+        if (blockIdx.x == 0 && lane == 0)
+            printf("  [v3 CTA 0, MMA warp] issue loop %lld clk, of which waiting for operands %lld, waiting for the epilogue %lld\n",
+                   clock64() - t_begin, w_full, w_acc);
+    } else {
+        // ===== epilogue warps 0..3 =====
+        double* tr = s_tr + warp * 32 * 33;
+        long long t_epi = 0, w_accf = 0;
+        for (int pass = 0; pass < NPASS && ok; ++pass) {
+            const int t_lo = 2 + ACC * pass, t_hi = min(S + 1, t_lo + ACC - 1);
+            long long c1_ = clock64();
+            ok = mbar_wait_bounded(smem_u32(&acc_full), pass & 1);
+            w_accf += clock64() - c1_; c1_ = clock64();
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            if (!ok) break;
+            for (int c0 = 0; c0 < TN_; c0 += 32) {
+                double acc[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+                for (int t = t_hi; t >= t_lo; --t) {
+                    uint32_t v[32];
+                    const uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t - t_lo) * TN_ + c0;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                                   "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                                   "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                 : "r"(addr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const double w = ldexp(1.0, -7 * t);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = fma((double)(int32_t)v[j], w, acc[j]);
+                }
+                // transpose through shared memory: lane = row -> lane = column, 256-byte row segments to global memory
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = acc[j];
+                __syncwarp();
+                const double sc = scale[n0 + c0 + lane];
+                double* dst0 = C + (size_t)(m0 + warp * 32) * ldc + n0 + c0 + lane;
+                if (pass == 0) {
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) dst0[(size_t)r * ldc] = tr[r * 33 + lane] * sc;
+                } else {                                                     // all 32 loads of the earlier partial sums in flight
+                    double old[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) old[r] = dst0[(size_t)r * ldc];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) dst0[(size_t)r * ldc] = old[r] + tr[r * 33 + lane] * sc;
+                }
+                __syncwarp();
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            mbar_arrive(smem_u32(&acc_empty));
+            t_epi += clock64() - c1_;
+        }
+        if (blockIdx.x == 0 && tid == 0)
+            printf("  [v3 CTA 0, epilogue warp 0] waiting for accumulators %lld clk, epilogue work %lld clk\n", w_accf, t_epi);
+    }
+    if (!ok && lane == 0) atomicExch(fail, 1);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    if (tid == 0) atomicMax(&g_t[3], gtime());
+}
+
 __global__ void k_col_scale(const int* __restrict__ expB, int expA, int N, double* __restrict__ scale) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < N) scale[n] = ldexp(1.0, expA + expB[n]);
@@ -542,7 +707,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // 3-D byte tensor (K, rows, planes) with a swizzled box of `kb` (32 / 64) K-bytes x 128 rows x planes: rows of kb bytes in
 // shared memory, 16-byte chunks XOR-swizzled the way the UMMA SWIZZLE_32B / _64B layouts expect
-static CUtensorMap make_slice_map_sw(const int8_t* base, int rows, int K, int planes_in_box, int kb) {
+static CUtensorMap make_slice_map_sw(const int8_t* base, int rows, int K, int planes_in_box, int kb, int box_rows = 128) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -552,7 +717,7 @@ static CUtensorMap make_slice_map_sw(const int8_t* base, int rows, int K, int pl
     CUtensorMap m;
     const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)S};
     const cuuint64_t gstr[2] = {(cuuint64_t)K, (cuuint64_t)rows * K};
-    const cuuint32_t box[3] = {(cuuint32_t)kb, 128, (cuuint32_t)planes_in_box};
+    const cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)box_rows, (cuuint32_t)planes_in_box};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = ((Fn)fn)(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           kb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -634,7 +799,11 @@ int main(int argc, char** argv) {
     const CUtensorMap mapA8 = make_slice_map_sw(dAs, Mbig, K, 8, KB), mapB8 = make_slice_map_sw(dBs, N, K, 8, KB);
     const size_t smem_v2 = (size_t)V2_STAGES * smem + 4 * 32 * 33 * 8;
     CK(cudaFuncSetAttribute(k_ozaki_gemm_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
-    for (int variant = 0; variant <= 2; ++variant)
+    const CUtensorMap m3A64 = make_slice_map_sw(dAs, Mbig, K, 2, 64), m3A32 = make_slice_map_sw(dAs, Mbig, K, 2, 32);
+    const CUtensorMap m3B64 = make_slice_map_sw(dBs, N, K, 2, 64, 256), m3B32 = make_slice_map_sw(dBs, N, K, 2, 32, 256);
+    const size_t smem_v3 = (size_t)2 * S * (TM + 256) * KB + 4 * 32 * 33 * 8;
+    CK(cudaFuncSetAttribute(k_ozaki_gemm_v3<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v3));
+    for (int variant = 0; variant <= 3; ++variant)
     for (int tri = 0; tri <= 1; ++tri) {
         CK(cudaMemset(dC, 0, (size_t)Mbig * N * 8));
         for (int rep = 0; rep < 2; ++rep) {
@@ -643,7 +812,8 @@ int main(int argc, char** argv) {
             CK(cudaEventRecord(e1));
             if (variant == 0) k_ozaki_gemm<<<(Mbig / TM) * (N / TN), THREADS, smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
             else if (variant == 1) k_ozaki_gemm_v1<<<(Mbig / TM) * (N / TN), V1_THREADS, NSTAGE * smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
-            else k_ozaki_gemm_v2<<<(Mbig / TM) * (N / TN), V2_THREADS, smem_v2>>>(mapA, mapB, mapA8, mapB8, Mbig, N, K, tri, dscale, dC, N, dfail);
+            else if (variant == 2) k_ozaki_gemm_v2<<<(Mbig / TM) * (N / TN), V2_THREADS, smem_v2>>>(mapA, mapB, mapA8, mapB8, Mbig, N, K, tri, dscale, dC, N, dfail);
+            else k_ozaki_gemm_v3<256, 2><<<(Mbig / TM) * (N / 256), V2_THREADS, smem_v3>>>(m3A64, m3B64, m3A32, m3B32, Mbig, N, K, tri, dscale, dC, N, dfail);
             CK(cudaEventRecord(e2));
             CK(cudaDeviceSynchronize());
         }
