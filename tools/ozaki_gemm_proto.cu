@@ -359,7 +359,7 @@ k_ozaki_gemm_v1(const int8_t* __restrict__ As, const int8_t* __restrict__ Bs, in
 // The slice planes are described to TMA as a 4-D byte tensor (16 B within a K-chunk, row, K-chunk, plane) so that ONE bulk copy
 // with box (16, 128, KB/16, 1) lands a plane of a stage directly in the canonical no-swizzle layout [chunk][row][16 B].
 // warp 4: TMA producer, warp 5: MMA issuer, warps 0..3: epilogue (coalesced through a padded shared-memory transpose).
-constexpr int V2_THREADS = 192, V2_STAGES = 3;
+constexpr int V2_THREADS = 192, V2_STAGES = 3, V3_THREADS = 320;
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -534,7 +534,7 @@ k_ozaki_gemm_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 // ---- v3: the same pipeline with the tile width TN_ and the number of anti-diagonals per pass ACC as parameters ---------------------
 // (TN_ = 256, ACC = 2: four passes over K, m128n256k32 MMAs; every bulk copy brings 2 slice planes)
 template <int TN_, int ACC>
-__global__ void __launch_bounds__(V2_THREADS, 1)
+__global__ void __launch_bounds__(V3_THREADS, 1)
 k_ozaki_gemm_v3(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const __grid_constant__ CUtensorMap mapA8, const __grid_constant__ CUtensorMap mapB8,   /* mapX: 64-byte rows, mapX8: 32-byte rows; 2 planes per box */ int M, int N, int K, int tri,
                 const double* __restrict__ scale, double* __restrict__ C, int ldc, int* __restrict__ fail) {
@@ -558,7 +558,7 @@ k_ozaki_gemm_v3(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&empty[s])));
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&acc_full)));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_u32(&acc_empty)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"(smem_u32(&acc_empty)));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 0) {
@@ -635,8 +635,9 @@ k_ozaki_gemm_v3(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             printf("  [v3 CTA 0, MMA warp] issue loop %lld clk, of which waiting for operands %lld, waiting for the epilogue %lld\n",
                    clock64() - t_begin, w_full, w_acc);
     } else {
-        // ===== epilogue warps 0..3 =====
-        double* tr = s_tr + warp * 32 * 33;
+        // ===== epilogue: warps 0..3 and 6..9; warps w and w' with w % 4 == w' % 4 share a TMEM lane quadrant and split the columns
+        const int quad = warp & 3, half = warp < 4 ? 0 : 1;
+        double* tr = s_tr + (half * 4 + quad) * 32 * 17;
         long long t_epi = 0, w_accf = 0;
         for (int pass = 0; pass < NPASS && ok; ++pass) {
             const int t_lo = 2 + ACC * pass, t_hi = min(S + 1, t_lo + ACC - 1);
@@ -645,13 +646,13 @@ k_ozaki_gemm_v3(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             w_accf += clock64() - c1_; c1_ = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;");
             if (!ok) break;
-            for (int c0 = 0; c0 < TN_; c0 += 32) {
+            for (int c0 = half * 32; c0 < TN_; c0 += 64) {
                 double acc[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[j] = 0.0;
                 for (int t = t_hi; t >= t_lo; --t) {
                     uint32_t v[32];
-                    const uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t - t_lo) * TN_ + c0;
+                    const uint32_t addr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t - t_lo) * TN_ + c0;
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
                                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -664,23 +665,28 @@ k_ozaki_gemm_v3(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc[j] = fma((double)(int32_t)v[j], w, acc[j]);
                 }
-                // transpose through shared memory: lane = row -> lane = column, 256-byte row segments to global memory
+                // transpose through shared memory in two 16-column halves: lane = row -> (lane & 15) = column, (lane >> 4) = row parity;
+                // every store instruction then writes two 128-byte row segments
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = acc[j];
-                __syncwarp();
-                const double sc = scale[n0 + c0 + lane];
-                double* dst0 = C + (size_t)(m0 + warp * 32) * ldc + n0 + c0 + lane;
-                if (pass == 0) {
-#pragma unroll 8
-                    for (int r = 0; r < 32; ++r) dst0[(size_t)r * ldc] = tr[r * 33 + lane] * sc;
-                } else {                                                     // all 32 loads of the earlier partial sums in flight
-                    double old[32];
+                for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                    for (int r = 0; r < 32; ++r) old[r] = dst0[(size_t)r * ldc];
+                    for (int j = 0; j < 16; ++j) tr[lane * 17 + j] = acc[h * 16 + j];
+                    __syncwarp();
+                    const int col = lane & 15, rsub = lane >> 4;
+                    const double sc = scale[n0 + c0 + h * 16 + col];
+                    double* dst0 = C + (size_t)(m0 + quad * 32 + rsub) * ldc + n0 + c0 + h * 16 + col;
+                    if (pass == 0) {
 #pragma unroll
-                    for (int r = 0; r < 32; ++r) dst0[(size_t)r * ldc] = old[r] + tr[r * 33 + lane] * sc;
+                        for (int r2 = 0; r2 < 16; ++r2) dst0[(size_t)(2 * r2) * ldc] = tr[(2 * r2 + rsub) * 17 + col] * sc;
+                    } else {
+                        double old[16];
+#pragma unroll
+                        for (int r2 = 0; r2 < 16; ++r2) old[r2] = dst0[(size_t)(2 * r2) * ldc];
+#pragma unroll
+                        for (int r2 = 0; r2 < 16; ++r2) dst0[(size_t)(2 * r2) * ldc] = old[r2] + tr[(2 * r2 + rsub) * 17 + col] * sc;
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             mbar_arrive(smem_u32(&acc_empty));
@@ -801,7 +807,7 @@ int main(int argc, char** argv) {
     CK(cudaFuncSetAttribute(k_ozaki_gemm_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
     const CUtensorMap m3A64 = make_slice_map_sw(dAs, Mbig, K, 2, 64), m3A32 = make_slice_map_sw(dAs, Mbig, K, 2, 32);
     const CUtensorMap m3B64 = make_slice_map_sw(dBs, N, K, 2, 64, 256), m3B32 = make_slice_map_sw(dBs, N, K, 2, 32, 256);
-    const size_t smem_v3 = (size_t)2 * S * (TM + 256) * KB + 4 * 32 * 33 * 8;
+    const size_t smem_v3 = (size_t)2 * S * (TM + 256) * KB + 8 * 32 * 17 * 8;
     CK(cudaFuncSetAttribute(k_ozaki_gemm_v3<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v3));
     for (int variant = 0; variant <= 3; ++variant)
     for (int tri = 0; tri <= 1; ++tri) {
@@ -813,7 +819,7 @@ int main(int argc, char** argv) {
             if (variant == 0) k_ozaki_gemm<<<(Mbig / TM) * (N / TN), THREADS, smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
             else if (variant == 1) k_ozaki_gemm_v1<<<(Mbig / TM) * (N / TN), V1_THREADS, NSTAGE * smem>>>(dAs, dBs, Mbig, N, K, tri, expA, dexpB, dC, N, dfail);
             else if (variant == 2) k_ozaki_gemm_v2<<<(Mbig / TM) * (N / TN), V2_THREADS, smem_v2>>>(mapA, mapB, mapA8, mapB8, Mbig, N, K, tri, dscale, dC, N, dfail);
-            else k_ozaki_gemm_v3<256, 2><<<(Mbig / TM) * (N / 256), V2_THREADS, smem_v3>>>(m3A64, m3B64, m3A32, m3B32, Mbig, N, K, tri, dscale, dC, N, dfail);
+            else k_ozaki_gemm_v3<256, 2><<<(Mbig / TM) * (N / 256), V3_THREADS, smem_v3>>>(m3A64, m3B64, m3A32, m3B32, Mbig, N, K, tri, dscale, dC, N, dfail);
             CK(cudaEventRecord(e2));
             CK(cudaDeviceSynchronize());
         }
