@@ -9,8 +9,10 @@ call of each optimiser batch has a fixed shape and is replayed as a CUDA graph (
 
 The initial conditions come from botorch's `gen_batch_initial_conditions` in the reference [3P, not installed here]; its
 heuristic is restated from the published algorithm (Sobol raw samples, Boltzmann selection with eta = 2 on the
-standardised acquisition values, the best raw sample always kept).  Constraints, fixed features, `sequential=True` and
-one-shot acquisition functions are not built (the reference's scripts never pass them, scripts/black_box_opt.py:131-143).
+standardised acquisition values, the best raw sample always kept).  `sequential=True` runs the reference's greedy loop (q
+single-point problems with the earlier points pending; the SGLD settings are passed on, where the reference falls back to
+its defaults).  Constraints, fixed features and one-shot acquisition functions are not built (the reference's scripts never
+pass them, scripts/black_box_opt.py:131-143).
 """
 from __future__ import annotations
 
@@ -111,7 +113,23 @@ def optimize_acqf_sgld(
     if inequality_constraints or equality_constraints or nonlinear_inequality_constraints or fixed_features:
         raise NotImplementedError("constraints / fixed features are not built (unused by the reference's scripts)")
     if sequential and q > 1:
-        raise NotImplementedError("sequential=True is not built (the reference's scripts optimise jointly)")
+        # sequential greedy: q single-point problems, each with the points found so far as pending (optimize.py:113-149)
+        if not return_best_only:
+            raise NotImplementedError("`return_best_only=False` only supported for joint optimization.")
+        candidate_list, acq_value_list = [], []
+        base_X_pending = acq_function.X_pending
+        for _ in range(q):
+            candidate, acq_value = optimize_acqf_sgld(
+                acq_function, bounds, 1, num_restarts, raw_samples=raw_samples, options=options,
+                post_processing_func=post_processing_func, batch_initial_conditions=None, return_best_only=True,
+                sequential=False, warmup_steps=warmup_steps, sgld_steps=sgld_steps, lr=lr, temperature=temperature)
+            candidate_list.append(candidate)
+            acq_value_list.append(acq_value)
+            candidates = torch.cat(candidate_list, dim=-2)
+            acq_function.set_X_pending(torch.cat([base_X_pending, candidates], dim=-2) if base_X_pending is not None
+                                       else candidates)
+        acq_function.set_X_pending(base_X_pending)             # reset to the previous X_pending state
+        return candidates, torch.stack(acq_value_list, dim=-1)
     if not bounds.is_cuda:
         raise RuntimeError("optimize_acqf_sgld runs on the device: `bounds` must be a CUDA tensor")
     options = options or {}

@@ -218,3 +218,20 @@ def test_graph_replay_loop_matches_the_direct_loop_bitwise():
                                         options=dict(callback=est.optimize_callback, cuda_graph=use_graph))
         res.append((traj.clone(), vals.clone(), est._train["target"].clone()))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+
+
+def test_sequential_greedy_mode_uses_pending_points():
+    """optimize_acqf_sgld(sequential=True): q single-point problems with the earlier picks as X_pending (optimize.py:113-149)."""
+    from conformal_bayesopt_b200.acquisitions import qConformalUpperConfidenceBound
+    from conformal_bayesopt_b200.optim import optimize_acqf_sgld
+    state, Xtr = _problem(seed=6)
+    d = Xtr.shape[1]
+    acq = qConformalUpperConfidenceBound(alpha=0.2, temp=3e-2, grid_res=32, max_grid_refinements=0, ratio_estimator=None,
+                                         model=state, beta=0.2)
+    bounds = torch.stack([torch.zeros(d), torch.ones(d)]).to(DEV, torch.float64)
+    torch.manual_seed(1)
+    cand, vals = optimize_acqf_sgld(acq, bounds, q=3, num_restarts=4, raw_samples=32, sequential=True, sgld_steps=12,
+                                    warmup_steps=2, lr=1e-2, temperature=4e-3, options=dict(seed=5))
+    assert cand.shape == (3, d) and vals.shape == (3,)
+    assert acq.X_pending is None                                   # restored
+    assert bool(((cand >= 0) & (cand <= 1)).all()) and bool(torch.isfinite(vals).all())
