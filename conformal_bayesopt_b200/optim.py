@@ -189,3 +189,33 @@ def optimize_acqf_sgld(
     if post_processing_func is not None:
         batch_candidates = post_processing_func(batch_candidates)
     return batch_candidates, batch_acq_values
+
+
+def optimize_acqf_sgld_list(acq_function_list, bounds: torch.Tensor, num_restarts: int, raw_samples: Optional[int] = None,
+                            options: Optional[Dict] = None, inequality_constraints=None, equality_constraints=None,
+                            fixed_features=None, post_processing_func=None, return_best_only: bool = True, **sgld_kwargs):
+    """One candidate per acquisition function, optimised in sequence with the earlier candidates pending (sequential greedy;
+    conformalbo/optim/optimize.py:286-357).  The ratio estimator's `optimize_callback` is installed as the SGLD callback when
+    the acquisition function has one (optimize.py:337-338).  `sgld_kwargs` (sgld_steps, lr, temperature, warmup_steps) are
+    passed on; the reference uses its defaults here."""
+    if not acq_function_list:
+        raise ValueError("acq_function_list must be non-empty.")
+    candidate_list, acq_value_list = [], []
+    candidates = torch.tensor([], device=bounds.device, dtype=bounds.dtype)
+    base_X_pending = acq_function_list[0].X_pending
+    for acq_function in acq_function_list:
+        if candidate_list:
+            acq_function.set_X_pending(torch.cat([base_X_pending, candidates], dim=-2) if base_X_pending is not None
+                                       else candidates)
+        opts = dict(options or {})
+        if hasattr(getattr(acq_function, "ratio_estimator", None), "optimize_callback"):
+            opts["callback"] = acq_function.ratio_estimator.optimize_callback
+        candidate, acq_value = optimize_acqf_sgld(
+            acq_function, bounds, 1, num_restarts, raw_samples=raw_samples, options=opts,
+            inequality_constraints=inequality_constraints, equality_constraints=equality_constraints,
+            fixed_features=fixed_features, post_processing_func=post_processing_func, return_best_only=True,
+            sequential=False, **sgld_kwargs)
+        candidate_list.append(candidate)
+        acq_value_list.append(acq_value)
+        candidates = torch.cat(candidate_list, dim=-2)
+    return candidates, torch.stack(acq_value_list, dim=-1)

@@ -235,3 +235,25 @@ def test_sequential_greedy_mode_uses_pending_points():
     assert cand.shape == (3, d) and vals.shape == (3,)
     assert acq.X_pending is None                                   # restored
     assert bool(((cand >= 0) & (cand <= 1)).all()) and bool(torch.isfinite(vals).all())
+
+
+def test_optimize_acqf_sgld_list_chains_pending_points_and_trains_the_estimator():
+    from conformal_bayesopt_b200.acquisitions import qConformalExpectedImprovement, qConformalUpperConfidenceBound
+    from conformal_bayesopt_b200.optim import optimize_acqf_sgld_list
+    from conformal_bayesopt_b200.ratio_estimation import RatioEstimator
+    state, Xtr = _problem(seed=8)
+    d = Xtr.shape[1]
+    est = RatioEstimator(in_size=d, device=DEV, dtype=torch.float64, lr=5e-3, ema_weight=2e-2, weight_decay=5e-6)
+    est.set_neg_samples(Xtr[:16].to(DEV))
+    kw = dict(alpha=0.2, temp=3e-2, grid_res=32, max_grid_refinements=0, ratio_estimator=est, randomized=True, model=state)
+    acqs = [qConformalUpperConfidenceBound(beta=0.2, **kw), qConformalExpectedImprovement(best_f=0.4, **kw)]
+    bounds = torch.stack([torch.zeros(d), torch.ones(d)]).to(DEV, torch.float64)
+    torch.manual_seed(2)
+    np.random.seed(2)
+    cand, vals = optimize_acqf_sgld_list(acqs, bounds, num_restarts=4, raw_samples=32, options=dict(seed=7), sgld_steps=16,
+                                         warmup_steps=4, lr=1e-2, temperature=4e-3)
+    assert cand.shape == (2, d) and vals.shape == (2,)
+    assert acqs[1].X_pending is not None and torch.equal(acqs[1].X_pending, cand[:1])      # second function saw the first pick
+    assert est._train is not None and est._train["step"] > 0                               # the callback was installed
+    with pytest.raises(ValueError):
+        optimize_acqf_sgld_list([], bounds, num_restarts=4, raw_samples=32)
