@@ -14,6 +14,12 @@
  *                              and _conformal_integration (acquisitions.py:225-248).
  *   cbo_conf_mask_to_bounds_f64  conf_mask_to_bounds (helpers.py:15-91).
  *   cbo_ratio_forward_f64      RatioEstimator.forward (ratio_estimation.py:97-99).
+ *   cbo_conformal_acq_grad_f64 the same path under autograd in optimize_acqf_sgld (conformalbo/optim/optimize.py:224-235).
+ *   cbo_cehvi_integrate_f64    qConformalExpectedHypervolumeImprovement (conformalbo/mobo_acquisitions.py:24-45).
+ *   cbo_model_build_f64 / cbo_model_append_f64   the model refit before the path (conformalbo/utils.py:382-390) and the
+ *                              observations a BO round adds (scripts/black_box_opt.py:154-155).
+ *   cbo_ratio_train_step_f64   RatioEstimator.optimize_callback (ratio_estimation.py:110-144).
+ *   cbo_sgld_update_f64        the SGLD / SGHMC step of optimize_acqf_sgld (optim/sgld.py:9-47, optim/optimize.py:224-235).
  *
  * Conventions
  *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host;
