@@ -257,3 +257,43 @@ def test_optimize_acqf_sgld_list_chains_pending_points_and_trains_the_estimator(
     assert est._train is not None and est._train["step"] > 0                               # the callback was installed
     with pytest.raises(ValueError):
         optimize_acqf_sgld_list([], bounds, num_restarts=4, raw_samples=32)
+
+
+@pytest.mark.parametrize("d,n_neg,n_pos", [(1, 3, 3), (2, 5, 9), (7, 64, 64), (33, 65, 1), (64, 130, 70)])
+def test_train_step_kernel_edge_shapes_match_the_oracle(d, n_neg, n_pos):
+    """Odd input widths (incl. the class default in_size = 1 and the kernel's maximum 64), ragged tiles, unequal class counts,
+    several steps with Adam state carried over -- against oracle/training.py."""
+    from conformal_bayesopt_b200 import ops
+    g = torch.Generator().manual_seed(d * 1000 + n_neg)
+    P = ops.ratio_num_params(d)
+    th0 = torch.randn(P, generator=g, dtype=torch.float64) * 0.3
+    neg = torch.rand(n_neg, d, generator=g, dtype=torch.float64)
+    pool = 0.5 + 0.3 * torch.randn(2 * n_pos + 3, d, generator=g, dtype=torch.float64)
+    idx = torch.randperm(pool.shape[0], generator=g)[:n_pos]
+    th, m, v, tg = th0.to(DEV).clone(), torch.zeros(P, dtype=torch.float64, device=DEV), torch.zeros(P, dtype=torch.float64, device=DEV), \
+        torch.zeros(P, dtype=torch.float64, device=DEV)
+    rt, rm, rv, rtg = th0.numpy().copy(), np.zeros(P), np.zeros(P), np.zeros(P)
+    loss = torch.zeros((), dtype=torch.float64, device=DEV)
+    for step in (1, 2, 3):
+        ops.ratio_train_step(th, m, v, tg, x_neg=neg.to(DEV), x_pos=pool.to(DEV), pos_idx=idx.to(DEV), n_pos=n_pos, step=step,
+                             lr=5e-3, weight_decay=1e-4, ema_weight=1e-2, loss=loss)
+        rt, rm, rv, rtg, rl = T.ratio_train_step(rt, rm, rv, rtg, step, neg.numpy(), pool.numpy()[idx.numpy()], d, 5e-3, 1e-4, 1e-2)
+        assert abs(loss.item() - rl) < 1e-13
+        np.testing.assert_allclose(th.cpu().numpy(), rt, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(tg.cpu().numpy(), rtg, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(m.cpu().numpy(), rm, rtol=1e-9, atol=1e-15)
+
+
+def test_train_step_rejects_unsupported_shapes():
+    from conformal_bayesopt_b200 import _lib
+    lib = _lib.load()
+    z = torch.zeros(8, dtype=torch.float64, device=DEV)
+    st = lib.cbo_ratio_train_step_f64(65, 64, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, z.data_ptr(),
+                                      None, 1, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1e-2, None, z.data_ptr(), 64, None)
+    assert st == 2                                                        # CBO_ERR_UNSUPPORTED: d > 64
+    st = lib.cbo_ratio_train_step_f64(2, 32, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, z.data_ptr(),
+                                      None, 1, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1e-2, None, z.data_ptr(), 64, None)
+    assert st == 2                                                        # hidden width other than 64
+    st = lib.cbo_ratio_train_step_f64(2, 64, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, z.data_ptr(),
+                                      None, 1, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1e-2, None, z.data_ptr(), 64, None)
+    assert st == 1                                                        # CBO_ERR_INVALID_ARG: step is 1-based
