@@ -71,9 +71,10 @@ def load():
     if path == lib_path() and _build.is_stale():
         try:
             _build.build()
-        except Exception as e:  # no nvcc on this host: use the shipped .so if there is one
+        except _build.NvccNotFound as e:    # no compiler on this host: the shipped .so is used -- if there is one
             if not os.path.exists(path):
                 raise CboError(f"libcbo.so is missing and could not be built: {e}") from e
+        # any other failure (a compile error in an edited source) propagates: never run stale kernels silently
     lib = C.CDLL(path)
     lib.cbo_version.restype = C.c_int
     lib.cbo_status_str.restype = C.c_char_p

@@ -233,6 +233,7 @@ class qConformalNoisyExpectedImprovement(ConformalAcquisition):
         return self.X_baseline.reshape(-1, self.X_baseline.shape[-1]).shape[0] + q
 
     def _acq_params(self):
-        if self._baseline is None:
-            self._baseline = ops.NeiBaseline.build(as_state(self.model), self.X_baseline)
-        return dict(kind="nei", nei_baseline=self._baseline)
+        state = as_state(self.model)
+        if self._baseline is None or self._baseline[0] is not state:        # rebuilt whenever the model state changes
+            self._baseline = (state, ops.NeiBaseline.build(state, self.X_baseline))
+        return dict(kind="nei", nei_baseline=self._baseline[1])

@@ -9,10 +9,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "cbo_api.cu")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libcbo.so")
+# -cudart shared: the library resolves the CUDA runtime from the process (torch has loaded libcudart.so.12 already; the
+# rpath covers a bare ctypes load) instead of embedding a static copy of it.
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-    "--shared", "-Xcompiler", "-fPIC",
+    "--shared", "-Xcompiler", "-fPIC", "-cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64",
 ]
+
+
+class NvccNotFound(RuntimeError):
+    """No CUDA compiler on this host (the only build failure `_lib.load()` tolerates, and only if a built .so exists)."""
 
 
 def sources():
@@ -33,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
-        raise RuntimeError("nvcc not found: cannot build libcbo.so")
+        raise NvccNotFound("nvcc not found: cannot build libcbo.so")
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)

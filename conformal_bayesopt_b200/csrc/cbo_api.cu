@@ -187,15 +187,16 @@ int validate(const cbo_gp_f64* gp, const cbo_params* p, int64_t b) {
     return CBO_OK;
 }
 
-int g_num_sms = 0;
+std::atomic<int> g_num_sms[cbo::kMaxDevices];      // per device (zero-initialised)
 int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    const int dev = cbo::current_device_slot();
+    if (dev < 0) return 148;
+    int n = g_num_sms[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        g_num_sms[dev].store(n, std::memory_order_relaxed);
     }
-    return g_num_sms;
+    return n;
 }
 
 template <bool SOFT>
@@ -214,12 +215,8 @@ cudaError_t launch_score(const cbo::ScoreArgs& a_in, cudaStream_t st) {
     if (ngroups < 1) return cudaErrorInvalidConfiguration;
     a.wpg_log2 = wl;
     size_t smem = cbo::score_smem_bytes(a.Np, a.G, ngroups);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(cbo::k_score<SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static cbo::SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(cbo::k_score<SOFT>, smem); e != cudaSuccess) return e;
     int grid = (a.n_cand + ngroups - 1) / ngroups;     // persistent: one CTA per SM, one warp group per candidate in flight
     if (grid > num_sms()) grid = num_sms();
     cbo::k_score<SOFT><<<grid, ngroups * (32 << wl), smem, st>>>(a);
@@ -242,12 +239,8 @@ cudaError_t launch_score_bwd(const cbo::ScoreBwdArgs& a_in, cudaStream_t st) {
     if (ngroups < 1) return cudaErrorInvalidConfiguration;
     a.f.wpg_log2 = wl;
     size_t smem = cbo::score_bwd_smem_bytes(a.f.Np, a.f.G, ngroups);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(cbo::k_score_bwd<SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static cbo::SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(cbo::k_score_bwd<SOFT>, smem); e != cudaSuccess) return e;
     int grid = (a.f.n_cand + ngroups - 1) / ngroups;
     if (grid > num_sms()) grid = num_sms();
     cbo::k_score_bwd<SOFT><<<grid, ngroups * (32 << wl), smem, st>>>(a);
@@ -259,8 +252,7 @@ cudaError_t launch_score_q_bwd_t(const cbo::ScoreQBwdArgs& a, cudaStream_t st) {
     size_t smem = cbo::score_q_bwd_smem_bytes(a.f.base.Np, a.f.base.G, Q);
     // a handful of joint batches (the SGLD loop): one thread-block cluster of 8 CTAs per joint batch (soft path)
     if (SOFT && a.f.base.n_cand * cbo::SQB_CLUSTER <= num_sms()) {
-        static size_t configured_cl = 0;
-        static int max_clusters = 0;         // clusters of 8 that are resident at once (GPC granularity), per smem size
+        static cbo::SmemOptIn optin_cl;      // aux: clusters of 8 that are resident at once (GPC granularity), per smem size
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(a.f.base.n_cand * cbo::SQB_CLUSTER);
@@ -272,24 +264,22 @@ cudaError_t launch_score_q_bwd_t(const cbo::ScoreQBwdArgs& a, cudaStream_t st) {
         attr.val.clusterDim.x = cbo::SQB_CLUSTER; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
-        if (smem > configured_cl) {
-            cudaError_t e = cudaFuncSetAttribute(cbo::k_score_q_bwd<Q, SOFT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured_cl = smem;
-            if (cudaOccupancyMaxActiveClusters(&max_clusters, cbo::k_score_q_bwd<Q, SOFT, true>, &cfg) != cudaSuccess) {
+        bool fresh = false;
+        if (cudaError_t e = optin_cl.ensure(cbo::k_score_q_bwd<Q, SOFT, true>, smem, &fresh); e != cudaSuccess) return e;
+        const int dev = cbo::current_device_slot() < 0 ? 0 : cbo::current_device_slot();
+        if (fresh) {
+            int mc = 0;
+            if (cudaOccupancyMaxActiveClusters(&mc, cbo::k_score_q_bwd<Q, SOFT, true>, &cfg) != cudaSuccess) {
                 cudaGetLastError();
-                max_clusters = 0;
+                mc = 0;
             }
+            optin_cl.aux[dev].store(mc, std::memory_order_release);
         }
-        if (a.f.base.n_cand <= max_clusters)   // one wave of clusters; otherwise one CTA per joint batch is as fast
+        if (a.f.base.n_cand <= optin_cl.aux[dev].load(std::memory_order_acquire))   // one wave of clusters; otherwise one CTA per joint batch is as fast
             return cudaLaunchKernelEx(&cfg, cbo::k_score_q_bwd<Q, SOFT, true>, a);
     }
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(cbo::k_score_q_bwd<Q, SOFT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static cbo::SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(cbo::k_score_q_bwd<Q, SOFT, false>, smem); e != cudaSuccess) return e;
     int grid = a.f.base.n_cand < 2 * num_sms() ? a.f.base.n_cand : 2 * num_sms();
     cbo::k_score_q_bwd<Q, SOFT, false><<<grid, cbo::SQ_THREADS, smem, st>>>(a);
     return cudaGetLastError();
@@ -307,12 +297,8 @@ cudaError_t launch_score_q_bwd(const cbo::ScoreQBwdArgs& a, int q, bool soft, cu
 template <int Q, bool SOFT>
 cudaError_t launch_score_q_t(const cbo::ScoreQArgs& a, cudaStream_t st) {
     size_t smem = cbo::score_q_smem_bytes(a.base.Np, a.base.G, Q);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(cbo::k_score_q<Q, SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static cbo::SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(cbo::k_score_q<Q, SOFT>, smem); e != cudaSuccess) return e;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
     int grid = a.base.n_cand < per_sm * num_sms() ? a.base.n_cand : per_sm * num_sms();
@@ -411,11 +397,8 @@ int cbo_ratio_train_step_f64(int64_t d, int64_t hidden, double* theta, double* a
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int tiles = int((n_rows + cbo::RT_ROWS - 1) / cbo::RT_ROWS);
     const size_t smem = cbo::ratio_train_smem_bytes((int)d);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CBO_CUDA(cudaFuncSetAttribute(cbo::k_ratio_train_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static cbo::SmemOptIn optin;
+    CBO_CUDA(optin.ensure(cbo::k_ratio_train_grad, smem));
     double* partial = static_cast<double*>(workspace);
     cbo::k_ratio_train_grad<<<tiles, cbo::RT_THREADS, smem, st>>>(theta, (int)d, x_neg, (int)n_neg, x_pos, pos_idx,
                                                                   (int)n_pos, partial);
@@ -742,11 +725,8 @@ int cbo_cehvi_integrate_f64(int64_t m, int64_t b, int64_t G, int64_t S, const do
     }
     a.eps_mc = eps_mc; a.cell_lower = cell_lower; a.cell_upper = cell_upper; a.acq = acq;
     size_t smem = size_t(2 * n_cells * m) * sizeof(double);
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        CBO_CUDA(cudaFuncSetAttribute(cbo::k_ehvi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static cbo::SmemOptIn optin;
+    CBO_CUDA(optin.ensure(cbo::k_ehvi, smem));
     cbo::k_ehvi<<<(int)((b + 7) / 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
     CBO_CUDA(cudaGetLastError());
     return CBO_OK;

@@ -3,7 +3,38 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace cbo {
+
+// ---- host: per-DEVICE state (one process may drive several GPUs from several threads; cbo.h promises re-entrancy) ------
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+    return dev;
+}
+// Opt-in to more than 48 KB of dynamic shared memory: cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device),
+// so the "already configured" size is cached per device.  Concurrent callers may both set the attribute: harmless.
+struct SmemOptIn {
+    std::atomic<size_t> done[kMaxDevices];
+    std::atomic<int> aux[kMaxDevices];          // optional per-device value computed together with the opt-in (occupancy)
+    template <typename F>
+    cudaError_t ensure(F* fn, size_t smem, bool* fresh = nullptr) {
+        const int dev = current_device_slot();
+        if (fresh) *fresh = false;
+        if (dev >= 0 && smem <= done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+        if (dev >= 0 && smem <= 48 * 1024 && done[dev].load(std::memory_order_acquire) == 0 && !fresh) {
+            done[dev].store(48 * 1024, std::memory_order_release);     // the default limit needs no opt-in
+            return cudaSuccess;
+        }
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (fresh) *fresh = true;
+        if (dev >= 0) done[dev].store(smem, std::memory_order_release);
+        return cudaSuccess;
+    }
+};
 
 constexpr int kWarp = 32;
 constexpr double kLog2Pi = 1.8378770664093453;   // log(2*pi)

@@ -157,11 +157,8 @@ inline cudaError_t model_build(const double* X, const double* y, int N, int d, c
                                 nullptr, 0, w.A, nullptr, nullptr, num_sms, s));
     k_fix_diag<<<(Np + 255) / 256, 256, 0, s>>>(w.A, N, Np, outputscale + noise);
     const size_t potrf_smem = sizeof(double) * (MB_NB * MB_LDS + MB_NB);
-    static bool configured = false;
-    if (!configured) {
-        MB_CHECK(cudaFuncSetAttribute(k_potrf_trtri_128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    MB_CHECK(optin.ensure(k_potrf_trtri_128, potrf_smem));
     // ---- left-looking blocked Cholesky, in place in A ---------------------------------------------------------------
     for (int j = 0; j < nb; ++j) {
         double* Ajj = w.A + (int64_t(j) * MB_NB) * Np + int64_t(j) * MB_NB;

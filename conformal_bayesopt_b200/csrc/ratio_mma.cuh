@@ -225,12 +225,8 @@ inline cudaError_t launch_ratio_mlp(const double* x, int n, int d, int H, const 
                                     const double* W2, const double* b2, const double* W3, const double* b3,
                                     double clamp_min, double* out, int num_sms, cudaStream_t st) {
     const size_t smem = ratio_mma_smem_bytes(d, false);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_ratio_mlp_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(k_ratio_mlp_mma, smem); e != cudaSuccess) return e;
     int grid = ((n + 15) / 16 + RM_WARPS - 1) / RM_WARPS;
     if (grid > 2 * num_sms) grid = 2 * num_sms;
     k_ratio_mlp_mma<<<grid, RM_WARPS * 32, smem, st>>>(x, n, d, H, W1, b1, W2, b2, W3, b3, clamp_min, out);
@@ -242,12 +238,8 @@ inline cudaError_t launch_ratio_mlp_bwd(const double* x, int n, int d, int H, co
                                         double clamp_min, const double* adj, int adj_stride, int adj_off, double* dX,
                                         int num_sms, cudaStream_t st) {
     const size_t smem = ratio_mma_smem_bytes(d, true);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_ratio_mlp_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(k_ratio_mlp_mma_bwd, smem); e != cudaSuccess) return e;
     int grid = ((n + 7) / 8 + RM_WARPS - 1) / RM_WARPS;
     if (grid > 2 * num_sms) grid = 2 * num_sms;
     k_ratio_mlp_mma_bwd<<<grid, RM_WARPS * 32, smem, st>>>(x, n, d, H, W1, b1, W2, b2, W3, b3, clamp_min, adj, adj_stride, adj_off, dX);

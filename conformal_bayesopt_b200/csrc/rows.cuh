@@ -235,12 +235,8 @@ inline cudaError_t launch_kernel_rows_t(const double* Xq, int n, const double* X
                                         const double* T, int Sp, double* U, double* mu, double* ut, int num_sms,
                                         cudaStream_t st) {
     const size_t smem = rows_smem_bytes(Np, d, (T && ut) ? Sp : 0, STAGE);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_kernel_rows<STAGE, NSP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(k_kernel_rows<STAGE, NSP>, smem); e != cudaSuccess) return e;
     const int groups = (n + ROWS_CPW - 1) / ROWS_CPW;
     int grid = (groups + ROWS_WARPS - 1) / ROWS_WARPS;
     if (grid > num_sms) grid = num_sms;                              // persistent: one 16-warp CTA per SM

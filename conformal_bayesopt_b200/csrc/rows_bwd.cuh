@@ -119,12 +119,8 @@ inline cudaError_t launch_rows_bwd_t(const double* Xq, int n, const double* XsT,
                                      double outputscale, const double* alpha, const double* Aw,
                                      const double* W, const double* adj, double* dX, int num_sms, cudaStream_t st) {
     const size_t smem = rows_smem_bytes(Np, d, 0, STAGE);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_rows_bwd<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(k_rows_bwd<STAGE>, smem); e != cudaSuccess) return e;
     const int groups = (n + ROWS_CPW - 1) / ROWS_CPW;
     int grid = (groups + ROWS_WARPS - 1) / ROWS_WARPS;
     if (grid > num_sms) grid = num_sms;

@@ -17,15 +17,30 @@ from .model_state import GPModelState
 from .sampling import IIDNormalSampler
 
 
+def _model_fingerprint(model):
+    """(data_ptr, version, shape) of every tensor the extracted state depends on: training data and hyper-parameters.
+    An in-place refit, `load_state_dict` (reference utils.py:149) or `set_train_data` changes it."""
+    tensors = [model.train_inputs[0], model.train_targets, model.covar_module.base_kernel.lengthscale,
+               model.covar_module.outputscale, model.likelihood.noise, model.mean_module.constant]
+    fp = []
+    for t in tensors:
+        t = torch.as_tensor(t)
+        fp.append((t.data_ptr(), t._version, tuple(t.shape)))
+    return tuple(fp)
+
+
 def as_state(model) -> GPModelState:
+    """The kernels' plain-tensor view of `model`.  A BoTorch model is extracted once and the state cached on it together
+    with a fingerprint of its data / hyper-parameters; the cache is rebuilt when the fingerprint changes."""
     if isinstance(model, GPModelState):
         return model
+    fp = _model_fingerprint(model)
     cached = getattr(model, "_cbo_state", None)
-    if cached is not None:
-        return cached
+    if cached is not None and cached[0] == fp:
+        return cached[1]
     state = GPModelState.from_botorch(model)
     try:
-        model._cbo_state = state
+        model._cbo_state = (fp, state)
     except Exception:
         pass
     return state

@@ -96,6 +96,10 @@ class GPModelState:
     def from_botorch(cls, model, output_index: int = 0) -> "GPModelState":
         """Duck-typed extraction from a BoTorch 0.7 `SingleTaskGP`.  botorch is not needed
         to import this module; the attributes below are the ones the reference itself reads."""
+        for attr in ("input_transform", "outcome_transform"):
+            if getattr(model, attr, None) is not None:
+                raise NotImplementedError(f"the model carries an {attr}: the kernels take the GP in its own (transformed) "
+                                          "space only -- build the GPModelState from the transformed data explicitly")
         X = model.train_inputs[0]
         y = model.train_targets
         ls = model.covar_module.base_kernel.lengthscale

@@ -83,15 +83,24 @@ class NeiBaseline:
 
     @classmethod
     def build(cls, state: GPModelState, X_baseline: torch.Tensor) -> "NeiBaseline":
-        from .model_state import matern52
+        """All of it on the library's own kernels (no cuBLAS / torch.linalg on the product path): k(X_b, X) and the posterior
+        mean by cbo_kernel_rows_f64, V_b = k(X_b, X) L^-T and V_b V_b^T by cbo_gemm_tn_f64, k(X_b, X_b) by a second
+        kernel-row call against a model state whose "training inputs" are the baseline points."""
         Xb = X_baseline.detach().to(state.device, torch.float64).reshape(-1, state.d).contiguous()
-        Kb = matern52(Xb, state.X, state.lengthscale, state.outputscale)
-        Vb = state.linv[:state.N, :state.N] @ Kb.T                         # L^-1 k(X, X_b)
-        Kbb = matern52(Xb, Xb, state.lengthscale, state.outputscale)
+        nb = Xb.shape[0]
+        KbX, mub = kernel_rows(state, Xb)                                   # (nb, Np) zero-padded, mean + k alpha
+        Vb = gemm_tn(KbX, state.linv, tri=1)                                # (nb, Np): rows L^-1 k(X, x_b)
+        nbp = (nb + 127) // 128 * 128
+        Vpad = torch.zeros(nbp, state.Np, dtype=torch.float64, device=state.device)
+        Vpad[:nb] = Vb
+        VVt = gemm_tn(Vb, Vpad, tri=0)[:, :nb]                              # V_b V_b^T
+        zeros = torch.zeros(nbp, dtype=torch.float64, device=state.device)
+        pseudo = GPModelState(X=Xb, y=mub, mean=0.0, lengthscale=state.lengthscale, outputscale=state.outputscale,
+                              noise=state.noise, alpha=zeros, linv=zeros, linv_t=zeros,       # factors: never read by kernel_rows
+                              inv_lengthscale=state.inv_lengthscale)
+        Kbb = kernel_rows(pseudo, Xb)[0][:, :nb]
         Kbb.diagonal().fill_(state.outputscale)
-        KbX = torch.zeros(Xb.shape[0], state.Np, dtype=torch.float64, device=state.device)
-        KbX[:, :state.N] = Kb
-        return cls(Xb, KbX, (Kbb - Vb.T @ Vb).contiguous(), (state.mean + Kb @ state.alpha[:state.N]).contiguous())
+        return cls(Xb, KbX, (Kbb - VVt).contiguous(), mub.contiguous())
 
     def c_struct(self) -> "_lib.NeiBaselineF64":
         return _lib.NeiBaselineF64(self.Xb.shape[0], self.Xb.data_ptr(), self.KbX.data_ptr(), self.Sbb.data_ptr(),
@@ -156,11 +165,17 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
         raise _lib.CboError(f"eps_grid must hold G*q or b*G*q values, got {tuple(eps_grid.shape)}")
     reducer = param_kw.pop("refine_reduce", None)            # callable(list of 4 floats) -> list of 4 floats, or None
     reduce_c = None
+    hook_error = []
     if reducer is not None:
         def _hook(ptr, _ctx, _f=reducer):
-            vals = _f([ptr[0], ptr[1], ptr[2], ptr[3]])
-            for k in range(4):
-                ptr[k] = float(vals[k])
+            # ctypes swallows exceptions raised inside a callback: keep the first one and re-raise it after the call
+            try:
+                vals = _f([ptr[0], ptr[1], ptr[2], ptr[3]])
+                for k in range(4):
+                    ptr[k] = float(vals[k])
+            except BaseException as e:  # noqa: BLE001
+                if not hook_error:
+                    hook_error.append(e)
         reduce_c = _lib.REFINE_REDUCE_FN(_hook)              # kept alive until the call returns
     baseline = param_kw.pop("nei_baseline", None)
     nei_c = baseline.c_struct() if baseline is not None else None          # kept alive until the call returns
@@ -193,11 +208,15 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
         st = lib.cbo_conformal_acq_grad_f64(C.byref(gp_c), ratio_p, C.byref(params), Xq.data_ptr(), b, eps_grid.data_ptr(),
                                             z.data_ptr(), eps_mc.data_ptr(), _ptr(u_rand), C.byref(cout), dX.data_ptr(),
                                             ws_ptr, ws.numel() - 256, chunk, cs)
+        if hook_error:
+            raise hook_error[0]
         _lib.check(st, "cbo_conformal_acq_grad_f64")
     else:
         st = lib.cbo_conformal_acq_f64(C.byref(gp_c), ratio_p, C.byref(params), Xq.data_ptr(), b, eps_grid.data_ptr(),
                                        z.data_ptr(), eps_mc.data_ptr(), _ptr(u_rand), C.byref(cout), ws_ptr,
                                        ws.numel() - 256, chunk, cs)
+        if hook_error:
+            raise hook_error[0]
         _lib.check(st, "cbo_conformal_acq_f64")
     LAUNCH_COUNT += count_launches(state, b, params, ratio is not None, chunk, grad=want_grad, extra_outputs=len(outputs) > 0)
     if q == 1:   # squeeze the q axis (the q = 1 layout of round-1 callers)

@@ -116,10 +116,9 @@ class RatioEstimator(nn.Module):
         return self._weights_cache[1]
 
     def forward(self, inputs: torch.Tensor) -> torch.Tensor:
-        if inputs.is_cuda:
-            return ops.ratio_forward(self.device_weights(inputs.device), inputs).to(inputs.dtype)
-        _p = self._target_network(inputs).squeeze(-1).sigmoid()     # CPU tensors: plain torch, not on the GPU hot path
-        return _p.clamp_max(1 - 1e-6) / (1 - _p).clamp_min(1e-6)
+        if not inputs.is_cuda:        # like every other entry point: no CPU path, never a silent torch fallback
+            raise _lib.CboError("libcbo has no CPU path: RatioEstimator.forward needs CUDA inputs")
+        return ops.ratio_forward(self.device_weights(inputs.device), inputs).to(inputs.dtype)
 
     def update_target_network(self):
         with torch.no_grad():

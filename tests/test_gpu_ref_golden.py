@@ -1,0 +1,148 @@
+"""GPU: the CUDA path (C ABI and the drop-in classes) against goldens produced by EXECUTING the reference's own
+conformalbo/helpers.py and conformalbo/acquisitions.py (oracle/make_golden_path.py; reference source unmodified, only
+the gpytorch/botorch exact-GP algebra comes from the stand-ins in oracle/_shim).
+
+North-star tolerances: acquisition values, grid, band endpoints 1e-6 relative; soft masks 1e-6 absolute; hard masks and
+the selected-candidate (arg-max) index identical."""
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-6
+DEV = "cuda:0"
+
+
+def _cases(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def _state(p):
+    from conformal_bayesopt_b200 import GPModelState
+    return GPModelState.fit_fixed(p["X"], p["y"], float(torch.as_tensor(p["mean"]).reshape(-1)[0]), p["lengthscale"],
+                                  float(torch.as_tensor(p["outputscale"]).reshape(-1)[0]),
+                                  float(torch.as_tensor(p["noise"]).reshape(-1)[0]), device=DEV)
+
+
+def _ratio(c):
+    from conformal_bayesopt_b200 import ops
+    return ops.RatioWeights(*[w.to(DEV) for w in c["ratio_weights"]]) if c["ratio"] else None
+
+
+def _check(c, acq, out):
+    want = c["out"]
+    b, G, q = c["b"], c["G"], c["q"] + c["x_pending"]
+    acq = acq.cpu()
+    assert torch.allclose(acq, want["acq"], rtol=RTOL, atol=1e-9), float((acq - want["acq"]).abs().max())
+    assert int(acq.argmax()) == want["argmax"]                       # selected-candidate index (utils.py:283)
+    o = {k: v.cpu().reshape(b, G, q) if k in ("target_grid", "conf_pred_mask") else v.cpu() for k, v in out.items()}
+    assert torch.allclose(o["target_grid"], want["target_grid"][..., 0], rtol=RTOL, atol=1e-9)
+    assert torch.allclose(o["grid_logp"].reshape(b, G), want["grid_logp"], rtol=RTOL, atol=1e-9)
+    wm = want["conf_pred_mask"][..., 0]
+    if c["temp"] > 0:
+        assert torch.allclose(o["conf_pred_mask"], wm, rtol=0, atol=1e-6), float((o["conf_pred_mask"] - wm).abs().max())
+    else:
+        assert torch.equal(o["conf_pred_mask"], wm)
+    assert torch.allclose(o["ood_mask"].reshape(b, 1, q).expand(b, G, q), want["ood_mask"][..., 0], rtol=RTOL, atol=1e-12)
+
+
+def _call_abi(c):
+    from conformal_bayesopt_b200 import ops
+    st = _state(c["problem"])
+    Xq = c["Xq"] if c["X_pending"] is None else torch.cat([c["Xq"], c["X_pending"].expand(c["b"], -1, -1)], dim=1)
+    kw = dict(kind=c["kind"], alpha=c["alpha"], temp=c["temp"], grid_res=c["G"], max_grid_refinements=c["refine"],
+              randomized=c["randomized"], optimistic=c["optimistic"], beta_prime=math.sqrt(c["beta"] * math.pi / 2),
+              best_f=c["best_f"])
+    if c["kind"] == "nei":
+        kw["nei_baseline"] = ops.NeiBaseline.build(st, c["X_baseline"].to(DEV))
+    out = ops.conformal_acq(st, Xq.to(DEV), eps_grid=c["eps_grid"].to(DEV), z=c["z"].to(DEV), eps_mc=c["eps_mc"].to(DEV),
+                            u_rand=None if c["u_rand"] is None else c["u_rand"].to(DEV), ratio=_ratio(c),
+                            outputs=("target_grid", "grid_logp", "conf_pred_mask", "ood_mask"), **kw)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("idx", range(12))
+def test_cuda_abi_against_reference_source_golden(idx):
+    c = _cases("ref_path.pt")["acq"][idx]
+    out = _call_abi(c)
+    _check(c, out["acq"], out)
+    if "lb" in c["out"]:
+        from conformal_bayesopt_b200 import ops
+        b, G = c["b"], c["G"]
+        lb, ub = ops.conf_mask_to_bounds(out["target_grid"].reshape(b, G, 1, 1), out["conf_pred_mask"].reshape(b, G, 1, 1))
+        lb, ub = lb.cpu().reshape(-1), ub.cpu().reshape(-1)
+        fin = torch.isfinite(c["out"]["lb"])
+        assert torch.equal(torch.isfinite(lb), fin)
+        if c["temp"] > 1e-3:
+            assert torch.allclose(lb[fin], c["out"]["lb"][fin], rtol=RTOL, atol=1e-7)
+            assert torch.allclose(ub[fin], c["out"]["ub"][fin], rtol=RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("idx", range(3))
+def test_cuda_abi_against_reference_source_golden_n1024(idx):
+    """BASELINE configs[1] sizes: N=1024, d=8, G=64 (cUCB; cEI + ratio + randomised; q=2)."""
+    c = _cases("ref_path_n1024.pt")["acq"][idx]
+    out = _call_abi(c)
+    _check(c, out["acq"], out)
+
+
+@pytest.mark.parametrize("name", ["cfg1_ucb_q2", "cfg4_pool", "small_ei_refine3", "small_nei", "small_pending"])
+def test_acquisition_classes_against_reference_source_golden(name):
+    """Same goldens through the drop-in classes (constructor keywords as the reference's hydra configs pass them)."""
+    import conformal_bayesopt_b200 as cbo
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    c = [x for x in _cases("ref_path.pt")["acq"] if x["name"] == name][0]
+    st = _state(c["problem"])
+    G, S = c["G"], c["S"]
+    gs, s = IIDNormalSampler(G), IIDNormalSampler(S, batch_range=(0, -3))
+    gs.set_base_samples(c["eps_grid"])
+    s.set_base_samples(c["eps_mc"])
+    kw = dict(alpha=c["alpha"], temp=c["temp"], grid_res=G, max_grid_refinements=c["refine"], ratio_estimator=_ratio(c),
+              optimistic=c["optimistic"], grid_sampler=gs, randomized=c["randomized"], model=st, sampler=s,
+              X_pending=None if c["X_pending"] is None else c["X_pending"].to(DEV))
+    if c["kind"] == "ucb":
+        acq_fn = cbo.qConformalUpperConfidenceBound(beta=c["beta"], **kw)
+    elif c["kind"] == "ei":
+        acq_fn = cbo.qConformalExpectedImprovement(best_f=c["best_f"], **kw)
+    else:
+        acq_fn = cbo.qConformalNoisyExpectedImprovement(X_baseline=c["X_baseline"].to(DEV), **kw)
+    acq_fn.fixed_probes = c["z"]
+    acq_fn.fixed_uniforms = None if c["u_rand"] is None else c["u_rand"].to(DEV)
+    with torch.no_grad():
+        acq = acq_fn(c["Xq"].to(DEV))
+    assert acq.shape == (c["b"],)
+    assert torch.allclose(acq.cpu(), c["out"]["acq"], rtol=RTOL, atol=1e-9)
+    assert int(acq.argmax()) == c["out"]["argmax"]
+
+
+@pytest.mark.parametrize("idx", range(2))
+def test_assess_coverage_against_reference_source_golden(idx):
+    """helpers.assess_coverage (credible vs conformal coverage of a hold-out set, per-point base samples)."""
+    from conformal_bayesopt_b200 import helpers
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    c = [x for x in _cases("ref_path.pt")["coverage"] if x["t"] == 1][idx]
+    st = _state(c["problem"])
+    G, n = c["G"], c["n"]
+    gs = IIDNormalSampler(G, resample=False, collapse_batch_dims=False)
+    gs.set_base_samples(c["eps_grid"].reshape(G, n, 1))
+    u = None if c["u_rand"] is None else c["u_rand"].reshape(n, G).to(DEV)
+    std_cov, conf_cov = helpers.assess_coverage(st, c["X_holdout"].to(DEV), c["Y_holdout"].to(DEV), c["alpha"], c["temp"], G,
+                                                c["refine"], _ratio(c), c["randomized"], probes=c["z"], u_rand=u,
+                                                grid_sampler=gs)
+    assert abs(std_cov - c["out"]["std_coverage"]) < 1e-6
+    assert abs(conf_cov - c["out"]["conformal_coverage"]) < 1e-6
+    tg, _, mk, _, _ = helpers.construct_conformal_bands(st, c["X_holdout"].to(DEV)[:, None], c["alpha"], c["temp"], G,
+                                                        c["refine"], gs, _ratio(c), randomized=c["randomized"],
+                                                        probes=c["z"], u_rand=u)
+    assert torch.allclose(tg.cpu(), c["out"]["target_grid"], rtol=RTOL, atol=1e-9)
+    assert torch.allclose(mk.cpu(), c["out"]["conf_pred_mask"], rtol=0, atol=1e-6)
+    lb, ub = helpers.conf_mask_to_bounds(tg, mk)
+    fin = torch.isfinite(c["out"]["lb"])
+    assert torch.equal(torch.isfinite(lb.cpu()), fin)
+    if c["temp"] > 1e-3:
+        assert torch.allclose(lb.cpu()[fin], c["out"]["lb"][fin], rtol=RTOL, atol=1e-7)
+        assert torch.allclose(ub.cpu()[fin], c["out"]["ub"][fin], rtol=RTOL, atol=1e-7)

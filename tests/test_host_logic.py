@@ -27,13 +27,14 @@ def test_sampler_reuses_base_samples_until_shape_changes():
 
 
 def test_untrained_ratio_estimator_is_one():
+    from conformal_bayesopt_b200 import _lib
     r = RatioEstimator(in_size=3, dtype=torch.float64)
-    out = r(torch.randn(5, 3, dtype=torch.float64))
-    assert torch.allclose(out, torch.ones(5, dtype=torch.float64))          # ratio_estimation.py:81-86
+    assert all(float(p.abs().sum()) == 0.0 for p in r._target_network.parameters())   # ratio_estimation.py:81-86: w == 1
     r.update_target_network()
     assert any(p.abs().sum() > 0 for p in r._target_network.parameters())
-    # positives are pooled on the device and the training step is a kernel: CPU-only use fails loudly
-    from conformal_bayesopt_b200 import _lib
+    # the forward pass and the training step are kernels: CPU tensors fail loudly, there is no torch fallback
+    with pytest.raises(_lib.CboError):
+        r(torch.randn(5, 3, dtype=torch.float64))
     with pytest.raises(_lib.CboError):
         r.optimize_callback(torch.randn(4, 3, dtype=torch.float64))
 

@@ -1,0 +1,94 @@
+"""CPU: both oracle restatements against goldens produced by EXECUTING the reference's own helpers.py / acquisitions.py
+(oracle/make_golden_path.py: reference source unmodified over the gpytorch/botorch stand-ins of oracle/_shim).
+
+Tolerances are the north star's: acquisition values, band endpoints, grid 1e-6 relative; soft masks 1e-6 absolute;
+arg-max index identical."""
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import closed_form, dense, pure
+from oracle import gp as ogp
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-6
+
+
+def load(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def acq_cases(name="ref_path.pt"):
+    return load(name)["acq"]
+
+
+def oracle_inputs(c):
+    p = c["problem"]
+    gp = ogp.build_state(p["X"], p["y"], p["mean"], p["lengthscale"], p["outputscale"], p["noise"])
+    Xq = c["Xq"] if c["X_pending"] is None else torch.cat([c["Xq"], c["X_pending"].expand(c["b"], -1, -1)], dim=1)
+    ratio = ogp.RatioMLP(*c["ratio_weights"]) if c["ratio"] else None
+    kw = dict(kind=c["kind"], alpha=c["alpha"], temp=c["temp"], grid_res=c["G"], max_grid_refinements=c["refine"],
+              eps_grid=c["eps_grid"], z=c["z"], eps_mc=c["eps_mc"], ratio=ratio, randomized=c["randomized"],
+              u_rand=c["u_rand"], optimistic=c["optimistic"], beta_prime=math.sqrt(c["beta"] * math.pi / 2),
+              best_f=c["best_f"], X_baseline=c["X_baseline"])
+    return gp, Xq, kw
+
+
+def check_against_golden(c, got, mask_atol=1e-6):
+    """got: dict with acq (b,), target_grid (b,G,q), logp (b,G), mask (b,G,q), ood (b,G,q) or (b,q)."""
+    want = c["out"]
+    b, G = c["b"], c["G"]
+    assert torch.allclose(got["acq"], want["acq"], rtol=RTOL, atol=1e-9), (got["acq"] - want["acq"]).abs().max()
+    assert int(got["acq"].argmax()) == want["argmax"]
+    assert torch.allclose(got["target_grid"], want["target_grid"][..., 0], rtol=RTOL, atol=1e-9)
+    assert torch.allclose(got["logp"], want["grid_logp"], rtol=RTOL, atol=1e-9)
+    wm = want["conf_pred_mask"][..., 0]
+    if c["temp"] > 0:
+        assert torch.allclose(got["mask"], wm, rtol=0, atol=mask_atol), (got["mask"] - wm).abs().max()
+    else:
+        assert torch.equal(got["mask"], wm)
+    ood = got["ood"] if got["ood"].ndim == 3 else got["ood"].unsqueeze(1).expand(b, G, -1)
+    assert torch.allclose(ood, want["ood_mask"][..., 0], rtol=RTOL, atol=1e-12)
+
+
+@pytest.mark.parametrize("idx", range(12))
+def test_closed_form_against_reference_source_golden(idx):
+    c = acq_cases()[idx]
+    gp, Xq, kw = oracle_inputs(c)
+    got = closed_form.conformal_acquisition(gp, Xq, **kw)
+    check_against_golden(c, got)
+    if "lb" in c["out"]:
+        lb, ub = pure.conf_mask_to_bounds(got["target_grid"].unsqueeze(-1), got["mask"].unsqueeze(-1))
+        fin = torch.isfinite(c["out"]["lb"])
+        assert torch.equal(torch.isfinite(lb.reshape(-1)), fin)
+        if c["temp"] > 1e-3:
+            assert torch.allclose(lb.reshape(-1)[fin], c["out"]["lb"][fin], rtol=RTOL, atol=1e-7)
+            assert torch.allclose(ub.reshape(-1)[fin], c["out"]["ub"][fin], rtol=RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("idx", range(12))
+def test_dense_against_reference_source_golden(idx):
+    c = acq_cases()[idx]
+    gp, Xq, kw = oracle_inputs(c)
+    got = dense.conformal_acquisition(gp, Xq, **kw)
+    check_against_golden(c, got)
+
+
+def test_golden_file_covers_the_named_configs():
+    names = [c["name"] for c in acq_cases()]
+    assert len(names) == 12
+    for want in ("cfg1_ucb_q1", "cfg1_ucb_q2", "cfg4_pool", "small_nei", "small_q3", "small_pending"):
+        assert want in names
+    big = [c["name"] for c in acq_cases("ref_path_n1024.pt")]
+    assert "cfg2_ucb" in big and "cfg2_ucb_q2" in big
+
+
+@pytest.mark.parametrize("idx", range(3))
+def test_closed_form_against_reference_source_golden_n1024(idx):
+    """BASELINE configs[1] sizes (N=1024, d=8, G=64): 48 candidates scored by the reference's dense algorithm."""
+    c = acq_cases("ref_path_n1024.pt")[idx]
+    gp, Xq, kw = oracle_inputs(c)
+    got = closed_form.conformal_acquisition(gp, Xq, **kw)
+    check_against_golden(c, got)

@@ -1,6 +1,6 @@
 // fp64 peak micro-benchmarks for B200 (sm_100a): DFMA, DMMA m8n8k4, DMMA m16n8k16,
 // and an interleaved DFMA+DMMA kernel (do the two share one pipe?).
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/fp64_peak tools/fp64_peak.cu
+// Build: nvcc -cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -o tools/fp64_peak tools/fp64_peak.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 

@@ -5,7 +5,7 @@
 // Operands are staged with plain stores in the K-major no-swizzle ("interleave") canonical layout: 16-byte K-chunk c of row r
 // at  c * ROWS * 16 + r * 16  (core matrix = 8 rows x 16 B contiguous; SBO = 128 B between 8-row groups, LBO = ROWS * 16 B
 // between K-chunks).  Every wait is bounded (trap after ~1 s) so that a wrong descriptor cannot hang the box.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/i8_mma_probe tools/i8_mma_probe.cu
+// Build: nvcc -cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/i8_mma_probe tools/i8_mma_probe.cu
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

@@ -6,7 +6,7 @@
 // One CTA per 128 x 128 output tile; the S anti-diagonals are accumulated four at a time (4 x 128 TMEM columns), i.e. K is
 // walked ceil(S/4) times.  Operands are staged by plain loads into the K-major no-swizzle canonical layout (see
 // i8_mma_probe.cu); v0 has no load/MMA overlap -- it exists to pin the arithmetic and to give a first rate.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/ozaki_gemm_proto tools/ozaki_gemm_proto.cu
+// Build: nvcc -cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/ozaki_gemm_proto tools/ozaki_gemm_proto.cu
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
