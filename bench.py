@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-grad-leg", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the ratio-estimator and strong-scaling legs")
     return ap.parse_args()
 
 
@@ -116,6 +117,7 @@ PARAMS = dict(kind="ucb", alpha=1.0 / math.sqrt(N_TRAIN), grid_res=GRID, max_gri
 def cpu_baseline(temp: float):
     """Rank 0, N=1 only: the oracle timed on the host cores, on a bounded sample of the same workload."""
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)
     from oracle import closed_form, dense
     from oracle import gp as ogp
     prob, inp, Xq = workload_cpu(0, 2048)
@@ -147,6 +149,7 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)    # torchrun exports OMP_NUM_THREADS=1: the CPU arm must not be strangled by it
     from oracle import dense
     from oracle import gp as ogp
     b = 2 if (args.steps + args.warmup) <= 16 else 1
@@ -226,7 +229,7 @@ def run_ours(args):
     nl = (C.c_int64 * 8)()
     lib.cbo_timing_collect(ms, nl)
     sampler = ClockSampler(local)
-    launches0 = ops.LAUNCH_COUNT
+    launches0 = lib.cbo_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     barrier()
@@ -237,7 +240,7 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     elapsed_ms = e0.elapsed_time(e1)
-    launches = ops.LAUNCH_COUNT - launches0
+    launches = lib.cbo_launch_count() - launches0      # counted by the library at its launch sites
     lib.cbo_timing_collect(ms, nl)
     lib.cbo_timing_enable(0)
     if world > 1:
@@ -271,7 +274,8 @@ def run_ours(args):
             e2e_ms = float(t.item())
         e2e = {"value": world * b * GRID * args.steps / (e2e_ms * 1e-3), "unit": "evals/s",
                "h2d_bytes_per_step": b * DIM * 8, "d2h_bytes_per_step": b * 8,
-               "api": "cbo_conformal_acq_host_f64 (pinned host candidates in, host acquisition values out)"}
+               "api": "cbo_conformal_acq_host_f64 (pinned host candidates in, host acquisition values out; H2D / D2H pipelined "
+                      "per 65536-candidate chunk on a copy stream)"}
 
     # ---- BASELINE configs[1] (4096 raw candidates per call), device-resident, rank 0 only, outside the timed region ----
     cfg2 = None
@@ -341,6 +345,84 @@ def run_ours(args):
                                 "grid=64, cucb, randomised, ratio estimator), CUDA-graph replay, fresh probes and uniforms per step",
                     "ms_per_call": ms_s, "value": 8 * GRID / (ms_s * 1e-3), "unit": "evals/s (joint batches x grid points)"}
 
+
+    # ---- density-ratio-weighted, randomised leg (seeded MLP 8->64->64->1, randomized=True with injected uniforms) at
+    # the headline size, device-resident; rank 0, outside the timed region; with its own per-kernel times and roofline fraction
+    cfg_ratio = None
+    if rank == 0 and not args.no_extra_legs:
+        from conformal_bayesopt_b200.synthetic import make_ratio_weights
+        ratio_w = ops.RatioWeights(*[t.to(dev) for t in make_ratio_weights(DIM)])
+        u_rand = torch.rand(b, GRID, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+        kwr = dict(kw, randomized=True, u_rand=u_rand, ratio=ratio_w)
+        for _ in range(2):
+            ops.conformal_acq(state, Xq, **kwr)
+        torch.cuda.synchronize()
+        lib.cbo_timing_enable(1)
+        msr_, nlr_ = (C.c_double * 8)(), (C.c_int64 * 8)()
+        lib.cbo_timing_collect(msr_, nlr_)
+        n_r = 3
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(n_r):
+            ops.conformal_acq(state, Xq, **kwr)
+        g1.record()
+        torch.cuda.synchronize()
+        lib.cbo_timing_collect(msr_, nlr_)
+        lib.cbo_timing_enable(0)
+        ms_r = g0.elapsed_time(g1) / n_r
+        score_tf = b * GRID * SCORE_FLOP_PER_EVAL / (msr_[4] / n_r * 1e-3) / 1e12
+        cfg_ratio = {"workload": f"{b}-candidate sweep at N=1024, d=8, grid=64, cucb WITH the density-ratio MLP (8->64->64->1, seeded) on "
+                                 "train points and candidates and randomized=True (injected uniforms, 8 bytes per eval), device-resident",
+                     "ms_per_step": ms_r, "value": b * GRID / (ms_r * 1e-3), "unit": "evals/s",
+                     "kernels_ms_per_step": {n: msr_[i] / n_r for i, n in enumerate(
+                         ["prep_tables", "kernel_rows+ratio_mlp", "gemm_pass1_dmma", "gemm_pass2_dmma", "score_rank_integrate"])},
+                     "roofline": {"bound": "tensor", "kernel": "score_rank_integrate", "achieved": score_tf, "peak": FP64_PEAK_TFLOPS,
+                                  "unit": "TFLOP/s", "frac": score_tf / FP64_PEAK_TFLOPS,
+                                  "whole_path_frac": b * GRID / (ms_r * 1e-3) * FLOP_PER_EVAL / 1e12 / FP64_PEAK_TFLOPS}}
+        del u_rand, kwr
+
+    # ---- strong scaling (north star: ONE optimize_acqf candidate batch sharded over the GPUs of the box, then a tiny exchange):
+    # a fixed TOTAL of 2^20 and of 4096 candidates; per step = local scoring + exchange + the host read of the winner
+    strong, argmax_check = [], None
+    if world > 1 and not args.no_extra_legs:
+        from conformal_bayesopt_b200 import distributed as cdist
+        _, _, Xall_cpu = workload_cpu(0, 1 << 20)                  # the same global candidate set on every rank
+        acq_fn = lambda X: ops.conformal_acq(state, X, **kw)["acq"]
+        for total in (1 << 20, 4096):
+            lo, hi = cdist.shard_bounds(total, rank, world)
+            Xs = Xall_cpu[lo:hi].to(dev)
+            res = {}
+            for mode in ("compute_only", "argmax_pairs", "score_all_gather"):
+                if mode == "compute_only":
+                    fn = lambda: acq_fn(Xs)
+                elif mode == "argmax_pairs":
+                    fn = lambda: cdist.sharded_argmax(acq_fn, Xs, lo)
+                else:
+                    Xfull = Xall_cpu[:total].to(dev)
+                    fn = lambda: int(cdist.sharded_acquisition(acq_fn, Xfull).argmax())
+                n_it = 3 if total > 100000 else 30
+                for _ in range(3):
+                    fn()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(n_it):
+                    fn()
+                barrier()
+                t = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_it], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                res[mode] = float(t.item())
+            strong.append({"total_candidates": total, "per_rank": hi - lo, "ms_per_step": res,
+                           "evals_per_s": {k: total * GRID / (v * 1e-3) for k, v in res.items()},
+                           "exchange_and_host_sync_share": {k: 1.0 - res["compute_only"] / res[k] for k in ("argmax_pairs", "score_all_gather")},
+                           "timing": "host wall clock around synchronised steps (every step ends in a host read of the winner), max over ranks"})
+        # the sharded (max, argmax) must be what ONE GPU finds on the same candidates: 2^16 subset, outside any timed region
+        sub = 1 << 16
+        lo, hi = cdist.shard_bounds(sub, rank, world)
+        got = cdist.sharded_argmax(acq_fn, Xall_cpu[lo:hi].to(dev), lo)
+        if rank == 0:
+            single = acq_fn(Xall_cpu[:sub].to(dev))
+            argmax_check = bool(int(single.argmax()) == got[1] and float(single.max()) == got[0])
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -393,7 +475,10 @@ def run_ours(args):
         "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
     }
     if cfg2 is not None:
-        line["other_configs"] = [c for c in (cfg2, cfg_grad, cfg_sgld) if c is not None]
+        line["other_configs"] = [c for c in (cfg2, cfg_ratio, cfg_grad, cfg_sgld) if c is not None]
+    if strong:
+        line["strong_scaling"] = strong
+        line["argmax_check"] = argmax_check
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

@@ -16,7 +16,7 @@ EXPORTS = [
     "cbo_cehvi_integrate_f64", "cbo_conformal_acq_grad_f64", "cbo_workspace_bytes_grad",
     "cbo_model_workspace_bytes", "cbo_model_build_f64",
     "cbo_model_append_workspace_bytes", "cbo_model_append_f64",
-    "cbo_ratio_train_workspace_bytes", "cbo_ratio_train_step_f64", "cbo_sgld_update_f64",
+    "cbo_ratio_train_workspace_bytes", "cbo_ratio_train_step_f64", "cbo_sgld_update_f64", "cbo_launch_count",
 ]
 
 c_dp = C.c_void_p  # device pointers travel as integers
@@ -77,6 +77,7 @@ def load():
         # any other failure (a compile error in an edited source) propagates: never run stale kernels silently
     lib = C.CDLL(path)
     lib.cbo_version.restype = C.c_int
+    lib.cbo_launch_count.restype = C.c_int64
     lib.cbo_status_str.restype = C.c_char_p
     lib.cbo_status_str.argtypes = [C.c_int]
     lib.cbo_last_cuda_error.restype = C.c_char_p

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/cbo.h"
@@ -44,7 +45,8 @@ constexpr int64_t kDefaultChunk = 65536;   // candidates per internal pass: 1.07
 // ---- optional per-kernel-class timing (CUDA events on the caller's stream; bench.py's roofline) ----
 enum { T_PREP = 0, T_ROWS = 1, T_GEMM1 = 2, T_GEMM2 = 3, T_SCORE = 4, T_SCORE_BWD = 5, T_GEMM_BWD = 6, T_ROWS_BWD = 7, T_NCLASS = 8 };
 struct Timing {
-    bool enabled = false;
+    std::atomic<bool> enabled{false};
+    std::mutex mu;                             // calls from several host threads may record into the same lists
     std::vector<cudaEvent_t> ev[T_NCLASS];     // start/stop pairs
     std::vector<cudaEvent_t> pool;
     int64_t launches[T_NCLASS] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -58,10 +60,16 @@ struct Timing {
 struct TimeScope {
     int cls; cudaStream_t s; bool on;
     TimeScope(int c, cudaStream_t st, int nlaunch) : cls(c), s(st), on(g_timing.enabled) {
-        if (on) { cudaEvent_t e = g_timing.get(); cudaEventRecord(e, s); g_timing.ev[cls].push_back(e); g_timing.launches[cls] += nlaunch; }
+        if (on) {
+            std::lock_guard<std::mutex> l(g_timing.mu);
+            cudaEvent_t e = g_timing.get(); cudaEventRecord(e, s); g_timing.ev[cls].push_back(e); g_timing.launches[cls] += nlaunch;
+        }
     }
     ~TimeScope() {
-        if (on) { cudaEvent_t e = g_timing.get(); cudaEventRecord(e, s); g_timing.ev[cls].push_back(e); }
+        if (on) {
+            std::lock_guard<std::mutex> l(g_timing.mu);
+            cudaEvent_t e = g_timing.get(); cudaEventRecord(e, s); g_timing.ev[cls].push_back(e);
+        }
     }
 };
 constexpr size_t kAlign = 256;
@@ -219,7 +227,7 @@ cudaError_t launch_score(const cbo::ScoreArgs& a_in, cudaStream_t st) {
     if (cudaError_t e = optin.ensure(cbo::k_score<SOFT>, smem); e != cudaSuccess) return e;
     int grid = (a.n_cand + ngroups - 1) / ngroups;     // persistent: one CTA per SM, one warp group per candidate in flight
     if (grid > num_sms()) grid = num_sms();
-    cbo::k_score<SOFT><<<grid, ngroups * (32 << wl), smem, st>>>(a);
+    CBO_LAUNCHED(), cbo::k_score<SOFT><<<grid, ngroups * (32 << wl), smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -243,7 +251,7 @@ cudaError_t launch_score_bwd(const cbo::ScoreBwdArgs& a_in, cudaStream_t st) {
     if (cudaError_t e = optin.ensure(cbo::k_score_bwd<SOFT>, smem); e != cudaSuccess) return e;
     int grid = (a.f.n_cand + ngroups - 1) / ngroups;
     if (grid > num_sms()) grid = num_sms();
-    cbo::k_score_bwd<SOFT><<<grid, ngroups * (32 << wl), smem, st>>>(a);
+    CBO_LAUNCHED(), cbo::k_score_bwd<SOFT><<<grid, ngroups * (32 << wl), smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -276,12 +284,12 @@ cudaError_t launch_score_q_bwd_t(const cbo::ScoreQBwdArgs& a, cudaStream_t st) {
             optin_cl.aux[dev].store(mc, std::memory_order_release);
         }
         if (a.f.base.n_cand <= optin_cl.aux[dev].load(std::memory_order_acquire))   // one wave of clusters; otherwise one CTA per joint batch is as fast
-            return cudaLaunchKernelEx(&cfg, cbo::k_score_q_bwd<Q, SOFT, true>, a);
+            return CBO_LAUNCHED(), cudaLaunchKernelEx(&cfg, cbo::k_score_q_bwd<Q, SOFT, true>, a);
     }
     static cbo::SmemOptIn optin;
     if (cudaError_t e = optin.ensure(cbo::k_score_q_bwd<Q, SOFT, false>, smem); e != cudaSuccess) return e;
     int grid = a.f.base.n_cand < 2 * num_sms() ? a.f.base.n_cand : 2 * num_sms();
-    cbo::k_score_q_bwd<Q, SOFT, false><<<grid, cbo::SQ_THREADS, smem, st>>>(a);
+    CBO_LAUNCHED(), cbo::k_score_q_bwd<Q, SOFT, false><<<grid, cbo::SQ_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -304,7 +312,7 @@ cudaError_t launch_score_q_t(const cbo::ScoreQArgs& a, cudaStream_t st) {
     int grid = a.base.n_cand < per_sm * num_sms() ? a.base.n_cand : per_sm * num_sms();
     // a handful of joint batches: 512 threads each (latency); many: 256 threads, more CTAs per SM
     const int threads = (Q <= 2 && a.base.n_cand < 2 * num_sms()) ? cbo::SQ_THREADS_SMALL : cbo::SQ_THREADS;
-    cbo::k_score_q<Q, SOFT><<<grid, threads, smem, st>>>(a);
+    CBO_LAUNCHED(), cbo::k_score_q<Q, SOFT><<<grid, threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -322,6 +330,8 @@ cudaError_t launch_score_q(const cbo::ScoreQArgs& a, int q, bool soft, cudaStrea
 extern "C" {
 
 int cbo_version(void) { return CBO_VERSION; }
+
+int64_t cbo_launch_count(void) { return (int64_t)cbo::launch_counter().load(std::memory_order_relaxed); }
 
 const char* cbo_status_str(int s) {
     switch (s) {
@@ -359,7 +369,7 @@ int cbo_kernel_rows_f64(const cbo_gp_f64* gp, const double* Xq, int64_t n, doubl
     if (!gp || !Xq || !U || !scratch || n <= 0) return CBO_ERR_INVALID_ARG;
     if (gp->d > cbo::MAX_D) return CBO_ERR_UNSUPPORTED;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    cbo::k_scale_transpose<<<(int)((gp->Np * gp->d + 255) / 256), 256, 0, s>>>(gp->X, (int)gp->N, (int)gp->Np, (int)gp->d,
+    CBO_LAUNCHED(), cbo::k_scale_transpose<<<(int)((gp->Np * gp->d + 255) / 256), 256, 0, s>>>(gp->X, (int)gp->N, (int)gp->Np, (int)gp->d,
                                                                              gp->inv_lengthscale, scratch);
     CBO_CUDA(cbo::launch_kernel_rows(Xq, (int)n, scratch, (int)gp->N, (int)gp->Np, (int)gp->d, gp->inv_lengthscale,
                                      gp->outputscale, gp->mean, gp->alpha, nullptr, 0, U, mu, nullptr, num_sms(), s));
@@ -400,12 +410,12 @@ int cbo_ratio_train_step_f64(int64_t d, int64_t hidden, double* theta, double* a
     static cbo::SmemOptIn optin;
     CBO_CUDA(optin.ensure(cbo::k_ratio_train_grad, smem));
     double* partial = static_cast<double*>(workspace);
-    cbo::k_ratio_train_grad<<<tiles, cbo::RT_THREADS, smem, st>>>(theta, (int)d, x_neg, (int)n_neg, x_pos, pos_idx,
+    CBO_LAUNCHED(), cbo::k_ratio_train_grad<<<tiles, cbo::RT_THREADS, smem, st>>>(theta, (int)d, x_neg, (int)n_neg, x_pos, pos_idx,
                                                                   (int)n_pos, partial);
     CBO_CUDA(cudaGetLastError());
     const int64_t P = cbo::ratio_num_params((int)d);
     const double bc1 = 1.0 - std::pow(beta1, double(step)), bc2 = 1.0 - std::pow(beta2, double(step));
-    cbo::k_ratio_adam_ema<<<int((P + 1 + 255) / 256), 256, 0, st>>>(theta, adam_m, adam_v, target, partial, tiles, P,
+    CBO_LAUNCHED(), cbo::k_ratio_adam_ema<<<int((P + 1 + 255) / 256), 256, 0, st>>>(theta, adam_m, adam_v, target, partial, tiles, P,
                                                                    double(n_rows), lr / bc1, 1.0 / std::sqrt(bc2), beta1,
                                                                    beta2, eps, weight_decay, ema_weight, loss);
     CBO_CUDA(cudaGetLastError());
@@ -420,7 +430,7 @@ int cbo_sgld_update_f64(double* X, double* momentum_buf, const double* dacq_dX, 
         return CBO_ERR_INVALID_ARG;
     const int64_t n = n_rows * d;
     const double ns = momentum > 0.0 ? std::sqrt(2.0 * lr * momentum * temperature) : std::sqrt(2.0 * lr * temperature);
-    cbo::k_sgld_update<<<int((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    CBO_LAUNCHED(), cbo::k_sgld_update<<<int((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         X, momentum_buf, dacq_dX, noise, lb, ub, n, (int)d, lr, momentum, ns, penalty_scale, penalty_width);
     CBO_CUDA(cudaGetLastError());
     return CBO_OK;
@@ -450,16 +460,24 @@ int cbo_conf_mask_to_bounds_f64(const double* grid, const double* mask, int64_t 
     if (G > cbo::BOUNDS_MAX_G) return CBO_ERR_UNSUPPORTED;
     int Gp = 2;
     while (Gp < G) Gp <<= 1;
-    cbo::k_mask_to_bounds<<<(int)(b * t), cbo::BOUNDS_THREADS, 2 * Gp * sizeof(double),
+    CBO_LAUNCHED(), cbo::k_mask_to_bounds<<<(int)(b * t), cbo::BOUNDS_THREADS, 2 * Gp * sizeof(double),
                             static_cast<cudaStream_t>(stream)>>>(grid, mask, (int)b, (int)G, (int)t, Gp, lb, ub);
     CBO_CUDA(cudaGetLastError());
     return CBO_OK;
 }
 
+// Per-chunk callbacks of the host-buffer entry point: `before` is called ahead of the first kernel that reads the chunk's
+// candidates, `after` behind the last kernel that writes its acquisition values (both only enqueue stream operations).
+struct ChunkHooks {
+    void* ctx;
+    int (*before)(void* ctx, int64_t c0, int64_t ncand);
+    int (*after)(void* ctx, int64_t c0, int64_t ncand);
+};
+
 static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* p, const double* Xq,
                               int64_t b, const double* eps_grid, const double* z, const double* eps_mc,
                               const double* u_rand, const cbo_outputs_f64* out, double* dX, void* workspace,
-                              size_t workspace_bytes, int64_t chunk, void* stream) {
+                              size_t workspace_bytes, int64_t chunk, void* stream, const ChunkHooks* hooks = nullptr) {
     int st = validate(gp, p, b);
     if (st != CBO_OK) return st;
     const bool grad = dX != nullptr;
@@ -484,8 +502,8 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
     // ---- per-call tables: T = A^-1 z[:N], dr_train, a, h0, zb, sum_dr -------------------------------
     {
     TimeScope ts_(T_PREP, s, 7);
-    cbo::k_scale_transpose<<<(Np * d + 255) / 256, 256, 0, s>>>(gp->X, N, Np, d, gp->inv_lengthscale, w.XsT);
-    cbo::k_pad_probes<<<(Np * Sp + 255) / 256, 256, 0, s>>>(z, N, Np, Sp, w.zp);
+    CBO_LAUNCHED(), cbo::k_scale_transpose<<<(Np * d + 255) / 256, 256, 0, s>>>(gp->X, N, Np, d, gp->inv_lengthscale, w.XsT);
+    CBO_LAUNCHED(), cbo::k_pad_probes<<<(Np * Sp + 255) / 256, 256, 0, s>>>(z, N, Np, Sp, w.zp);
     // T^T = Z^T A^-1 (Sp x Np): the probe vectors are Sp more "rows" for the two triangular passes (split-K: a handful of rows)
     CBO_CUDA(cbo::launch_gemm_tn(w.zp, Np, gp->linv, Np, w.tmp, Np, Sp, Np, Np, cbo::TRI_LOWER, nullptr, s, num_sms(), w.splitk));
     CBO_CUDA(cbo::launch_gemm_tn(w.tmp, Np, gp->linv_t, Np, w.T, Np, Sp, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms(), w.splitk));
@@ -493,12 +511,12 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
         CBO_CUDA(cbo::launch_ratio_mlp(gp->X, N, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2, ratio->b2,
                                        ratio->W3, ratio->b3, 1e-6, w.dr_train, num_sms(), s));
     else
-        cbo::k_fill<<<(Np + 255) / 256, 256, 0, s>>>(w.dr_train, Np, 1.0);
+        CBO_LAUNCHED(), cbo::k_fill<<<(Np + 255) / 256, 256, 0, s>>>(w.dr_train, Np, 1.0);
     if (p->q == 1) {
         const int rows = p->eps_per_candidate ? (int)b : 1;
-        cbo::k_eps_absmax<<<(rows + 7) / 8, 256, 0, s>>>(eps_grid, rows, G, w.eps_absmax);
+        CBO_LAUNCHED(), cbo::k_eps_absmax<<<(rows + 7) / 8, 256, 0, s>>>(eps_grid, rows, G, w.eps_absmax);
     }
-    cbo::k_train_tables<<<1, 256, 0, s>>>(gp->alpha, z, w.T, N, Np, Sp, gp->noise, w.dr_train, w.a, w.h0, w.zb,
+    CBO_LAUNCHED(), cbo::k_train_tables<<<1, 256, 0, s>>>(gp->alpha, z, w.T, N, Np, Sp, gp->noise, w.dr_train, w.a, w.h0, w.zb,
                                           w.sum_dr);
     }
     CBO_CUDA(cudaGetLastError());
@@ -510,6 +528,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
         const int ncand = (int)((b - c0 < C) ? (b - c0) : C);
         const int n = ncand * q;                                  // kernel rows of this chunk: one per candidate POINT
         const double* Xc = Xq + c0 * q * d;
+        if (hooks) { int hs_ = hooks->before(hooks->ctx, c0, ncand); if (hs_ != CBO_OK) return hs_; }
         // ---- kernel rows, mu, u^T T; candidate density ratios -------------------------------------
         {
             TimeScope ts_(T_ROWS, s, ratio ? 2 : 1);
@@ -561,7 +580,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 na.eps_grid = x.eps_grid; na.eps_per_candidate = x.eps_per_candidate; na.eps_mc = eps_mc;
                 na.values = w.nei_values;
                 na.V = w.V;
-                if (q == 1) cbo::k_nei_values<<<(ncand + 3) / 4, 128, 0, s>>>(na);
+                if (q == 1) CBO_LAUNCHED(), cbo::k_nei_values<<<(ncand + 3) / 4, 128, 0, s>>>(na);
                 else {
                     cudaError_t e = cbo::launch_nei_values_q(na, q, s);
                     if (e != cudaSuccess) return e;
@@ -626,7 +645,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                     CBO_CUDA(cbo::launch_rows_bwd(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->alpha, rhs,
                                                   w.UW, w.adj, dX + c0 * q * d, num_sms(), s));
                 else    // joint batches, and q = 1 calls with a handful of candidates (CTA per candidate point)
-                    cbo::k_rows_bwd_q<<<n, cbo::RBQ_THREADS, 0, s>>>(Xc, n, q, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale,
+                    CBO_LAUNCHED(), cbo::k_rows_bwd_q<<<n, cbo::RBQ_THREADS, 0, s>>>(Xc, n, q, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale,
                                                                  gp->alpha, rhs, w.UW, w.adj,
                                                                  q == 1 ? cbo::ADJ_STRIDE : cbo::ADJQ_STRIDE, q == 1 ? 1 : 0,
                                                                  dX + c0 * q * d);
@@ -647,7 +666,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             // grid refinement (helpers.py:129-189): probe passes keep only the accepted counts; the pass with the
             // smallest grid_score is then re-run into the caller's buffers.  One host sync per pass, like the
             // reference (helpers.py:151-152,177).
-            cbo::k_fill<<<(n + 255) / 256, 256, 0, s>>>(w.cscale, n, 1.0);
+            CBO_LAUNCHED(), cbo::k_fill<<<(n + 255) / 256, 256, 0, s>>>(w.cscale, n, 1.0);
             float best_score = INFINITY;
             int best_step = 0;
             double* scratch_acq = w.acq_scratch;          // acquisition values of probe passes are discarded
@@ -657,7 +676,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 pa.acq = scratch_acq;
                 pa.num_acc = w.nacc;
                 CBO_CUDA(run_score(pa));
-                k_accept_stats<<<1, 256, 0, s>>>(w.nacc, n, G, w.stats);
+                CBO_LAUNCHED(), k_accept_stats<<<1, 256, 0, s>>>(w.nacc, n, G, w.stats);
                 double hs[4];
                 CBO_CUDA(cudaMemcpyAsync(hs, w.stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
                 CBO_CUDA(cudaStreamSynchronize(s));
@@ -670,7 +689,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 bool rescale = hs[0] < 2.0 || hs[1] > double(G - 2);
                 if (!rescale) break;
                 if (step < R)
-                    k_rescale<<<(n + 255) / 256, 256, 0, s>>>(w.nacc, w.cscale + int64_t(step) * b * q,
+                    CBO_LAUNCHED(), k_rescale<<<(n + 255) / 256, 256, 0, s>>>(w.nacc, w.cscale + int64_t(step) * b * q,
                                                               w.cscale + int64_t(step + 1) * b * q, n, G, q);
             }
             cbo::ScoreArgs fa = a;
@@ -679,6 +698,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             int rs = run_final(fa);
             if (rs != CBO_OK) return rs;
         }
+        if (hooks) { int hs_ = hooks->after(hooks->ctx, c0, ncand); if (hs_ != CBO_OK) return hs_; }
     }
     return CBO_OK;
 }
@@ -727,7 +747,7 @@ int cbo_cehvi_integrate_f64(int64_t m, int64_t b, int64_t G, int64_t S, const do
     size_t smem = size_t(2 * n_cells * m) * sizeof(double);
     static cbo::SmemOptIn optin;
     CBO_CUDA(optin.ensure(cbo::k_ehvi, smem));
-    cbo::k_ehvi<<<(int)((b + 7) / 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    CBO_LAUNCHED(), cbo::k_ehvi<<<(int)((b + 7) / 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
     CBO_CUDA(cudaGetLastError());
     return CBO_OK;
 }
@@ -758,6 +778,7 @@ void cbo_timing_enable(int on) {
 // Sums elapsed ms per kernel class since the last collect (synchronises on the recorded events).
 int cbo_timing_collect(double* ms_out /* 8 */, int64_t* launches_out /* 8 */) {
     if (!ms_out || !launches_out) return CBO_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> l(g_timing.mu);
     for (int c = 0; c < T_NCLASS; ++c) {
         double tot = 0.0;
         auto& v = g_timing.ev[c];
@@ -776,23 +797,97 @@ int cbo_timing_collect(double* ms_out /* 8 */, int64_t* launches_out /* 8 */) {
     return CBO_OK;
 }
 
-int cbo_conformal_acq_host_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* p,
+}  // extern "C"
+
+// ---- host-buffer entry point: per-chunk pipeline ------------------------------------------------------------------
+// The candidates of chunk k+1 travel host -> device and the acquisition values of chunk k-1 device -> host on a private copy
+// stream while the kernels of chunk k run on the caller's stream (events order the two); one copy stream and a pool of
+// timing-free events per device, created on first use (no device memory is allocated).
+namespace {
+struct HostPipe {
+    std::mutex mu;
+    cudaStream_t copy = nullptr;
+    std::vector<cudaEvent_t> ev;
+    cudaError_t ensure(size_t n_events) {
+        if (!copy) {
+            cudaError_t e = cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking);
+            if (e != cudaSuccess) return e;
+        }
+        while (ev.size() < n_events) {
+            cudaEvent_t x;
+            cudaError_t e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+            ev.push_back(x);
+        }
+        return cudaSuccess;
+    }
+};
+HostPipe g_host_pipe[cbo::kMaxDevices];
+
+struct HostPipeCtx {
+    HostPipe* pipe;
+    cudaStream_t compute;
+    const double* X_host; double* X_dev; double* acq_host; double* acq_dev;
+    int64_t b, C, row;          // candidates, chunk size, doubles per candidate (q * d)
+    cudaError_t err = cudaSuccess;
+    cudaEvent_t h2d_done(int64_t k) { return pipe->ev[2 * k + 1]; }
+    cudaEvent_t chunk_done(int64_t k) { return pipe->ev[2 * k + 2]; }
+    cudaError_t upload(int64_t k) {     // candidates of chunk k
+        const int64_t c0 = k * C, n = (b - c0 < C) ? (b - c0) : C;
+        cudaError_t e = cudaMemcpyAsync(X_dev + c0 * row, X_host + c0 * row, sizeof(double) * n * row, cudaMemcpyHostToDevice, pipe->copy);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(h2d_done(k), pipe->copy);
+    }
+};
+int host_before(void* v, int64_t c0, int64_t) {
+    HostPipeCtx* c = static_cast<HostPipeCtx*>(v);
+    const int64_t k = c0 / c->C;
+    if ((k + 1) * c->C < c->b) { if ((c->err = c->upload(k + 1)) != cudaSuccess) return CBO_ERR_CUDA; }   // prefetch the next chunk
+    if ((c->err = cudaStreamWaitEvent(c->compute, c->h2d_done(k), 0)) != cudaSuccess) return CBO_ERR_CUDA;
+    return CBO_OK;
+}
+int host_after(void* v, int64_t c0, int64_t ncand) {
+    HostPipeCtx* c = static_cast<HostPipeCtx*>(v);
+    const int64_t k = c0 / c->C;
+    if ((c->err = cudaEventRecord(c->chunk_done(k), c->compute)) != cudaSuccess) return CBO_ERR_CUDA;
+    if ((c->err = cudaStreamWaitEvent(c->pipe->copy, c->chunk_done(k), 0)) != cudaSuccess) return CBO_ERR_CUDA;
+    if ((c->err = cudaMemcpyAsync(c->acq_host + c0, c->acq_dev + c0, sizeof(double) * ncand, cudaMemcpyDeviceToHost,
+                                  c->pipe->copy)) != cudaSuccess) return CBO_ERR_CUDA;
+    return CBO_OK;
+}
+}  // namespace
+
+extern "C" int cbo_conformal_acq_host_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* p,
                                const double* Xq_host, int64_t b, const double* eps_grid, const double* z,
                                const double* eps_mc, const double* u_rand, double* acq_host, double* Xq_staging,
                                double* acq_staging, void* workspace, size_t workspace_bytes, int64_t chunk,
                                void* stream) {
     if (!gp || !p || !Xq_host || !acq_host || !Xq_staging || !acq_staging || b <= 0) return CBO_ERR_INVALID_ARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    CBO_CUDA(cudaMemcpyAsync(Xq_staging, Xq_host, sizeof(double) * b * p->q * gp->d, cudaMemcpyHostToDevice, s));
+    const int dev = cbo::current_device_slot();
+    if (dev < 0) return CBO_ERR_NO_DEVICE;
+    HostPipe& pipe = g_host_pipe[dev];
+    std::lock_guard<std::mutex> lock(pipe.mu);            // one host-buffer call per device at a time shares the copy stream
+    const int64_t C = pick_chunk(b, p, chunk), n_chunks = (b + C - 1) / C;
+    CBO_CUDA(pipe.ensure(size_t(2 * n_chunks + 2)));
+    HostPipeCtx ctx;
+    ctx.pipe = &pipe; ctx.compute = s; ctx.X_host = Xq_host; ctx.X_dev = Xq_staging; ctx.acq_host = acq_host;
+    ctx.acq_dev = acq_staging; ctx.b = b; ctx.C = C; ctx.row = p->q * gp->d;
+    // the copy stream starts behind whatever the caller's stream still has in flight on the staging buffers
+    CBO_CUDA(cudaEventRecord(pipe.ev[0], s));
+    CBO_CUDA(cudaStreamWaitEvent(pipe.copy, pipe.ev[0], 0));
+    CBO_CUDA(ctx.upload(0));
     cbo_outputs_f64 out;
     memset(&out, 0, sizeof(out));
     out.acq = acq_staging;
-    int st = cbo_conformal_acq_f64(gp, ratio, p, Xq_staging, b, eps_grid, z, eps_mc, u_rand, &out, workspace,
-                                   workspace_bytes, chunk, stream);
+    ChunkHooks hooks{&ctx, host_before, host_after};
+    int st = conformal_acq_impl(gp, ratio, p, Xq_staging, b, eps_grid, z, eps_mc, u_rand, &out, nullptr, workspace,
+                                workspace_bytes, chunk, stream, &hooks);
+    if (st == CBO_ERR_CUDA && ctx.err != cudaSuccess) cuda_fail(ctx.err, "host pipeline");
+    // drain both streams before returning (the host buffers belong to the caller again)
+    cudaError_t e1 = cudaStreamSynchronize(pipe.copy), e2 = cudaStreamSynchronize(s);
     if (st != CBO_OK) return st;
-    CBO_CUDA(cudaMemcpyAsync(acq_host, acq_staging, sizeof(double) * b, cudaMemcpyDeviceToHost, s));
-    CBO_CUDA(cudaStreamSynchronize(s));
+    CBO_CUDA(e1);
+    CBO_CUDA(e2);
     return CBO_OK;
 }
-
-}  // extern "C"

@@ -7,6 +7,13 @@
 
 namespace cbo {
 
+// Kernels launched by the library since it was loaded (cbo_launch_count): every launch site is prefixed with CBO_LAUNCHED().
+inline std::atomic<long long>& launch_counter() {
+    static std::atomic<long long> c{0};
+    return c;
+}
+#define CBO_LAUNCHED() ((void)cbo::launch_counter().fetch_add(1, std::memory_order_relaxed))
+
 // ---- host: per-DEVICE state (one process may drive several GPUs from several threads; cbo.h promises re-entrancy) ------
 constexpr int kMaxDevices = 64;
 inline int current_device_slot() {

@@ -218,7 +218,7 @@ inline cudaError_t launch_gemm_tn_t(const double* A, int64_t lda, const double* 
         attr_set = true;
     }
     int tiles_m = (M + 16 * MF - 1) / (16 * MF), tiles_n = Nn / GEMM_BN;
-    k_gemm_tn_f64<MF><<<dim3(tiles_m * tiles_n, splits), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(
+    CBO_LAUNCHED(), k_gemm_tn_f64<MF><<<dim3(tiles_m * tiles_n, splits), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(
         A, lda, B, ldb, C, ldc, M, Nn, K, tri, rownorm_partial, splits, part_stride);
     return cudaGetLastError();
 }
@@ -267,9 +267,9 @@ inline cudaError_t launch_gemm_tn(const double* A, int64_t lda, const double* B,
             ? launch_gemm_tn_t<2>(A, lda, B, ldb, splitk_scratch, Nn, M, Nn, K, tri, nullptr, stream, GEMM_SPLITK, ps)
             : launch_gemm_tn_t<1>(A, lda, B, ldb, splitk_scratch, Nn, M, Nn, K, tri, nullptr, stream, GEMM_SPLITK, ps);
         if (e != cudaSuccess) return e;
-        k_splitk_reduce<<<(M * Nn + 255) / 256, 256, 0, stream>>>(splitk_scratch, GEMM_SPLITK, ps, Nn, C, ldc, M, Nn);
+        CBO_LAUNCHED(), k_splitk_reduce<<<(M * Nn + 255) / 256, 256, 0, stream>>>(splitk_scratch, GEMM_SPLITK, ps, Nn, C, ldc, M, Nn);
         if (rownorm_partial != nullptr)
-            k_rownorm_tiles<<<(M * (Nn / GEMM_BN) + 7) / 8, 256, 0, stream>>>(C, ldc, M, Nn / GEMM_BN, rownorm_partial);
+            CBO_LAUNCHED(), k_rownorm_tiles<<<(M * (Nn / GEMM_BN) + 7) / 8, 256, 0, stream>>>(C, ldc, M, Nn / GEMM_BN, rownorm_partial);
         return cudaGetLastError();
     }
     // pick the largest m-tile that still yields ~2 CTAs per SM; few rows -> small tiles (latency, no wasted rows)

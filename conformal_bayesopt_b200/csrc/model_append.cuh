@@ -111,10 +111,10 @@ inline cudaError_t model_append(double* X, int64_t N, int64_t d, int64_t Np, con
         const double* xn = x_new + p * d;
         const int nblk = (n + MA_THREADS - 1) / MA_THREADS, nwb = (n + MA_THREADS / 32 - 1) / (MA_THREADS / 32);
         if (n > 0) {
-            k_append_kvec<<<nblk, MA_THREADS, 0, s>>>(X, n, (int)d, inv_ls, outputscale, xn, alpha, kvec, part);
-            k_append_v<<<nwb, MA_THREADS, 0, s>>>(linv, (int)Np, n, kvec, v);
+            CBO_LAUNCHED(), k_append_kvec<<<nblk, MA_THREADS, 0, s>>>(X, n, (int)d, inv_ls, outputscale, xn, alpha, kvec, part);
+            CBO_LAUNCHED(), k_append_v<<<nwb, MA_THREADS, 0, s>>>(linv, (int)Np, n, kvec, v);
         }
-        k_append_row<<<nwb > 0 ? nwb : 1, MA_THREADS, 0, s>>>(linv, linv_t, (int)Np, n, (int)d, v, part, n > 0 ? nblk : 0,
+        CBO_LAUNCHED(), k_append_row<<<nwb > 0 ? nwb : 1, MA_THREADS, 0, s>>>(linv, linv_t, (int)Np, n, (int)d, v, part, n > 0 ? nblk : 0,
                                                             outputscale + noise, y_new + p, mean, xn, X, alpha, info);
     }
     return cudaGetLastError();

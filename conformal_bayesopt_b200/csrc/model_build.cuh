@@ -152,10 +152,10 @@ inline cudaError_t model_build(const double* X, const double* y, int N, int d, c
     MB_CHECK(cudaMemsetAsync(w.A, 0, sizeof(double) * size_t(Np) * Np, s));
     MB_CHECK(cudaMemsetAsync(linv_t, 0, sizeof(double) * size_t(Np) * Np, s));
     // ---- A = K(X, X) + noise I (identity on the padding) ---------------------------------------------------------
-    k_scale_transpose<<<(Np * d + 255) / 256, 256, 0, s>>>(X, N, Np, d, inv_ls, w.XsT);
+    CBO_LAUNCHED(), k_scale_transpose<<<(Np * d + 255) / 256, 256, 0, s>>>(X, N, Np, d, inv_ls, w.XsT);
     MB_CHECK(launch_kernel_rows(X, N, w.XsT, N, Np, d, inv_ls, outputscale, 0.0, w.yc /* unused alpha: any Np buffer */,
                                 nullptr, 0, w.A, nullptr, nullptr, num_sms, s));
-    k_fix_diag<<<(Np + 255) / 256, 256, 0, s>>>(w.A, N, Np, outputscale + noise);
+    CBO_LAUNCHED(), k_fix_diag<<<(Np + 255) / 256, 256, 0, s>>>(w.A, N, Np, outputscale + noise);
     const size_t potrf_smem = sizeof(double) * (MB_NB * MB_LDS + MB_NB);
     static SmemOptIn optin;
     MB_CHECK(optin.ensure(k_potrf_trtri_128, potrf_smem));
@@ -166,22 +166,22 @@ inline cudaError_t model_build(const double* X, const double* y, int N, int d, c
         const int K = j * MB_NB;
         if (j > 0) {
             MB_CHECK(launch_gemm_tn(Lj0, Np, Lj0, Np, w.P1, MB_NB, MB_NB, MB_NB, K, TRI_FULL, nullptr, s, num_sms));
-            k_block_sub<<<(MB_NB * MB_NB + 255) / 256, 256, 0, s>>>(Ajj, Np, w.P1, MB_NB, w.S, MB_NB, MB_NB);
+            CBO_LAUNCHED(), k_block_sub<<<(MB_NB * MB_NB + 255) / 256, 256, 0, s>>>(Ajj, Np, w.P1, MB_NB, w.S, MB_NB, MB_NB);
         } else {
-            k_block_sub<<<(MB_NB * MB_NB + 255) / 256, 256, 0, s>>>(Ajj, Np, nullptr, 0, w.S, MB_NB, MB_NB);
+            CBO_LAUNCHED(), k_block_sub<<<(MB_NB * MB_NB + 255) / 256, 256, 0, s>>>(Ajj, Np, nullptr, 0, w.S, MB_NB, MB_NB);
         }
         double* Tj = w.Tb + size_t(j) * MB_NB * MB_NB;
         double* nTj = w.negTb + size_t(j) * MB_NB * MB_NB;
-        k_potrf_trtri_128<<<1, 256, potrf_smem, s>>>(w.S, MB_NB, Ajj, Np, Tj, nTj, j * MB_NB, info);
+        CBO_LAUNCHED(), k_potrf_trtri_128<<<1, 256, potrf_smem, s>>>(w.S, MB_NB, Ajj, Np, Tj, nTj, j * MB_NB, info);
         const int M = Np - (j + 1) * MB_NB;
         if (M > 0) {
             double* Aij = w.A + (int64_t(j + 1) * MB_NB) * Np + int64_t(j) * MB_NB;     // panel below the diagonal block
             const double* Li0 = w.A + (int64_t(j + 1) * MB_NB) * Np;
             if (j > 0) {
                 MB_CHECK(launch_gemm_tn(Li0, Np, Lj0, Np, w.P1, MB_NB, M, MB_NB, K, TRI_FULL, nullptr, s, num_sms));
-                k_block_sub<<<(M * MB_NB + 255) / 256, 256, 0, s>>>(Aij, Np, w.P1, MB_NB, w.P2, MB_NB, M);
+                CBO_LAUNCHED(), k_block_sub<<<(M * MB_NB + 255) / 256, 256, 0, s>>>(Aij, Np, w.P1, MB_NB, w.P2, MB_NB, M);
             } else {
-                k_block_sub<<<(M * MB_NB + 255) / 256, 256, 0, s>>>(Aij, Np, nullptr, 0, w.P2, MB_NB, M);
+                CBO_LAUNCHED(), k_block_sub<<<(M * MB_NB + 255) / 256, 256, 0, s>>>(Aij, Np, nullptr, 0, w.P2, MB_NB, M);
             }
             MB_CHECK(launch_gemm_tn(w.P2, MB_NB, Tj, MB_NB, Aij, Np, M, MB_NB, MB_NB, TRI_FULL, nullptr, s, num_sms));
         }
@@ -190,7 +190,7 @@ inline cudaError_t model_build(const double* X, const double* y, int N, int d, c
     for (int i = 0; i < nb; ++i) {
         const double* Ti = w.Tb + size_t(i) * MB_NB * MB_NB;
         const double* nTi = w.negTb + size_t(i) * MB_NB * MB_NB;
-        k_block_transpose_out<<<dim3(4, 4), dim3(32, 8), 0, s>>>(Ti, linv_t + (int64_t(i) * MB_NB) * Np + int64_t(i) * MB_NB, Np);
+        CBO_LAUNCHED(), k_block_transpose_out<<<dim3(4, 4), dim3(32, 8), 0, s>>>(Ti, linv_t + (int64_t(i) * MB_NB) * Np + int64_t(i) * MB_NB, Np);
         if (i > 0) {
             const int M = i * MB_NB;                                        // rows 0 .. 128 i of linv_t
             const double* Li0 = w.A + (int64_t(i) * MB_NB) * Np;
@@ -201,11 +201,11 @@ inline cudaError_t model_build(const double* X, const double* y, int N, int d, c
                                     nullptr, s, num_sms));
         }
     }
-    k_transpose_zero_pad<<<dim3(Np / 32, Np / 32), dim3(32, 8), 0, s>>>(linv_t, linv, N, Np);
+    CBO_LAUNCHED(), k_transpose_zero_pad<<<dim3(Np / 32, Np / 32), dim3(32, 8), 0, s>>>(linv_t, linv, N, Np);
     // ---- alpha = L^-T (L^-1 (y - m)) ---------------------------------------------------------------------------------------
-    k_center_targets<<<(Np + 255) / 256, 256, 0, s>>>(y, N, Np, mean, w.yc);
-    k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(linv, Np, w.yc, 1, w.t1, 0, 1);
-    k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(linv_t, Np, w.t1, 1, alpha, 1, 0);
+    CBO_LAUNCHED(), k_center_targets<<<(Np + 255) / 256, 256, 0, s>>>(y, N, Np, mean, w.yc);
+    CBO_LAUNCHED(), k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(linv, Np, w.yc, 1, w.t1, 0, 1);
+    CBO_LAUNCHED(), k_probe_matvec<<<(Np + 7) / 8, 256, 0, s>>>(linv_t, Np, w.t1, 1, alpha, 1, 0);
 #undef MB_CHECK
     return cudaGetLastError();
 }

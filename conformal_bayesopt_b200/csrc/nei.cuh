@@ -315,9 +315,9 @@ k_nei_values_q(const NeiArgs p) {
 inline cudaError_t launch_nei_values_q(const NeiArgs& a, int q, cudaStream_t s) {
     const int grid = (a.n_cand + 3) / 4;
     switch (q) {
-        case 2: k_nei_values_q<2><<<grid, 128, 0, s>>>(a); break;
-        case 3: k_nei_values_q<3><<<grid, 128, 0, s>>>(a); break;
-        case 4: k_nei_values_q<4><<<grid, 128, 0, s>>>(a); break;
+        case 2: CBO_LAUNCHED(), k_nei_values_q<2><<<grid, 128, 0, s>>>(a); break;
+        case 3: CBO_LAUNCHED(), k_nei_values_q<3><<<grid, 128, 0, s>>>(a); break;
+        case 4: CBO_LAUNCHED(), k_nei_values_q<4><<<grid, 128, 0, s>>>(a); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -229,7 +229,7 @@ inline cudaError_t launch_ratio_mlp(const double* x, int n, int d, int H, const 
     if (cudaError_t e = optin.ensure(k_ratio_mlp_mma, smem); e != cudaSuccess) return e;
     int grid = ((n + 15) / 16 + RM_WARPS - 1) / RM_WARPS;
     if (grid > 2 * num_sms) grid = 2 * num_sms;
-    k_ratio_mlp_mma<<<grid, RM_WARPS * 32, smem, st>>>(x, n, d, H, W1, b1, W2, b2, W3, b3, clamp_min, out);
+    CBO_LAUNCHED(), k_ratio_mlp_mma<<<grid, RM_WARPS * 32, smem, st>>>(x, n, d, H, W1, b1, W2, b2, W3, b3, clamp_min, out);
     return cudaGetLastError();
 }
 
@@ -242,7 +242,7 @@ inline cudaError_t launch_ratio_mlp_bwd(const double* x, int n, int d, int H, co
     if (cudaError_t e = optin.ensure(k_ratio_mlp_mma_bwd, smem); e != cudaSuccess) return e;
     int grid = ((n + 7) / 8 + RM_WARPS - 1) / RM_WARPS;
     if (grid > 2 * num_sms) grid = 2 * num_sms;
-    k_ratio_mlp_mma_bwd<<<grid, RM_WARPS * 32, smem, st>>>(x, n, d, H, W1, b1, W2, b2, W3, b3, clamp_min, adj, adj_stride, adj_off, dX);
+    CBO_LAUNCHED(), k_ratio_mlp_mma_bwd<<<grid, RM_WARPS * 32, smem, st>>>(x, n, d, H, W1, b1, W2, b2, W3, b3, clamp_min, adj, adj_stride, adj_off, dX);
     return cudaGetLastError();
 }
 

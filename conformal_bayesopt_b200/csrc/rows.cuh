@@ -240,7 +240,7 @@ inline cudaError_t launch_kernel_rows_t(const double* Xq, int n, const double* X
     const int groups = (n + ROWS_CPW - 1) / ROWS_CPW;
     int grid = (groups + ROWS_WARPS - 1) / ROWS_WARPS;
     if (grid > num_sms) grid = num_sms;                              // persistent: one 16-warp CTA per SM
-    k_kernel_rows<STAGE, NSP><<<grid, ROWS_WARPS * 32, smem, st>>>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, mean, alpha,
+    CBO_LAUNCHED(), k_kernel_rows<STAGE, NSP><<<grid, ROWS_WARPS * 32, smem, st>>>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, mean, alpha,
                                                                    T, Sp, U, mu, ut);
     return cudaGetLastError();
 }
@@ -250,7 +250,7 @@ inline cudaError_t launch_kernel_rows(const double* Xq, int n, const double* XsT
                                       const double* T, int Sp, double* U, double* mu, double* ut, int num_sms,
                                       cudaStream_t st, bool small_call = false) {
     if (small_call) {   // decided per CALL by the API (<= 32 candidate points), never per chunk
-        k_kernel_rows_small<<<n, ROWS_SMALL_THREADS, 0, st>>>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, mean, alpha, T, Sp, U,
+        CBO_LAUNCHED(), k_kernel_rows_small<<<n, ROWS_SMALL_THREADS, 0, st>>>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, mean, alpha, T, Sp, U,
                                                               mu, ut);
         return cudaGetLastError();
     }

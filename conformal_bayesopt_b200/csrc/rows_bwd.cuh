@@ -124,7 +124,7 @@ inline cudaError_t launch_rows_bwd_t(const double* Xq, int n, const double* XsT,
     const int groups = (n + ROWS_CPW - 1) / ROWS_CPW;
     int grid = (groups + ROWS_WARPS - 1) / ROWS_WARPS;
     if (grid > num_sms) grid = num_sms;
-    k_rows_bwd<STAGE><<<grid, ROWS_WARPS * 32, smem, st>>>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, alpha, Aw, W, adj, dX);
+    CBO_LAUNCHED(), k_rows_bwd<STAGE><<<grid, ROWS_WARPS * 32, smem, st>>>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, alpha, Aw, W, adj, dX);
     return cudaGetLastError();
 }
 

@@ -109,9 +109,10 @@ class GPModelState:
         if X.ndim == 3:  # batched multi-output model: (t, N, d)
             X, y = X[output_index], y[output_index]
             ls, os_, noise, mean = ls[output_index], os_[output_index], noise[output_index], mean[output_index]
-        return cls.fit_fixed(X.detach(), y.detach(), float(torch.as_tensor(mean).reshape(-1)[0]),
-                             ls.detach().reshape(-1), float(torch.as_tensor(os_).reshape(-1)[0]),
-                             float(torch.as_tensor(noise).reshape(-1)[0]), device=X.device)
+        def scalar(v):       # never through torch.as_tensor(python float): that rounds to float32
+            return float(v.detach().reshape(-1)[0]) if torch.is_tensor(v) else float(v)
+        return cls.fit_fixed(X.detach(), y.detach(), scalar(mean), ls.detach().reshape(-1), scalar(os_), scalar(noise),
+                             device=X.device)
 
     def append(self, X_new: torch.Tensor, y_new: torch.Tensor, check_pd: bool = True) -> "GPModelState":
         """A NEW state with the observations (X_new (q, d), y_new (q)) added, hyper-parameters unchanged: rank-1 extensions

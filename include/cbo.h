@@ -130,6 +130,9 @@ typedef struct {
 } cbo_outputs_f64;
 
 int cbo_version(void);
+/* Kernels this library has launched since it was loaded (all entry points, all threads): what bench.py reports as
+ * gpu_launches for its timed region. */
+int64_t cbo_launch_count(void);
 const char* cbo_status_str(int status);
 const char* cbo_last_cuda_error(void);
 int64_t cbo_padded_n(int64_t N);
@@ -156,8 +159,9 @@ int cbo_conformal_acq_grad_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ra
                                const double* eps_mc, const double* u_rand, const cbo_outputs_f64* out,
                                double* dacq_dX, void* workspace, size_t workspace_bytes, int64_t chunk, void* stream);
 
-/* Same call with HOST candidate / result buffers (pinned for full speed): H2D of Xq_host and
- * D2H of acq_host are issued on `stream` inside the call; synchronises the stream on return. */
+/* Same call with HOST candidate / result buffers (pinned for full speed), pipelined per internal chunk: the candidates of
+ * chunk k+1 go host -> device and the values of chunk k-1 device -> host on a library-private copy stream (one per
+ * device, created on first use) while chunk k computes on `stream`; both streams are drained before the call returns. */
 int cbo_conformal_acq_host_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* params,
                                const double* Xq_host, int64_t b, const double* eps_grid, const double* z,
                                const double* eps_mc, const double* u_rand, double* acq_host,

@@ -20,11 +20,15 @@ def _cases(name):
     return torch.load(os.path.join(GOLD, name), weights_only=False)
 
 
+def _scalar(v):
+    """python float of a scalar hyper-parameter (NOT via torch.as_tensor(float): that would round it to float32)."""
+    return float(v.reshape(-1)[0]) if torch.is_tensor(v) else float(v)
+
+
 def _state(p):
     from conformal_bayesopt_b200 import GPModelState
-    return GPModelState.fit_fixed(p["X"], p["y"], float(torch.as_tensor(p["mean"]).reshape(-1)[0]), p["lengthscale"],
-                                  float(torch.as_tensor(p["outputscale"]).reshape(-1)[0]),
-                                  float(torch.as_tensor(p["noise"]).reshape(-1)[0]), device=DEV)
+    return GPModelState.fit_fixed(p["X"], p["y"], _scalar(p["mean"]), p["lengthscale"], _scalar(p["outputscale"]),
+                                  _scalar(p["noise"]), device=DEV)
 
 
 def _ratio(c):
