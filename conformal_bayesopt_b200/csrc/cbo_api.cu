@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <vector>
@@ -15,6 +16,7 @@
 #include "gemm_tri.cuh"
 #include "rows.cuh"
 #include "score.cuh"
+#include "score_ws.cuh"
 #include "score_bwd.cuh"
 #include "score_q.cuh"
 #include "mobo.cuh"
@@ -207,9 +209,26 @@ int num_sms() {
     return n;
 }
 
+// CBO_SCORE_WS=0 / 1 forces the pair kernel / the warp-specialised kernel (A/B timing, tests of small batches); unset: by size
+int score_ws_override() {
+    const char* e = getenv("CBO_SCORE_WS");
+    return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
+}
+
 template <bool SOFT>
-cudaError_t launch_score(const cbo::ScoreArgs& a_in, cudaStream_t st) {
+cudaError_t launch_score(const cbo::ScoreArgs& a_in, cudaStream_t st, bool many) {
     cbo::ScoreArgs a = a_in;
+    // a call with many candidates: warp-specialised kernel (4 candidates in flight per SM, helper warps for phases A/C/D)
+    const int ov = score_ws_override();
+    if ((ov == 1 || (ov < 0 && many && SOFT)) && cbo::score_ws_fits(a.Np, a.G)) {   // hard path: the sweep is too short for one helper warp per candidate to keep up
+        const size_t smem = cbo::score_ws_smem_bytes(a.Np, a.G);
+        static cbo::SmemOptIn optin_ws;
+        if (cudaError_t e = optin_ws.ensure(cbo::k_score_ws<SOFT>, smem); e != cudaSuccess) return e;
+        int grid = (a.n_cand + cbo::SWS_GROUPS - 1) / cbo::SWS_GROUPS;
+        if (grid > num_sms()) grid = num_sms();
+        CBO_LAUNCHED(), cbo::k_score_ws<SOFT><<<grid, cbo::SWS_THREADS, smem, st>>>(a);
+        return cudaGetLastError();
+    }
     // warps per candidate: pairs when there are enough candidates to fill the SMs, wider groups for small batches
     int wl = 1;
     while (wl < 4 && a.n_cand * (1 << wl) < 16 * num_sms()) ++wl;
@@ -523,6 +542,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
 
     const int R = (int)p->max_grid_refinements;
     const int q = (int)p->q;
+    const bool many = b >= int64_t(2) * cbo::SWS_GROUPS * num_sms();   // decided per CALL (chunking stays bit-invariant): every group gets >= 2 candidates
     double* splitk = (b * q <= cbo::GEMM_SPLITK_MAX_M) ? w.splitk : nullptr;   // a handful of candidate points in the whole call: split-K GEMMs
     for (int64_t c0 = 0; c0 < b; c0 += C) {
         const int ncand = (int)((b - c0 < C) ? (b - c0) : C);
@@ -557,6 +577,8 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
         a.beta_prime = p->beta_prime; a.best_f = p->best_f;
         a.k_magic = 6755399441055744.0; a.k_c0 = 0.9999999988534117; a.k_c1n = -0.043321698775061875;
         a.k_c2 = 0.0009384214835622084; a.k_c3n = -1.3551125681305332e-05;
+        // monic form of the same cubic (score_rows8): P(y) = c3 (((y + a2) y + a1) y + a0)
+        a.k8_c3 = a.k_c3n; a.k8_a2 = a.k_c2 / a.k_c3n; a.k8_a1 = a.k_c1n / a.k_c3n; a.k8_a0 = a.k_c0 / a.k_c3n;
         a.unit_dr = ratio ? 0 : 1;
         a.kind = p->kind; a.optimistic = p->optimistic; a.randomized = p->randomized;
         a.eps_per_candidate = p->eps_per_candidate;
@@ -587,7 +609,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 }
                 x.ext_values = w.nei_values;
             }
-            if (q == 1) return soft_path ? launch_score<true>(x, s) : launch_score<false>(x, s);
+            if (q == 1) return soft_path ? launch_score<true>(x, s, many) : launch_score<false>(x, s, many);
             cbo::ScoreQArgs y = aq;
             y.base = x;
             return launch_score_q(y, q, soft_path, s);
@@ -770,6 +792,15 @@ int cbo_model_build_f64(const double* X, const double* y, int64_t N, int64_t d, 
                               num_sms(), static_cast<cudaStream_t>(stream)));
     return CBO_OK;
 }
+
+#ifdef CBO_WS_PROFILE
+int cbo_debug_ws_prof(unsigned long long* out8) {   // experiment builds only (tools/score_ab.py): read and clear the counters
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out8, cbo::g_ws_prof, sizeof(z)) != cudaSuccess) return CBO_ERR_CUDA;
+    if (cudaMemcpyToSymbol(cbo::g_ws_prof, z, sizeof(z)) != cudaSuccess) return CBO_ERR_CUDA;
+    return CBO_OK;
+}
+#endif
 
 void cbo_timing_enable(int on) {
     g_timing.enabled = on != 0;

@@ -47,6 +47,8 @@ struct ScoreArgs {
     int unit_dr;            // no ratio estimator: all train-point importance weights are 1
     // sigmoid constants, passed as parameters so that they are constant-bank operands instead of per-iteration moves
     double k_magic, k_c0, k_c1n, k_c2, k_c3n;
+    // the same cubic in the monic form of score_rows8: P(y) = c3 (((y + a2) y + a1) y + a0)
+    double k8_a2, k8_a1, k8_a0, k8_c3;
     // per-call tables (train side)
     const double* a;        // Np  noise*alpha
     const double* h0;       // Np
@@ -197,6 +199,87 @@ __device__ __forceinline__ void score_rows(const ScoreArgs& p, const double* __r
                 pl = fma(pl, yn[k], kC0);                     // exp(-yn ln2/16)
                 double ts = exp_tab_scaled(tab_s, __double2loint(t[k]));   // 2^(j/16) 2^kk
                 e[k] = fma(ts, pl, 1.0);                      // 1 + e: the product and the sum are ONE fma
+            }
+#pragma unroll
+            for (int k = 0; k < GPW; ++k) {
+                double d = e[k];
+                double y0;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+                double err1 = fma(-d, y0, 2.0);               // Newton: rho = y0 (2 - d y0), folded into the running sum
+                if (UNIT) {
+                    sr[k] = fma(y0, err1, sr[k]);
+                } else {
+                    double rho = y0 * err1;
+                    sr[k] += rho;
+                    sw[k] = fma(rho, dr, sw[k]);
+                }
+            }
+        } else if (!UNIT) {
+#pragma unroll
+            for (int k = 0; k < GPW; ++k) sw[k] += (__double2hiint(x[k]) >= 0) ? dr : 0.0;
+        }
+        qa = qa_n; qb = qb_n; qc = qc_n; dr = dr_n;
+    }
+}
+
+// ---- score_rows8: the same sweep, arranged for the REGISTER-FILE read ports -------------------------------------------
+// Measured on B200 (tools/dfma_operands*.cu, profiles/r02_dfma_operands.log): a DFMA that reads three distinct register
+// pairs issues every 3 clocks (66 % of the fp64 pipe), one that reads two (or one) every 2 clocks -- the pipe's own rate;
+// immediates, constant-bank / uniform-register operands and operand-reuse-cache hits are free, and integer instructions
+// pay for their register operands on the same ports.  score_rows spent 149 clocks per (32 train points x 4 grid points)
+// against 88 of fp64-pipe time.  Here the cubic P(y) = exp(-y ln2/16) is evaluated in MONIC form,
+//     P = c3 (((y + a2) y + a1) y + a0),   a_k = c_k / c3,
+// so that every step has ONE constant operand (Horner starts with fma(y, c3, c2): two constants, i.e. two more register
+// pairs per instruction once the constants sit in registers), and c3 is folded into the table: tab8[j] = c3 2^(j/16), so
+// e = 2^(n/16) P(y) is still one fma on the exponent-scaled entry.  Same 11 fp64 instructions per element, ~20 register
+// pairs read instead of 24.  (tools/score_loop_bench.cu times the loop alone with ablations.)
+__device__ __forceinline__ void exp_tab8_init(double* tab, int j, double c3) {
+    double v = c3 * exp2(double(j) / 16.0);
+    tab[j] = __hiloint2double(__double2hiint(v) - (j << 16), __double2loint(v));
+}
+
+template <bool SOFT, bool CLAMP, bool UNIT, int GPW>
+__device__ __forceinline__ void score_rows8(const ScoreArgs& p, const double* __restrict__ sq, const double* __restrict__ sdr,
+                                            unsigned tab_s, int lane, int N32,
+                                            const double (&bg)[GPW], double (&sr)[GPW], double (&sw)[GPW],
+                                            unsigned (&cneg)[GPW]) {
+    const double kMagic = p.k_magic;                          // 1.5 * 2^52
+    const double kA2 = p.k8_a2, kA1 = p.k8_a1, kA0 = p.k8_a0;
+    constexpr int kSatHi = 0x408d9000;                        // hiword(946.0)
+    const double* tq = sq + 3 * lane;
+    const double* td = sdr + lane;
+    double qa = tq[0], qb = tq[1], qc = tq[2], dr = UNIT ? 1.0 : td[0];
+    for (int i = lane; i < N32; i += 32) {
+        tq += 96; td += 32;                                   // next row (reads past N32 stay inside shared memory)
+        const double qa_n = tq[0], qb_n = tq[1], qc_n = tq[2], dr_n = UNIT ? 1.0 : td[0];
+        double x[GPW];
+#pragma unroll
+        for (int k = 0; k < GPW; ++k) x[k] = fma(qa, bg[k], qb);
+#pragma unroll
+        for (int k = 0; k < GPW; ++k) {
+            x[k] = fma(x[k], bg[k], qc);
+            cneg[k] += unsigned(__double2hiint(x[k])) >> 31;  // counts score_c < score_i
+        }
+        if (SOFT) {
+            double t[GPW], y[GPW], e[GPW];
+#pragma unroll
+            for (int k = 0; k < GPW; ++k) {
+                double xc = x[k];
+                if (CLAMP) {
+                    int hi = __double2hiint(x[k]);
+                    int ch = min(hi & 0x7fffffff, kSatHi) | (hi & 0x80000000);
+                    xc = __hiloint2double(ch, __double2loint(x[k]));         // clamp(x, -946, 946)
+                }
+                t[k] = kMagic - xc;                           // low word = -round(x)
+                y[k] = xc + (t[k] - kMagic);                  // x - round(x) in [-1/2, 1/2]
+            }
+#pragma unroll
+            for (int k = 0; k < GPW; ++k) {
+                double pl = y[k] + kA2;
+                pl = fma(pl, y[k], kA1);
+                pl = fma(pl, y[k], kA0);                      // exp(-y ln2/16) / c3
+                double ts = exp_tab_scaled(tab_s, __double2loint(t[k]));     // c3 2^(j/16) 2^kk (tab_s: the tab8 table)
+                e[k] = fma(ts, pl, 1.0);                      // 1 + e
             }
 #pragma unroll
             for (int k = 0; k < GPW; ++k) {

@@ -1,0 +1,128 @@
+// score_loop_bench.cu -- the phase-B hot loop of k_score / k_score_ws in isolation (16 warps per SM, tables in shared memory),
+// with compile-time ablations, to find what bounds it:  nvcc -DVAR=<n> ...   prints clocks per (32 train points x 4 grid
+// points) warp step per SM sub-partition (fp64 pipe alone: 44 instructions x 2 = 88).
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -cudart shared -DVAR=0 -o tools/score_loop_bench tools/score_loop_bench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../conformal_bayesopt_b200/csrc/score.cuh"
+#ifndef VAR
+#define VAR 0
+#endif
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
+using namespace cbo;
+
+template <int V>
+__device__ __forceinline__ void rows(const ScoreArgs& p, const double* __restrict__ sq, unsigned tab_s, unsigned tab8_s, int lane, int N32,
+                                     const double (&bg)[4], double (&sr)[4], unsigned (&cneg)[4]) {
+    if (V == 20) {            // the round-1 loop
+        double sw[4] = {0, 0, 0, 0};
+        score_rows<true, false, true, 4>(p, sq, sq, tab_s, lane, N32, bg, sr, sw, cneg);
+        return;
+    }
+    if (V == 0) {             // the loop the kernels use
+        double sw[4] = {0, 0, 0, 0};
+        score_rows8<true, false, true, 4>(p, sq, sq, tab8_s, lane, N32, bg, sr, sw, cneg);
+        return;
+    }
+    const double kMagic = p.k_magic, kA2 = p.k8_a2, kA1 = p.k8_a1, kA0 = p.k8_a0;
+    const double* tq = sq + 3 * lane;
+    double qa = tq[0], qb = tq[1], qc = tq[2];
+    for (int i = lane; i < N32; i += 32) {
+        tq += 96;
+        const double qa_n = tq[0], qb_n = tq[1], qc_n = tq[2];
+        double x[4], t[4], y[4], e[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = fma(qa, bg[k], qb);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            x[k] = fma(x[k], bg[k], qc);
+            if (V != 1 && V != 5) cneg[k] += unsigned(__double2hiint(x[k])) >> 31;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            t[k] = kMagic - x[k];
+            y[k] = x[k] + (t[k] - kMagic);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double pl = y[k] + kA2;
+            pl = fma(pl, y[k], kA1);
+            pl = fma(pl, y[k], kA0);
+            double ts;
+            if (V == 2 || V == 5) ts = __hiloint2double(0xbee00000 + (__double2loint(t[k]) << 16), 0);   // no table load
+            else ts = exp_tab_scaled(tab8_s, __double2loint(t[k]));
+            e[k] = fma(ts, pl, 1.0);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double d = e[k], y0;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+            double err1 = fma(-d, y0, 2.0);
+            sr[k] = fma(y0, err1, sr[k]);
+        }
+        qa = qa_n; qb = qb_n; qc = qc_n;
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) k(const ScoreArgs p, const double* coef, double* out, int passes) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ __align__(128) double tab8[16];
+    __shared__ __align__(128) double tab[16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 16) { exp_tab8_init(tab8, tid, p.k8_c3); exp_tab_init(tab, tid); }
+    double* sq = sm + size_t(warp >> 1) * (3 * 1024 + 96);
+    for (int i = tid & 63; i < 3 * 1024 + 96; i += 64) sq[i] = coef[i % (3 * 1024)];
+    __syncthreads();
+    double tot = 0.0;
+    unsigned ctot = 0;
+    for (int ps = 0; ps < passes; ++ps) {
+        double bg[4], sr[4] = {0, 0, 0, 0};
+        unsigned cneg[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) bg[kk] = 0.01 * ((ps * 4 + kk + warp) % 64) - 0.3;
+        rows<VAR>(p, sq, smem_u32(tab), smem_u32(tab8), lane, 1024, bg, sr, cneg);
+        tot += sr[0] + sr[1] + sr[2] + sr[3];
+        ctot += cneg[0] + cneg[1] + cneg[2] + cneg[3];
+    }
+    out[blockIdx.x * 512 + tid] = tot + ctot;
+}
+
+int main() {
+    cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
+    const int sms = pr.multiProcessorCount;
+    ScoreArgs a; memset(&a, 0, sizeof(a));
+    const double c0 = 0.9999999988534117, c1n = -0.043321698775061875, c2 = 0.0009384214835622084, c3n = -1.3551125681305332e-05;
+    a.k_magic = 6755399441055744.0; a.k_c0 = c0; a.k_c1n = c1n; a.k_c2 = c2; a.k_c3n = c3n;
+    a.k8_c3 = c3n; a.k8_a2 = c2 / c3n; a.k8_a1 = c1n / c3n; a.k8_a0 = c0 / c3n;
+    static double h[3 * 1024];
+    for (int i = 0; i < 1024; ++i) { h[3 * i] = -40.0 - 0.01 * i; h[3 * i + 1] = 3.0 + 0.001 * i; h[3 * i + 2] = 20.0 * ((i % 17) - 8); }
+    double *coef, *out;
+    CK(cudaMalloc(&coef, sizeof(h))); CK(cudaMemcpy(coef, h, sizeof(h), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&out, sizeof(double) * sms * 512));
+    const size_t smem = sizeof(double) * 8 * (3 * 1024 + 96);
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int passes = 400;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k<<<sms, 512, smem>>>(a, coef, out, passes);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 3; ++r) {
+        cudaEventRecord(e0); k<<<sms, 512, smem>>>(a, coef, out, passes); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    double hsum = 0; static double ho[512]; CK(cudaMemcpy(ho, out, sizeof(ho), cudaMemcpyDeviceToHost)); for (double v : ho) hsum += v;
+    // per sub-partition: 4 warps x passes x 32 steps
+    {   // host reference of thread 0's total: train points 0, 32, 64, ... x every pass' 4 grid points (warp 0)
+        double ref = 0; long cnt = 0;
+        for (int ps = 0; ps < passes; ++ps) for (int kk = 0; kk < 4; ++kk) {
+            double bgv = 0.01 * ((ps * 4 + kk + 0) % 64) - 0.3;
+            for (int i = 0; i < 1024; i += 32) {
+                double x = fma(fma(h[3 * i], bgv, h[3 * i + 1]), bgv, h[3 * i + 2]);
+                ref += 1.0 / (1.0 + exp(-x * 0.6931471805599453 / 16.0)); cnt += x < 0;
+            }
+        }
+        printf("thread 0: device %.12e  host reference %.12e (rho sum %+.3e, count %ld)\n", ho[0], ref + cnt, ho[0] - ref - cnt, cnt);
+    }
+    printf("VAR %d: %.3f ms  %.1f clk per warp step per sub-partition  (checksum %.6e)\n", VAR, best, best * pr.clockRate / (4.0 * passes * 32), hsum);
+    return 0;
+}
