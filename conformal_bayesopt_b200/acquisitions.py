@@ -16,6 +16,7 @@ posterior transforms, gradients for cNEI / cEHVI.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -72,6 +73,9 @@ class ConformalAcquisition(nn.Module):
         # candidate-sharded scoring with max_grid_refinements > 0: distributed.refine_reducer() makes the refinement
         # decisions batch-global again; None: per-call statistics
         self.refine_reduce = None
+        # the plain cUCB / cEI call goes through the dispatcher-registered operator torch.ops.cbo.conformal_acq (csrc/torch_ext.cpp,
+        # Autograd kernel included); False (or CBO_NO_TORCH_EXT=1): the ctypes binding of the same C entry points
+        self.use_torch_ops = os.environ.get("CBO_NO_TORCH_EXT", "0") != "1"
         self.last_outputs = {}
 
     def set_X_pending(self, X_pending=None):
@@ -150,6 +154,15 @@ class ConformalAcquisition(nn.Module):
         u = self.fixed_uniforms
         if self.randomized and u is None:
             u = torch.rand(b, G, q, dtype=torch.float64, device=dev)
+        rr = self.refine_reduce if self.max_grid_refinements > 0 else None
+        if self.use_torch_ops and self._kind in ("ucb", "ei") and not outputs and not raw_grad and rr is None:
+            from . import torch_ops
+            acq = torch_ops.conformal_acq(state, X.reshape(-1, q, d).to(torch.float64), eps_grid=eps, z=z, eps_mc=eps_mc, u_rand=u,
+                                          ratio=_ratio_weights(self.ratio_estimator, dev), alpha=self.alpha, temp=self.temp,
+                                          grid_res=G, max_grid_refinements=self.max_grid_refinements,
+                                          randomized=self.randomized, optimistic=self.optimistic, **self._acq_params())
+            self.last_outputs = {"acq": acq.detach()}
+            return acq.reshape(lead).to(X.dtype)
         out = ops.conformal_acq(state, Xf, eps_grid=eps, z=z, eps_mc=eps_mc, u_rand=u,
                                 ratio=_ratio_weights(self.ratio_estimator, dev), outputs=outputs, want_grad=want_grad,
                                 refine_reduce=self.refine_reduce if self.max_grid_refinements > 0 else None,

@@ -65,3 +65,19 @@ def test_ops_refuse_cpu_tensors():
     from conformal_bayesopt_b200 import _lib, ops
     with pytest.raises(_lib.CboError):
         ops.conf_mask_to_bounds(torch.zeros(2, 4, 1, 1, dtype=torch.float64), torch.zeros(2, 4, 1, 1, dtype=torch.float64))
+
+
+def test_torch_extension_builds_loads_and_registers_its_operators():
+    """lib/libcbo_torch.so (csrc/torch_ext.cpp): TORCH_LIBRARY(cbo) schemas are visible without a GPU; a CPU tensor finds no
+    kernel (there is no CPU path to fall back to)."""
+    import pytest
+    import torch
+    from conformal_bayesopt_b200 import torch_ops
+    t = torch_ops.load()
+    for name in ("conformal_acq", "conformal_acq_raw", "model_build", "conf_mask_to_bounds", "ratio_forward", "ratio_train_step",
+                 "sgld_update"):
+        assert hasattr(t, name), name
+    schema = str(torch._C._jit_get_schemas_for_operator("cbo::conformal_acq")[0])
+    assert "Tensor Xq" in schema and "Tensor? u_rand" in schema and schema.endswith("-> Tensor")
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        t.conf_mask_to_bounds(torch.zeros(2, 4, 1, 1, dtype=torch.float64), torch.zeros(2, 4, 1, 1, dtype=torch.float64))

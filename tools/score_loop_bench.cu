@@ -27,16 +27,20 @@ __device__ __forceinline__ void rows(const ScoreArgs& p, const double* __restric
     const double kMagic = p.k_magic, kA2 = p.k8_a2, kA1 = p.k8_a1, kA0 = p.k8_a0;
     const double* tq = sq + 3 * lane;
     double qa = tq[0], qb = tq[1], qc = tq[2];
-    for (int i = lane; i < N32; i += 32) {
+    double bgu[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bgu[k] = (V == 30 || V == 31) ? __shfl_sync(0xffffffffu, bg[k], 0) : bg[k];
+    const int nsteps = N32 >> 5;
+    for (int it = 0; it < nsteps; ++it) {
         tq += 96;
         const double qa_n = tq[0], qb_n = tq[1], qc_n = tq[2];
         double x[4], t[4], y[4], e[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) x[k] = fma(qa, bg[k], qb);
+        for (int k = 0; k < 4; ++k) x[k] = fma(qa, bgu[k], qb);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            x[k] = fma(x[k], bg[k], qc);
-            if (V != 1 && V != 5) cneg[k] += unsigned(__double2hiint(x[k])) >> 31;
+            x[k] = fma(x[k], bgu[k], qc);
+            if (V != 1 && V != 5 && V != 31) cneg[k] += unsigned(__double2hiint(x[k])) >> 31;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -49,7 +53,7 @@ __device__ __forceinline__ void rows(const ScoreArgs& p, const double* __restric
             pl = fma(pl, y[k], kA1);
             pl = fma(pl, y[k], kA0);
             double ts;
-            if (V == 2 || V == 5) ts = __hiloint2double(0xbee00000 + (__double2loint(t[k]) << 16), 0);   // no table load
+            if (V == 2 || V == 5 || V == 31) ts = __hiloint2double(0xbee00000 + (__double2loint(t[k]) << 16), 0);   // no table load
             else ts = exp_tab_scaled(tab8_s, __double2loint(t[k]));
             e[k] = fma(ts, pl, 1.0);
         }
