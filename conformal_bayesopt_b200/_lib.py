@@ -13,7 +13,7 @@ EXPORTS = [
     "cbo_version", "cbo_status_str", "cbo_last_cuda_error", "cbo_padded_n", "cbo_workspace_bytes",
     "cbo_conformal_acq_f64", "cbo_conformal_acq_host_f64", "cbo_conf_mask_to_bounds_f64",
     "cbo_ratio_forward_f64", "cbo_gemm_tn_f64", "cbo_kernel_rows_f64", "cbo_timing_enable", "cbo_timing_collect",
-    "cbo_cehvi_integrate_f64", "cbo_conformal_acq_grad_f64", "cbo_workspace_bytes_grad",
+    "cbo_cehvi_integrate_f64", "cbo_cehvi_integrate_q_f64", "cbo_conformal_acq_grad_f64", "cbo_workspace_bytes_grad",
     "cbo_model_workspace_bytes", "cbo_model_build_f64",
     "cbo_model_append_workspace_bytes", "cbo_model_append_f64",
     "cbo_ratio_train_workspace_bytes", "cbo_ratio_train_step_f64", "cbo_sgld_update_f64", "cbo_launch_count",
@@ -51,7 +51,7 @@ REFINE_REDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_void_p)
 class OutputsF64(C.Structure):
     _fields_ = [(n, c_dp) for n in ("acq", "target_grid", "grid_logp", "conf_pred_mask", "ood_mask",
                                      "q_conf_scores", "post_mean", "post_var", "num_accepted", "refit_mean",
-                                     "refit_sd")]
+                                     "refit_sd", "mc_values")]
 
 
 class CboError(RuntimeError):
@@ -112,6 +112,10 @@ def load():
     lib.cbo_cehvi_integrate_f64.restype = C.c_int
     lib.cbo_cehvi_integrate_f64.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64, PP, PP, PP, PP, PP, PP, PP, c_dp,
                                             c_dp, c_dp, C.c_int64, C.c_double, C.c_int32, c_dp, c_dp]
+    lib.cbo_cehvi_integrate_q_f64.restype = C.c_int
+    lib.cbo_cehvi_integrate_q_f64.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, PP, PP, PP, PP, PP, PP,
+                                              C.POINTER(C.c_double), PP, c_dp, c_dp, c_dp, C.c_int64, C.c_int32, C.c_double,
+                                              C.c_int32, c_dp, c_dp, c_dp]
     lib.cbo_model_workspace_bytes.restype = C.c_size_t
     lib.cbo_model_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
     lib.cbo_model_build_f64.restype = C.c_int
@@ -135,7 +139,7 @@ def load():
     lib.cbo_timing_enable.argtypes = [C.c_int]
     lib.cbo_timing_collect.restype = C.c_int
     lib.cbo_timing_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
-    if lib.cbo_version() != 100:
+    if lib.cbo_version() != 101:
         raise CboError(f"libcbo.so version mismatch: {lib.cbo_version()}")
     _LIB = lib
     return lib

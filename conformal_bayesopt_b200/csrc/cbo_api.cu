@@ -133,7 +133,7 @@ Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, 
     w.nacc = c.take<double>(R > 0 ? b * p->q : 1);
     w.acq_scratch = c.take<double>(R > 0 ? b : 1);
     w.stats = c.take<double>(8);
-    w.nei_values = c.take<double>(p->kind == CBO_ACQ_NEI ? C * p->num_mc * p->grid_res : 1);
+    w.nei_values = c.take<double>((p->kind == CBO_ACQ_NEI || p->kind == CBO_ACQ_JOINT) ? C * p->num_mc * p->grid_res : 1);
     w.splitk = c.take<double>(cbo::gemm_splitk_scratch_doubles((int)Np));
     w.X3 = c.take<double>(grad ? C * Np : 1);
     w.adj = c.take<double>(grad ? C * (cbo::ADJQ_STRIDE > cbo::ADJ_STRIDE ? cbo::ADJQ_STRIDE : cbo::ADJ_STRIDE) : 1);
@@ -182,8 +182,8 @@ int validate(const cbo_gp_f64* gp, const cbo_params* p, int64_t b) {
     if (!gp->X || !gp->alpha || !gp->linv || !gp->linv_t || !gp->inv_lengthscale) return CBO_ERR_INVALID_ARG;
     if (gp->N <= 0 || gp->d <= 0 || gp->Np != cbo_padded_n(gp->N)) return CBO_ERR_INVALID_ARG;
     if (p->grid_res < 2) return CBO_ERR_INVALID_ARG;                       // helpers.py:113
-    if (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI && p->kind != CBO_ACQ_NEI) return CBO_ERR_INVALID_ARG;
-    if (p->kind == CBO_ACQ_NEI) {
+    if (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI && p->kind != CBO_ACQ_NEI && p->kind != CBO_ACQ_JOINT) return CBO_ERR_INVALID_ARG;
+    if (p->kind == CBO_ACQ_NEI || p->kind == CBO_ACQ_JOINT) {
         if (!p->nei || !p->nei->Xb || !p->nei->KbX || !p->nei->Sbb || !p->nei->mub || p->nei->nb < 1) return CBO_ERR_INVALID_ARG;
         if (p->nei->nb > cbo::NEI_MAX_NB || p->nei->nb + p->q > 32) return CBO_ERR_UNSUPPORTED;
     }
@@ -342,6 +342,14 @@ cudaError_t launch_score_q(const cbo::ScoreQArgs& a, int q, bool soft, cudaStrea
         case 4: return soft ? launch_score_q_t<4, true>(a, st) : launch_score_q_t<4, false>(a, st);
         default: return cudaErrorInvalidValue;
     }
+}
+
+template <int Q>
+cudaError_t launch_ehvi_q(const cbo::EhviQArgs& a, size_t smem, cudaStream_t st) {
+    static cbo::SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(cbo::k_ehvi_q<Q>, smem); e != cudaSuccess) return e;
+    CBO_LAUNCHED(), cbo::k_ehvi_q<Q><<<(a.b + cbo::EHVIQ_WARPS - 1) / cbo::EHVIQ_WARPS, cbo::EHVIQ_WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -593,21 +601,22 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
         aq.post_cov = (q > 1 && out->post_var) ? out->post_var + c0 * q * q : nullptr;
         auto run_score = [&](const cbo::ScoreArgs& x_in) -> cudaError_t {
             cbo::ScoreArgs x = x_in;
-            if (p->kind == CBO_ACQ_NEI) {
+            if (p->kind == CBO_ACQ_NEI || p->kind == CBO_ACQ_JOINT) {
                 cbo::NeiArgs na;
                 na.N = N; na.Np = Np; na.d = d; na.nb = (int)p->nei->nb; na.G = G; na.S = (int)p->num_mc; na.n_cand = ncand;
                 na.tiles_n = tiles_n; na.noise = gp->noise; na.kappa = gp->outputscale; na.temp = p->temp;
                 na.Xq = Xc; na.inv_ls = gp->inv_lengthscale; na.Xb = p->nei->Xb; na.KbX = p->nei->KbX; na.Sbb = p->nei->Sbb;
                 na.mub = p->nei->mub; na.W = w.UW; na.rn_partial = w.rn; na.mu = w.mu; na.cscale = x.cscale;
                 na.eps_grid = x.eps_grid; na.eps_per_candidate = x.eps_per_candidate; na.eps_mc = eps_mc;
-                na.values = w.nei_values;
+                na.values = out->mc_values ? out->mc_values + c0 * q * int64_t(p->num_mc) * G : w.nei_values;
+                na.raw = p->kind == CBO_ACQ_JOINT;
                 na.V = w.V;
                 if (q == 1) CBO_LAUNCHED(), cbo::k_nei_values<<<(ncand + 3) / 4, 128, 0, s>>>(na);
                 else {
                     cudaError_t e = cbo::launch_nei_values_q(na, q, s);
                     if (e != cudaSuccess) return e;
                 }
-                x.ext_values = w.nei_values;
+                x.ext_values = na.values;
             }
             if (q == 1) return soft_path ? launch_score<true>(x, s, many) : launch_score<false>(x, s, many);
             cbo::ScoreQArgs y = aq;
@@ -771,6 +780,45 @@ int cbo_cehvi_integrate_f64(int64_t m, int64_t b, int64_t G, int64_t S, const do
     CBO_CUDA(optin.ensure(cbo::k_ehvi, smem));
     CBO_LAUNCHED(), cbo::k_ehvi<<<(int)((b + 7) / 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
     CBO_CUDA(cudaGetLastError());
+    return CBO_OK;
+}
+
+int cbo_cehvi_integrate_q_f64(int64_t m, int64_t b, int64_t G, int64_t S, int64_t q, const double* const* mask,
+                              const double* const* logp, const double* const* grid, const double* const* mu,
+                              const double* const* ood, const double* const* cov, const double* noise_host,
+                              const double* const* fx, const double* eps_mc, const double* cell_lower,
+                              const double* cell_upper, int64_t n_cells, int32_t cells_per_sample, double alpha,
+                              int32_t optimistic, double* acq, double* values_out, void* stream) {
+    if (!mask || !logp || !grid || !mu || !ood || !cell_lower || !cell_upper || !acq) return CBO_ERR_INVALID_ARG;
+    if (m < 1 || b <= 0 || G < 2 || S < 1 || n_cells < 1 || q < 1) return CBO_ERR_INVALID_ARG;
+    if (!fx && (!cov || !noise_host || !eps_mc)) return CBO_ERR_INVALID_ARG;
+    if (m > cbo::MAX_M || q > cbo::MAX_Q) return CBO_ERR_UNSUPPORTED;
+    const int64_t ncell_tot = n_cells * (cells_per_sample ? S : 1);
+    const size_t smem = cbo::ehvi_q_smem_bytes((int)m, (int)q, (int)ncell_tot);
+    if (smem > 200 * 1024) return CBO_ERR_UNSUPPORTED;
+    cbo::EhviQArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = (int)m; a.b = (int)b; a.G = (int)G; a.S = (int)S; a.q = (int)q; a.n_cells = (int)n_cells; a.optimistic = optimistic;
+    a.cells_per_sample = cells_per_sample; a.alpha_lvl = alpha;
+    for (int k = 0; k < m; ++k) {
+        if (!mask[k] || !logp[k] || !grid[k] || !mu[k] || !ood[k]) return CBO_ERR_INVALID_ARG;
+        a.mask[k] = mask[k]; a.logp[k] = logp[k]; a.grid[k] = grid[k]; a.mu[k] = mu[k]; a.ood[k] = ood[k];
+        a.fx[k] = fx ? fx[k] : nullptr;
+        if (!a.fx[k]) {
+            if (!cov || !cov[k] || !noise_host || !eps_mc) return CBO_ERR_INVALID_ARG;
+            a.cov[k] = cov[k]; a.noise[k] = noise_host[k];
+        }
+    }
+    a.eps_mc = eps_mc; a.cell_lower = cell_lower; a.cell_upper = cell_upper; a.acq = acq; a.values = values_out;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    switch (q) {
+        case 1: e = launch_ehvi_q<1>(a, smem, st); break;
+        case 2: e = launch_ehvi_q<2>(a, smem, st); break;
+        case 3: e = launch_ehvi_q<3>(a, smem, st); break;
+        default: e = launch_ehvi_q<4>(a, smem, st); break;
+    }
+    CBO_CUDA(e);
     return CBO_OK;
 }
 

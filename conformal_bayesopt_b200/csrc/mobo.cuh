@@ -86,4 +86,194 @@ k_ehvi(const EhviArgs p) {
         p.acq[c] = (1.0 - ood) * ((1.0 - p.alpha_lvl) * A / fmax(scw, 1e-6) + p.alpha_lvl * B / fmax(snc, 1e-6));
 }
 
+// ---- joint batches (q <= 4, incl. pending points) and per-sample cells (cNEHVI) -----------------------------------------
+// k_ehvi_q: the same integration for q candidate points evaluated jointly.  Per output k the per-output call
+// (k_score / k_score_q) supplies mask (b x G x q), the joint log-density (b x G), the grid, mu, ood and the q x q Schur
+// complement S_k; the refit posterior at the candidates is  mean = mu + (I - noise S^-1)(y_g - mu),
+// cov = noise (I - noise sym(S^-1))  (SURVEY.md App. A-6/A-8), sampled with the lower Cholesky factor and the base samples
+// eps_mc (S x G x q x m).  Masks / optimistic masks / ood multiply over outputs AND over the q points, log-densities add
+// (acquisitions.py:230-235 collapse every trailing axis), the value is botorch's _compute_qehvi: per cell, inclusion-
+// exclusion over the non-empty subsets J of the q points of  prod_k clamp(min(min_{j in J} f_jk, u_k) - l_k, 0), summed
+// over cells, averaged over the MC samples (App. B-9).
+// cNEHVI (mobo_acquisitions.py:196-213): the samples f(X) come from the JOINT refit posterior over [X_baseline; X] of every
+// output (k_nei_values*, raw-sample mode: fx[k], b x S x G x q) and every MC sample s has its own box decomposition
+// (cells_per_sample: cell_lower / cell_upper are S x n_cells x m).
+template <int Q>
+__device__ __forceinline__ bool small_chol(const double* A, double* L) {      // row-major Q x Q, lower triangle of A read
+    bool ok = true;
+    for (int j = 0; j < Q; ++j) {
+        double dsum = A[j * Q + j];
+        for (int k = 0; k < j; ++k) dsum -= L[j * Q + k] * L[j * Q + k];
+        ok = ok && (dsum > 0.0);
+        const double ljj = sqrt(dsum);
+        L[j * Q + j] = ljj;
+        for (int i = 0; i < Q; ++i) {
+            if (i < j) L[i * Q + j] = 0.0;
+            if (i > j) {
+                double s = A[i * Q + j];
+                for (int k = 0; k < j; ++k) s -= L[i * Q + k] * L[j * Q + k];
+                L[i * Q + j] = s / ljj;
+            }
+        }
+    }
+    return ok;
+}
+
+struct EhviQArgs {
+    int m, b, G, S, q, n_cells, optimistic, cells_per_sample;
+    double alpha_lvl;
+    double noise[MAX_M];
+    const double* mask[MAX_M];     // b x G x q
+    const double* logp[MAX_M];     // b x G
+    const double* grid[MAX_M];     // b x G x q
+    const double* mu[MAX_M];       // b x q
+    const double* ood[MAX_M];      // b x q
+    const double* cov[MAX_M];      // b x q x q   S = K_qq + noise I - V^T V  (internal sampling; unused with fx)
+    const double* fx[MAX_M];       // b x S x G x q  joint-posterior samples of f(X) (cNEHVI) or nullptr
+    const double* eps_mc;          // S x G x q x m  (internal sampling)
+    const double* cell_lower;      // [S x] n_cells x m
+    const double* cell_upper;
+    double* acq;                   // b
+    double* values;                // b x G or nullptr: MC-averaged hyper-volume improvement per grid point
+};
+
+constexpr int EHVIQ_WARPS = 8;
+
+template <int Q>
+__global__ void __launch_bounds__(EHVIQ_WARPS * 32)
+k_ehvi_q(const EhviQArgs p) {
+    extern __shared__ double s_dyn[];              // cells: lower | upper ; then per warp: m x (shr[Q*Q], Lf[Q*Q])
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = p.m, G = p.G, S = p.S;
+    const int ncell_tot = p.n_cells * (p.cells_per_sample ? S : 1);
+    for (int e = threadIdx.x; e < ncell_tot * m; e += blockDim.x) {
+        s_dyn[e] = p.cell_lower[e];
+        s_dyn[ncell_tot * m + e] = p.cell_upper[e];
+    }
+    const double* lo = s_dyn;
+    const double* up = s_dyn + ncell_tot * m;
+    double* wmat = s_dyn + 2 * ncell_tot * m + size_t(warp) * MAX_M * 2 * Q * Q;
+    __syncthreads();
+    const int c = blockIdx.x * EHVIQ_WARPS + warp;
+    if (c >= p.b) return;
+    int bad = 0;
+    if (lane < m && !p.fx[lane]) {                 // one lane per output: shrinkage and refit factor of this candidate batch
+        const int k = lane;
+        double Sm[Q * Q], Ls[Q * Q], Li[Q * Q], Si[Q * Q], Cf[Q * Q];
+        for (int e = 0; e < Q * Q; ++e) Sm[e] = p.cov[k][int64_t(c) * Q * Q + e];
+        bad |= !small_chol<Q>(Sm, Ls);
+        for (int j = 0; j < Q; ++j)                // L^-1 (lower)
+            for (int i = 0; i < Q; ++i) {
+                if (i < j) Li[i * Q + j] = 0.0;
+                else if (i == j) Li[i * Q + j] = 1.0 / Ls[i * Q + i];
+                else {
+                    double s = 0.0;
+                    for (int kk = j; kk < i; ++kk) s += Ls[i * Q + kk] * Li[kk * Q + j];
+                    Li[i * Q + j] = -s / Ls[i * Q + i];
+                }
+            }
+        for (int i = 0; i < Q; ++i)
+            for (int j = 0; j < Q; ++j) {
+                double s = 0.0;
+                for (int kk = 0; kk < Q; ++kk) s += Li[kk * Q + i] * Li[kk * Q + j];
+                Si[i * Q + j] = s;
+            }
+        const double nz = p.noise[k];
+        double* shr = wmat + size_t(k) * 2 * Q * Q;
+        double* Lf = shr + Q * Q;
+        for (int i = 0; i < Q; ++i)
+            for (int j = 0; j < Q; ++j) {
+                shr[i * Q + j] = ((i == j) ? 1.0 : 0.0) - nz * Si[i * Q + j];
+                Cf[i * Q + j] = nz * (((i == j) ? 1.0 : 0.0) - nz * 0.5 * (Si[i * Q + j] + Si[j * Q + i]));
+            }
+        if (Q == 1) { Lf[0] = sqrt(fmax(Cf[0], 0.0)); }
+        else bad |= !small_chol<Q>(Cf, Lf);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    __syncwarp();
+    double ood = 1.0;
+    for (int k = 0; k < m; ++k)
+        for (int j = 0; j < Q; ++j) ood *= p.ood[k][int64_t(c) * Q + j];
+    double scw = 0.0, snc = 0.0, A = 0.0, B = 0.0;
+    for (int g = lane; g < G; g += 32) {
+        double mk = 1.0, op = 1.0, lp = 0.0;
+        double mf[MAX_M][Q];
+        for (int k = 0; k < m; ++k) {
+            const int64_t ix = (int64_t(c) * G + g) * Q;
+            lp += p.logp[k][int64_t(c) * G + g];
+            double dev[Q];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                const double muj = p.mu[k][int64_t(c) * Q + j], yg = p.grid[k][ix + j];
+                mk *= p.mask[k][ix + j];
+                if (p.optimistic) op *= (yg >= muj) ? 1.0 : 0.0;
+                dev[j] = yg - muj;
+                mf[k][j] = muj;
+            }
+            if (!p.fx[k]) {
+                const double* shr = wmat + size_t(k) * 2 * Q * Q;
+#pragma unroll
+                for (int j = 0; j < Q; ++j)
+#pragma unroll
+                    for (int l = 0; l < Q; ++l) mf[k][j] = fma(shr[j * Q + l], dev[l], mf[k][j]);
+            }
+        }
+        double val = 0.0;
+        for (int s = 0; s < S; ++s) {
+            double f[MAX_M][Q];
+            for (int k = 0; k < m; ++k) {
+                if (p.fx[k]) {
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) f[k][j] = p.fx[k][((int64_t(c) * S + s) * G + g) * Q + j];
+                } else {
+                    const double* Lf = wmat + size_t(k) * 2 * Q * Q + Q * Q;
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) {
+                        double a = mf[k][j];
+#pragma unroll
+                        for (int l = 0; l < Q; ++l)
+                            if (l <= j) a = fma(Lf[j * Q + l], p.eps_mc[((int64_t(s) * G + g) * Q + l) * m + k], a);
+                        f[k][j] = a;
+                    }
+                }
+            }
+            const double* los = lo + (p.cells_per_sample ? size_t(s) * p.n_cells * m : 0);
+            const double* ups = up + (p.cells_per_sample ? size_t(s) * p.n_cells * m : 0);
+            double hv = 0.0;
+            for (int sub = 1; sub < (1 << Q); ++sub) {          // inclusion-exclusion over the non-empty subsets of the q points
+                double vmin[MAX_M];
+                for (int k = 0; k < m; ++k) {
+                    double v = INFINITY;
+#pragma unroll
+                    for (int j = 0; j < Q; ++j)
+                        if ((sub >> j) & 1) v = fmin(v, f[k][j]);
+                    vmin[k] = v;
+                }
+                double tot = 0.0;
+                for (int cell = 0; cell < p.n_cells; ++cell) {
+                    double vol = 1.0;
+                    for (int k = 0; k < m; ++k) vol *= fmax(fmin(vmin[k], ups[cell * m + k]) - los[cell * m + k], 0.0);
+                    tot += vol;
+                }
+                hv += (__popc(sub) & 1) ? tot : -tot;
+            }
+            val += hv;
+        }
+        val /= double(S);
+        if (p.values) p.values[int64_t(c) * G + g] = bad ? nan("") : val;
+        const double cw = mk * op / fmax(exp(lp), 1e-6), nc = (1.0 - mk) * op;
+        scw += cw; snc += nc;
+        A = fma(cw, val, A); B = fma(nc, val, B);
+    }
+    scw = warp_sum(scw); snc = warp_sum(snc); A = warp_sum(A); B = warp_sum(B);
+    if (lane == 0) {
+        const double r = (1.0 - ood) * ((1.0 - p.alpha_lvl) * A / fmax(scw, 1e-6) + p.alpha_lvl * B / fmax(snc, 1e-6));
+        p.acq[c] = bad ? nan("") : r;
+    }
+}
+
+inline size_t ehvi_q_smem_bytes(int m, int q, int n_cells_total) {
+    return sizeof(double) * (size_t(2) * n_cells_total * m + size_t(EHVIQ_WARPS) * MAX_M * 2 * q * q);
+}
+
 }  // namespace cbo

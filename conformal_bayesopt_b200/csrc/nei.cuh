@@ -34,6 +34,7 @@ struct NeiArgs {
     int eps_per_candidate;
     const double* eps_mc;    // S x G x (nb+1)
     double* values;          // n_cand x S x G (x q)
+    int raw;                 // 1: write the joint-posterior samples f(x) themselves (cNEHVI), 0: the noisy-EI improvement
     const double* V;         // joint batches only: rows x Np (v = L^-1 u); rows = n_cand * q
 };
 
@@ -120,6 +121,7 @@ k_nei_values(const NeiArgs p) {
         } else {
             val = fmax(fx - mx, 0.0);
         }
+        if (p.raw) val = fx;
         p.values[(int64_t(c) * p.S + smp) * p.G + g] = ok ? val : nan("");
     }
 }
@@ -307,6 +309,7 @@ k_nei_values_q(const NeiArgs p) {
             } else {
                 val = fmax(fx[j] - smax, 0.0);
             }
+            if (p.raw) val = fx[j];
             p.values[((int64_t(c) * p.S + smp) * p.G + g) * Q + j] = ok ? val : nan("");
         }
     }

@@ -1,9 +1,11 @@
 """Multi-objective conformal acquisition (reference: conformalbo/mobo_acquisitions.py:24-45).
 
-`qConformalExpectedHypervolumeImprovement.forward(X: b x 1 x d) -> Tensor(b)`: one cbo_conformal_acq_f64 call per
-objective (independent GPs) and one cbo_cehvi_integrate_f64.  The reference's EHVI integration is shape-broken
+`qConformalExpectedHypervolumeImprovement.forward(X: b x q x d) -> Tensor(b)`: one cbo_conformal_acq_f64 call per
+objective (independent GPs) and one cbo_cehvi_integrate_q_f64.  The reference's EHVI integration is shape-broken
 (raises unless b in {1, G}) and scrambles multi-output labels (App. C-6); this implements the
-intent -- see oracle/mobo.py.  Built: q = 1, max_grid_refinements = 0.  cNEHVI is a "next" row.
+intent -- see oracle/mobo.py.  Joint batches q <= 4 incl. pending points; `qConformalNoisyExpectedHypervolumeImprovement`
+(mobo_acquisitions.py:184-219) samples f(X) jointly with the baseline under every refit model and carries one box
+decomposition per MC sample.
 """
 from __future__ import annotations
 
@@ -38,6 +40,13 @@ def box_decomposition_2d(ref_point: torch.Tensor, Y: torch.Tensor):
 
 
 class qConformalExpectedHypervolumeImprovement(ConformalAcquisition):
+    """mobo_acquisitions.py:24-45.  `model`: a list of m independent single-output models / GPModelStates (the reference's
+    batched multi-output SingleTaskGP is m independent GPs).  Joint batches q <= 4 including pending
+    points; with max_grid_refinements > 0 every output refines its own grid (the reference's loop takes its decisions over
+    all outputs at once, helpers.py:150-182 -- unpinned either way, App. C-5/C-6)."""
+
+    _kind = "ehvi"
+
     def __init__(self, alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic=False,
                  grid_sampler=None, randomized=False, *, model=None, ref_point=None, partitioning=None, sampler=None,
                  objective=None, constraints=None, X_pending=None, eta=1e-3):
@@ -59,40 +68,50 @@ class qConformalExpectedHypervolumeImprovement(ConformalAcquisition):
         models: Sequence = self.model if isinstance(self.model, (list, tuple)) else [self.model]
         return [as_state(m) for m in models]
 
-    def forward(self, X: torch.Tensor) -> torch.Tensor:
+    _PER_OUTPUT = ("conf_pred_mask", "grid_logp", "target_grid", "post_mean", "ood_mask", "post_var")
+
+    def _prepare(self, X):
+        """Shared front end of cEHVI / cNEHVI: shapes, pending points, base samples, probes, uniforms."""
         if self.model is None:
             raise AttributeError("ConformalAcquisition must be subclassed")
         if X.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError("d acq / d X is not built yet (SURVEY.md §8f-1); call under torch.no_grad()")
-        if self.max_grid_refinements > 0:
-            raise NotImplementedError("cEHVI grid refinement (joint over the objectives) is not built yet")
+            raise NotImplementedError("d acq / d X is not built for the multi-objective acquisitions (SURVEY.md §8f-1); "
+                                      "call under torch.no_grad()")
         states = self._states()
         m = len(states)
         if X.ndim == 2:
             X = X.unsqueeze(0)
-        if self.X_pending is not None or X.shape[-2] != 1:
-            raise NotImplementedError("cEHVI is built for q = 1")
-        lead, d = X.shape[:-2], X.shape[-1]
+        if self.X_pending is not None:                           # concatenate_pending_points
+            X = torch.cat([X, self.X_pending.to(X).expand(*X.shape[:-2], -1, -1)], dim=-2)
+        lead, (q, d) = X.shape[:-2], X.shape[-2:]
+        if q > 4:
+            raise NotImplementedError("joint batches are built for q <= 4 (incl. pending points)")
         dev = X.device
-        Xf = X.reshape(-1, 1, d)
+        Xf = X.detach().reshape(-1, q, d)
         b, G = Xf.shape[0], self.grid_res
         self.grid_sampler._sample_shape = torch.Size([G])
-        eps = self.grid_sampler.draw((G, 1, m), dev)[:, 0, :]                       # (G, m): base samples (G,1,q,t)
-        S = int(self.sampler.sample_shape[0])
-        eps_mc = self.sampler.draw((S, G, 1, m), dev)[:, :, 0, :].contiguous()      # (S, G, m)
-        z = (self.fixed_probes if self.fixed_probes is not None else draw_probes(states[0].N + 1)).to(dev)
-        u = self.fixed_uniforms                                                     # (b, G, m)
+        eps = self.grid_sampler.draw((G, q, m), dev)                                # base samples (G, 1, q, t)
+        z = (self.fixed_probes if self.fixed_probes is not None else draw_probes(states[0].N + q)).to(dev)
+        u = self.fixed_uniforms                                                     # (b, G, q, m)
         if self.randomized and u is None:
-            u = torch.rand(b, G, m, dtype=torch.float64, device=dev)
-        outs = []
-        for k, st in enumerate(states):
-            outs.append(ops.conformal_acq(
-                st, Xf, eps_grid=eps[:, k].contiguous(), z=z, eps_mc=torch.zeros(1, G, dtype=torch.float64, device=dev),
-                u_rand=None if u is None else u[:, :, k].contiguous(), ratio=_ratio_weights(self.ratio_estimator, dev),
-                outputs=("conf_pred_mask", "grid_logp", "target_grid", "post_mean", "ood_mask", "refit_mean", "refit_sd"),
-                kind="ucb", alpha=self.alpha, temp=self.temp, grid_res=G, max_grid_refinements=0,
-                randomized=self.randomized, optimistic=self.optimistic))
-        acq = ops.cehvi_integrate(outs, eps_mc, self.cell_lower.to(dev), self.cell_upper.to(dev), alpha=self.alpha,
-                                  optimistic=self.optimistic)
-        self.last_outputs = {"per_output": outs, "acq": acq}
+            u = torch.rand(b, G, q, m, dtype=torch.float64, device=dev)
+        return states, m, X, Xf, lead, q, b, G, dev, eps, z, u
+
+    def _per_output(self, st, k, Xf, q, G, dev, eps, z, u, **extra):
+        kw = dict(kind="ucb", eps_mc=torch.zeros(1, G, q, dtype=torch.float64, device=dev), outputs=self._PER_OUTPUT)
+        kw.update(extra)
+        return ops.conformal_acq(
+            st, Xf, eps_grid=eps[:, :, k].contiguous(), z=z, u_rand=None if u is None else u.reshape(-1, G, q, u.shape[-1])[..., k].contiguous(),
+            ratio=_ratio_weights(self.ratio_estimator, dev), alpha=self.alpha, temp=self.temp, grid_res=G,
+            max_grid_refinements=self.max_grid_refinements, randomized=self.randomized, optimistic=self.optimistic, **kw)
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        states, m, X, Xf, lead, q, b, G, dev, eps, z, u = self._prepare(X)
+        S = int(self.sampler.sample_shape[0])
+        eps_mc = self.sampler.draw((S, G, q, m), dev).contiguous()                  # base samples (S, 1, G, q, t)
+        outs = [self._per_output(st, k, Xf, q, G, dev, eps, z, u) for k, st in enumerate(states)]
+        acq, values = ops.cehvi_integrate_q(outs, [st.noise for st in states], eps_mc, self.cell_lower.to(dev),
+                                            self.cell_upper.to(dev), q=q, alpha=self.alpha, optimistic=self.optimistic,
+                                            want_values=True)
+        self.last_outputs = {"per_output": outs, "acq": acq, "values": values}
         return acq.reshape(lead).to(X.dtype)

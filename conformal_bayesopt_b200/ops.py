@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from .model_state import GPModelState
 
-ACQ_KINDS = {"ucb": 0, "ei": 1, "nei": 2}
+ACQ_KINDS = {"ucb": 0, "ei": 1, "nei": 2, "joint": 3}
 _WORKSPACES: Dict[tuple, torch.Tensor] = {}
 LAUNCH_COUNT = 0   # kernels launched through this module (bench.py reports it as gpu_launches)
 
@@ -179,7 +179,7 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
         reduce_c = _lib.REFINE_REDUCE_FN(_hook)              # kept alive until the call returns
     baseline = param_kw.pop("nei_baseline", None)
     nei_c = baseline.c_struct() if baseline is not None else None          # kept alive until the call returns
-    per_sample = (baseline.Xb.shape[0] + 1) if baseline is not None else q
+    per_sample = (baseline.Xb.shape[0] + q) if baseline is not None else q
     num_mc = eps_mc.numel() // (G * per_sample)
     params = make_params(q=q, num_mc=num_mc, num_probes=z.shape[-1], eps_per_candidate=eps_per_candidate, nei=nei_c,
                          refine_reduce=reduce_c, **param_kw)
@@ -194,6 +194,9 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
               "refit_mean": (b, G), "refit_sd": (b,)}
     if q > 1 and ("refit_mean" in outputs or "refit_sd" in outputs):
         raise _lib.CboError("refit_mean / refit_sd are q = 1 outputs")
+    shapes["mc_values"] = (b, num_mc, G, q)             # kind nei / joint: the per-sample values the integration consumed
+    if "mc_values" in outputs and baseline is None:
+        raise _lib.CboError("mc_values is an output of the joint-sample kinds (nei, joint)")
     for name in outputs:
         out_t[name] = torch.empty(shapes[name], dtype=torch.float64, device=dev)
     cout = _lib.OutputsF64(**{k: _ptr(v) for k, v in out_t.items()})
@@ -278,6 +281,50 @@ def cehvi_integrate(per_output, eps_mc: torch.Tensor, cell_lower: torch.Tensor, 
     _lib.check(st, "cbo_cehvi_integrate_f64")
     LAUNCH_COUNT += 1
     return acq
+
+
+def cehvi_integrate_q(per_output, noise, eps_mc: Optional[torch.Tensor], cell_lower: torch.Tensor, cell_upper: torch.Tensor, *,
+                      q: int, alpha: float, optimistic: bool, cells_per_sample: bool = False, want_values: bool = False):
+    """cbo_cehvi_integrate_q_f64: joint batches q <= 4 and cNEHVI.  `per_output`: list (one per objective) of the dicts returned
+    by `conformal_acq(..., outputs=(conf_pred_mask, grid_logp, target_grid, post_mean, ood_mask, post_var[, mc_values]))`.
+    Entries that carry 'mc_values' (b, S, G, q) supply the samples themselves (cNEHVI), the others are sampled from the refit
+    posterior with eps_mc (S, G, q, m).  cells: (n_cells, m) or, with `cells_per_sample`, (S, n_cells, m)."""
+    lib = _lib.load()
+    m = len(per_output)
+    dev = per_output[0]["conf_pred_mask"].device
+    b, G = per_output[0]["grid_logp"].shape
+    keep = []
+    def ptrs(key, shape):
+        ts = [_f64(o[key]).reshape(shape) for o in per_output]
+        keep.append(ts)
+        return (C.c_void_p * m)(*[t.data_ptr() for t in ts])
+    mask, grid = ptrs("conf_pred_mask", (b, G, q)), ptrs("target_grid", (b, G, q))
+    logp, mu, ood = ptrs("grid_logp", (b, G)), ptrs("post_mean", (b, q)), ptrs("ood_mask", (b, q))
+    ext = ["mc_values" in o for o in per_output]
+    if any(ext) and not all(ext):
+        raise _lib.CboError("either every output supplies mc_values or none does")
+    fx = cov = None
+    if all(ext):
+        S = per_output[0]["mc_values"].shape[1]
+        fx = ptrs("mc_values", (b, S, G, q))
+    else:
+        cov = ptrs("post_var", (b, q, q))
+        eps_mc = _f64(eps_mc)
+        _require_cuda(eps_mc)
+        S = eps_mc.numel() // (G * q * m)
+    cell_lower, cell_upper = _f64(cell_lower), _f64(cell_upper)
+    _require_cuda(cell_lower, cell_upper)
+    n_cells = cell_lower.shape[-2]
+    if cells_per_sample and cell_lower.shape[0] != S:
+        raise _lib.CboError("per-sample cells must be (S, n_cells, m)")
+    noise_c = (C.c_double * m)(*[float(v) for v in noise])
+    acq = torch.empty(b, dtype=torch.float64, device=dev)
+    values = torch.empty(b, G, dtype=torch.float64, device=dev) if want_values else None
+    st = lib.cbo_cehvi_integrate_q_f64(m, b, G, S, q, mask, logp, grid, mu, ood, cov, noise_c, fx, _ptr(eps_mc) if fx is None else None,
+                                       cell_lower.data_ptr(), cell_upper.data_ptr(), n_cells, int(bool(cells_per_sample)),
+                                       float(alpha), int(bool(optimistic)), acq.data_ptr(), _ptr(values), _stream())
+    _lib.check(st, "cbo_cehvi_integrate_q_f64")
+    return (acq, values) if want_values else acq
 
 
 def conf_mask_to_bounds(target_grid: torch.Tensor, conf_pred_mask: torch.Tensor):

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CBO_VERSION 100
+#define CBO_VERSION 101
 
 typedef enum {
     CBO_OK = 0,
@@ -56,7 +56,10 @@ typedef enum {
     CBO_ERR_NO_DEVICE = 5        /* no sm_100 device visible */
 } cbo_status;
 
-typedef enum { CBO_ACQ_UCB = 0, CBO_ACQ_EI = 1, CBO_ACQ_NEI = 2 } cbo_acq_kind;
+/* CBO_ACQ_JOINT: the joint-posterior samples of f(X) over [X_baseline; X] under every refit model themselves (what cNEI turns
+ * into improvements); they are integrated like cUCB samples and exported through cbo_outputs_f64.mc_values -- the per-output
+ * call of cNEHVI (conformalbo/mobo_acquisitions.py:196-213). */
+typedef enum { CBO_ACQ_UCB = 0, CBO_ACQ_EI = 1, CBO_ACQ_NEI = 2, CBO_ACQ_JOINT = 3 } cbo_acq_kind;
 
 /* One output's exact GP, prepared once per model fit (all device pointers, fp64, row-major).
  * Np = cbo_padded_n(N) (N rounded up to a multiple of 128); rows/cols >= N are zero. */
@@ -106,7 +109,7 @@ typedef struct {
     int32_t eps_per_candidate; /* 0: eps_grid is (G) shared (collapse_batch_dims), 1: (b x G) */
     double beta_prime;         /* cUCB: sqrt(beta*pi/2)                     */
     double best_f;             /* cEI incumbent                             */
-    const cbo_nei_baseline_f64* nei;   /* kind == CBO_ACQ_NEI only (eps_mc is then S x G x (nb+1)), else NULL */
+    const cbo_nei_baseline_f64* nei;   /* kind == CBO_ACQ_NEI / CBO_ACQ_JOINT only (eps_mc is then S x G x (nb+q)), else NULL */
     /* max_grid_refinements > 0 and the candidate batch is sharded over several ranks: called on the HOST once per
      * refinement pass with stats = {min accepted, max accepted, sum of (accepted/G - 1/2)^2, candidates} of this rank's
      * shard; must overwrite them with the values over all ranks (min / max / sum / sum).  NULL: single batch. */
@@ -127,6 +130,7 @@ typedef struct {
     double* num_accepted;      /* b x q       #{g : mask >= 0.5}                                 */
     double* refit_mean;        /* b x G       q = 1: posterior mean at x under the model refit on (x, y_g)  */
     double* refit_sd;          /* b           q = 1: its (noise-free) posterior sd                          */
+    double* mc_values;         /* b x S x G x q   kind NEI / JOINT: the per-sample values the integration consumed  */
 } cbo_outputs_f64;
 
 int cbo_version(void);
@@ -177,6 +181,21 @@ int cbo_cehvi_integrate_f64(int64_t m, int64_t b, int64_t G, int64_t S, const do
                             const double* const* ood, const double* const* refit_mean, const double* const* refit_sd,
                             const double* eps_mc, const double* cell_lower, const double* cell_upper, int64_t n_cells,
                             double alpha, int32_t optimistic, double* acq, void* stream);
+
+/* cEHVI for joint batches q <= 4 (incl. pending points) and cNEHVI (mobo_acquisitions.py:24-45, 184-219): per output k the
+ * results of one cbo_conformal_acq_f64 call with q points per candidate batch -- mask / grid: b x G x q, logp: b x G, mu / ood:
+ * b x q, cov: b x q x q (cbo_outputs_f64.post_var; b for q = 1), noise[k] (HOST array of m values).  The refit posterior at the
+ * candidates is sampled with eps_mc (S x G x q x m) -- or, when fx != NULL, fx[k] (b x S x G x q, cbo_outputs_f64.mc_values of
+ * a CBO_ACQ_JOINT call) are the samples (cNEHVI: joint with the baseline).  cells_per_sample != 0: cell_lower / cell_upper are
+ * S x n_cells x m, one box decomposition per MC sample (cNEHVI), else n_cells x m.  Masks, optimistic masks and ood masks
+ * multiply over outputs and over the q points, log-densities add; values are botorch's _compute_qehvi (inclusion-exclusion
+ * over the q-subsets).  values_out (b x G, may be NULL) receives the MC-averaged hyper-volume improvements. */
+int cbo_cehvi_integrate_q_f64(int64_t m, int64_t b, int64_t G, int64_t S, int64_t q, const double* const* mask,
+                              const double* const* logp, const double* const* grid, const double* const* mu,
+                              const double* const* ood, const double* const* cov, const double* noise_host,
+                              const double* const* fx, const double* eps_mc, const double* cell_lower,
+                              const double* cell_upper, int64_t n_cells, int32_t cells_per_sample, double alpha,
+                              int32_t optimistic, double* acq, double* values_out, void* stream);
 
 /* conf_mask_to_bounds: grid, mask: b x G x t (q = 1 squeezed) -> lb, ub: b x t.  G <= 2048. */
 int cbo_conf_mask_to_bounds_f64(const double* target_grid, const double* conf_pred_mask, int64_t b, int64_t G,

@@ -123,7 +123,7 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
             break
     _, grid, logp, mask, dev = best
 
-    if kind == "nei":
+    if kind in ("nei", "joint"):
         # joint posterior of the refit model over [X_baseline; X] (acquisitions.py:115-134).  With c = Cov_D(f(X_b), y(X))
         # (nb x q), Cov_D(f(X), y(X)) = S - noise I and B_g = S^-1 (y_g - mu):
         #   mean = [mu_b + c B_g ; mu + (I - noise S^-1)(y_g - mu)]
@@ -148,7 +148,9 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
                           mu.unsqueeze(1) + dev @ (eye - noise * Sinv).transpose(-1, -2)], dim=-1)          # (b,G,nb+q)
         samples = mean.unsqueeze(0) + torch.einsum("bij,sgj->sbgi", root, eps_mc)
         fb, fx = samples[..., :nb], samples[..., nb:]                      # (S,b,G,nb), (S,b,G,q)
-        if temp > 0:
+        if kind == "joint":                                                # cNEHVI: the samples of f(X) themselves
+            values = fx
+        elif temp > 0:
             diffs = (fx - temp * torch.logsumexp(fb / temp, -1, keepdim=True)) / temp
             values = temp * (torch.clamp_min(diffs, 0) + torch.log1p(torch.exp(-diffs.abs())))
         else:
@@ -159,7 +161,7 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
     cov_f = noise * shrink
     cov_f = 0.5 * (cov_f + cov_f.transpose(-1, -2))
     root = cov_f.clamp_min(0.0).sqrt() if q == 1 else torch.linalg.cholesky(cov_f)
-    if kind != "nei":
+    if kind not in ("nei", "joint"):
         samples = mean_f.unsqueeze(0) + torch.einsum("bij,sgj->sbgi", root, eps_mc)
     if kind == "ucb":
         m = samples.mean(0)
@@ -167,7 +169,9 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
     elif kind == "ei":
         x = (samples - best_f) / temp
         values = temp * (torch.clamp_min(x, 0) + torch.log1p(torch.exp(-x.abs())))
-    elif kind == "nei":
+    elif kind == "raw":                                                    # cEHVI: the samples of f(X) themselves
+        values = samples
+    elif kind in ("nei", "joint"):
         pass                                                               # computed above from the joint posterior
     else:
         raise ValueError(kind)

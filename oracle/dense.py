@@ -142,7 +142,7 @@ def refit_posterior_at_candidates(gp: GPState, refit, q: int):
     return mean_f, cov_f
 
 
-def nei_values(gp, refit, Xq, X_baseline, eps_mc, temp):
+def nei_values(gp, refit, Xq, X_baseline, eps_mc, temp, raw=False):
     """qConformalNoisyExpectedImprovement._nonconformal_fwd (acquisitions.py:115-134): joint posterior of the refit model over
     X_full = [X_baseline; X], joint samples (base samples (S,G,nb+q)), smooth improvement over the baseline."""
     b, q, d = Xq.shape
@@ -158,6 +158,8 @@ def nei_values(gp, refit, Xq, X_baseline, eps_mc, temp):
     cov = 0.5 * (cov + cov.transpose(-1, -2))
     root = _chol(cov)
     samples = mean.unsqueeze(0) + (root.unsqueeze(0) @ eps_mc.unsqueeze(1).unsqueeze(-1)).squeeze(-1)   # (S,b,G,nb+q)
+    if raw:                                                          # cNEHVI (mobo_acquisitions.py:204-211): f(X) of the joint sample
+        return samples[..., -q:]
     diffs = samples[..., -q:] - softplus(samples[..., :-q], -1, temp, keepdim=True)
     return softplus(torch.stack([diffs, torch.zeros_like(diffs)], dim=-1), -1, temp)             # (S,b,G,q)
 
@@ -174,6 +176,8 @@ def nonconformal_values(gp, refit, q, eps_mc, kind, *, beta_prime=None, best_f=N
     else:
         root = _chol(cov_f)
     samples = mean_f.unsqueeze(0) + (root.unsqueeze(0) @ eps_mc.unsqueeze(1).unsqueeze(-1)).squeeze(-1)  # (S,b,G,q)
+    if kind == "raw":
+        return samples
     if kind == "ucb":
         m = samples.mean(dim=0)
         return m + beta_prime * (samples - m).abs()
@@ -233,8 +237,8 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
         opt_mask = (target_grid >= mean.unsqueeze(1)).to(target_grid)
     else:
         opt_mask = torch.ones_like(target_grid)
-    if kind == "nei":
-        values = nei_values(gp, refit, Xq, X_baseline, eps_mc, temp)
+    if kind in ("nei", "joint"):
+        values = nei_values(gp, refit, Xq, X_baseline, eps_mc, temp, raw=kind == "joint")
     else:
         values = nonconformal_values(gp, refit, q, eps_mc, kind, beta_prime=beta_prime, best_f=best_f, temp=temp)
     res = conformal_integration(values, mask.unsqueeze(-1), logp[..., None, None], alpha,

@@ -1,7 +1,7 @@
 """cEHVI oracle (test infrastructure only; "parity unpinned").
 
-qConformalExpectedHypervolumeImprovement (conformalbo/mobo_acquisitions.py:24-45) for q = 1 and m independent
-single-output GPs.  The reference's own `_conformal_integration` collapses the wrong axes for EHVI-shaped values and
+qConformalExpectedHypervolumeImprovement (conformalbo/mobo_acquisitions.py:24-45) and
+qConformalNoisyExpectedHypervolumeImprovement (:184-219) for joint batches of q points and m independent single-output GPs.  The reference's own `_conformal_integration` collapses the wrong axes for EHVI-shaped values and
 raises unless b in {1, G} (verified there), and its multi-output label layout is scrambled by a
 `.view` (App. C-6); like the product, this oracle implements the evident intent: per-output full-conformal masks,
 product over outputs, sum of log-densities, botorch `_compute_qehvi` values (App. B-9), integration over the grid.
@@ -38,47 +38,58 @@ def box_decomposition_2d(ref_point: torch.Tensor, Y: torch.Tensor):
     return torch.tensor(lower, dtype=torch.float64), torch.tensor(upper, dtype=torch.float64)
 
 
+def qehvi(f, cell_lower, cell_upper):
+    """botorch `_compute_qehvi` before the MC mean.  f: (S, ..., q, m); cells (n_cells, m) or (S, n_cells, m)
+    (one box decomposition per MC sample: qNoisyExpectedHypervolumeImprovement).  Returns (S, ...)."""
+    from itertools import combinations
+    S, q = f.shape[0], f.shape[-2]
+    extra = f.dim() - 3
+    if cell_lower.dim() == 2:
+        shape = (1,) + (1,) * extra + cell_lower.shape
+    else:
+        shape = (S,) + (1,) * extra + cell_lower.shape[1:]
+    lo, up = cell_lower.reshape(shape), cell_upper.reshape(shape)           # (S|1, ..., cells, m)
+    total = torch.zeros(f.shape[:-2], dtype=f.dtype)
+    for i in range(1, q + 1):
+        for sub in combinations(range(q), i):
+            v = f[..., list(sub), :].min(dim=-2).values                     # (S, ..., m)
+            vol = (torch.minimum(v.unsqueeze(-2), up) - lo).clamp_min(0).prod(-1).sum(-1)
+            total = total + (-1) ** (i + 1) * vol
+    return total
+
+
 def cehvi(gps, Xq, *, alpha, temp, grid_res, eps_grid, z, eps_mc, cell_lower, cell_upper, ratio=None, randomized=False,
-          u_rand=None, optimistic=False, impl="closed"):
-    """gps: list of m GPState; Xq (b,1,d); eps_grid (G,m); eps_mc (S,G,m); u_rand (b,G,m).  Returns acq (b,)."""
-    m = len(gps)
-    b, G = Xq.shape[0], grid_res
+          u_rand=None, optimistic=False, impl="closed", max_grid_refinements=0, X_baseline=None):
+    """gps: list of m GPState; Xq (b,q,d); eps_grid (G,q,m); eps_mc (S,G,q,m) -- or (S,G,nb+q,m) with X_baseline (cNEHVI: the
+    samples of f(X) come from the joint refit posterior over [X_baseline; X], cells are then (S,n_cells,m)); u_rand (b,G,q,m).
+    Returns dict(acq (b,), values (b,G)).  Differentiable in Xq (torch autograd)."""
+    mod = closed_form if impl == "closed" else dense
+    b, q, _ = Xq.shape
+    G = grid_res
     mask = torch.ones(b, G, dtype=torch.float64)
     opt = torch.ones(b, G, dtype=torch.float64)
     logp = torch.zeros(b, G, dtype=torch.float64)
     ood = torch.ones(b, dtype=torch.float64)
-    mean_f, sd_f = [], []
+    fs = []
     for k, gp in enumerate(gps):
-        eg = eps_grid[:, k:k + 1]
-        ur = None if u_rand is None else u_rand[:, :, k:k + 1]
-        if impl == "closed":
-            o = closed_form.conformal_acquisition(gp, Xq, kind="ucb", alpha=alpha, temp=temp, grid_res=G, eps_grid=eg, z=z,
-                                                  eps_mc=torch.zeros(1, G, 1, dtype=torch.float64), ratio=ratio,
-                                                  randomized=randomized, u_rand=ur, optimistic=optimistic, beta_prime=1.0)
-            grid, lp, mk, od, mu, s = o["target_grid"][..., 0], o["logp"], o["mask"][..., 0], o["ood"][:, 0, 0], o["mu"][:, 0], o["S"][:, 0, 0]
-            mf = mu[:, None] + (grid - mu[:, None]) * (1 - gp.noise / s)[:, None]
-            sd = (gp.noise * (1 - gp.noise / s)).clamp_min(0).sqrt()
-        else:
-            grid3, lp, mk3, refit, od3 = dense.construct_conformal_bands(gp, Xq, alpha, temp, G, 0, eg, z, ratio, randomized, ur)
-            grid, mk, od = grid3[..., 0], mk3[..., 0], od3[:, 0, 0]
-            mu, _ = dense.posterior(gp, Xq, observation_noise=False)
-            mu = mu[:, 0]
-            mfull, cov = dense.refit_posterior_at_candidates(gp, refit, 1)
-            mf, sd = mfull[..., 0], cov[:, 0, 0, 0].clamp_min(0).sqrt()     # the refit variance does not depend on g
-        mask = mask * mk
-        logp = logp + lp
-        ood = ood * od
+        o = mod.conformal_acquisition(gp, Xq, kind="raw" if X_baseline is None else "joint", alpha=alpha, temp=temp, grid_res=G,
+                                      max_grid_refinements=max_grid_refinements, eps_grid=eps_grid[..., k], z=z,
+                                      eps_mc=eps_mc[..., k], ratio=ratio, randomized=randomized,
+                                      u_rand=None if u_rand is None else u_rand[..., k], optimistic=optimistic,
+                                      beta_prime=1.0, X_baseline=X_baseline)
+        mask = mask * o["mask"].prod(-1)                                   # product over the q points and over outputs
+        logp = logp + o["logp"]
+        ood = ood * o["ood"][:, 0, :].prod(-1)
         if optimistic:
-            opt = opt * (grid >= mu[:, None]).double()
-        mean_f.append(mf)
-        sd_f.append(sd)
-    mean_f = torch.stack(mean_f, -1)                                   # (b,G,m)
-    sd_f = torch.stack(sd_f, -1)                                       # (b,m)
-    f = mean_f.unsqueeze(0) + sd_f[None, :, None, :] * eps_mc[:, None]  # (S,b,G,m)
-    vol = (torch.minimum(f.unsqueeze(-2), cell_upper) - cell_lower).clamp_min(0).prod(-1)   # (S,b,G,cells)
-    values = vol.sum(-1).mean(0)                                       # (b,G): _compute_qehvi takes the MC mean
+            with torch.no_grad():
+                mu = gp.mean + gp.k(Xq, gp.X) @ gp.alpha                   # (b,q)
+            opt = opt * (o["target_grid"] >= mu.unsqueeze(1)).double().prod(-1)
+        fs.append(o["values"])                                             # (S,b,G,q)
+    f = torch.stack(fs, -1)                                                # (S,b,G,q,m)
+    values = qehvi(f, cell_lower, cell_upper).mean(0)                      # (b,G)
     nonconf = (1 - mask) * opt
     nonconf = nonconf / nonconf.sum(1, keepdim=True).clamp_min(1e-6)
     conf = mask * opt / logp.exp().clamp_min(1e-6)
     conf = conf / conf.sum(1, keepdim=True).clamp_min(1e-6)
-    return ((1 - ood)[:, None] * ((1 - alpha) * conf + alpha * nonconf) * values).sum(1)
+    acq = ((1 - ood)[:, None] * ((1 - alpha) * conf + alpha * nonconf) * values).sum(1)
+    return dict(acq=acq, values=values, mask=mask, logp=logp)

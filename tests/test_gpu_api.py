@@ -183,8 +183,10 @@ def test_ratio_estimator_forward_on_cuda():
     assert out.shape == (3, 7) and torch.allclose(out.cpu(), ratio(x), rtol=1e-10)
 
 
-def test_cehvi_matches_oracle():
-    """BASELINE config 3 shape: two objectives, conformal bands over both (intent semantics, see oracle/mobo.py)."""
+@pytest.mark.parametrize("q,pending,refine", [(1, 0, 0), (2, 0, 0), (1, 1, 0), (3, 1, 0), (2, 0, 2)])
+def test_cehvi_matches_oracle(q, pending, refine):
+    """BASELINE config 3 shape: two objectives, conformal bands over both (intent semantics, see oracle/mobo.py); joint
+    batches of q points of which `pending` are X_pending (concatenate_pending_points), per-output grid refinement."""
     from conformal_bayesopt_b200 import GPModelState
     from conformal_bayesopt_b200.mobo_acquisitions import box_decomposition_2d, qConformalExpectedHypervolumeImprovement
     from conformal_bayesopt_b200.sampling import IIDNormalSampler
@@ -197,31 +199,34 @@ def test_cehvi_matches_oracle():
     hyp = [(0.0, [0.4 + 0.1 * k] * d, 1.0 + 0.2 * k, 1e-2 * (k + 1)) for k in range(m)]
     gps = [ogp.build_state(X, Y[:, k], *hyp[k]) for k in range(m)]
     states = [GPModelState.fit_fixed(X, Y[:, k], *hyp[k], device=dev) for k in range(m)]
-    Xq = torch.rand(b, 1, d, generator=g, dtype=torch.float64)
-    eps_grid = torch.randn(G, m, generator=g, dtype=torch.float64)
-    eps_mc = torch.randn(S, G, m, generator=g, dtype=torch.float64)
-    z = 2.0 * ((torch.rand(N + 1, 8, generator=g) > 0.5).double() - 0.5)
-    u = torch.rand(b, G, m, generator=g, dtype=torch.float64)
+    Xq = torch.rand(b, q, d, generator=g, dtype=torch.float64)
+    if pending:
+        Xq[:, q - pending:] = Xq[0, q - pending:]                  # the pending points are shared by every candidate batch
+    eps_grid = torch.randn(G, q, m, generator=g, dtype=torch.float64)
+    eps_mc = torch.randn(S, G, q, m, generator=g, dtype=torch.float64)
+    z = 2.0 * ((torch.rand(N + q, 8, generator=g) > 0.5).double() - 0.5)
+    u = torch.rand(b, G, q, m, generator=g, dtype=torch.float64)
     ref = torch.tensor([-1.5, -1.5], dtype=torch.float64)
     lo, up = box_decomposition_2d(ref, Y)
     lo_o, up_o = mobo.box_decomposition_2d(ref, Y)
     assert torch.equal(lo, lo_o) and torch.equal(up, up_o)
     gs = IIDNormalSampler(G)
-    gs.set_base_samples(eps_grid.view(G, 1, m))
+    gs.set_base_samples(eps_grid)
     mc = IIDNormalSampler(S, batch_range=(0, -3))
-    mc.set_base_samples(eps_mc.view(S, G, 1, m))
+    mc.set_base_samples(eps_mc)
     for optimistic in (False, True):
-        acq = qConformalExpectedHypervolumeImprovement(alpha=0.2, temp=3e-2, grid_res=G, max_grid_refinements=0,
+        acq = qConformalExpectedHypervolumeImprovement(alpha=0.2, temp=3e-2, grid_res=G, max_grid_refinements=refine,
                                                        ratio_estimator=None, optimistic=optimistic, grid_sampler=gs,
                                                        randomized=True, model=states, ref_point=ref, partitioning=(lo, up),
-                                                       sampler=mc)
+                                                       sampler=mc, X_pending=Xq[0, q - pending:].to(dev) if pending else None)
         acq.fixed_probes, acq.fixed_uniforms = z, u.to(dev)
         with torch.no_grad():
-            got = acq(Xq.to(dev))
+            got = acq(Xq[:, :q - pending].to(dev))
         want = mobo.cehvi(gps, Xq, alpha=0.2, temp=3e-2, grid_res=G, eps_grid=eps_grid, z=z, eps_mc=eps_mc, cell_lower=lo,
-                          cell_upper=up, randomized=True, u_rand=u, optimistic=optimistic)
-        assert got.shape == (b,) and (want > 0).any()
-        assert torch.allclose(got.cpu(), want, rtol=1e-6, atol=1e-10)
+                          cell_upper=up, randomized=True, u_rand=u, optimistic=optimistic, max_grid_refinements=refine)
+        assert got.shape == (b,) and (want["acq"] > 0).any()
+        assert torch.allclose(got.cpu(), want["acq"], rtol=1e-6, atol=1e-10)
+        assert torch.allclose(acq.last_outputs["values"].cpu(), want["values"], rtol=1e-6, atol=1e-10)
 
 
 @pytest.mark.parametrize("temp,refine,q", [(3e-2, 0, 1), (1e-2, 2, 1), (3e-2, 0, 2), (1e-2, 2, 2), (3e-2, 0, 3), (3e-2, 1, 4),

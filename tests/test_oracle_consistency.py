@@ -81,27 +81,55 @@ def test_finite_sample_coverage():
     assert hits / trials >= 1 - alpha - 0.12   # 60 trials: ~2.3 sigma slack below the nominal 0.8
 
 
-def test_cehvi_dense_equals_closed_form():
-    """Multi-objective oracle (intent semantics, App. C-5/C-6): dense refit pieces == closed-form pieces."""
-    from oracle import mobo
-    N, d, b, G, m = 16, 2, 5, 12, 2          # BASELINE config 3 shape: BraninCurrin-like d=2, t=2, N=16
-    g = torch.Generator().manual_seed(3)
+def _mobo_problem(N, d, m, seed):
+    g = torch.Generator().manual_seed(seed)
     X = torch.rand(N, d, generator=g, dtype=torch.float64)
     Y = torch.stack([torch.sin(3 * X.sum(-1)), torch.cos(2 * X[:, 0]) - X[:, 1]], -1)
     gps = [ogp.build_state(X, Y[:, k], 0.0, [0.4 + 0.1 * k] * d, 1.0 + 0.2 * k, 1e-2 * (k + 1)) for k in range(m)]
-    Xq = torch.rand(b, 1, d, generator=g, dtype=torch.float64)
-    eps_grid = torch.randn(G, m, generator=g, dtype=torch.float64)
-    eps_mc = torch.randn(3, G, m, generator=g, dtype=torch.float64)
-    z = 2.0 * ((torch.rand(N + 1, 8, generator=g) > 0.5).double() - 0.5)
-    u = torch.rand(b, G, m, generator=g, dtype=torch.float64)
+    return g, X, Y, gps
+
+
+@pytest.mark.parametrize("q,refine", [(1, 0), (2, 0), (2, 2), (3, 0)])
+def test_cehvi_dense_equals_closed_form(q, refine):
+    """Multi-objective oracle (intent semantics, App. C-5/C-6): dense refit pieces == closed-form pieces, joint batches."""
+    from oracle import mobo
+    N, d, b, G, m = 16, 2, 5, 12, 2          # BASELINE config 3 shape: BraninCurrin-like d=2, t=2, N=16
+    g, X, Y, gps = _mobo_problem(N, d, m, 3)
+    Xq = torch.rand(b, q, d, generator=g, dtype=torch.float64)
+    eps_grid = torch.randn(G, q, m, generator=g, dtype=torch.float64)
+    eps_mc = torch.randn(3, G, q, m, generator=g, dtype=torch.float64)
+    z = 2.0 * ((torch.rand(N + q, 8, generator=g) > 0.5).double() - 0.5)
+    u = torch.rand(b, G, q, m, generator=g, dtype=torch.float64)
     lo, up = mobo.box_decomposition_2d(torch.tensor([-1.5, -1.5], dtype=torch.float64), Y)
     assert lo.shape[0] >= 2 and torch.isinf(up[:, 1]).all()
     kw = dict(alpha=0.2, temp=3e-2, grid_res=G, eps_grid=eps_grid, z=z, eps_mc=eps_mc, cell_lower=lo, cell_upper=up,
-              randomized=True, u_rand=u, optimistic=False)
+              randomized=True, u_rand=u, optimistic=False, max_grid_refinements=refine)
     a = mobo.cehvi(gps, Xq, impl="dense", **kw)
     c = mobo.cehvi(gps, Xq, impl="closed", **kw)
-    assert (a > 0).any()
-    assert torch.allclose(a, c, rtol=1e-9, atol=1e-12)
+    assert (a["acq"] > 0).any()
+    assert torch.allclose(a["acq"], c["acq"], rtol=1e-9, atol=1e-12)
+    assert torch.allclose(a["values"], c["values"], rtol=1e-9, atol=1e-12)
+    if q == 1:      # q = 1 inclusion-exclusion has one term: the plain box overlap
+        f = torch.tensor([[[[0.3, -0.2]]]], dtype=torch.float64)
+        want = (torch.minimum(f[0, 0], up) - lo).clamp_min(0).prod(-1).sum()
+        assert torch.allclose(mobo.qehvi(f, lo, up)[0, 0], want)
+
+
+def test_qehvi_inclusion_exclusion_is_the_volume_of_the_union():
+    """q = 2 against a direct computation: hv(a) + hv(b) - hv(min(a, b)) per cell; per-sample cells pick their own sample."""
+    from oracle import mobo
+    g = torch.Generator().manual_seed(5)
+    lo = torch.tensor([[0.0, 0.5], [0.4, 0.0]], dtype=torch.float64)
+    up = torch.tensor([[0.4, float("inf")], [float("inf"), float("inf")]], dtype=torch.float64)
+    f = torch.rand(3, 4, 2, 2, generator=g, dtype=torch.float64) * 1.5
+    hv = lambda y, l, u: (torch.minimum(y.unsqueeze(-2), u) - l).clamp_min(0).prod(-1).sum(-1)
+    want = hv(f[..., 0, :], lo, up) + hv(f[..., 1, :], lo, up) - hv(f.min(-2).values, lo, up)
+    assert torch.allclose(mobo.qehvi(f, lo, up), want)
+    lo_s = torch.stack([lo, lo + 0.1, lo - 0.1])
+    up_s = torch.stack([up, up, up])
+    got = mobo.qehvi(f, lo_s, up_s)
+    for s in range(3):
+        assert torch.allclose(got[s], mobo.qehvi(f[s:s + 1], lo_s[s], up_s[s])[0])
 
 
 @pytest.mark.parametrize("q", [1, 2, 3])
