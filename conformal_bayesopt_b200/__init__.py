@@ -10,9 +10,12 @@ from .acquisitions import (  # noqa: F401
     qConformalNoisyExpectedImprovement,
     qConformalUpperConfidenceBound,
 )
-from .mobo_acquisitions import qConformalExpectedHypervolumeImprovement  # noqa: F401
+from .mobo_acquisitions import (  # noqa: F401
+    qConformalExpectedHypervolumeImprovement,
+    qConformalNoisyExpectedHypervolumeImprovement,
+)
 from .ratio_estimation import RatioEstimator  # noqa: F401
 
 __all__ = ["GPModelState", "build", "_lib", "ConformalAcquisition", "qConformalUpperConfidenceBound",
            "qConformalExpectedImprovement", "qConformalNoisyExpectedImprovement",
-           "qConformalExpectedHypervolumeImprovement", "RatioEstimator"]
+           "qConformalExpectedHypervolumeImprovement", "qConformalNoisyExpectedHypervolumeImprovement", "RatioEstimator"]

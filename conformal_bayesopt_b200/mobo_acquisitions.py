@@ -115,3 +115,86 @@ class qConformalExpectedHypervolumeImprovement(ConformalAcquisition):
                                             want_values=True)
         self.last_outputs = {"per_output": outs, "acq": acq, "values": values}
         return acq.reshape(lead).to(X.dtype)
+
+
+def psd_safe_cholesky(A: torch.Tensor) -> torch.Tensor:
+    """Lower Cholesky factor with gpytorch's escalating diagonal jitter (1e-8 ... 1e-3 of nothing: absolute), used for the
+    small baseline covariances at construction time (host side, like the box decompositions)."""
+    L, info = torch.linalg.cholesky_ex(A)
+    jitter = 1e-8
+    while int(info.max()) != 0 and jitter <= 1e-2:
+        L, info = torch.linalg.cholesky_ex(A + jitter * torch.eye(A.shape[-1], dtype=A.dtype))
+        jitter *= 10.0
+    if int(info.max()) != 0:
+        raise RuntimeError("baseline posterior covariance is not positive definite")
+    return L
+
+
+def per_sample_cells(ref_point: torch.Tensor, fb: torch.Tensor):
+    """One box decomposition per MC sample of the baseline values fb (S, nb, 2) -> (lower, upper), each (S, n_cells, 2),
+    padded with zero-volume cells (lower = upper = ref_point) to the largest cell count."""
+    cells = [box_decomposition_2d(ref_point, fb[s]) for s in range(fb.shape[0])]
+    n = max(c[0].shape[0] for c in cells)
+    ref = ref_point.detach().double().cpu().reshape(1, -1)
+    lo = torch.stack([torch.cat([c[0], ref.expand(n - c[0].shape[0], -1)]) for c in cells])
+    up = torch.stack([torch.cat([c[1], ref.expand(n - c[1].shape[0], -1)]) for c in cells])
+    return lo.contiguous(), up.contiguous()
+
+
+class qConformalNoisyExpectedHypervolumeImprovement(qConformalExpectedHypervolumeImprovement):
+    """mobo_acquisitions.py:184-219 (+ botorch qNoisyExpectedHypervolumeImprovement(model, ref_point, X_baseline, sampler, ...,
+    cache_root=False)).  At construction the baseline values f(X_baseline) are sampled under the model (base samples
+    `baseline_base_samples`, (S, nb, m)) and every MC sample gets its own box decomposition of the non-dominated region; per
+    call f(X) is sampled JOINTLY with the baseline under every refit model -- the baseline part of the joint base samples is
+    the stored one, shared by all grid points (botorch `_set_sampler`), the new points draw (S, G, q, m) -- and the
+    hyper-volume improvement of sample s is taken against the cells of sample s.  Built for two objectives (the 2-D box
+    decomposition), a pruned baseline of nb + q <= 32 points, q <= 4 incl. pending points."""
+
+    _kind = "nehvi"
+
+    def __init__(self, alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic=False,
+                 grid_sampler=None, randomized=False, *, model=None, ref_point=None, X_baseline=None, sampler=None,
+                 objective=None, constraints=None, X_pending=None, eta=1e-3, prune_baseline=False, cache_pending=True,
+                 max_iep=0, incremental_nehvi=True, cache_root=False, baseline_base_samples=None, **unused):
+        ConformalAcquisition.__init__(self, alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic,
+                                      grid_sampler, randomized, model=model, sampler=sampler, objective=objective,
+                                      X_pending=X_pending)
+        assert constraints is None
+        if X_baseline is None or ref_point is None:
+            raise TypeError("qConformalNoisyExpectedHypervolumeImprovement needs X_baseline and ref_point")
+        states = self._states()
+        m = len(states)
+        if m != 2:
+            raise NotImplementedError("the box decomposition is built for two objectives")
+        Xb = X_baseline.reshape(-1, X_baseline.shape[-1])
+        if Xb.shape[0] > 31:
+            raise NotImplementedError("cNEHVI is built for at most 31 baseline points: pass the pruned baseline")
+        self.X_baseline = X_baseline
+        self.ref_point = torch.as_tensor(ref_point, dtype=torch.float64).reshape(-1)
+        self._baselines = [ops.NeiBaseline.build(st, Xb) for st in states]
+        S, nb = int(self.sampler.sample_shape[0]), Xb.shape[0]
+        if baseline_base_samples is None:          # botorch: base_sampler = deepcopy(sampler), drawn once for the cell bounds
+            baseline_base_samples = IIDNormalSampler(S, seed=self.sampler.seed).draw((S, nb, m))
+        self.baseline_base_samples = baseline_base_samples.detach().to("cpu", torch.float64).reshape(S, nb, m).contiguous()
+        fb = torch.stack([bl.mub.cpu().unsqueeze(0) + self.baseline_base_samples[:, :, k] @ psd_safe_cholesky(bl.Sbb.cpu()).T
+                          for k, bl in enumerate(self._baselines)], dim=-1)                       # (S, nb, m)
+        self.baseline_samples = fb
+        lo, up = per_sample_cells(self.ref_point, fb)
+        self.register_buffer("cell_lower", lo)
+        self.register_buffer("cell_upper", up)
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        states, m, X, Xf, lead, q, b, G, dev, eps, z, u = self._prepare(X)
+        S, nb = self.baseline_base_samples.shape[0], self.baseline_base_samples.shape[1]
+        if nb + q > 32:
+            raise NotImplementedError("cNEHVI: nb + q <= 32")
+        eps_new = self.sampler.draw((S, G, q, m), dev)                                           # base samples (S, 1, G, q, t)
+        eps_joint = torch.cat([self.baseline_base_samples.to(dev).unsqueeze(1).expand(S, G, nb, m), eps_new], dim=2)
+        outs = [self._per_output(st, k, Xf, q, G, dev, eps, z, u, kind="joint", nei_baseline=self._baselines[k],
+                                 eps_mc=eps_joint[..., k].contiguous(), outputs=self._PER_OUTPUT + ("mc_values",))
+                for k, st in enumerate(states)]
+        acq, values = ops.cehvi_integrate_q(outs, [st.noise for st in states], None, self.cell_lower.to(dev),
+                                            self.cell_upper.to(dev), q=q, alpha=self.alpha, optimistic=self.optimistic,
+                                            cells_per_sample=True, want_values=True)
+        self.last_outputs = {"per_output": outs, "acq": acq, "values": values}
+        return acq.reshape(lead).to(X.dtype)               # _prev_nehvi = 0: pending points are scored jointly instead

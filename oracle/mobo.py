@@ -93,3 +93,29 @@ def cehvi(gps, Xq, *, alpha, temp, grid_res, eps_grid, z, eps_mc, cell_lower, ce
     conf = conf / conf.sum(1, keepdim=True).clamp_min(1e-6)
     acq = ((1 - ood)[:, None] * ((1 - alpha) * conf + alpha * nonconf) * values).sum(1)
     return dict(acq=acq, values=values, mask=mask, logp=logp)
+
+
+def nehvi_cells(gps, X_baseline, eps_b, ref_point):
+    """qNoisyExpectedHypervolumeImprovement._set_cell_bounds (botorch 0.7, from memory -- "parity unpinned"): sample the
+    baseline values under the model, f_b^s = mean + chol(cov) eps_b[s] per output (psd-safe Cholesky: escalating jitter), and
+    decompose the non-dominated region of every sample.  eps_b (S, nb, m) -> (lower, upper) (S, n_cells, m), zero-volume padding."""
+    S = eps_b.shape[0]
+    fb = []
+    for k, gp in enumerate(gps):
+        Kb = gp.k(X_baseline, gp.X)
+        mu = gp.mean + Kb @ gp.alpha
+        Vb = torch.linalg.solve_triangular(gp.L, Kb.T, upper=False)
+        cov = gp.k(X_baseline, X_baseline) - Vb.T @ Vb
+        L, info = torch.linalg.cholesky_ex(cov)
+        jitter = 1e-8
+        while int(info) != 0:
+            L, info = torch.linalg.cholesky_ex(cov + jitter * torch.eye(cov.shape[0], dtype=cov.dtype))
+            jitter *= 10.0
+        fb.append(mu.unsqueeze(0) + eps_b[:, :, k] @ L.T)
+    fb = torch.stack(fb, -1)                                               # (S, nb, m)
+    cells = [box_decomposition_2d(ref_point, fb[s]) for s in range(S)]
+    n = max(c[0].shape[0] for c in cells)
+    pad = ref_point.reshape(1, -1).double()
+    lo = torch.stack([torch.cat([c[0], pad.expand(n - c[0].shape[0], -1)]) for c in cells])
+    up = torch.stack([torch.cat([c[1], pad.expand(n - c[1].shape[0], -1)]) for c in cells])
+    return lo, up, fb

@@ -229,6 +229,55 @@ def test_cehvi_matches_oracle(q, pending, refine):
         assert torch.allclose(acq.last_outputs["values"].cpu(), want["values"], rtol=1e-6, atol=1e-10)
 
 
+@pytest.mark.parametrize("q,pending", [(1, 0), (2, 0), (2, 1)])
+def test_cnehvi_matches_oracle(q, pending):
+    """qConformalNoisyExpectedHypervolumeImprovement (mobo_acquisitions.py:184-219): joint samples with a pruned baseline under
+    every refit model, per-sample box decompositions; against oracle/mobo.py (dense == closed form on the CPU)."""
+    from conformal_bayesopt_b200 import GPModelState
+    from conformal_bayesopt_b200.mobo_acquisitions import qConformalNoisyExpectedHypervolumeImprovement
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    from oracle import mobo
+    dev = _dev()
+    N, d, b, G, m, S, nb = 16, 2, 30, 32, 2, 3, 6
+    g = torch.Generator().manual_seed(9)
+    X = torch.rand(N, d, generator=g, dtype=torch.float64)
+    Y = torch.stack([torch.sin(3 * X.sum(-1)), torch.cos(2 * X[:, 0]) - X[:, 1]], -1)
+    hyp = [(0.0, [0.4 + 0.1 * k] * d, 1.0 + 0.2 * k, 1e-2 * (k + 1)) for k in range(m)]
+    gps = [ogp.build_state(X, Y[:, k], *hyp[k]) for k in range(m)]
+    states = [GPModelState.fit_fixed(X, Y[:, k], *hyp[k], device=dev) for k in range(m)]
+    Xb = torch.cat([X[:nb - 1], torch.rand(1, d, generator=g, dtype=torch.float64)])
+    Xq = torch.rand(b, q, d, generator=g, dtype=torch.float64)
+    if pending:
+        Xq[:, q - pending:] = Xq[0, q - pending:]
+    eps_grid = torch.randn(G, q, m, generator=g, dtype=torch.float64)
+    eps_b = torch.randn(S, nb, m, generator=g, dtype=torch.float64)
+    eps_new = torch.randn(S, G, q, m, generator=g, dtype=torch.float64)
+    eps_mc = torch.cat([eps_b.unsqueeze(1).expand(S, G, nb, m), eps_new], dim=2)
+    z = 2.0 * ((torch.rand(N + q, 8, generator=g) > 0.5).double() - 0.5)
+    u = torch.rand(b, G, q, m, generator=g, dtype=torch.float64)
+    ref = torch.tensor([-1.5, -1.5], dtype=torch.float64)
+    lo, up, fb = mobo.nehvi_cells(gps, Xb, eps_b, ref)
+    gs = IIDNormalSampler(G)
+    gs.set_base_samples(eps_grid)
+    mc = IIDNormalSampler(S, batch_range=(0, -3))
+    mc.set_base_samples(eps_new)
+    acq = qConformalNoisyExpectedHypervolumeImprovement(alpha=0.2, temp=3e-2, grid_res=G, max_grid_refinements=0,
+                                                        ratio_estimator=None, optimistic=True, grid_sampler=gs, randomized=True,
+                                                        model=states, ref_point=ref, X_baseline=Xb.to(dev), sampler=mc,
+                                                        prune_baseline=True, baseline_base_samples=eps_b,
+                                                        X_pending=Xq[0, q - pending:].to(dev) if pending else None)
+    assert torch.allclose(acq.baseline_samples, fb, rtol=1e-9, atol=1e-11)
+    assert torch.allclose(acq.cell_lower.cpu(), lo, rtol=1e-9, atol=1e-11) and torch.equal(torch.isinf(acq.cell_upper.cpu()), torch.isinf(up))
+    acq.fixed_probes, acq.fixed_uniforms = z, u.to(dev)
+    with torch.no_grad():
+        got = acq(Xq[:, :q - pending].to(dev))
+    want = mobo.cehvi(gps, Xq, alpha=0.2, temp=3e-2, grid_res=G, eps_grid=eps_grid, z=z, eps_mc=eps_mc, cell_lower=lo,
+                      cell_upper=up, randomized=True, u_rand=u, optimistic=True, X_baseline=Xb)
+    assert got.shape == (b,) and (want["acq"] > 0).any()
+    assert torch.allclose(acq.last_outputs["values"].cpu(), want["values"], rtol=1e-6, atol=1e-10)
+    assert torch.allclose(got.cpu(), want["acq"], rtol=1e-6, atol=1e-10)
+
+
 @pytest.mark.parametrize("temp,refine,q", [(3e-2, 0, 1), (1e-2, 2, 1), (3e-2, 0, 2), (1e-2, 2, 2), (3e-2, 0, 3), (3e-2, 1, 4),
                                            (0.0, 0, 2)])
 def test_cnei_matches_oracle(temp, refine, q):

@@ -115,6 +115,32 @@ def test_cehvi_dense_equals_closed_form(q, refine):
         assert torch.allclose(mobo.qehvi(f, lo, up)[0, 0], want)
 
 
+@pytest.mark.parametrize("q", [1, 2])
+def test_cnehvi_dense_equals_closed_form(q):
+    """qConformalNoisyExpectedHypervolumeImprovement (mobo_acquisitions.py:184-219): f(X) from the joint refit posterior over
+    [X_baseline; X], one box decomposition per MC sample of the baseline values."""
+    from oracle import mobo
+    N, d, b, G, m, S, nb = 16, 2, 4, 10, 2, 3, 5
+    g, X, Y, gps = _mobo_problem(N, d, m, 7)
+    Xb = torch.cat([X[:nb - 1], torch.rand(1, d, generator=g, dtype=torch.float64)])
+    Xq = torch.rand(b, q, d, generator=g, dtype=torch.float64)
+    eps_grid = torch.randn(G, q, m, generator=g, dtype=torch.float64)
+    eps_b = torch.randn(S, nb, m, generator=g, dtype=torch.float64)
+    eps_new = torch.randn(S, G, q, m, generator=g, dtype=torch.float64)
+    eps_mc = torch.cat([eps_b.unsqueeze(1).expand(S, G, nb, m), eps_new], dim=2)
+    z = 2.0 * ((torch.rand(N + q, 8, generator=g) > 0.5).double() - 0.5)
+    ref = torch.tensor([-1.5, -1.5], dtype=torch.float64)
+    lo, up, fb = mobo.nehvi_cells(gps, Xb, eps_b, ref)
+    assert lo.shape == up.shape and lo.shape[0] == S and lo.shape[2] == m
+    kw = dict(alpha=0.2, temp=3e-2, grid_res=G, eps_grid=eps_grid, z=z, eps_mc=eps_mc, cell_lower=lo, cell_upper=up,
+              optimistic=(q == 1), X_baseline=Xb)       # q = 2, optimistic: 4 masks must agree, G = 10 leaves no mass
+    a = mobo.cehvi(gps, Xq, impl="dense", **kw)
+    c = mobo.cehvi(gps, Xq, impl="closed", **kw)
+    assert (a["acq"] > 0).any()
+    assert torch.allclose(a["acq"], c["acq"], rtol=1e-8, atol=1e-12)
+    assert torch.allclose(a["values"], c["values"], rtol=1e-8, atol=1e-12)
+
+
 def test_qehvi_inclusion_exclusion_is_the_volume_of_the_union():
     """q = 2 against a direct computation: hv(a) + hv(b) - hv(min(a, b)) per cell; per-sample cells pick their own sample."""
     from oracle import mobo
