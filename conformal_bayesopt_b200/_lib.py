@@ -42,7 +42,8 @@ class Params(C.Structure):
                 ("num_mc", C.c_int64), ("num_probes", C.c_int64), ("max_grid_refinements", C.c_int64),
                 ("kind", C.c_int32), ("optimistic", C.c_int32), ("randomized", C.c_int32),
                 ("eps_per_candidate", C.c_int32), ("beta_prime", C.c_double), ("best_f", C.c_double),
-                ("nei", C.POINTER(NeiBaselineF64)), ("refine_reduce", C.c_void_p), ("refine_ctx", C.c_void_p)]
+                ("nei", C.POINTER(NeiBaselineF64)), ("refine_reduce", C.c_void_p), ("refine_ctx", C.c_void_p),
+                ("grid_cov_scale", C.c_void_p)]
 
 
 REFINE_REDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_void_p)

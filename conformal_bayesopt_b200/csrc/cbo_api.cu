@@ -690,6 +690,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             return CBO_OK;
         };
         if (R == 0) {
+            if (p->grid_cov_scale) a.cscale = p->grid_cov_scale + c0 * q;
             set_outputs(a);
             int rs = run_final(a);
             if (rs != CBO_OK) return rs;
@@ -697,7 +698,8 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             // grid refinement (helpers.py:129-189): probe passes keep only the accepted counts; the pass with the
             // smallest grid_score is then re-run into the caller's buffers.  One host sync per pass, like the
             // reference (helpers.py:151-152,177).
-            CBO_LAUNCHED(), cbo::k_fill<<<(n + 255) / 256, 256, 0, s>>>(w.cscale, n, 1.0);
+            if (p->grid_cov_scale) CBO_CUDA(cudaMemcpyAsync(w.cscale, p->grid_cov_scale, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+            else CBO_LAUNCHED(), cbo::k_fill<<<(n + 255) / 256, 256, 0, s>>>(w.cscale, n, 1.0);
             float best_score = INFINITY;
             int best_step = 0;
             double* scratch_acq = w.acq_scratch;          // acquisition values of probe passes are discarded

@@ -109,13 +109,13 @@ class NeiBaseline:
 
 def make_params(*, alpha, temp, grid_res, q=1, num_mc=1, num_probes=8, max_grid_refinements=0, kind="ucb",
                 optimistic=True, randomized=False, eps_per_candidate=False, beta_prime=0.0, best_f=0.0,
-                nei=None, refine_reduce=None) -> "_lib.Params":
+                nei=None, refine_reduce=None, grid_cov_scale=None) -> "_lib.Params":
     """`refine_reduce`: a `_lib.REFINE_REDUCE_FN` instance (kept alive by the caller) or None."""
     fn = C.cast(refine_reduce, C.c_void_p) if refine_reduce is not None else None
     return _lib.Params(float(alpha), float(temp), int(grid_res), int(q), int(num_mc), int(num_probes),
                        int(max_grid_refinements), ACQ_KINDS[kind], int(bool(optimistic)), int(bool(randomized)),
                        int(bool(eps_per_candidate)), float(beta_prime), float(best_f),
-                       C.pointer(nei) if nei is not None else None, fn, None)
+                       C.pointer(nei) if nei is not None else None, fn, None, grid_cov_scale)
 
 
 def workspace(state: GPModelState, b: int, params, chunk: int = 0, grad: bool = False, stream: Optional[int] = None) -> torch.Tensor:
@@ -177,12 +177,18 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
                 if not hook_error:
                     hook_error.append(e)
         reduce_c = _lib.REFINE_REDUCE_FN(_hook)              # kept alive until the call returns
+    cov_scale = param_kw.pop("grid_cov_scale", None)        # (b, q) device tensor: initial row scales of the grid covariance
+    if cov_scale is not None:
+        cov_scale = _f64(cov_scale)
+        _require_cuda(cov_scale)
+        if cov_scale.numel() != b * q:
+            raise _lib.CboError("grid_cov_scale must hold b*q scales")
     baseline = param_kw.pop("nei_baseline", None)
     nei_c = baseline.c_struct() if baseline is not None else None          # kept alive until the call returns
     per_sample = (baseline.Xb.shape[0] + q) if baseline is not None else q
     num_mc = eps_mc.numel() // (G * per_sample)
     params = make_params(q=q, num_mc=num_mc, num_probes=z.shape[-1], eps_per_candidate=eps_per_candidate, nei=nei_c,
-                         refine_reduce=reduce_c, **param_kw)
+                         refine_reduce=reduce_c, grid_cov_scale=_ptr(cov_scale), **param_kw)
     if z.shape[0] != state.N + q:
         raise _lib.CboError(f"z must have N+q = {state.N + q} rows, got {z.shape[0]}")
     if u_rand is not None and u_rand.numel() != b * G * q:

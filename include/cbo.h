@@ -115,6 +115,10 @@ typedef struct {
      * shard; must overwrite them with the values over all ranks (min / max / sum / sum).  NULL: single batch. */
     void (*refine_reduce)(double* stats, void* ctx);
     void* refine_ctx;
+    /* Initial row scales of the grid covariance, b x q (device) or NULL (= 1): the covar_scale products a caller-driven
+     * refinement loop has accumulated (helpers.py:166-182) -- multi-output bands take the loop's decisions over ALL outputs,
+     * so the t per-output calls of one step run with max_grid_refinements = 0 and the scales of the step. */
+    const double* grid_cov_scale;
 } cbo_params;
 
 /* Any pointer may be NULL (that output is skipped) except acq. */

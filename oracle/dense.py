@@ -60,7 +60,7 @@ def posterior(gp: GPState, Xq: torch.Tensor, observation_noise: bool):
 
 
 def conformal_gp_regression(gp: GPState, Xq, target_grid, alpha, temp, z, ratio=None,
-                            randomized=False, u_rand=None):
+                            randomized=False, u_rand=None, score_labels=None):
     """helpers.py:218-333 for one output (t=1).  Xq (b,q,d), target_grid (b,G,q).
 
     Returns conf_pred_mask (b,G,q), refit (dict of dense per-(b,G) quantities), q_conf_scores
@@ -88,7 +88,10 @@ def conformal_gp_regression(gp: GPState, Xq, target_grid, alpha, temp, z, ratio=
 
     # helpers.py:268-272  scores = log N(label; mean, var)
     std = post_var.sqrt()
-    conf_scores = -((labels - mean_train) ** 2) / (2 * post_var) - std.log() - 0.5 * LOG2PI     # (b,G,n)
+    # score_labels: the labels the scores are evaluated AT when they are not the labels the model was refit on -- the
+    # multi-output `.view` scramble of helpers.py:257-258 (oracle/multi.py)
+    lab = labels if score_labels is None else score_labels
+    conf_scores = -((lab - mean_train) ** 2) / (2 * post_var) - std.log() - 0.5 * LOG2PI        # (b,G,n)
 
     threshold = conf_scores[..., N:]                                                            # (b,G,q)
     rank_mask = (threshold.unsqueeze(-2) >= conf_scores.unsqueeze(-1)).to(conf_scores)          # (b,G,n,q)

@@ -150,3 +150,41 @@ def test_assess_coverage_against_reference_source_golden(idx):
     if c["temp"] > 1e-3:
         assert torch.allclose(lb.cpu()[fin], c["out"]["lb"][fin], rtol=RTOL, atol=1e-7)
         assert torch.allclose(ub.cpu()[fin], c["out"]["ub"][fin], rtol=RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["cov_t2", "cov_t2_rand"])
+def test_multi_output_bands_and_coverage_intent_layout(name):
+    """t = 2 (helpers.py:252-258, 336-387, 408-411): the device path implements label_layout='intent' with the reference's
+    joint refinement decisions; checked against oracle/multi.py (whose 'reference' layout is pinned to the reference-source
+    goldens in tests/test_oracle_ref_path.py).  label_layout='reference' is refused loudly on the device."""
+    from conformal_bayesopt_b200 import GPModelState, helpers
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    from oracle import gp as ogp
+    from oracle import multi
+    c = [x for x in _cases("ref_path.pt")["coverage"] if x["name"] == name][0]
+    p, t, G, n = c["problem"], c["t"], c["G"], c["n"]
+    hyp = [(float(p["mean"][k]), p["lengthscale"][k], float(p["outputscale"][k]), float(p["noise"][k])) for k in range(t)]
+    gps = [ogp.build_state(p["X"], p["Y"][:, k], *hyp[k]) for k in range(t)]
+    states = [GPModelState.fit_fixed(p["X"], p["Y"][:, k], *hyp[k], device=DEV) for k in range(t)]
+    oratio = ogp.RatioMLP(*c["ratio_weights"]) if c["ratio"] else None
+    want = multi.assess_coverage(gps, c["X_holdout"], c["Y_holdout"], c["alpha"], c["temp"], G, c["refine"], c["eps_grid"],
+                                 c["z"], ratio=oratio, randomized=c["randomized"], u_rand=c["u_rand"], label_layout="intent")
+    gs = IIDNormalSampler(G, resample=False, collapse_batch_dims=False)
+    gs.set_base_samples(c["eps_grid"])                                     # (G, n, 1, t)
+    u = None if c["u_rand"] is None else c["u_rand"].to(DEV)
+    std_cov, conf_cov = helpers.assess_coverage(states, c["X_holdout"].to(DEV), c["Y_holdout"].to(DEV), c["alpha"], c["temp"], G,
+                                                c["refine"], _ratio(c), c["randomized"], probes=c["z"], u_rand=u, grid_sampler=gs)
+    assert abs(std_cov - want[0]) < 1e-6 and abs(conf_cov - want[1]) < 1e-6
+    tg, w, mk, _, ood = helpers.construct_conformal_bands(states, c["X_holdout"].to(DEV)[:, None], c["alpha"], c["temp"], G,
+                                                          c["refine"], gs, _ratio(c), randomized=c["randomized"],
+                                                          probes=c["z"], u_rand=u)
+    assert tg.shape == (n, G, 1, t) and w.shape == (n, G, 1, 1) and mk.shape == (n, G, 1, t) and ood.shape == (n, G, 1, t)
+    assert torch.allclose(tg.cpu(), want[2], rtol=RTOL, atol=1e-9)
+    assert torch.allclose(mk.cpu(), want[3], rtol=0, atol=1e-6)
+    lb, ub = helpers.conf_mask_to_bounds(tg, mk)
+    fin = torch.isfinite(want[4])
+    assert torch.equal(torch.isfinite(lb.cpu()), fin)
+    assert torch.allclose(lb.cpu()[fin], want[4][fin], rtol=RTOL, atol=1e-7) and torch.allclose(ub.cpu()[fin], want[5][fin], rtol=RTOL, atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        helpers.construct_conformal_bands(states, c["X_holdout"].to(DEV)[:, None], c["alpha"], c["temp"], G, 0, gs, None,
+                                          label_layout="reference")

@@ -92,3 +92,53 @@ def test_closed_form_against_reference_source_golden_n1024(idx):
     gp, Xq, kw = oracle_inputs(c)
     got = closed_form.conformal_acquisition(gp, Xq, **kw)
     check_against_golden(c, got)
+
+
+def _multi_gps(c):
+    p = c["problem"]
+    t = c["t"]
+    return [ogp.build_state(p["X"], p["Y"][:, k], float(p["mean"][k]), p["lengthscale"][k], float(p["outputscale"][k]),
+                            float(p["noise"][k])) for k in range(t)]
+
+
+@pytest.mark.parametrize("name", ["cov_t2", "cov_t2_rand"])
+def test_multi_output_bands_against_reference_source_golden(name):
+    """t = 2: oracle/multi.py with label_layout='reference' (the `.view` scramble of helpers.py:257-258)
+    reproduces what helpers.assess_coverage itself computes; label_layout='intent' differs (that is the point of the flag)."""
+    from oracle import multi
+    c = [x for x in load("ref_path.pt")["coverage"] if x["name"] == name][0]
+    gps = _multi_gps(c)
+    ratio = ogp.RatioMLP(*c["ratio_weights"]) if c["ratio"] else None
+    kw = dict(ratio=ratio, randomized=c["randomized"], u_rand=c["u_rand"])
+    std_cov, conf_cov, grid, mask, lb, ub = multi.assess_coverage(
+        gps, c["X_holdout"], c["Y_holdout"], c["alpha"], c["temp"], c["G"], c["refine"], c["eps_grid"], c["z"],
+        label_layout="reference", **kw)
+    want = c["out"]
+    assert abs(std_cov - want["std_coverage"]) < 1e-6 and abs(conf_cov - want["conformal_coverage"]) < 1e-6
+    assert torch.allclose(grid, want["target_grid"], rtol=RTOL, atol=1e-9)
+    assert torch.allclose(mask, want["conf_pred_mask"], rtol=0, atol=1e-6), (mask - want["conf_pred_mask"]).abs().max()
+    fin = torch.isfinite(want["lb"])
+    assert torch.equal(torch.isfinite(lb), fin)
+    assert torch.allclose(lb[fin], want["lb"][fin], rtol=RTOL, atol=1e-7) and torch.allclose(ub[fin], want["ub"][fin], rtol=RTOL, atol=1e-7)
+    _, _, grid_i, mask_i, _, _ = multi.assess_coverage(
+        gps, c["X_holdout"], c["Y_holdout"], c["alpha"], c["temp"], c["G"], c["refine"], c["eps_grid"], c["z"],
+        label_layout="intent", **kw)
+    assert (mask_i - mask).abs().max() > 1e-3          # the scramble is not a no-op
+
+
+def test_multi_output_intent_layout_is_t_independent_single_output_problems():
+    """label_layout='intent' without refinement == the single-output oracle per output (stacked); with refinement the
+    outputs are tied through the joint accept statistics only."""
+    from oracle import multi
+    c = [x for x in load("ref_path.pt")["coverage"] if x["name"] == "cov_t2"][0]
+    gps = _multi_gps(c)
+    X = c["X_holdout"][:6, None]
+    eps = c["eps_grid"].movedim(0, 1)[:6]                                   # (n, G, 1, t)
+    grid, logp, mask, ood = multi.construct_conformal_bands(gps, X, c["alpha"], c["temp"], c["G"], 0, eps, c["z"],
+                                                            label_layout="intent")
+    lp = 0.0
+    for k, gp in enumerate(gps):
+        g1, l1, m1, _, o1 = dense.construct_conformal_bands(gp, X, c["alpha"], c["temp"], c["G"], 0, eps[..., k], c["z"])
+        assert torch.allclose(grid[..., k], g1) and torch.allclose(mask[..., k], m1) and torch.allclose(ood[..., k], o1)
+        lp = lp + l1
+    assert torch.allclose(logp, lp)
