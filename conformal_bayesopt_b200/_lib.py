@@ -13,7 +13,7 @@ EXPORTS = [
     "cbo_version", "cbo_status_str", "cbo_last_cuda_error", "cbo_padded_n", "cbo_workspace_bytes",
     "cbo_conformal_acq_f64", "cbo_conformal_acq_host_f64", "cbo_conf_mask_to_bounds_f64",
     "cbo_ratio_forward_f64", "cbo_gemm_tn_f64", "cbo_kernel_rows_f64", "cbo_timing_enable", "cbo_timing_collect",
-    "cbo_cehvi_integrate_f64", "cbo_cehvi_integrate_q_f64", "cbo_conformal_acq_grad_f64", "cbo_workspace_bytes_grad",
+    "cbo_cehvi_integrate_f64", "cbo_cehvi_integrate_q_f64", "cbo_cehvi_integrate_q_grad_f64", "cbo_conformal_acq_grad_f64", "cbo_workspace_bytes_grad",
     "cbo_model_workspace_bytes", "cbo_model_build_f64",
     "cbo_model_append_workspace_bytes", "cbo_model_append_f64",
     "cbo_ratio_train_workspace_bytes", "cbo_ratio_train_step_f64", "cbo_sgld_update_f64", "cbo_launch_count",
@@ -37,13 +37,17 @@ class NeiBaselineF64(C.Structure):
     _fields_ = [("nb", C.c_int64), ("Xb", c_dp), ("KbX", c_dp), ("Sbb", c_dp), ("mub", c_dp)]
 
 
+class ExtAdjointsF64(C.Structure):
+    _fields_ = [("mask_bar", c_dp), ("ood_bar", c_dp), ("f_bar", c_dp)]
+
+
 class Params(C.Structure):
     _fields_ = [("alpha", C.c_double), ("temp", C.c_double), ("grid_res", C.c_int64), ("q", C.c_int64),
                 ("num_mc", C.c_int64), ("num_probes", C.c_int64), ("max_grid_refinements", C.c_int64),
                 ("kind", C.c_int32), ("optimistic", C.c_int32), ("randomized", C.c_int32),
                 ("eps_per_candidate", C.c_int32), ("beta_prime", C.c_double), ("best_f", C.c_double),
                 ("nei", C.POINTER(NeiBaselineF64)), ("refine_reduce", C.c_void_p), ("refine_ctx", C.c_void_p),
-                ("grid_cov_scale", C.c_void_p)]
+                ("grid_cov_scale", C.c_void_p), ("ext_adjoints", C.POINTER(ExtAdjointsF64))]
 
 
 REFINE_REDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_void_p)
@@ -117,6 +121,8 @@ def load():
     lib.cbo_cehvi_integrate_q_f64.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, PP, PP, PP, PP, PP, PP,
                                               C.POINTER(C.c_double), PP, c_dp, c_dp, c_dp, C.c_int64, C.c_int32, C.c_double,
                                               C.c_int32, c_dp, c_dp, c_dp]
+    lib.cbo_cehvi_integrate_q_grad_f64.restype = C.c_int
+    lib.cbo_cehvi_integrate_q_grad_f64.argtypes = lib.cbo_cehvi_integrate_q_f64.argtypes[:-1] + [PP, PP, PP, c_dp]
     lib.cbo_model_workspace_bytes.restype = C.c_size_t
     lib.cbo_model_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
     lib.cbo_model_build_f64.restype = C.c_int
@@ -140,7 +146,7 @@ def load():
     lib.cbo_timing_enable.argtypes = [C.c_int]
     lib.cbo_timing_collect.restype = C.c_int
     lib.cbo_timing_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
-    if lib.cbo_version() != 101:
+    if lib.cbo_version() != 102:
         raise CboError(f"libcbo.so version mismatch: {lib.cbo_version()}")
     _LIB = lib
     return lib

@@ -6,12 +6,12 @@
 reference (acquisitions.py:80-86, 107-113, 143-149) and the BoTorch bases it mixes in
 (`model`, `beta` / `best_f`, `sampler`, `objective`, `posterior_transform`, `X_pending`).
 
-Joint batches q <= 4 (incl. X_pending) are supported.  `forward` is differentiable in X for cUCB / cEI
+Joint batches q <= 4 (incl. X_pending) are supported.  `forward` is differentiable in X for cUCB / cEI / cNEI
 (q = 1 and joint batches up to 4, the reference's default SGLD loop uses q_batch_size = 2): when X
 requires grad, ONE call of cbo_conformal_acq_grad_f64 returns the values and d acq / d X, and a custom
 autograd.Function hands the stored Jacobian blocks to `backward` (what optimize_acqf_sgld / L-BFGS-B need:
-conformalbo/optim/optimize.py:224-235).  Not built yet (raise, never silently fall back): non-identity objectives /
-posterior transforms, gradients for cNEI / cEHVI.
+conformalbo/optim/optimize.py:224-235; cEHVI / cNEHVI: mobo_acquisitions.py).  Not built (raise, never silently fall
+back): non-identity objectives / posterior transforms.
 """
 from __future__ import annotations
 
@@ -112,8 +112,8 @@ class ConformalAcquisition(nn.Module):
             raise ValueError("grid refinement / pending points are not captured")
         if not self.grid_sampler.collapse_batch_dims or self.grid_sampler.resample or self.sampler.resample:
             raise ValueError("base samples that change per call are not captured")
-        if want_grad and self._kind not in ("ucb", "ei"):
-            raise ValueError("d acq / d X is built for cUCB / cEI")
+        if self._kind not in ("ucb", "ei", "nei"):
+            raise ValueError("one library call per step is captured; the multi-objective acquisitions take several")
         state = as_state(self.model)
         dev, G = state.device, self.grid_res
         self.grid_sampler._sample_shape = torch.Size([G])
@@ -137,8 +137,6 @@ class ConformalAcquisition(nn.Module):
         if self.X_pending is not None:                           # concatenate_pending_points
             X = torch.cat([X, self.X_pending.to(X).expand(*X.shape[:-2], -1, -1)], dim=-2)
         lead, (q, d) = X.shape[:-2], X.shape[-2:]
-        if want_grad and self._kind not in ("ucb", "ei"):
-            raise NotImplementedError("d acq / d X is built for cUCB / cEI (SURVEY.md §8f-1); call under torch.no_grad()")
         dev = X.device
         Xf = X.detach().reshape(-1, q, d)
         b, G = Xf.shape[0], self.grid_res

@@ -27,6 +27,7 @@
 #include "model_build.cuh"
 #include "model_append.cuh"
 #include "score_q_bwd.cuh"
+#include "nei_bwd.cuh"
 
 namespace {
 
@@ -96,6 +97,7 @@ struct Workspace {
     double *UW, *V, *mu, *ut, *drc, *rn;
     double *cscale, *nacc, *acq_scratch, *stats;      // refinement only
     double* nei_values;                               // cNEI only: C x S x G
+    double *val_bar, *cv_bar;                         // cNEI gradient only: C x S x G value adjoints, C x nb adjoints of c
     double* splitk;                                   // split-K partial tiles (calls with <= 32 candidate points)
     double *X3, *adj;                                 // gradient only: C x Np solve scratch, C x ADJ_STRIDE adjoints
     size_t bytes;
@@ -135,6 +137,9 @@ Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, 
     w.stats = c.take<double>(8);
     w.nei_values = c.take<double>((p->kind == CBO_ACQ_NEI || p->kind == CBO_ACQ_JOINT) ? C * p->num_mc * p->grid_res : 1);
     w.splitk = c.take<double>(cbo::gemm_splitk_scratch_doubles((int)Np));
+    const bool nei_kind = p->kind == CBO_ACQ_NEI || p->kind == CBO_ACQ_JOINT;
+    w.val_bar = c.take<double>(grad && nei_kind ? C * p->num_mc * p->grid_res : 1);
+    w.cv_bar = c.take<double>(grad && nei_kind ? C * cbo::NEI_MAX_NB : 1);
     w.X3 = c.take<double>(grad ? C * Np : 1);
     w.adj = c.take<double>(grad ? C * (cbo::ADJQ_STRIDE > cbo::ADJ_STRIDE ? cbo::ADJQ_STRIDE : cbo::ADJ_STRIDE) : 1);
     w.bytes = c.off;
@@ -314,6 +319,7 @@ cudaError_t launch_score_q_bwd_t(const cbo::ScoreQBwdArgs& a, cudaStream_t st) {
 
 cudaError_t launch_score_q_bwd(const cbo::ScoreQBwdArgs& a, int q, bool soft, cudaStream_t st) {
     switch (q) {
+        case 1: return soft ? launch_score_q_bwd_t<1, true>(a, st) : launch_score_q_bwd_t<1, false>(a, st);
         case 2: return soft ? launch_score_q_bwd_t<2, true>(a, st) : launch_score_q_bwd_t<2, false>(a, st);
         case 3: return soft ? launch_score_q_bwd_t<3, true>(a, st) : launch_score_q_bwd_t<3, false>(a, st);
         case 4: return soft ? launch_score_q_bwd_t<4, true>(a, st) : launch_score_q_bwd_t<4, false>(a, st);
@@ -344,12 +350,57 @@ cudaError_t launch_score_q(const cbo::ScoreQArgs& a, int q, bool soft, cudaStrea
     }
 }
 
-template <int Q>
+template <int Q, bool BWD>
 cudaError_t launch_ehvi_q(const cbo::EhviQArgs& a, size_t smem, cudaStream_t st) {
     static cbo::SmemOptIn optin;
-    if (cudaError_t e = optin.ensure(cbo::k_ehvi_q<Q>, smem); e != cudaSuccess) return e;
-    CBO_LAUNCHED(), cbo::k_ehvi_q<Q><<<(a.b + cbo::EHVIQ_WARPS - 1) / cbo::EHVIQ_WARPS, cbo::EHVIQ_WARPS * 32, smem, st>>>(a);
+    if (cudaError_t e = optin.ensure(cbo::k_ehvi_q<Q, BWD>, smem); e != cudaSuccess) return e;
+    CBO_LAUNCHED(), cbo::k_ehvi_q<Q, BWD><<<(a.b + cbo::EHVIQ_WARPS - 1) / cbo::EHVIQ_WARPS, cbo::EHVIQ_WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();
+}
+
+int cehvi_integrate_q_impl(int64_t m, int64_t b, int64_t G, int64_t S, int64_t q, const double* const* mask,
+                           const double* const* logp, const double* const* grid, const double* const* mu,
+                           const double* const* ood, const double* const* cov, const double* noise_host,
+                           const double* const* fx, const double* eps_mc, const double* cell_lower,
+                           const double* cell_upper, int64_t n_cells, int32_t cells_per_sample, double alpha,
+                           int32_t optimistic, double* acq, double* values_out, bool bwd, double* const* mask_bar,
+                           double* const* ood_bar, double* const* f_bar, void* stream) {
+    if (!mask || !logp || !grid || !mu || !ood || !cell_lower || !cell_upper || !acq) return CBO_ERR_INVALID_ARG;
+    if (m < 1 || b <= 0 || G < 2 || S < 1 || n_cells < 1 || q < 1) return CBO_ERR_INVALID_ARG;
+    if (!fx && (!cov || !noise_host || !eps_mc)) return CBO_ERR_INVALID_ARG;
+    if (bwd && (!values_out || !mask_bar || !ood_bar || !f_bar)) return CBO_ERR_INVALID_ARG;
+    if (m > cbo::MAX_M || q > cbo::MAX_Q) return CBO_ERR_UNSUPPORTED;
+    const int64_t ncell_tot = n_cells * (cells_per_sample ? S : 1);
+    const size_t smem = cbo::ehvi_q_smem_bytes((int)m, (int)q, (int)ncell_tot);
+    if (smem > 200 * 1024) return CBO_ERR_UNSUPPORTED;
+    cbo::EhviQArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = (int)m; a.b = (int)b; a.G = (int)G; a.S = (int)S; a.q = (int)q; a.n_cells = (int)n_cells; a.optimistic = optimistic;
+    a.cells_per_sample = cells_per_sample; a.alpha_lvl = alpha;
+    for (int k = 0; k < m; ++k) {
+        if (!mask[k] || !logp[k] || !grid[k] || !mu[k] || !ood[k]) return CBO_ERR_INVALID_ARG;
+        a.mask[k] = mask[k]; a.logp[k] = logp[k]; a.grid[k] = grid[k]; a.mu[k] = mu[k]; a.ood[k] = ood[k];
+        a.fx[k] = fx ? fx[k] : nullptr;
+        if (!a.fx[k]) {
+            if (!cov || !cov[k] || !noise_host || !eps_mc) return CBO_ERR_INVALID_ARG;
+            a.cov[k] = cov[k]; a.noise[k] = noise_host[k];
+        }
+        if (bwd) {
+            if (!mask_bar[k] || !ood_bar[k]) return CBO_ERR_INVALID_ARG;
+            a.mask_bar[k] = mask_bar[k]; a.ood_bar[k] = ood_bar[k]; a.f_bar[k] = f_bar[k];
+        }
+    }
+    a.eps_mc = eps_mc; a.cell_lower = cell_lower; a.cell_upper = cell_upper; a.acq = acq; a.values = values_out;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    switch (q) {
+        case 1: e = bwd ? launch_ehvi_q<1, true>(a, smem, st) : launch_ehvi_q<1, false>(a, smem, st); break;
+        case 2: e = bwd ? launch_ehvi_q<2, true>(a, smem, st) : launch_ehvi_q<2, false>(a, smem, st); break;
+        case 3: e = bwd ? launch_ehvi_q<3, true>(a, smem, st) : launch_ehvi_q<3, false>(a, smem, st); break;
+        default: e = bwd ? launch_ehvi_q<4, true>(a, smem, st) : launch_ehvi_q<4, false>(a, smem, st); break;
+    }
+    CBO_CUDA(e);
+    return CBO_OK;
 }
 
 }  // namespace
@@ -508,10 +559,16 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
     int st = validate(gp, p, b);
     if (st != CBO_OK) return st;
     const bool grad = dX != nullptr;
-    if (grad) {   // the reverse pass is built for cUCB / cEI (q = 1: throughput kernels; 2 <= q <= 4: k_score_q_bwd)
-        if (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI) return CBO_ERR_UNSUPPORTED;
-        if (p->q == 1 && (p->grid_res > 2048 || cbo::score_bwd_groups_for((int)gp->Np, (int)p->grid_res, 16) < 1)) return CBO_ERR_UNSUPPORTED;
-        if (p->q > 1 && cbo::score_q_bwd_smem_bytes((int)gp->Np, (int)p->grid_res, (int)p->q) > 227 * 1024) return CBO_ERR_UNSUPPORTED;
+    const bool nei_kind = p->kind == CBO_ACQ_NEI || p->kind == CBO_ACQ_JOINT;
+    const cbo_ext_adjoints_f64* ext = grad ? p->ext_adjoints : nullptr;
+    // reverse pass: q = 1 cUCB / cEI on the throughput kernels; joint batches, cNEI / joint samples and external adjoints on
+    // k_score_q_bwd (one CTA or cluster per joint batch, q = 1 included)
+    const bool qpath = p->q > 1 || (grad && (nei_kind || ext));
+    if (grad) {
+        if (ext && (!ext->mask_bar || !ext->ood_bar)) return CBO_ERR_INVALID_ARG;
+        if (p->kind == CBO_ACQ_JOINT && !ext) return CBO_ERR_UNSUPPORTED;     // joint samples have no integration of their own to differentiate
+        if (!qpath && (p->grid_res > 2048 || cbo::score_bwd_groups_for((int)gp->Np, (int)p->grid_res, 16) < 1)) return CBO_ERR_UNSUPPORTED;
+        if (qpath && cbo::score_q_bwd_smem_bytes((int)gp->Np, (int)p->grid_res, (int)p->q) > 227 * 1024) return CBO_ERR_UNSUPPORTED;
     }
     if (!Xq || !eps_grid || !z || !eps_mc || !out || !out->acq || !workspace) return CBO_ERR_INVALID_ARG;
     if (p->randomized && !u_rand) return CBO_ERR_INVALID_ARG;
@@ -599,9 +656,10 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
         cbo::ScoreQArgs aq;
         aq.V = w.V; aq.Xq = Xc; aq.inv_ls = gp->inv_lengthscale; aq.d = d;
         aq.post_cov = (q > 1 && out->post_var) ? out->post_var + c0 * q * q : nullptr;
-        auto run_score = [&](const cbo::ScoreArgs& x_in) -> cudaError_t {
-            cbo::ScoreArgs x = x_in;
-            if (p->kind == CBO_ACQ_NEI || p->kind == CBO_ACQ_JOINT) {
+        cbo::NeiArgs na_last;                                     // the joint-sample launch of the final pass (its reverse needs it)
+        memset(&na_last, 0, sizeof(na_last));
+        auto run_nei = [&](cbo::ScoreArgs& x) -> cudaError_t {
+            {
                 cbo::NeiArgs na;
                 na.N = N; na.Np = Np; na.d = d; na.nb = (int)p->nei->nb; na.G = G; na.S = (int)p->num_mc; na.n_cand = ncand;
                 na.tiles_n = tiles_n; na.noise = gp->noise; na.kappa = gp->outputscale; na.temp = p->temp;
@@ -617,7 +675,14 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                     if (e != cudaSuccess) return e;
                 }
                 x.ext_values = na.values;
+                na_last = na;
             }
+            return cudaGetLastError();
+        };
+        auto run_score = [&](const cbo::ScoreArgs& x_in) -> cudaError_t {
+            cbo::ScoreArgs x = x_in;
+            if (nei_kind)
+                if (cudaError_t e = run_nei(x); e != cudaSuccess) return e;
             if (q == 1) return soft_path ? launch_score<true>(x, s, many) : launch_score<false>(x, s, many);
             cbo::ScoreQArgs y = aq;
             y.base = x;
@@ -646,7 +711,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 CBO_CUDA(run_score(fa));
             }
             if (!grad) return CBO_OK;
-            if (q == 1) {
+            if (!qpath) {
                 TimeScope ts_(T_SCORE_BWD, s, 1);
                 cbo::ScoreBwdArgs ba;
                 ba.f = fa;
@@ -656,15 +721,32 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             } else {
                 TimeScope ts_(T_SCORE_BWD, s, 1);
                 cbo::ScoreQBwdArgs bq;
+                memset(&bq, 0, sizeof(bq));
                 bq.f = aq;
                 bq.f.base = fa;
                 bq.f.post_cov = nullptr;
                 bq.wbar = w.X3;                                      // v (w.V) is read by phase 0: right-hand sides go to the scratch buffer
                 bq.adjq = w.adj;
+                if (nei_kind) CBO_CUDA(run_nei(bq.f.base));          // sample values of the joint posterior (constants of k_score_q_bwd)
+                if (ext) {
+                    bq.ext_mask_bar = ext->mask_bar + c0 * G * q;
+                    bq.ext_ood_bar = ext->ood_bar + c0 * q;
+                    if (!nei_kind && ext->f_bar) bq.ext_f_bar = ext->f_bar + c0 * int64_t(p->num_mc) * G * q;
+                } else if (nei_kind) {
+                    bq.val_bar = w.val_bar;
+                }
                 CBO_CUDA(launch_score_q_bwd(bq, q, soft_path, s));
+                if (nei_kind && (!ext || ext->f_bar)) {              // reverse of the joint posterior: adds to adjq / wbar, writes cv_bar
+                    cbo::NeiBwdArgs nb_;
+                    nb_.f = na_last;
+                    nb_.val_bar = ext ? ext->f_bar + c0 * int64_t(p->num_mc) * G * q : w.val_bar;
+                    nb_.adjq = w.adj; nb_.wbar = w.X3; nb_.cv_bar = w.cv_bar;
+                    CBO_CUDA(cbo::launch_nei_values_q_bwd(nb_, q, s));
+                }
             }
-            double* rhs = (q == 1) ? w.V : w.X3;                    // right-hand sides w_bar'
-            double* sol = (q == 1) ? w.X3 : w.V;                    // scratch of the two-pass solve
+            const bool nei_rev = qpath && nei_kind && (!ext || ext->f_bar);
+            double* rhs = !qpath ? w.V : w.X3;                      // right-hand sides w_bar'
+            double* sol = !qpath ? w.X3 : w.V;                      // scratch of the two-pass solve
             {
                 TimeScope ts_(T_GEMM_BWD, s, 2);
                 CBO_CUDA(cbo::launch_gemm_tn(rhs, Np, gp->linv, Np, sol, Np, n, Np, Np, cbo::TRI_LOWER, nullptr, s, num_sms(), splitk));
@@ -672,18 +754,19 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             }
             {
                 TimeScope ts_(T_ROWS_BWD, s, ratio ? 2 : 1);
-                if (q == 1 && splitk == nullptr)
+                if (!qpath && splitk == nullptr)
                     CBO_CUDA(cbo::launch_rows_bwd(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->alpha, rhs,
                                                   w.UW, w.adj, dX + c0 * q * d, num_sms(), s));
                 else    // joint batches, and q = 1 calls with a handful of candidates (CTA per candidate point)
                     CBO_LAUNCHED(), cbo::k_rows_bwd_q<<<n, cbo::RBQ_THREADS, 0, s>>>(Xc, n, q, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale,
                                                                  gp->alpha, rhs, w.UW, w.adj,
-                                                                 q == 1 ? cbo::ADJ_STRIDE : cbo::ADJQ_STRIDE, q == 1 ? 1 : 0,
-                                                                 dX + c0 * q * d);
+                                                                 !qpath ? cbo::ADJ_STRIDE : cbo::ADJQ_STRIDE, !qpath ? 1 : 0,
+                                                                 nei_rev ? p->nei->Xb : nullptr, nei_rev ? (int)p->nei->nb : 0,
+                                                                 nei_rev ? w.cv_bar : nullptr, dX + c0 * q * d);
                 if (ratio)
                     CBO_CUDA(cbo::launch_ratio_mlp_bwd(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2,
                                                        ratio->b2, ratio->W3, ratio->b3, 1e-6, w.adj,
-                                                       q == 1 ? cbo::ADJ_STRIDE : cbo::ADJQ_STRIDE, q == 1 ? 2 : 1,
+                                                       !qpath ? cbo::ADJ_STRIDE : cbo::ADJQ_STRIDE, !qpath ? 2 : 1,
                                                        dX + c0 * q * d, num_sms(), s));
                 CBO_CUDA(cudaGetLastError());
             }
@@ -791,37 +874,21 @@ int cbo_cehvi_integrate_q_f64(int64_t m, int64_t b, int64_t G, int64_t S, int64_
                               const double* const* fx, const double* eps_mc, const double* cell_lower,
                               const double* cell_upper, int64_t n_cells, int32_t cells_per_sample, double alpha,
                               int32_t optimistic, double* acq, double* values_out, void* stream) {
-    if (!mask || !logp || !grid || !mu || !ood || !cell_lower || !cell_upper || !acq) return CBO_ERR_INVALID_ARG;
-    if (m < 1 || b <= 0 || G < 2 || S < 1 || n_cells < 1 || q < 1) return CBO_ERR_INVALID_ARG;
-    if (!fx && (!cov || !noise_host || !eps_mc)) return CBO_ERR_INVALID_ARG;
-    if (m > cbo::MAX_M || q > cbo::MAX_Q) return CBO_ERR_UNSUPPORTED;
-    const int64_t ncell_tot = n_cells * (cells_per_sample ? S : 1);
-    const size_t smem = cbo::ehvi_q_smem_bytes((int)m, (int)q, (int)ncell_tot);
-    if (smem > 200 * 1024) return CBO_ERR_UNSUPPORTED;
-    cbo::EhviQArgs a;
-    memset(&a, 0, sizeof(a));
-    a.m = (int)m; a.b = (int)b; a.G = (int)G; a.S = (int)S; a.q = (int)q; a.n_cells = (int)n_cells; a.optimistic = optimistic;
-    a.cells_per_sample = cells_per_sample; a.alpha_lvl = alpha;
-    for (int k = 0; k < m; ++k) {
-        if (!mask[k] || !logp[k] || !grid[k] || !mu[k] || !ood[k]) return CBO_ERR_INVALID_ARG;
-        a.mask[k] = mask[k]; a.logp[k] = logp[k]; a.grid[k] = grid[k]; a.mu[k] = mu[k]; a.ood[k] = ood[k];
-        a.fx[k] = fx ? fx[k] : nullptr;
-        if (!a.fx[k]) {
-            if (!cov || !cov[k] || !noise_host || !eps_mc) return CBO_ERR_INVALID_ARG;
-            a.cov[k] = cov[k]; a.noise[k] = noise_host[k];
-        }
-    }
-    a.eps_mc = eps_mc; a.cell_lower = cell_lower; a.cell_upper = cell_upper; a.acq = acq; a.values = values_out;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e;
-    switch (q) {
-        case 1: e = launch_ehvi_q<1>(a, smem, st); break;
-        case 2: e = launch_ehvi_q<2>(a, smem, st); break;
-        case 3: e = launch_ehvi_q<3>(a, smem, st); break;
-        default: e = launch_ehvi_q<4>(a, smem, st); break;
-    }
-    CBO_CUDA(e);
-    return CBO_OK;
+    return cehvi_integrate_q_impl(m, b, G, S, q, mask, logp, grid, mu, ood, cov, noise_host, fx, eps_mc, cell_lower, cell_upper,
+                                  n_cells, cells_per_sample, alpha, optimistic, acq, values_out, false, nullptr, nullptr,
+                                  nullptr, stream);
+}
+
+int cbo_cehvi_integrate_q_grad_f64(int64_t m, int64_t b, int64_t G, int64_t S, int64_t q, const double* const* mask,
+                                   const double* const* logp, const double* const* grid, const double* const* mu,
+                                   const double* const* ood, const double* const* cov, const double* noise_host,
+                                   const double* const* fx, const double* eps_mc, const double* cell_lower,
+                                   const double* cell_upper, int64_t n_cells, int32_t cells_per_sample, double alpha,
+                                   int32_t optimistic, double* acq, double* values_out, double* const* mask_bar,
+                                   double* const* ood_bar, double* const* f_bar, void* stream) {
+    return cehvi_integrate_q_impl(m, b, G, S, q, mask, logp, grid, mu, ood, cov, noise_host, fx, eps_mc, cell_lower, cell_upper,
+                                  n_cells, cells_per_sample, alpha, optimistic, acq, values_out, true, mask_bar, ood_bar,
+                                  f_bar, stream);
 }
 
 size_t cbo_model_workspace_bytes(int64_t N, int64_t d) {

@@ -135,11 +135,16 @@ struct EhviQArgs {
     const double* cell_upper;
     double* acq;                   // b
     double* values;                // b x G or nullptr: MC-averaged hyper-volume improvement per grid point
+    // reverse pass (k_ehvi_q<Q, true>; values is then required): adjoints of d acq[c] for the per-output gradient calls
+    // (cbo_ext_adjoints_f64)
+    double* mask_bar[MAX_M];       // b x G x q
+    double* ood_bar[MAX_M];        // b x q
+    double* f_bar[MAX_M];          // b x S x G x q   adjoint of the samples (internal sampling or fx)
 };
 
 constexpr int EHVIQ_WARPS = 8;
 
-template <int Q>
+template <int Q, bool BWD = false>
 __global__ void __launch_bounds__(EHVIQ_WARPS * 32)
 k_ehvi_q(const EhviQArgs p) {
     extern __shared__ double s_dyn[];              // cells: lower | upper ; then per warp: m x (shr[Q*Q], Lf[Q*Q])
@@ -269,6 +274,120 @@ k_ehvi_q(const EhviQArgs p) {
     if (lane == 0) {
         const double r = (1.0 - ood) * ((1.0 - p.alpha_lvl) * A / fmax(scw, 1e-6) + p.alpha_lvl * B / fmax(snc, 1e-6));
         p.acq[c] = bad ? nan("") : r;
+    }
+    if constexpr (BWD) {
+        // ---- reverse: d acq[c] / d (mask_kgj, ood_kj, f_sgkj); the grid, its log-density and the optimistic mask are constants ----
+        __syncwarp();
+        const double dcw = fmax(scw, 1e-6), dnc = fmax(snc, 1e-6);
+        const double inner = (1.0 - p.alpha_lvl) * A / dcw + p.alpha_lvl * B / dnc;
+        const double nanv = nan("");
+        if (lane == 0)
+            for (int k = 0; k < m; ++k)
+                for (int j = 0; j < Q; ++j) {
+                    double others = 1.0;
+                    for (int k2 = 0; k2 < m; ++k2)
+                        for (int j2 = 0; j2 < Q; ++j2)
+                            if (k2 != k || j2 != j) others *= p.ood[k2][int64_t(c) * Q + j2];
+                    p.ood_bar[k][int64_t(c) * Q + j] = bad ? nanv : -inner * others;
+                }
+        const double c1 = (1.0 - ood) * (1.0 - p.alpha_lvl), c2 = (1.0 - ood) * p.alpha_lvl;
+        for (int g = lane; g < G; g += 32) {
+            const int64_t ix = (int64_t(c) * G + g) * Q;
+            double mk = 1.0, op = 1.0, lp = 0.0;
+            double mf[MAX_M][Q];
+            for (int k = 0; k < m; ++k) {
+                lp += p.logp[k][int64_t(c) * G + g];
+                double dev[Q];
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    const double muj = p.mu[k][int64_t(c) * Q + j], yg = p.grid[k][ix + j];
+                    mk *= p.mask[k][ix + j];
+                    if (p.optimistic) op *= (yg >= muj) ? 1.0 : 0.0;
+                    dev[j] = yg - muj;
+                    mf[k][j] = muj;
+                }
+                if (!p.fx[k]) {
+                    const double* shr = wmat + size_t(k) * 2 * Q * Q;
+#pragma unroll
+                    for (int j = 0; j < Q; ++j)
+#pragma unroll
+                        for (int l = 0; l < Q; ++l) mf[k][j] = fma(shr[j * Q + l], dev[l], mf[k][j]);
+                }
+            }
+            const double kd = 1.0 / fmax(exp(lp), 1e-6);
+            const double val = p.values[int64_t(c) * G + g];
+            const double cw = mk * op * kd, nc = (1.0 - mk) * op;
+            const double val_bar = (c1 * cw / dcw + c2 * nc / dnc) / double(S);
+            const double cw_bar = c1 * (val / dcw - ((scw > 1e-6) ? A / (dcw * dcw) : 0.0));
+            const double nc_bar = c2 * (val / dnc - ((snc > 1e-6) ? B / (dnc * dnc) : 0.0));
+            const double mk_bar = (cw_bar * kd - nc_bar) * op;
+            for (int k = 0; k < m; ++k)
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    double others = 1.0;
+                    for (int k2 = 0; k2 < m; ++k2)
+#pragma unroll
+                        for (int j2 = 0; j2 < Q; ++j2)
+                            if (k2 != k || j2 != j) others *= p.mask[k2][ix + j2];
+                    p.mask_bar[k][ix + j] = bad ? nanv : mk_bar * others;
+                }
+            for (int s = 0; s < S; ++s) {
+                double f[MAX_M][Q], fb[MAX_M][Q];
+                for (int k = 0; k < m; ++k) {
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) fb[k][j] = 0.0;
+                    if (p.fx[k]) {
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) f[k][j] = p.fx[k][((int64_t(c) * S + s) * G + g) * Q + j];
+                    } else {
+                        const double* Lf = wmat + size_t(k) * 2 * Q * Q + Q * Q;
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) {
+                            double a = mf[k][j];
+#pragma unroll
+                            for (int l = 0; l < Q; ++l)
+                                if (l <= j) a = fma(Lf[j * Q + l], p.eps_mc[((int64_t(s) * G + g) * Q + l) * m + k], a);
+                            f[k][j] = a;
+                        }
+                    }
+                }
+                const double* los = lo + (p.cells_per_sample ? size_t(s) * p.n_cells * m : 0);
+                const double* ups = up + (p.cells_per_sample ? size_t(s) * p.n_cells * m : 0);
+                for (int sub = 1; sub < (1 << Q); ++sub) {
+                    double vmin[MAX_M], dv[MAX_M];
+                    int arg[MAX_M];
+                    for (int k = 0; k < m; ++k) {
+                        double v = INFINITY;
+                        int a = 0;
+#pragma unroll
+                        for (int j = 0; j < Q; ++j)
+                            if (((sub >> j) & 1) && f[k][j] < v) { v = f[k][j]; a = j; }
+                        vmin[k] = v; arg[k] = a; dv[k] = 0.0;
+                    }
+                    for (int cell = 0; cell < p.n_cells; ++cell) {
+                        double len[MAX_M];
+                        for (int k = 0; k < m; ++k) len[k] = fmax(fmin(vmin[k], ups[cell * m + k]) - los[cell * m + k], 0.0);
+                        for (int k = 0; k < m; ++k) {
+                            if (!(vmin[k] < ups[cell * m + k]) || !(len[k] > 0.0)) continue;
+                            double o = 1.0;
+                            for (int k2 = 0; k2 < m; ++k2)
+                                if (k2 != k) o *= len[k2];
+                            dv[k] += o;
+                        }
+                    }
+                    const double sgn = (__popc(sub) & 1) ? 1.0 : -1.0;
+                    for (int k = 0; k < m; ++k)
+#pragma unroll
+                        for (int j = 0; j < Q; ++j)
+                            if (j == arg[k]) fb[k][j] = fma(sgn, dv[k], fb[k][j]);
+                }
+                for (int k = 0; k < m; ++k)
+                    if (p.f_bar[k])
+#pragma unroll
+                        for (int j = 0; j < Q; ++j)
+                            p.f_bar[k][((int64_t(c) * S + s) * G + g) * Q + j] = bad ? nanv : val_bar * fb[k][j];
+            }
+        }
     }
 }
 

@@ -25,6 +25,15 @@ struct ScoreQBwdArgs {
     ScoreQArgs f;
     double* wbar;          // rows x Np
     double* adjq;          // rows x ADJQ_STRIDE
+    // f.base.ext_values (cNEI): the sample values are another kernel's -- constants of THIS reverse pass; the adjoints
+    // d acq / d values_sgj go to val_bar (n_cand x S x G x Q) for that kernel's own reverse pass (k_nei_values_q_bwd).
+    double* val_bar;
+    // External adjoints (cEHVI / cNEHVI and any other outer integration over several outputs): the kernel is then the
+    // vector-Jacobian product of (conf_pred_mask, ood_mask, samples of the refit posterior) with respect to X; its own
+    // integration (phase D) is not differentiated and acq is not written.
+    const double* ext_mask_bar;   // n_cand x G x Q   d L / d mask_gj        (all three null: the kernel's own integration)
+    const double* ext_ood_bar;    // n_cand x Q       d L / d ood_j
+    const double* ext_f_bar;      // n_cand x S x G x Q   d L / d f_sgj of the internally sampled refit posterior, or null
 };
 
 __host__ __device__ inline size_t score_q_bwd_smem_bytes(int Np, int G, int Q) {
@@ -120,6 +129,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
     const double c1q = inv_temp * 23.083120654223414;                    // 16 / (temp ln 2)
     const double sum_dr = p.sum_dr[0];
     const double alpha_lvl = p.alpha_lvl;
+    const bool ext_adj = qb.ext_mask_bar != nullptr;
     __shared__ __align__(128) double tab[16];
     if (tid < 16) exp_tab_init(tab, tid);
     const unsigned tab_s = smem_u32(tab);
@@ -424,7 +434,10 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             }
             double f = mf + fs;
             sgn = 0.0; dv_f = 1.0;
-            if (p.kind == 0) {
+            if (p.ext_values) {            // another kernel's values (cNEI): constants here, their adjoint is exported
+                val = p.ext_values[((int64_t(c) * S + s) * G + g) * Q + j];
+                dv_f = 0.0;
+            } else if (p.kind == 0) {
                 if (S > 1) { double m = mf + ms; double dm = f - m; sgn = (dm > 0.0) ? 1.0 : (dm < 0.0 ? -1.0 : 0.0); val = m + p.beta_prime * fabs(dm); }
                 else val = f;
             } else {
@@ -503,6 +516,16 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                         const double wv = c1 * cw / dcw + c2 * nc / dnc;      // d res_sj / d val_sgj
                         double cw_bar = 0.0, nc_bar = 0.0, meanf_bar = 0.0;
                         double m_bar = 0.0;
+                        if (ext_adj) {             // adjoints of an outer integration: masks and samples only
+                            if (qb.ext_f_bar)
+                                for (int s = 0; s < S; ++s) {
+                                    const double f_bar = qb.ext_f_bar[((int64_t(c) * S + s) * G + g) * Q + j];
+                                    meanf_bar += f_bar;
+#pragma unroll
+                                    for (int k = 0; k < Q; ++k)
+                                        if (k <= j) a_lf[j][k] = fma(f_bar, p.eps_mc[(int64_t(s) * G + g) * Q + k], a_lf[j][k]);
+                                }
+                        } else {
                         // two sweeps over the MC samples for the S > 1 cUCB mean term
                         for (int s = 0; s < S; ++s) {
                             const double kap = s_kap[s * MAX_Q + j];
@@ -511,11 +534,15 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                             sample_val(s, g, j, val, dv, sg);
                             cw_bar += kap * c1 * (val / dcw - ((scw[j] > 1e-6) ? s_A[s * MAX_Q + j] / (dcw * dcw) : 0.0));
                             nc_bar += kap * c2 * (val / dnc - ((snc[j] > 1e-6) ? s_B[s * MAX_Q + j] / (dnc * dnc) : 0.0));
-                            if (p.kind == 0) m_bar += kap * wv * (1.0 - p.beta_prime * sg);
+                            if (p.kind == 0 && !p.ext_values) m_bar += kap * wv * (1.0 - p.beta_prime * sg);
                         }
                         for (int s = 0; s < S; ++s) {
                             const double kap = s_kap[s * MAX_Q + j];
                             double f_bar;
+                            if (p.ext_values) {
+                                if (qb.val_bar && crank == 0) qb.val_bar[((int64_t(c) * S + s) * G + g) * Q + j] = kap * wv;
+                                continue;
+                            }
                             if (p.kind == 0) {
                                 double val, dv, sg = 0.0;
                                 if (kap != 0.0 && S > 1) sample_val(s, g, j, val, dv, sg);
@@ -532,11 +559,12 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                             for (int k = 0; k < Q; ++k)
                                 if (k <= j) a_lf[j][k] = fma(f_bar, p.eps_mc[(int64_t(s) * G + g) * Q + k], a_lf[j][k]);
                         }
+                        }
                         a_mu[j] += meanf_bar;
 #pragma unroll
                         for (int k = 0; k < Q; ++k) a_shr[j][k] = fma(meanf_bar, g_dev[g * Q + k], a_shr[j][k]);
                         if (SOFT) {
-                            const double mk_bar = (cw_bar * kd - nc_bar) * op;
+                            const double mk_bar = ext_adj ? qb.ext_mask_bar[(int64_t(c) * G + g) * Q + j] : (cw_bar * kd - nc_bar) * op;
                             const double M_bar = mk_bar * mk * (1.0 - mk) * inv_temp;
                             const double scale = g_scale[o], srj = g_sr[o], swj = g_sw[o], kl = g_kl[o], Mraw = g_Mraw[o];
                             double scale_bar = M_bar * (swj + 0.5 * drc[j]) / norm[j];
@@ -825,6 +853,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                     for (int s = 0; s < S; ++s)
                         inner += s_kap[s * MAX_Q + j] * ((1.0 - alpha_lvl) * s_A[s * MAX_Q + j] / fmax(scw[j], 1e-6) +
                                                          alpha_lvl * s_B[s * MAX_Q + j] / fmax(snc[j], 1e-6));
+                    if (ext_adj) inner = -qb.ext_ood_bar[int64_t(c) * Q + j];           // d L / d ood_j, handed in
                     const double om_bar = tot[SqbIdx::om(j)] - inner * ood[j] * (1.0 - ood[j]) * inv_temp;
                     const double nrm_bar = tot[SqbIdx::nrm(j)] - om_bar * omega[j] / norm[j];
                     drc_bar = tot[SqbIdx::drc(j)] + om_bar / norm[j] + nrm_bar;
@@ -839,7 +868,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                     adj[8 + s] = -ub;
                 }
             }
-            p.acq[c] = tot_acq / double(S);
+            if (!ext_adj) p.acq[c] = tot_acq / double(S);
         }
         __syncthreads();
         if constexpr (CL) {        // ut_bar lives in rank 0's shared memory
@@ -873,7 +902,9 @@ __global__ void __launch_bounds__(RBQ_THREADS)
 k_rows_bwd_q(const double* __restrict__ Xq, int rows, int q, const double* __restrict__ XsT, int N, int Np, int d,
              const double* __restrict__ inv_ls, double outputscale, const double* __restrict__ alpha,
              const double* __restrict__ Aw, const double* __restrict__ W, const double* __restrict__ adjq,
-             int adj_stride, int q1_layout, double* __restrict__ dX) {
+             int adj_stride, int q1_layout, const double* __restrict__ Xb, int nb, const double* __restrict__ cv_bar,
+             double* __restrict__ dX) {
+    // Xb / cv_bar (cNEI): c_rj = k(X_b,r, x_j) - ... adds sum_r cv_bar[c, r, j] dk(X_b,r, x_j)/dx_j
     // q1_layout: the adjoint record of k_score_bwd ({mu_bar, s_bar, ...}; Ssym = 2 s_bar) instead of k_score_q_bwd's
     __shared__ double s_x[MAX_D], s_red[RBQ_THREADS / 32][8], s_adj[2 + MAX_Q];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -928,6 +959,16 @@ k_rows_bwd_q(const double* __restrict__ Xq, int rows, int q, const double* __res
                 const double t = kSqrt5 * sqrt(fmax(r2, 1e-30));
                 const double dfk = s_x[kd] - Xq[int64_t(c * q + k) * d + kd] * inv_ls[kd];
                 v = fma(s_adj[2 + k] * kfac * (1.0 + t) * exp(-t), dfk, v);
+            }
+            for (int rb = 0; rb < nb; ++rb) {
+                double r2 = 0.0;
+                for (int e = 0; e < d; ++e) {
+                    double df = s_x[e] - Xb[rb * d + e] * inv_ls[e];
+                    r2 = fma(df, df, r2);
+                }
+                const double t = kSqrt5 * sqrt(fmax(r2, 1e-30));
+                const double dfk = s_x[kd] - Xb[rb * d + kd] * inv_ls[kd];
+                v = fma(cv_bar[(int64_t(c) * nb + rb) * q + j] * kfac * (1.0 + t) * exp(-t), dfk, v);
             }
             dX[int64_t(r) * d + kd] = v * inv_ls[kd];
         }

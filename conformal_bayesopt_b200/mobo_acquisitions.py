@@ -74,9 +74,6 @@ class qConformalExpectedHypervolumeImprovement(ConformalAcquisition):
         """Shared front end of cEHVI / cNEHVI: shapes, pending points, base samples, probes, uniforms."""
         if self.model is None:
             raise AttributeError("ConformalAcquisition must be subclassed")
-        if X.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError("d acq / d X is not built for the multi-objective acquisitions (SURVEY.md §8f-1); "
-                                      "call under torch.no_grad()")
         states = self._states()
         m = len(states)
         if X.ndim == 2:
@@ -105,7 +102,56 @@ class qConformalExpectedHypervolumeImprovement(ConformalAcquisition):
             ratio=_ratio_weights(self.ratio_estimator, dev), alpha=self.alpha, temp=self.temp, grid_res=G,
             max_grid_refinements=self.max_grid_refinements, randomized=self.randomized, optimistic=self.optimistic, **kw)
 
+    def _per_output_grad(self, st, k, Xf, q, G, dev, eps, z, u, bars, **extra):
+        """d (this output's masks, ood masks, samples) / d X contracted with the integration's adjoints `bars`."""
+        kw = dict(kind="ucb")
+        kw.update(extra)
+        if self.max_grid_refinements > 0:
+            raise NotImplementedError("d acq / d X of the multi-objective acquisitions is built without grid refinement")
+        out = ops.conformal_acq(
+            st, Xf, eps_grid=eps[:, :, k].contiguous(), z=z, u_rand=None if u is None else u.reshape(-1, G, q, u.shape[-1])[..., k].contiguous(),
+            ratio=_ratio_weights(self.ratio_estimator, dev), alpha=self.alpha, temp=self.temp, grid_res=G,
+            max_grid_refinements=0, randomized=self.randomized, optimistic=self.optimistic, want_grad=True,
+            ext_adjoints=bars, **kw)
+        return out["dacq_dX"]
+
+    def _value_and_grad(self, X):
+        states, m, X, Xf, lead, q, b, G, dev, eps, z, u = self._prepare(X)
+        S = int(self.sampler.sample_shape[0])
+        eps_mc = self.sampler.draw((S, G, q, m), dev).contiguous()                  # base samples (S, 1, G, q, t)
+        outs = [self._per_output(st, k, Xf, q, G, dev, eps, z, u) for k, st in enumerate(states)]
+        acq, values, bars = ops.cehvi_integrate_q_grad(outs, [st.noise for st in states], eps_mc, self.cell_lower.to(dev),
+                                                       self.cell_upper.to(dev), q=q, alpha=self.alpha,
+                                                       optimistic=self.optimistic)
+        dX = None
+        for k, st in enumerate(states):
+            g = self._per_output_grad(st, k, Xf, q, G, dev, eps, z, u, bars[k], eps_mc=eps_mc[..., k].contiguous())
+            dX = g if dX is None else dX + g
+        self.last_outputs = {"per_output": outs, "acq": acq, "values": values}
+        return acq, dX, lead, q
+
+    def value_and_grad(self, X: torch.Tensor):
+        """(acq (b,), d acq / d X (b, q_in, d)): 2 m + 1 library calls (m forward, the integration with its reverse pass, m
+        vector-Jacobian products); pending points carry no gradient."""
+        Xd = X.detach()
+        q_in = (Xd.unsqueeze(0) if Xd.ndim == 2 else Xd).shape[-2]
+        acq, dX, lead, q = self._value_and_grad(Xd)
+        return acq.reshape(lead), dX[:, :q_in, :].reshape(*lead, q_in, dX.shape[-1])
+
+    def graphed(self, b, q, want_grad=True):
+        raise ValueError("one library call per step is captured; the multi-objective acquisitions take several")
+
+    def _forward_with_grad(self, X):
+        from .acquisitions import _ConformalAcqFn
+        Xg = X.unsqueeze(0) if X.ndim == 2 else X
+        q_in, d = Xg.shape[-2:]
+        acq, dX, lead, q = self._value_and_grad(X.detach())
+        out = _ConformalAcqFn.apply(Xg.reshape(-1, q_in, d), acq, dX[:, :q_in, :].to(X.dtype))
+        return out.reshape(lead).to(X.dtype)
+
     def forward(self, X: torch.Tensor) -> torch.Tensor:
+        if X.requires_grad and torch.is_grad_enabled():
+            return self._forward_with_grad(X)
         states, m, X, Xf, lead, q, b, G, dev, eps, z, u = self._prepare(X)
         S = int(self.sampler.sample_shape[0])
         eps_mc = self.sampler.draw((S, G, q, m), dev).contiguous()                  # base samples (S, 1, G, q, t)
@@ -183,7 +229,7 @@ class qConformalNoisyExpectedHypervolumeImprovement(qConformalExpectedHypervolum
         self.register_buffer("cell_lower", lo)
         self.register_buffer("cell_upper", up)
 
-    def forward(self, X: torch.Tensor) -> torch.Tensor:
+    def _joint_outputs(self, X):
         states, m, X, Xf, lead, q, b, G, dev, eps, z, u = self._prepare(X)
         S, nb = self.baseline_base_samples.shape[0], self.baseline_base_samples.shape[1]
         if nb + q > 32:
@@ -193,6 +239,27 @@ class qConformalNoisyExpectedHypervolumeImprovement(qConformalExpectedHypervolum
         outs = [self._per_output(st, k, Xf, q, G, dev, eps, z, u, kind="joint", nei_baseline=self._baselines[k],
                                  eps_mc=eps_joint[..., k].contiguous(), outputs=self._PER_OUTPUT + ("mc_values",))
                 for k, st in enumerate(states)]
+        return states, Xf, lead, q, G, dev, eps, z, u, eps_joint, outs
+
+    def _value_and_grad(self, X):
+        """The box decompositions belong to the baseline samples drawn at construction: constants of the reverse pass."""
+        states, Xf, lead, q, G, dev, eps, z, u, eps_joint, outs = self._joint_outputs(X)
+        acq, values, bars = ops.cehvi_integrate_q_grad(outs, [st.noise for st in states], None, self.cell_lower.to(dev),
+                                                       self.cell_upper.to(dev), q=q, alpha=self.alpha,
+                                                       optimistic=self.optimistic, cells_per_sample=True)
+        dX = None
+        for k, st in enumerate(states):
+            g = self._per_output_grad(st, k, Xf, q, G, dev, eps, z, u, bars[k], kind="joint",
+                                      nei_baseline=self._baselines[k], eps_mc=eps_joint[..., k].contiguous())
+            dX = g if dX is None else dX + g
+        self.last_outputs = {"per_output": outs, "acq": acq, "values": values}
+        return acq, dX, lead, q
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        if X.requires_grad and torch.is_grad_enabled():
+            return self._forward_with_grad(X)
+        states, Xf, lead, q, G, dev, eps, z, u, eps_joint, outs = self._joint_outputs(X)
+        dev = Xf.device
         acq, values = ops.cehvi_integrate_q(outs, [st.noise for st in states], None, self.cell_lower.to(dev),
                                             self.cell_upper.to(dev), q=q, alpha=self.alpha, optimistic=self.optimistic,
                                             cells_per_sample=True, want_values=True)

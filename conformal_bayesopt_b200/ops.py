@@ -109,13 +109,14 @@ class NeiBaseline:
 
 def make_params(*, alpha, temp, grid_res, q=1, num_mc=1, num_probes=8, max_grid_refinements=0, kind="ucb",
                 optimistic=True, randomized=False, eps_per_candidate=False, beta_prime=0.0, best_f=0.0,
-                nei=None, refine_reduce=None, grid_cov_scale=None) -> "_lib.Params":
+                nei=None, refine_reduce=None, grid_cov_scale=None, ext_adjoints=None) -> "_lib.Params":
     """`refine_reduce`: a `_lib.REFINE_REDUCE_FN` instance (kept alive by the caller) or None."""
     fn = C.cast(refine_reduce, C.c_void_p) if refine_reduce is not None else None
     return _lib.Params(float(alpha), float(temp), int(grid_res), int(q), int(num_mc), int(num_probes),
                        int(max_grid_refinements), ACQ_KINDS[kind], int(bool(optimistic)), int(bool(randomized)),
                        int(bool(eps_per_candidate)), float(beta_prime), float(best_f),
-                       C.pointer(nei) if nei is not None else None, fn, None, grid_cov_scale)
+                       C.pointer(nei) if nei is not None else None, fn, None, grid_cov_scale,
+                       C.pointer(ext_adjoints) if ext_adjoints is not None else None)
 
 
 def workspace(state: GPModelState, b: int, params, chunk: int = 0, grad: bool = False, stream: Optional[int] = None) -> torch.Tensor:
@@ -183,12 +184,25 @@ def conformal_acq(state: GPModelState, Xq: torch.Tensor, *, eps_grid: torch.Tens
         _require_cuda(cov_scale)
         if cov_scale.numel() != b * q:
             raise _lib.CboError("grid_cov_scale must hold b*q scales")
+    ext = param_kw.pop("ext_adjoints", None)                # (mask_bar (b,G,q), ood_bar (b,q), f_bar (b,S,G,q) or None): VJP mode
+    ext_c = None
+    if ext is not None:
+        if not want_grad:
+            raise _lib.CboError("ext_adjoints belong to the gradient call")
+        ext = tuple(None if t is None else _f64(t) for t in ext)
+        _require_cuda(*ext)
+        ext_c = _lib.ExtAdjointsF64(*[_ptr(t) for t in ext])
     baseline = param_kw.pop("nei_baseline", None)
     nei_c = baseline.c_struct() if baseline is not None else None          # kept alive until the call returns
     per_sample = (baseline.Xb.shape[0] + q) if baseline is not None else q
     num_mc = eps_mc.numel() // (G * per_sample)
     params = make_params(q=q, num_mc=num_mc, num_probes=z.shape[-1], eps_per_candidate=eps_per_candidate, nei=nei_c,
-                         refine_reduce=reduce_c, grid_cov_scale=_ptr(cov_scale), **param_kw)
+                         refine_reduce=reduce_c, grid_cov_scale=_ptr(cov_scale), ext_adjoints=ext_c, **param_kw)
+    if ext is not None:
+        want = (b * G * q, b * q, b * num_mc * G * q)
+        for t, n in zip(ext, want):
+            if t is not None and t.numel() != n:
+                raise _lib.CboError("ext_adjoints: mask_bar (b,G,q), ood_bar (b,q), f_bar (b,S,G,q)")
     if z.shape[0] != state.N + q:
         raise _lib.CboError(f"z must have N+q = {state.N + q} rows, got {z.shape[0]}")
     if u_rand is not None and u_rand.numel() != b * G * q:
@@ -331,6 +345,54 @@ def cehvi_integrate_q(per_output, noise, eps_mc: Optional[torch.Tensor], cell_lo
                                        float(alpha), int(bool(optimistic)), acq.data_ptr(), _ptr(values), _stream())
     _lib.check(st, "cbo_cehvi_integrate_q_f64")
     return (acq, values) if want_values else acq
+
+
+def cehvi_integrate_q_grad(per_output, noise, eps_mc: Optional[torch.Tensor], cell_lower: torch.Tensor, cell_upper: torch.Tensor, *,
+                           q: int, alpha: float, optimistic: bool, cells_per_sample: bool = False):
+    """cbo_cehvi_integrate_q_grad_f64: `cehvi_integrate_q` plus its reverse pass.  Returns (acq (b,), values (b,G),
+    [(mask_bar (b,G,q), ood_bar (b,q), f_bar (b,S,G,q)) per output]) -- the `ext_adjoints` of the per-output gradient calls."""
+    global LAUNCH_COUNT
+    lib = _lib.load()
+    m = len(per_output)
+    dev = per_output[0]["conf_pred_mask"].device
+    b, G = per_output[0]["grid_logp"].shape
+    keep = []
+    def ptrs(key, shape):
+        ts = [_f64(o[key]).reshape(shape) for o in per_output]
+        keep.append(ts)
+        return (C.c_void_p * m)(*[t.data_ptr() for t in ts])
+    mask, grid = ptrs("conf_pred_mask", (b, G, q)), ptrs("target_grid", (b, G, q))
+    logp, mu, ood = ptrs("grid_logp", (b, G)), ptrs("post_mean", (b, q)), ptrs("ood_mask", (b, q))
+    ext = ["mc_values" in o for o in per_output]
+    if any(ext) and not all(ext):
+        raise _lib.CboError("either every output supplies mc_values or none does")
+    fx = cov = None
+    if all(ext):
+        S = per_output[0]["mc_values"].shape[1]
+        fx = ptrs("mc_values", (b, S, G, q))
+    else:
+        cov = ptrs("post_var", (b, q, q))
+        eps_mc = _f64(eps_mc)
+        _require_cuda(eps_mc)
+        S = eps_mc.numel() // (G * q * m)
+    cell_lower, cell_upper = _f64(cell_lower), _f64(cell_upper)
+    _require_cuda(cell_lower, cell_upper)
+    n_cells = cell_lower.shape[-2]
+    if cells_per_sample and cell_lower.shape[0] != S:
+        raise _lib.CboError("per-sample cells must be (S, n_cells, m)")
+    noise_c = (C.c_double * m)(*[float(v) for v in noise])
+    acq = torch.empty(b, dtype=torch.float64, device=dev)
+    values = torch.empty(b, G, dtype=torch.float64, device=dev)
+    bars = [(torch.empty(b, G, q, dtype=torch.float64, device=dev), torch.empty(b, q, dtype=torch.float64, device=dev),
+             torch.empty(b, S, G, q, dtype=torch.float64, device=dev)) for _ in range(m)]
+    arr = lambda i: (C.c_void_p * m)(*[t[i].data_ptr() for t in bars])
+    st = lib.cbo_cehvi_integrate_q_grad_f64(m, b, G, S, q, mask, logp, grid, mu, ood, cov, noise_c, fx,
+                                            _ptr(eps_mc) if fx is None else None, cell_lower.data_ptr(), cell_upper.data_ptr(),
+                                            n_cells, int(bool(cells_per_sample)), float(alpha), int(bool(optimistic)),
+                                            acq.data_ptr(), values.data_ptr(), arr(0), arr(1), arr(2), _stream())
+    _lib.check(st, "cbo_cehvi_integrate_q_grad_f64")
+    LAUNCH_COUNT += 1
+    return acq, values, bars
 
 
 def conf_mask_to_bounds(target_grid: torch.Tensor, conf_pred_mask: torch.Tensor):

@@ -16,6 +16,7 @@
  *   cbo_ratio_forward_f64      RatioEstimator.forward (ratio_estimation.py:97-99).
  *   cbo_conformal_acq_grad_f64 the same path under autograd in optimize_acqf_sgld (conformalbo/optim/optimize.py:224-235).
  *   cbo_cehvi_integrate_f64    qConformalExpectedHypervolumeImprovement (conformalbo/mobo_acquisitions.py:24-45).
+ *   cbo_cehvi_integrate_q_f64 / _grad_f64   the same for joint batches, cNEHVI (mobo_acquisitions.py:184-219), and its reverse pass.
  *   cbo_model_build_f64 / cbo_model_append_f64   the model refit before the path (conformalbo/utils.py:382-390) and the
  *                              observations a BO round adds (scripts/black_box_opt.py:154-155).
  *   cbo_ratio_train_step_f64   RatioEstimator.optimize_callback (ratio_estimation.py:110-144).
@@ -45,7 +46,7 @@
 extern "C" {
 #endif
 
-#define CBO_VERSION 101
+#define CBO_VERSION 102
 
 typedef enum {
     CBO_OK = 0,
@@ -95,6 +96,16 @@ typedef struct {
     const double* mub;         /* nb        posterior mean of f(X_b)                            */
 } cbo_nei_baseline_f64;
 
+/* Adjoints handed in by an outer integration over several outputs (cEHVI / cNEHVI, cbo_cehvi_integrate_q_grad_f64): the
+ * gradient call is then the vector-Jacobian product of this output's (conf_pred_mask, ood_mask, posterior samples at the
+ * candidates under the refit models) with respect to Xq; the call's own integration is not differentiated. */
+typedef struct {
+    const double* mask_bar;    /* b x G x q       d L / d conf_pred_mask                                             */
+    const double* ood_bar;     /* b x q           d L / d ood_mask                                                   */
+    const double* f_bar;       /* b x S x G x q   d L / d samples: of the refit posterior drawn with eps_mc (S x G x q;
+                                * kind UCB / EI), or of the joint samples mc_values (kind CBO_ACQ_JOINT); may be NULL */
+} cbo_ext_adjoints_f64;
+
 typedef struct {
     double alpha;              /* miscoverage level                         (acquisitions.py:32) */
     double temp;               /* sigmoid temperature; <= 0 selects the hard path (helpers.py:277,316) */
@@ -119,6 +130,8 @@ typedef struct {
      * refinement loop has accumulated (helpers.py:166-182) -- multi-output bands take the loop's decisions over ALL outputs,
      * so the t per-output calls of one step run with max_grid_refinements = 0 and the scales of the step. */
     const double* grid_cov_scale;
+    /* cbo_conformal_acq_grad_f64 only: NULL = differentiate the call's own acquisition value. */
+    const cbo_ext_adjoints_f64* ext_adjoints;
 } cbo_params;
 
 /* Any pointer may be NULL (that output is skipped) except acq. */
@@ -156,11 +169,13 @@ int cbo_conformal_acq_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, 
                           const double* eps_mc, const double* u_rand, const cbo_outputs_f64* out,
                           void* workspace, size_t workspace_bytes, int64_t chunk, void* stream);
 
-/* Value and gradient (cUCB / cEI, q <= 4): additionally writes dacq_dX (b x q x d) = d acq[c] / d Xq[c, :, :], what the reference
+/* Value and gradient (cUCB / cEI / cNEI, q <= 4): additionally writes dacq_dX (b x q x d) = d acq[c] / d Xq[c, :, :], what the reference
  * obtains by autograd through the same path inside optimize_acqf_sgld (conformalbo/optim/optimize.py:224-235:
  * acq_function(X).sum().backward()); the target grid, its log-density and the optimistic mask are constants, as they are
  * built under torch.no_grad() there (helpers.py:118-119, acquisitions.py:58-59).  temp <= 0: the masks are step functions
- * (zero gradient through them), the value path still differentiates.  Workspace: cbo_workspace_bytes_grad. */
+ * (zero gradient through them), the value path still differentiates.  cNEI (and CBO_ACQ_JOINT with external adjoints)
+ * add the reverse pass of the joint posterior over [X_baseline; X] (Cholesky reverse of the (nb+q)^2 factor).  With
+ * params->ext_adjoints the result is the vector-Jacobian product described there.  Workspace: cbo_workspace_bytes_grad. */
 size_t cbo_workspace_bytes_grad(int64_t N, int64_t d, int64_t b, const cbo_params* params, int64_t chunk);
 int cbo_conformal_acq_grad_f64(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* params,
                                const double* Xq, int64_t b, const double* eps_grid, const double* z,
@@ -200,6 +215,19 @@ int cbo_cehvi_integrate_q_f64(int64_t m, int64_t b, int64_t G, int64_t S, int64_
                               const double* const* fx, const double* eps_mc, const double* cell_lower,
                               const double* cell_upper, int64_t n_cells, int32_t cells_per_sample, double alpha,
                               int32_t optimistic, double* acq, double* values_out, void* stream);
+
+/* The same integration with its reverse pass: additionally writes, per output k, d acq[c] / d mask (b x G x q), d acq[c] / d ood
+ * (b x q) and d acq[c] / d samples (b x S x G x q: of the internally sampled refit posterior, or of fx[k]) -- the
+ * cbo_ext_adjoints_f64 of the m per-output cbo_conformal_acq_grad_f64 calls whose dacq_dX sum to d acq / d X (what autograd does
+ * through mobo_acquisitions.py:24-45 inside optimize_acqf_sgld).  Grid, log-densities, optimistic masks and cells are constants.
+ * values_out (b x G) is required (scratch between the two passes); f_bar[k] may be NULL. */
+int cbo_cehvi_integrate_q_grad_f64(int64_t m, int64_t b, int64_t G, int64_t S, int64_t q, const double* const* mask,
+                                   const double* const* logp, const double* const* grid, const double* const* mu,
+                                   const double* const* ood, const double* const* cov, const double* noise_host,
+                                   const double* const* fx, const double* eps_mc, const double* cell_lower,
+                                   const double* cell_upper, int64_t n_cells, int32_t cells_per_sample, double alpha,
+                                   int32_t optimistic, double* acq, double* values_out, double* const* mask_bar,
+                                   double* const* ood_bar, double* const* f_bar, void* stream);
 
 /* conf_mask_to_bounds: grid, mask: b x G x t (q = 1 squeezed) -> lb, ub: b x t.  G <= 2048. */
 int cbo_conf_mask_to_bounds_f64(const double* target_grid, const double* conf_pred_mask, int64_t b, int64_t G,
