@@ -223,20 +223,25 @@ class qConformalExpectedImprovement(ConformalAcquisition):
 class qConformalNoisyExpectedImprovement(ConformalAcquisition):
     """acquisitions.py:106-139 (+ botorch qNoisyExpectedImprovement(model, X_baseline, sampler, ..., prune_baseline)).
 
-    Joint sampling over [X_baseline; X] under every refit model.  Built for q <= 4 (incl. pending points) and at most 31
-    baseline points (nb + q <= 32) -- pass the pruned baseline (the reference configs set `prune_baseline: true`, hydra_config/acq_fn/cnei.yaml:3; botorch's
-    `prune_inferior_points` is an MC procedure outside this path)."""
+    Joint sampling over [X_baseline; X] under every refit model.  Built for q <= 4 (incl. pending points) and nb + q <= 64
+    baseline + candidate points (one Cholesky of the joint (nb+q)^2 covariance per joint batch in shared memory).
+    `prune_baseline=True` (every reference config: hydra_config/acq_fn/cnei.yaml:3) runs botorch's `prune_inferior_points`
+    at construction (`sampling.prune_inferior_points`; base samples `prune_base_samples` (S, nb) or Sobol with `prune_seed`)."""
 
     def __init__(self, alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic=False,
                  grid_sampler=None, randomized=False, *, model=None, X_baseline=None, sampler=None, objective=None,
-                 posterior_transform=None, X_pending=None, prune_baseline=False, cache_root=False):
+                 posterior_transform=None, X_pending=None, prune_baseline=False, cache_root=False, prune_base_samples=None,
+                 prune_seed=None):
         super().__init__(alpha, temp, grid_res, max_grid_refinements, ratio_estimator, optimistic, grid_sampler,
                          randomized, model=model, sampler=sampler, objective=objective,
                          posterior_transform=posterior_transform, X_pending=X_pending)
         if X_baseline is None:
             raise TypeError("qConformalNoisyExpectedImprovement needs X_baseline")
-        if X_baseline.reshape(-1, X_baseline.shape[-1]).shape[0] > 31:
-            raise NotImplementedError("cNEI is built for at most 31 baseline points: pass the pruned baseline")
+        if prune_baseline:
+            from .sampling import prune_inferior_points
+            X_baseline = prune_inferior_points(model, X_baseline, base_samples=prune_base_samples, seed=prune_seed)
+        if X_baseline.reshape(-1, X_baseline.shape[-1]).shape[0] > 60:
+            raise NotImplementedError("cNEI is built for nb + q <= 64 joint points: prune the baseline (prune_baseline=True)")
         self.X_baseline = X_baseline
         self._baseline = None
 

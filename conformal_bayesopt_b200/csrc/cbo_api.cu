@@ -190,7 +190,7 @@ int validate(const cbo_gp_f64* gp, const cbo_params* p, int64_t b) {
     if (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI && p->kind != CBO_ACQ_NEI && p->kind != CBO_ACQ_JOINT) return CBO_ERR_INVALID_ARG;
     if (p->kind == CBO_ACQ_NEI || p->kind == CBO_ACQ_JOINT) {
         if (!p->nei || !p->nei->Xb || !p->nei->KbX || !p->nei->Sbb || !p->nei->mub || p->nei->nb < 1) return CBO_ERR_INVALID_ARG;
-        if (p->nei->nb > cbo::NEI_MAX_NB || p->nei->nb + p->q > 32) return CBO_ERR_UNSUPPORTED;
+        if (p->nei->nb > cbo::NEI_MAX_NB || p->nei->nb + p->q > cbo::NEI_MAX_M) return CBO_ERR_UNSUPPORTED;
     }
     if (p->q < 1 || p->q > cbo::MAX_Q) return CBO_ERR_UNSUPPORTED;
     if (p->q > 1 && cbo::score_q_smem_bytes((int)gp->Np, (int)p->grid_res, (int)p->q) > 227 * 1024) return CBO_ERR_UNSUPPORTED;
@@ -669,11 +669,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 na.values = out->mc_values ? out->mc_values + c0 * q * int64_t(p->num_mc) * G : w.nei_values;
                 na.raw = p->kind == CBO_ACQ_JOINT;
                 na.V = w.V;
-                if (q == 1) CBO_LAUNCHED(), cbo::k_nei_values<<<(ncand + 3) / 4, 128, 0, s>>>(na);
-                else {
-                    cudaError_t e = cbo::launch_nei_values_q(na, q, s);
-                    if (e != cudaSuccess) return e;
-                }
+                if (cudaError_t e = cbo::launch_nei_values_q(na, q, s); e != cudaSuccess) return e;
                 x.ext_values = na.values;
                 na_last = na;
             }

@@ -1,13 +1,10 @@
-// nei.cuh -- cNEI sample values: joint posterior of the refit model over [X_baseline; x] (q = 1).
+// nei.cuh -- cNEI / cNEHVI sample values: joint posterior of the refit model over [X_baseline; X].
 //
 // qConformalNoisyExpectedImprovement._nonconformal_fwd (conformalbo/acquisitions.py:115-134) samples f jointly at the
-// baseline points and the candidate under every refit model and scores  softplus(f_x - smoothmax(f_b)).  With
-//   c_j = Cov_D(f(X_b,j), y(x)) = k(X_b,j, x) - K_bX[j,:] w,   P = Var_D(f(x)) = s - noise,   b_g = (y_g - mu)/s
-// the refit joint posterior is  mean = [mu_b + c b_g ; mu + P b_g],
-//   cov = [[Sigma_bb - c c^T / s,  c noise/s], [.,  P noise/s]]       -- independent of the grid point,
-// so one (nb+1)^2 Cholesky per candidate serves all G grid points (the reference factorises per (candidate, grid point)).
-// One warp per candidate; nb <= 31 (botorch prunes the baseline to the few points that can still be the best:
-// hydra_config/acq_fn/cnei.yaml `prune_baseline: true`).
+// baseline points and the candidates under every refit model and scores  softplus(f_x - smoothmax(f_b)).  The covariance of
+// that joint posterior does not depend on the grid point, so ONE (nb+q)^2 Cholesky per joint batch serves all G grid points and
+// MC samples (the reference factorises per (candidate, grid point)).  nb + q <= 64: botorch prunes the baseline to the few
+// points that can still be the best (hydra_config/acq_fn/cnei.yaml `prune_baseline: true`; sampling.prune_inferior_points).
 #pragma once
 #include "common.cuh"
 #include "rows.cuh"
@@ -15,137 +12,41 @@
 
 namespace cbo {
 
-constexpr int NEI_MAX_NB = 31;
+constexpr int NEI_MAX_M = 64;                  // rows of the joint factor: nb + q <= 64 (each lane owns rows lane and lane + 32)
+constexpr int NEI_MAX_NB = NEI_MAX_M - 1;
 
 struct NeiArgs {
     int N, Np, d, nb, G, S, n_cand, tiles_n;
     double noise, kappa, temp;
-    const double* Xq;        // n_cand x d
+    const double* Xq;        // rows x d
     const double* inv_ls;    // d
     const double* Xb;        // nb x d
     const double* KbX;       // nb x Np   k(X_b, X)
     const double* Sbb;       // nb x nb   posterior covariance of f(X_b) given the data (noise-free)
     const double* mub;       // nb        posterior mean of f(X_b)
-    const double* W;         // n_cand x Np
+    const double* W;         // rows x Np
     const double* rn_partial;
-    const double* mu;        // n_cand
-    const double* cscale;    // n_cand or nullptr
-    const double* eps_grid;  // G or n_cand x G
+    const double* mu;        // rows
+    const double* cscale;    // rows or nullptr
+    const double* eps_grid;  // G x q or n_cand x G x q
     int eps_per_candidate;
-    const double* eps_mc;    // S x G x (nb+1)
-    double* values;          // n_cand x S x G (x q)
+    const double* eps_mc;    // S x G x (nb+q)
+    double* values;          // n_cand x S x G x q
     int raw;                 // 1: write the joint-posterior samples f(x) themselves (cNEHVI), 0: the noisy-EI improvement
-    const double* V;         // joint batches only: rows x Np (v = L^-1 u); rows = n_cand * q
+    const double* V;         // rows x Np (v = L^-1 u); rows = n_cand * q
 };
 
-__global__ void __launch_bounds__(128)
-k_nei_values(const NeiArgs p) {
-    __shared__ double sL[4][(NEI_MAX_NB + 1) * (NEI_MAX_NB + 1)];
-    __shared__ double sc[4][NEI_MAX_NB + 1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * 4 + warp;
-    if (c >= p.n_cand) return;
-    const int nb = p.nb, n1 = nb + 1;
-    double* L = sL[warp];
-    double* cv = sc[warp];
-    double vnorm = 0.0;
-    for (int t = 0; t < p.tiles_n; ++t) vnorm += p.rn_partial[int64_t(c) * p.tiles_n + t];
-    const double s = p.kappa + p.noise - vnorm, P = s - p.noise, mu = p.mu[c];
-    // c_j: lanes stride over the train points, one baseline point at a time
-    const double* Wc = p.W + int64_t(c) * p.Np;
-    for (int j = 0; j < nb; ++j) {
-        double acc = 0.0;
-        for (int i = lane; i < p.N; i += 32) acc = fma(p.KbX[int64_t(j) * p.Np + i], Wc[i], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            double r2 = 0.0;
-            for (int e = 0; e < p.d; ++e) {
-                double df = (p.Xb[j * p.d + e] - p.Xq[int64_t(c) * p.d + e]) * p.inv_ls[e];
-                r2 = fma(df, df, r2);
-            }
-            double r = sqrt(fmax(r2, 1e-30));
-            cv[j] = p.kappa * (1.0 + kSqrt5 * r + (5.0 / 3.0) * r * r) * exp(-kSqrt5 * r) - acc;
-        }
-    }
-    __syncwarp();
-    // covariance (lower triangle), lane = row
-    if (lane < n1) {
-        for (int k = 0; k <= lane; ++k) {
-            double v;
-            if (lane < nb) v = p.Sbb[lane * nb + k] - cv[lane] * cv[k] / s;
-            else v = (k < nb) ? cv[k] * p.noise / s : P * p.noise / s;
-            L[lane * n1 + k] = v;
-        }
-    }
-    __syncwarp();
-    // right-looking Cholesky, lane = row
-    bool ok = true;
-    for (int j = 0; j < n1; ++j) {
-        double djj = L[j * n1 + j];
-        ok = ok && (djj > 0.0);
-        double ljj = sqrt(djj);
-        __syncwarp();
-        if (lane == j) L[j * n1 + j] = ljj;
-        if (lane > j && lane < n1) L[lane * n1 + j] /= ljj;
-        __syncwarp();
-        if (lane > j && lane < n1) {
-            double lij = L[lane * n1 + j];
-            for (int k = j + 1; k <= lane; ++k) L[lane * n1 + k] -= lij * L[k * n1 + j];
-        }
-        __syncwarp();
-    }
-    const double cscale = p.cscale ? p.cscale[c] : 1.0;
-    const double gsd = sqrt(cscale * s);
-    const double inv_temp = p.temp > 0.0 ? 1.0 / p.temp : 0.0;
-    for (int sg = lane; sg < p.S * p.G; sg += 32) {
-        const int smp = sg / p.G, g = sg - smp * p.G;
-        double eps = p.eps_grid[p.eps_per_candidate ? int64_t(c) * p.G + g : g];
-        double bg = gsd * eps / s;
-        const double* e = p.eps_mc + (int64_t(smp) * p.G + g) * n1;
-        // f = mean + L eps ; smooth max over the baseline, softplus of the improvement
-        double mx = -INFINITY, fx = 0.0;
-        double fb[NEI_MAX_NB];
-        for (int r = 0; r < n1; ++r) {
-            double acc = (r < nb) ? p.mub[r] + cv[r] * bg : mu + P * bg;
-            for (int k = 0; k <= r; ++k) acc = fma(L[r * n1 + k], e[k], acc);
-            if (r < nb) { fb[r] = acc; mx = fmax(mx, acc); }
-            else fx = acc;
-        }
-        double val;
-        if (p.temp > 0.0) {
-            double se = 0.0;
-            for (int r = 0; r < nb; ++r) se += exp((fb[r] - mx) * inv_temp);
-            double smax = mx + p.temp * log(se);                     // temp * logsumexp(f_b / temp)
-            double xt = (fx - smax) * inv_temp;
-            val = p.temp * (fmax(xt, 0.0) + log1p(exp(-fabs(xt))));
-        } else {
-            val = fmax(fx - mx, 0.0);
-        }
-        if (p.raw) val = fx;
-        p.values[(int64_t(c) * p.S + smp) * p.G + g] = ok ? val : nan("");
-    }
-}
+__host__ __device__ inline int nei_ld(int m) { return m | 1; }                         // odd row stride: conflict-free rows and columns
+__host__ __device__ inline size_t nei_warp_doubles(int nb, int q) { return size_t(nb + q) * nei_ld(nb + q) + 2 * size_t(nb) * q; }
 
-// Joint batches (q = Q candidate points per batch, nb + Q <= 32): with c = Cov_D(f(X_b), y(X)) (nb x Q),
-// S = K_qq + noise I - V^T V and B_g = S^-1 (y_g - mu) the refit joint posterior over [X_baseline; X] is
-//   mean = [mu_b + c B_g ; mu + (y_g - mu) - noise B_g],
-//   cov  = [[Sigma_bb - c S^-1 c^T, noise c S^-1], [., noise (I - noise S^-1)]]       -- independent of the grid point.
-// One warp per joint batch (lane = row of the (nb+Q)^2 factor); values: n_cand x S x G x Q, read by k_score_q.
+// Per joint batch: Schur complement S, its inverse, the factor of the (row-scaled) grid covariance, c = Cov_D(f(X_b), y(X)),
+// c S^-1, and the Cholesky factor L (row stride ld) of the joint refit covariance.  One warp; every lane ends up with the small
+// q x q matrices, the shared arrays hold L, c (cv) and c S^-1 (cs).  Returns false when a pivot is not positive.
 template <int Q>
-__global__ void __launch_bounds__(128)
-k_nei_values_q(const NeiArgs p) {
-    __shared__ double sL[4][32 * 32];
-    __shared__ double scv[4][NEI_MAX_NB * Q];
-    __shared__ double scs[4][NEI_MAX_NB * Q];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * 4 + warp;
-    if (c >= p.n_cand) return;
-    const int nb = p.nb, m = nb + Q, r0 = c * Q;
-    double* L = sL[warp];
-    double* cv = scv[warp];      // c[r][j]
-    double* cs = scs[warp];      // (c S^-1)[r][j]
-    // Schur complement of the joint batch, its inverse and the factor of the (row-scaled) grid covariance: every lane redundantly
-    double Sm[Q][Q], Ls[Q][Q], Si[Q][Q], Cov[Q][Q], Lc[Q][Q];
+__device__ __forceinline__ bool nei_setup(const NeiArgs& p, int c, int lane, double* L, double* cv, double* cs,
+                                          double (&Sm)[Q][Q], double (&Si)[Q][Q], double (&Lc)[Q][Q]) {
+    const int nb = p.nb, m = nb + Q, r0 = c * Q, ld = nei_ld(m);
+    double Ls[Q][Q], Cov[Q][Q];
 #pragma unroll
     for (int j = 0; j < Q; ++j)
 #pragma unroll
@@ -198,26 +99,26 @@ k_nei_values_q(const NeiArgs p) {
         }
     }
     __syncwarp();
-    if (lane < nb) {
+    for (int r = lane; r < nb; r += 32) {
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             double a = 0.0;
 #pragma unroll
-            for (int k = 0; k < Q; ++k) a = fma(cv[lane * Q + k], 0.5 * (Si[k][j] + Si[j][k]), a);
-            cs[lane * Q + j] = a;
+            for (int k = 0; k < Q; ++k) a = fma(cv[r * Q + k], 0.5 * (Si[k][j] + Si[j][k]), a);
+            cs[r * Q + j] = a;
         }
     }
     __syncwarp();
-    // covariance (lower triangle), lane = row
-    if (lane < m) {
-        for (int k = 0; k <= lane; ++k) {
+    // covariance (lower triangle), a lane owns rows lane, lane + 32
+    for (int r = lane; r < m; r += 32) {
+        for (int k = 0; k <= r; ++k) {
             double v;
-            if (lane < nb) {
-                v = p.Sbb[lane * nb + k];
+            if (r < nb) {
+                v = p.Sbb[r * nb + k];
 #pragma unroll
-                for (int j = 0; j < Q; ++j) v -= cs[lane * Q + j] * cv[k * Q + j];
+                for (int j = 0; j < Q; ++j) v -= cs[r * Q + j] * cv[k * Q + j];
             } else {
-                const int j = lane - nb;
+                const int j = r - nb;
                 if (k < nb) v = p.noise * cs[k * Q + j];
                 else {
                     const int j2 = k - nb;
@@ -230,24 +131,52 @@ k_nei_values_q(const NeiArgs p) {
                     v = p.noise * (((j == j2) ? 1.0 : 0.0) - p.noise * sij);
                 }
             }
-            L[lane * m + k] = v;
+            L[r * ld + k] = v;
         }
+        for (int k = r + 1; k < m; ++k) L[r * ld + k] = 0.0;
     }
     __syncwarp();
+    // right-looking Cholesky
     for (int j = 0; j < m; ++j) {
-        const double djj = L[j * m + j];
+        const double djj = L[j * ld + j];
         ok = ok && (djj > 0.0);
         const double ljj = sqrt(djj);
         __syncwarp();
-        if (lane == j) L[j * m + j] = ljj;
-        if (lane > j && lane < m) L[lane * m + j] /= ljj;
+        if (lane == 0) L[j * ld + j] = ljj;
+        for (int r = lane; r < m; r += 32)
+            if (r > j) L[r * ld + j] /= ljj;
         __syncwarp();
-        if (lane > j && lane < m) {
-            const double lij = L[lane * m + j];
-            for (int k = j + 1; k <= lane; ++k) L[lane * m + k] -= lij * L[k * m + j];
-        }
+        for (int r = lane; r < m; r += 32)
+            if (r > j) {
+                const double lij = L[r * ld + j];
+                for (int k = j + 1; k <= r; ++k) L[r * ld + k] -= lij * L[k * ld + j];
+            }
         __syncwarp();
     }
+    return ok;
+}
+
+// Joint batches (q = Q candidate points per batch, nb + Q <= 64): with c = Cov_D(f(X_b), y(X)) (nb x Q),
+// S = K_qq + noise I - V^T V and B_g = S^-1 (y_g - mu) the refit joint posterior over [X_baseline; X] is
+//   mean = [mu_b + c B_g ; mu + (y_g - mu) - noise B_g],
+//   cov  = [[Sigma_bb - c S^-1 c^T, noise c S^-1], [., noise (I - noise S^-1)]]       -- independent of the grid point.
+// One warp per joint batch for the factor; then one lane per (MC sample, grid point).  values: n_cand x S x G x Q, read by
+// k_score (Q = 1) / k_score_q.
+constexpr int NEI_WARPS = 4;
+
+template <int Q>
+__global__ void __launch_bounds__(NEI_WARPS * 32)
+k_nei_values_q(const NeiArgs p) {
+    extern __shared__ double nei_sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * NEI_WARPS + warp;
+    if (c >= p.n_cand) return;
+    const int nb = p.nb, m = nb + Q, r0 = c * Q, ld = nei_ld(m);
+    double* L = nei_sm + size_t(warp) * nei_warp_doubles(nb, Q);
+    double* cv = L + size_t(m) * ld;      // c[r][j]
+    double* cs = cv + size_t(nb) * Q;     // (c S^-1)[r][j]
+    double Sm[Q][Q], Si[Q][Q], Lc[Q][Q];
+    const bool ok = nei_setup<Q>(p, c, lane, L, cv, cs, Sm, Si, Lc);
     double mu[Q];
 #pragma unroll
     for (int j = 0; j < Q; ++j) mu[j] = p.mu[r0 + j];
@@ -272,8 +201,8 @@ k_nei_values_q(const NeiArgs p) {
             Bg[j] = a;
         }
         const double* e = p.eps_mc + (int64_t(smp) * p.G + g) * m;
-        double mx = -INFINITY;
-        double fb[NEI_MAX_NB], fx[Q];
+        // baseline rows: running (max, sum of exponentials) of f_b / temp; then the candidate rows
+        double mx = -INFINITY, se = 0.0, fx[Q];
         for (int r = 0; r < m; ++r) {
             double acc;
             if (r < nb) {
@@ -286,20 +215,19 @@ k_nei_values_q(const NeiArgs p) {
                 for (int j = 0; j < Q; ++j)
                     if (j == r - nb) acc = mu[j] + dev[j] - p.noise * Bg[j];
             }
-            for (int k = 0; k <= r; ++k) acc = fma(L[r * m + k], e[k], acc);
-            if (r < nb) { fb[r] = acc; mx = fmax(mx, acc); }
-            else {
+            for (int k = 0; k <= r; ++k) acc = fma(L[r * ld + k], e[k], acc);
+            if (r < nb) {
+                if (p.temp > 0.0) {
+                    if (acc > mx) { se = se * exp((mx - acc) * inv_temp) + 1.0; mx = acc; }
+                    else se += exp((acc - mx) * inv_temp);
+                } else mx = fmax(mx, acc);
+            } else {
 #pragma unroll
                 for (int j = 0; j < Q; ++j)
                     if (j == r - nb) fx[j] = acc;
             }
         }
-        double smax = mx;
-        if (p.temp > 0.0) {
-            double se = 0.0;
-            for (int r = 0; r < nb; ++r) se += exp((fb[r] - mx) * inv_temp);
-            smax = mx + p.temp * log(se);                            // temp * logsumexp(f_b / temp)
-        }
+        const double smax = (p.temp > 0.0) ? mx + p.temp * log(se) : mx;     // temp * logsumexp(f_b / temp)
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             double val;
@@ -315,15 +243,23 @@ k_nei_values_q(const NeiArgs p) {
     }
 }
 
+template <int Q>
+inline cudaError_t launch_nei_values_t(const NeiArgs& a, cudaStream_t s) {
+    const size_t smem = sizeof(double) * NEI_WARPS * nei_warp_doubles(a.nb, Q);
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(k_nei_values_q<Q>, smem); e != cudaSuccess) return e;
+    CBO_LAUNCHED(), k_nei_values_q<Q><<<(a.n_cand + NEI_WARPS - 1) / NEI_WARPS, NEI_WARPS * 32, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 inline cudaError_t launch_nei_values_q(const NeiArgs& a, int q, cudaStream_t s) {
-    const int grid = (a.n_cand + 3) / 4;
     switch (q) {
-        case 2: CBO_LAUNCHED(), k_nei_values_q<2><<<grid, 128, 0, s>>>(a); break;
-        case 3: CBO_LAUNCHED(), k_nei_values_q<3><<<grid, 128, 0, s>>>(a); break;
-        case 4: CBO_LAUNCHED(), k_nei_values_q<4><<<grid, 128, 0, s>>>(a); break;
+        case 1: return launch_nei_values_t<1>(a, s);
+        case 2: return launch_nei_values_t<2>(a, s);
+        case 3: return launch_nei_values_t<3>(a, s);
+        case 4: return launch_nei_values_t<4>(a, s);
         default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 }  // namespace cbo

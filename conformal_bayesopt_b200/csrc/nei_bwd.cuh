@@ -9,15 +9,13 @@
 //   S_bar + S_bar^T   added to the record                    (adjq[2..])
 //   c_bar (nb x Q)    c_rj = k(X_b,r, x_j) - K_bX[r,:] w_j:  w_bar'_j -= K_bX^T c_bar_j (right-hand side of the A^-1 solve),
 //                     and the direct term sum_r c_bar_rj dk(X_b,r, x_j)/dx_j, added by k_rows_bwd_q from cv_bar.
-// One warp per joint batch, lane = row of the (nb+Q)^2 factor; the Cholesky reverse  Sigma_bar = L^-T Phi(L^T L_bar) L^-1
+// One warp per joint batch, a lane owns rows lane and lane + 32 of the (nb+Q)^2 factor; the Cholesky reverse  Sigma_bar = L^-T Phi(L^T L_bar) L^-1
 // is two triangular solves with one column / one row per lane.  oracle: torch.autograd through oracle/closed_form.py.
 #pragma once
 #include "nei.cuh"
 #include "score_q_bwd.cuh"
 
 namespace cbo {
-
-constexpr int NEI_LD = 33;                     // padded row stride of the 32 x 32 work matrices (conflict-free rows AND columns)
 
 struct NeiBwdArgs {
     NeiArgs f;
@@ -27,145 +25,54 @@ struct NeiBwdArgs {
     double* cv_bar;            // n_cand x nb x Q      (out)
 };
 
+__host__ __device__ inline size_t nei_bwd_doubles(int nb, int q) { return 3 * size_t(nb + q) * nei_ld(nb + q) + 3 * size_t(nb + q) * q; }
+
 template <int Q>
 __global__ void __launch_bounds__(32)
 k_nei_values_q_bwd(const NeiBwdArgs qb) {
     const NeiArgs& p = qb.f;
-    __shared__ double sL[32 * NEI_LD], sLb[32 * NEI_LD], sY[32 * NEI_LD];
-    __shared__ double cv[32 * Q], cs[32 * Q], cvb_s[32 * Q];
+    extern __shared__ double nei_sm[];
     const int lane = threadIdx.x;
     const int c = blockIdx.x;
     if (c >= p.n_cand) return;
-    const int nb = p.nb, m = nb + Q, r0 = c * Q;
+    const int nb = p.nb, m = nb + Q, r0 = c * Q, ld = nei_ld(m);
     const double noise = p.noise;
+    double* L = nei_sm;
+    double* Lb = L + size_t(m) * ld;
+    double* Y = Lb + size_t(m) * ld;
+    double* cv = Y + size_t(m) * ld;
+    double* cs = cv + size_t(m) * Q;
+    double* cvb_s = cs + size_t(m) * Q;
     // ---- forward set-up (as k_nei_values_q) -------------------------------------------------------------------------
-    double Sm[Q][Q], Ls[Q][Q], Si[Q][Q], Cov[Q][Q], Lc[Q][Q];
-#pragma unroll
-    for (int j = 0; j < Q; ++j)
-#pragma unroll
-        for (int k = 0; k < Q; ++k) {
-            if (k > j) continue;
-            double acc = 0.0;
-            for (int i = lane; i < p.N; i += 32) acc = fma(p.V[int64_t(r0 + j) * p.Np + i], p.V[int64_t(r0 + k) * p.Np + i], acc);
-            acc = warp_sum(acc);
-            double r2 = 0.0;
-            for (int e = 0; e < p.d; ++e) {
-                const double df = (p.Xq[int64_t(r0 + j) * p.d + e] - p.Xq[int64_t(r0 + k) * p.d + e]) * p.inv_ls[e];
-                r2 = fma(df, df, r2);
-            }
-            const double r = sqrt(fmax(r2, 1e-30));
-            const double kk = p.kappa * (1.0 + kSqrt5 * r + (5.0 / 3.0) * r * r) * exp(-kSqrt5 * r);
-            const double v = kk - acc + ((j == k) ? noise : 0.0);
-            Sm[j][k] = v; Sm[k][j] = v;
-        }
-    bool ok = chol_lower<Q>(Sm, Ls);
-    inv_from_chol<Q>(Ls, Si);
-#pragma unroll
-    for (int j = 0; j < Q; ++j) {
-        const double rs = p.cscale ? p.cscale[r0 + j] : 1.0;
-#pragma unroll
-        for (int k = 0; k < Q; ++k) Cov[j][k] = rs * Sm[j][k];
-    }
-    ok = chol_lower<Q>(Cov, Lc) && ok;
-    double Sis[Q][Q];
+    double Sm[Q][Q], Si[Q][Q], Lc[Q][Q], Sis[Q][Q];
+    const bool ok = nei_setup<Q>(p, c, lane, L, cv, cs, Sm, Si, Lc);
 #pragma unroll
     for (int j = 0; j < Q; ++j)
 #pragma unroll
         for (int k = 0; k < Q; ++k) Sis[j][k] = 0.5 * (Si[j][k] + Si[k][j]);
-    for (int r = 0; r < nb; ++r) {
-        double acc[Q];
-#pragma unroll
-        for (int j = 0; j < Q; ++j) acc[j] = 0.0;
-        for (int i = lane; i < p.N; i += 32) {
-            const double kb = p.KbX[int64_t(r) * p.Np + i];
-#pragma unroll
-            for (int j = 0; j < Q; ++j) acc[j] = fma(kb, p.W[int64_t(r0 + j) * p.Np + i], acc[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            acc[j] = warp_sum(acc[j]);
-            if (lane == j) {
-                double r2 = 0.0;
-                for (int e = 0; e < p.d; ++e) {
-                    const double df = (p.Xb[r * p.d + e] - p.Xq[int64_t(r0 + j) * p.d + e]) * p.inv_ls[e];
-                    r2 = fma(df, df, r2);
-                }
-                const double rr = sqrt(fmax(r2, 1e-30));
-                cv[r * Q + j] = p.kappa * (1.0 + kSqrt5 * rr + (5.0 / 3.0) * rr * rr) * exp(-kSqrt5 * rr) - acc[j];
-            }
-        }
-    }
-    __syncwarp();
-    if (lane < nb) {
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            double a = 0.0;
-#pragma unroll
-            for (int k = 0; k < Q; ++k) a = fma(cv[lane * Q + k], Sis[k][j], a);
-            cs[lane * Q + j] = a;
-        }
-    }
-    __syncwarp();
-    double* L = sL;
-    double* Lb = sLb;
-    double* Y = sY;
-    for (int k = 0; k < 32; ++k) { L[lane * NEI_LD + k] = 0.0; Lb[lane * NEI_LD + k] = 0.0; Y[lane * NEI_LD + k] = 0.0; }
-    if (lane < m) {
-        for (int k = 0; k <= lane; ++k) {
-            double v;
-            if (lane < nb) {
-                v = p.Sbb[lane * nb + k];
-#pragma unroll
-                for (int j = 0; j < Q; ++j) v -= cs[lane * Q + j] * cv[k * Q + j];
-            } else {
-                const int j = lane - nb;
-                if (k < nb) v = noise * cs[k * Q + j];
-                else {
-                    const int j2 = k - nb;
-                    double sij = 0.0;
-#pragma unroll
-                    for (int a = 0; a < Q; ++a)
-#pragma unroll
-                        for (int b2 = 0; b2 < Q; ++b2)
-                            if (a == j && b2 == j2) sij = Sis[a][b2];
-                    v = noise * (((j == j2) ? 1.0 : 0.0) - noise * sij);
-                }
-            }
-            L[lane * NEI_LD + k] = v;
-        }
-    }
-    __syncwarp();
-    for (int j = 0; j < m; ++j) {
-        const double djj = L[j * NEI_LD + j];
-        ok = ok && (djj > 0.0);
-        const double ljj = sqrt(djj);
-        __syncwarp();
-        if (lane == j) L[j * NEI_LD + j] = ljj;
-        if (lane > j && lane < m) L[lane * NEI_LD + j] /= ljj;
-        __syncwarp();
-        if (lane > j && lane < m) {
-            const double lij = L[lane * NEI_LD + j];
-            for (int k = j + 1; k <= lane; ++k) L[lane * NEI_LD + k] -= lij * L[k * NEI_LD + j];
-        }
-        __syncwarp();
-    }
+    for (int r = lane; r < m; r += 32)
+        for (int k = 0; k < m; ++k) { Lb[r * ld + k] = 0.0; Y[r * ld + k] = 0.0; }
     double mu[Q];
 #pragma unroll
     for (int j = 0; j < Q; ++j) mu[j] = p.mu[r0 + j];
     const double inv_temp = p.temp > 0.0 ? 1.0 / p.temp : 0.0;
+    __syncwarp();
 
-    // ---- reverse sweep over (MC sample, grid point): all lanes in lockstep, lane = row of the joint sample ----------------
-    double cvb[Q], mub[Q], Sib[Q][Q];
+    // ---- reverse sweep over (MC sample, grid point): all lanes in lockstep, a lane owns rows lane (slot 0) and lane + 32 (slot 1) ----
+    double cvb[2][Q], cvr[2][Q], mubr[2], mub[Q], Sib[Q][Q];
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
-        cvb[j] = 0.0; mub[j] = 0.0;
+        mub[j] = 0.0;
 #pragma unroll
         for (int k = 0; k < Q; ++k) Sib[j][k] = 0.0;
     }
-    double cvr[Q];                                   // this lane's row of c
 #pragma unroll
-    for (int j = 0; j < Q; ++j) cvr[j] = (lane < nb) ? cv[lane * Q + j] : 0.0;
-    const double mub_r = (lane < nb) ? p.mub[lane] : 0.0;
+    for (int t = 0; t < 2; ++t) {
+        const int r = lane + 32 * t;
+        mubr[t] = (r < nb) ? p.mub[r] : 0.0;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) { cvb[t][j] = 0.0; cvr[t][j] = (r < nb) ? cv[r * Q + j] : 0.0; }
+    }
     for (int sg = 0; sg < p.S * p.G; ++sg) {
         const int smp = sg / p.G, g = sg - smp * p.G;
         const double* eg = p.eps_grid + (p.eps_per_candidate ? int64_t(c) * p.G + g : int64_t(g)) * Q;
@@ -186,65 +93,86 @@ k_nei_values_q_bwd(const NeiBwdArgs qb) {
             Bg[j] = a;
         }
         const double* e = p.eps_mc + (int64_t(smp) * p.G + g) * m;
-        double f = 0.0;
-        if (lane < m) {
-            if (lane < nb) {
-                f = mub_r;
+        double f[2];
 #pragma unroll
-                for (int j = 0; j < Q; ++j) f = fma(cvr[j], Bg[j], f);
-            } else {
+        for (int t = 0; t < 2; ++t) {
+            const int r = lane + 32 * t;
+            f[t] = 0.0;
+            if (r < m) {
+                if (r < nb) {
+                    f[t] = mubr[t];
 #pragma unroll
-                for (int j = 0; j < Q; ++j)
-                    if (j == lane - nb) f = mu[j] + dev[j] - noise * Bg[j];
+                    for (int j = 0; j < Q; ++j) f[t] = fma(cvr[t][j], Bg[j], f[t]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < Q; ++j)
+                        if (j == r - nb) f[t] = mu[j] + dev[j] - noise * Bg[j];
+                }
+                for (int k = 0; k <= r; ++k) f[t] = fma(L[r * ld + k], e[k], f[t]);
             }
-            for (int k = 0; k <= lane; ++k) f = fma(L[lane * NEI_LD + k], e[k], f);
         }
         double vb[Q];
 #pragma unroll
         for (int j = 0; j < Q; ++j) vb[j] = qb.val_bar[((int64_t(c) * p.S + smp) * p.G + g) * Q + j];
-        double fbar = 0.0, fxb[Q];                   // fxb[j]: adjoint of the sample at candidate point j (every lane)
+        double fbar[2] = {0.0, 0.0}, fxb[Q];           // fxb[j]: adjoint of the sample at candidate point j (every lane)
         if (p.raw) {
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
                 fxb[j] = vb[j];
-                if (lane == nb + j) fbar = vb[j];
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+                    if (lane + 32 * t == nb + j) fbar[t] = vb[j];
             }
         } else {
-            double fb = (lane < nb) ? f : -INFINITY;
-            double mx = fb;
+            double mx = fmax((lane < nb) ? f[0] : -INFINITY, (lane + 32 < nb) ? f[1] : -INFINITY);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            double sm_r, smax;
+            double sm_r[2], smax;
             if (p.temp > 0.0) {
-                const double ex = (lane < nb) ? exp((f - mx) * inv_temp) : 0.0;
-                const double se = warp_sum(ex);
+                const double ex0 = (lane < nb) ? exp((f[0] - mx) * inv_temp) : 0.0;
+                const double ex1 = (lane + 32 < nb) ? exp((f[1] - mx) * inv_temp) : 0.0;
+                const double se = warp_sum(ex0 + ex1);
                 smax = mx + p.temp * log(se);
-                sm_r = ex / se;
+                sm_r[0] = ex0 / se; sm_r[1] = ex1 / se;
             } else {                                  // hard maximum: its adjoint goes to the first arg-max
-                const unsigned hit = __ballot_sync(0xffffffffu, lane < nb && f == mx);
-                sm_r = (lane == __ffs(hit) - 1) ? 1.0 : 0.0;
+                const unsigned hit0 = __ballot_sync(0xffffffffu, lane < nb && f[0] == mx);
+                const unsigned hit1 = __ballot_sync(0xffffffffu, lane + 32 < nb && f[1] == mx);
+                sm_r[0] = (hit0 && lane == __ffs(hit0) - 1) ? 1.0 : 0.0;
+                sm_r[1] = (!hit0 && hit1 && lane == __ffs(hit1) - 1) ? 1.0 : 0.0;
                 smax = mx;
             }
             double tsum = 0.0;
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
-                const double fx = __shfl_sync(0xffffffffu, f, nb + j);
+                const int rx = nb + j;
+                const double fx = __shfl_sync(0xffffffffu, (rx >= 32) ? f[1] : f[0], rx & 31);
                 double dv;
                 if (p.temp > 0.0) dv = sigmoid_acc((fx - smax) * inv_temp);
                 else dv = (fx - smax > 0.0) ? 1.0 : 0.0;
                 fxb[j] = vb[j] * dv;
                 tsum += fxb[j];
-                if (lane == nb + j) fbar = fxb[j];
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+                    if (lane + 32 * t == rx) fbar[t] = fxb[j];
             }
-            if (lane < nb) fbar = -tsum * sm_r;
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+                if (lane + 32 * t < nb) fbar[t] = -tsum * sm_r[t];
         }
-        if (lane < m)
-            for (int k = 0; k <= lane; ++k) Lb[lane * NEI_LD + k] = fma(fbar, e[k], Lb[lane * NEI_LD + k]);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int r = lane + 32 * t;
+            if (r < m)
+                for (int k = 0; k <= r; ++k) Lb[r * ld + k] = fma(fbar[t], e[k], Lb[r * ld + k]);
+        }
         double Bgb[Q];
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
-            if (lane < nb) cvb[j] = fma(fbar, Bg[j], cvb[j]);
-            Bgb[j] = warp_sum((lane < nb) ? fbar * cvr[j] : 0.0) - noise * fxb[j];
+            double part = 0.0;
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+                if (lane + 32 * t < nb) { cvb[t][j] = fma(fbar[t], Bg[j], cvb[t][j]); part = fma(fbar[t], cvr[t][j], part); }
+            Bgb[j] = warp_sum(part) - noise * fxb[j];
         }
 #pragma unroll
         for (int k = 0; k < Q; ++k) {
@@ -260,67 +188,69 @@ k_nei_values_q_bwd(const NeiBwdArgs qb) {
     __syncwarp();
 
     // ---- Cholesky reverse: Sigma_bar = L^-T Phi(L^T L_bar) L^-1 ---------------------------------------------------------------
-    if (lane < m) {                                   // row `lane` of Phi(L^T L_bar) -> Y
-        for (int k = 0; k <= lane; ++k) {
+    for (int r = lane; r < m; r += 32)                // row r of Phi(L^T L_bar) -> Y
+        for (int k = 0; k <= r; ++k) {
             double s = 0.0;
-            for (int i = lane; i < m; ++i) s = fma(L[i * NEI_LD + lane], Lb[i * NEI_LD + k], s);
-            Y[lane * NEI_LD + k] = (k == lane) ? 0.5 * s : s;
+            for (int i = r; i < m; ++i) s = fma(L[i * ld + r], Lb[i * ld + k], s);
+            Y[r * ld + k] = (k == r) ? 0.5 * s : s;
         }
-    }
     __syncwarp();
-    if (lane < m) {                                   // column `lane`: L^T y = phi  (back substitution, in place)
+    for (int col = lane; col < m; col += 32)          // column col: L^T y = phi  (back substitution, in place)
         for (int i = m - 1; i >= 0; --i) {
-            double s = Y[i * NEI_LD + lane];
-            for (int t = i + 1; t < m; ++t) s = fma(-L[t * NEI_LD + i], Y[t * NEI_LD + lane], s);
-            Y[i * NEI_LD + lane] = s / L[i * NEI_LD + i];
+            double s = Y[i * ld + col];
+            for (int t = i + 1; t < m; ++t) s = fma(-L[t * ld + i], Y[t * ld + col], s);
+            Y[i * ld + col] = s / L[i * ld + i];
         }
-    }
     __syncwarp();
-    if (lane < m) {                                   // row `lane`: x L = y  (in place)
+    for (int r = lane; r < m; r += 32)                // row r: x L = y  (in place)
         for (int k = m - 1; k >= 0; --k) {
-            double s = Y[lane * NEI_LD + k];
-            for (int t = k + 1; t < m; ++t) s = fma(-Y[lane * NEI_LD + t], L[t * NEI_LD + k], s);
-            Y[lane * NEI_LD + k] = s / L[k * NEI_LD + k];
+            double s = Y[r * ld + k];
+            for (int t = k + 1; t < m; ++t) s = fma(-Y[r * ld + t], L[t * ld + k], s);
+            Y[r * ld + k] = s / L[k * ld + k];
         }
-    }
     __syncwarp();
-    // symmetrised adjoint M = (Y + Y^T)/2 into Lb
-    if (lane < m)
-        for (int k = 0; k < m; ++k) Lb[lane * NEI_LD + k] = 0.5 * (Y[lane * NEI_LD + k] + Y[k * NEI_LD + lane]);
+    for (int r = lane; r < m; r += 32)                // symmetrised adjoint M = (Y + Y^T)/2 into Lb
+        for (int k = 0; k < m; ++k) Lb[r * ld + k] = 0.5 * (Y[r * ld + k] + Y[k * ld + r]);
     __syncwarp();
     const double* M = Lb;
 
     // ---- Sigma_bar -> c_bar, S^-1_bar ------------------------------------------------------------------------------------
-    double csb[Q];
+    double csb[2][Q];
 #pragma unroll
-    for (int j = 0; j < Q; ++j) csb[j] = 0.0;
-    if (lane < nb) {
+    for (int t = 0; t < 2; ++t) {
+        const int r = lane + 32 * t;
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
-            double a = 0.0, b2 = 0.0;
-            for (int k = 0; k < nb; ++k) {
-                a = fma(M[lane * NEI_LD + k], cv[k * Q + j], a);
-                b2 = fma(M[lane * NEI_LD + k], cs[k * Q + j], b2);
+            csb[t][j] = 0.0;
+            if (r < nb) {
+                double a = 0.0, b2 = 0.0;
+                for (int k = 0; k < nb; ++k) {
+                    a = fma(M[r * ld + k], cv[k * Q + j], a);
+                    b2 = fma(M[r * ld + k], cs[k * Q + j], b2);
+                }
+                csb[t][j] = -a + 2.0 * noise * M[(nb + j) * ld + r];
+                cvb[t][j] -= b2;
             }
-            csb[j] = -a + 2.0 * noise * M[(nb + j) * NEI_LD + lane];
-            cvb[j] -= b2;
         }
     }
     double Sisb[Q][Q];
 #pragma unroll
     for (int k = 0; k < Q; ++k)
 #pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            Sisb[k][j] = warp_sum((lane < nb) ? cvr[k] * csb[j] : 0.0) - noise * noise * M[(nb + k) * NEI_LD + nb + j];
-        }
-    if (lane < nb) {
+        for (int j = 0; j < Q; ++j)
+            Sisb[k][j] = warp_sum(cvr[0][k] * csb[0][j] + cvr[1][k] * csb[1][j]) - noise * noise * M[(nb + k) * ld + nb + j];
 #pragma unroll
-        for (int k = 0; k < Q; ++k) {
-            double a = cvb[k];
+    for (int t = 0; t < 2; ++t) {
+        const int r = lane + 32 * t;
+        if (r < nb) {
 #pragma unroll
-            for (int j = 0; j < Q; ++j) a = fma(csb[j], Sis[k][j], a);
-            cvb_s[lane * Q + k] = a;
-            qb.cv_bar[(int64_t(c) * nb + lane) * Q + k] = ok ? a : nan("");
+            for (int k = 0; k < Q; ++k) {
+                double a = cvb[t][k];
+#pragma unroll
+                for (int j = 0; j < Q; ++j) a = fma(csb[t][j], Sis[k][j], a);
+                cvb_s[r * Q + k] = a;
+                qb.cv_bar[(int64_t(c) * nb + r) * Q + k] = ok ? a : nan("");
+            }
         }
     }
     __syncwarp();
@@ -372,15 +302,23 @@ k_nei_values_q_bwd(const NeiBwdArgs qb) {
     }
 }
 
+template <int Q>
+inline cudaError_t launch_nei_values_bwd_t(const NeiBwdArgs& a, cudaStream_t s) {
+    const size_t smem = sizeof(double) * nei_bwd_doubles(a.f.nb, Q);
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(k_nei_values_q_bwd<Q>, smem); e != cudaSuccess) return e;
+    CBO_LAUNCHED(), k_nei_values_q_bwd<Q><<<a.f.n_cand, 32, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 inline cudaError_t launch_nei_values_q_bwd(const NeiBwdArgs& a, int q, cudaStream_t s) {
     switch (q) {
-        case 1: CBO_LAUNCHED(), k_nei_values_q_bwd<1><<<a.f.n_cand, 32, 0, s>>>(a); break;
-        case 2: CBO_LAUNCHED(), k_nei_values_q_bwd<2><<<a.f.n_cand, 32, 0, s>>>(a); break;
-        case 3: CBO_LAUNCHED(), k_nei_values_q_bwd<3><<<a.f.n_cand, 32, 0, s>>>(a); break;
-        case 4: CBO_LAUNCHED(), k_nei_values_q_bwd<4><<<a.f.n_cand, 32, 0, s>>>(a); break;
+        case 1: return launch_nei_values_bwd_t<1>(a, s);
+        case 2: return launch_nei_values_bwd_t<2>(a, s);
+        case 3: return launch_nei_values_bwd_t<3>(a, s);
+        case 4: return launch_nei_values_bwd_t<4>(a, s);
         default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 }  // namespace cbo

@@ -194,7 +194,8 @@ class qConformalNoisyExpectedHypervolumeImprovement(qConformalExpectedHypervolum
     call f(X) is sampled JOINTLY with the baseline under every refit model -- the baseline part of the joint base samples is
     the stored one, shared by all grid points (botorch `_set_sampler`), the new points draw (S, G, q, m) -- and the
     hyper-volume improvement of sample s is taken against the cells of sample s.  Built for two objectives (the 2-D box
-    decomposition), a pruned baseline of nb + q <= 32 points, q <= 4 incl. pending points."""
+    decomposition), a (pruned: `prune_baseline=True` runs sampling.prune_inferior_points_multi_objective) baseline of
+    nb + q <= 64 points, q <= 4 incl. pending points."""
 
     _kind = "nehvi"
 
@@ -213,8 +214,13 @@ class qConformalNoisyExpectedHypervolumeImprovement(qConformalExpectedHypervolum
         if m != 2:
             raise NotImplementedError("the box decomposition is built for two objectives")
         Xb = X_baseline.reshape(-1, X_baseline.shape[-1])
-        if Xb.shape[0] > 31:
-            raise NotImplementedError("cNEHVI is built for at most 31 baseline points: pass the pruned baseline")
+        if prune_baseline:
+            from .sampling import prune_inferior_points_multi_objective
+            Xb = prune_inferior_points_multi_objective(states, Xb, ref_point, base_samples=unused.get("prune_base_samples"),
+                                                       seed=unused.get("prune_seed"))
+            X_baseline = Xb
+        if Xb.shape[0] > 60:
+            raise NotImplementedError("cNEHVI is built for nb + q <= 64 joint points: prune the baseline (prune_baseline=True)")
         self.X_baseline = X_baseline
         self.ref_point = torch.as_tensor(ref_point, dtype=torch.float64).reshape(-1)
         self._baselines = [ops.NeiBaseline.build(st, Xb) for st in states]
@@ -232,8 +238,8 @@ class qConformalNoisyExpectedHypervolumeImprovement(qConformalExpectedHypervolum
     def _joint_outputs(self, X):
         states, m, X, Xf, lead, q, b, G, dev, eps, z, u = self._prepare(X)
         S, nb = self.baseline_base_samples.shape[0], self.baseline_base_samples.shape[1]
-        if nb + q > 32:
-            raise NotImplementedError("cNEHVI: nb + q <= 32")
+        if nb + q > 64:
+            raise NotImplementedError("cNEHVI: nb + q <= 64")
         eps_new = self.sampler.draw((S, G, q, m), dev)                                           # base samples (S, 1, G, q, t)
         eps_joint = torch.cat([self.baseline_base_samples.to(dev).unsqueeze(1).expand(S, G, nb, m), eps_new], dim=2)
         outs = [self._per_output(st, k, Xf, q, G, dev, eps, z, u, kind="joint", nei_baseline=self._baselines[k],

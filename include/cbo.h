@@ -87,7 +87,7 @@ typedef struct {
     const double* W3; const double* b3;   /* 1 x H, 1 */
 } cbo_ratio_mlp_f64;
 
-/* cNEI baseline (conformalbo/acquisitions.py:115-134), prepared once per acquisition object; q = 1, nb <= 31 */
+/* cNEI baseline (conformalbo/acquisitions.py:115-134), prepared once per acquisition object; nb + q <= 64 */
 typedef struct {
     int64_t nb;                /* baseline points (after botorch's prune_baseline)              */
     const double* Xb;          /* nb x d                                                        */

@@ -264,7 +264,7 @@ def test_cnehvi_matches_oracle(q, pending):
     acq = qConformalNoisyExpectedHypervolumeImprovement(alpha=0.2, temp=3e-2, grid_res=G, max_grid_refinements=0,
                                                         ratio_estimator=None, optimistic=True, grid_sampler=gs, randomized=True,
                                                         model=states, ref_point=ref, X_baseline=Xb.to(dev), sampler=mc,
-                                                        prune_baseline=True, baseline_base_samples=eps_b,
+                                                        prune_baseline=False, baseline_base_samples=eps_b,
                                                         X_pending=Xq[0, q - pending:].to(dev) if pending else None)
     assert torch.allclose(acq.baseline_samples, fb, rtol=1e-9, atol=1e-11)
     assert torch.allclose(acq.cell_lower.cpu(), lo, rtol=1e-9, atol=1e-11) and torch.equal(torch.isinf(acq.cell_upper.cpu()), torch.isinf(up))
@@ -299,7 +299,7 @@ def test_cnei_matches_oracle(temp, refine, q):
     mc.set_base_samples(eps_mc)
     acq = qConformalNoisyExpectedImprovement(alpha=0.15, temp=temp, grid_res=G, max_grid_refinements=refine,
                                              ratio_estimator=est, grid_sampler=gs, randomized=True, model=_state(p, dev),
-                                             X_baseline=Xb.to(dev), sampler=mc, prune_baseline=True)
+                                             X_baseline=Xb.to(dev), sampler=mc, prune_baseline=False)
     acq.fixed_probes, acq.fixed_uniforms = inp["z"], inp["u_rand"].to(dev)
     with torch.no_grad():
         got = acq(inp["Xq"].to(dev))

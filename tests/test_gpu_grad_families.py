@@ -56,7 +56,7 @@ def test_cnei_grad_matches_autograd_of_oracle(temp, q, ratio_on, S):
     mc.set_base_samples(eps_mc)
     acq = qConformalNoisyExpectedImprovement(alpha=0.15, temp=temp, grid_res=G, max_grid_refinements=0, ratio_estimator=est,
                                              grid_sampler=gs, randomized=True, model=_state(p, dev), X_baseline=Xb.to(dev),
-                                             sampler=mc, prune_baseline=True)
+                                             sampler=mc, prune_baseline=False)
     acq.fixed_probes, acq.fixed_uniforms = inp["z"], inp["u_rand"].to(dev)
     X = inp["Xq"].to(dev).requires_grad_(True)
     got = acq(X)
@@ -153,7 +153,7 @@ def test_cnehvi_grad_matches_autograd_of_oracle(q, pending):
     acq = qConformalNoisyExpectedHypervolumeImprovement(alpha=0.2, temp=3e-2, grid_res=G, max_grid_refinements=0,
                                                         ratio_estimator=None, optimistic=True, grid_sampler=gs, randomized=True,
                                                         model=P["states"], ref_point=P["ref"], X_baseline=P["Xb"].to(dev),
-                                                        sampler=mc, prune_baseline=True, baseline_base_samples=P["eps_b"],
+                                                        sampler=mc, prune_baseline=False, baseline_base_samples=P["eps_b"],
                                                         X_pending=P["Xq"][0, q - pending:].to(dev) if pending else None)
     acq.fixed_probes, acq.fixed_uniforms = P["z"], P["u"].to(dev)
     X = P["Xq"][:, :q - pending].to(dev).requires_grad_(True)
@@ -167,3 +167,79 @@ def test_cnehvi_grad_matches_autograd_of_oracle(q, pending):
     assert torch.allclose(got.detach().cpu(), want["acq"].detach(), rtol=1e-6, atol=1e-10)
     assert gw.abs().max() > 0
     assert _grad_close(X.grad.cpu(), gw)
+
+
+@pytest.mark.parametrize("nb,q", [(40, 2), (60, 4), (33, 1)])
+def test_cnei_wide_baseline_value_and_grad(nb, q):
+    """More than 32 joint points (each lane owns two rows of the (nb+q)^2 factor): value and gradient against the oracle."""
+    from conformal_bayesopt_b200.acquisitions import qConformalNoisyExpectedImprovement
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    dev = _dev()
+    N, d, b, G, S = 120, 3, 6, 16, 2
+    p = make_problem(N, d, seed=21, noise=1e-2)
+    inp = make_inputs(N, d, b, q, G, S=S, seed=21)
+    g = torch.Generator().manual_seed(5)
+    Xb = torch.rand(nb, d, generator=g, dtype=torch.float64)       # spread-out baseline: a well-conditioned joint covariance
+    eps_mc = torch.randn(S, G, nb + q, generator=g, dtype=torch.float64)
+    gs = IIDNormalSampler(G)
+    gs.set_base_samples(inp["eps_grid"])
+    mc = IIDNormalSampler(S, batch_range=(0, -3))
+    mc.set_base_samples(eps_mc)
+    acq = qConformalNoisyExpectedImprovement(alpha=0.15, temp=3e-2, grid_res=G, max_grid_refinements=0, ratio_estimator=None,
+                                             grid_sampler=gs, randomized=True, model=_state(p, dev), X_baseline=Xb.to(dev),
+                                             sampler=mc)
+    acq.fixed_probes, acq.fixed_uniforms = inp["z"], inp["u_rand"].to(dev)
+    X = inp["Xq"].to(dev).requires_grad_(True)
+    got = acq(X)
+    got.sum().backward()
+    Xo = inp["Xq"].clone().requires_grad_(True)
+    want = closed_form.conformal_acquisition(oracle_state(p), Xo, kind="nei", alpha=0.15, temp=3e-2, grid_res=G,
+                                             eps_grid=inp["eps_grid"], z=inp["z"], eps_mc=eps_mc, randomized=True,
+                                             u_rand=inp["u_rand"], optimistic=False, X_baseline=Xb)
+    (gw,) = torch.autograd.grad(want["acq"].sum(), Xo)
+    assert torch.allclose(got.detach().cpu(), want["acq"].detach(), rtol=1e-6, atol=1e-10)
+    scale = gw.abs().max()
+    assert scale > 0 and torch.allclose(X.grad.cpu(), gw, rtol=1e-5, atol=float(1e-7 * scale))   # 60-wide factor: cond(Sigma) enters
+    with torch.no_grad():
+        assert torch.allclose(acq(inp["Xq"].to(dev)), got.detach(), rtol=1e-12, atol=1e-14)
+
+
+def test_prune_baseline_matches_botorch_semantics():
+    """`prune_baseline=True` (hydra_config/acq_fn/cnei.yaml:3): botorch's prune_inferior_points restated on the CPU with the
+    same injected base samples -- keep the points that win at least one joint posterior sample."""
+    from conformal_bayesopt_b200.acquisitions import qConformalNoisyExpectedImprovement
+    from conformal_bayesopt_b200.sampling import prune_inferior_points, prune_inferior_points_multi_objective
+    dev = _dev()
+    N, d, S = 90, 4, 256
+    p = make_problem(N, d, seed=13, noise=1e-2)
+    st = _state(p, dev)
+    gp = oracle_state(p)
+    g = torch.Generator().manual_seed(8)
+    base = torch.randn(S, N, generator=g, dtype=torch.float64)
+    kept = prune_inferior_points(st, p["X"].to(dev), base_samples=base)
+    # oracle: noise-free posterior at the training inputs
+    K = gp.k(gp.X, gp.X)
+    Vb = torch.linalg.solve_triangular(gp.L, K, upper=False)
+    mean = gp.mean + K @ gp.alpha
+    cov = K - Vb.T @ Vb
+    cov = 0.5 * (cov + cov.T)
+    L, info = torch.linalg.cholesky_ex(cov)
+    jitter = 1e-8
+    while int(info) != 0:
+        L, info = torch.linalg.cholesky_ex(cov + jitter * torch.eye(N, dtype=cov.dtype))
+        jitter *= 10.0
+    want_idx = torch.unique((mean.unsqueeze(0) + base @ L.T).argmax(-1))
+    assert 0 < kept.shape[0] < N
+    assert kept.shape[0] == want_idx.numel() and torch.allclose(kept.cpu(), p["X"][want_idx], atol=0)
+    acq = qConformalNoisyExpectedImprovement(alpha=0.15, temp=3e-2, grid_res=16, max_grid_refinements=0, ratio_estimator=None,
+                                             model=st, X_baseline=p["X"].to(dev), prune_baseline=True, prune_base_samples=base)
+    assert torch.equal(acq.X_baseline.cpu(), kept.cpu())
+    # Sobol default draws: a deterministic, non-empty subset
+    a = prune_inferior_points(st, p["X"].to(dev), num_samples=128, seed=3)
+    b = prune_inferior_points(st, p["X"].to(dev), num_samples=128, seed=3)
+    assert torch.equal(a, b) and 0 < a.shape[0] <= N
+    # two objectives: every kept point is Pareto-optimal in at least one sample
+    P = _mobo_problem(1, 0, 2, 8, 1)
+    base2 = torch.randn(64, P["N"], 2, generator=g, dtype=torch.float64)
+    kept2 = prune_inferior_points_multi_objective(P["states"], P["X"].to(dev), P["ref"], base_samples=base2)
+    assert 0 < kept2.shape[0] <= P["N"]
