@@ -356,6 +356,19 @@ def test_bo_loop_demo_runs_on_the_drop_in_classes():
     assert len(best) == 3 and all(math.isfinite(v) for v in best) and best[-1] >= best[0]
 
 
+@pytest.mark.parametrize("acq", ["cei", "cnei", "cehvi", "cnehvi"])
+def test_bo_loop_demo_runs_every_acquisition_through_the_sgld_optimiser(acq):
+    """conformalbo/utils.py:243-246 sends every acquisition with a ratio estimator to optimize_acqf_sgld: raw scoring, SGLD
+    steps on d acq / d X (cNEI: graph replay; cEHVI / cNEHVI: 2 m + 1 library calls per step), estimator training, re-scoring."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bo_demo", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "bo_demo.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    vals = mod.run_family(acq, rounds=2, sgld_steps=6, raw=64, restarts=3, verbose=False)
+    assert len(vals) == 2 and all(math.isfinite(v) for v in vals)
+
+
 def test_sharded_grid_refinement_matches_the_single_batch():
     """SURVEY.md §8e exception: with max_grid_refinements > 0 the reference's rescale / best-pass decisions are batch-global.
     Two 'ranks' (threads on their own streams, distinct workspaces) score the two halves of a batch; the refine_reduce hook

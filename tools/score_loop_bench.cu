@@ -29,7 +29,14 @@ __device__ __forceinline__ void rows(const ScoreArgs& p, const double* __restric
     double qa = tq[0], qb = tq[1], qc = tq[2];
     double bgu[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) bgu[k] = (V == 30 || V == 31) ? __shfl_sync(0xffffffffu, bg[k], 0) : bg[k];
+    for (int k = 0; k < 4; ++k) {
+        bgu[k] = (V == 30 || V == 31) ? __shfl_sync(0xffffffffu, bg[k], 0) : bg[k];
+        if (V == 40 || V == 42) {     // warp-uniform by construction: REDUX writes a UNIFORM register
+            const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)__double2loint(bg[k]));
+            const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)__double2hiint(bg[k]));
+            bgu[k] = __hiloint2double((int)hi, (int)lo);
+        }
+    }
     const int nsteps = N32 >> 5;
     for (int it = 0; it < nsteps; ++it) {
         tq += 96;
@@ -51,8 +58,15 @@ __device__ __forceinline__ void rows(const ScoreArgs& p, const double* __restric
         for (int k = 0; k < 4; ++k) {
             double pl = y[k] + kA2;
             pl = fma(pl, y[k], kA1);
-            pl = fma(pl, y[k], kA0);
+            if (V != 41 && V != 42) pl = fma(pl, y[k], kA0);
             double ts;
+            if (V == 41 || V == 42) {             // 128-entry table + quadratic (timing only: same constants)
+                const int n = __double2loint(t[k]);
+                unsigned addr = ((unsigned(n) << 3) & 0x3f8u) | tab_s;
+                int lo, hi;
+                asm("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
+                ts = __hiloint2double(hi + (n << 13), lo);
+            } else
             if (V == 2 || V == 5 || V == 31) ts = __hiloint2double(0xbee00000 + (__double2loint(t[k]) << 16), 0);   // no table load
             else ts = exp_tab_scaled(tab8_s, __double2loint(t[k]));
             e[k] = fma(ts, pl, 1.0);
@@ -71,9 +85,10 @@ __device__ __forceinline__ void rows(const ScoreArgs& p, const double* __restric
 __global__ void __launch_bounds__(512, 1) k(const ScoreArgs p, const double* coef, double* out, int passes) {
     extern __shared__ __align__(16) double sm[];
     __shared__ __align__(128) double tab8[16];
-    __shared__ __align__(128) double tab[16];
+    __shared__ __align__(1024) double tab[128];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 16) { exp_tab8_init(tab8, tid, p.k8_c3); exp_tab_init(tab, tid); }
+    if (tid >= 16 && tid < 128) tab[tid] = tab[tid & 15] ;
     double* sq = sm + size_t(warp >> 1) * (3 * 1024 + 96);
     for (int i = tid & 63; i < 3 * 1024 + 96; i += 64) sq[i] = coef[i % (3 * 1024)];
     __syncthreads();
