@@ -49,6 +49,8 @@ struct ScoreArgs {
     double k_magic, k_c0, k_c1n, k_c2, k_c3n;
     // the same cubic in the monic form of score_rows8: P(y) = c3 (((y + a2) y + a1) y + a0)
     double k8_a2, k8_a1, k8_a0, k8_c3;
+    // score_rows_fx: the monic cubic in w = 1 + z 2^-32 (kFxB2, kFxB1, kFxB0)
+    double fx_b2, fx_b1, fx_b0;
     // per-call tables (train side)
     const double* a;        // Np  noise*alpha
     const double* h0;       // Np
@@ -301,6 +303,86 @@ __device__ __forceinline__ void score_rows8(const ScoreArgs& p, const double* __
         }
         qa = qa_n; qb = qb_n; qc = qc_n; dr = dr_n;
     }
+}
+
+// ---- score_rows_fx: the soft-rank sweep with the exponent split folded into the quadratic -------------------------------
+// e = exp(-dd/temp) = 2^(X/16), X = -x.  The coefficient table holds (qa, qb, M - qc) with M = 1.5 * 2^20, so that the second
+// fma of the quadratic already delivers t = M + X rounded to 32 fraction bits: the low word of t IS z = X - floor(X) as a
+// 32-bit fraction, the high word carries floor(X) = 16 kk + j in its low bits (what exp_tab_scaled wants) and [x <= 0] in
+// bit 19 (the hard count).  Two integer instructions turn z into the double w = 1 + z 2^-32 in [1, 2), and
+// 2^(z/16) = c3 (((w + b2) w + b1) w + b0) (monic minimax cubic on [1, 2], rel. err 1.2e-9 like score_rows8, c3 folded into
+// the table) -- the three DADDs that split x into round(x) and x - round(x) are gone: 8 fp64-pipe instructions per element
+// instead of 11 (10 instead of 13 with a ratio estimator).  Measured (tools/score_loop_bench.cu VAR 50 against VAR 0): 112.9
+// instead of 121.0 clocks per (32 train points x 4 grid points).  The same cubic on the integer pipes (three IMAD.HI in 2^-36
+// fixed point, 5 fp64 instructions per element) was measured too and is SLOWER (132 clocks: the loop is bound by issue slots
+// and register-file reads, not by the fp64 pipe; profiles/r02_score_loop_fx.log).
+// Rounding X to 2^-32 moves a score difference by < 2e-13 * temp: far inside the tolerance of a rank tie; an exact tie
+// x == 0 counts as "score_c < score_i" here and as ">=" in score_rows (measure zero for real data).
+// Valid while |x| < 946 (the caller's `big` flag; the CLAMP variant clamps t first, two integer instructions).
+constexpr double kFxMagic = 1572864.0;                                   // 1.5 * 2^20
+constexpr double kFxC3 = 1.384801912537204e-05;
+constexpr double kFxB2 = 64.74963271891839, kFxB1 = 2995.871356125411, kFxB0 = 69150.87307076537;
+__device__ __forceinline__ void exp_tabfx_init(double* tab, int j) {
+    double v = kFxC3 * exp2(double(j) / 16.0);
+    tab[j] = __hiloint2double(__double2hiint(v) - (j << 16), __double2loint(v));
+}
+
+template <bool CLAMP, bool UNIT, int GPW>
+__device__ __forceinline__ void score_rows_fx(const ScoreArgs& p, const double* __restrict__ sq, const double* __restrict__ sdr,
+                                              unsigned tab_s, int lane, int N32,
+                                              const double (&bg)[GPW], double (&sr)[GPW], double (&sw)[GPW],
+                                              unsigned (&cneg)[GPW]) {
+    const double kB2 = p.fx_b2, kB1 = p.fx_b1, kB0 = p.fx_b0;  // kernel parameters: constant-bank operands
+    const double* tq = sq + 3 * lane;
+    const double* td = sdr + lane;
+    double qa = tq[0], qb = tq[1], qc = tq[2], dr = UNIT ? 1.0 : td[0];
+    const int nsteps = N32 >> 5;
+    for (int it = 0; it < nsteps; ++it) {
+        tq += 96; td += 32;                                   // next row (reads past N32 stay inside shared memory)
+        const double qa_n = tq[0], qb_n = tq[1], qc_n = tq[2], dr_n = UNIT ? 1.0 : td[0];
+        double t[GPW], e[GPW];
+#pragma unroll
+        for (int k = 0; k < GPW; ++k) t[k] = fma(qa, bg[k], qb);
+#pragma unroll
+        for (int k = 0; k < GPW; ++k) {
+            t[k] = fma(-t[k], bg[k], qc);                     // M - x
+            if (CLAMP) {   // clamp(t, M - 946, M + 947) on the high word: positive doubles order like their bit patterns, and a
+                           // negative t (x > M) has a negative high word; the low word adds < 1 to |x|
+                constexpr int kLo = 0x4137fc4e, kHi = 0x413803b2;   // high words of M - 946, M + 946
+                const int h = min(max(__double2hiint(t[k]), kLo), kHi);
+                t[k] = __hiloint2double(h, __double2loint(t[k]));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < GPW; ++k) {
+            const unsigned z = unsigned(__double2loint(t[k]));
+            const int hi = __double2hiint(t[k]);
+            cneg[k] += unsigned(hi) >> 19;                    // 0x826 + [x <= 0]; the constant is removed after the loop
+            const double w = __hiloint2double(int(0x3ff00000u + (z >> 12)), int(z << 20));   // 1 + z 2^-32
+            double pl = w + kB2;
+            pl = fma(pl, w, kB1);
+            pl = fma(pl, w, kB0);                             // 2^(z/16) / c3
+            const double ts = exp_tab_scaled(tab_s, hi);      // c3 2^(j/16) 2^kk
+            e[k] = fma(ts, pl, 1.0);                          // 1 + e
+        }
+#pragma unroll
+        for (int k = 0; k < GPW; ++k) {
+            double d = e[k];
+            double y0;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+            double err1 = fma(-d, y0, 2.0);                   // Newton: rho = y0 (2 - d y0), folded into the running sum
+            if (UNIT) {
+                sr[k] = fma(y0, err1, sr[k]);
+            } else {
+                double rho = y0 * err1;
+                sr[k] += rho;
+                sw[k] = fma(rho, dr, sw[k]);
+            }
+        }
+        qa = qa_n; qb = qb_n; qc = qc_n; dr = dr_n;
+    }
+#pragma unroll
+    for (int k = 0; k < GPW; ++k) cneg[k] -= unsigned(nsteps) * 0x826u;   // high word of t >> 19 = 0x826 + [x <= 0]
 }
 
 template <bool SOFT>

@@ -17,7 +17,9 @@
 
 namespace cbo {
 
-constexpr int SWS_GROUPS = 4;                                  // candidates in flight per CTA
+constexpr int SWS_GROUPS = 4;                                  // candidates in flight per CTA (maximum; the launch may use fewer:
+                                                               // blockDim.x = groups * 160, a smaller footprint that leaves room
+                                                               // for a co-resident GEMM CTA, see the overlapped chunk pipeline)
 constexpr int SWS_CW = 4;                                      // compute warps per candidate
 constexpr int SWS_COMPUTE_WARPS = SWS_GROUPS * SWS_CW;
 constexpr int SWS_THREADS = (SWS_COMPUTE_WARPS + SWS_GROUPS) * 32;
@@ -29,10 +31,12 @@ __host__ __device__ inline size_t score_ws_gp(int G) { return (size_t(G) + 3) & 
 __host__ __device__ inline size_t score_ws_group_doubles(int Np, int G) {
     return 6 * size_t(Np) + 10 * score_ws_gp(G) + 64 + 2 * SWS_NSCAL + 2 + 4;
 }
-__host__ __device__ inline size_t score_ws_smem_bytes(int Np, int G) {
-    return sizeof(double) * (size_t(Np) + SWS_GROUPS * score_ws_group_doubles(Np, G));
+__host__ __device__ inline size_t score_ws_smem_bytes(int Np, int G, int groups = SWS_GROUPS) {
+    return sizeof(double) * (size_t(Np) + groups * score_ws_group_doubles(Np, G));
 }
-inline bool score_ws_fits(int Np, int G) { return score_ws_smem_bytes(Np, G) + 256 <= 227 * 1024 && 10 * score_ws_gp(G) + 72 >= 96; }
+inline bool score_ws_fits(int Np, int G, int groups = SWS_GROUPS) {
+    return score_ws_smem_bytes(Np, G, groups) + 256 <= 227 * 1024 && 10 * score_ws_gp(G) + 72 >= 96;
+}
 
 #ifdef CBO_WS_PROFILE
 __device__ unsigned long long g_ws_prof[8];   // [0] compute: clk waiting on full, [1] compute: clk total, [2] helper: clk waiting on done, [3] helper total, [4] helper phase A, [5] helper C/D
@@ -48,10 +52,11 @@ __global__ void __launch_bounds__(SWS_THREADS, 1)
 k_score_ws(const ScoreArgs p) {
     extern __shared__ __align__(16) double sm[];
     __shared__ __align__(128) double tab[16];           // exp_neg_pat / sigmoid_pat of the helper warps (phases C / D)
-    __shared__ __align__(128) double tab8[16];          // score_rows8 of the compute warps
+    __shared__ __align__(128) double tabfx[16];         // score_rows_fx of the compute warps
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool helper = warp >= SWS_COMPUTE_WARPS;
-    const int grp = helper ? warp - SWS_COMPUTE_WARPS : warp >> 2;
+    const int n_groups = int(blockDim.x) / ((SWS_CW + 1) * 32);   // compute warps first, then one helper warp per group
+    const bool helper = warp >= n_groups * SWS_CW;
+    const int grp = helper ? warp - n_groups * SWS_CW : warp >> 2;
     const int cw = warp & 3;
     const int N = p.N, Np = p.Np, G = p.G, Sp = p.Sp;
     const int Gp = int(score_ws_gp(G));
@@ -68,8 +73,8 @@ k_score_ws(const ScoreArgs p) {
     uint64_t* full = reinterpret_cast<uint64_t*>(scal0 + 2 * SWS_NSCAL + 2);
     uint64_t* done = full + 2;
 
-    if (tid < 16) { exp_tab_init(tab, tid); exp_tab8_init(tab8, tid, p.k8_c3); }
-    const unsigned tab_s = smem_u32(tab), tab8_s = smem_u32(tab8);
+    if (tid < 16) { exp_tab_init(tab, tid); exp_tabfx_init(tabfx, tid); }
+    const unsigned tab_s = smem_u32(tab), tabfx_s = smem_u32(tabfx);
     for (int i = tid; i < Np; i += blockDim.x) sdr[i] = (i < N) ? p.dr[i] : 0.0;
     if (helper && lane == 0) {
         mbar_init(&full[0], 1); mbar_init(&full[1], 1);
@@ -77,8 +82,8 @@ k_score_ws(const ScoreArgs p) {
     }
     __syncthreads();                                    // the only block-wide barrier
 
-    const int total_groups = gridDim.x * SWS_GROUPS;
-    const int first = blockIdx.x * SWS_GROUPS + grp;
+    const int total_groups = gridDim.x * n_groups;
+    const int first = blockIdx.x * n_groups + grp;
     const int n_mine = first < p.n_cand ? (p.n_cand - first + total_groups - 1) / total_groups : 0;
 
     if (!helper) {
@@ -105,12 +110,17 @@ k_score_ws(const ScoreArgs p) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { sr[j] = 0.0; sw[j] = 0.0; cneg[j] = 0u; }
                 if (!bad) {
-                    if (p.unit_dr) {
-                        if (big) score_rows8<SOFT, true, true, 4>(p, sq, sdr, tab8_s, lane, N32, bg, sr, sw, cneg);
-                        else score_rows8<SOFT, false, true, 4>(p, sq, sdr, tab8_s, lane, N32, bg, sr, sw, cneg);
-                    } else {
-                        if (big) score_rows8<SOFT, true, false, 4>(p, sq, sdr, tab8_s, lane, N32, bg, sr, sw, cneg);
-                        else score_rows8<SOFT, false, false, 4>(p, sq, sdr, tab8_s, lane, N32, bg, sr, sw, cneg);
+                    if (SOFT) {          // tables hold (qa, qb, M - qc): score_rows_fx
+                        if (p.unit_dr) {
+                            if (big) score_rows_fx<true, true, 4>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                            else score_rows_fx<false, true, 4>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                        } else {
+                            if (big) score_rows_fx<true, false, 4>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                            else score_rows_fx<false, false, 4>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                        }
+                    } else {             // hard path: the sign of x only
+                        if (p.unit_dr) score_rows8<false, false, true, 4>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                        else score_rows8<false, false, false, 4>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
                     }
                 }
                 int ci[4];
@@ -219,7 +229,7 @@ k_score_ws(const ScoreArgs p) {
                             qc = c1 * (fma(iv * ai[j], ai[j], lv_c - lv));
                             big |= !(fma(fma(fabs(qa), bmax, fabs(qb)), bmax, fabs(qc)) < 900.0);
                         }
-                        sq[3 * i] = qa; sq[3 * i + 1] = qb; sq[3 * i + 2] = qc;
+                        sq[3 * i] = qa; sq[3 * i + 1] = qb; sq[3 * i + 2] = SOFT ? kFxMagic - qc : qc;   // score_rows_fx wants M - qc
                     }
                 }
             }

@@ -24,6 +24,22 @@ __device__ __forceinline__ void rows(const ScoreArgs& p, const double* __restric
         score_rows8<true, false, true, 4>(p, sq, sq, tab8_s, lane, N32, bg, sr, sw, cneg);
         return;
     }
+    if (V == 50) {            // score_rows_fx: exponent split folded into the quadratic, 8 fp64 instructions per element
+        double sw[4] = {0, 0, 0, 0};
+        score_rows_fx<false, true, 4>(p, sq, sq, tab_s, lane, N32, bg, sr, sw, cneg);
+        return;
+    }
+    if (V == 52) {            // ... with a ratio estimator (10 fp64 instructions per element)
+        double sw[4] = {0, 0, 0, 0};
+        score_rows_fx<false, false, 4>(p, sq, sq, tab_s, lane, N32, bg, sr, sw, cneg);
+        sr[0] += sw[0]; sr[1] += sw[1]; sr[2] += sw[2]; sr[3] += sw[3];
+        return;
+    }
+    if (V == 53) {            // ... clamped
+        double sw[4] = {0, 0, 0, 0};
+        score_rows_fx<true, true, 4>(p, sq, sq, tab_s, lane, N32, bg, sr, sw, cneg);
+        return;
+    }
     const double kMagic = p.k_magic, kA2 = p.k8_a2, kA1 = p.k8_a1, kA0 = p.k8_a0;
     const double* tq = sq + 3 * lane;
     double qa = tq[0], qb = tq[1], qc = tq[2];
@@ -89,8 +105,16 @@ __global__ void __launch_bounds__(512, 1) k(const ScoreArgs p, const double* coe
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 16) { exp_tab8_init(tab8, tid, p.k8_c3); exp_tab_init(tab, tid); }
     if (tid >= 16 && tid < 128) tab[tid] = tab[tid & 15] ;
+    if (VAR >= 50) {
+        __syncthreads();
+        if (tid < 16) exp_tabfx_init(tab, tid);
+    }
     double* sq = sm + size_t(warp >> 1) * (3 * 1024 + 96);
-    for (int i = tid & 63; i < 3 * 1024 + 96; i += 64) sq[i] = coef[i % (3 * 1024)];
+    for (int i = tid & 63; i < 3 * 1024 + 96; i += 64) {
+        double v = coef[i % (3 * 1024)];
+        if ((VAR >= 50) && (i % 3) == 2) v = 1572864.0 - v;      // M - qc, M = 1.5 * 2^20
+        sq[i] = v;
+    }
     __syncthreads();
     double tot = 0.0;
     unsigned ctot = 0;
@@ -112,6 +136,7 @@ int main() {
     ScoreArgs a; memset(&a, 0, sizeof(a));
     const double c0 = 0.9999999988534117, c1n = -0.043321698775061875, c2 = 0.0009384214835622084, c3n = -1.3551125681305332e-05;
     a.k_magic = 6755399441055744.0; a.k_c0 = c0; a.k_c1n = c1n; a.k_c2 = c2; a.k_c3n = c3n;
+    a.fx_b2 = kFxB2; a.fx_b1 = kFxB1; a.fx_b0 = kFxB0;
     a.k8_c3 = c3n; a.k8_a2 = c2 / c3n; a.k8_a1 = c1n / c3n; a.k8_a0 = c0 / c3n;
     static double h[3 * 1024];
     for (int i = 0; i < 1024; ++i) { h[3 * i] = -40.0 - 0.01 * i; h[3 * i + 1] = 3.0 + 0.001 * i; h[3 * i + 2] = 20.0 * ((i % 17) - 8); }
