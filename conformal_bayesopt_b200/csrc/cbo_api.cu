@@ -100,7 +100,6 @@ struct Workspace {
     double *val_bar, *cv_bar;                         // cNEI gradient only: C x S x G value adjoints, C x nb adjoints of c
     double* splitk;                                   // split-K partial tiles (calls with <= 32 candidate points)
     double *X3, *adj;                                 // gradient only: C x Np solve scratch, C x ADJ_STRIDE adjoints
-    double *UW2, *V2, *mu2, *ut2, *drc2, *rn2;        // overlapped chunk pipeline only: the second set of per-chunk buffers
     size_t bytes;
 };
 
@@ -108,32 +107,6 @@ int64_t pick_chunk(int64_t b, const cbo_params* p, int64_t chunk) {
     if (p->max_grid_refinements > 0) return b;     // batch-global statistics need every candidate resident
     if (chunk <= 0) chunk = kDefaultChunk;
     return chunk < b ? chunk : b;
-}
-
-// ---- overlapped chunk pipeline (q = 1 value calls with several chunks) -------------------------------------------------------
-// k_score_ws is bound by register-file reads and issue slots (fp64 pipe 67 % busy), the DMMA GEMM by the pipe itself with very
-// little register traffic: co-resident on an SM they fill each other's gaps.  The rows + GEMM passes of chunk k+1 run on the
-// caller's stream while the score kernel of chunk k runs on a library-private HIGH-priority stream (its persistent CTAs are
-// placed first; GEMM CTAs fill the rest of each SM), with footprints chosen so that both fit: a k_score_ws CTA of
-// `ws_groups` candidate groups and a GEMM CTA with a `gemm_stages`-deep ring.  CBO_OVERLAP=0 disables it;
-// CBO_WS_GROUPS / CBO_GEMM_STAGES override the footprints (A/B timing).
-struct OverlapCfg { bool on; int ws_groups, gemm_stages; };
-int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return (e && *e) ? atoi(e) : dflt;
-}
-OverlapCfg overlap_cfg(int64_t N, int64_t b, const cbo_params* p, int64_t chunk, bool grad) {
-    OverlapCfg c{false, cbo::SWS_GROUPS, cbo::GEMM_STAGES};
-    const int64_t C = pick_chunk(b, p, chunk);
-    if (grad || p->q != 1 || p->max_grid_refinements > 0 || !(p->temp > 0.0) || b < 2 * C) return c;
-    if (p->kind != CBO_ACQ_UCB && p->kind != CBO_ACQ_EI) return c;
-    if (env_int("CBO_OVERLAP", 0) == 0) return c;
-    c.ws_groups = env_int("CBO_WS_GROUPS", 2);
-    c.gemm_stages = env_int("CBO_GEMM_STAGES", 2);
-    if (c.ws_groups < 1 || c.ws_groups > cbo::SWS_GROUPS || (c.gemm_stages != 2 && c.gemm_stages != 3 && c.gemm_stages != 4)) return c;
-    if (!cbo::score_ws_fits((int)cbo_padded_n(N), (int)p->grid_res, c.ws_groups)) return c;
-    c.on = true;
-    return c;
 }
 
 Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, int64_t chunk, bool grad = false) {
@@ -169,13 +142,6 @@ Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, 
     w.cv_bar = c.take<double>(grad && nei_kind ? C * cbo::NEI_MAX_NB : 1);
     w.X3 = c.take<double>(grad ? C * Np : 1);
     w.adj = c.take<double>(grad ? C * (cbo::ADJQ_STRIDE > cbo::ADJ_STRIDE ? cbo::ADJQ_STRIDE : cbo::ADJ_STRIDE) : 1);
-    const bool ovl = overlap_cfg(N, b, p, chunk, grad).on;
-    w.UW2 = c.take<double>(ovl ? C * Np : 1);
-    w.V2 = c.take<double>(ovl ? C * Np : 1);
-    w.mu2 = c.take<double>(ovl ? C : 1);
-    w.ut2 = c.take<double>(ovl ? C * Sp : 1);
-    w.drc2 = c.take<double>(ovl ? C : 1);
-    w.rn2 = c.take<double>(ovl ? C * tiles_n : 1);
     w.bytes = c.off;
     return w;
 }
@@ -255,17 +221,17 @@ int score_ws_override() {
 }
 
 template <bool SOFT>
-cudaError_t launch_score(const cbo::ScoreArgs& a_in, cudaStream_t st, bool many, int ws_groups = cbo::SWS_GROUPS) {
+cudaError_t launch_score(const cbo::ScoreArgs& a_in, cudaStream_t st, bool many) {
     cbo::ScoreArgs a = a_in;
     // a call with many candidates: warp-specialised kernel (4 candidates in flight per SM, helper warps for phases A/C/D)
     const int ov = score_ws_override();
-    if ((ov == 1 || (ov < 0 && many && SOFT)) && cbo::score_ws_fits(a.Np, a.G, ws_groups)) {   // hard path: the sweep is too short for one helper warp per candidate to keep up
-        const size_t smem = cbo::score_ws_smem_bytes(a.Np, a.G, ws_groups);
+    if ((ov == 1 || (ov < 0 && many && SOFT)) && cbo::score_ws_fits(a.Np, a.G)) {   // hard path: the sweep is too short for one helper warp per candidate to keep up
+        const size_t smem = cbo::score_ws_smem_bytes(a.Np, a.G);
         static cbo::SmemOptIn optin_ws;
-        if (cudaError_t e = optin_ws.ensure(cbo::k_score_ws<SOFT>, cbo::score_ws_smem_bytes(a.Np, a.G)); e != cudaSuccess) return e;
-        int grid = (a.n_cand + ws_groups - 1) / ws_groups;
+        if (cudaError_t e = optin_ws.ensure(cbo::k_score_ws<SOFT>, smem); e != cudaSuccess) return e;
+        int grid = (a.n_cand + cbo::SWS_GROUPS - 1) / cbo::SWS_GROUPS;
         if (grid > num_sms()) grid = num_sms();
-        CBO_LAUNCHED(), cbo::k_score_ws<SOFT><<<grid, ws_groups * (cbo::SWS_CW + 1) * 32, smem, st>>>(a);
+        CBO_LAUNCHED(), cbo::k_score_ws<SOFT><<<grid, cbo::SWS_THREADS, smem, st>>>(a);
         return cudaGetLastError();
     }
     // warps per candidate: pairs when there are enough candidates to fill the SMs, wider groups for small batches
@@ -578,46 +544,12 @@ int cbo_conf_mask_to_bounds_f64(const double* grid, const double* mask, int64_t 
     return CBO_OK;
 }
 
-// Library-private streams / events of the overlapped chunk pipeline: one set per device, created on first use.
-struct OverlapStreams {
-    cudaStream_t hi = nullptr;
-    cudaEvent_t ev_prep = nullptr, ev_front[2] = {nullptr, nullptr}, ev_score[2] = {nullptr, nullptr};
-    std::mutex mu;
-    std::mutex call_mu;        // one overlapped call per device at a time shares the stream and the events
-    bool ready = false;
-};
-OverlapStreams g_overlap[cbo::kMaxDevices];
-OverlapStreams* overlap_streams() {
-    const int dev = cbo::current_device_slot();
-    if (dev < 0) return nullptr;
-    OverlapStreams& o = g_overlap[dev];
-    std::lock_guard<std::mutex> l(o.mu);
-    if (!o.ready) {
-        int lo = 0, hi = 0;
-        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
-        if (cudaStreamCreateWithPriority(&o.hi, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
-        cudaEvent_t* evs[5] = {&o.ev_prep, &o.ev_front[0], &o.ev_front[1], &o.ev_score[0], &o.ev_score[1]};
-        for (cudaEvent_t* e : evs)
-            if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        o.ready = true;
-    }
-    return &o;
-}
-
-// forward GEMM pass of a chunk: the stand-alone kernel, or the shallow-ring variant that fits beside a k_score_ws CTA
-cudaError_t launch_gemm_fwd(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int Nn,
-                            int K, int tri, double* rn, cudaStream_t st, double* splitk, const OverlapCfg& ovl) {
-    if (ovl.on && ovl.gemm_stages == 2) return cbo::launch_gemm_tn_shallow<2>(A, lda, B, ldb, C, ldc, M, Nn, K, tri, rn, st);
-    if (ovl.on && ovl.gemm_stages == 3) return cbo::launch_gemm_tn_shallow<3>(A, lda, B, ldb, C, ldc, M, Nn, K, tri, rn, st);
-    return cbo::launch_gemm_tn(A, lda, B, ldb, C, ldc, M, Nn, K, tri, rn, st, num_sms(), splitk);
-}
-
 // Per-chunk callbacks of the host-buffer entry point: `before` is called ahead of the first kernel that reads the chunk's
 // candidates, `after` behind the last kernel that writes its acquisition values (both only enqueue stream operations).
 struct ChunkHooks {
     void* ctx;
-    int (*before)(void* ctx, int64_t c0, int64_t ncand, cudaStream_t consumer);   // stream of the kernels that read the candidates
-    int (*after)(void* ctx, int64_t c0, int64_t ncand, cudaStream_t producer);    // stream of the kernel that wrote the values
+    int (*before)(void* ctx, int64_t c0, int64_t ncand);
+    int (*after)(void* ctx, int64_t c0, int64_t ncand);
 };
 
 static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* ratio, const cbo_params* p, const double* Xq,
@@ -675,33 +607,13 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
 
     const int R = (int)p->max_grid_refinements;
     const int q = (int)p->q;
-    const Workspace wsave = w;
     const bool many = b >= int64_t(2) * cbo::SWS_GROUPS * num_sms();   // decided per CALL (chunking stays bit-invariant): every group gets >= 2 candidates
     double* splitk = (b * q <= cbo::GEMM_SPLITK_MAX_M) ? w.splitk : nullptr;   // a handful of candidate points in the whole call: split-K GEMMs
-    // overlapped chunk pipeline: score(k) on the library's high-priority stream beside rows + GEMMs(k+1) on the caller's
-    OverlapCfg ovl = overlap_cfg(gp->N, b, p, chunk, grad);
-    ovl.on = ovl.on && many && score_ws_override() != 0;
-    OverlapStreams* os = nullptr;
-    cudaStream_t s_score = s;
-    std::unique_lock<std::mutex> ovl_lock;
-    if (ovl.on) {
-        os = overlap_streams();
-        if (!os) return CBO_ERR_CUDA;
-        ovl_lock = std::unique_lock<std::mutex>(os->call_mu);
-        s_score = os->hi;
-        CBO_CUDA(cudaEventRecord(os->ev_prep, s));                        // per-call tables are ready
-        CBO_CUDA(cudaStreamWaitEvent(os->hi, os->ev_prep, 0));
-    }
-    int64_t chunk_idx = 0;
-    for (int64_t c0 = 0; c0 < b; c0 += C, ++chunk_idx) {
+    for (int64_t c0 = 0; c0 < b; c0 += C) {
         const int ncand = (int)((b - c0 < C) ? (b - c0) : C);
         const int n = ncand * q;                                  // kernel rows of this chunk: one per candidate POINT
         const double* Xc = Xq + c0 * q * d;
-        const int set = ovl.on ? int(chunk_idx & 1) : 0;
-        if (set == 1) { w.UW = wsave.UW2; w.V = wsave.V2; w.mu = wsave.mu2; w.ut = wsave.ut2; w.drc = wsave.drc2; w.rn = wsave.rn2; }
-        else { w.UW = wsave.UW; w.V = wsave.V; w.mu = wsave.mu; w.ut = wsave.ut; w.drc = wsave.drc; w.rn = wsave.rn; }
-        if (ovl.on && chunk_idx >= 2) CBO_CUDA(cudaStreamWaitEvent(s, os->ev_score[set], 0));   // the buffers of chunk k-2 are free
-        if (hooks) { int hs_ = hooks->before(hooks->ctx, c0, ncand, s); if (hs_ != CBO_OK) return hs_; }
+        if (hooks) { int hs_ = hooks->before(hooks->ctx, c0, ncand); if (hs_ != CBO_OK) return hs_; }
         // ---- kernel rows, mu, u^T T; candidate density ratios -------------------------------------
         {
             TimeScope ts_(T_ROWS, s, ratio ? 2 : 1);
@@ -715,15 +627,11 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
         // ---- v = L^-1 u (+ ||v||^2 partials), w = L^-T v ------------------------------------------
         {
             TimeScope ts_(T_GEMM1, s, 1);
-            CBO_CUDA(launch_gemm_fwd(w.UW, Np, gp->linv, Np, w.V, Np, n, Np, Np, cbo::TRI_LOWER, w.rn, s, splitk, ovl));
+            CBO_CUDA(cbo::launch_gemm_tn(w.UW, Np, gp->linv, Np, w.V, Np, n, Np, Np, cbo::TRI_LOWER, w.rn, s, num_sms(), splitk));
         }
         {
             TimeScope ts_(T_GEMM2, s, 1);
-            CBO_CUDA(launch_gemm_fwd(w.V, Np, gp->linv_t, Np, w.UW, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s, splitk, ovl));
-        }
-        if (ovl.on) {
-            CBO_CUDA(cudaEventRecord(os->ev_front[set], s));
-            CBO_CUDA(cudaStreamWaitEvent(os->hi, os->ev_front[set], 0));
+            CBO_CUDA(cbo::launch_gemm_tn(w.V, Np, gp->linv_t, Np, w.UW, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms(), splitk));
         }
 
         // ---- scores / rank / mask / integration ----------------------------------------------------
@@ -734,9 +642,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
         a.beta_prime = p->beta_prime; a.best_f = p->best_f;
         a.k_magic = 6755399441055744.0; a.k_c0 = 0.9999999988534117; a.k_c1n = -0.043321698775061875;
         a.k_c2 = 0.0009384214835622084; a.k_c3n = -1.3551125681305332e-05;
-        // monic form of the same cubic (score_rows8): P(y) = c3 (((y + a2) y + a1) y + a0)
-        a.k8_c3 = a.k_c3n; a.k8_a2 = a.k_c2 / a.k_c3n; a.k8_a1 = a.k_c1n / a.k_c3n; a.k8_a0 = a.k_c0 / a.k_c3n;
-        a.fx_b2 = cbo::kFxB2; a.fx_b1 = cbo::kFxB1; a.fx_b0 = cbo::kFxB0;                   // score_rows_fx (k_score_ws)
+        a.fx_b2 = cbo::kFxB2; a.fx_b1 = cbo::kFxB1; a.fx_b0 = cbo::kFxB0;   // score_rows_fx (soft path of k_score, k_score_ws, k_score_bwd)
         a.unit_dr = ratio ? 0 : 1;
         a.kind = p->kind; a.optimistic = p->optimistic; a.randomized = p->randomized;
         a.eps_per_candidate = p->eps_per_candidate;
@@ -772,8 +678,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             cbo::ScoreArgs x = x_in;
             if (nei_kind)
                 if (cudaError_t e = run_nei(x); e != cudaSuccess) return e;
-            if (q == 1) return soft_path ? launch_score<true>(x, s_score, many, ovl.on ? ovl.ws_groups : cbo::SWS_GROUPS)
-                                         : launch_score<false>(x, s_score, many);
+            if (q == 1) return soft_path ? launch_score<true>(x, s, many) : launch_score<false>(x, s, many);
             cbo::ScoreQArgs y = aq;
             y.base = x;
             return launch_score_q(y, q, soft_path, s);
@@ -797,7 +702,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                                out->q_conf_scores || out->post_mean || out->post_var || out->num_accepted ||
                                out->refit_mean || out->refit_sd;
             if (!grad || extra) {
-                TimeScope ts_(T_SCORE, s_score, 1);
+                TimeScope ts_(T_SCORE, s, 1);
                 CBO_CUDA(run_score(fa));
             }
             if (!grad) return CBO_OK;
@@ -904,12 +809,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             int rs = run_final(fa);
             if (rs != CBO_OK) return rs;
         }
-        if (ovl.on) CBO_CUDA(cudaEventRecord(os->ev_score[set], os->hi));
-        if (hooks) { int hs_ = hooks->after(hooks->ctx, c0, ncand, s_score); if (hs_ != CBO_OK) return hs_; }
-    }
-    if (ovl.on) {                                                        // join: the caller's stream continues behind the last scores
-        CBO_CUDA(cudaStreamWaitEvent(s, os->ev_score[0], 0));
-        CBO_CUDA(cudaStreamWaitEvent(s, os->ev_score[1], 0));
+        if (hooks) { int hs_ = hooks->after(hooks->ctx, c0, ncand); if (hs_ != CBO_OK) return hs_; }
     }
     return CBO_OK;
 }
@@ -1082,17 +982,17 @@ struct HostPipeCtx {
         return cudaEventRecord(h2d_done(k), pipe->copy);
     }
 };
-int host_before(void* v, int64_t c0, int64_t, cudaStream_t consumer) {
+int host_before(void* v, int64_t c0, int64_t) {
     HostPipeCtx* c = static_cast<HostPipeCtx*>(v);
     const int64_t k = c0 / c->C;
     if ((k + 1) * c->C < c->b) { if ((c->err = c->upload(k + 1)) != cudaSuccess) return CBO_ERR_CUDA; }   // prefetch the next chunk
-    if ((c->err = cudaStreamWaitEvent(consumer, c->h2d_done(k), 0)) != cudaSuccess) return CBO_ERR_CUDA;
+    if ((c->err = cudaStreamWaitEvent(c->compute, c->h2d_done(k), 0)) != cudaSuccess) return CBO_ERR_CUDA;
     return CBO_OK;
 }
-int host_after(void* v, int64_t c0, int64_t ncand, cudaStream_t producer) {
+int host_after(void* v, int64_t c0, int64_t ncand) {
     HostPipeCtx* c = static_cast<HostPipeCtx*>(v);
     const int64_t k = c0 / c->C;
-    if ((c->err = cudaEventRecord(c->chunk_done(k), producer)) != cudaSuccess) return CBO_ERR_CUDA;
+    if ((c->err = cudaEventRecord(c->chunk_done(k), c->compute)) != cudaSuccess) return CBO_ERR_CUDA;
     if ((c->err = cudaStreamWaitEvent(c->pipe->copy, c->chunk_done(k), 0)) != cudaSuccess) return CBO_ERR_CUDA;
     if ((c->err = cudaMemcpyAsync(c->acq_host + c0, c->acq_dev + c0, sizeof(double) * ncand, cudaMemcpyDeviceToHost,
                                   c->pipe->copy)) != cudaSuccess) return CBO_ERR_CUDA;

@@ -31,9 +31,6 @@ constexpr int GEMM_THREADS = 256;
 constexpr int GEMM_MGROUP = 64;          // m-tiles per L2 group (see the tile order in the kernel)
 constexpr int GEMM_STAGE_DOUBLES = (GEMM_BM + GEMM_BN) * GEMM_LDS;
 constexpr size_t GEMM_SMEM_BYTES = size_t(GEMM_STAGES) * GEMM_STAGE_DOUBLES * sizeof(double) + 2 * GEMM_STAGES * sizeof(uint64_t);
-__host__ __device__ constexpr size_t gemm_smem_bytes(int stages) {
-    return size_t(stages) * GEMM_STAGE_DOUBLES * sizeof(double) + 2 * size_t(stages) * sizeof(uint64_t);
-}
 
 enum { TRI_FULL = 0, TRI_LOWER = 1, TRI_UPPER = 2 };
 
@@ -63,9 +60,7 @@ __device__ __forceinline__ void gemm_load_stage(double* sA, double* sB, const do
 
 // MF = 8-row DMMA fragments per warp in m: CTA tile (16 MF) x 128.  MF = 8 is the throughput configuration; smaller MF
 // keep all SMs busy (and cut the wasted rows) when there are only a few hundred candidate rows.
-// STAGES: depth of the cp.async ring (4: the stand-alone configuration, 160 KB; 2: 80 KB, the footprint that fits beside a
-// two-group k_score_ws CTA on the same SM -- the co-resident score warps then cover the shallower ring's load latency).
-template <int MF, int STAGES = GEMM_STAGES>
+template <int MF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
               double* __restrict__ C, int64_t ldc, int M, int Nn, int K, int tri,
@@ -77,7 +72,7 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     // triangular skipping on the diagonal block (below) loads every sub-partition's fp64 pipe equally.
     const int wm = warp >> 2, wn = (warp < 4) ? warp : 7 - warp;
     constexpr int BM = 16 * MF;
-    constexpr int PF = (STAGES > GEMM_PREFETCH) ? GEMM_PREFETCH : STAGES - 1;
+    constexpr int PF = GEMM_PREFETCH;
     const int tiles_m = (M + BM - 1) / BM;
     const int tiles_n = Nn / GEMM_BN;
     // longest-K tiles first: lower -> last n-tile first; upper / full -> first n-tile first
@@ -117,11 +112,11 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     // copies of the tile in stage s have landed (cp.async.mbarrier.arrive); empty[s] completes when all 8 warps have
     // consumed it.  Tiles are prefetched PREFETCH ahead into a ring of STAGES, so warps may drift apart by
     // STAGES - PREFETCH tiles (absorbs the triangular imbalance on the diagonal block and scheduling jitter).
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * GEMM_STAGE_DOUBLES);
-    uint64_t* empty = full + STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(GEMM_STAGES) * GEMM_STAGE_DOUBLES);
+    uint64_t* empty = full + GEMM_STAGES;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], GEMM_THREADS); mbar_init(&empty[s], GEMM_THREADS / 32); }
+        for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full[s], GEMM_THREADS); mbar_init(&empty[s], GEMM_THREADS / 32); }
     }
     __syncthreads();
 #pragma unroll
@@ -138,20 +133,20 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
         {   // producer side: tile kt + PREFETCH goes into the stage last used by tile kt + PREFETCH - STAGES
             const int nt = kt + PF;
             if (nt < nk) {
-                const int st = nt % STAGES;
-                mbar_wait(&empty[st], ((nt / STAGES) & 1) ^ 1);
+                const int st = nt % GEMM_STAGES;
+                mbar_wait(&empty[st], ((nt / GEMM_STAGES) & 1) ^ 1);
                 double* sA = smem + st * GEMM_STAGE_DOUBLES;
                 gemm_load_stage<BM>(sA, sA + BM * GEMM_LDS, A, lda, B, ldb, m0, n0, kpos(nt), M, tid);
                 cp_async_mbar_arrive(&full[st]);
             }
         }
-        const int st = kt % STAGES;
+        const int st = kt % GEMM_STAGES;
         // On the diagonal 128 x 128 block of the triangular factor this warp's 32 columns see only zeros for part of
         // the K range: lower  -> k < n_warp_end,  upper -> k + BK > n_warp_begin.  Skip those MMAs (warp-uniform).
         const int k0 = kpos(kt);
         const bool skip = (tri == TRI_LOWER && k0 >= n0 + 32 * (wn + 1)) || (tri == TRI_UPPER && k0 + GEMM_BK <= n0 + 32 * wn);
         if (!skip) {
-            mbar_wait(&full[st], (kt / STAGES) & 1);
+            mbar_wait(&full[st], (kt / GEMM_STAGES) & 1);
             const double* sA = smem + st * GEMM_STAGE_DOUBLES + (wm * (8 * MF) + fr) * GEMM_LDS + fk;
             const double* sB = smem + st * GEMM_STAGE_DOUBLES + BM * GEMM_LDS + (wn * 32 + fr) * GEMM_LDS + fk;
 #pragma unroll
@@ -209,19 +204,6 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
             }
         }
     }
-}
-
-// the throughput tile with a shallow ring (co-resident configuration)
-template <int STAGES>
-inline cudaError_t launch_gemm_tn_shallow(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
-                                          int M, int Nn, int K, int tri, double* rownorm_partial, cudaStream_t stream) {
-    static SmemOptIn optin;
-    constexpr size_t smem = gemm_smem_bytes(STAGES);
-    if (cudaError_t e = optin.ensure(k_gemm_tn_f64<8, STAGES>, smem); e != cudaSuccess) return e;
-    int tiles_m = (M + 127) / 128, tiles_n = Nn / GEMM_BN;
-    CBO_LAUNCHED(), k_gemm_tn_f64<8, STAGES><<<dim3(tiles_m * tiles_n, 1), GEMM_THREADS, smem, stream>>>(
-        A, lda, B, ldb, C, ldc, M, Nn, K, tri, rownorm_partial, 1, 0);
-    return cudaGetLastError();
 }
 
 template <int MF>

@@ -47,8 +47,6 @@ struct ScoreArgs {
     int unit_dr;            // no ratio estimator: all train-point importance weights are 1
     // sigmoid constants, passed as parameters so that they are constant-bank operands instead of per-iteration moves
     double k_magic, k_c0, k_c1n, k_c2, k_c3n;
-    // the same cubic in the monic form of score_rows8: P(y) = c3 (((y + a2) y + a1) y + a0)
-    double k8_a2, k8_a1, k8_a0, k8_c3;
     // score_rows_fx: the monic cubic in w = 1 + z 2^-32 (kFxB2, kFxB1, kFxB0)
     double fx_b2, fx_b1, fx_b0;
     // per-call tables (train side)
@@ -224,93 +222,14 @@ __device__ __forceinline__ void score_rows(const ScoreArgs& p, const double* __r
     }
 }
 
-// ---- score_rows8: the same sweep, arranged for the REGISTER-FILE read ports -------------------------------------------
-// Measured on B200 (tools/dfma_operands*.cu, profiles/r02_dfma_operands.log): a DFMA that reads three distinct register
-// pairs issues every 3 clocks (66 % of the fp64 pipe), one that reads two (or one) every 2 clocks -- the pipe's own rate;
-// immediates, constant-bank / uniform-register operands and operand-reuse-cache hits are free, and integer instructions
-// pay for their register operands on the same ports.  score_rows spent 149 clocks per (32 train points x 4 grid points)
-// against 88 of fp64-pipe time.  Here the cubic P(y) = exp(-y ln2/16) is evaluated in MONIC form,
-//     P = c3 (((y + a2) y + a1) y + a0),   a_k = c_k / c3,
-// so that every step has ONE constant operand (Horner starts with fma(y, c3, c2): two constants, i.e. two more register
-// pairs per instruction once the constants sit in registers), and c3 is folded into the table: tab8[j] = c3 2^(j/16), so
-// e = 2^(n/16) P(y) is still one fma on the exponent-scaled entry.  Same 11 fp64 instructions per element, ~20 register
-// pairs read instead of 24.  (tools/score_loop_bench.cu times the loop alone with ablations.)
-__device__ __forceinline__ void exp_tab8_init(double* tab, int j, double c3) {
-    double v = c3 * exp2(double(j) / 16.0);
-    tab[j] = __hiloint2double(__double2hiint(v) - (j << 16), __double2loint(v));
-}
-
-template <bool SOFT, bool CLAMP, bool UNIT, int GPW>
-__device__ __forceinline__ void score_rows8(const ScoreArgs& p, const double* __restrict__ sq, const double* __restrict__ sdr,
-                                            unsigned tab_s, int lane, int N32,
-                                            const double (&bg)[GPW], double (&sr)[GPW], double (&sw)[GPW],
-                                            unsigned (&cneg)[GPW]) {
-    const double kMagic = p.k_magic;                          // 1.5 * 2^52
-    const double kA2 = p.k8_a2, kA1 = p.k8_a1, kA0 = p.k8_a0;
-    constexpr int kSatHi = 0x408d9000;                        // hiword(946.0)
-    const double* tq = sq + 3 * lane;
-    const double* td = sdr + lane;
-    double qa = tq[0], qb = tq[1], qc = tq[2], dr = UNIT ? 1.0 : td[0];
-    for (int i = lane; i < N32; i += 32) {
-        tq += 96; td += 32;                                   // next row (reads past N32 stay inside shared memory)
-        const double qa_n = tq[0], qb_n = tq[1], qc_n = tq[2], dr_n = UNIT ? 1.0 : td[0];
-        double x[GPW];
-#pragma unroll
-        for (int k = 0; k < GPW; ++k) x[k] = fma(qa, bg[k], qb);
-#pragma unroll
-        for (int k = 0; k < GPW; ++k) {
-            x[k] = fma(x[k], bg[k], qc);
-            cneg[k] += unsigned(__double2hiint(x[k])) >> 31;  // counts score_c < score_i
-        }
-        if (SOFT) {
-            double t[GPW], y[GPW], e[GPW];
-#pragma unroll
-            for (int k = 0; k < GPW; ++k) {
-                double xc = x[k];
-                if (CLAMP) {
-                    int hi = __double2hiint(x[k]);
-                    int ch = min(hi & 0x7fffffff, kSatHi) | (hi & 0x80000000);
-                    xc = __hiloint2double(ch, __double2loint(x[k]));         // clamp(x, -946, 946)
-                }
-                t[k] = kMagic - xc;                           // low word = -round(x)
-                y[k] = xc + (t[k] - kMagic);                  // x - round(x) in [-1/2, 1/2]
-            }
-#pragma unroll
-            for (int k = 0; k < GPW; ++k) {
-                double pl = y[k] + kA2;
-                pl = fma(pl, y[k], kA1);
-                pl = fma(pl, y[k], kA0);                      // exp(-y ln2/16) / c3
-                double ts = exp_tab_scaled(tab_s, __double2loint(t[k]));     // c3 2^(j/16) 2^kk (tab_s: the tab8 table)
-                e[k] = fma(ts, pl, 1.0);                      // 1 + e
-            }
-#pragma unroll
-            for (int k = 0; k < GPW; ++k) {
-                double d = e[k];
-                double y0;
-                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
-                double err1 = fma(-d, y0, 2.0);               // Newton: rho = y0 (2 - d y0), folded into the running sum
-                if (UNIT) {
-                    sr[k] = fma(y0, err1, sr[k]);
-                } else {
-                    double rho = y0 * err1;
-                    sr[k] += rho;
-                    sw[k] = fma(rho, dr, sw[k]);
-                }
-            }
-        } else if (!UNIT) {
-#pragma unroll
-            for (int k = 0; k < GPW; ++k) sw[k] += (__double2hiint(x[k]) >= 0) ? dr : 0.0;
-        }
-        qa = qa_n; qb = qb_n; qc = qc_n; dr = dr_n;
-    }
-}
-
 // ---- score_rows_fx: the soft-rank sweep with the exponent split folded into the quadratic -------------------------------
 // e = exp(-dd/temp) = 2^(X/16), X = -x.  The coefficient table holds (qa, qb, M - qc) with M = 1.5 * 2^20, so that the second
 // fma of the quadratic already delivers t = M + X rounded to 32 fraction bits: the low word of t IS z = X - floor(X) as a
 // 32-bit fraction, the high word carries floor(X) = 16 kk + j in its low bits (what exp_tab_scaled wants) and [x <= 0] in
 // bit 19 (the hard count).  Two integer instructions turn z into the double w = 1 + z 2^-32 in [1, 2), and
-// 2^(z/16) = c3 (((w + b2) w + b1) w + b0) (monic minimax cubic on [1, 2], rel. err 1.2e-9 like score_rows8, c3 folded into
+// 2^(z/16) = c3 (((w + b2) w + b1) w + b0) (monic minimax cubic on [1, 2], rel. err 1.2e-9 like the cubic of score_rows; monic, so that every
+// step has ONE constant operand -- a DFMA that reads three fresh register pairs issues every 3 clocks instead of 2,
+// tools/dfma_operands*.cu; c3 folded into
 // the table) -- the three DADDs that split x into round(x) and x - round(x) are gone: 8 fp64-pipe instructions per element
 // instead of 11 (10 instead of 13 with a ratio estimator).  Measured (tools/score_loop_bench.cu VAR 50 against VAR 0): 112.9
 // instead of 121.0 clocks per (32 train points x 4 grid points).  The same cubic on the integer pipes (three IMAD.HI in 2^-36
@@ -408,8 +327,9 @@ k_score(const ScoreArgs p) {
     double* zt = g_mk + G;                              // zt[t][e] = sum_{b<4} (+-) c_{4t+b}, sign from bit b of e
 
     // ---- once per CTA: candidate-independent tables ------------------------------------------------
-    if (tid < 16) exp_tab_init(tab, tid);
-    const unsigned tab_s = smem_u32(tab);
+    __shared__ __align__(128) double tabfx[16];         // c3 2^(j/16): score_rows_fx (soft path)
+    if (tid < 16) { exp_tab_init(tab, tid); exp_tabfx_init(tabfx, tid); }
+    const unsigned tab_s = smem_u32(tab), tabfx_s = smem_u32(tabfx);
     for (int i = tid; i < Np; i += blockDim.x) sdr[i] = (i < N) ? p.dr[i] : 0.0;
     __syncthreads();                                    // the only block-wide barrier
 
@@ -498,7 +418,7 @@ k_score(const ScoreArgs p) {
                         qc = c1 * (fma(iv * ai[j], ai[j], lv_c - lv));   // constant
                         big |= !(fma(fma(fabs(qa), bmax, fabs(qb)), bmax, fabs(qc)) < 900.0);
                     }
-                    sq[3 * i] = qa; sq[3 * i + 1] = qb; sq[3 * i + 2] = qc;
+                    sq[3 * i] = qa; sq[3 * i + 1] = qb; sq[3 * i + 2] = SOFT ? kFxMagic - qc : qc;   // soft path: score_rows_fx wants M - qc
                 }
             }
         }
@@ -520,13 +440,18 @@ k_score(const ScoreArgs p) {
                 bg[k] = gsd * eps * inv_s;                              // (y_g - mu) / s
                 sr[k] = 0.0; sw[k] = 0.0; cneg[k] = 0u;
             }
-            if (!bad) {
-                if (p.unit_dr) {       // padded rows carry rho ~ 1e-17 each into sum rho * dr here (dr is not read): negligible
-                    if (big) score_rows<SOFT, true, true, SCORE_FWD_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
-                    else score_rows<SOFT, false, true, SCORE_FWD_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
+            if (!bad) {   // (no ratio estimator: padded rows carry rho ~ 1e-17 each into sum rho * dr, dr is not read: negligible)
+                if (SOFT) {
+                    if (p.unit_dr) {
+                        if (big) score_rows_fx<true, true, SCORE_FWD_GPW>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                        else score_rows_fx<false, true, SCORE_FWD_GPW>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                    } else {
+                        if (big) score_rows_fx<true, false, SCORE_FWD_GPW>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                        else score_rows_fx<false, false, SCORE_FWD_GPW>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                    }
                 } else {
-                    if (big) score_rows<SOFT, true, false, SCORE_FWD_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
-                    else score_rows<SOFT, false, false, SCORE_FWD_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
+                    if (p.unit_dr) score_rows<false, false, true, SCORE_FWD_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
+                    else score_rows<false, false, false, SCORE_FWD_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
                 }
             }
             if (SCORE_FWD_GPW == 4) {   // transposed reductions: lanes 8k..8k+7 end up with the totals of grid point g0 + k

@@ -70,13 +70,13 @@ __device__ __forceinline__ double soft_rho(double x, unsigned tab_s, double kMag
 
 // Pass 2 for SB_RI train points of one thread: E_k = sum_g Gamma_g b_g^k.
 // rec[g] = UNIT ? {b, pq, pq b, pq b^2} : {b, b^2, P, Q}   (P, Q, pq already divided by temp)
+// rho by the instruction sequence of score_rows_fx (qcm = M - qc: the tables of the soft path hold it that way).
 template <bool CLAMP, bool UNIT>
 __device__ __forceinline__ void moment_sweep(const ScoreArgs& p, const double* __restrict__ rec, int G,
-                                             unsigned tab_s, const double (&qa)[SB_RI],
-                                             const double (&qb)[SB_RI], const double (&qc)[SB_RI], const double (&dri)[SB_RI],
+                                             unsigned tabfx_s, const double (&qa)[SB_RI],
+                                             const double (&qb)[SB_RI], const double (&qcm)[SB_RI], const double (&dri)[SB_RI],
                                              double (&E0)[SB_RI], double (&E1)[SB_RI], double (&E2)[SB_RI]) {
-    const double kMagic = p.k_magic, kC0 = p.k_c0, kC1n = p.k_c1n, kC2 = p.k_c2, kC3n = p.k_c3n;
-    constexpr int kSatHi = 0x408d9000;
+    const double kB2 = p.fx_b2, kB1 = p.fx_b1, kB0 = p.fx_b0;
     // Stage-wise over SB_RI rows x SB_GI grid points (as score_rows): written out so that the dependency chains are
     // interleaved instead of being scheduled one after the other; 2 x 2 keeps the live coefficients / moments at 12 doubles.
     static_assert(SB_GI == 2, "moment_sweep is written for two grid points per step");
@@ -89,29 +89,31 @@ __device__ __forceinline__ void moment_sweep(const ScoreArgs& p, const double* _
         r23[0] = *reinterpret_cast<const double2*>(rec + 4 * g + 2);
         r01[1] = *reinterpret_cast<const double2*>(rec + 4 * g1);
         r23[1] = *reinterpret_cast<const double2*>(rec + 4 * g1 + 2);
-        double t[SB_RI][SB_GI], yn[SB_RI][SB_GI], dd[SB_RI][SB_GI];
+        double t[SB_RI][SB_GI], dd[SB_RI][SB_GI];
 #pragma unroll
         for (int r = 0; r < SB_RI; ++r)
 #pragma unroll
             for (int k = 0; k < SB_GI; ++k) {
                 const double bg = r01[k].x;
-                double x = fma(fma(qa[r], bg, qb[r]), bg, qc[r]);
+                double tt = fma(-fma(qa[r], bg, qb[r]), bg, qcm[r]);         // M - x
                 if (CLAMP) {
-                    int hi = __double2hiint(x);
-                    int ch = min(hi & 0x7fffffff, kSatHi) | (hi & 0x80000000);
-                    x = __hiloint2double(ch, __double2loint(x));
+                    constexpr int kLo = 0x4137fc4e, kHi = 0x413803b2;        // high words of M - 946, M + 946
+                    const int h = min(max(__double2hiint(tt), kLo), kHi);
+                    tt = __hiloint2double(h, __double2loint(tt));
                 }
-                t[r][k] = kMagic - x;
-                yn[r][k] = x + (t[r][k] - kMagic);
+                t[r][k] = tt;
             }
 #pragma unroll
         for (int r = 0; r < SB_RI; ++r)
 #pragma unroll
             for (int k = 0; k < SB_GI; ++k) {
-                double pl = fma(yn[r][k], kC3n, kC2);
-                pl = fma(pl, yn[r][k], kC1n);
-                pl = fma(pl, yn[r][k], kC0);
-                dd[r][k] = fma(exp_tab_scaled(tab_s, __double2loint(t[r][k])), pl, 1.0);
+                const unsigned z = unsigned(__double2loint(t[r][k]));
+                const int hi = __double2hiint(t[r][k]);
+                const double w = __hiloint2double(int(0x3ff00000u + (z >> 12)), int(z << 20));
+                double pl = w + kB2;
+                pl = fma(pl, w, kB1);
+                pl = fma(pl, w, kB0);
+                dd[r][k] = fma(exp_tab_scaled(tabfx_s, hi), pl, 1.0);
             }
 #pragma unroll
         for (int r = 0; r < SB_RI; ++r)
@@ -163,8 +165,9 @@ k_score_bwd(const ScoreBwdArgs q) {
     double* part2 = part1 + 16 * 32;                    // [WPG][32]: phase E partial sums
     double* s_utb = part2 + 16 * 32;                    // ut_bar[Sp] of the current candidate
 
-    if (tid < 16) exp_tab_init(tab, tid);
-    const unsigned tab_s = smem_u32(tab);
+    __shared__ __align__(128) double tabfx[16];         // score_rows_fx / moment_sweep (soft path)
+    if (tid < 16) { exp_tab_init(tab, tid); exp_tabfx_init(tabfx, tid); }
+    const unsigned tab_s = smem_u32(tab), tabfx_s = smem_u32(tabfx);
     for (int i = tid; i < Np; i += blockDim.x) sdr[i] = (i < N) ? p.dr[i] : 0.0;
     __syncthreads();
 
@@ -252,7 +255,7 @@ k_score_bwd(const ScoreBwdArgs q) {
                         qc = c1 * (fma(iv * ai[j], ai[j], lv_c - lv));
                         big |= !(fma(fma(fabs(qa), bmax, fabs(qb)), bmax, fabs(qc)) < 900.0);
                     }
-                    sq[3 * i] = qa; sq[3 * i + 1] = qb; sq[3 * i + 2] = qc;
+                    sq[3 * i] = qa; sq[3 * i + 1] = qb; sq[3 * i + 2] = SOFT ? kFxMagic - qc : qc;   // soft path: score_rows_fx wants M - qc
                 }
             }
         }
@@ -275,12 +278,17 @@ k_score_bwd(const ScoreBwdArgs q) {
                 sr[k] = 0.0; sw[k] = 0.0; cneg[k] = 0u;
             }
             if (!bad) {
-                if (p.unit_dr) {
-                    if (big) score_rows<SOFT, true, true, SCORE_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
-                    else score_rows<SOFT, false, true, SCORE_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
+                if (SOFT) {
+                    if (p.unit_dr) {
+                        if (big) score_rows_fx<true, true, SCORE_GPW>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                        else score_rows_fx<false, true, SCORE_GPW>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                    } else {
+                        if (big) score_rows_fx<true, false, SCORE_GPW>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                        else score_rows_fx<false, false, SCORE_GPW>(p, sq, sdr, tabfx_s, lane, N32, bg, sr, sw, cneg);
+                    }
                 } else {
-                    if (big) score_rows<SOFT, true, false, SCORE_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
-                    else score_rows<SOFT, false, false, SCORE_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
+                    if (p.unit_dr) score_rows<false, false, true, SCORE_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
+                    else score_rows<false, false, false, SCORE_GPW>(p, sq, sdr, tab_s, lane, N32, bg, sr, sw, cneg);
                 }
             }
             {   // transposed reductions: lanes 8k..8k+7 end up with the totals of grid point g0 + k
@@ -444,16 +452,16 @@ k_score_bwd(const ScoreBwdArgs q) {
                 for (int r = 0; r < SB_RI; ++r) {
                     int i = i0 + GT * r;
                     bool ok = i < N32;
-                    qa[r] = ok ? sq[3 * i] : 0.0; qb[r] = ok ? sq[3 * i + 1] : 0.0; qc[r] = ok ? sq[3 * i + 2] : -900.0;
+                    qa[r] = ok ? sq[3 * i] : 0.0; qb[r] = ok ? sq[3 * i + 1] : 0.0; qc[r] = ok ? sq[3 * i + 2] : kFxMagic + 900.0;   // M - qc
                     dri[r] = (ok && !p.unit_dr) ? sdr[i] : 1.0;
                     E0[r] = E1[r] = E2[r] = 0.0;
                 }
                 if (p.unit_dr) {
-                    if (big) moment_sweep<true, true>(p, rec, G, tab_s, qa, qb, qc, dri, E0, E1, E2);
-                    else moment_sweep<false, true>(p, rec, G, tab_s, qa, qb, qc, dri, E0, E1, E2);
+                    if (big) moment_sweep<true, true>(p, rec, G, tabfx_s, qa, qb, qc, dri, E0, E1, E2);
+                    else moment_sweep<false, true>(p, rec, G, tabfx_s, qa, qb, qc, dri, E0, E1, E2);
                 } else {
-                    if (big) moment_sweep<true, false>(p, rec, G, tab_s, qa, qb, qc, dri, E0, E1, E2);
-                    else moment_sweep<false, false>(p, rec, G, tab_s, qa, qb, qc, dri, E0, E1, E2);
+                    if (big) moment_sweep<true, false>(p, rec, G, tabfx_s, qa, qb, qc, dri, E0, E1, E2);
+                    else moment_sweep<false, false>(p, rec, G, tabfx_s, qa, qb, qc, dri, E0, E1, E2);
                 }
 #pragma unroll
                 for (int r = 0; r < SB_RI; ++r) {
