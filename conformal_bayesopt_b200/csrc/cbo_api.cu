@@ -544,6 +544,28 @@ int cbo_conf_mask_to_bounds_f64(const double* grid, const double* mask, int64_t 
     return CBO_OK;
 }
 
+// Side stream of the latency path (a call with a handful of candidate points, e.g. one SGLD step of 8 restarts x q = 2): the
+// density-ratio MLP over the train points and over the candidates depends on nothing the probe solves produce, so it runs on
+// a library-private stream BESIDE them (fork / join through events: legal under stream capture, the side stream becomes a
+// branch of the caller's graph).  One stream and three timing-free events per device, created on first use; `call_mu`
+// serialises the enqueue of calls that share them.
+struct SideStream {
+    std::mutex mu, call_mu;
+    cudaStream_t st = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
+    cudaError_t ensure() {
+        std::lock_guard<std::mutex> l(mu);
+        if (st) return cudaSuccess;
+        cudaStream_t x;
+        if (cudaError_t e = cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking); e != cudaSuccess) return e;
+        for (cudaEvent_t* ev : {&fork, &join, &join2})
+            if (cudaError_t e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming); e != cudaSuccess) return e;
+        st = x;
+        return cudaSuccess;
+    }
+};
+SideStream g_side[cbo::kMaxDevices];
+
 // Per-chunk callbacks of the host-buffer entry point: `before` is called ahead of the first kernel that reads the chunk's
 // candidates, `after` behind the last kernel that writes its acquisition values (both only enqueue stream operations).
 struct ChunkHooks {
@@ -583,6 +605,21 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
     const int tiles_n = Np / cbo::GEMM_BN;
     const int64_t C = pick_chunk(b, p, chunk);
 
+    // latency path with a ratio estimator (one chunk of <= 32 candidate points): both MLP launches on the side stream
+    SideStream* side = nullptr;
+    std::unique_lock<std::mutex> side_lock;
+    if (ratio && b * p->q <= cbo::GEMM_SPLITK_MAX_M && C >= b && !hooks) {
+        const int dev = cbo::current_device_slot();
+        if (dev >= 0) {
+            side = &g_side[dev];
+            CBO_CUDA(side->ensure());
+            side_lock = std::unique_lock<std::mutex>(side->call_mu);
+            CBO_CUDA(cudaEventRecord(side->fork, s));
+            CBO_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+        }
+    }
+    cudaStream_t s_ratio = side ? side->st : s;
+
     // ---- per-call tables: T = A^-1 z[:N], dr_train, a, h0, zb, sum_dr -------------------------------
     {
     TimeScope ts_(T_PREP, s, 7);
@@ -591,10 +628,14 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
     // T^T = Z^T A^-1 (Sp x Np): the probe vectors are Sp more "rows" for the two triangular passes (split-K: a handful of rows)
     CBO_CUDA(cbo::launch_gemm_tn(w.zp, Np, gp->linv, Np, w.tmp, Np, Sp, Np, Np, cbo::TRI_LOWER, nullptr, s, num_sms(), w.splitk));
     CBO_CUDA(cbo::launch_gemm_tn(w.tmp, Np, gp->linv_t, Np, w.T, Np, Sp, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms(), w.splitk));
-    if (ratio)
+    if (ratio) {
         CBO_CUDA(cbo::launch_ratio_mlp(gp->X, N, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2, ratio->b2,
-                                       ratio->W3, ratio->b3, 1e-6, w.dr_train, num_sms(), s));
-    else
+                                       ratio->W3, ratio->b3, 1e-6, w.dr_train, num_sms(), s_ratio));
+        if (side) {                                            // k_train_tables below reads dr_train
+            CBO_CUDA(cudaEventRecord(side->join, side->st));
+            CBO_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+        }
+    } else
         CBO_LAUNCHED(), cbo::k_fill<<<(Np + 255) / 256, 256, 0, s>>>(w.dr_train, Np, 1.0);
     if (p->q == 1) {
         const int rows = p->eps_per_candidate ? (int)b : 1;
@@ -621,7 +662,11 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                                              gp->alpha, w.T, Sp, w.UW, w.mu, w.ut, num_sms(), s, splitk != nullptr));
             if (ratio)
                 CBO_CUDA(cbo::launch_ratio_mlp(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2, ratio->b2,
-                                               ratio->W3, ratio->b3, 1e-6, w.drc, num_sms(), s));
+                                               ratio->W3, ratio->b3, 1e-6, w.drc, num_sms(), s_ratio));
+            if (side) {                                        // joined ahead of the score kernel, the first reader of drc
+                CBO_CUDA(cudaEventRecord(side->join2, side->st));
+                CBO_CUDA(cudaStreamWaitEvent(s, side->join2, 0));
+            }
             CBO_CUDA(cudaGetLastError());
         }
         // ---- v = L^-1 u (+ ||v||^2 partials), w = L^-T v ------------------------------------------

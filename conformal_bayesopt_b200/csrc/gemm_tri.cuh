@@ -149,17 +149,40 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
             mbar_wait(&full[st], (kt / GEMM_STAGES) & 1);
             const double* sA = smem + st * GEMM_STAGE_DOUBLES + (wm * (8 * MF) + fr) * GEMM_LDS + fk;
             const double* sB = smem + st * GEMM_STAGE_DOUBLES + BM * GEMM_LDS + (wn * 32 + fr) * GEMM_LDS + fk;
+            // rel = position of this k-tile inside the warp's own 32 x 32 diagonal sub-block (0 or 16), else outside [0, 32)
+            const int rel = (tri == TRI_FULL) ? -1 : k0 - (n0 + 32 * wn);
+            if (rel >= 0 && rel < 32) {
+                // the two k-tiles that cross the diagonal: 8-column fragment j sees only zeros at k-step ks when
+                // lower: k0 + 4 ks >= n_frag + 8,  upper: k0 + 4 ks + 4 <= n_frag  -- skip those MMAs too (12 of 32 here)
 #pragma unroll
-            for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
-                double a[MF], b[4];
+                for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
+                    double a[MF], b[4];
 #pragma unroll
-                for (int i = 0; i < MF; ++i) a[i] = sA[i * 8 * GEMM_LDS + ks * 4];
+                    for (int i = 0; i < MF; ++i) a[i] = sA[i * 8 * GEMM_LDS + ks * 4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = sB[j * 8 * GEMM_LDS + ks * 4];
+                    for (int j = 0; j < 4; ++j) b[j] = sB[j * 8 * GEMM_LDS + ks * 4];
 #pragma unroll
-                for (int i = 0; i < MF; ++i)
+                    for (int j = 0; j < 4; ++j) {
+                        const bool live = (tri == TRI_LOWER) ? (rel + 4 * ks < 8 * j + 8) : (rel + 4 * ks + 4 > 8 * j);
+                        if (live) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                            for (int i = 0; i < MF; ++i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
+                    double a[MF], b[4];
+#pragma unroll
+                    for (int i = 0; i < MF; ++i) a[i] = sA[i * 8 * GEMM_LDS + ks * 4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) b[j] = sB[j * 8 * GEMM_LDS + ks * 4];
+#pragma unroll
+                    for (int i = 0; i < MF; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
             }
         }
         __syncwarp();
