@@ -787,6 +787,18 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             const bool nei_rev = qpath && nei_kind && (!ext || ext->f_bar);
             double* rhs = !qpath ? w.V : w.X3;                      // right-hand sides w_bar'
             double* sol = !qpath ? w.X3 : w.V;                      // scratch of the two-pass solve
+            // latency path: the ratio estimator's reverse pass needs only the adjoint records -- it runs on the side stream
+            // beside the two reverse solves and WRITES dX, the kernel-row term is then added (same sum, other order of issue)
+            const bool ratio_first = side && ratio && (qpath || splitk != nullptr);
+            if (ratio_first) {
+                CBO_CUDA(cudaEventRecord(side->fork, s));
+                CBO_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+                CBO_CUDA(cbo::launch_ratio_mlp_bwd(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2,
+                                                   ratio->b2, ratio->W3, ratio->b3, 1e-6, w.adj,
+                                                   !qpath ? cbo::ADJ_STRIDE : cbo::ADJQ_STRIDE, !qpath ? 2 : 1,
+                                                   dX + c0 * q * d, num_sms(), side->st, false));
+                CBO_CUDA(cudaEventRecord(side->join, side->st));
+            }
             {
                 TimeScope ts_(T_GEMM_BWD, s, 2);
                 CBO_CUDA(cbo::launch_gemm_tn(rhs, Np, gp->linv, Np, sol, Np, n, Np, Np, cbo::TRI_LOWER, nullptr, s, num_sms(), splitk));
@@ -797,13 +809,15 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 if (!qpath && splitk == nullptr)
                     CBO_CUDA(cbo::launch_rows_bwd(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->alpha, rhs,
                                                   w.UW, w.adj, dX + c0 * q * d, num_sms(), s));
-                else    // joint batches, and q = 1 calls with a handful of candidates (CTA per candidate point)
+                else {  // joint batches, and q = 1 calls with a handful of candidates (CTA per candidate point)
+                    if (ratio_first) CBO_CUDA(cudaStreamWaitEvent(s, side->join, 0));
                     CBO_LAUNCHED(), cbo::k_rows_bwd_q<<<n, cbo::RBQ_THREADS, 0, s>>>(Xc, n, q, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale,
                                                                  gp->alpha, rhs, w.UW, w.adj,
                                                                  !qpath ? cbo::ADJ_STRIDE : cbo::ADJQ_STRIDE, !qpath ? 1 : 0,
                                                                  nei_rev ? p->nei->Xb : nullptr, nei_rev ? (int)p->nei->nb : 0,
-                                                                 nei_rev ? w.cv_bar : nullptr, dX + c0 * q * d);
-                if (ratio)
+                                                                 nei_rev ? w.cv_bar : nullptr, dX + c0 * q * d, ratio_first ? 1 : 0);
+                }
+                if (ratio && !ratio_first)
                     CBO_CUDA(cbo::launch_ratio_mlp_bwd(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2,
                                                        ratio->b2, ratio->W3, ratio->b3, 1e-6, w.adj,
                                                        !qpath ? cbo::ADJ_STRIDE : cbo::ADJQ_STRIDE, !qpath ? 2 : 1,

@@ -150,12 +150,12 @@ k_ratio_mlp_mma(const double* __restrict__ x, int n, int d, int H, const double*
     }
 }
 
-// reverse: dX[p, :] += adj[p][2] * d ratio(x_p) / d x   (1 m-tile per warp pass; clamps cut the gradient like torch.clamp)
+// reverse: dX[p, :] (+)= adj[p][2] * d ratio(x_p) / d x   (1 m-tile per warp pass; clamps cut the gradient like torch.clamp)
 __global__ void __launch_bounds__(RM_WARPS * 32)
 k_ratio_mlp_mma_bwd(const double* __restrict__ x, int n, int d, int H, const double* __restrict__ W1,
                     const double* __restrict__ b1, const double* __restrict__ W2, const double* __restrict__ b2,
                     const double* __restrict__ W3, const double* __restrict__ b3, double clamp_min,
-                    const double* __restrict__ adj, int adj_stride, int adj_off, double* __restrict__ dX) {
+                    const double* __restrict__ adj, int adj_stride, int adj_off, double* __restrict__ dX, int accumulate) {
     extern __shared__ __align__(16) double rsm[];
     const RatioMmaSmem s = ratio_mma_stage(rsm, d, H, W1, b1, W2, b2, W3, true);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
@@ -214,8 +214,8 @@ k_ratio_mlp_mma_bwd(const double* __restrict__ x, int n, int d, int H, const dou
             const int k0 = 8 * dto + 2 * q;
             if (p0 + r < n) {
                 double* o = dX + int64_t(p0 + r) * d + k0;
-                if (k0 < d) o[0] += a0;
-                if (k0 + 1 < d) o[1] += a1;
+                if (k0 < d) o[0] = accumulate ? o[0] + a0 : a0;          // accumulate = 0: this kernel runs FIRST (side stream) and
+                if (k0 + 1 < d) o[1] = accumulate ? o[1] + a1 : a1;      // the kernel-row term is added to it afterwards
             }
         }
     }
@@ -236,13 +236,13 @@ inline cudaError_t launch_ratio_mlp(const double* x, int n, int d, int H, const 
 inline cudaError_t launch_ratio_mlp_bwd(const double* x, int n, int d, int H, const double* W1, const double* b1,
                                         const double* W2, const double* b2, const double* W3, const double* b3,
                                         double clamp_min, const double* adj, int adj_stride, int adj_off, double* dX,
-                                        int num_sms, cudaStream_t st) {
+                                        int num_sms, cudaStream_t st, bool accumulate = true) {
     const size_t smem = ratio_mma_smem_bytes(d, true);
     static SmemOptIn optin;
     if (cudaError_t e = optin.ensure(k_ratio_mlp_mma_bwd, smem); e != cudaSuccess) return e;
     int grid = ((n + 7) / 8 + RM_WARPS - 1) / RM_WARPS;
     if (grid > 2 * num_sms) grid = 2 * num_sms;
-    CBO_LAUNCHED(), k_ratio_mlp_mma_bwd<<<grid, RM_WARPS * 32, smem, st>>>(x, n, d, H, W1, b1, W2, b2, W3, b3, clamp_min, adj, adj_stride, adj_off, dX);
+    CBO_LAUNCHED(), k_ratio_mlp_mma_bwd<<<grid, RM_WARPS * 32, smem, st>>>(x, n, d, H, W1, b1, W2, b2, W3, b3, clamp_min, adj, adj_stride, adj_off, dX, accumulate ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -903,7 +903,7 @@ k_rows_bwd_q(const double* __restrict__ Xq, int rows, int q, const double* __res
              const double* __restrict__ inv_ls, double outputscale, const double* __restrict__ alpha,
              const double* __restrict__ Aw, const double* __restrict__ W, const double* __restrict__ adjq,
              int adj_stride, int q1_layout, const double* __restrict__ Xb, int nb, const double* __restrict__ cv_bar,
-             double* __restrict__ dX) {
+             double* __restrict__ dX, int accumulate) {
     // Xb / cv_bar (cNEI): c_rj = k(X_b,r, x_j) - ... adds sum_r cv_bar[c, r, j] dk(X_b,r, x_j)/dx_j
     // q1_layout: the adjoint record of k_score_bwd ({mu_bar, s_bar, ...}; Ssym = 2 s_bar) instead of k_score_q_bwd's
     __shared__ double s_x[MAX_D], s_red[RBQ_THREADS / 32][8], s_adj[2 + MAX_Q];
@@ -970,7 +970,8 @@ k_rows_bwd_q(const double* __restrict__ Xq, int rows, int q, const double* __res
                 const double dfk = s_x[kd] - Xb[rb * d + kd] * inv_ls[kd];
                 v = fma(cv_bar[(int64_t(c) * nb + rb) * q + j] * kfac * (1.0 + t) * exp(-t), dfk, v);
             }
-            dX[int64_t(r) * d + kd] = v * inv_ls[kd];
+            const double out = v * inv_ls[kd];
+            dX[int64_t(r) * d + kd] = accumulate ? dX[int64_t(r) * d + kd] + out : out;   // accumulate: the ratio term is there already
         }
         __syncthreads();
     }
