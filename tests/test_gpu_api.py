@@ -448,3 +448,32 @@ def test_model_append_matches_a_rebuild(N, q):
     a = ops.conformal_acq(app, inp["Xq"].to(dev), **call)["acq"]
     b = ops.conformal_acq(full, inp["Xq"].to(dev), **call)["acq"]
     assert float((a - b).abs().max() / b.abs().max()) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("temp,ratio_on", [(3e-2, False), (3e-2, True), (1e-5, True)])
+def test_pair_and_warp_specialised_score_kernels_are_bit_identical(monkeypatch, temp, ratio_on):
+    """k_score (warp pairs) and k_score_ws (warp-specialised; picked by batch size) share ONE soft-rank sweep
+    (score_rows_fx, also its clamped variant at tiny temp): forcing either kernel on the same call gives the same bits,
+    so the batch-size switch can never move a result.  Both are checked against the closed-form oracle."""
+    from conformal_bayesopt_b200 import ops
+    dev = _dev()
+    N, d, b, G = 200, 5, 150, 48
+    p = make_problem(N, d, seed=21)
+    inp = make_inputs(N, d, b, 1, G, S=1, seed=21)
+    ratio = ogp.make_ratio_mlp(d) if ratio_on else None
+    rw = ops.RatioWeights(*[t.to(dev) for t in (ratio.W1, ratio.b1, ratio.W2, ratio.b2, ratio.W3, ratio.b3)]) if ratio_on else None
+    kw = dict(kind="ucb", alpha=0.1, temp=temp, grid_res=G, randomized=True, optimistic=True, beta_prime=1.0)
+    outs = ("conf_pred_mask", "num_accepted", "ood_mask")
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CBO_SCORE_WS", mode)
+        res[mode] = ops.conformal_acq(_state(p, dev), inp["Xq"].to(dev), eps_grid=inp["eps_grid"][:, 0].to(dev),
+                                      z=inp["z"].to(dev), eps_mc=inp["eps_mc"][:, :, 0].to(dev),
+                                      u_rand=inp["u_rand"][:, :, 0].to(dev), ratio=rw, outputs=outs, **kw)
+    for k in ("acq",) + outs:
+        assert torch.equal(res["0"][k], res["1"][k]), k
+    want = closed_form.conformal_acquisition(oracle_state(p), inp["Xq"], eps_grid=inp["eps_grid"], z=inp["z"],
+                                             eps_mc=inp["eps_mc"], u_rand=inp["u_rand"], ratio=ratio, **kw)
+    assert torch.allclose(res["1"]["acq"].cpu(), want["acq"], rtol=1e-6, atol=1e-9)
+    assert torch.allclose(res["1"]["conf_pred_mask"].cpu(), want["mask"][:, :, 0], rtol=0, atol=1e-6)

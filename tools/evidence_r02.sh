@@ -22,6 +22,9 @@ python tools/prof_grad_run.py 65536 2 > $O/r02_prof_grad_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o $O/prof_r02_grad \
     python tools/prof_grad_run.py 65536 2 > $O/r02_ncu_grad.log 2>&1
 python tools/sgld_step_time.py > $O/r02_sgld_step_time.log 2>&1
-ls -la $O/prof_r02_fwd.ncu-rep $O/prof_r02_grad.ncu-rep
+# the .ncu-rep files (60-70 MB each) exceed what gpurun copies back: summarise them here and drop them
+{ echo "==== forward call, 65536 candidates (tools/prof_run.py) ===="; python tools/ncu_summary.py $O/prof_r02_fwd.ncu-rep;
+  echo; echo "==== value + gradient call, 65536 candidates (tools/prof_grad_run.py) ===="; python tools/ncu_summary.py $O/prof_r02_grad.ncu-rep; } > $O/r02_ncu_summary_final.txt 2>&1
+rm -f $O/prof_r02_fwd.ncu-rep $O/prof_r02_grad.ncu-rep
 tail -3 $O/r02_gputest_final.log
 head -c 400 $O/r02_bench_n1.json

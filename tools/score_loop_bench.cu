@@ -125,6 +125,45 @@ __device__ __forceinline__ void rows(const ScoreArgs& p, const double* __restric
         score_rows_fx<true, true, 4>(p, sq, sq, tab_s, lane, N32, bg, sr, sw, cneg);
         return;
     }
+    if (V == 65) {   // score_rows_fx with ONE reciprocal per two grid points: 1/d0 = d1 r, 1/d1 = d0 r, r = 1/(d0 d1)
+        const double kB2 = p.fx_b2, kB1 = p.fx_b1, kB0 = p.fx_b0;
+        const double* tq = sq + 3 * lane;
+        double qa = tq[0], qb = tq[1], qc = tq[2];
+        const int nsteps = N32 >> 5;
+        for (int it = 0; it < nsteps; ++it) {
+            tq += 96;
+            const double qa_n = tq[0], qb_n = tq[1], qc_n = tq[2];
+            double t[4], e[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = fma(qa, bg[k], qb);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = fma(-t[k], bg[k], qc);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned z = unsigned(__double2loint(t[k]));
+                const int hi = __double2hiint(t[k]);
+                cneg[k] += unsigned(hi) >> 19;
+                const double w = __hiloint2double(int(0x3ff00000u + (z >> 12)), int(z << 20));
+                double pl = w + kB2;
+                pl = fma(pl, w, kB1);
+                pl = fma(pl, w, kB0);
+                e[k] = fma(exp_tab_scaled(tab_s, hi), pl, 1.0);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k += 2) {
+                const double m = e[k] * e[k + 1];
+                double y0;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(m));
+                const double r = y0 * fma(-m, y0, 2.0);
+                sr[k] = fma(e[k + 1], r, sr[k]);
+                sr[k + 1] = fma(e[k], r, sr[k + 1]);
+            }
+            qa = qa_n; qb = qb_n; qc = qc_n;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cneg[k] -= unsigned(nsteps) * 0x826u;
+        return;
+    }
     if (V == 63 || V == 64) {   // score_rows_fx, software-pipelined: the quadratic of row i+1 is issued beside the sigmoid of row i
         const double kB2 = p.fx_b2, kB1 = p.fx_b1, kB0 = p.fx_b0;
         const double* tq = sq + 3 * lane;
