@@ -8,6 +8,9 @@
 #ifndef VAR
 #define VAR 0
 #endif
+#ifndef NW
+#define NW 16          // warps per SM (4 per sub-partition in the kernels)
+#endif
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
 using namespace cbo;
 
@@ -272,7 +275,7 @@ __device__ __forceinline__ void rows(const ScoreArgs& p, const double* __restric
     }
 }
 
-__global__ void __launch_bounds__(512, 1) k(const ScoreArgs p, const double* coef, double* out, int passes) {
+__global__ void __launch_bounds__(NW * 32, 1) k(const ScoreArgs p, const double* coef, double* out, int passes) {
     extern __shared__ __align__(16) double sm[];
     __shared__ __align__(128) double tab8[16];
     __shared__ __align__(1024) double tab[128];
@@ -283,8 +286,8 @@ __global__ void __launch_bounds__(512, 1) k(const ScoreArgs p, const double* coe
         __syncthreads();
         if (tid < 16) exp_tabfx_init(tab, tid);
     }
-    double* sq = sm + size_t(warp >> 1) * (3 * 1024 + 96);
-    for (int i = tid & 63; i < 3 * 1024 + 96; i += 64) {
+    double* sq = sm + size_t(warp & 7) * (3 * 1024 + 96);
+    for (int i = (warp < 8) ? lane : 3 * 1024 + 96; i < 3 * 1024 + 96; i += 32) {   // warps 0..7 fill table (warp & 7)
         double v = coef[i % (3 * 1024)];
         if ((VAR >= 50) && (i % 3) == 2) v = 1572864.0 - v;      // M - qc, M = 1.5 * 2^20
         sq[i] = v;
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(512, 1) k(const ScoreArgs p, const double* coe
         tot += sr[0] + sr[1] + sr[2] + sr[3];
         ctot += cneg[0] + cneg[1] + cneg[2] + cneg[3];
     }
-    out[blockIdx.x * 512 + tid] = tot + ctot;
+    out[blockIdx.x * (NW * 32) + tid] = tot + ctot;
 }
 
 int main() {
@@ -316,16 +319,16 @@ int main() {
     for (int i = 0; i < 1024; ++i) { h[3 * i] = -40.0 - 0.01 * i; h[3 * i + 1] = 3.0 + 0.001 * i; h[3 * i + 2] = 20.0 * ((i % 17) - 8); }
     double *coef, *out;
     CK(cudaMalloc(&coef, sizeof(h))); CK(cudaMemcpy(coef, h, sizeof(h), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&out, sizeof(double) * sms * 512));
+    CK(cudaMalloc(&out, sizeof(double) * sms * NW * 32));
     const size_t smem = sizeof(double) * 8 * (3 * 1024 + 96);
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int passes = 400;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k<<<sms, 512, smem>>>(a, coef, out, passes);
+    k<<<sms, NW * 32, smem>>>(a, coef, out, passes);
     CK(cudaDeviceSynchronize());
     float best = 1e30f;
     for (int r = 0; r < 3; ++r) {
-        cudaEventRecord(e0); k<<<sms, 512, smem>>>(a, coef, out, passes); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventRecord(e0); k<<<sms, NW * 32, smem>>>(a, coef, out, passes); cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
     double hsum = 0; static double ho[512]; CK(cudaMemcpy(ho, out, sizeof(ho), cudaMemcpyDeviceToHost)); for (double v : ho) hsum += v;
@@ -341,6 +344,6 @@ int main() {
         }
         printf("thread 0: device %.12e  host reference %.12e (rho sum %+.3e, count %ld)\n", ho[0], ref + cnt, ho[0] - ref - cnt, cnt);
     }
-    printf("VAR %d: %.3f ms  %.1f clk per warp step per sub-partition  (checksum %.6e)\n", VAR, best, best * pr.clockRate / (4.0 * passes * 32), hsum);
+    printf("NW %d VAR %d: %.3f ms  %.1f clk per warp step per sub-partition  (checksum %.6e)\n", NW, VAR, best, best * pr.clockRate / (NW / 4.0 * passes * 32), hsum);
     return 0;
 }
