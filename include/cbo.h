@@ -27,7 +27,13 @@
  *   - the caller owns every buffer; the library allocates no device memory, ever;
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); the only host
  *     synchronisation is one per grid-refinement pass when max_grid_refinements > 0 (the
- *     reference synchronises there too, helpers.py:151-152,177);
+ *     reference synchronises there too, helpers.py:151-152,177).  A call with a ratio estimator and
+ *     at most 32 candidate points (an SGLD step) also runs the estimator's launches on a
+ *     library-private side stream that is forked from `stream` and joined back into it through
+ *     events before the call returns: the caller still only sees work ordered on `stream`, and the
+ *     call can be captured into a CUDA graph (the side stream becomes a branch of it).  The side
+ *     stream, its events and the kernels' shared-memory attributes are created on the FIRST call
+ *     per device: make one un-captured call of the same shape before capturing;
  *   - every entry point returns a cbo_status (0 = ok); no C++ exception crosses the ABI;
  *   - NaN inputs propagate to NaN outputs (no validation on device);
  *   - re-entrant for distinct workspaces; the model arrays are read-only.
