@@ -608,7 +608,8 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
     // latency path with a ratio estimator (one chunk of <= 32 candidate points): both MLP launches on the side stream
     SideStream* side = nullptr;
     std::unique_lock<std::mutex> side_lock;
-    if (ratio && b * p->q <= cbo::GEMM_SPLITK_MAX_M && C >= b && !hooks) {
+    static const bool side_enabled = [] { const char* e = getenv("CBO_SIDE_STREAM"); return !(e && e[0] == '0'); }();   // A/B switch
+    if (side_enabled && ratio && b * p->q <= cbo::GEMM_SPLITK_MAX_M && C >= b && !hooks) {
         const int dev = cbo::current_device_slot();
         if (dev >= 0) {
             side = &g_side[dev];
