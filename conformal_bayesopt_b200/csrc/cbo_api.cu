@@ -99,6 +99,7 @@ struct Workspace {
     double* nei_values;                               // cNEI only: C x S x G
     double *val_bar, *cv_bar;                         // cNEI gradient only: C x S x G value adjoints, C x nb adjoints of c
     double* splitk;                                   // split-K partial tiles (calls with <= 32 candidate points)
+    double* splitk2;                                  // ... of the probe solves, which run beside the candidates' on the latency path
     double *X3, *adj;                                 // gradient only: C x Np solve scratch, C x ADJ_STRIDE adjoints
     size_t bytes;
 };
@@ -137,6 +138,7 @@ Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, 
     w.stats = c.take<double>(8);
     w.nei_values = c.take<double>((p->kind == CBO_ACQ_NEI || p->kind == CBO_ACQ_JOINT) ? C * p->num_mc * p->grid_res : 1);
     w.splitk = c.take<double>(cbo::gemm_splitk_scratch_doubles((int)Np));
+    w.splitk2 = c.take<double>(cbo::gemm_splitk_scratch_doubles((int)Np));
     const bool nei_kind = p->kind == CBO_ACQ_NEI || p->kind == CBO_ACQ_JOINT;
     w.val_bar = c.take<double>(grad && nei_kind ? C * p->num_mc * p->grid_res : 1);
     w.cv_bar = c.take<double>(grad && nei_kind ? C * cbo::NEI_MAX_NB : 1);
@@ -544,22 +546,28 @@ int cbo_conf_mask_to_bounds_f64(const double* grid, const double* mask, int64_t 
     return CBO_OK;
 }
 
-// Side stream of the latency path (a call with a handful of candidate points, e.g. one SGLD step of 8 restarts x q = 2): the
-// density-ratio MLP over the train points and over the candidates depends on nothing the probe solves produce, so it runs on
-// a library-private stream BESIDE them (fork / join through events: legal under stream capture, the side stream becomes a
-// branch of the caller's graph).  One stream and three timing-free events per device, created on first use; `call_mu`
-// serialises the enqueue of calls that share them.
+// Side streams of the latency path (a call with a handful of candidate points, e.g. one SGLD step of 8 restarts x q = 2).
+// Such a call is a chain of ~20 kernels of 3-15 us; three sub-chains do not depend on each other until late:
+//   caller's stream   scaled inputs -> kernel rows (U, mu) -> pass 1 (V, ||v||^2) -> [T] u^T T -> pass 2 (W) -> [tables, drc] scores ...
+//   st2 (probes)      padded probes -> two split-K passes (T = A^-1 z) -> [dr_train] per-train-point tables
+//   st  (ratio)       density-ratio MLP over the train points (dr_train), over the candidates (drc); in the reverse pass the
+//                     estimator's reverse beside the two reverse solves
+// Fork / join through events only: legal under stream capture (the side streams become branches of the caller's graph), and
+// the caller still sees all work ordered on its own stream when the call returns.  Two streams and five timing-free events
+// per device, created on first use; `call_mu` serialises the enqueue of calls that share them.
 struct SideStream {
     std::mutex mu, call_mu;
-    cudaStream_t st = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr, ev_T = nullptr, ev_tables = nullptr;
     cudaError_t ensure() {
         std::lock_guard<std::mutex> l(mu);
         if (st) return cudaSuccess;
-        cudaStream_t x;
+        cudaStream_t x, y;
         if (cudaError_t e = cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking); e != cudaSuccess) return e;
-        for (cudaEvent_t* ev : {&fork, &join, &join2})
+        if (cudaError_t e = cudaStreamCreateWithFlags(&y, cudaStreamNonBlocking); e != cudaSuccess) return e;
+        for (cudaEvent_t* ev : {&fork, &join, &join2, &ev_T, &ev_tables})
             if (cudaError_t e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming); e != cudaSuccess) return e;
+        st2 = y;
         st = x;
         return cudaSuccess;
     }
@@ -605,45 +613,53 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
     const int tiles_n = Np / cbo::GEMM_BN;
     const int64_t C = pick_chunk(b, p, chunk);
 
-    // latency path with a ratio estimator (one chunk of <= 32 candidate points): both MLP launches on the side stream
+    // latency path (one chunk of <= 32 candidate points): three branches, see SideStream
     SideStream* side = nullptr;
     std::unique_lock<std::mutex> side_lock;
-    static const bool side_enabled = [] { const char* e = getenv("CBO_SIDE_STREAM"); return !(e && e[0] == '0'); }();   // A/B switch
-    if (side_enabled && ratio && b * p->q <= cbo::GEMM_SPLITK_MAX_M && C >= b && !hooks) {
+    const char* side_env = getenv("CBO_SIDE_STREAM");                 // "0": everything on the caller's stream (A/B timing, tests)
+    const bool side_enabled = !(side_env && side_env[0] == '0');
+    // (not with grid refinement: those calls synchronise with the host and run the caller's reduce hook once per pass --
+    // `call_mu` must never be held across a callback -- and their latency is dominated by that anyway)
+    if (side_enabled && b * p->q <= cbo::GEMM_SPLITK_MAX_M && C >= b && !hooks && p->max_grid_refinements == 0) {
         const int dev = cbo::current_device_slot();
         if (dev >= 0) {
             side = &g_side[dev];
             CBO_CUDA(side->ensure());
             side_lock = std::unique_lock<std::mutex>(side->call_mu);
             CBO_CUDA(cudaEventRecord(side->fork, s));
-            CBO_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+            CBO_CUDA(cudaStreamWaitEvent(side->st2, side->fork, 0));
+            if (ratio) CBO_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
         }
     }
-    cudaStream_t s_ratio = side ? side->st : s;
+    cudaStream_t s_ratio = side ? side->st : s;       // density-ratio MLP launches
+    cudaStream_t s_probe = side ? side->st2 : s;      // probe solves and per-train-point tables
 
     // ---- per-call tables: T = A^-1 z[:N], dr_train, a, h0, zb, sum_dr -------------------------------
     {
     TimeScope ts_(T_PREP, s, 7);
     CBO_LAUNCHED(), cbo::k_scale_transpose<<<(Np * d + 255) / 256, 256, 0, s>>>(gp->X, N, Np, d, gp->inv_lengthscale, w.XsT);
-    CBO_LAUNCHED(), cbo::k_pad_probes<<<(Np * Sp + 255) / 256, 256, 0, s>>>(z, N, Np, Sp, w.zp);
+    CBO_LAUNCHED(), cbo::k_pad_probes<<<(Np * Sp + 255) / 256, 256, 0, s_probe>>>(z, N, Np, Sp, w.zp);
     // T^T = Z^T A^-1 (Sp x Np): the probe vectors are Sp more "rows" for the two triangular passes (split-K: a handful of rows)
-    CBO_CUDA(cbo::launch_gemm_tn(w.zp, Np, gp->linv, Np, w.tmp, Np, Sp, Np, Np, cbo::TRI_LOWER, nullptr, s, num_sms(), w.splitk));
-    CBO_CUDA(cbo::launch_gemm_tn(w.tmp, Np, gp->linv_t, Np, w.T, Np, Sp, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms(), w.splitk));
+    double* splitk_probe = side ? w.splitk2 : w.splitk;      // the candidates' split-K passes may run at the same time
+    CBO_CUDA(cbo::launch_gemm_tn(w.zp, Np, gp->linv, Np, w.tmp, Np, Sp, Np, Np, cbo::TRI_LOWER, nullptr, s_probe, num_sms(), splitk_probe));
+    CBO_CUDA(cbo::launch_gemm_tn(w.tmp, Np, gp->linv_t, Np, w.T, Np, Sp, Np, Np, cbo::TRI_UPPER, nullptr, s_probe, num_sms(), splitk_probe));
+    if (side) CBO_CUDA(cudaEventRecord(side->ev_T, side->st2));
     if (ratio) {
         CBO_CUDA(cbo::launch_ratio_mlp(gp->X, N, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2, ratio->b2,
                                        ratio->W3, ratio->b3, 1e-6, w.dr_train, num_sms(), s_ratio));
         if (side) {                                            // k_train_tables below reads dr_train
             CBO_CUDA(cudaEventRecord(side->join, side->st));
-            CBO_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+            CBO_CUDA(cudaStreamWaitEvent(side->st2, side->join, 0));
         }
     } else
-        CBO_LAUNCHED(), cbo::k_fill<<<(Np + 255) / 256, 256, 0, s>>>(w.dr_train, Np, 1.0);
+        CBO_LAUNCHED(), cbo::k_fill<<<(Np + 255) / 256, 256, 0, s_probe>>>(w.dr_train, Np, 1.0);
     if (p->q == 1) {
         const int rows = p->eps_per_candidate ? (int)b : 1;
-        CBO_LAUNCHED(), cbo::k_eps_absmax<<<(rows + 7) / 8, 256, 0, s>>>(eps_grid, rows, G, w.eps_absmax);
+        CBO_LAUNCHED(), cbo::k_eps_absmax<<<(rows + 7) / 8, 256, 0, s_probe>>>(eps_grid, rows, G, w.eps_absmax);
     }
-    CBO_LAUNCHED(), cbo::k_train_tables<<<1, 256, 0, s>>>(gp->alpha, z, w.T, N, Np, Sp, gp->noise, w.dr_train, w.a, w.h0, w.zb,
+    CBO_LAUNCHED(), cbo::k_train_tables<<<1, 256, 0, s_probe>>>(gp->alpha, z, w.T, N, Np, Sp, gp->noise, w.dr_train, w.a, w.h0, w.zb,
                                           w.sum_dr);
+    if (side) CBO_CUDA(cudaEventRecord(side->ev_tables, side->st2));
     }
     CBO_CUDA(cudaGetLastError());
 
@@ -659,15 +675,14 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
         // ---- kernel rows, mu, u^T T; candidate density ratios -------------------------------------
         {
             TimeScope ts_(T_ROWS, s, ratio ? 2 : 1);
+            // latency path: the rows do not wait for T (the probe branch); u^T T follows between the two passes
             CBO_CUDA(cbo::launch_kernel_rows(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->mean,
-                                             gp->alpha, w.T, Sp, w.UW, w.mu, w.ut, num_sms(), s, splitk != nullptr));
+                                             gp->alpha, side ? nullptr : w.T, Sp, w.UW, w.mu, side ? nullptr : w.ut, num_sms(), s,
+                                             splitk != nullptr));
             if (ratio)
                 CBO_CUDA(cbo::launch_ratio_mlp(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2, ratio->b2,
                                                ratio->W3, ratio->b3, 1e-6, w.drc, num_sms(), s_ratio));
-            if (side) {                                        // joined ahead of the score kernel, the first reader of drc
-                CBO_CUDA(cudaEventRecord(side->join2, side->st));
-                CBO_CUDA(cudaStreamWaitEvent(s, side->join2, 0));
-            }
+            if (side && ratio) CBO_CUDA(cudaEventRecord(side->join2, side->st));
             CBO_CUDA(cudaGetLastError());
         }
         // ---- v = L^-1 u (+ ||v||^2 partials), w = L^-T v ------------------------------------------
@@ -675,9 +690,17 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             TimeScope ts_(T_GEMM1, s, 1);
             CBO_CUDA(cbo::launch_gemm_tn(w.UW, Np, gp->linv, Np, w.V, Np, n, Np, Np, cbo::TRI_LOWER, w.rn, s, num_sms(), splitk));
         }
+        if (side) {   // u^T T from the stored rows, before pass 2 overwrites them (same accumulation order as the fused kernel)
+            CBO_CUDA(cudaStreamWaitEvent(s, side->ev_T, 0));
+            CBO_LAUNCHED(), cbo::k_ut_small<<<n, cbo::ROWS_SMALL_THREADS, 0, s>>>(w.UW, N, Np, w.T, Sp, w.ut);
+        }
         {
             TimeScope ts_(T_GEMM2, s, 1);
             CBO_CUDA(cbo::launch_gemm_tn(w.V, Np, gp->linv_t, Np, w.UW, Np, n, Np, Np, cbo::TRI_UPPER, nullptr, s, num_sms(), splitk));
+        }
+        if (side) {   // join: per-train-point tables (probe branch) and the candidates' density ratios ahead of the score kernel
+            CBO_CUDA(cudaStreamWaitEvent(s, side->ev_tables, 0));
+            if (ratio) CBO_CUDA(cudaStreamWaitEvent(s, side->join2, 0));
         }
 
         // ---- scores / rank / mask / integration ----------------------------------------------------

@@ -225,6 +225,40 @@ k_kernel_rows_small(const double* __restrict__ Xq, int n, const double* __restri
     }
 }
 
+// ut[c, s] = sum_i U[c, i] T[s, i] from the STORED kernel rows: the probe correction of k_kernel_rows_small as a kernel of
+// its own (latency path: the rows are computed while T = A^-1 z is still being solved for on another stream).  Same
+// per-thread order, warp reduction and warp order as the fused accumulation, so both give the same bits.
+__global__ void __launch_bounds__(ROWS_SMALL_THREADS)
+k_ut_small(const double* __restrict__ U, int N, int Np, const double* __restrict__ T, int Sp, double* __restrict__ ut) {
+    __shared__ double s_red[ROWS_SMALL_THREADS / 32][MAX_SP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x;
+    double acc_ut[MAX_SP];
+#pragma unroll
+    for (int s = 0; s < MAX_SP; ++s) acc_ut[s] = 0.0;
+    for (int i = tid; i < Np; i += ROWS_SMALL_THREADS) {
+        if (i < N) {
+            const double kv = U[int64_t(c) * Np + i];
+#pragma unroll
+            for (int s = 0; s < MAX_SP; ++s)
+                if (s < Sp) acc_ut[s] = fma(kv, T[int64_t(s) * Np + i], acc_ut[s]);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < MAX_SP; ++s)
+        if (s < Sp) {
+            double v = warp_sum(acc_ut[s]);
+            if (lane == 0) s_red[warp][s] = v;
+        }
+    __syncthreads();
+    if (tid < Sp) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < ROWS_SMALL_THREADS / 32; ++w) v += s_red[w][tid];
+        ut[int64_t(c) * Sp + tid] = v;
+    }
+}
+
 inline size_t rows_smem_bytes(int Np, int d, int Sp, bool stage) {
     return sizeof(double) * (16 + size_t(ROWS_WARPS) * ROWS_CPW * d + (stage ? size_t(Np) * (d + 1 + Sp) : 0));
 }

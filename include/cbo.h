@@ -27,12 +27,12 @@
  *   - the caller owns every buffer; the library allocates no device memory, ever;
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); the only host
  *     synchronisation is one per grid-refinement pass when max_grid_refinements > 0 (the
- *     reference synchronises there too, helpers.py:151-152,177).  A call with a ratio estimator and
- *     at most 32 candidate points (an SGLD step) also runs the estimator's launches on a
- *     library-private side stream that is forked from `stream` and joined back into it through
+ *     reference synchronises there too, helpers.py:151-152,177).  A call with at most 32 candidate
+ *     points and no grid refinement (an SGLD step) also uses two library-private side streams (probe
+ *     solves; ratio estimator) that are forked from `stream` and joined back into it through
  *     events before the call returns: the caller still only sees work ordered on `stream`, and the
- *     call can be captured into a CUDA graph (the side stream becomes a branch of it).  The side
- *     stream, its events and the kernels' shared-memory attributes are created on the FIRST call
+ *     call can be captured into a CUDA graph (the side streams become branches of it).  The side
+ *     streams, their events and the kernels' shared-memory attributes are created on the FIRST call
  *     per device: make one un-captured call of the same shape before capturing;
  *   - every entry point returns a cbo_status (0 = ok); no C++ exception crosses the ABI;
  *   - NaN inputs propagate to NaN outputs (no validation on device);

@@ -477,3 +477,47 @@ def test_pair_and_warp_specialised_score_kernels_are_bit_identical(monkeypatch, 
                                              eps_mc=inp["eps_mc"], u_rand=inp["u_rand"], ratio=ratio, **kw)
     assert torch.allclose(res["1"]["acq"].cpu(), want["acq"], rtol=1e-6, atol=1e-9)
     assert torch.allclose(res["1"]["conf_pred_mask"].cpu(), want["mask"][:, :, 0], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("q,ratio_on,kind", [(1, True, "ucb"), (2, True, "ucb"), (2, False, "ei"), (1, True, "nei")])
+def test_latency_path_branches_give_the_bits_of_the_single_stream_path(monkeypatch, q, ratio_on, kind):
+    """A call with <= 32 candidate points forks into three stream branches (probe solves | kernel rows and candidate solves |
+    ratio estimator; csrc/cbo_api.cu SideStream) and joins them through events.  The branches only reorder independent work:
+    values and gradient rows must equal those of the same call issued on one stream (CBO_SIDE_STREAM=0), bit for bit, also
+    when the call is repeated back to back (buffer reuse across calls) and replayed as a CUDA graph."""
+    from conformal_bayesopt_b200 import ops
+    dev = _dev()
+    N, d, b, G = 150, 5, 8, 32
+    p = make_problem(N, d, seed=31)
+    inp = make_inputs(N, d, b, q, G, S=2, seed=31)
+    ratio = ogp.make_ratio_mlp(d) if ratio_on else None
+    rw = ops.RatioWeights(*[t.to(dev) for t in (ratio.W1, ratio.b1, ratio.W2, ratio.b2, ratio.W3, ratio.b3)]) if ratio_on else None
+    kw = dict(kind=kind, alpha=0.1, temp=3e-2, grid_res=G, randomized=True, optimistic=True, beta_prime=1.0, best_f=0.3)
+    st = _state(p, dev)
+    if kind == "nei":
+        kw["nei_baseline"] = ops.NeiBaseline.build(st, p["X"][:6].to(dev))
+    eg = inp["eps_grid"].to(dev) if q > 1 else inp["eps_grid"][:, 0].to(dev)
+    em = inp["eps_mc"].to(dev) if q > 1 else inp["eps_mc"][:, :, 0].to(dev)
+    u = inp["u_rand"].to(dev) if q > 1 else inp["u_rand"][:, :, 0].to(dev)
+    if kind == "nei":
+        em = torch.randn(2, G, 6 + q, dtype=torch.float64, generator=torch.Generator().manual_seed(3)).to(dev)
+
+    Xd, zd = inp["Xq"].to(dev), inp["z"].to(dev)
+
+    def call():
+        return ops.conformal_acq(st, Xd, eps_grid=eg, z=zd, eps_mc=em, u_rand=u, ratio=rw, want_grad=True, **kw)
+    monkeypatch.setenv("CBO_SIDE_STREAM", "0")
+    ref = call()
+    monkeypatch.setenv("CBO_SIDE_STREAM", "1")
+    for _ in range(3):
+        got = call()
+        torch.cuda.synchronize()
+        assert torch.equal(got["acq"], ref["acq"]) and torch.equal(got["dacq_dX"], ref["dacq_dX"])
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):                 # every input is a device tensor made before the capture
+        out = call()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["acq"], ref["acq"]) and torch.equal(out["dacq_dX"], ref["dacq_dX"])
