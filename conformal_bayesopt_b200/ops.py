@@ -75,7 +75,7 @@ def _stream() -> int:
 
 @dataclass
 class NeiBaseline:
-    """Device arrays of the cNEI baseline (acquisitions.py:117-122), built once per acquisition object with torch.linalg."""
+    """Device arrays of the cNEI baseline (acquisitions.py:117-122), built once per acquisition object (see `build`)."""
     Xb: torch.Tensor     # (nb, d)
     KbX: torch.Tensor    # (nb, Np)
     Sbb: torch.Tensor    # (nb, nb)
