@@ -29,8 +29,6 @@ constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_PREFETCH = 2;         // tiles in flight; STAGES - PREFETCH = tiles of slack between warps
 constexpr int GEMM_THREADS = 256;
 constexpr int GEMM_MGROUP = 64;          // m-tiles per L2 group (see the tile order in the kernel)
-constexpr int GEMM_STAGE_DOUBLES = (GEMM_BM + GEMM_BN) * GEMM_LDS;
-constexpr size_t GEMM_SMEM_BYTES = size_t(GEMM_STAGES) * GEMM_STAGE_DOUBLES * sizeof(double) + 2 * GEMM_STAGES * sizeof(uint64_t);
 
 enum { TRI_FULL = 0, TRI_LOWER = 1, TRI_UPPER = 2 };
 
@@ -60,8 +58,13 @@ __device__ __forceinline__ void gemm_load_stage(double* sA, double* sB, const do
 
 // MF = 8-row DMMA fragments per warp in m: CTA tile (16 MF) x 128.  MF = 8 is the throughput configuration; smaller MF
 // keep all SMs busy (and cut the wasted rows) when there are only a few hundred candidate rows.
-template <int MF>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// STAGES / PER_SM: ring depth and co-resident CTAs per SM.  <8, 4, 1> is the 128 x 128 tile alone on its SM (160 KB ring, 202
+// registers) -- the configuration in use.  <4, 3, 2>, TWO 64 x 128 tiles per SM (92 KB rings, 128 registers) so that one CTA's
+// MMAs cover the other's launch, ring fill and epilogue stores (the 4.3 us of fixed cost per tile), was measured and is 5 %
+// SLOWER (2.280 against 2.170 ms per triangular pass of 65536 rows: the smaller tile's main loop loses more than the overlap
+// wins; profiles/r02_gemm_shape_time.log).
+template <int MF, int STAGES = GEMM_STAGES, int PER_SM = 1>
+__global__ void __launch_bounds__(GEMM_THREADS, PER_SM)
 k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
               double* __restrict__ C, int64_t ldc, int M, int Nn, int K, int tri,
               double* __restrict__ rownorm_partial, int splits, int64_t part_stride) {
@@ -72,7 +75,8 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     // triangular skipping on the diagonal block (below) loads every sub-partition's fp64 pipe equally.
     const int wm = warp >> 2, wn = (warp < 4) ? warp : 7 - warp;
     constexpr int BM = 16 * MF;
-    constexpr int PF = GEMM_PREFETCH;
+    constexpr int SD = (BM + GEMM_BN) * GEMM_LDS;          // doubles per ring stage (A tile + B tile, padded rows)
+    constexpr int PF = (STAGES > GEMM_PREFETCH) ? GEMM_PREFETCH : STAGES - 1;
     const int tiles_m = (M + BM - 1) / BM;
     const int tiles_n = Nn / GEMM_BN;
     // longest-K tiles first: lower -> last n-tile first; upper / full -> first n-tile first
@@ -112,17 +116,17 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     // copies of the tile in stage s have landed (cp.async.mbarrier.arrive); empty[s] completes when all 8 warps have
     // consumed it.  Tiles are prefetched PREFETCH ahead into a ring of STAGES, so warps may drift apart by
     // STAGES - PREFETCH tiles (absorbs the triangular imbalance on the diagonal block and scheduling jitter).
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(GEMM_STAGES) * GEMM_STAGE_DOUBLES);
-    uint64_t* empty = full + GEMM_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * SD);
+    uint64_t* empty = full + STAGES;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full[s], GEMM_THREADS); mbar_init(&empty[s], GEMM_THREADS / 32); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], GEMM_THREADS); mbar_init(&empty[s], GEMM_THREADS / 32); }
     }
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < PF; ++s) {
         if (s < nk) {
-            double* sA = smem + s * GEMM_STAGE_DOUBLES;
+            double* sA = smem + s * SD;
             gemm_load_stage<BM>(sA, sA + BM * GEMM_LDS, A, lda, B, ldb, m0, n0, kpos(s), M, tid);
             cp_async_mbar_arrive(&full[s]);
         }
@@ -133,22 +137,22 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
         {   // producer side: tile kt + PREFETCH goes into the stage last used by tile kt + PREFETCH - STAGES
             const int nt = kt + PF;
             if (nt < nk) {
-                const int st = nt % GEMM_STAGES;
-                mbar_wait(&empty[st], ((nt / GEMM_STAGES) & 1) ^ 1);
-                double* sA = smem + st * GEMM_STAGE_DOUBLES;
+                const int st = nt % STAGES;
+                mbar_wait(&empty[st], ((nt / STAGES) & 1) ^ 1);
+                double* sA = smem + st * SD;
                 gemm_load_stage<BM>(sA, sA + BM * GEMM_LDS, A, lda, B, ldb, m0, n0, kpos(nt), M, tid);
                 cp_async_mbar_arrive(&full[st]);
             }
         }
-        const int st = kt % GEMM_STAGES;
+        const int st = kt % STAGES;
         // On the diagonal 128 x 128 block of the triangular factor this warp's 32 columns see only zeros for part of
         // the K range: lower  -> k < n_warp_end,  upper -> k + BK > n_warp_begin.  Skip those MMAs (warp-uniform).
         const int k0 = kpos(kt);
         const bool skip = (tri == TRI_LOWER && k0 >= n0 + 32 * (wn + 1)) || (tri == TRI_UPPER && k0 + GEMM_BK <= n0 + 32 * wn);
         if (!skip) {
-            mbar_wait(&full[st], (kt / GEMM_STAGES) & 1);
-            const double* sA = smem + st * GEMM_STAGE_DOUBLES + (wm * (8 * MF) + fr) * GEMM_LDS + fk;
-            const double* sB = smem + st * GEMM_STAGE_DOUBLES + BM * GEMM_LDS + (wn * 32 + fr) * GEMM_LDS + fk;
+            mbar_wait(&full[st], (kt / STAGES) & 1);
+            const double* sA = smem + st * SD + (wm * (8 * MF) + fr) * GEMM_LDS + fk;
+            const double* sB = smem + st * SD + BM * GEMM_LDS + (wn * 32 + fr) * GEMM_LDS + fk;
             // rel = position of this k-tile inside the warp's own 32 x 32 diagonal sub-block (0 or 16), else outside [0, 32)
             const int rel = (tri == TRI_FULL) ? -1 : k0 - (n0 + 32 * wn);
             if (rel >= 0 && rel < 32) {
@@ -229,19 +233,19 @@ k_gemm_tn_f64(const double* __restrict__ A, int64_t lda, const double* __restric
     }
 }
 
-template <int MF>
+__host__ __device__ constexpr size_t gemm_smem_bytes(int MF, int stages) {
+    return size_t(stages) * (16 * MF + GEMM_BN) * GEMM_LDS * sizeof(double) + 2 * size_t(stages) * sizeof(uint64_t);
+}
+
+template <int MF, int STAGES = GEMM_STAGES, int PER_SM = 1>
 inline cudaError_t launch_gemm_tn_t(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                                     int M, int Nn, int K, int tri, double* rownorm_partial, cudaStream_t stream,
                                     int splits = 1, int64_t part_stride = 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tn_f64<MF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)GEMM_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    constexpr size_t smem = gemm_smem_bytes(MF, STAGES);
+    static SmemOptIn optin;                      // per (function, device)
+    if (cudaError_t e = optin.ensure(k_gemm_tn_f64<MF, STAGES, PER_SM>, smem); e != cudaSuccess) return e;
     int tiles_m = (M + 16 * MF - 1) / (16 * MF), tiles_n = Nn / GEMM_BN;
-    CBO_LAUNCHED(), k_gemm_tn_f64<MF><<<dim3(tiles_m * tiles_n, splits), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(
+    CBO_LAUNCHED(), k_gemm_tn_f64<MF, STAGES, PER_SM><<<dim3(tiles_m * tiles_n, splits), GEMM_THREADS, smem, stream>>>(
         A, lda, B, ldb, C, ldc, M, Nn, K, tri, rownorm_partial, splits, part_stride);
     return cudaGetLastError();
 }
@@ -298,7 +302,7 @@ inline cudaError_t launch_gemm_tn(const double* A, int64_t lda, const double* B,
     // pick the largest m-tile that still yields ~2 CTAs per SM; few rows -> small tiles (latency, no wasted rows)
     const int tiles_n = Nn / GEMM_BN;
     auto ctas = [&](int bm) { return ((M + bm - 1) / bm) * tiles_n; };
-    if (ctas(128) >= 2 * num_sms || M > 2048)
+    if (ctas(128) >= 2 * num_sms || M > 2048)   // (launch_gemm_tn_t<4, 3, 2>, two 64 x 128 tiles per SM, was measured here: 5 % slower)
         return launch_gemm_tn_t<8>(A, lda, B, ldb, C, ldc, M, Nn, K, tri, rownorm_partial, stream);
     if (ctas(64) >= 2 * num_sms || M > 64)
         return launch_gemm_tn_t<4>(A, lda, B, ldb, C, ldc, M, Nn, K, tri, rownorm_partial, stream);
