@@ -13,7 +13,8 @@ Randomness is injected, never re-seeded: sampler base samples through the stand-
 patching `torch.rand` for the one (n, 8) draw of helpers.py:399, the randomised step by patching `Bernoulli.sample` to
 `u < probs` (helpers.py:311).
 
-Usage:  python oracle/make_golden_path.py [--only NAME]   (writes tests/golden/ref_path.pt, ref_path_n1024.pt)
+Usage:  python oracle/make_golden_path.py [--only NAME] [--ehvi]   (writes tests/golden/ref_path.pt, ref_path_n1024.pt,
+        ref_path_ehvi.pt)
 """
 import argparse
 import contextlib
@@ -242,6 +243,71 @@ def run_coverage_case(ref, name, *, N, d, n, G, temp, alpha, refine, randomized,
                          conf_pred_mask=captured["mask"], lb=captured["lb"], ub=captured["ub"]))
 
 
+def run_ehvi_case(ref, name, *, N, d, b, q, G, temp, alpha, S=2, randomized=False, ratio=False, optimistic=False, seed=0,
+                  noise=1e-2):
+    """cEHVI (mobo_acquisitions.py:24-45) on a two-output model: the reference's `_conformal_fwd` runs up to the call of
+    `_conformal_integration`, whose ARGUMENTS are recorded -- `values` = the reference's `_nonconformal_fwd` (`_compute_qehvi`
+    under every refit model: the cEHVI inner expectation, (b, G)), the masks, the grid log-density, the optimistic and ood
+    masks.  The integration itself cannot be pinned: for these shapes the reference's own function raises unless b in
+    {1, G} and then returns a (G,) tensor."""
+    from botorch.sampling import IIDNormalSampler
+    from conformal_bayesopt_b200.synthetic import make_problem
+    from oracle.mobo import box_decomposition_2d
+    t0 = time.time()
+    t = 2
+    p = make_problem(N, d, seed=seed, noise=noise, ard_spread=0.1)
+    g = torch.Generator().manual_seed(900 + seed)
+    extra = torch.sin(3.0 * p["X"].sum(-1)) + 0.1 * torch.randn(N, generator=g, dtype=torch.float64)
+    Y = torch.stack([p["y"], (extra - extra.mean()) / extra.std()], dim=-1)
+    ls = torch.stack([p["lengthscale"] * (1.0 + 0.3 * k) for k in range(t)])
+    os_ = torch.tensor([1.0 + 0.5 * k for k in range(t)], dtype=torch.float64)
+    nz = torch.tensor([noise * (1.0 + k) for k in range(t)], dtype=torch.float64)
+    mc_ = torch.tensor([0.1 * k for k in range(t)], dtype=torch.float64)
+    prob = dict(X=p["X"], Y=Y, y=Y[:, 0], mean=mc_, lengthscale=ls, outputscale=os_, noise=nz)
+    model = make_model(prob, t=t)
+    est, W = make_ratio(ref, d) if ratio else (None, None)
+    Xq = torch.rand(b, q, d, generator=g, dtype=torch.float64)
+    eps_grid = torch.randn(G, 1, q, t, generator=g, dtype=torch.float64)
+    eps_mc = torch.randn(S, 1, G, q, t, generator=g, dtype=torch.float64)
+    z = 2.0 * ((torch.rand(N + q, 8, generator=g) > 0.5).double() - 0.5)
+    u = torch.rand(b, G, t, q, generator=g, dtype=torch.float64)          # layout of ub_prob for a batched model
+    ref_point = Y.min(0).values - 0.1
+    lower, upper = box_decomposition_2d(ref_point, Y)
+    part = types.SimpleNamespace(get_hypercell_bounds=lambda: torch.stack([lower, upper]))
+    acq = ref.mobo_acquisitions.qConformalExpectedHypervolumeImprovement(
+        alpha, temp, G, 0, est, optimistic, IIDNormalSampler(G), randomized, model=model, ref_point=ref_point.tolist(),
+        partitioning=part, sampler=IIDNormalSampler(S, batch_range=(0, -3)))
+    captured = {}
+    real_int = ref.acquisitions._conformal_integration
+
+    def spy(values, conf_pred_mask, grid_logp, alpha_, opt_mask, ood_mask):
+        captured.update(values=values.detach().clone(), conf_pred_mask=conf_pred_mask.detach().clone(),
+                        grid_logp=grid_logp.detach().clone(), opt_mask=opt_mask.detach().clone(),
+                        ood_mask=ood_mask.detach().clone().to(torch.float64))
+        return values.new_zeros(1, values.shape[0], 1)            # the literal integration raises for these shapes
+
+    ref.acquisitions._conformal_integration = spy
+    try:
+        draws = {tuple(eps_grid.shape): eps_grid, tuple(eps_mc.shape): eps_mc}
+        with injected(z=z, u_rand=u if randomized else None, draws=draws) as used:
+            acq._conformal_fwd(Xq)
+    finally:
+        ref.acquisitions._conformal_integration = real_int
+    assert "values" in captured and captured["values"].shape == (b, G), captured.get("values", torch.zeros(0)).shape
+    print(f"  {name}: cEHVI values {tuple(captured['values'].shape)} in {time.time() - t0:.1f}s, draws={used['draws']}, "
+          f"range [{float(captured['values'].min()):.4g}, {float(captured['values'].max()):.4g}]", flush=True)
+    return dict(name=name, N=N, d=d, b=b, q=q, G=G, S=S, t=t, temp=temp, alpha=alpha, randomized=randomized, ratio=ratio,
+                optimistic=optimistic, problem=prob, Xq=Xq, eps_grid=eps_grid, eps_mc=eps_mc, z=z,
+                u_rand=u if randomized else None, ref_point=ref_point, cell_lower=lower, cell_upper=upper,
+                ratio_weights=[w.clone() for w in W] if W is not None else None, out=captured)
+
+
+EHVI_CASES = dict(
+    ehvi_q1=dict(N=40, d=2, b=12, q=1, G=32, temp=3e-2, alpha=0.1, S=2, seed=51),
+    ehvi_q2_rand=dict(N=36, d=3, b=7, q=2, G=16, temp=3e-2, alpha=0.15, S=3, randomized=True, ratio=True, optimistic=True, seed=52),
+)
+
+
 BP = math.sqrt(0.2 * math.pi / 2)
 
 ACQ_CASES = dict(
@@ -282,15 +348,21 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     ap.add_argument("--skip-big", action="store_true")
+    ap.add_argument("--ehvi", action="store_true", help="only (re)generate tests/golden/ref_path_ehvi.pt")
     args = ap.parse_args()
     torch.set_default_dtype(torch.float64)       # the north star fixes fp64 (the reference's scripts default to fp32)
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
     sel = lambda cases: {k: v for k, v in cases.items() if args.only in (None, k)}
+    if args.ehvi:
+        torch.save(dict(ehvi=[run_ehvi_case(ref, k, **v) for k, v in EHVI_CASES.items()]), os.path.join(OUT, "ref_path_ehvi.pt"))
+        return
     small = dict(acq=[run_acq_case(ref, k, **v) for k, v in sel(ACQ_CASES).items()],
                  coverage=[run_coverage_case(ref, k, **v) for k, v in sel(COV_CASES).items()])
     if args.only is None:
         torch.save(small, os.path.join(OUT, "ref_path.pt"))
+    if args.only is None:
+        torch.save(dict(ehvi=[run_ehvi_case(ref, k, **v) for k, v in EHVI_CASES.items()]), os.path.join(OUT, "ref_path_ehvi.pt"))
     if not args.skip_big:
         big = dict(acq=[run_acq_case(ref, k, **v) for k, v in sel(BIG_CASES).items()], coverage=[])
         if args.only is None:

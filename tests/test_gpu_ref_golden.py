@@ -188,3 +188,54 @@ def test_multi_output_bands_and_coverage_intent_layout(name):
     with pytest.raises(NotImplementedError):
         helpers.construct_conformal_bands(states, c["X_holdout"].to(DEV)[:, None], c["alpha"], c["temp"], G, 0, gs, None,
                                           label_layout="reference")
+
+
+@pytest.mark.parametrize("name", ["ehvi_q1", "ehvi_q2_rand"])
+def test_cehvi_inner_expectation_against_reference_source_golden(name):
+    """qConformalExpectedHypervolumeImprovement on a two-output model against what the reference's OWN `_conformal_fwd` hands
+    to `_conformal_integration` (oracle/make_golden_path.py::run_ehvi_case): `values` (b, G) -- `_compute_qehvi` under every
+    refit model, the cEHVI inner expectation named by the north star (`k_ehvi_q`) -- the joint grid log-density and the
+    optimistic mask.  (The masks of that golden follow the reference's label scramble for t > 1, App. C-6: they are checked
+    on the band-construction path, `helpers.construct_conformal_bands(label_layout="reference")`; the integration itself is
+    unpinned, App. C-5.)"""
+    from conformal_bayesopt_b200 import GPModelState
+    from conformal_bayesopt_b200.mobo_acquisitions import qConformalExpectedHypervolumeImprovement
+    from conformal_bayesopt_b200.ratio_estimation import RatioEstimator
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    c = [x for x in _cases("ref_path_ehvi.pt")["ehvi"] if x["name"] == name][0]
+    p, want = c["problem"], c["out"]
+    b, q, G, S, t = c["b"], c["q"], c["G"], c["S"], c["t"]
+    states = [GPModelState.fit_fixed(p["X"], p["Y"][:, k], float(p["mean"][k]), p["lengthscale"][k], float(p["outputscale"][k]),
+                                     float(p["noise"][k]), device=DEV) for k in range(t)]
+    est = None
+    if c["ratio"]:
+        est = RatioEstimator(in_size=c["d"], device=torch.device(DEV), dtype=torch.float64)
+        lin = [m for m in est._target_network if isinstance(m, torch.nn.Linear)]
+        with torch.no_grad():
+            for k, layer in enumerate(lin):
+                layer.weight.copy_(c["ratio_weights"][2 * k])
+                layer.bias.copy_(c["ratio_weights"][2 * k + 1])
+    # a non-interleaved MultitaskMultivariateNormal consumes (..., q, t) base samples as the flat task-major event (App. B)
+    remap = lambda e: e.reshape(*e.shape[:-2], e.shape[-1], e.shape[-2]).transpose(-1, -2).contiguous()
+    gs = IIDNormalSampler(G)
+    gs.set_base_samples(remap(c["eps_grid"][:, 0]))
+    mc = IIDNormalSampler(S, batch_range=(0, -3))
+    mc.set_base_samples(remap(c["eps_mc"][:, 0]))
+    acq = qConformalExpectedHypervolumeImprovement(alpha=c["alpha"], temp=c["temp"], grid_res=G, max_grid_refinements=0,
+                                                   ratio_estimator=est, optimistic=c["optimistic"], grid_sampler=gs,
+                                                   randomized=c["randomized"], model=states, ref_point=c["ref_point"],
+                                                   partitioning=(c["cell_lower"], c["cell_upper"]), sampler=mc)
+    acq.fixed_probes = c["z"]
+    acq.fixed_uniforms = c["u_rand"].permute(0, 1, 3, 2).contiguous().to(DEV) if c["randomized"] else None
+    with torch.no_grad():
+        val = acq(c["Xq"].to(DEV))
+    assert val.shape == (b,) and torch.isfinite(val).all()
+    got = acq.last_outputs
+    values = got["values"].cpu().reshape(b, G)
+    assert torch.allclose(values, want["values"], rtol=RTOL, atol=1e-9), float((values - want["values"]).abs().max())
+    logp = sum(o["grid_logp"].cpu().reshape(b, G) for o in got["per_output"])
+    assert torch.allclose(logp, want["grid_logp"].reshape(b, G), rtol=RTOL, atol=1e-9)
+    if c["optimistic"]:
+        for k, o in enumerate(got["per_output"]):
+            opt = (o["target_grid"].cpu().reshape(b, G, q) >= o["post_mean"].cpu().reshape(b, 1, q)).double()
+            assert torch.equal(opt, want["opt_mask"][..., k].double())

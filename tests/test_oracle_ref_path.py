@@ -142,3 +142,46 @@ def test_multi_output_intent_layout_is_t_independent_single_output_problems():
         assert torch.allclose(grid[..., k], g1) and torch.allclose(mask[..., k], m1) and torch.allclose(ood[..., k], o1)
         lp = lp + l1
     assert torch.allclose(logp, lp)
+
+
+@pytest.mark.parametrize("name", ["ehvi_q1", "ehvi_q2_rand"])
+def test_cehvi_inner_expectation_against_reference_source_golden(name):
+    """cEHVI (mobo_acquisitions.py:24-45) on a two-output model.  The golden holds the ARGUMENTS with which the reference's
+    own `_conformal_fwd` calls `_conformal_integration` (oracle/make_golden_path.py::run_ehvi_case): `values` = the
+    reference's `_nonconformal_fwd` -- `_compute_qehvi` under every refit model, the cEHVI inner expectation (b, G) -- the
+    conformal masks, the joint grid log-density, the optimistic mask.  oracle/mobo.py reproduces values / log-density /
+    optimistic mask, oracle/multi.py (label_layout='reference') the masks.  The integration that follows is unpinned: the
+    reference's function raises for these shapes."""
+    from oracle import mobo, multi
+    c = [x for x in load("ref_path_ehvi.pt")["ehvi"] if x["name"] == name][0]
+    gps = _multi_gps(c)
+    ratio = ogp.RatioMLP(*c["ratio_weights"]) if c["ratio"] else None
+    want = c["out"]
+    b, q, G = c["b"], c["q"], c["G"]
+    # A non-interleaved MultitaskMultivariateNormal consumes its (..., q, t) base samples as the FLAT task-major event
+    # (oracle/_shim/gpytorch/distributions.py, SURVEY.md App. B): entry (point j, task k) gets flat[k * q + j]
+    remap = lambda e: e.reshape(*e.shape[:-2], e.shape[-1], e.shape[-2]).transpose(-1, -2)
+    eps_grid = remap(c["eps_grid"][:, 0])                                   # (G, q, t)
+    eps_mc = remap(c["eps_mc"][:, 0])                                       # (S, G, q, t)
+    u_qm = c["u_rand"].permute(0, 1, 3, 2) if c["randomized"] else None     # (b, G, t, q) -> (b, G, q, m)
+    got = mobo.cehvi(gps, c["Xq"], alpha=c["alpha"], temp=c["temp"], grid_res=G, eps_grid=eps_grid, z=c["z"], eps_mc=eps_mc,
+                     cell_lower=c["cell_lower"], cell_upper=c["cell_upper"], ratio=ratio, randomized=c["randomized"],
+                     u_rand=u_qm, optimistic=c["optimistic"], impl="dense")
+    assert want["values"].abs().max() > 1e-2
+    assert torch.allclose(got["values"], want["values"], rtol=RTOL, atol=1e-9), (got["values"] - want["values"]).abs().max()
+    assert torch.allclose(got["logp"], want["grid_logp"].reshape(b, G), rtol=RTOL, atol=1e-9)
+    closed = mobo.cehvi(gps, c["Xq"], alpha=c["alpha"], temp=c["temp"], grid_res=G, eps_grid=eps_grid, z=c["z"], eps_mc=eps_mc,
+                        cell_lower=c["cell_lower"], cell_upper=c["cell_upper"], ratio=ratio, randomized=c["randomized"],
+                        u_rand=u_qm, optimistic=c["optimistic"], impl="closed")
+    assert torch.allclose(closed["values"], want["values"], rtol=RTOL, atol=1e-9)
+    # the masks the reference hands to its integration are those of its (label-scrambling) multi-output band construction
+    grid, logp, mask, ood = multi.construct_conformal_bands(gps, c["Xq"], c["alpha"], c["temp"], G, 0, eps_grid, c["z"],
+                                                            ratio=ratio, randomized=c["randomized"], u_rand=c["u_rand"],
+                                                            label_layout="reference")
+    assert torch.allclose(mask, want["conf_pred_mask"], rtol=0, atol=1e-6), (mask - want["conf_pred_mask"]).abs().max()
+    assert torch.allclose(ood, want["ood_mask"], rtol=RTOL, atol=1e-12)
+    if c["optimistic"]:
+        mu = torch.stack([gp.mean + gp.k(c["Xq"], gp.X) @ gp.alpha for gp in gps], -1)      # (b, q, t)
+        assert torch.equal((grid >= mu.unsqueeze(1)).double(), want["opt_mask"].double())
+    else:
+        assert bool((want["opt_mask"] == 1).all())
