@@ -1,4 +1,7 @@
-"""cEHVI oracle (test infrastructure only; "parity unpinned").
+"""cEHVI oracle (test infrastructure only).  Pinning: the inner expectation (`values`, b x G), the joint grid log-density and
+the optimistic mask match what the reference's own `_conformal_fwd` hands to `_conformal_integration` (executed over
+oracle/_shim: tests/golden/ref_path_ehvi.pt, tests/test_oracle_ref_path.py); the integration over the grid, the per-output
+("intent") label layout of the masks and cNEHVI's baseline box decompositions are "parity unpinned" (see below).
 
 qConformalExpectedHypervolumeImprovement (conformalbo/mobo_acquisitions.py:24-45) and
 qConformalNoisyExpectedHypervolumeImprovement (:184-219) for joint batches of q points and m independent single-output GPs.  The reference's own `_conformal_integration` collapses the wrong axes for EHVI-shaped values and
