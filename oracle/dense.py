@@ -191,13 +191,23 @@ def nonconformal_values(gp, refit, q, eps_mc, kind, *, beta_prime=None, best_f=N
 
 
 def construct_conformal_bands(gp: GPState, Xq, alpha, temp, grid_res, max_grid_refinements, eps_grid, z,
-                              ratio=None, randomized=False, u_rand=None):
+                              ratio=None, randomized=False, u_rand=None, lazy_prior_grad=False):
     """helpers.py:94-202 (t=1).  Returns target_grid (b,G,q), weights (b,G), conf_pred_mask (b,G,q),
     refit (dense caches of the kept pass), ood_mask (b,G,q)."""
     assert Xq.ndim >= 3 and grid_res >= 2
     b, q, _ = Xq.shape
     with torch.no_grad():                                            # helpers.py:118-119
         mean, cov = posterior(gp, Xq, observation_noise=True)
+    if lazy_prior_grad and Xq.requires_grad:
+        # GRADIENT SEMANTICS ONLY (values unchanged).  helpers.py:118-119 builds y_post under torch.no_grad(), but GPyTorch
+        # returns the predictive covariance LAZILY: the prior block k(X, X) is a lazily evaluated kernel that is only
+        # evaluated when the grid is sampled, after the no_grad block has exited, and so tracks d/dX; the correction term
+        # k(X, X_train) A^-1 k(X_train, X) was solved for eagerly and is a constant (SURVEY.md App. B; oracle/_shim restates
+        # exactly this).  For q = 1 the prior block is the constant outputscale and nothing leaks; for q >= 2 the grid
+        # depends on X through k(x_j, x_k).  The product (and the default of this oracle) treats the grid as the constant
+        # the no_grad block intends; this switch reproduces the reference's autograd to 1e-6 (tests/test_oracle_ref_path.py).
+        Kxx = gp.k(Xq, Xq)
+        cov = cov + (Kxx - Kxx.detach())
     if eps_grid.ndim == 2:
         eps_grid = eps_grid.unsqueeze(0).expand(b, -1, -1)           # collapse_batch_dims=True: shared over candidates
     best = (float("inf"), None, None, None, None, None)
@@ -229,11 +239,13 @@ def construct_conformal_bands(gp: GPState, Xq, alpha, temp, grid_res, max_grid_r
 
 def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_grid_refinements=0,
                           eps_grid, z, eps_mc, ratio=None, randomized=False, u_rand=None,
-                          optimistic=True, beta_prime=None, best_f=None, X_baseline=None):
-    """ConformalAcquisition.forward (acquisitions.py:53-76).  Returns dict with acq (b,) and the bands."""
+                          optimistic=True, beta_prime=None, best_f=None, X_baseline=None, lazy_prior_grad=False):
+    """ConformalAcquisition.forward (acquisitions.py:53-76).  Returns dict with acq (b,) and the bands.
+    lazy_prior_grad: see construct_conformal_bands (gradient semantics of the reference's lazily evaluated grid covariance)."""
     b, q, _ = Xq.shape
     target_grid, logp, mask, refit, ood = construct_conformal_bands(
-        gp, Xq, alpha, temp, grid_res, max_grid_refinements, eps_grid, z, ratio, randomized, u_rand)
+        gp, Xq, alpha, temp, grid_res, max_grid_refinements, eps_grid, z, ratio, randomized, u_rand,
+        lazy_prior_grad=lazy_prior_grad)
     if optimistic:
         with torch.no_grad():                                        # acquisitions.py:58-59
             mean, _ = posterior(gp, Xq, observation_noise=False)

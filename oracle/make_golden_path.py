@@ -13,8 +13,8 @@ Randomness is injected, never re-seeded: sampler base samples through the stand-
 patching `torch.rand` for the one (n, 8) draw of helpers.py:399, the randomised step by patching `Bernoulli.sample` to
 `u < probs` (helpers.py:311).
 
-Usage:  python oracle/make_golden_path.py [--only NAME] [--ehvi]   (writes tests/golden/ref_path.pt, ref_path_n1024.pt,
-        ref_path_ehvi.pt)
+Usage:  python oracle/make_golden_path.py [--only NAME] [--ehvi] [--grad]   (writes tests/golden/ref_path.pt,
+        ref_path_n1024.pt, ref_path_ehvi.pt, ref_path_grad.pt)
 """
 import argparse
 import contextlib
@@ -115,7 +115,8 @@ def make_ratio(ref, d, seed=1):
 
 
 def run_acq_case(ref, name, *, N, d, b, q, G, kind, temp, alpha, refine=0, randomized=False, ratio=False, S=1, seed=0,
-                 noise=1e-2, optimistic=None, beta=0.2, best_f=0.3, nb=0, chunk=None, bounds=True, Sp=8, x_pending=0):
+                 noise=1e-2, optimistic=None, beta=0.2, best_f=0.3, nb=0, chunk=None, bounds=True, Sp=8, x_pending=0,
+                 want_grad=False):
     """One acquisition-forward case through the reference classes.  chunk: candidates per forward call (the reference's
     callers chunk by batch_limit; only valid with refine == 0, where candidates are independent)."""
     from botorch.sampling import IIDNormalSampler
@@ -150,7 +151,7 @@ def run_acq_case(ref, name, *, N, d, b, q, G, kind, temp, alpha, refine=0, rando
             return A.qConformalNoisyExpectedImprovement(X_baseline=Xb, prune_baseline=False, **kw)
         raise ValueError(kind)
 
-    outs = dict(acq=[], target_grid=[], grid_logp=[], conf_pred_mask=[], ood_mask=[], lb=[], ub=[])
+    outs = dict(acq=[], target_grid=[], grid_logp=[], conf_pred_mask=[], ood_mask=[], lb=[], ub=[], dacq_dX=[])
     step = chunk or b
     assert step == b or refine == 0
     for lo in range(0, b, step):
@@ -167,7 +168,13 @@ def run_acq_case(ref, name, *, N, d, b, q, G, kind, temp, alpha, refine=0, rando
         n_pass = used["z"]
         acq_fn = build()                                                  # fresh samplers: same injected draws again
         with injected(z=inp["z"], u_rand=u, draws=draws) as used:
-            val = acq_fn(Xc)
+            if want_grad:     # d acq / d X by autograd through the reference's own code (optimize.py:224-235 does exactly this)
+                Xg = Xc.clone().requires_grad_(True)
+                val = acq_fn(Xg)
+                (gX,) = torch.autograd.grad(val.sum(), Xg)
+                outs["dacq_dX"].append(gX.detach())
+            else:
+                val = acq_fn(Xc)
         assert used["z"] == n_pass and n_pass >= 1
         outs["acq"].append(val.detach())
         outs["target_grid"].append(grid)
@@ -336,6 +343,15 @@ BIG_CASES = dict(
     cfg2_ucb_q2=dict(N=1024, d=8, b=16, q=2, G=64, kind="ucb", temp=3e-2, alpha=1 / 32, randomized=True, ratio=True, chunk=2, seed=33),
 )
 
+# gradients: the same reference classes under torch.autograd (small shapes; refine = 0: the SGLD / L-BFGS callers' setting)
+GRAD_CASES = dict(
+    grad_ucb_q1=dict(N=40, d=3, b=10, q=1, G=32, kind="ucb", temp=3e-2, alpha=0.1, randomized=True, ratio=True, seed=61, want_grad=True),
+    grad_ucb_q2=dict(N=30, d=2, b=8, q=2, G=32, kind="ucb", temp=3e-2, alpha=0.15, randomized=True, ratio=True, seed=62, want_grad=True),
+    grad_ei_q1_S2=dict(N=36, d=4, b=9, q=1, G=16, kind="ei", temp=1e-2, alpha=0.1, S=2, seed=63, want_grad=True),
+    grad_nei_q2=dict(N=32, d=3, b=6, q=2, G=16, kind="nei", temp=3e-2, alpha=0.1, ratio=True, nb=5, seed=64, want_grad=True),
+    grad_pending=dict(N=30, d=2, b=7, q=1, x_pending=1, G=32, kind="ucb", temp=3e-2, alpha=0.1, randomized=True, seed=65, want_grad=True),
+)
+
 COV_CASES = dict(
     cov_soft=dict(N=60, d=3, n=40, G=64, temp=1e-2, alpha=0.1, refine=4, randomized=False, ratio=False, seed=41),
     cov_hard_rand=dict(N=60, d=3, n=40, G=64, temp=1e-6, alpha=0.2, refine=1, randomized=True, ratio=True, seed=42),
@@ -349,11 +365,15 @@ def main():
     ap.add_argument("--only", default=None)
     ap.add_argument("--skip-big", action="store_true")
     ap.add_argument("--ehvi", action="store_true", help="only (re)generate tests/golden/ref_path_ehvi.pt")
+    ap.add_argument("--grad", action="store_true", help="only (re)generate tests/golden/ref_path_grad.pt")
     args = ap.parse_args()
     torch.set_default_dtype(torch.float64)       # the north star fixes fp64 (the reference's scripts default to fp32)
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
     sel = lambda cases: {k: v for k, v in cases.items() if args.only in (None, k)}
+    if args.grad:
+        torch.save(dict(acq=[run_acq_case(ref, k, **v) for k, v in GRAD_CASES.items()]), os.path.join(OUT, "ref_path_grad.pt"))
+        return
     if args.ehvi:
         torch.save(dict(ehvi=[run_ehvi_case(ref, k, **v) for k, v in EHVI_CASES.items()]), os.path.join(OUT, "ref_path_ehvi.pt"))
         return

@@ -239,3 +239,39 @@ def test_cehvi_inner_expectation_against_reference_source_golden(name):
         for k, o in enumerate(got["per_output"]):
             opt = (o["target_grid"].cpu().reshape(b, G, q) >= o["post_mean"].cpu().reshape(b, 1, q)).double()
             assert torch.equal(opt, want["opt_mask"][..., k].double())
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_cuda_gradients_against_reference_source_golden(idx):
+    """d acq / d X of cbo_conformal_acq_grad_f64 against torch.autograd through the reference's OWN classes
+    (tests/golden/ref_path_grad.pt, oracle/make_golden_path.py --grad).  q = 1 (cUCB with ratio estimator and randomised step,
+    cEI with two MC samples): equal to the reference's gradient, 1e-6.  Joint batches (cUCB q = 2, cNEI q = 2, a pending
+    point): the reference leaks a gradient through the lazily evaluated prior block of the grid covariance
+    (tests/test_oracle_ref_path.py::test_oracle_gradients_against_reference_source_golden); the library implements the constant
+    grid the reference's no_grad block intends and is compared with autograd through the oracle under that convention."""
+    from conformal_bayesopt_b200 import ops
+    from tests.test_oracle_ref_path import oracle_inputs
+    from oracle import closed_form
+    c = _cases("ref_path_grad.pt")["acq"][idx]
+    st = _state(c["problem"])
+    Xq = c["Xq"] if c["X_pending"] is None else torch.cat([c["Xq"], c["X_pending"].expand(c["b"], -1, -1)], dim=1)
+    kw = dict(kind=c["kind"], alpha=c["alpha"], temp=c["temp"], grid_res=c["G"], max_grid_refinements=0,
+              randomized=c["randomized"], optimistic=c["optimistic"], beta_prime=math.sqrt(c["beta"] * math.pi / 2),
+              best_f=c["best_f"])
+    if c["kind"] == "nei":
+        kw["nei_baseline"] = ops.NeiBaseline.build(st, c["X_baseline"].to(DEV))
+    out = ops.conformal_acq(st, Xq.to(DEV), eps_grid=c["eps_grid"].to(DEV), z=c["z"].to(DEV), eps_mc=c["eps_mc"].to(DEV),
+                            u_rand=None if c["u_rand"] is None else c["u_rand"].to(DEV), ratio=_ratio(c), want_grad=True, **kw)
+    torch.cuda.synchronize()
+    want = c["out"]
+    assert torch.allclose(out["acq"].cpu(), want["acq"], rtol=RTOL, atol=1e-9)
+    g = out["dacq_dX"].cpu()[:, :c["q"]]
+    if Xq.shape[1] == 1:
+        ref_g = want["dacq_dX"]
+    else:
+        gp, Xo, okw = oracle_inputs(c)
+        Xo = Xo.clone().requires_grad_(True)
+        (ref_g,) = torch.autograd.grad(closed_form.conformal_acquisition(gp, Xo, **okw)["acq"].sum(), Xo)
+        ref_g = ref_g[:, :c["q"]]
+    scale = ref_g.abs().max()
+    assert torch.allclose(g, ref_g, rtol=RTOL, atol=float(1e-8 * scale)), float((g - ref_g).abs().max() / scale)
