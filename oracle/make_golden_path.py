@@ -13,8 +13,8 @@ Randomness is injected, never re-seeded: sampler base samples through the stand-
 patching `torch.rand` for the one (n, 8) draw of helpers.py:399, the randomised step by patching `Bernoulli.sample` to
 `u < probs` (helpers.py:311).
 
-Usage:  python oracle/make_golden_path.py [--only NAME] [--ehvi] [--grad]   (writes tests/golden/ref_path.pt,
-        ref_path_n1024.pt, ref_path_ehvi.pt, ref_path_grad.pt)
+Usage:  python oracle/make_golden_path.py [--only NAME] [--ehvi] [--grad] [--more]   (writes tests/golden/ref_path.pt,
+        ref_path_n1024.pt, ref_path_ehvi.pt, ref_path_grad.pt, ref_path_more.pt)
 """
 import argparse
 import contextlib
@@ -343,6 +343,18 @@ BIG_CASES = dict(
     cfg2_ucb_q2=dict(N=1024, d=8, b=16, q=2, G=64, kind="ucb", temp=3e-2, alpha=1 / 32, randomized=True, ratio=True, chunk=2, seed=33),
 )
 
+# more shapes / flag combinations through the same reference classes (tests/golden/ref_path_more.pt)
+MORE_CASES = dict(
+    more_ei_q2_S2=dict(N=36, d=3, b=14, q=2, G=32, kind="ei", temp=3e-2, alpha=0.12, randomized=True, ratio=True, S=2, seed=71),
+    more_ucb_q4=dict(N=28, d=2, b=6, q=4, G=16, kind="ucb", temp=3e-2, alpha=0.2, randomized=True, seed=72),
+    more_nei_pending=dict(N=40, d=3, b=8, q=1, x_pending=1, G=32, kind="nei", temp=2e-1, alpha=0.1, ratio=True, nb=7, S=2, seed=73),
+    more_hard_refine=dict(N=48, d=4, b=18, q=1, G=64, kind="ucb", temp=0.0, alpha=0.15, randomized=True, ratio=True, refine=2, seed=74),
+    more_ei_q3_nonopt=dict(N=32, d=5, b=7, q=3, G=24, kind="ei", temp=1e-2, alpha=0.1, optimistic=False, refine=1, seed=75),
+    more_g128=dict(N=64, d=6, b=10, q=1, G=128, kind="ucb", temp=3e-2, alpha=0.08, randomized=True, ratio=True, seed=76),
+    more_ucb_optoff_S3=dict(N=44, d=2, b=12, q=2, G=32, kind="ucb", temp=5e-2, alpha=0.1, optimistic=False, S=3, seed=77),
+    more_tiny_temp_q2=dict(N=30, d=3, b=9, q=2, G=32, kind="ucb", temp=1e-6, alpha=0.2, randomized=True, ratio=True, refine=1, seed=78),
+)
+
 # gradients: the same reference classes under torch.autograd (small shapes; refine = 0: the SGLD / L-BFGS callers' setting)
 GRAD_CASES = dict(
     grad_ucb_q1=dict(N=40, d=3, b=10, q=1, G=32, kind="ucb", temp=3e-2, alpha=0.1, randomized=True, ratio=True, seed=61, want_grad=True),
@@ -366,11 +378,15 @@ def main():
     ap.add_argument("--skip-big", action="store_true")
     ap.add_argument("--ehvi", action="store_true", help="only (re)generate tests/golden/ref_path_ehvi.pt")
     ap.add_argument("--grad", action="store_true", help="only (re)generate tests/golden/ref_path_grad.pt")
+    ap.add_argument("--more", action="store_true", help="only (re)generate tests/golden/ref_path_more.pt")
     args = ap.parse_args()
     torch.set_default_dtype(torch.float64)       # the north star fixes fp64 (the reference's scripts default to fp32)
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
     sel = lambda cases: {k: v for k, v in cases.items() if args.only in (None, k)}
+    if args.more:
+        torch.save(dict(acq=[run_acq_case(ref, k, **v) for k, v in MORE_CASES.items()], coverage=[]), os.path.join(OUT, "ref_path_more.pt"))
+        return
     if args.grad:
         torch.save(dict(acq=[run_acq_case(ref, k, **v) for k, v in GRAD_CASES.items()]), os.path.join(OUT, "ref_path_grad.pt"))
         return

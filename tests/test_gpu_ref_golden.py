@@ -275,3 +275,12 @@ def test_cuda_gradients_against_reference_source_golden(idx):
         ref_g = ref_g[:, :c["q"]]
     scale = ref_g.abs().max()
     assert torch.allclose(g, ref_g, rtol=RTOL, atol=float(1e-8 * scale)), float((g - ref_g).abs().max() / scale)
+
+
+@pytest.mark.parametrize("idx", range(8))
+def test_cuda_abi_against_more_reference_source_goldens(idx):
+    """tests/golden/ref_path_more.pt: further shapes and flag combinations executed by the reference's own classes (see
+    tests/test_oracle_ref_path.py::test_closed_form_against_more_reference_source_goldens)."""
+    c = _cases("ref_path_more.pt")["acq"][idx]
+    out = _call_abi(c)
+    _check(c, out["acq"], out)

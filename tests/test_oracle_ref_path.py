@@ -225,3 +225,13 @@ def test_oracle_gradients_against_reference_source_golden(idx):
     else:
         rel = float((g_const - want["dacq_dX"]).abs().max() / want["dacq_dX"].abs().max())
         assert rel > 1e-3                                          # the leak is not a rounding effect
+
+
+@pytest.mark.parametrize("idx", range(8))
+def test_closed_form_against_more_reference_source_goldens(idx):
+    """tests/golden/ref_path_more.pt (oracle/make_golden_path.py --more): cEI q = 2 with two MC samples, q = 4, cNEI with a
+    pending point, the hard path with two refinements, q = 3 non-optimistic with refinement, G = 128, three MC samples
+    without the optimistic mask, temp = 1e-6 with q = 2 and refinement."""
+    c = acq_cases("ref_path_more.pt")[idx]
+    gp, Xq, kw = oracle_inputs(c)
+    check_against_golden(c, closed_form.conformal_acquisition(gp, Xq, **kw))
