@@ -47,7 +47,7 @@ class Params(C.Structure):
                 ("kind", C.c_int32), ("optimistic", C.c_int32), ("randomized", C.c_int32),
                 ("eps_per_candidate", C.c_int32), ("beta_prime", C.c_double), ("best_f", C.c_double),
                 ("nei", C.POINTER(NeiBaselineF64)), ("refine_reduce", C.c_void_p), ("refine_ctx", C.c_void_p),
-                ("grid_cov_scale", C.c_void_p), ("ext_adjoints", C.POINTER(ExtAdjointsF64))]
+                ("grid_cov_scale", C.c_void_p), ("ext_adjoints", C.POINTER(ExtAdjointsF64)), ("grid_grad_leak", C.c_int32)]
 
 
 REFINE_REDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_void_p)
@@ -146,7 +146,7 @@ def load():
     lib.cbo_timing_enable.argtypes = [C.c_int]
     lib.cbo_timing_collect.restype = C.c_int
     lib.cbo_timing_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
-    if lib.cbo_version() != 102:
+    if lib.cbo_version() != 103:
         raise CboError(f"libcbo.so version mismatch: {lib.cbo_version()}")
     _LIB = lib
     return lib

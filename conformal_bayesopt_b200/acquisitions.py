@@ -76,6 +76,10 @@ class ConformalAcquisition(nn.Module):
         # the plain cUCB / cEI call goes through the dispatcher-registered operator torch.ops.cbo.conformal_acq (csrc/torch_ext.cpp,
         # Autograd kernel included); False (or CBO_NO_TORCH_EXT=1): the ctypes binding of the same C entry points
         self.use_torch_ops = os.environ.get("CBO_NO_TORCH_EXT", "0") != "1"
+        # d acq / d X of joint batches (q + pending >= 2, cUCB / cEI, no grid refinement): False = the target grid is a constant
+        # (the intent of the reference's no_grad block); True = also the gradient the reference's autograd leaks through the
+        # lazily evaluated prior block of the grid covariance (cbo_params.grid_grad_leak)
+        self.grid_grad_leak = False
         self.last_outputs = {}
 
     def set_X_pending(self, X_pending=None):
@@ -124,7 +128,9 @@ class ConformalAcquisition(nn.Module):
         return GraphedConformalAcq(state, b, q, eps_grid=eps, eps_mc=eps_mc, ratio=_ratio_weights(self.ratio_estimator, dev),
                                    want_grad=want_grad, alpha=self.alpha, temp=self.temp, grid_res=G,
                                    max_grid_refinements=0, randomized=self.randomized, optimistic=self.optimistic,
-                                   device_probes=self.device_probes, **self._acq_params())
+                                   device_probes=self.device_probes,
+                                   grid_grad_leak=bool(self.grid_grad_leak) and want_grad and self._kind in ("ucb", "ei"),
+                                   **self._acq_params())
 
     def _conformal_fwd(self, X: torch.Tensor, outputs=(), raw_grad=False) -> torch.Tensor:
         if self.model is None:
@@ -153,7 +159,8 @@ class ConformalAcquisition(nn.Module):
         if self.randomized and u is None:
             u = torch.rand(b, G, q, dtype=torch.float64, device=dev)
         rr = self.refine_reduce if self.max_grid_refinements > 0 else None
-        if self.use_torch_ops and self._kind in ("ucb", "ei") and not outputs and not raw_grad and rr is None:
+        leak = bool(self.grid_grad_leak) and want_grad and self._kind in ("ucb", "ei")
+        if self.use_torch_ops and self._kind in ("ucb", "ei") and not outputs and not raw_grad and rr is None and not leak:
             from . import torch_ops
             acq = torch_ops.conformal_acq(state, X.reshape(-1, q, d).to(torch.float64), eps_grid=eps, z=z, eps_mc=eps_mc, u_rand=u,
                                           ratio=_ratio_weights(self.ratio_estimator, dev), alpha=self.alpha, temp=self.temp,
@@ -166,7 +173,7 @@ class ConformalAcquisition(nn.Module):
                                 refine_reduce=self.refine_reduce if self.max_grid_refinements > 0 else None,
                                 alpha=self.alpha, temp=self.temp, grid_res=G,
                                 max_grid_refinements=self.max_grid_refinements, randomized=self.randomized,
-                                optimistic=self.optimistic, **self._acq_params())
+                                optimistic=self.optimistic, grid_grad_leak=leak, **self._acq_params())
         self.last_outputs = out
         if raw_grad:
             q_in = (X_in.unsqueeze(0) if X_in.ndim == 2 else X_in).shape[-2]

@@ -791,6 +791,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 bq.f.post_cov = nullptr;
                 bq.wbar = w.X3;                                      // v (w.V) is read by phase 0: right-hand sides go to the scratch buffer
                 bq.adjq = w.adj;
+                bq.grid_leak = p->grid_grad_leak ? 1 : 0;
                 if (nei_kind) CBO_CUDA(run_nei(bq.f.base));          // sample values of the joint posterior (constants of k_score_q_bwd)
                 if (ext) {
                     bq.ext_mask_bar = ext->mask_bar + c0 * G * q;

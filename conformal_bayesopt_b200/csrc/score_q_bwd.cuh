@@ -17,7 +17,8 @@
 
 namespace cbo {
 
-constexpr int ADJQ_STRIDE = 8 + MAX_SP;        // per row: {mu_bar, drc_bar, Ssym[0..3], -, -, ut_bar[Sp]}
+constexpr int ADJQ_STRIDE = 8 + MAX_SP + MAX_Q;   // per row: {mu_bar, drc_bar, Ssym[0..3], -, -, ut_bar[MAX_SP], Kleak[0..3]}
+constexpr int ADJQ_LEAK = 8 + MAX_SP;         // Kleak: adjoint of the PRIOR block k(x_j, x_k) through the target grid (grid_leak)
 constexpr int SQB_GJ = 12;                     // per-(grid point, column) arrays
 constexpr int SQB_NT = 4 * MAX_Q + 4 * MAX_Q * MAX_Q + 4 * MAX_Q;   // totals: see enum below
 
@@ -34,6 +35,10 @@ struct ScoreQBwdArgs {
     const double* ext_mask_bar;   // n_cand x G x Q   d L / d mask_gj        (all three null: the kernel's own integration)
     const double* ext_ood_bar;    // n_cand x Q       d L / d ood_j
     const double* ext_f_bar;      // n_cand x S x G x Q   d L / d f_sgj of the internally sampled refit posterior, or null
+    // cbo_params.grid_grad_leak: the reference builds the target grid under torch.no_grad(), but the prior block k(x_j, x_k) of
+    // its lazily evaluated covariance is only evaluated when the grid is sampled and so tracks d/dX: add
+    // d acq / d y_g  d y_g / d k(x_j, x_k) for joint batches.  Own integration only (cUCB / cEI), unscaled grid covariance.
+    int grid_leak;
 };
 
 __host__ __device__ inline size_t score_q_bwd_smem_bytes(int Np, int G, int Q) {
@@ -812,6 +817,61 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                     for (int m = 0; m < Q; ++m) s += Li[m][j] * Tm[m][k];
                     Cfb[j][k] = s;
                 }
+            // grid leak (see ScoreQBwdArgs::grid_leak).  Everything depends on the grid through dev_g = y_g - mu = Lc eps_g:
+            // B_g = Sinv dev_g and the refit mean mu + shr dev_g, so  sum_g dev_bar_g dev_g^T = Sinv^T Mb + shr^T Mm  with the
+            // moments Mb = sum_g B_bar_g dev_g^T, Mm = sum_g meanf_bar_g dev_g^T this reverse pass has anyway (they make
+            // Sinv_bar).  With eps_g = Lc^-1 dev_g:  Lc_bar = tril((sum_g dev_bar_g dev_g^T) Lc^-T), then the Cholesky reverse.
+            double leak[Q][Q];
+            for (int j = 0; j < Q; ++j)
+                for (int k = 0; k < Q; ++k) leak[j][k] = 0.0;
+            if (Q > 1 && qb.grid_leak && !ext_adj && !p.ext_values && p.cscale == nullptr) {
+                double Dm[Q][Q], Lc[Q][Q], Lci[Q][Q], Lcb[Q][Q], Pc[Q][Q], Tc[Q][Q];
+                for (int a = 0; a < Q; ++a)
+                    for (int k = 0; k < Q; ++k) {
+                        double s = 0.0;
+                        for (int j = 0; j < Q; ++j) {
+                            const double mb = tot[SqbIdx::sinv(j, k)] - 2.0 * ivc[j] * noise * noise * tot[SqbIdx::t3(j, k)];
+                            s += Si[j][a] * mb + shr[j][a] * tot[SqbIdx::shr(j, k)];
+                        }
+                        Dm[a][k] = s;
+                        Lc[a][k] = s_Lc[a * Q + k];
+                    }
+                for (int j = 0; j < Q; ++j)                                                   // Lci = Lc^-1 (lower)
+                    for (int i2 = 0; i2 < Q; ++i2) {
+                        if (i2 < j) Lci[i2][j] = 0.0;
+                        else if (i2 == j) Lci[i2][j] = 1.0 / Lc[i2][i2];
+                        else {
+                            double s = 0.0;
+                            for (int k = j; k < i2; ++k) s += Lc[i2][k] * Lci[k][j];
+                            Lci[i2][j] = -s / Lc[i2][i2];
+                        }
+                    }
+                for (int a = 0; a < Q; ++a)
+                    for (int m = 0; m < Q; ++m) {
+                        double s = 0.0;
+                        if (m <= a)
+                            for (int k = 0; k < Q; ++k) s += Dm[a][k] * Lci[m][k];
+                        Lcb[a][m] = s;
+                    }
+                for (int j = 0; j < Q; ++j)
+                    for (int k = 0; k < Q; ++k) {
+                        double s = 0.0;
+                        for (int m = 0; m < Q; ++m) s += Lc[m][j] * Lcb[m][k];
+                        Pc[j][k] = (k < j) ? s : (k == j ? 0.5 * s : 0.0);
+                    }
+                for (int j = 0; j < Q; ++j)
+                    for (int k = 0; k < Q; ++k) {
+                        double s = 0.0;
+                        for (int m = 0; m < Q; ++m) s += Pc[j][m] * Lci[m][k];
+                        Tc[j][k] = s;
+                    }
+                for (int j = 0; j < Q; ++j)
+                    for (int k = 0; k < Q; ++k) {
+                        double s = 0.0;
+                        for (int m = 0; m < Q; ++m) s += Lci[m][j] * Tc[m][k];
+                        leak[j][k] = s;                                                       // Cov_bar (not yet symmetrised)
+                    }
+            }
             for (int j = 0; j < Q; ++j)
                 for (int k = 0; k < Q; ++k) shr_bar[j][k] += noise * 0.5 * (Cfb[j][k] + Cfb[k][j]);
             double var_c_bar[Q], Bsum[Q];
@@ -861,6 +921,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                 adj[0] = bad ? nan("") : mb;
                 adj[1] = bad ? nan("") : drc_bar;
                 for (int k = 0; k < MAX_Q; ++k) adj[2 + k] = (k < Q) ? (bad ? nan("") : Sb[j][k] + Sb[k][j]) : 0.0;
+                for (int k = 0; k < MAX_Q; ++k) adj[ADJQ_LEAK + k] = (k < Q && k != j && !bad) ? leak[j][k] + leak[k][j] : 0.0;
                 for (int s = 0; s < Sp; ++s) {
                     double ub = 0.0;
                     for (int m = 0; m < Q; ++m) ub = fma(Si[m][j], s_Cbar[m * MAX_SP + s], ub);   // (Sinv^T C_bar)_js
@@ -919,6 +980,7 @@ k_rows_bwd_q(const double* __restrict__ Xq, int rows, int q, const double* __res
     __syncthreads();
     const double mu_bar = s_adj[0];
     const double kfac = -(5.0 / 3.0) * outputscale;
+    const double* leak = q1_layout ? nullptr : adjq + int64_t(r) * adj_stride + ADJQ_LEAK;   // prior-block adjoint through the grid
     for (int k0 = 0; k0 < d; k0 += 8) {
         double acc[8];
 #pragma unroll
@@ -958,7 +1020,7 @@ k_rows_bwd_q(const double* __restrict__ Xq, int rows, int q, const double* __res
                 }
                 const double t = kSqrt5 * sqrt(fmax(r2, 1e-30));
                 const double dfk = s_x[kd] - Xq[int64_t(c * q + k) * d + kd] * inv_ls[kd];
-                v = fma(s_adj[2 + k] * kfac * (1.0 + t) * exp(-t), dfk, v);
+                v = fma((s_adj[2 + k] + (leak ? leak[k] : 0.0)) * kfac * (1.0 + t) * exp(-t), dfk, v);
             }
             for (int rb = 0; rb < nb; ++rb) {
                 double r2 = 0.0;

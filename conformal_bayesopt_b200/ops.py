@@ -109,14 +109,14 @@ class NeiBaseline:
 
 def make_params(*, alpha, temp, grid_res, q=1, num_mc=1, num_probes=8, max_grid_refinements=0, kind="ucb",
                 optimistic=True, randomized=False, eps_per_candidate=False, beta_prime=0.0, best_f=0.0,
-                nei=None, refine_reduce=None, grid_cov_scale=None, ext_adjoints=None) -> "_lib.Params":
+                nei=None, refine_reduce=None, grid_cov_scale=None, ext_adjoints=None, grid_grad_leak=False) -> "_lib.Params":
     """`refine_reduce`: a `_lib.REFINE_REDUCE_FN` instance (kept alive by the caller) or None."""
     fn = C.cast(refine_reduce, C.c_void_p) if refine_reduce is not None else None
     return _lib.Params(float(alpha), float(temp), int(grid_res), int(q), int(num_mc), int(num_probes),
                        int(max_grid_refinements), ACQ_KINDS[kind], int(bool(optimistic)), int(bool(randomized)),
                        int(bool(eps_per_candidate)), float(beta_prime), float(best_f),
                        C.pointer(nei) if nei is not None else None, fn, None, grid_cov_scale,
-                       C.pointer(ext_adjoints) if ext_adjoints is not None else None)
+                       C.pointer(ext_adjoints) if ext_adjoints is not None else None, int(bool(grid_grad_leak)))
 
 
 def workspace(state: GPModelState, b: int, params, chunk: int = 0, grad: bool = False, stream: Optional[int] = None) -> torch.Tensor:

@@ -284,3 +284,33 @@ def test_cuda_abi_against_more_reference_source_goldens(idx):
     c = _cases("ref_path_more.pt")["acq"][idx]
     out = _call_abi(c)
     _check(c, out["acq"], out)
+
+
+@pytest.mark.parametrize("name", ["grad_ucb_q2", "grad_pending", "grad_ucb_q1"])
+def test_cuda_gradients_with_the_reference_grid_leak(name):
+    """cbo_params.grid_grad_leak = 1: the reverse pass adds the gradient the reference's autograd propagates through the
+    lazily evaluated prior block k(x_j, x_k) of the grid covariance.  cUCB q = 2 and a q = 1 + pending batch then
+    equal `torch.autograd` through the reference's OWN classes (tests/golden/ref_path_grad.pt) to 1e-6; q = 1 is unaffected."""
+    from conformal_bayesopt_b200 import ops
+    c = [x for x in _cases("ref_path_grad.pt")["acq"] if x["name"] == name][0]
+    st = _state(c["problem"])
+    Xq = c["Xq"] if c["X_pending"] is None else torch.cat([c["Xq"], c["X_pending"].expand(c["b"], -1, -1)], dim=1)
+    kw = dict(kind=c["kind"], alpha=c["alpha"], temp=c["temp"], grid_res=c["G"], max_grid_refinements=0,
+              randomized=c["randomized"], optimistic=c["optimistic"], beta_prime=math.sqrt(c["beta"] * math.pi / 2),
+              best_f=c["best_f"])
+    out = {}
+    for leak in (False, True):
+        out[leak] = ops.conformal_acq(st, Xq.to(DEV), eps_grid=c["eps_grid"].to(DEV), z=c["z"].to(DEV), eps_mc=c["eps_mc"].to(DEV),
+                                      u_rand=None if c["u_rand"] is None else c["u_rand"].to(DEV), ratio=_ratio(c),
+                                      want_grad=True, grid_grad_leak=leak, **kw)
+    torch.cuda.synchronize()
+    want = c["out"]["dacq_dX"]
+    scale = want.abs().max()
+    g = out[True]["dacq_dX"].cpu()[:, :c["q"]]
+    assert torch.equal(out[True]["acq"], out[False]["acq"])
+    assert torch.allclose(g, want, rtol=RTOL, atol=float(1e-8 * scale)), float((g - want).abs().max() / scale)
+    g0 = out[False]["dacq_dX"].cpu()[:, :c["q"]]
+    if Xq.shape[1] == 1:
+        assert torch.equal(g0, g)
+    else:
+        assert float((g0 - want).abs().max() / scale) > 1e-3           # without the switch: the constant-grid convention
