@@ -314,3 +314,39 @@ def test_cuda_gradients_with_the_reference_grid_leak(name):
         assert torch.equal(g0, g)
     else:
         assert float((g0 - want).abs().max() / scale) > 1e-3           # without the switch: the constant-grid convention
+
+
+@pytest.mark.parametrize("name", ["grad_ucb_q2", "grad_pending"])
+def test_class_backward_with_the_reference_grid_leak(name):
+    """`acq.grid_grad_leak = True` on the drop-in class: `acq(X).sum().backward()` (what optim/optimize.py:224-235 does) then
+    gives the gradient torch.autograd gives through the reference's own class, 1e-6; `value_and_grad` and the graph-replayed
+    call (`acq.graphed`) give the same rows."""
+    import conformal_bayesopt_b200 as cbo
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    c = [x for x in _cases("ref_path_grad.pt")["acq"] if x["name"] == name][0]
+    st = _state(c["problem"])
+    G, S = c["G"], c["S"]
+    gs, s = IIDNormalSampler(G), IIDNormalSampler(S, batch_range=(0, -3))
+    gs.set_base_samples(c["eps_grid"])
+    s.set_base_samples(c["eps_mc"])
+    acq_fn = cbo.qConformalUpperConfidenceBound(
+        beta=c["beta"], alpha=c["alpha"], temp=c["temp"], grid_res=G, max_grid_refinements=0, ratio_estimator=_ratio(c),
+        optimistic=c["optimistic"], grid_sampler=gs, randomized=c["randomized"], model=st, sampler=s,
+        X_pending=None if c["X_pending"] is None else c["X_pending"].to(DEV))
+    acq_fn.fixed_probes = c["z"]
+    acq_fn.fixed_uniforms = None if c["u_rand"] is None else c["u_rand"].to(DEV)
+    acq_fn.grid_grad_leak = True
+    X = c["Xq"].to(DEV).requires_grad_(True)
+    val = acq_fn(X)
+    val.sum().backward()
+    want = c["out"]
+    scale = want["dacq_dX"].abs().max()
+    assert torch.allclose(val.detach().cpu(), want["acq"], rtol=RTOL, atol=1e-9)
+    assert torch.allclose(X.grad.cpu(), want["dacq_dX"], rtol=RTOL, atol=float(1e-8 * scale))
+    v2, g2 = acq_fn.value_and_grad(c["Xq"].to(DEV))
+    assert torch.equal(g2, X.grad) and torch.equal(v2, val.detach())
+    if c["X_pending"] is None:
+        graphed = acq_fn.graphed(c["b"], c["q"])
+        out = graphed(c["Xq"].to(DEV), z=c["z"].to(DEV), u_rand=acq_fn.fixed_uniforms)
+        torch.cuda.synchronize()
+        assert torch.equal(out["dacq_dX"], X.grad.reshape(out["dacq_dX"].shape))
