@@ -76,7 +76,7 @@ class ConformalAcquisition(nn.Module):
         # the plain cUCB / cEI call goes through the dispatcher-registered operator torch.ops.cbo.conformal_acq (csrc/torch_ext.cpp,
         # Autograd kernel included); False (or CBO_NO_TORCH_EXT=1): the ctypes binding of the same C entry points
         self.use_torch_ops = os.environ.get("CBO_NO_TORCH_EXT", "0") != "1"
-        # d acq / d X of joint batches (q + pending >= 2, cUCB / cEI, no grid refinement): False = the target grid is a constant
+        # d acq / d X of joint batches (q + pending >= 2, cUCB / cEI / cNEI, no grid refinement): False = the target grid is a constant
         # (the intent of the reference's no_grad block); True = also the gradient the reference's autograd leaks through the
         # lazily evaluated prior block of the grid covariance (cbo_params.grid_grad_leak)
         self.grid_grad_leak = False
@@ -129,7 +129,7 @@ class ConformalAcquisition(nn.Module):
                                    want_grad=want_grad, alpha=self.alpha, temp=self.temp, grid_res=G,
                                    max_grid_refinements=0, randomized=self.randomized, optimistic=self.optimistic,
                                    device_probes=self.device_probes,
-                                   grid_grad_leak=bool(self.grid_grad_leak) and want_grad and self._kind in ("ucb", "ei"),
+                                   grid_grad_leak=bool(self.grid_grad_leak) and want_grad and self._kind in ("ucb", "ei", "nei"),
                                    **self._acq_params())
 
     def _conformal_fwd(self, X: torch.Tensor, outputs=(), raw_grad=False) -> torch.Tensor:
@@ -159,7 +159,7 @@ class ConformalAcquisition(nn.Module):
         if self.randomized and u is None:
             u = torch.rand(b, G, q, dtype=torch.float64, device=dev)
         rr = self.refine_reduce if self.max_grid_refinements > 0 else None
-        leak = bool(self.grid_grad_leak) and want_grad and self._kind in ("ucb", "ei")
+        leak = bool(self.grid_grad_leak) and want_grad and self._kind in ("ucb", "ei", "nei")
         if self.use_torch_ops and self._kind in ("ucb", "ei") and not outputs and not raw_grad and rr is None and not leak:
             from . import torch_ops
             acq = torch_ops.conformal_acq(state, X.reshape(-1, q, d).to(torch.float64), eps_grid=eps, z=z, eps_mc=eps_mc, u_rand=u,

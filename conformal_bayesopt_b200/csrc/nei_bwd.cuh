@@ -23,6 +23,8 @@ struct NeiBwdArgs {
     double* adjq;              // rows x ADJQ_STRIDE   (+=)
     double* wbar;              // rows x Np            (+=)
     double* cv_bar;            // n_cand x nb x Q      (out)
+    int grid_leak;             // cbo_params.grid_grad_leak: add this kernel's part of the adjoint of the prior block k(x_j, x_k)
+                               // that flows through the target grid (score_q_bwd.cuh, grid_leak_from_moments) to adjq[ADJQ_LEAK..]
 };
 
 __host__ __device__ inline size_t nei_bwd_doubles(int nb, int q) { return 3 * size_t(nb + q) * nei_ld(nb + q) + 3 * size_t(nb + q) * q; }
@@ -59,12 +61,12 @@ k_nei_values_q_bwd(const NeiBwdArgs qb) {
     __syncwarp();
 
     // ---- reverse sweep over (MC sample, grid point): all lanes in lockstep, a lane owns rows lane (slot 0) and lane + 32 (slot 1) ----
-    double cvb[2][Q], cvr[2][Q], mubr[2], mub[Q], Sib[Q][Q];
+    double cvb[2][Q], cvr[2][Q], mubr[2], mub[Q], Sib[Q][Q], Fx[Q][Q];    // Fx = sum f_x_bar dev^T (grid leak: f_x = y_g - noise B_g)
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
         mub[j] = 0.0;
 #pragma unroll
-        for (int k = 0; k < Q; ++k) Sib[j][k] = 0.0;
+        for (int k = 0; k < Q; ++k) Sib[j][k] = Fx[j][k] = 0.0;
     }
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
@@ -181,11 +183,31 @@ k_nei_values_q_bwd(const NeiBwdArgs qb) {
             for (int j = 0; j < Q; ++j) {
                 db = fma(Si[j][k], Bgb[j], db);
                 Sib[j][k] = fma(Bgb[j], dev[k], Sib[j][k]);
+                Fx[j][k] = fma(fxb[j], dev[k], Fx[j][k]);
             }
             mub[k] -= db;                            // dev = y_g - mu with the grid point held fixed
         }
     }
     __syncwarp();
+    // grid leak: dev_bar_g = f_x_bar_g + Sinv^T B_bar_g, so sum_g dev_bar_g dev_g^T = Fx + Sinv^T (sum_g B_bar_g dev_g^T)
+    double leak[Q][Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j)
+#pragma unroll
+        for (int k = 0; k < Q; ++k) leak[j][k] = 0.0;
+    if (Q > 1 && qb.grid_leak && p.cscale == nullptr) {
+        double Dm[Q][Q];
+#pragma unroll
+        for (int a = 0; a < Q; ++a)
+#pragma unroll
+            for (int k = 0; k < Q; ++k) {
+                double s2 = Fx[a][k];
+#pragma unroll
+                for (int j = 0; j < Q; ++j) s2 = fma(Si[j][a], Sib[j][k], s2);
+                Dm[a][k] = s2;
+            }
+        grid_leak_from_moments<Q>(Dm, Lc, leak);
+    }
 
     // ---- Cholesky reverse: Sigma_bar = L^-T Phi(L^T L_bar) L^-1 ---------------------------------------------------------------
     for (int r = lane; r < m; r += 32)                // row r of Phi(L^T L_bar) -> Y
@@ -285,6 +307,9 @@ k_nei_values_q_bwd(const NeiBwdArgs qb) {
             adj[0] += ok ? mub[j] : nan("");
 #pragma unroll
             for (int k = 0; k < Q; ++k) adj[2 + k] += Sb[j][k] + Sb[k][j];
+#pragma unroll
+            for (int k = 0; k < Q; ++k)
+                if (k != j && ok) adj[ADJQ_LEAK + k] += leak[j][k] + leak[k][j];
         }
     }
     // right-hand sides of the A^-1 solve: c_rj = ... - K_bX[r,:] w_j

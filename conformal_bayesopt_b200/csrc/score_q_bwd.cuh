@@ -37,7 +37,8 @@ struct ScoreQBwdArgs {
     const double* ext_f_bar;      // n_cand x S x G x Q   d L / d f_sgj of the internally sampled refit posterior, or null
     // cbo_params.grid_grad_leak: the reference builds the target grid under torch.no_grad(), but the prior block k(x_j, x_k) of
     // its lazily evaluated covariance is only evaluated when the grid is sampled and so tracks d/dX: add
-    // d acq / d y_g  d y_g / d k(x_j, x_k) for joint batches.  Own integration only (cUCB / cEI), unscaled grid covariance.
+    // d acq / d y_g  d y_g / d k(x_j, x_k) for joint batches.  Own integration only (cUCB / cEI; cNEI together with
+    // k_nei_values_q_bwd, which adds the part that flows through its sample values), unscaled grid covariance.
     int grid_leak;
 };
 
@@ -61,6 +62,49 @@ struct SqbIdx {
     static __host__ __device__ constexpr int bsum(int j) { return 7 * MAX_Q + 4 * MAX_Q * MAX_Q + j; }
 };
 static_assert(SqbIdx::bsum(MAX_Q - 1) < SQB_NT, "totals layout");
+
+// Gradient that reaches the PRIOR block k(x_j, x_k) of the grid covariance through the target grid (cbo_params.grid_grad_leak).
+// Everything depends on the grid through dev_g = y_g - mu = Lc eps_g; with Dm = sum_g dev_bar_g dev_g^T and eps_g = Lc^-1 dev_g:
+// Lc_bar = tril(Dm Lc^-T), Cov_bar = Lc^-T Phi(Lc^T Lc_bar) Lc^-1 (returned unsymmetrised; the caller adds Cov_bar + Cov_bar^T).
+template <int Q>
+__device__ inline void grid_leak_from_moments(const double (&Dm)[Q][Q], const double (&Lc)[Q][Q], double (&leak)[Q][Q]) {
+    double Lci[Q][Q], Lcb[Q][Q], Pc[Q][Q], Tc[Q][Q];
+    for (int j = 0; j < Q; ++j)                                                   // Lci = Lc^-1 (lower)
+        for (int i2 = 0; i2 < Q; ++i2) {
+            if (i2 < j) Lci[i2][j] = 0.0;
+            else if (i2 == j) Lci[i2][j] = 1.0 / Lc[i2][i2];
+            else {
+                double s = 0.0;
+                for (int k = j; k < i2; ++k) s += Lc[i2][k] * Lci[k][j];
+                Lci[i2][j] = -s / Lc[i2][i2];
+            }
+        }
+    for (int a = 0; a < Q; ++a)
+        for (int m = 0; m < Q; ++m) {
+            double s = 0.0;
+            if (m <= a)
+                for (int k = 0; k < Q; ++k) s += Dm[a][k] * Lci[m][k];
+            Lcb[a][m] = s;
+        }
+    for (int j = 0; j < Q; ++j)
+        for (int k = 0; k < Q; ++k) {
+            double s = 0.0;
+            for (int m = 0; m < Q; ++m) s += Lc[m][j] * Lcb[m][k];
+            Pc[j][k] = (k < j) ? s : (k == j ? 0.5 * s : 0.0);
+        }
+    for (int j = 0; j < Q; ++j)
+        for (int k = 0; k < Q; ++k) {
+            double s = 0.0;
+            for (int m = 0; m < Q; ++m) s += Pc[j][m] * Lci[m][k];
+            Tc[j][k] = s;
+        }
+    for (int j = 0; j < Q; ++j)
+        for (int k = 0; k < Q; ++k) {
+            double s = 0.0;
+            for (int m = 0; m < Q; ++m) s += Lci[m][j] * Tc[m][k];
+            leak[j][k] = s;
+        }
+}
 
 // add this thread's value to totals slot `slot` (deterministic: warp tree, then fixed-order sum of the warp partials)
 struct SqbReducer {
@@ -824,8 +868,8 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             double leak[Q][Q];
             for (int j = 0; j < Q; ++j)
                 for (int k = 0; k < Q; ++k) leak[j][k] = 0.0;
-            if (Q > 1 && qb.grid_leak && !ext_adj && !p.ext_values && p.cscale == nullptr) {
-                double Dm[Q][Q], Lc[Q][Q], Lci[Q][Q], Lcb[Q][Q], Pc[Q][Q], Tc[Q][Q];
+            if (Q > 1 && qb.grid_leak && !ext_adj && p.cscale == nullptr) {
+                double Dm[Q][Q], Lc[Q][Q];
                 for (int a = 0; a < Q; ++a)
                     for (int k = 0; k < Q; ++k) {
                         double s = 0.0;
@@ -836,41 +880,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                         Dm[a][k] = s;
                         Lc[a][k] = s_Lc[a * Q + k];
                     }
-                for (int j = 0; j < Q; ++j)                                                   // Lci = Lc^-1 (lower)
-                    for (int i2 = 0; i2 < Q; ++i2) {
-                        if (i2 < j) Lci[i2][j] = 0.0;
-                        else if (i2 == j) Lci[i2][j] = 1.0 / Lc[i2][i2];
-                        else {
-                            double s = 0.0;
-                            for (int k = j; k < i2; ++k) s += Lc[i2][k] * Lci[k][j];
-                            Lci[i2][j] = -s / Lc[i2][i2];
-                        }
-                    }
-                for (int a = 0; a < Q; ++a)
-                    for (int m = 0; m < Q; ++m) {
-                        double s = 0.0;
-                        if (m <= a)
-                            for (int k = 0; k < Q; ++k) s += Dm[a][k] * Lci[m][k];
-                        Lcb[a][m] = s;
-                    }
-                for (int j = 0; j < Q; ++j)
-                    for (int k = 0; k < Q; ++k) {
-                        double s = 0.0;
-                        for (int m = 0; m < Q; ++m) s += Lc[m][j] * Lcb[m][k];
-                        Pc[j][k] = (k < j) ? s : (k == j ? 0.5 * s : 0.0);
-                    }
-                for (int j = 0; j < Q; ++j)
-                    for (int k = 0; k < Q; ++k) {
-                        double s = 0.0;
-                        for (int m = 0; m < Q; ++m) s += Pc[j][m] * Lci[m][k];
-                        Tc[j][k] = s;
-                    }
-                for (int j = 0; j < Q; ++j)
-                    for (int k = 0; k < Q; ++k) {
-                        double s = 0.0;
-                        for (int m = 0; m < Q; ++m) s += Lci[m][j] * Tc[m][k];
-                        leak[j][k] = s;                                                       // Cov_bar (not yet symmetrised)
-                    }
+                grid_leak_from_moments<Q>(Dm, Lc, leak);
             }
             for (int j = 0; j < Q; ++j)
                 for (int k = 0; k < Q; ++k) shr_bar[j][k] += noise * 0.5 * (Cfb[j][k] + Cfb[k][j]);

@@ -286,10 +286,10 @@ def test_cuda_abi_against_more_reference_source_goldens(idx):
     _check(c, out["acq"], out)
 
 
-@pytest.mark.parametrize("name", ["grad_ucb_q2", "grad_pending", "grad_ucb_q1"])
+@pytest.mark.parametrize("name", ["grad_ucb_q2", "grad_pending", "grad_ucb_q1", "grad_nei_q2"])
 def test_cuda_gradients_with_the_reference_grid_leak(name):
     """cbo_params.grid_grad_leak = 1: the reverse pass adds the gradient the reference's autograd propagates through the
-    lazily evaluated prior block k(x_j, x_k) of the grid covariance.  cUCB q = 2 and a q = 1 + pending batch then
+    lazily evaluated prior block k(x_j, x_k) of the grid covariance.  cUCB q = 2, a q = 1 + pending batch and cNEI q = 2 (k_nei_values_q_bwd adds the part through its sample values) then
     equal `torch.autograd` through the reference's OWN classes (tests/golden/ref_path_grad.pt) to 1e-6; q = 1 is unaffected."""
     from conformal_bayesopt_b200 import ops
     c = [x for x in _cases("ref_path_grad.pt")["acq"] if x["name"] == name][0]
@@ -298,6 +298,8 @@ def test_cuda_gradients_with_the_reference_grid_leak(name):
     kw = dict(kind=c["kind"], alpha=c["alpha"], temp=c["temp"], grid_res=c["G"], max_grid_refinements=0,
               randomized=c["randomized"], optimistic=c["optimistic"], beta_prime=math.sqrt(c["beta"] * math.pi / 2),
               best_f=c["best_f"])
+    if c["kind"] == "nei":
+        kw["nei_baseline"] = ops.NeiBaseline.build(st, c["X_baseline"].to(DEV))
     out = {}
     for leak in (False, True):
         out[leak] = ops.conformal_acq(st, Xq.to(DEV), eps_grid=c["eps_grid"].to(DEV), z=c["z"].to(DEV), eps_mc=c["eps_mc"].to(DEV),
