@@ -362,6 +362,8 @@ GRAD_CASES = dict(
     grad_ei_q1_S2=dict(N=36, d=4, b=9, q=1, G=16, kind="ei", temp=1e-2, alpha=0.1, S=2, seed=63, want_grad=True),
     grad_nei_q2=dict(N=32, d=3, b=6, q=2, G=16, kind="nei", temp=3e-2, alpha=0.1, ratio=True, nb=5, seed=64, want_grad=True),
     grad_pending=dict(N=30, d=2, b=7, q=1, x_pending=1, G=32, kind="ucb", temp=3e-2, alpha=0.1, randomized=True, seed=65, want_grad=True),
+    # the reference's default SGLD shape at the BASELINE size: N = 1024, d = 8, G = 64, q = 2, ratio estimator, randomised
+    grad_cfg2_ucb_q2=dict(N=1024, d=8, b=4, q=2, G=64, kind="ucb", temp=3e-2, alpha=1 / 32, randomized=True, ratio=True, chunk=2, seed=66, want_grad=True),
 )
 
 COV_CASES = dict(

@@ -241,7 +241,7 @@ def test_cehvi_inner_expectation_against_reference_source_golden(name):
             assert torch.equal(opt, want["opt_mask"][..., k].double())
 
 
-@pytest.mark.parametrize("idx", range(5))
+@pytest.mark.parametrize("idx", range(6))
 def test_cuda_gradients_against_reference_source_golden(idx):
     """d acq / d X of cbo_conformal_acq_grad_f64 against torch.autograd through the reference's OWN classes
     (tests/golden/ref_path_grad.pt, oracle/make_golden_path.py --grad).  q = 1 (cUCB with ratio estimator and randomised step,
@@ -286,11 +286,13 @@ def test_cuda_abi_against_more_reference_source_goldens(idx):
     _check(c, out["acq"], out)
 
 
-@pytest.mark.parametrize("name", ["grad_ucb_q2", "grad_pending", "grad_ucb_q1", "grad_nei_q2"])
+@pytest.mark.parametrize("name", ["grad_ucb_q2", "grad_pending", "grad_ucb_q1", "grad_nei_q2", "grad_cfg2_ucb_q2"])
 def test_cuda_gradients_with_the_reference_grid_leak(name):
     """cbo_params.grid_grad_leak = 1: the reverse pass adds the gradient the reference's autograd propagates through the
     lazily evaluated prior block k(x_j, x_k) of the grid covariance.  cUCB q = 2, a q = 1 + pending batch and cNEI q = 2 (k_nei_values_q_bwd adds the part through its sample values) then
-    equal `torch.autograd` through the reference's OWN classes (tests/golden/ref_path_grad.pt) to 1e-6; q = 1 is unaffected."""
+    equal `torch.autograd` through the reference's OWN classes (tests/golden/ref_path_grad.pt) to 1e-6; q = 1 is unaffected.
+    grad_cfg2_ucb_q2 is the reference's default SGLD shape at the BASELINE size (N = 1024, d = 8, G = 64, q = 2, ratio estimator,
+    randomised step)."""
     from conformal_bayesopt_b200 import ops
     c = [x for x in _cases("ref_path_grad.pt")["acq"] if x["name"] == name][0]
     st = _state(c["problem"])
