@@ -202,8 +202,8 @@ def construct_conformal_bands(gp: GPState, Xq, alpha, temp, grid_res, max_grid_r
         # GRADIENT SEMANTICS ONLY (values unchanged).  helpers.py:118-119 builds y_post under torch.no_grad(), but GPyTorch
         # returns the predictive covariance LAZILY: the prior block k(X, X) is a lazily evaluated kernel that is only
         # evaluated when the grid is sampled, after the no_grad block has exited, and so tracks d/dX; the correction term
-        # k(X, X_train) A^-1 k(X_train, X) was solved for eagerly and is a constant (oracle/_shim restates
-        # exactly this).  For q = 1 the prior block is the constant outputscale and nothing leaks; for q >= 2 the grid
+        # k(X, X_train) A^-1 k(X_train, X) was solved for eagerly and is a constant (GPyTorch's LazyEvaluatedKernelTensor;
+        # oracle/_shim restates exactly this).  For q = 1 the prior block is the constant outputscale and nothing leaks; for q >= 2 the grid
         # depends on X through k(x_j, x_k).  The product (and the default of this oracle) treats the grid as the constant
         # the no_grad block intends; this switch reproduces the reference's autograd to 1e-6 (tests/test_oracle_ref_path.py).
         Kxx = gp.k(Xq, Xq)
