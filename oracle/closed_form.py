@@ -39,7 +39,10 @@ def candidate_solves(gp: GPState, Xq: torch.Tensor):
 
 def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_grid_refinements=0,
                           eps_grid, z, eps_mc, ratio=None, randomized=False, u_rand=None,
-                          optimistic=True, beta_prime=None, best_f=None, X_baseline=None):
+                          optimistic=True, beta_prime=None, best_f=None, X_baseline=None, lazy_prior_grad=False):
+    """lazy_prior_grad: GRADIENT semantics only -- the prior block k(x_j, x_k) of the grid covariance tracks d/dX, as in the
+    reference's lazily evaluated predictive covariance (see oracle/dense.py::construct_conformal_bands); default: the grid is a
+    constant, the intent of the reference's no_grad block."""
     b, q, _ = Xq.shape
     N, G, noise = gp.N, grid_res, gp.noise
     Sp = z.shape[-1]
@@ -68,13 +71,13 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
     def one_pass(cov):
         # the grid and its log-density are built under torch.no_grad() in the reference (helpers.py:118-119): constants
         # w.r.t. the candidate; everything below (the refit on (x, y_g)) is differentiable in x
-        with torch.no_grad():
+        with torch.set_grad_enabled(bool(lazy_prior_grad) and torch.is_grad_enabled()):
             Lc = torch.linalg.cholesky(cov)
             dev0 = (Lc.unsqueeze(1) @ eps_grid.unsqueeze(-1)).squeeze(-1)   # (b,G,q) = y_g - mu
             sol = torch.linalg.solve_triangular(Lc.unsqueeze(1), dev0.unsqueeze(-1), upper=False).squeeze(-1)
             logdet = 2.0 * torch.diagonal(Lc, dim1=-2, dim2=-1).log().sum(-1)
             logp = -0.5 * (sol.pow(2).sum(-1) + logdet.unsqueeze(1) + q * LOG2PI)
-            grid_const = mu.unsqueeze(1) + dev0
+            grid_const = mu.detach().unsqueeze(1) + dev0
         dev = grid_const - mu.unsqueeze(1)                                  # same numbers; carries d/dx of mu
         Bg = dev @ Sinv.transpose(-1, -2)                                   # (b,G,q)  S^-1 (y_g - mu)
         r_train = noise * (gp.alpha.view(1, 1, N) - Bg @ W)                 # (b,G,N)
@@ -109,6 +112,9 @@ def conformal_acquisition(gp: GPState, Xq, *, kind, alpha, temp, grid_res, max_g
         return grid_const, logp, mask, dev
 
     cov = S.detach().clone()
+    if lazy_prior_grad and Xq.requires_grad:
+        Kxx = gp.k(Xq, Xq)
+        cov = cov + (Kxx - Kxx.detach())                                    # value unchanged, d/dX of the prior block only
     best = (float("inf"),)
     for _ in range(max_grid_refinements + 1):
         grid, logp, mask, dev = one_pass(cov)

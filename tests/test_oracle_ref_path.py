@@ -192,7 +192,7 @@ def _grad_close(got, want, rtol=1e-6):
     return torch.allclose(got, want, rtol=rtol, atol=float(1e-8 * scale))
 
 
-@pytest.mark.parametrize("idx", range(5))
+@pytest.mark.parametrize("idx", range(6))
 def test_oracle_gradients_against_reference_source_golden(idx):
     """d acq / d X: torch.autograd through the reference's OWN classes (over the exact-GP stand-in; what
     conformalbo/optim/optimize.py:224-235 does every SGLD step) recorded in tests/golden/ref_path_grad.pt -- cUCB q = 1, 2,
@@ -217,9 +217,13 @@ def test_oracle_gradients_against_reference_source_golden(idx):
         (g,) = torch.autograd.grad(got["acq"].sum(), X)
         return g[:, :c["q"]]                                       # pending points carry no gradient
 
-    assert _grad_close(grad_of(dense, lazy_prior_grad=True), want["dacq_dX"])
+    big = c["N"] > 256                                             # N = 1024: closed form only (the dense refit needs GBs under autograd)
+    if not big:
+        assert _grad_close(grad_of(dense, lazy_prior_grad=True), want["dacq_dX"])
+    assert _grad_close(grad_of(closed_form, lazy_prior_grad=True), want["dacq_dX"])
     g_const = grad_of(closed_form)
-    assert _grad_close(g_const, grad_of(dense))                    # the two oracles share ONE convention
+    if not big:
+        assert _grad_close(g_const, grad_of(dense))                # the two oracles share ONE convention
     if not joint:
         assert _grad_close(g_const, want["dacq_dX"])
     else:
