@@ -76,7 +76,7 @@ class ConformalAcquisition(nn.Module):
         # the plain cUCB / cEI call goes through the dispatcher-registered operator torch.ops.cbo.conformal_acq (csrc/torch_ext.cpp,
         # Autograd kernel included); False (or CBO_NO_TORCH_EXT=1): the ctypes binding of the same C entry points
         self.use_torch_ops = os.environ.get("CBO_NO_TORCH_EXT", "0") != "1"
-        # d acq / d X of joint batches (q + pending >= 2, cUCB / cEI / cNEI, no grid refinement): False = the target grid is a constant
+        # d acq / d X of joint batches (q + pending >= 2, no grid refinement; every acquisition class): False = the target grid is a constant
         # (the intent of the reference's no_grad block); True = also the gradient the reference's autograd leaks through the
         # lazily evaluated prior block of the grid covariance (cbo_params.grid_grad_leak)
         self.grid_grad_leak = False

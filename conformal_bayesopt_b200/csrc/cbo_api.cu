@@ -791,7 +791,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                 bq.f.post_cov = nullptr;
                 bq.wbar = w.X3;                                      // v (w.V) is read by phase 0: right-hand sides go to the scratch buffer
                 bq.adjq = w.adj;
-                bq.grid_leak = (p->grid_grad_leak && !ext) ? 1 : 0;
+                bq.grid_leak = p->grid_grad_leak ? 1 : 0;
                 if (nei_kind) CBO_CUDA(run_nei(bq.f.base));          // sample values of the joint posterior (constants of k_score_q_bwd)
                 if (ext) {
                     bq.ext_mask_bar = ext->mask_bar + c0 * G * q;
@@ -806,7 +806,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                     nb_.f = na_last;
                     nb_.val_bar = ext ? ext->f_bar + c0 * int64_t(p->num_mc) * G * q : w.val_bar;
                     nb_.adjq = w.adj; nb_.wbar = w.X3; nb_.cv_bar = w.cv_bar;
-                    nb_.grid_leak = (p->grid_grad_leak && !ext && !p->grid_cov_scale && R == 0) ? 1 : 0;
+                    nb_.grid_leak = (p->grid_grad_leak && !p->grid_cov_scale && R == 0) ? 1 : 0;
                     CBO_CUDA(cbo::launch_nei_values_q_bwd(nb_, q, s));
                 }
             }

@@ -37,8 +37,8 @@ struct ScoreQBwdArgs {
     const double* ext_f_bar;      // n_cand x S x G x Q   d L / d f_sgj of the internally sampled refit posterior, or null
     // cbo_params.grid_grad_leak: the reference builds the target grid under torch.no_grad(), but the prior block k(x_j, x_k) of
     // its lazily evaluated covariance is only evaluated when the grid is sampled and so tracks d/dX: add
-    // d acq / d y_g  d y_g / d k(x_j, x_k) for joint batches.  Own integration only (cUCB / cEI; cNEI together with
-    // k_nei_values_q_bwd, which adds the part that flows through its sample values), unscaled grid covariance.
+    // d acq / d y_g  d y_g / d k(x_j, x_k) for joint batches (cNEI / cNEHVI together with k_nei_values_q_bwd, which adds
+    // the part that flows through its sample values; cEHVI / cNEHVI per output in vector-Jacobian mode), unscaled grid covariance.
     int grid_leak;
 };
 
@@ -868,7 +868,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             double leak[Q][Q];
             for (int j = 0; j < Q; ++j)
                 for (int k = 0; k < Q; ++k) leak[j][k] = 0.0;
-            if (Q > 1 && qb.grid_leak && !ext_adj && p.cscale == nullptr) {
+            if (Q > 1 && qb.grid_leak && p.cscale == nullptr) {      // (also in vector-Jacobian mode: the moments are the handed-in adjoints')
                 double Dm[Q][Q], Lc[Q][Q];
                 for (int a = 0; a < Q; ++a)
                     for (int k = 0; k < Q; ++k) {

@@ -112,7 +112,7 @@ class qConformalExpectedHypervolumeImprovement(ConformalAcquisition):
             st, Xf, eps_grid=eps[:, :, k].contiguous(), z=z, u_rand=None if u is None else u.reshape(-1, G, q, u.shape[-1])[..., k].contiguous(),
             ratio=_ratio_weights(self.ratio_estimator, dev), alpha=self.alpha, temp=self.temp, grid_res=G,
             max_grid_refinements=0, randomized=self.randomized, optimistic=self.optimistic, want_grad=True,
-            ext_adjoints=bars, **kw)
+            ext_adjoints=bars, grid_grad_leak=bool(self.grid_grad_leak), **kw)
         return out["dacq_dX"]
 
     def _value_and_grad(self, X):

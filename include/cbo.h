@@ -138,7 +138,7 @@ typedef struct {
     const double* grid_cov_scale;
     /* cbo_conformal_acq_grad_f64 only: NULL = differentiate the call's own acquisition value. */
     const cbo_ext_adjoints_f64* ext_adjoints;
-    /* cbo_conformal_acq_grad_f64 only, joint batches (q >= 2) of kind UCB / EI / NEI without grid refinement.  0: the target grid
+    /* cbo_conformal_acq_grad_f64 only, joint batches (q >= 2) without grid refinement (every kind; with ext_adjoints per output).  0: the target grid
      * is a constant of the reverse pass (what the reference's torch.no_grad() block, helpers.py:118-119, intends).  1: add
      * the gradient the reference's autograd actually propagates: the prior block k(x_j, x_k) of its lazily evaluated
      * predictive covariance is evaluated when the grid is sampled, outside the no_grad block, so the grid depends on X

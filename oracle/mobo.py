@@ -62,7 +62,7 @@ def qehvi(f, cell_lower, cell_upper):
 
 
 def cehvi(gps, Xq, *, alpha, temp, grid_res, eps_grid, z, eps_mc, cell_lower, cell_upper, ratio=None, randomized=False,
-          u_rand=None, optimistic=False, impl="closed", max_grid_refinements=0, X_baseline=None):
+          u_rand=None, optimistic=False, impl="closed", max_grid_refinements=0, X_baseline=None, lazy_prior_grad=False):
     """gps: list of m GPState; Xq (b,q,d); eps_grid (G,q,m); eps_mc (S,G,q,m) -- or (S,G,nb+q,m) with X_baseline (cNEHVI: the
     samples of f(X) come from the joint refit posterior over [X_baseline; X], cells are then (S,n_cells,m)); u_rand (b,G,q,m).
     Returns dict(acq (b,), values (b,G)).  Differentiable in Xq (torch autograd)."""
@@ -79,7 +79,7 @@ def cehvi(gps, Xq, *, alpha, temp, grid_res, eps_grid, z, eps_mc, cell_lower, ce
                                       max_grid_refinements=max_grid_refinements, eps_grid=eps_grid[..., k], z=z,
                                       eps_mc=eps_mc[..., k], ratio=ratio, randomized=randomized,
                                       u_rand=None if u_rand is None else u_rand[..., k], optimistic=optimistic,
-                                      beta_prime=1.0, X_baseline=X_baseline)
+                                      beta_prime=1.0, X_baseline=X_baseline, lazy_prior_grad=lazy_prior_grad)
         mask = mask * o["mask"].prod(-1)                                   # product over the q points and over outputs
         logp = logp + o["logp"]
         ood = ood * o["ood"][:, 0, :].prod(-1)

@@ -243,3 +243,49 @@ def test_prune_baseline_matches_botorch_semantics():
     base2 = torch.randn(64, P["N"], 2, generator=g, dtype=torch.float64)
     kept2 = prune_inferior_points_multi_objective(P["states"], P["X"].to(dev), P["ref"], base_samples=base2)
     assert 0 < kept2.shape[0] <= P["N"]
+
+
+@pytest.mark.parametrize("cls_kind", ["cehvi", "cnehvi"])
+def test_multi_objective_grad_with_the_grid_leak_switch(cls_kind):
+    """`acq.grid_grad_leak = True` on the multi-objective classes (per-output vector-Jacobian calls with
+    cbo_params.grid_grad_leak): the gradient then includes what flows through each output's target grid via the prior block
+    k(x_j, x_k) -- compared with torch.autograd through the oracle under the same convention
+    (`mobo.cehvi(lazy_prior_grad=True)`); without the switch the rows differ."""
+    from conformal_bayesopt_b200.mobo_acquisitions import (box_decomposition_2d, qConformalExpectedHypervolumeImprovement,
+                                                         qConformalNoisyExpectedHypervolumeImprovement)
+    from conformal_bayesopt_b200.sampling import IIDNormalSampler
+    from oracle import mobo
+    q, b, G, S = 2, 7, 32, 2
+    nb = 5 if cls_kind == "cnehvi" else 0
+    P = _mobo_problem(q, 0, b, G, S, nb=nb)
+    dev = P["dev"]
+    gs = IIDNormalSampler(G)
+    gs.set_base_samples(P["eps_grid"])
+    mc = IIDNormalSampler(S, batch_range=(0, -3))
+    mc.set_base_samples(P["eps_new"])
+    common = dict(alpha=0.2, temp=3e-2, grid_res=G, max_grid_refinements=0, ratio_estimator=None, optimistic=False,
+                  grid_sampler=gs, randomized=True, model=P["states"], ref_point=P["ref"], sampler=mc)
+    if cls_kind == "cehvi":
+        lo, up = box_decomposition_2d(P["ref"], P["Y"])
+        acq = qConformalExpectedHypervolumeImprovement(partitioning=(lo, up), **common)
+        okw = dict(eps_mc=P["eps_new"], cell_lower=lo, cell_upper=up)
+    else:
+        acq = qConformalNoisyExpectedHypervolumeImprovement(X_baseline=P["Xb"].to(dev), prune_baseline=False,
+                                                            baseline_base_samples=P["eps_b"], **common)
+        lo, up, _ = mobo.nehvi_cells(P["gps"], P["Xb"], P["eps_b"], P["ref"])
+        eps_joint = torch.cat([P["eps_b"].unsqueeze(1).expand(S, G, nb, P["m"]), P["eps_new"]], dim=2)
+        okw = dict(eps_mc=eps_joint, cell_lower=lo, cell_upper=up, X_baseline=P["Xb"])
+    acq.fixed_probes, acq.fixed_uniforms = P["z"], P["u"].to(dev)
+    grads = {}
+    for leak in (False, True):
+        acq.grid_grad_leak = leak
+        X = P["Xq"].to(dev).requires_grad_(True)
+        acq(X).sum().backward()
+        grads[leak] = X.grad.cpu()
+        Xo = P["Xq"].clone().requires_grad_(True)
+        want = mobo.cehvi(P["gps"], Xo, alpha=0.2, temp=3e-2, grid_res=G, eps_grid=P["eps_grid"], z=P["z"], randomized=True,
+                          u_rand=P["u"], optimistic=False, lazy_prior_grad=leak, **okw)
+        (gw,) = torch.autograd.grad(want["acq"].sum(), Xo)
+        assert gw.abs().max() > 0
+        assert _grad_close(grads[leak], gw), (leak, float((grads[leak] - gw).abs().max() / gw.abs().max()))
+    assert float((grads[True] - grads[False]).abs().max() / grads[False].abs().max()) > 1e-4
