@@ -413,6 +413,13 @@ int cbo_version(void) { return CBO_VERSION; }
 
 int64_t cbo_launch_count(void) { return (int64_t)cbo::launch_counter().load(std::memory_order_relaxed); }
 
+#ifdef CBO_SQB_CLOCKS   // experiment builds only (tools/sqb_phase_clocks.py): phase clocks of CTA 0 of the last k_score_q_bwd
+int cbo_debug_sqb_clocks(long long* out32) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out32, cbo::g_sqb_clk, sizeof(long long) * 32);
+}
+#endif
+
 const char* cbo_status_str(int s) {
     switch (s) {
         case CBO_OK: return "ok";

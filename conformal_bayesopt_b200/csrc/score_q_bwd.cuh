@@ -43,7 +43,8 @@ struct ScoreQBwdArgs {
 };
 
 __host__ __device__ inline size_t score_q_bwd_smem_bytes(int Np, int G, int Q) {
-    return sizeof(double) * (size_t(4 + Q) * Np + size_t(SQB_GJ * Q + 1) * G + 1024 + SQ_WARPS * SQB_NT + SQB_NT);
+    return sizeof(double) * (size_t(4 + Q) * Np + size_t(SQB_GJ * Q + 1) * G + 1024 + SQ_WARPS * SQB_NT + SQB_NT +
+                             size_t(SQ_THREADS / 2) * (3 + Q));
 }
 
 // totals layout (doubles): per column / per pair accumulators reduced over the block
@@ -128,11 +129,39 @@ struct SqbReducer {
     }
 };
 
+// NV block sums behind ONE pair of barriers; every value is summed exactly as block_sum does it (same bits)
+template <int NV>
+__device__ __forceinline__ void block_sum_n(double (&v)[NV], double* red, int tid) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) red[(tid >> 5) * NV + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < SQ_WARPS; ++w) t += red[w * NV + k];
+        v[k] = t;
+    }
+}
+
 // CL = true: a thread-block CLUSTER of SQB_CLUSTER CTAs works on ONE joint batch (a handful of joint batches per call would
 // otherwise keep 8 SMs busy): every CTA owns a window of the train points for the O(N G q) sweeps (phase 0 Gram sums, phase A
 // tables, phase B, pass 2), the partial sums are exchanged through distributed shared memory (cluster.map_shared_rank) at
 // three cluster barriers, the O(G q) phases C-E run redundantly in every CTA, rank 0 does the final q x q algebra.
 constexpr int SQB_CLUSTER = 8;
+
+// Phase clocks of CTA 0 (experiment builds only: tools/sqb_phase_clocks.py compiles with -DCBO_SQB_CLOCKS; never in libcbo.so)
+#ifdef CBO_SQB_CLOCKS
+__device__ long long g_sqb_clk[32];
+#define SQB_CLK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_sqb_clk[k] = clock64(); } while (0)
+#else
+#define SQB_CLK(k) do { } while (0)
+#endif
 
 template <int Q, bool SOFT, bool CL>
 __global__ void __launch_bounds__(SQ_THREADS)
@@ -169,8 +198,10 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
     double* s_Cbar = s_kap + MAX_S * MAX_Q;  // Q x MAX_SP
     double* s_utb = s_Cbar + MAX_Q * MAX_SP; // Q x MAX_SP
     double* s_xg = s_utb + MAX_Q * MAX_SP;   // [Q*Q + 1]: this CTA's Gram partial sums and its `bad` flag (cluster exchange)
+    double* red_n = sc + 576;                // [SQ_WARPS][2 MAX_Q]  batched block sums (phase D)
     double* wred = sc + 1024;                // [SQ_WARPS][SQB_NT]
     double* tot = wred + SQ_WARPS * SQB_NT;  // [SQB_NT]
+    double* s_x2 = tot + SQB_NT;             // [SQ_THREADS / 2][3 + Q]  pass 2 (cluster): moments of the second half of the grid
     const SqbReducer R{wred, tot, tid};
     const double noise = p.noise;
     const double kvar = noise / (double(Sp) + 1e-6);
@@ -198,6 +229,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
     for (int c = CL ? blockIdx.x / SQB_CLUSTER : blockIdx.x; c < p.n_cand; c += cstep) {
         const int r0 = c * Q;
         for (int e = tid; e < SQB_NT; e += SQ_THREADS) tot[e] = 0.0;
+        SQB_CLK(0);
         // ---- phase 0 (as k_score_q) -----------------------------------------------------------------------------------
         double gsum[Q][Q];
 #pragma unroll
@@ -219,6 +251,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
 #pragma unroll
             for (int k = 0; k < Q; ++k)
                 if (k <= j) gsum[j][k] = block_sum(gsum[j][k], red, tid);
+        SQB_CLK(1);
         if constexpr (CL) {                                              // Gram sums over all windows, fixed rank order
             if (tid == 0)
                 for (int j = 0; j < Q; ++j)
@@ -232,6 +265,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                         gsum[j][k] = t;
                     }
         }
+        SQB_CLK(2);
         if (tid == 0) {
             double Sm[Q][Q], Ls[Q][Q], Si[Q][Q];
             for (int j = 0; j < Q; ++j)
@@ -284,7 +318,20 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             s_misc[Q + 1] = ok ? 0.0 : 1.0;
         }
         __syncthreads();
+        SQB_CLK(3);
         int bad = s_misc[Q + 1] != 0.0;
+
+        double mu[Q], drc[Q], norm[Q], omega[Q], ivc[Q], lvc[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            mu[j] = p.mu[r0 + j];
+            drc[j] = p.drc ? p.drc[r0 + j] : 1.0;
+            norm[j] = sum_dr + drc[j];
+            omega[j] = drc[j] / norm[j];
+            ivc[j] = 0.5 / s_misc[j];
+            lvc[j] = -0.5 * log(s_misc[j]) - 0.5 * kLog2Pi;
+        }
+        const double logdet = s_misc[Q];
 
         // ---- phase A: per-train-point tables ---------------------------------------------------------------------------
         for (int i = i_lo + tid; i < i_hi; i += SQ_THREADS) {
@@ -307,23 +354,10 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
 #pragma unroll
             for (int j = 0; j < Q; ++j) s_wp[size_t(j) * Np + i] = noise * w[j] * siv;
         }
-        bad = __syncthreads_or(bad);                                     // CL: this window only; combined after phase B
-
-        double mu[Q], drc[Q], norm[Q], omega[Q], ivc[Q], lvc[Q];
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            mu[j] = p.mu[r0 + j];
-            drc[j] = p.drc ? p.drc[r0 + j] : 1.0;
-            norm[j] = sum_dr + drc[j];
-            omega[j] = drc[j] / norm[j];
-            ivc[j] = 0.5 / s_misc[j];
-            lvc[j] = -0.5 * log(s_misc[j]) - 0.5 * kLog2Pi;
-        }
-        const double logdet = s_misc[Q];
-
-        // ---- phase B + C: warp per grid point (forward) -------------------------------------------------------------------
-        for (int g = warp; g < G; g += SQ_WARPS) {
-            double eps[Q], dev[Q], Bg[Q], thr[Q];
+        // per-grid-point quantities (dev = Lc eps, B = S^-1 dev, threshold score), thread per grid point, counted from the
+        // top of the block so that they run beside phase A (which occupies the low threads of a cluster window)
+        for (int g = SQ_THREADS - 1 - tid; g < G; g += SQ_THREADS) {
+            double eps[Q], dev[Q];
             double e2 = 0.0;
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
@@ -338,70 +372,99 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                     if (k <= j) s = fma(s_Lc[j * Q + k], eps[k], s);
                 dev[j] = s;
             }
+            g_kd[g] = e2;
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
                 double s = 0.0;
 #pragma unroll
                 for (int k = 0; k < Q; ++k) s = fma(s_Sinv[j * Q + k], dev[k], s);
-                Bg[j] = s;
-                double rc = noise * s;
-                thr[j] = fma(-rc * rc, ivc[j], lvc[j]);
+                const double rc = noise * s;
+                g_dev[g * Q + j] = dev[j]; g_Bg[g * Q + j] = s; g_thr[g * Q + j] = fma(-rc * rc, ivc[j], lvc[j]);
             }
-            double sr[Q], sw[Q];
-            int cnt[Q];
+        }
+        bad = __syncthreads_or(bad);                                     // CL: this window only; combined after phase B
+        SQB_CLK(4);
+
+        // ---- phase B + C: warp per grid point (forward), GU grid points in flight -------------------------------------------
+        constexpr int GU = (Q <= 2) ? 2 : 1;
+        for (int g0 = warp; g0 < G; g0 += GU * SQ_WARPS) {
+            double Bg[GU][Q], thr[GU][Q], sr[GU][Q], sw[GU][Q];
+            int cnt[GU][Q];
 #pragma unroll
-            for (int j = 0; j < Q; ++j) { sr[j] = 0.0; sw[j] = 0.0; cnt[j] = 0; }
+            for (int u = 0; u < GU; ++u) {
+                const int g = min(g0 + u * SQ_WARPS, G - 1);
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    Bg[u][j] = g_Bg[g * Q + j]; thr[u][j] = g_thr[g * Q + j];
+                    sr[u][j] = 0.0; sw[u][j] = 0.0; cnt[u][j] = 0;
+                }
+            }
             if (!bad) {
-                // two train points per lane and step (i, i + 32): 2 Q independent sigmoid chains instead of Q
+                // two train points per lane and step (i, i + 32): 2 GU Q independent sigmoid chains
                 for (int i = i_lo + lane; i < i_hi; i += 64) {
                     const int i2 = i + 32;
                     const bool ok2 = i2 < i_hi;
                     const int i2c = ok2 ? i2 : i;
-                    double rp0 = s_ap[i], rp1 = s_ap[i2c];
-#pragma unroll
-                    for (int j = 0; j < Q; ++j) {
-                        rp0 = fma(-s_wp[size_t(j) * Np + i], Bg[j], rp0);
-                        rp1 = fma(-s_wp[size_t(j) * Np + i2c], Bg[j], rp1);
-                    }
-                    const double sci0 = fma(-rp0, rp0, s_lv[i]), sci1 = fma(-rp1, rp1, s_lv[i2c]);
+                    const double ap0 = s_ap[i], ap1 = s_ap[i2c], lv0 = s_lv[i], lv1 = s_lv[i2c];
                     const double dr0 = s_dr[i], dr1 = ok2 ? s_dr[i2c] : 0.0;
+                    double w0[Q], w1[Q];
 #pragma unroll
-                    for (int j = 0; j < Q; ++j) {
-                        const double dd0 = thr[j] - sci0, dd1 = thr[j] - sci1;
-                        const bool ge0 = dd0 >= 0.0, ge1 = ok2 && (dd1 >= 0.0);
-                        cnt[j] += (ge0 ? 1 : 0) + (ge1 ? 1 : 0);
-                        if (SOFT) {
-                            const double rho0 = soft_rho<true>(dd0 * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
-                            double rho1 = soft_rho<true>(dd1 * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
-                            rho1 = ok2 ? rho1 : 0.0;
-                            sr[j] += rho0 + rho1;
-                            sw[j] = fma(rho0, dr0, fma(rho1, dr1, sw[j]));
-                        } else {
-                            sw[j] += (ge0 ? dr0 : 0.0) + (ge1 ? dr1 : 0.0);
+                    for (int j = 0; j < Q; ++j) { w0[j] = s_wp[size_t(j) * Np + i]; w1[j] = s_wp[size_t(j) * Np + i2c]; }
+#pragma unroll
+                    for (int u = 0; u < GU; ++u) {
+                        double rp0 = ap0, rp1 = ap1;
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) {
+                            rp0 = fma(-w0[j], Bg[u][j], rp0);
+                            rp1 = fma(-w1[j], Bg[u][j], rp1);
+                        }
+                        const double sci0 = fma(-rp0, rp0, lv0), sci1 = fma(-rp1, rp1, lv1);
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) {
+                            const double dd0 = thr[u][j] - sci0, dd1 = thr[u][j] - sci1;
+                            const bool ge0 = dd0 >= 0.0, ge1 = ok2 && (dd1 >= 0.0);
+                            cnt[u][j] += (ge0 ? 1 : 0) + (ge1 ? 1 : 0);
+                            if (SOFT) {
+                                const double rho0 = soft_rho<true>(dd0 * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
+                                double rho1 = soft_rho<true>(dd1 * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
+                                rho1 = ok2 ? rho1 : 0.0;
+                                sr[u][j] += rho0 + rho1;
+                                sw[u][j] = fma(rho0, dr0, fma(rho1, dr1, sw[u][j]));
+                            } else {
+                                sw[u][j] += (ge0 ? dr0 : 0.0) + (ge1 ? dr1 : 0.0);
+                            }
                         }
                     }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < Q; ++j) {
-                cnt[j] = warp_sum_int(cnt[j]);
-                sw[j] = warp_sum(sw[j]);
-                if (SOFT) sr[j] = warp_sum(sr[j]);
-            }
-            if (lane == 0) {           // raw sums only: the per-(grid point, column) epilogue runs thread-parallel below
-                g_kd[g] = e2;
+            for (int u = 0; u < GU; ++u)
 #pragma unroll
                 for (int j = 0; j < Q; ++j) {
-                    const int o = g * Q + j;
-                    g_dev[o] = dev[j]; g_Bg[o] = Bg[j]; g_thr[o] = thr[j];
-                    if (CL) { g_P[o] = sr[j]; g_Q[o] = sw[j]; g_kl[o] = double(cnt[j]); }      // window partials
-                    else { g_sr[o] = sr[j]; g_sw[o] = sw[j]; g_scale[o] = double(cnt[j]); }
+                    cnt[u][j] = warp_sum_int(cnt[u][j]);
+                    sw[u][j] = warp_sum(sw[u][j]);
+                    if (SOFT) sr[u][j] = warp_sum(sr[u][j]);
+                }
+            if (lane == 0) {           // raw sums only: the per-(grid point, column) epilogue runs thread-parallel below
+#pragma unroll
+                for (int u = 0; u < GU; ++u) {
+                    const int g = g0 + u * SQ_WARPS;
+                    if (g < G) {
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) {
+                            const int o = g * Q + j;
+                            if (CL) { g_P[o] = sr[u][j]; g_Q[o] = sw[u][j]; g_kl[o] = double(cnt[u][j]); }   // window partials
+                            else { g_sr[o] = sr[u][j]; g_sw[o] = sw[u][j]; g_scale[o] = double(cnt[u][j]); }
+                        }
+                    }
                 }
             }
         }
+        SQB_CLK(5);
         if constexpr (CL) {        // sums over the windows of all CTAs of the cluster (fixed rank order) + the `bad` flags
             if (tid == 0) s_xg[Q * Q] = bad ? 1.0 : 0.0;
             cg::this_cluster().sync();
+            SQB_CLK(6);
             auto cl = cg::this_cluster();
             for (int o = tid; o < G * Q; o += SQ_THREADS) {
                 double a = 0.0, b2 = 0.0, c2 = 0.0;
@@ -416,6 +479,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             cl.sync();             // every remote read of the partial arrays is done before phase C reuses them
         }
         __syncthreads();
+        SQB_CLK(7);
         // ---- phase C: thread per (grid point, column) ------------------------------------------------------------------------
         for (int o = tid; o < G * Q; o += SQ_THREADS) {
             const int g = o / Q, j = o - g * Q;
@@ -464,10 +528,11 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             g_kd[g] = 1.0 / fmax(exp(lp), 1e-6);
         }
         __syncthreads();
+        SQB_CLK(8);
 
         // sample value of (s, g, j): f = refit mean + (L_f eps)_j; returns val, d val / d f pieces
-        auto sample_val = [&](int s, int g, int j, double& val, double& dv_f, double& sgn) {
-            double mf = mu[j], fs = 0.0, ms = 0.0;
+        auto sample_val = [&](int s, int g, int j, double mu_j, double& val, double& dv_f, double& sgn) {
+            double mf = mu_j, fs = 0.0, ms = 0.0;
 #pragma unroll
             for (int k = 0; k < Q; ++k) {
                 double shr = ((j == k) ? 1.0 : 0.0) - noise * s_Sinv[j * Q + k];
@@ -498,35 +563,45 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
 
         // ---- phase D: forward integration per column; arg-max over q per MC sample ----------------------------------------
         double ood[Q], scw[Q], snc[Q];
+        {
+            double v[2 * Q];
 #pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            ood[j] = SOFT ? sigmoid_acc((omega[j] - alpha_lvl) * inv_temp) : ((omega[j] >= alpha_lvl) ? 1.0 : 0.0);
-            double a1 = 0.0, a2 = 0.0;
-            for (int g = tid; g < G; g += SQ_THREADS) {
-                double mk = g_mask[g * Q + j], op = g_opt[g * Q + j];
-                a1 += mk * op * g_kd[g];
-                a2 += (1.0 - mk) * op;
+            for (int j = 0; j < Q; ++j) {
+                ood[j] = SOFT ? sigmoid_acc((omega[j] - alpha_lvl) * inv_temp) : ((omega[j] >= alpha_lvl) ? 1.0 : 0.0);
+                double a1 = 0.0, a2 = 0.0;
+                for (int g = tid; g < G; g += SQ_THREADS) {
+                    double mk = g_mask[g * Q + j], op = g_opt[g * Q + j];
+                    a1 += mk * op * g_kd[g];
+                    a2 += (1.0 - mk) * op;
+                }
+                v[2 * j] = a1; v[2 * j + 1] = a2;
             }
-            scw[j] = block_sum(a1, red, tid);
-            snc[j] = block_sum(a2, red, tid);
+            block_sum_n<2 * Q>(v, red_n, tid);
+#pragma unroll
+            for (int j = 0; j < Q; ++j) { scw[j] = v[2 * j]; snc[j] = v[2 * j + 1]; }
         }
         double tot_acq = 0.0;
         for (int s = 0; s < S; ++s) {
             double best = -INFINITY;
             int jbest = 0;
             bool isnan_any = false;
+            double v[2 * Q];
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
                 double A = 0.0, B = 0.0;
                 for (int g = tid; g < G; g += SQ_THREADS) {
                     double val, dv, sg;
-                    sample_val(s, g, j, val, dv, sg);
+                    sample_val(s, g, j, mu[j], val, dv, sg);
                     double mk = g_mask[g * Q + j], op = g_opt[g * Q + j];
                     A = fma(mk * op * g_kd[g], val, A);
                     B = fma((1.0 - mk) * op, val, B);
                 }
-                A = block_sum(A, red, tid);
-                B = block_sum(B, red, tid);
+                v[2 * j] = A; v[2 * j + 1] = B;
+            }
+            block_sum_n<2 * Q>(v, red_n, tid);
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                const double A = v[2 * j], B = v[2 * j + 1];
                 double r = (1.0 - ood[j]) * ((1.0 - alpha_lvl) * A / fmax(scw[j], 1e-6) + alpha_lvl * B / fmax(snc[j], 1e-6));
                 isnan_any = isnan_any || (r != r);
                 if (r > best) { best = r; jbest = j; }
@@ -537,52 +612,52 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                 for (int j = 0; j < Q; ++j) s_kap[s * MAX_Q + j] = (j == jbest) ? 1.0 / double(S) : 0.0;
         }
         __syncthreads();
+        SQB_CLK(9);
 
-        // ---- phase E: thread per grid point (reverse) ------------------------------------------------------------------------
+        // ---- phase E: thread per (grid point, column), whole warps per column (reverse) ---------------------------------------
         R.zero_partials();
         __syncthreads();
         {
-            double a_drc[Q], a_nrm[Q], a_om[Q], a_mu[Q], a_lf[Q][Q], a_shr[Q][Q], a_t1[Q], a_t2[Q], a_t4[Q], a_t3[Q][Q];
+            constexpr int TPJ = ((SQ_THREADS / Q) / 32) * 32;
+            const int jt = tid / TPJ, gt = tid - jt * TPJ;
+            const bool jact = jt < Q;                                      // warp-uniform
+            const int j = jact ? jt : 0;
+            double ood_j = ood[0], scw_j = scw[0], snc_j = snc[0], drc_j = drc[0], norm_j = norm[0], omega_j = omega[0], mu_j = mu[0];
 #pragma unroll
-            for (int j = 0; j < Q; ++j) {
-                a_drc[j] = a_nrm[j] = a_om[j] = a_mu[j] = a_t1[j] = a_t2[j] = a_t4[j] = 0.0;
+            for (int k = 1; k < Q; ++k)
+                if (k == j) { ood_j = ood[k]; scw_j = scw[k]; snc_j = snc[k]; drc_j = drc[k]; norm_j = norm[k]; omega_j = omega[k]; mu_j = mu[k]; }
+            double a_drc = 0.0, a_nrm = 0.0, a_om = 0.0, a_mu = 0.0, a_lf[Q], a_shr[Q];
 #pragma unroll
-                for (int k = 0; k < Q; ++k) a_lf[j][k] = a_shr[j][k] = a_t3[j][k] = 0.0;
-            }
-            if (!bad) {
-                for (int g = tid; g < G; g += SQ_THREADS) {
-                    double thr_bar[Q];
-#pragma unroll
-                    for (int j = 0; j < Q; ++j) thr_bar[j] = 0.0;
+            for (int k = 0; k < Q; ++k) a_lf[k] = a_shr[k] = 0.0;
+            if (!bad && jact) {
+                const double dcw = fmax(scw_j, 1e-6), dnc = fmax(snc_j, 1e-6);
+                const double c1 = (1.0 - ood_j) * (1.0 - alpha_lvl), c2 = (1.0 - ood_j) * alpha_lvl;
+                for (int g = gt; g < G; g += TPJ) {
+                    const int o = g * Q + j;
                     const double kd = g_kd[g];
+                    const double mk = g_mask[o], op = g_opt[o];
+                    const double cw = mk * op * kd, nc = (1.0 - mk) * op;
+                    const double wv = c1 * cw / dcw + c2 * nc / dnc;      // d res_sj / d val_sgj
+                    double cw_bar = 0.0, nc_bar = 0.0, meanf_bar = 0.0;
+                    double m_bar = 0.0;
+                    if (ext_adj) {                 // adjoints of an outer integration: masks and samples only
+                        if (qb.ext_f_bar)
+                            for (int s = 0; s < S; ++s) {
+                                const double f_bar = qb.ext_f_bar[((int64_t(c) * S + s) * G + g) * Q + j];
+                                meanf_bar += f_bar;
 #pragma unroll
-                    for (int j = 0; j < Q; ++j) {
-                        const int o = g * Q + j;
-                        const double mk = g_mask[o], op = g_opt[o];
-                        const double cw = mk * op * kd, nc = (1.0 - mk) * op;
-                        const double dcw = fmax(scw[j], 1e-6), dnc = fmax(snc[j], 1e-6);
-                        const double c1 = (1.0 - ood[j]) * (1.0 - alpha_lvl), c2 = (1.0 - ood[j]) * alpha_lvl;
-                        const double wv = c1 * cw / dcw + c2 * nc / dnc;      // d res_sj / d val_sgj
-                        double cw_bar = 0.0, nc_bar = 0.0, meanf_bar = 0.0;
-                        double m_bar = 0.0;
-                        if (ext_adj) {             // adjoints of an outer integration: masks and samples only
-                            if (qb.ext_f_bar)
-                                for (int s = 0; s < S; ++s) {
-                                    const double f_bar = qb.ext_f_bar[((int64_t(c) * S + s) * G + g) * Q + j];
-                                    meanf_bar += f_bar;
-#pragma unroll
-                                    for (int k = 0; k < Q; ++k)
-                                        if (k <= j) a_lf[j][k] = fma(f_bar, p.eps_mc[(int64_t(s) * G + g) * Q + k], a_lf[j][k]);
-                                }
-                        } else {
+                                for (int k = 0; k < Q; ++k)
+                                    if (k <= j) a_lf[k] = fma(f_bar, p.eps_mc[(int64_t(s) * G + g) * Q + k], a_lf[k]);
+                            }
+                    } else {
                         // two sweeps over the MC samples for the S > 1 cUCB mean term
                         for (int s = 0; s < S; ++s) {
                             const double kap = s_kap[s * MAX_Q + j];
                             if (kap == 0.0) continue;
                             double val, dv, sg;
-                            sample_val(s, g, j, val, dv, sg);
-                            cw_bar += kap * c1 * (val / dcw - ((scw[j] > 1e-6) ? s_A[s * MAX_Q + j] / (dcw * dcw) : 0.0));
-                            nc_bar += kap * c2 * (val / dnc - ((snc[j] > 1e-6) ? s_B[s * MAX_Q + j] / (dnc * dnc) : 0.0));
+                            sample_val(s, g, j, mu_j, val, dv, sg);
+                            cw_bar += kap * c1 * (val / dcw - ((scw_j > 1e-6) ? s_A[s * MAX_Q + j] / (dcw * dcw) : 0.0));
+                            nc_bar += kap * c2 * (val / dnc - ((snc_j > 1e-6) ? s_B[s * MAX_Q + j] / (dnc * dnc) : 0.0));
                             if (p.kind == 0 && !p.ext_values) m_bar += kap * wv * (1.0 - p.beta_prime * sg);
                         }
                         for (int s = 0; s < S; ++s) {
@@ -594,69 +669,76 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                             }
                             if (p.kind == 0) {
                                 double val, dv, sg = 0.0;
-                                if (kap != 0.0 && S > 1) sample_val(s, g, j, val, dv, sg);
+                                if (kap != 0.0 && S > 1) sample_val(s, g, j, mu_j, val, dv, sg);
                                 f_bar = kap * wv * p.beta_prime * sg + m_bar / double(S);
                                 if (S == 1) f_bar = kap * wv;
                             } else {
                                 if (kap == 0.0) continue;
                                 double val, dv, sg;
-                                sample_val(s, g, j, val, dv, sg);
+                                sample_val(s, g, j, mu_j, val, dv, sg);
                                 f_bar = kap * wv * dv;
                             }
                             meanf_bar += f_bar;
 #pragma unroll
                             for (int k = 0; k < Q; ++k)
-                                if (k <= j) a_lf[j][k] = fma(f_bar, p.eps_mc[(int64_t(s) * G + g) * Q + k], a_lf[j][k]);
-                        }
-                        }
-                        a_mu[j] += meanf_bar;
-#pragma unroll
-                        for (int k = 0; k < Q; ++k) a_shr[j][k] = fma(meanf_bar, g_dev[g * Q + k], a_shr[j][k]);
-                        if (SOFT) {
-                            const double mk_bar = ext_adj ? qb.ext_mask_bar[(int64_t(c) * G + g) * Q + j] : (cw_bar * kd - nc_bar) * op;
-                            const double M_bar = mk_bar * mk * (1.0 - mk) * inv_temp;
-                            const double scale = g_scale[o], srj = g_sr[o], swj = g_sw[o], kl = g_kl[o], Mraw = g_Mraw[o];
-                            double scale_bar = M_bar * (swj + 0.5 * drc[j]) / norm[j];
-                            const double D_bar = -kl * M_bar;
-                            scale_bar = fma(D_bar, 0.5 * omega[j], scale_bar);
-                            a_om[j] = fma(D_bar, 0.5 * scale, a_om[j]);
-                            const double P = M_bar * scale / norm[j];
-                            const double Qv = -scale_bar * scale / srj;
-                            a_drc[j] = fma(0.5, P, a_drc[j]);
-                            a_nrm[j] -= M_bar * Mraw / norm[j];
-                            g_P[o] = P * inv_temp; g_Q[o] = Qv * inv_temp;
-                            // candidate-vs-candidate rank terms: d/d(thr_j - thr_k) = Q_gj rhoc (1 - rhoc) / temp
-#pragma unroll
-                            for (int k = 0; k < Q; ++k) {
-                                if (k != j) {
-                                    double rc = sigmoid_acc(fmin(fmax((g_thr[o] - g_thr[g * Q + k]) * inv_temp, -745.0), 745.0));
-                                    double gc = Qv * inv_temp * rc * (1.0 - rc);
-                                    thr_bar[j] += gc; thr_bar[k] -= gc;
-                                }
-                            }
+                                if (k <= j) a_lf[k] = fma(f_bar, p.eps_mc[(int64_t(s) * G + g) * Q + k], a_lf[k]);
                         }
                     }
+                    a_mu += meanf_bar;
 #pragma unroll
-                    for (int j = 0; j < Q; ++j) {
-                        const double Bj = g_Bg[g * Q + j], tb = thr_bar[j];
-                        a_t1[j] += tb; a_t2[j] = fma(tb * Bj, Bj, a_t2[j]); a_t4[j] = fma(tb, Bj, a_t4[j]);
-#pragma unroll
-                        for (int k = 0; k < Q; ++k) a_t3[j][k] = fma(tb * Bj, g_dev[g * Q + k], a_t3[j][k]);
+                    for (int k = 0; k < Q; ++k) a_shr[k] = fma(meanf_bar, g_dev[g * Q + k], a_shr[k]);
+                    if (SOFT) {
+                        const double mk_bar = ext_adj ? qb.ext_mask_bar[(int64_t(c) * G + g) * Q + j] : (cw_bar * kd - nc_bar) * op;
+                        const double M_bar = mk_bar * mk * (1.0 - mk) * inv_temp;
+                        const double scale = g_scale[o], srj = g_sr[o], swj = g_sw[o], kl = g_kl[o], Mraw = g_Mraw[o];
+                        double scale_bar = M_bar * (swj + 0.5 * drc_j) / norm_j;
+                        const double D_bar = -kl * M_bar;
+                        scale_bar = fma(D_bar, 0.5 * omega_j, scale_bar);
+                        a_om = fma(D_bar, 0.5 * scale, a_om);
+                        const double P = M_bar * scale / norm_j;
+                        const double Qv = -scale_bar * scale / srj;
+                        a_drc = fma(0.5, P, a_drc);
+                        a_nrm -= M_bar * Mraw / norm_j;
+                        g_P[o] = P * inv_temp; g_Q[o] = Qv * inv_temp;
                     }
                 }
             }
+            __syncthreads();
+            // candidate-vs-candidate rank terms: d/d(thr_j - thr_k) = Q_gj rhoc (1 - rhoc) / temp, and rhoc (1 - rhoc) is the same
+            // for the pair (k, j): thr_bar_gj = sum_k rhoc (1 - rhoc) (Q_gj - Q_gk) / temp
+            double a_t1 = 0.0, a_t2 = 0.0, a_t4 = 0.0, a_t3[Q];
 #pragma unroll
-            for (int j = 0; j < Q; ++j) {
-                R.put(SqbIdx::drc(j), a_drc[j]); R.put(SqbIdx::nrm(j), a_nrm[j]); R.put(SqbIdx::om(j), a_om[j]);
-                R.put(SqbIdx::mu(j), a_mu[j]); R.put(SqbIdx::t1(j), a_t1[j]); R.put(SqbIdx::t2(j), a_t2[j]);
-                R.put(SqbIdx::t4(j), a_t4[j]);
+            for (int k = 0; k < Q; ++k) a_t3[k] = 0.0;
+            if (SOFT && !bad && jact) {
+                for (int g = gt; g < G; g += TPJ) {
+                    const int o = g * Q + j;
+                    const double thr_j = g_thr[o], gq_j = g_Q[o];
+                    double tb = 0.0;
+#pragma unroll
+                    for (int k = 0; k < Q; ++k)
+                        if (k != j) {
+                            const double rc = sigmoid_acc(fmin(fmax((thr_j - g_thr[g * Q + k]) * inv_temp, -745.0), 745.0));
+                            tb = fma(rc * (1.0 - rc), gq_j - g_Q[g * Q + k], tb);
+                        }
+                    const double Bj = g_Bg[o];
+                    a_t1 += tb; a_t2 = fma(tb * Bj, Bj, a_t2); a_t4 = fma(tb, Bj, a_t4);
+#pragma unroll
+                    for (int k = 0; k < Q; ++k) a_t3[k] = fma(tb * Bj, g_dev[g * Q + k], a_t3[k]);
+                }
+            }
+            SQB_CLK(19);
+            if (jact) {
+                R.put(SqbIdx::drc(j), a_drc); R.put(SqbIdx::nrm(j), a_nrm); R.put(SqbIdx::om(j), a_om);
+                R.put(SqbIdx::mu(j), a_mu); R.put(SqbIdx::t1(j), a_t1); R.put(SqbIdx::t2(j), a_t2);
+                R.put(SqbIdx::t4(j), a_t4);
 #pragma unroll
                 for (int k = 0; k < Q; ++k) {
-                    R.put(SqbIdx::lf(j, k), a_lf[j][k]); R.put(SqbIdx::shr(j, k), a_shr[j][k]); R.put(SqbIdx::t3(j, k), a_t3[j][k]);
+                    R.put(SqbIdx::lf(j, k), a_lf[k]); R.put(SqbIdx::shr(j, k), a_shr[k]); R.put(SqbIdx::t3(j, k), a_t3[k]);
                 }
             }
         }
         __syncthreads();
+        SQB_CLK(10);
         R.commit();
         __syncthreads();
         if (CL && crank != 0) {    // phases C-E ran redundantly: their totals count once (rank 0) in the cluster sum
@@ -667,6 +749,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
         // ---- pass 2: thread per train point, loop over the grid ------------------------------------------------------------------
         R.zero_partials();
         __syncthreads();
+        SQB_CLK(11);
         {
             double a_t1[Q], a_t2[Q], a_t4[Q], a_t3[Q][Q], a_bs[Q], a_si[Q][Q];
 #pragma unroll
@@ -675,9 +758,90 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
 #pragma unroll
                 for (int k = 0; k < Q; ++k) a_t3[j][k] = a_si[j][k] = 0.0;
             }
+            if constexpr (CL) {
+                // cluster window (N / 8 train points): the two halves of the block take the two halves of the grid for the same
+                // train point; the second half hands its moments over through shared memory, the first half finishes the row
+                constexpr int HT = SQ_THREADS / 2, XS = 3 + Q;
+                const int half = tid / HT, th = tid - half * HT;
+                const int Gh = (G + 1) / 2, g_lo = half ? Gh : 0, g_hi = half ? G : Gh;
+                for (int base = p_lo; base < p_hi; base += HT) {
+                    const int i = base + th;
+                    const bool ok = (i < i_hi) && !bad;                  // SOFT on this path
+                    const int ic = ok ? i : (i_lo < N ? i_lo : 0);
+                    const double ap = s_ap[ic], lv = s_lv[ic], dr = s_dr[ic], siv = s_siv[ic];
+                    double wp[Q], m0 = 0.0, mrr = 0.0, mr = 0.0, mrd[Q];
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) { wp[j] = s_wp[size_t(j) * Np + ic]; mrd[j] = 0.0; }
+                    if (ok) {
+#pragma unroll 2
+                        for (int g = g_lo; g < g_hi; ++g) {
+                            double rp = ap;
+#pragma unroll
+                            for (int j = 0; j < Q; ++j) rp = fma(-wp[j], g_Bg[g * Q + j], rp);
+                            const double sci = fma(-rp, rp, lv);
+                            double gam = 0.0;
+#pragma unroll
+                            for (int j = 0; j < Q; ++j) {
+                                const int o = g * Q + j;
+                                const double rho = soft_rho<true>((g_thr[o] - sci) * c1q, tab_s, p.k_magic, p.k_c0, p.k_c1n, p.k_c2, p.k_c3n);
+                                const double gj_ = fma(g_P[o], dr, g_Q[o]) * fma(-rho, rho, rho);
+                                gam += gj_;
+                                const double Bj = g_Bg[o], gB = gj_ * Bj;
+                                a_t1[j] += gj_; a_t2[j] = fma(gB, Bj, a_t2[j]); a_t4[j] += gB;
+#pragma unroll
+                                for (int k = 0; k < Q; ++k) a_t3[j][k] = fma(gB, g_dev[g * Q + k], a_t3[j][k]);
+                            }
+                            const double grp = gam * rp;
+                            m0 += gam; mrr = fma(grp, rp, mrr); mr += grp;
+#pragma unroll
+                            for (int k = 0; k < Q; ++k) mrd[k] = fma(grp, g_dev[g * Q + k], mrd[k]);
+                        }
+                    }
+                    if (half == 1) {
+                        double* x = s_x2 + th * XS;
+                        x[0] = m0; x[1] = mrr; x[2] = mr;
+#pragma unroll
+                        for (int k = 0; k < Q; ++k) x[3 + k] = mrd[k];
+                    }
+                    __syncthreads();
+                    if (half == 0 && i < p_hi) {
+                        if (!ok) {
+#pragma unroll
+                            for (int j = 0; j < Q; ++j) {
+                                qb.wbar[int64_t(r0 + j) * Np + i] = 0.0;
+                                if (i < N) s_wp[size_t(j) * Np + i] = 0.0;
+                            }
+                        } else {
+                            const double* x = s_x2 + th * XS;
+                            m0 += x[0]; mrr += x[1]; mr += x[2];
+#pragma unroll
+                            for (int k = 0; k < Q; ++k) mrd[k] += x[3 + k];
+                            const double iv = siv * siv;
+                            const double var_bar = iv * (m0 - 2.0 * mrr);
+                            const double vk = var_bar * noise * kvar;
+                            const uint32_t bits = p.zb[i];
+#pragma unroll
+                            for (int j = 0; j < Q; ++j) {
+                                double mrB = 0.0;
+#pragma unroll
+                                for (int k = 0; k < Q; ++k) mrB = fma(s_Sinv[j * Q + k], mrd[k], mrB);
+                                double zdot = 0.0;
+                                for (int s2 = 0; s2 < Sp; ++s2) zdot += ((bits >> s2) & 1u) ? s_C[j * MAX_SP + s2] : -s_C[j * MAX_SP + s2];
+                                const double w_ji = wp[j] / (noise * siv);
+                                qb.wbar[int64_t(r0 + j) * Np + i] = fma(vk, zdot, -2.0 * noise * siv * mrB);
+                                s_wp[size_t(j) * Np + i] = vk * w_ji;                   // zdot_bar_ji (this row's table entry is dead)
+                                a_bs[j] = fma(-2.0 * wp[j], mr, a_bs[j]);
+#pragma unroll
+                                for (int k = 0; k < Q; ++k) a_si[j][k] = fma(-2.0 * wp[j], mrd[k], a_si[j][k]);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            } else {
             // RI train points per thread are swept together: RI Q independent sigmoid chains, and the per-column totals
             // (which depend on the grid point only) are accumulated once per grid point for all RI rows
-            constexpr int RI = CL ? 1 : ((Q <= 2) ? 4 : 2);
+            constexpr int RI = (Q <= 2) ? 4 : 2;
             for (int i0 = p_lo + tid; i0 < p_hi; i0 += SQ_THREADS * RI) {
                 double ap[RI], lv[RI], dr[RI], siv[RI], vm[RI], wp[RI][Q], m0[RI], mrr[RI], mr[RI], mrd[RI][Q];
 #pragma unroll
@@ -761,6 +925,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                     }
                 }
             }
+            }
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
                 R.put(SqbIdx::t1(j), a_t1[j]); R.put(SqbIdx::t2(j), a_t2[j]); R.put(SqbIdx::t4(j), a_t4[j]);
@@ -770,6 +935,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             }
         }
         __syncthreads();
+        SQB_CLK(12);
         R.commit();
         // C_bar_js (train part) = sum_i (+-) zdot_bar_ji: thread = (pair (j, s), slice of the train points), then a fixed-order sum
         {
@@ -794,6 +960,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             }
         }
         __syncthreads();
+        SQB_CLK(13);
         if constexpr (CL) {        // totals and C_bar over the windows: rank 0 sums them (fixed rank order)
             auto cl = cg::this_cluster();
             cl.sync();
@@ -820,6 +987,7 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             }
         }
 
+        SQB_CLK(14);
         // ---- final: q x q algebra (one thread; rank 0 of the cluster) ------------------------------------------------------------
         if (tid == 0 && crank == 0) {
             double Si[Q][Q], Lf[Q][Q], shr[Q][Q], shr_bar[Q][Q], Sinv_bar[Q][Q];
@@ -942,12 +1110,14 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
             if (!ext_adj) p.acq[c] = tot_acq / double(S);
         }
         __syncthreads();
+        SQB_CLK(15);
         if constexpr (CL) {        // ut_bar lives in rank 0's shared memory
             auto cl = cg::this_cluster();
             cl.sync();
             if (crank != 0 && tid < MAX_Q * MAX_SP) s_utb[tid] = cl.map_shared_rank(s_utb, 0)[tid];
             __syncthreads();
         }
+        SQB_CLK(16);
         // fold the probe term into the right-hand sides: w_bar'_j = w_bar_j + z ut_bar_j   (T = A^-1 z)
         if (SOFT && !bad)
             for (int i = i_lo + tid; i < i_hi; i += SQ_THREADS) {
@@ -960,7 +1130,9 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
                 }
             }
         __syncthreads();
+        SQB_CLK(17);
         if constexpr (CL) cg::this_cluster().sync();      // remote shared memory stays valid until every CTA is done with it
+        SQB_CLK(18);
     }
 }
 
