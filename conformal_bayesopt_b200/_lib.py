@@ -16,7 +16,7 @@ EXPORTS = [
     "cbo_cehvi_integrate_f64", "cbo_cehvi_integrate_q_f64", "cbo_cehvi_integrate_q_grad_f64", "cbo_conformal_acq_grad_f64", "cbo_workspace_bytes_grad",
     "cbo_model_workspace_bytes", "cbo_model_build_f64",
     "cbo_model_append_workspace_bytes", "cbo_model_append_f64",
-    "cbo_ratio_train_workspace_bytes", "cbo_ratio_train_step_f64", "cbo_sgld_update_f64", "cbo_launch_count",
+    "cbo_ratio_train_workspace_bytes", "cbo_ratio_train_step_f64", "cbo_sample_subset_i64", "cbo_sgld_update_f64", "cbo_launch_count",
 ]
 
 c_dp = C.c_void_p  # device pointers travel as integers
@@ -139,6 +139,8 @@ def load():
     lib.cbo_ratio_train_step_f64.argtypes = [C.c_int64, C.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int64, c_dp, c_dp,
                                              C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                              C.c_double, C.c_double, c_dp, c_dp, C.c_size_t, c_dp]
+    lib.cbo_sample_subset_i64.restype = C.c_int
+    lib.cbo_sample_subset_i64.argtypes = [C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.cbo_sgld_update_f64.restype = C.c_int
     lib.cbo_sgld_update_f64.argtypes = [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int64, C.c_int64, C.c_double, C.c_double,
                                         C.c_double, C.c_double, C.c_double, c_dp]
@@ -146,7 +148,7 @@ def load():
     lib.cbo_timing_enable.argtypes = [C.c_int]
     lib.cbo_timing_collect.restype = C.c_int
     lib.cbo_timing_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
-    if lib.cbo_version() != 103:
+    if lib.cbo_version() != 104:
         raise CboError(f"libcbo.so version mismatch: {lib.cbo_version()}")
     _LIB = lib
     return lib

@@ -509,6 +509,17 @@ int cbo_ratio_train_step_f64(int64_t d, int64_t hidden, double* theta, double* a
     return CBO_OK;
 }
 
+int cbo_sample_subset_i64(int64_t n, int64_t k, uint64_t seed, int64_t* out_idx, void* stream) {
+    if (n <= 0 || k < 0 || k > n || (k > 0 && !out_idx)) return CBO_ERR_INVALID_ARG;
+    if (n > (int64_t(1) << 31)) return CBO_ERR_UNSUPPORTED;
+    if (k == 0) return CBO_OK;
+    int half_bits = 1;
+    while ((int64_t(1) << (2 * half_bits)) < n) ++half_bits;
+    CBO_LAUNCHED(), cbo::k_sample_subset<<<int((k + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, k, seed, half_bits, out_idx);
+    CBO_CUDA(cudaGetLastError());
+    return CBO_OK;
+}
+
 int cbo_sgld_update_f64(double* X, double* momentum_buf, const double* dacq_dX, const double* noise, const double* lb,
                         const double* ub, int64_t n_rows, int64_t d, double lr, double momentum, double temperature,
                         double penalty_scale, double penalty_width, void* stream) {

@@ -266,4 +266,34 @@ __global__ void k_sgld_update(double* __restrict__ X, double* __restrict__ buf, 
     X[e] = x + b;
 }
 
+// k distinct pseudo-random indices out of [0, n): out[t] = P(t), P a keyed bijection of [0, n) -- a 6-round Feistel network on
+// the next even-bit-width power of two (<= 4 n points) with cycle walking back into range (expected < 4 rounds per index).
+// The first k values of a pseudo-random permutation: what RatioEstimator.optimize_callback draws with
+// np.random.permutation(num_positive)[:num_negative] (conformalbo/ratio_estimation.py:129-131) without building the permutation.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return x;
+}
+__global__ void k_sample_subset(int64_t n, int64_t k, uint64_t seed, int half_bits, int64_t* __restrict__ out) {
+    const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    const uint32_t mask = (1u << half_bits) - 1u;
+    uint32_t key[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) key[r] = mix32(uint32_t(seed >> ((r & 1) ? 32 : 0)) + 0x9e3779b9u * uint32_t(r + 1));
+    uint64_t x = uint64_t(t);
+    do {
+        uint32_t L = uint32_t(x >> half_bits) & mask, R = uint32_t(x) & mask;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const uint32_t F = mix32(R ^ key[r]) & mask;
+            const uint32_t nl = R;
+            R = L ^ F;
+            L = nl;
+        }
+        x = (uint64_t(L) << half_bits) | R;
+    } while (x >= uint64_t(n));
+    out[t] = int64_t(x);
+}
+
 }  // namespace cbo

@@ -451,6 +451,25 @@ def ratio_train_step(theta: torch.Tensor, adam_m: torch.Tensor, adam_v: torch.Te
     return workspace
 
 
+def sample_subset(n: int, k: int, seed: int, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cbo_sample_subset_i64: k distinct pseudo-random indices out of [0, n) (the first k values of a keyed permutation), drawn
+    on the device in one launch -- the minibatch draw of RatioEstimator.optimize_callback (ratio_estimation.py:129-131)."""
+    global LAUNCH_COUNT
+    lib = _lib.load()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.CboError("sample_subset draws on the device (libcbo has no CPU path)")
+    if out is None or out.numel() < k:
+        out = torch.empty(max(k, 1), dtype=torch.int64, device=device)
+    assert out.dtype == torch.int64 and out.is_contiguous() and out.device.type == "cuda"
+    with torch.cuda.device(out.device):
+        st = lib.cbo_sample_subset_i64(int(n), int(k), int(seed) & 0xFFFFFFFFFFFFFFFF, out.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream)
+    _lib.check(st, "cbo_sample_subset_i64")
+    LAUNCH_COUNT += 1
+    return out[:k]
+
+
 def sgld_update(X: torch.Tensor, momentum_buf: Optional[torch.Tensor], dacq_dX: torch.Tensor, noise: torch.Tensor,
                 lb: torch.Tensor, ub: torch.Tensor, *, lr: float, momentum: float, temperature: float,
                 penalty_scale: float = 1e2, penalty_width: float = 1e-2):

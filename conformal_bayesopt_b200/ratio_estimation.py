@@ -41,7 +41,12 @@ class RatioEstimator(nn.Module):
         self._train = None                # device training state, created by the first training step
         self._pos_pool, self._num_pos = None, 0
         self._neg_dev = None
-        self.device_permutation = False   # True: draw the positive minibatch with torch.randperm on the device
+        # True (default): the positive minibatch is drawn on the device (cbo_sample_subset_i64, one launch, seeded from
+        # torch's seed at construction + the step count); False: the reference's own host draw, np.random.permutation
+        # (ratio_estimation.py:129-131) -- the parity setting the reference-executed goldens are checked with
+        self.device_permutation = True
+        self._perm_seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+        self._perm_idx = None
         self.last_loss = None             # device scalar, minibatch loss of the latest step
 
     def set_neg_samples(self, neg_samples):
@@ -164,12 +169,15 @@ class RatioEstimator(nn.Module):
             return None
         if self._neg_dev is None or self._neg_dev[0] is not self._neg_samples or self._neg_dev[1].device != device:
             self._neg_dev = (self._neg_samples, self._neg_samples.detach().to(device, torch.float64).contiguous())
+        t = self._train_state(device)
         if self.device_permutation:
-            idx = torch.randperm(num_positive, device=device)[:num_negative].contiguous()
+            if self._perm_idx is None or self._perm_idx.numel() < num_negative or self._perm_idx.device != device:
+                self._perm_idx = torch.empty(num_negative, dtype=torch.int64, device=device)
+            idx = ops.sample_subset(num_positive, num_negative, self._perm_seed + 0x9E3779B97F4A7C15 * (t["step"] + 1), device,
+                                    out=self._perm_idx)
         else:       # the reference's generator and draw (:129-131), 8 bytes per row to the device
             from .helpers import _PinnedRing
             idx = _PinnedRing.upload(torch.from_numpy(np.random.permutation(num_positive)[:num_negative].copy()), device)
-        t = self._train_state(device)
         t["step"] += 1
         t["ws"] = ops.ratio_train_step(t["theta"], t["m"], t["v"], t["target"], x_neg=self._neg_dev[1],
                                        x_pos=self._pos_pool, pos_idx=idx, n_pos=num_negative, step=t["step"],

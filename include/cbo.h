@@ -20,6 +20,7 @@
  *   cbo_model_build_f64 / cbo_model_append_f64   the model refit before the path (conformalbo/utils.py:382-390) and the
  *                              observations a BO round adds (scripts/black_box_opt.py:154-155).
  *   cbo_ratio_train_step_f64   RatioEstimator.optimize_callback (ratio_estimation.py:110-144).
+ *   cbo_sample_subset_i64      the minibatch draw of the same callback (ratio_estimation.py:129-131) on the device.
  *   cbo_sgld_update_f64        the SGLD / SGHMC step of optimize_acqf_sgld (optim/sgld.py:9-47, optim/optimize.py:224-235).
  *
  * Conventions
@@ -52,7 +53,7 @@
 extern "C" {
 #endif
 
-#define CBO_VERSION 103
+#define CBO_VERSION 104
 
 typedef enum {
     CBO_OK = 0,
@@ -275,6 +276,12 @@ int cbo_ratio_train_step_f64(int64_t d, int64_t hidden, double* theta, double* a
                              int64_t n_pos, int64_t step, double lr, double beta1, double beta2, double eps,
                              double weight_decay, double ema_weight, double* loss, void* workspace,
                              size_t workspace_bytes, void* stream);
+
+/* The positive minibatch of RatioEstimator.optimize_callback drawn on the device: k distinct indices out of [0, n), the first
+ * k values of a keyed pseudo-random permutation of [0, n) (what conformalbo/ratio_estimation.py:129-131 takes from
+ * np.random.permutation(num_positive)[:num_negative], without building the permutation and without the host).  The same
+ * (n, k, seed) gives the same indices; out_idx (k int64) feeds cbo_ratio_train_step_f64's pos_idx.  n <= 2^31.  One launch. */
+int cbo_sample_subset_i64(int64_t n, int64_t k, uint64_t seed, int64_t* out_idx, void* stream);
 
 /* One SGLD / SGHMC update of the candidates inside optimize_acqf_sgld (conformalbo/optim/optimize.py:224-235 with
  * conformalbo/optim/sgld.py:9-47): gradient of  -sum(acq) + penalty_scale * (sigmoid((lb - X)/w).mean() +

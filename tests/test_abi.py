@@ -23,7 +23,7 @@ def test_header_symbols_are_exported():
     for name in declared:
         assert hasattr(lib, name), name
     lib.cbo_status_str.restype = ctypes.c_char_p
-    assert lib.cbo_version() == 103
+    assert lib.cbo_version() == 104
     assert lib.cbo_status_str(0) == b"ok" and lib.cbo_status_str(2) == b"unsupported shape"
     lib.cbo_padded_n.restype = ctypes.c_int64
     lib.cbo_padded_n.argtypes = [ctypes.c_int64]

@@ -48,7 +48,7 @@ def _close(a, b, rtol=RTOL, atol=1e-9):
 def test_library_loaded_is_in_tree():
     from conformal_bayesopt_b200 import _lib
     lib = _lib.load()
-    assert lib.cbo_version() == 103
+    assert lib.cbo_version() == 104
     assert "conformal_bayesopt_b200/lib/libcbo.so" in _lib.lib_path()
 
 

@@ -66,6 +66,7 @@ def test_ratio_estimator_class_trains_like_the_reference(gold, idx):
                          weight_decay=case["weight_decay"])
     torch.nn.utils.vector_to_parameters(case["theta0"].to(DEV).clone(), est.classifier.parameters())
     est.set_neg_samples(case["neg"].to(DEV))
+    est.device_permutation = False                        # parity setting: the reference's np.random minibatch draw
     np.random.seed(case["seed"])
     flat = lambda net: torch.cat([p.detach().reshape(-1) for p in net.parameters()])
     for k, xk in enumerate(case["callbacks"]):
@@ -297,3 +298,52 @@ def test_train_step_rejects_unsupported_shapes():
     st = lib.cbo_ratio_train_step_f64(2, 64, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, z.data_ptr(),
                                       None, 1, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1e-2, None, z.data_ptr(), 64, None)
     assert st == 1                                                        # CBO_ERR_INVALID_ARG: step is 1-based
+
+
+def test_sample_subset_draws_distinct_indices_on_the_device():
+    """cbo_sample_subset_i64 (the device-side minibatch draw of RatioEstimator.optimize_callback): k distinct indices in
+    [0, n), reproducible for a seed, different across seeds, every index about equally likely, also at the edges
+    (k = n is a permutation, n = 1, n just above a power of four)."""
+    from conformal_bayesopt_b200 import ops, _lib
+    for n, k in [(1, 1), (2, 2), (5, 3), (257, 257), (1025, 64), (31392, 1024), (4 ** 8 + 1, 4096)]:
+        a = ops.sample_subset(n, k, 1234, DEV).clone()
+        b = ops.sample_subset(n, k, 1234, DEV).clone()
+        c = ops.sample_subset(n, k, 1235, DEV).clone()
+        assert a.shape == (k,) and torch.equal(a, b)
+        assert int(a.min()) >= 0 and int(a.max()) < n and a.unique().numel() == k
+        if n > 64 and k < n:
+            assert not torch.equal(a, c)
+    n, k, reps = 200, 50, 400
+    counts = torch.zeros(n, dtype=torch.float64, device=DEV)
+    for s in range(reps):
+        counts.index_add_(0, ops.sample_subset(n, k, 77 + s, DEV), torch.ones(k, dtype=torch.float64, device=DEV))
+    expect = reps * k / n                                  # 100 per index; binomial sd ~ 8.7
+    assert float((counts - expect).abs().max()) < 6 * (expect * (1 - k / n)) ** 0.5
+    chi2 = float(((counts - expect) ** 2 / (expect * (1 - k / n))).sum())
+    assert 0.5 * n < chi2 < 1.6 * n
+    with pytest.raises(_lib.CboError):
+        ops.sample_subset(4, 5, 0, DEV)
+
+
+def test_callback_minibatch_draw_on_the_device_is_seeded_and_trains():
+    """Default RatioEstimator: the positive minibatch comes from cbo_sample_subset_i64 (no host RNG, no upload); two estimators
+    built under the same torch seed train identically, and the loss falls on a separable problem."""
+    from conformal_bayesopt_b200.ratio_estimation import RatioEstimator
+    d = 3
+    g = torch.Generator().manual_seed(5)
+    neg = torch.rand(64, d, dtype=torch.float64, generator=g).to(DEV)
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(11)
+        est = RatioEstimator(in_size=d, device=DEV, dtype=torch.float64, lr=5e-3, ema_weight=2e-2, weight_decay=5e-6)
+        assert est.device_permutation
+        est.set_neg_samples(neg)
+        gg = torch.Generator().manual_seed(6)
+        losses = []
+        for step in range(60):
+            est.optimize_callback((0.2 * torch.rand(16, d, dtype=torch.float64, generator=gg) + 2.0).to(DEV))
+            if est.last_loss is not None:
+                losses.append(float(est.last_loss))
+        outs.append((est._train["theta"].clone(), losses))
+    assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+    assert len(outs[0][1]) > 20 and outs[0][1][-1] < 0.7 * outs[0][1][0]

@@ -12,7 +12,7 @@ for N in (256, 1024):
     p = make_problem(N, d, seed=0)
     st = GPModelState.fit_fixed(p["X"], p["y"], p["mean"], p["lengthscale"], p["outputscale"], p["noise"], device=dev)
     rw = ops.RatioWeights(*[t.to(dev) for t in make_ratio_weights(d)])
-    for (b, q) in ((8, 2), (8, 1), (8, 4)):
+    for (b, q) in ((8, 2), (8, 1), (8, 4)) + (((4, 2), (6, 2)) if os.environ.get("SGS_SMALL") else ()):
         inp = make_inputs(N, d, b, q, G, seed=3)
         kw = dict(kind="ucb", alpha=N ** -0.35, temp=3e-2, grid_res=G, randomized=True, optimistic=True, beta_prime=1.0, ratio=rw)
         gacq = GraphedConformalAcq(st, b, q, eps_grid=inp["eps_grid"].to(dev), eps_mc=inp["eps_mc"].to(dev), **kw)

@@ -20,6 +20,7 @@ for N in (80, 1024):
     torch.manual_seed(0); np.random.seed(0)
     est = RatioEstimator(in_size=d, device=dev, dtype=torch.float64, lr=5e-3, ema_weight=2e-2, weight_decay=5e-6)
     est.set_neg_samples(p["X"].to(dev))
+    est.device_permutation = False      # first the reference's own host draw (np.random.permutation), then the device draw (the default)
     acq = qConformalUpperConfidenceBound(alpha=N ** -0.35, temp=3e-2, grid_res=G, max_grid_refinements=0,
                                          ratio_estimator=est, randomized=True, model=st, beta=0.2)
     bounds = torch.stack([torch.zeros(d), torch.ones(d)]).to(dev, torch.float64)
