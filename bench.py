@@ -345,6 +345,33 @@ def run_ours(args):
                                 "grid=64, cucb, randomised, ratio estimator), CUDA-graph replay, fresh probes and uniforms per step",
                     "ms_per_call": ms_s, "value": 8 * GRID / (ms_s * 1e-3), "unit": "evals/s (joint batches x grid points)"}
 
+        # the whole inner loop of optimize_acqf_sgld as the reference runs it (optim/optimize.py:196-247: callback = one training
+        # step of the ratio estimator per SGLD step after warm-up, value + gradient, SGHMC update, trajectory scored at the end)
+        from conformal_bayesopt_b200.acquisitions import qConformalUpperConfidenceBound
+        from conformal_bayesopt_b200.optim import optimize_acqf_sgld
+        from conformal_bayesopt_b200.ratio_estimation import RatioEstimator
+        torch.manual_seed(0)
+        est = RatioEstimator(in_size=DIM, device=dev, dtype=torch.float64, lr=5e-3, ema_weight=2e-2, weight_decay=5e-6)
+        est.set_neg_samples(state.X[:N_TRAIN].contiguous())
+        cacq = qConformalUpperConfidenceBound(alpha=N_TRAIN ** -0.35, temp=args.temp, grid_res=GRID, max_grid_refinements=0,
+                                              ratio_estimator=est, randomized=True, model=state, beta=0.2)
+        cacq.device_probes = True
+        bnds = torch.stack([torch.zeros(DIM), torch.ones(DIM)]).to(dev, torch.float64)
+        ics = torch.rand(8, 2, DIM, dtype=torch.float64, device=dev)
+
+        def sgld_loop(n):
+            torch.cuda.synchronize()
+            t0_ = _time.perf_counter()
+            optimize_acqf_sgld(cacq, bnds, q=2, num_restarts=8, batch_initial_conditions=ics, sgld_steps=n, warmup_steps=32, lr=2e-2,
+                               temperature=4e-3, return_full_traj=True, options=dict(callback=est.optimize_callback))
+            torch.cuda.synchronize()
+            return _time.perf_counter() - t0_
+        sgld_loop(40)
+        t128 = min(sgld_loop(128) for _ in range(2))
+        t512 = min(sgld_loop(512) for _ in range(2))
+        cfg_sgld["loop"] = {"workload": "optimize_acqf_sgld, 8 restarts x q=2, ratio estimator trained by the callback, graph-replayed "
+                                        "steps, probes and minibatch drawn on the device, trajectory scored at the end",
+                            "ms_per_step_128_steps_all_in": t128 / 128 * 1e3, "ms_per_step_marginal": (t512 - t128) / 384 * 1e3}
 
     # ---- density-ratio-weighted, randomised leg (seeded MLP 8->64->64->1, randomized=True with injected uniforms) at
     # the headline size, device-resident; rank 0, outside the timed region; with its own per-kernel times and roofline fraction

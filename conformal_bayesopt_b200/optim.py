@@ -140,6 +140,9 @@ def optimize_acqf_sgld(
             raise ValueError("Must specify `raw_samples` when `batch_initial_conditions` is `None`.")
         batch_initial_conditions = gen_batch_initial_conditions(acq_function, bounds, q, num_restarts, raw_samples, options)
     batch_limit = options.get("batch_limit", num_restarts)
+    # the trajectory is scored in calls of up to `score_batch_limit` joint batches: the reference scores it `batch_limit` at a
+    # time (optimize.py:243-246, a memory limit of its dense path) -- here that would be one ~0.1 ms latency-path call per step
+    score_limit = max(int(options.get("score_batch_limit", 4096)), 1)
     # one contiguous (restarts, q, d) fp64 buffer per optimiser batch, updated in place
     batched_ics = [b.contiguous() for b in
                    batch_initial_conditions.detach().to(bounds.device, torch.float64).clone().split(batch_limit)]
@@ -168,7 +171,7 @@ def optimize_acqf_sgld(
     batch_candidates = torch.cat([torch.stack(it, dim=1) for it in sgld_iterates])      # (restarts, T, q, d)
     if return_full_traj:
         with torch.no_grad():
-            batch_acq_values = torch.cat([acq_function(c) for c in batch_candidates.flatten(0, -3).split(batch_limit)
+            batch_acq_values = torch.cat([acq_function(c) for c in batch_candidates.flatten(0, -3).split(score_limit)
                                           ]).view(batch_candidates.shape[:-2])
     else:
         select_cands, select_vals = [], []
@@ -178,7 +181,7 @@ def optimize_acqf_sgld(
                 feas = cand_traj[in_bounds]
                 if feas.shape[0] == 0:
                     raise RuntimeError("no SGLD iterate of a restart lies inside the bounds")
-                vals = torch.cat([acq_function(c) for c in feas.split(batch_limit)])
+                vals = torch.cat([acq_function(c) for c in feas.split(score_limit)])
                 best = vals.argmax(0)
                 select_cands.append(feas[best])
                 select_vals.append(vals[best])

@@ -59,9 +59,14 @@ class RatioEstimator(nn.Module):
     def num_positive(self) -> int:
         return self._num_pos
 
-    @staticmethod
-    def _token(net):
-        return tuple((p.data_ptr(), p._version) for p in net.parameters())
+    def _token(self, net):
+        # (storage, version) of every parameter; the parameter list of a module is walked once (nn.Module.parameters() costs
+        # ~10 us per call, and a training step asks half a dozen times) and again only if the module object is replaced
+        cache = self.__dict__.setdefault("_param_lists", {})
+        ent = cache.get(id(net))
+        if ent is None or ent[0] is not net:
+            ent = cache[id(net)] = (net, list(net.parameters()))
+        return tuple((p.data_ptr(), p._version) for p in ent[1])
 
     def _train_state(self, device):
         """Flat fp64 device vectors (theta, Adam moments, target) shared with the kernels.  The nn modules stay the

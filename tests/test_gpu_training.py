@@ -216,7 +216,8 @@ def test_graph_replay_loop_matches_the_direct_loop_bitwise():
         acq.fixed_uniforms = torch.rand(5, 32, 2, dtype=torch.float64, generator=torch.Generator().manual_seed(4)).to(DEV)
         traj, vals = optimize_acqf_sgld(acq, bounds, q=2, num_restarts=5, batch_initial_conditions=ics, sgld_steps=24,
                                         warmup_steps=4, lr=1e-2, temperature=4e-3, return_full_traj=True,
-                                        options=dict(callback=est.optimize_callback, cuda_graph=use_graph))
+                                        options=dict(callback=est.optimize_callback, cuda_graph=use_graph,
+                                                     score_batch_limit=5))    # fixed_uniforms are sized for 5 joint batches per call
         res.append((traj.clone(), vals.clone(), est._train["target"].clone()))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
 
