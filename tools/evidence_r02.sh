@@ -22,6 +22,8 @@ python tools/prof_grad_run.py 65536 2 > $O/r02_prof_grad_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o $O/prof_r02_grad \
     python tools/prof_grad_run.py 65536 2 > $O/r02_ncu_grad.log 2>&1
 python tools/sgld_step_time.py > $O/r02_sgld_step_time.log 2>&1
+python tools/sgld_loop_time.py > $O/r02_sgld_loop_time.log 2>&1
+python tools/sgld_graph_step.py > $O/r02_sgld_graph_step.log 2>&1
 # the .ncu-rep files (60-70 MB each) exceed what gpurun copies back: summarise them here and drop them
 { echo "==== forward call, 65536 candidates (tools/prof_run.py) ===="; python tools/ncu_summary.py $O/prof_r02_fwd.ncu-rep;
   echo; echo "==== value + gradient call, 65536 candidates (tools/prof_grad_run.py) ===="; python tools/ncu_summary.py $O/prof_r02_grad.ncu-rep; } > $O/r02_ncu_summary_final.txt 2>&1
