@@ -100,6 +100,7 @@ struct Workspace {
     double *val_bar, *cv_bar;                         // cNEI gradient only: C x S x G value adjoints, C x nb adjoints of c
     double* splitk;                                   // split-K partial tiles (calls with <= 32 candidate points)
     double* splitk2;                                  // ... of the probe solves, which run beside the candidates' on the latency path
+    double* U2;                                       // latency path: second copy of the kernel rows for u^T T (runs beside pass 2)
     double *X3, *adj;                                 // gradient only: C x Np solve scratch, C x ADJ_STRIDE adjoints
     size_t bytes;
 };
@@ -139,6 +140,7 @@ Workspace carve(void* ws, int64_t N, int64_t d, int64_t b, const cbo_params* p, 
     w.nei_values = c.take<double>((p->kind == CBO_ACQ_NEI || p->kind == CBO_ACQ_JOINT) ? C * p->num_mc * p->grid_res : 1);
     w.splitk = c.take<double>(cbo::gemm_splitk_scratch_doubles((int)Np));
     w.splitk2 = c.take<double>(cbo::gemm_splitk_scratch_doubles((int)Np));
+    w.U2 = c.take<double>(int64_t(cbo::GEMM_SPLITK_MAX_M) * Np);
     const bool nei_kind = p->kind == CBO_ACQ_NEI || p->kind == CBO_ACQ_JOINT;
     w.val_bar = c.take<double>(grad && nei_kind ? C * p->num_mc * p->grid_res : 1);
     w.cv_bar = c.take<double>(grad && nei_kind ? C * cbo::NEI_MAX_NB : 1);
@@ -576,14 +578,14 @@ int cbo_conf_mask_to_bounds_f64(const double* grid, const double* mask, int64_t 
 struct SideStream {
     std::mutex mu, call_mu;
     cudaStream_t st = nullptr, st2 = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr, ev_T = nullptr, ev_tables = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr, ev_T = nullptr, ev_tables = nullptr, ev_rows = nullptr, ev_ut = nullptr;
     cudaError_t ensure() {
         std::lock_guard<std::mutex> l(mu);
         if (st) return cudaSuccess;
         cudaStream_t x, y;
         if (cudaError_t e = cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking); e != cudaSuccess) return e;
         if (cudaError_t e = cudaStreamCreateWithFlags(&y, cudaStreamNonBlocking); e != cudaSuccess) return e;
-        for (cudaEvent_t* ev : {&fork, &join, &join2, &ev_T, &ev_tables})
+        for (cudaEvent_t* ev : {&fork, &join, &join2, &ev_T, &ev_tables, &ev_rows, &ev_ut})
             if (cudaError_t e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming); e != cudaSuccess) return e;
         st2 = y;
         st = x;
@@ -646,7 +648,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             side_lock = std::unique_lock<std::mutex>(side->call_mu);
             CBO_CUDA(cudaEventRecord(side->fork, s));
             CBO_CUDA(cudaStreamWaitEvent(side->st2, side->fork, 0));
-            if (ratio) CBO_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+            CBO_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));      // (u^T T runs there also without a ratio estimator)
         }
     }
     cudaStream_t s_ratio = side ? side->st : s;       // density-ratio MLP launches
@@ -696,7 +698,8 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             // latency path: the rows do not wait for T (the probe branch); u^T T follows between the two passes
             CBO_CUDA(cbo::launch_kernel_rows(Xc, n, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale, gp->mean,
                                              gp->alpha, side ? nullptr : w.T, Sp, w.UW, w.mu, side ? nullptr : w.ut, num_sms(), s,
-                                             splitk != nullptr));
+                                             splitk != nullptr, side ? w.U2 : nullptr));
+            if (side) CBO_CUDA(cudaEventRecord(side->ev_rows, s));
             if (ratio)
                 CBO_CUDA(cbo::launch_ratio_mlp(Xc, n, d, (int)ratio->hidden, ratio->W1, ratio->b1, ratio->W2, ratio->b2,
                                                ratio->W3, ratio->b3, 1e-6, w.drc, num_sms(), s_ratio));
@@ -708,9 +711,12 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
             TimeScope ts_(T_GEMM1, s, 1);
             CBO_CUDA(cbo::launch_gemm_tn(w.UW, Np, gp->linv, Np, w.V, Np, n, Np, Np, cbo::TRI_LOWER, w.rn, s, num_sms(), splitk));
         }
-        if (side) {   // u^T T from the stored rows, before pass 2 overwrites them (same accumulation order as the fused kernel)
-            CBO_CUDA(cudaStreamWaitEvent(s, side->ev_T, 0));
-            CBO_LAUNCHED(), cbo::k_ut_small<<<n, cbo::ROWS_SMALL_THREADS, 0, s>>>(w.UW, N, Np, w.T, Sp, w.ut);
+        if (side) {   // u^T T from a second copy of the stored rows, on the third stream beside pass 2 (which overwrites the rows);
+                      // same accumulation order as the fused kernel: same bits
+            CBO_CUDA(cudaStreamWaitEvent(side->st, side->ev_rows, 0));
+            CBO_CUDA(cudaStreamWaitEvent(side->st, side->ev_T, 0));
+            CBO_LAUNCHED(), cbo::k_ut_small<<<n, cbo::ROWS_SMALL_THREADS, 0, side->st>>>(w.U2, N, Np, w.T, Sp, w.ut);
+            CBO_CUDA(cudaEventRecord(side->ev_ut, side->st));
         }
         {
             TimeScope ts_(T_GEMM2, s, 1);
@@ -718,6 +724,7 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
         }
         if (side) {   // join: per-train-point tables (probe branch) and the candidates' density ratios ahead of the score kernel
             CBO_CUDA(cudaStreamWaitEvent(s, side->ev_tables, 0));
+            CBO_CUDA(cudaStreamWaitEvent(s, side->ev_ut, 0));            // (behind the candidates' density ratios on that stream)
             if (ratio) CBO_CUDA(cudaStreamWaitEvent(s, side->join2, 0));
         }
 

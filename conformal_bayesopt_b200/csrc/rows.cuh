@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(ROWS_SMALL_THREADS)
 k_kernel_rows_small(const double* __restrict__ Xq, int n, const double* __restrict__ XsT, int N, int Np, int d,
                     const double* __restrict__ inv_ls, double outputscale, double mean, const double* __restrict__ alpha,
                     const double* __restrict__ T, int Sp, double* __restrict__ U, double* __restrict__ mu,
-                    double* __restrict__ ut) {
+                    double* __restrict__ ut,
+                    double* __restrict__ U2 = nullptr) {
     __shared__ double s_x[MAX_D], s_tab[16], s_red[ROWS_SMALL_THREADS / 32][1 + MAX_SP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x;
@@ -204,6 +205,7 @@ k_kernel_rows_small(const double* __restrict__ Xq, int n, const double* __restri
             }
         }
         U[int64_t(c) * Np + i] = kv;
+        if (U2) U2[int64_t(c) * Np + i] = kv;          // second copy for k_ut_small (pass 2 overwrites U while it runs)
     }
     acc_mu = warp_sum(acc_mu);
     if (lane == 0) s_red[warp][0] = acc_mu;
@@ -282,10 +284,10 @@ inline cudaError_t launch_kernel_rows_t(const double* Xq, int n, const double* X
 inline cudaError_t launch_kernel_rows(const double* Xq, int n, const double* XsT, int N, int Np, int d,
                                       const double* inv_ls, double outputscale, double mean, const double* alpha,
                                       const double* T, int Sp, double* U, double* mu, double* ut, int num_sms,
-                                      cudaStream_t st, bool small_call = false) {
+                                      cudaStream_t st, bool small_call = false, double* U2 = nullptr) {
     if (small_call) {   // decided per CALL by the API (<= 32 candidate points), never per chunk
         CBO_LAUNCHED(), k_kernel_rows_small<<<n, ROWS_SMALL_THREADS, 0, st>>>(Xq, n, XsT, N, Np, d, inv_ls, outputscale, mean, alpha, T, Sp, U,
-                                                              mu, ut);
+                                                              mu, ut, U2);
         return cudaGetLastError();
     }
     const bool stage = rows_smem_bytes(Np, d, (T && ut) ? Sp : 0, true) <= 220 * 1024;
