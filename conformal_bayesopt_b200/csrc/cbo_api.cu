@@ -862,7 +862,14 @@ static int conformal_acq_impl(const cbo_gp_f64* gp, const cbo_ratio_mlp_f64* rat
                                                   w.UW, w.adj, dX + c0 * q * d, num_sms(), s));
                 else {  // joint batches, and q = 1 calls with a handful of candidates (CTA per candidate point)
                     if (ratio_first) CBO_CUDA(cudaStreamWaitEvent(s, side->join, 0));
-                    CBO_LAUNCHED(), cbo::k_rows_bwd_q<<<n, cbo::RBQ_THREADS, 0, s>>>(Xc, n, q, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale,
+                    if (splitk != nullptr && N > 512)   // (per call: a handful of rows, enough train points for 32 warps)
+                        CBO_LAUNCHED(), cbo::k_rows_bwd_q<1024><<<n, 1024, 0, s>>>(Xc, n, q, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale,
+                                                                 gp->alpha, rhs, w.UW, w.adj,
+                                                                 !qpath ? cbo::ADJ_STRIDE : cbo::ADJQ_STRIDE, !qpath ? 1 : 0,
+                                                                 nei_rev ? p->nei->Xb : nullptr, nei_rev ? (int)p->nei->nb : 0,
+                                                                 nei_rev ? w.cv_bar : nullptr, dX + c0 * q * d, ratio_first ? 1 : 0);
+                    else
+                        CBO_LAUNCHED(), cbo::k_rows_bwd_q<256><<<n, 256, 0, s>>>(Xc, n, q, w.XsT, N, Np, d, gp->inv_lengthscale, gp->outputscale,
                                                                  gp->alpha, rhs, w.UW, w.adj,
                                                                  !qpath ? cbo::ADJ_STRIDE : cbo::ADJQ_STRIDE, !qpath ? 1 : 0,
                                                                  nei_rev ? p->nei->Xb : nullptr, nei_rev ? (int)p->nei->nb : 0,

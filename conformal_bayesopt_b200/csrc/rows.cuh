@@ -238,20 +238,33 @@ k_ut_small(const double* __restrict__ U, int N, int Np, const double* __restrict
     double acc_ut[MAX_SP];
 #pragma unroll
     for (int s = 0; s < MAX_SP; ++s) acc_ut[s] = 0.0;
-    for (int i = tid; i < Np; i += ROWS_SMALL_THREADS) {
-        if (i < N) {
-            const double kv = U[int64_t(c) * Np + i];
+    // four train points per thread with all their loads in flight at once, accumulated in the order of the plain loop
+    constexpr int UNR = 4;
+    for (int i0 = tid; i0 < Np; i0 += ROWS_SMALL_THREADS * UNR) {
+        double kv[UNR], tv[UNR][MAX_SP];
 #pragma unroll
-            for (int s = 0; s < MAX_SP; ++s)
-                if (s < Sp) acc_ut[s] = fma(kv, T[int64_t(s) * Np + i], acc_ut[s]);
+        for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * ROWS_SMALL_THREADS;
+            const bool ok = i < N;
+            kv[u] = ok ? U[int64_t(c) * Np + i] : 0.0;
+#pragma unroll
+            for (int s = 0; s < MAX_SP; ++s) tv[u][s] = (ok && s < Sp) ? T[int64_t(s) * Np + i] : 0.0;
         }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+            if (i0 + u * ROWS_SMALL_THREADS < N) {
+#pragma unroll
+                for (int s = 0; s < MAX_SP; ++s)
+                    if (s < Sp) acc_ut[s] = fma(kv[u], tv[u][s], acc_ut[s]);
+            }
     }
 #pragma unroll
-    for (int s = 0; s < MAX_SP; ++s)
-        if (s < Sp) {
-            double v = warp_sum(acc_ut[s]);
-            if (lane == 0) s_red[warp][s] = v;
-        }
+    for (int s = 0; s < MAX_SP; ++s) acc_ut[s] = warp_sum(acc_ut[s]);      // (independent chains; slots >= Sp are zeros)
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < MAX_SP; ++s)
+            if (s < Sp) s_red[warp][s] = acc_ut[s];
+    }
     __syncthreads();
     if (tid < Sp) {
         double v = 0.0;

@@ -1140,7 +1140,9 @@ k_score_q_bwd(const ScoreQBwdArgs qb) {
 // the train points of ONE row are spread over 8 warps (latency, not throughput).
 //   u_bar_i = (A^-1 w_bar')_i + mu_bar alpha_i - sum_k Ssym_jk w_ki
 //   x_bar   = sum_i u_bar_i k'(r_i)/r_i (x - X_i)/l^2 + sum_{k != j} Ssym_jk k'(r_jk)/r_jk (x_j - x_k)/l^2
-constexpr int RBQ_THREADS = 256;
+// RBQ_THREADS = 256 is the throughput shape; calls with a handful of rows (the SGLD step, decided per CALL like split-K) use
+// 1024 threads: one train point per thread at N = 1024, i.e. one round of loads instead of four in a row.
+template <int RBQ_THREADS>
 __global__ void __launch_bounds__(RBQ_THREADS)
 k_rows_bwd_q(const double* __restrict__ Xq, int rows, int q, const double* __restrict__ XsT, int N, int Np, int d,
              const double* __restrict__ inv_ls, double outputscale, const double* __restrict__ alpha,
