@@ -153,7 +153,13 @@ def optimize_acqf_sgld(
     lb, ub = bounds[0].contiguous(), bounds[1].contiguous()
     callback = options.get("callback")
     sgld_iterates = [[b.clone()] for b in batched_ics]
+    timing = options.get("timing")                          # dict or None: wall seconds of the stages (synchronises; diagnostics only)
+    if timing is not None:
+        import time as _t
+        torch.cuda.synchronize(); _t0 = _t.perf_counter()
     steppers = [_stepper(acq_function, b, options.get("cuda_graph", True)) for b in batched_ics]
+    if timing is not None:
+        torch.cuda.synchronize(); _t1 = _t.perf_counter(); timing["setup_s"] = _t1 - _t0
 
     for _s in range(sgld_steps):
         lr_s = cosine_lr(_s, lr, T_max, eta_min)
@@ -168,6 +174,8 @@ def optimize_acqf_sgld(
                 ops.sgld_update(ic_batch, bufs[batch_idx], dacq.to(torch.float64).contiguous(), noise, lb, ub, lr=lr_s,
                                 momentum=momentum, temperature=scaled_temp)
 
+    if timing is not None:
+        torch.cuda.synchronize(); _t2 = _t.perf_counter(); timing["steps_s"] = _t2 - _t1
     batch_candidates = torch.cat([torch.stack(it, dim=1) for it in sgld_iterates])      # (restarts, T, q, d)
     if return_full_traj:
         with torch.no_grad():
@@ -189,6 +197,8 @@ def optimize_acqf_sgld(
         if return_best_only:
             best = batch_acq_values.argmax(0)
             batch_candidates, batch_acq_values = batch_candidates[best], batch_acq_values[best]
+    if timing is not None:
+        torch.cuda.synchronize(); timing["scoring_s"] = _t.perf_counter() - _t2
     if post_processing_func is not None:
         batch_candidates = post_processing_func(batch_candidates)
     return batch_candidates, batch_acq_values
