@@ -24,6 +24,7 @@ ncu --set full --clock-control none --import-source on --profile-from-start off 
 python tools/sgld_step_time.py > $O/r02_sgld_step_time.log 2>&1
 python tools/sgld_loop_time.py > $O/r02_sgld_loop_time.log 2>&1
 python tools/sgld_graph_step.py > $O/r02_sgld_graph_step.log 2>&1
+python tools/sgld_loop_stages.py > $O/r02_sgld_loop_stages_after.log 2>&1
 # the .ncu-rep files (60-70 MB each) exceed what gpurun copies back: summarise them here and drop them
 { echo "==== forward call, 65536 candidates (tools/prof_run.py) ===="; python tools/ncu_summary.py $O/prof_r02_fwd.ncu-rep;
   echo; echo "==== value + gradient call, 65536 candidates (tools/prof_grad_run.py) ===="; python tools/ncu_summary.py $O/prof_r02_grad.ncu-rep; } > $O/r02_ncu_summary_final.txt 2>&1
