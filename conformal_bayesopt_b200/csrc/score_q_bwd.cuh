@@ -164,7 +164,7 @@ __device__ long long g_sqb_clk[32];
 #endif
 
 template <int Q, bool SOFT, bool CL>
-__global__ void __launch_bounds__(SQ_THREADS)
+__global__ void __launch_bounds__(SQ_THREADS, 1)
 k_score_q_bwd(const ScoreQBwdArgs qb) {
     namespace cg = cooperative_groups;
     const ScoreQArgs& pq = qb.f;
