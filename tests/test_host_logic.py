@@ -153,3 +153,13 @@ def test_initial_conditions_keep_the_best_raw_sample():
     assert any(torch.equal(ic, best) for ic in ics)
     with pytest.raises(RuntimeError):
         gen_batch_initial_conditions(acq, bounds, q=2, num_restarts=100, raw_samples=64)
+
+
+def test_sample_subset_has_no_cpu_path():
+    """cbo_sample_subset_i64 (the device-side minibatch draw of RatioEstimator.optimize_callback) draws on the device only."""
+    from conformal_bayesopt_b200 import _lib, ops
+    with pytest.raises(_lib.CboError):
+        ops.sample_subset(10, 3, 0, "cpu")
+    from conformal_bayesopt_b200.ratio_estimation import RatioEstimator
+    r = RatioEstimator(in_size=3, dtype=torch.float64)
+    assert r.device_permutation is True          # default; False = the reference's np.random.permutation draw (parity setting)
